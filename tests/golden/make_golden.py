@@ -1,0 +1,76 @@
+#!/usr/bin/env python3
+"""Regenerates the committed fixtures under tests/golden/.
+
+Run HERE (the build container), where /root/reference exists and
+`make -C oracle ref` has produced oracle/_ref/phnrec_ref (the reference's own
+sources compiled in place, canonicalised fexp.h — see oracle/Makefile).
+
+Outputs
+  ref_labels.json   the 7 golden label files the reference ships (parsed verbatim:
+                    start/end frame, phoneme, printed score) + which model/audio
+                    produced each.
+  ref_run_*.npz     outputs of oracle/_ref/phnrec_ref on the reference's own test
+                    audio: un-normalised log-mel (`-t par`), linear posteriors
+                    (`-t post`, float32, full matrix for CZ / EN, every 8th row for
+                    the others) and the `.rec` text incl. the %f scores.
+Nothing in tests/ reads /root/reference at run time; only these files.
+"""
+import json
+import subprocess
+import sys
+import tempfile
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parents[2]
+sys.path.insert(0, str(ROOT))
+from oracle import oracle as orc  # noqa: E402
+
+REF = Path("/root/reference")
+OUT = Path(__file__).resolve().parent
+
+GOLDENS = [  # (golden file, model dir under oracle/_ref/models, audio under oracle/_ref/audio, is_mlf)
+    ("test_en.rec", "PHN_EN_TIMIT_LCRC_N500", "test.raw", False),
+    ("test.rec.org", "PHN_CZ_SPDAT_LCRC_N1500", "test.raw", False),
+    ("test_hu.rec", "PHN_HU_SPDAT_LCRC_N1500", "test.raw", False),
+    ("test_ru.rec", "PHN_RU_SPDAT_LCRC_N1500", "test.raw", False),
+    ("test.rec", "PHN_CZ_SPDAT_LCRC_N1500", "8580.wav", False),
+    ("test/8580.rec", "PHN_ES", "8580.wav", False),
+    ("test/test", "PHN_ES", "8580.wav", True),
+    ("es.rec", "PHN_ES", "es.wav", False),
+]
+
+
+def main():
+    labels = {}
+    for g, model, audio, mlf in GOLDENS:
+        txt = (REF / g).read_text()
+        labels[g] = {"model": model, "audio": audio, "mlf": mlf, "text": txt,
+                     "labels": [list(x) for x in orc.parse_rec(txt)]}
+    (OUT / "ref_labels.json").write_text(json.dumps(labels, indent=1))
+
+    runs = sorted({(m, a) for _, m, a, _ in GOLDENS})
+    with tempfile.TemporaryDirectory() as td:
+        td = Path(td)
+        for model, audio in runs:
+            cfg = orc.REF_MODELS / model
+            wav = orc.REF_AUDIO / audio
+            orc.run_ref(["-c", cfg, "-i", wav, "-o", td / "o.rec"])
+            orc.run_ref(["-c", cfg, "-t", "par", "-i", wav, "-o", td / "o.par"])
+            orc.run_ref(["-c", cfg, "-t", "post", "-i", wav, "-o", td / "o.post"])
+            # decode from the saved posteriors with a non-default penalty (-s post -p)
+            orc.run_ref(["-c", cfg, "-s", "post", "-p", "-1.5", "-i", td / "o.post", "-o", td / "p.rec"])
+            mel = orc.read_htk(td / "o.par")
+            post = orc.read_htk(td / "o.post")
+            full = model in ("PHN_CZ_SPDAT_LCRC_N1500", "PHN_EN_TIMIT_LCRC_N500") and audio == "test.raw"
+            rows = np.arange(post.shape[0]) if full else np.arange(0, post.shape[0], 8)
+            name = f"ref_run_{model}_{audio.replace('.', '_')}.npz"
+            np.savez_compressed(OUT / name, mel=mel, post_rows=rows.astype(np.int32), post=post[rows],
+                                rec=np.array((td / "o.rec").read_text()),
+                                rec_p15=np.array((td / "p.rec").read_text()))
+            print(name, mel.shape, post.shape, "full" if full else "subsampled")
+
+
+if __name__ == "__main__":
+    main()
