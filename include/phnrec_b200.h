@@ -1,0 +1,166 @@
+/*
+ * phnrec_b200.h — C ABI of the B200-native PhnRec recognition hot path.
+ *
+ * The reference (rampa069/PhnRec) has no FFI layer: its hot path sits behind four C++
+ * class seams inside SpeechRec.  This header is the drop-in boundary
+ * that replaces those seams; each entry point names the reference interface it
+ * replaces (paths relative to the reference checkout).  Plain C types only: pointers,
+ * sizes, integer status codes; caller-allocated outputs; no exceptions cross it.
+ *
+ * Batch convention ("ragged batch"): n_utt utterances are concatenated in one buffer;
+ * off[u] .. off[u+1] delimits utterance u (off has n_utt+1 entries, off[0] = 0).
+ *   byte_off  : offsets into the audio buffer, in BYTES
+ *   frame_off : offsets into mel / posterior matrices, in FRAMES (rows)
+ *   label_off : offsets into the label array, in LABELS
+ *
+ * There is NO CPU fallback: every compute entry point runs hand-written sm_100a CUDA
+ * kernels and returns PHN_ERR_CUDA when no device / kernel image is available.
+ */
+#ifndef PHNREC_B200_H
+#define PHNREC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct phn_ctx phn_ctx;
+
+/* One recognised segment; times are frame indices (x 100000 = HTK 100 ns units when
+ * printed, phndec.cpp:230,292).  Replaces the DECODER_CALLBACK tuple
+ * (unsigned msg, char* word, long_long start, long_long stop, float score) of
+ * decoder.h:30 — `phn` indexes dicts/phonemes (phn_phoneme()). */
+typedef struct {
+    int32_t phn;
+    int32_t start;
+    int32_t end;
+    float like;
+} phn_label;
+
+/* Status codes.  1..5 mirror NN_* (nn.h:35-42), 10..13 mirror EN_* (configz.h:29-33),
+ * 20.. mirror DECERR_* (decoder.h:37-42); the rest are ours. */
+enum {
+    PHN_OK = 0,
+    PHN_ERR_NN_FILE = 1,      /* NN_FILEERR / NN_READERR: weights nbin file missing or truncated */
+    PHN_ERR_NN_FORMAT = 2,    /* NN_INVFORMAT: not a 3-layer .nbin */
+    PHN_ERR_CFG_FILE = 10,    /* EN_FILEERR  */
+    PHN_ERR_CFG_UNKVAR = 11,  /* EN_UNKVAR   */
+    PHN_ERR_CFG_BADVAL = 12,  /* EN_BADVAL   */
+    PHN_ERR_CFG_INVVAR = 13,  /* EN_INVVAR   */
+    PHN_ERR_DEC_INPUT = 20,   /* DECERR_INPUTFILE-class: phoneme list / window files */
+    PHN_ERR_UNSUPPORTED = 30, /* config selects something outside the hot path */
+    PHN_ERR_ARG = 31,
+    PHN_ERR_CAPACITY = 32,    /* caller buffer too small; required size is reported */
+    PHN_ERR_NOMEM = 33,
+    PHN_ERR_CUDA = 40         /* no device, no sm_100a image, or a CUDA runtime failure */
+};
+
+enum { PHN_WAVE_LIN16 = 0, PHN_WAVE_ALAW = 1 };        /* SpeechRec::wave_format, srec.h */
+enum {
+    PHN_MLP_EXACT_FP32 = 0, /* CUDA-core fp32, reference summation order: bit-identical posteriors */
+    PHN_MLP_TC_F16 = 1      /* tcgen05/TMEM GEMMs, fp16 operands, fp32 accumulate */
+};
+
+typedef struct {
+    int32_t sample_freq, wave_format, nbanks, vector_size, vector_step, fft_size;
+    int32_t n_phonemes, n_states, n_outputs;     /* decoder uses the first n_phonemes*n_states outputs */
+    int32_t band_inputs, merger_inputs, hidden;  /* .nbin header sizes (nn.cpp:464-531) */
+    int32_t sent_mean_norm, time_pruning, mlp_mode, device;
+    float wpenalty;
+} phn_info;
+
+/* -- lifetime ---------------------------------------------------------------------- */
+/* Replaces SpeechRec::Init (srec.cpp:235-707) for the offline phndec/LCRC path:
+ * parses <cfg_dir>/config (configz.cpp:102-165 dialect, variable table srec.cpp:34-110),
+ * loads weights/{band0,band1,merger}.nbin (nn.cpp:464-531), windows/band{0,1}.window
+ * (traps.cpp:549-570), dicts/phonemes (phndec.cpp:305-350); builds the Hamming / mel
+ * filterbank / FFT twiddle / DCT tables on the host with the reference's float
+ * expressions (dspc.cpp:80-225, dspc.h:162-221) and uploads everything to `device`. */
+int phn_create(const char *cfg_dir, int device, phn_ctx **out);
+void phn_destroy(phn_ctx *ctx);
+/* Message of the last failure on this context (or of the last failed phn_create when
+ * ctx == NULL).  Text follows the reference's MERROR strings where one exists. */
+const char *phn_last_error(const phn_ctx *ctx);
+int phn_get_info(const phn_ctx *ctx, phn_info *info);
+const char *phn_phoneme(const phn_ctx *ctx, int index); /* PhnDec::LoadPhnList, phndec.cpp:305 */
+
+/* -- knobs ------------------------------------------------------------------------- */
+int phn_set_penalty(phn_ctx *ctx, float wpenalty);   /* Decoder::SetWPenalty, decoder.h:70 / phnrec.cpp:212-221 */
+int phn_set_wave_format(phn_ctx *ctx, int fmt);      /* SpeechRec::SetWaveFormat, phnrec.cpp:224-225 */
+int phn_set_mlp_mode(phn_ctx *ctx, int mode);        /* ours: PHN_MLP_* */
+
+/* srec.cpp:945 — frames of one utterance of `nbytes` bytes in the current wave format. */
+int64_t phn_num_frames(const phn_ctx *ctx, int64_t nbytes);
+/* Upper bound on labels for a batch with these frame offsets (sizes label arrays). */
+int64_t phn_label_capacity(const phn_ctx *ctx, const int64_t *frame_off, int n_utt);
+
+/* -- the three stages, HOST buffers (copies inside) --------------------------------- */
+/* audio -> un-normalised log mel-bank energies, what `-t par` saves.
+ * Replaces ConvertWaveformFormat + MelBanks::{AddWaveform,GetFeatures} (srec.cpp:709-791,
+ * 942-971; melbanks.h:70-92).  frame_off [n_utt+1] is written; mel_out is
+ * [frame_off[n_utt]][nbanks] (pass NULL to only get frame_off). */
+int phn_mel(phn_ctx *ctx, const void *audio, const int64_t *byte_off, int n_utt, float *mel_out, int64_t *frame_off);
+
+/* mel -> linear posteriors, what `-t post` saves.  Replaces SentenceBasedNormalization
+ * + Traps::CalcFeaturesBunched (+ the 15-frame warm-up / tail driver) + NeuralNet::Forward x3
+ * (srec.cpp:999-1070, traps.h:58-75, nn.h:50-59).  post_out is [frames][n_outputs]. */
+int phn_posteriors(phn_ctx *ctx, const float *mel, const int64_t *frame_off, int n_utt, float *post_out);
+
+/* linear posteriors -> labels: decSoftFunc=log (srec.cpp:1088-1097) then
+ * Decoder::{Init,ProcessFrame,Done} (decoder.h:58-74, phndec.cpp:44-302), once per
+ * penalty (the `-s post -p P` sweep).  penalties == NULL -> the context's penalty, n_pen = 1.
+ * Output order: penalty-major, i.e. label_off has n_pen*n_utt+1 entries and utterance u
+ * under penalty k is segment k*n_utt+u.  Returns PHN_ERR_CAPACITY (and label_off filled
+ * with the needed counts) when label_cap is too small. */
+int phn_decode(phn_ctx *ctx, const float *post, const int64_t *frame_off, int n_utt, const float *penalties, int n_pen,
+               phn_label *labels, int64_t label_cap, int64_t *label_off);
+
+/* audio -> labels with no host round trip in between; replaces SpeechRec::ProcessOffline
+ * (srec.cpp:929-1111) for dfWaveform -> dfStrings.  frame_off_out may be NULL. */
+int phn_recognize(phn_ctx *ctx, const void *audio, const int64_t *byte_off, int n_utt, phn_label *labels,
+                  int64_t label_cap, int64_t *label_off, int64_t *frame_off_out);
+
+/* -- device-resident variants (inputs already in HBM; used by bench.py and servers) -- */
+/* d_audio is a DEVICE pointer on the context's device; byte_off stays a host array.
+ * Runs wave -> mean -> STC -> MLPs -> Viterbi -> traceback on the context's stream and
+ * leaves mel / posteriors / labels in the context's device buffers.  Asynchronous:
+ * call phn_sync() or a phn_fetch_* before reading results. */
+int phn_recognize_device(phn_ctx *ctx, const void *d_audio, const int64_t *byte_off, int n_utt);
+int phn_sync(phn_ctx *ctx);
+/* Copy results of the last *_device / host call back. Any output may be NULL. */
+int phn_fetch_labels(phn_ctx *ctx, phn_label *labels, int64_t label_cap, int64_t *label_off);
+int phn_fetch_mel(phn_ctx *ctx, float *mel_out);
+int phn_fetch_posteriors(phn_ctx *ctx, float *post_out);
+/* Raw CUDA handles for callers that share the device (opaque integers/pointers). */
+void *phn_stream(phn_ctx *ctx);          /* cudaStream_t */
+void *phn_device_alloc(phn_ctx *ctx, int64_t nbytes);
+void phn_device_free(phn_ctx *ctx, void *p);
+void *phn_host_alloc_pinned(int64_t nbytes);
+void phn_host_free_pinned(void *p);
+int phn_memcpy_h2d(phn_ctx *ctx, void *dst, const void *src, int64_t nbytes); /* async on the context's stream */
+int phn_memcpy_d2h(phn_ctx *ctx, void *dst, const void *src, int64_t nbytes); /* synchronous */
+/* Deterministic synthetic audio generated ON the device (bench): utterance u
+ * of `bytes_per_utt` bytes in the current wave format, seeded by seed and u. */
+int phn_synth_audio_device(phn_ctx *ctx, void *d_audio, int64_t bytes_per_utt, int n_utt, uint64_t seed);
+
+/* -- instrumentation ---------------------------------------------------------------- */
+/* Per-kernel-family device time of the last call, measured with CUDA events on the
+ * context's stream when profiling is enabled.  families: see PHN_K_*. */
+enum { PHN_K_WAVE = 0, PHN_K_MEAN, PHN_K_STC, PHN_K_MLP, PHN_K_VIT, PHN_K_COUNT };
+int phn_set_profiling(phn_ctx *ctx, int on);
+int phn_last_timing(phn_ctx *ctx, float ms[PHN_K_COUNT], int64_t launches[PHN_K_COUNT]);
+
+/* N2: online normaliser arithmetic (Normalization::ProcessFrame, norm.cpp:216-234;
+ * ChannelNormParams::{Accum,Update,Norm}, norm.cpp:92-148) on a [frames][nbanks] host
+ * matrix, in place on the device: estimate over the first `interval` frames, apply after. */
+int phn_online_norm(phn_ctx *ctx, float *x, int64_t frames, int nbanks, int interval, int mean_norm, int var_norm);
+
+/* Library / build identification. */
+const char *phn_version(void);
+int phn_device_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PHNREC_B200_H */

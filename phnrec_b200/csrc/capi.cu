@@ -1,0 +1,628 @@
+// capi.cu — the C ABI (include/phnrec_b200.h): context lifetime, batch planning, stage sequencing
+// on one CUDA stream, host<->device copies.  No computation happens on the host.
+#include "internal.h"
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <sys/stat.h>
+
+static std::string g_create_err;
+
+namespace phn {
+
+int fail(phn_ctx *c, int code, const char *fmt, ...)
+{
+    char buf[2048];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (c) c->err = buf; else g_create_err = buf;
+    return code;
+}
+
+int ensure(phn_ctx *c, phn_ctx::Buf &b, size_t bytes)
+{
+    if (bytes <= b.cap) return PHN_OK;
+    if (b.p) {
+        PHN_CUDA(c, cudaStreamSynchronize(c->stream));
+        PHN_CUDA(c, cudaFree(b.p));
+        b.p = nullptr; b.cap = 0;
+    }
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&b.p, want);
+    if (e != cudaSuccess) {
+        b.p = nullptr;
+        return fail(c, PHN_ERR_NOMEM, "cudaMalloc of %zu bytes failed: %s\n", want, cudaGetErrorString(e));
+    }
+    b.cap = want;
+    PHN_CUDA(c, cudaMemsetAsync(b.p, 0, want, c->stream));  // padding columns rely on zero fill
+    return PHN_OK;
+}
+
+template <typename T>
+static int upload(phn_ctx *c, T **dst, const T *src, size_t n)
+{
+    PHN_CUDA(c, cudaMalloc((void **)dst, sizeof(T) * (n ? n : 1)));
+    if (n) PHN_CUDA(c, cudaMemcpy(*dst, src, sizeof(T) * n, cudaMemcpyHostToDevice));
+    return PHN_OK;
+}
+
+static int up16(int n) { return (n + 15) / 16 * 16; }
+
+static int upload_net(phn_ctx *c, int which)
+{
+    const HostNet &h = c->hnet[which];
+    DevNet &d = c->net[which];
+    d.nin = h.nin; d.nhid = h.nhid; d.nout = h.nout; d.nin4 = h.nin4; d.nhid4 = h.nhid4; d.nout4 = h.nout4;
+    d.kp = up16(h.nin4);
+    d.ldh = up16(h.nhid4);
+    d.w1h = nullptr; d.w2h = nullptr; d.k1P = (h.nin + 63) / 64 * 64; d.nhidP = 0; d.noutP = 0;
+    int rc;
+    if ((rc = upload(c, &d.w1, h.w1.data(), h.w1.size()))) return rc;
+    if ((rc = upload(c, &d.w2, h.w2.data(), h.w2.size()))) return rc;
+    if ((rc = upload(c, &d.b1, h.b1.data(), h.b1.size()))) return rc;
+    if ((rc = upload(c, &d.b2, h.b2.data(), h.b2.size()))) return rc;
+    if ((rc = upload(c, &d.mean, h.mean.data(), h.mean.size()))) return rc;
+    if ((rc = upload(c, &d.dev, h.dev.data(), h.dev.size()))) return rc;
+    return PHN_OK;
+}
+
+// frames of one utterance (srec.cpp:945)
+static int64_t frames_of(const phn_ctx *c, int64_t nbytes)
+{
+    const int64_t n = c->fmt == PHN_WAVE_LIN16 ? nbytes / 2 : nbytes;
+    return n > c->vs ? (n - c->vs) / c->step + 1 : 1;
+}
+
+// ---- batch planning: offsets + device buffers for `n_pen` decoder passes
+static int plan_frames(phn_ctx *c, const int64_t *frame_off, int n_utt, int n_pen)
+{
+    if (n_utt < 0 || n_pen < 1) return fail(c, PHN_ERR_ARG, "invalid batch\n");
+    c->n_utt = n_utt; c->n_pen = n_pen;
+    c->h_frame_off.assign(frame_off, frame_off + n_utt + 1);
+    if (c->h_frame_off[0] != 0) return fail(c, PHN_ERR_ARG, "offsets must start at 0\n");
+    for (int u = 0; u < n_utt; ++u)
+        if (c->h_frame_off[u + 1] < c->h_frame_off[u]) return fail(c, PHN_ERR_ARG, "offsets must be non-decreasing\n");
+    c->total_frames = c->h_frame_off[n_utt];
+    const int nseg = n_utt * n_pen;
+    c->h_lab_off.resize((size_t)nseg + 1);
+    c->h_lab_off[0] = 0;
+    for (int k = 0; k < n_pen; ++k)
+        for (int u = 0; u < n_utt; ++u) {
+            const int64_t T = c->h_frame_off[u + 1] - c->h_frame_off[u];
+            c->h_lab_off[(size_t)k * n_utt + u + 1] = c->h_lab_off[(size_t)k * n_utt + u] + T + 48;
+        }
+    c->label_cap = c->h_lab_off[nseg];
+    const int64_t F = c->total_frames;
+    const int nout = c->net[2].nout;
+    int rc;
+    if ((rc = ensure(c, c->d_frame_off, sizeof(int64_t) * (n_utt + 1)))) return rc;
+    if ((rc = ensure(c, c->d_lab_off, sizeof(int64_t) * (nseg + 1)))) return rc;
+    if ((rc = ensure(c, c->d_mel, sizeof(float) * F * c->nbanks))) return rc;
+    if ((rc = ensure(c, c->d_mean, sizeof(float) * (size_t)n_utt * c->nbanks))) return rc;
+    if ((rc = ensure(c, c->d_post, sizeof(float) * F * nout))) return rc;
+    if ((rc = ensure(c, c->d_rec, (size_t)20 * F * n_pen))) return rc;
+    if ((rc = ensure(c, c->d_labels, sizeof(phn_label) * (size_t)c->label_cap))) return rc;
+    if ((rc = ensure(c, c->d_nlab, sizeof(int) * (size_t)nseg))) return rc;
+    if ((rc = ensure(c, c->d_pen, sizeof(float) * n_pen))) return rc;
+    PHN_CUDA(c, cudaMemcpyAsync(c->d_frame_off.p, c->h_frame_off.data(), sizeof(int64_t) * (n_utt + 1),
+                                cudaMemcpyHostToDevice, c->stream));
+    PHN_CUDA(c, cudaMemcpyAsync(c->d_lab_off.p, c->h_lab_off.data(), sizeof(int64_t) * (nseg + 1), cudaMemcpyHostToDevice,
+                                c->stream));
+    return PHN_OK;
+}
+
+static int plan_audio(phn_ctx *c, const int64_t *byte_off, int n_utt)
+{
+    if (n_utt < 0 || !byte_off) return fail(c, PHN_ERR_ARG, "invalid batch\n");
+    c->h_byte_off.assign(byte_off, byte_off + n_utt + 1);
+    if (c->h_byte_off[0] != 0) return fail(c, PHN_ERR_ARG, "offsets must start at 0\n");
+    std::vector<int64_t> fo((size_t)n_utt + 1, 0);
+    for (int u = 0; u < n_utt; ++u) {
+        const int64_t nb = byte_off[u + 1] - byte_off[u];
+        if (nb < 0) return fail(c, PHN_ERR_ARG, "offsets must be non-decreasing\n");
+        fo[u + 1] = fo[u] + frames_of(c, nb);
+    }
+    c->total_bytes = byte_off[n_utt];
+    int rc;
+    if ((rc = plan_frames(c, fo.data(), n_utt, 1))) return rc;
+    if ((rc = ensure(c, c->d_byte_off, sizeof(int64_t) * (n_utt + 1)))) return rc;
+    PHN_CUDA(c, cudaMemcpyAsync(c->d_byte_off.p, c->h_byte_off.data(), sizeof(int64_t) * (n_utt + 1), cudaMemcpyHostToDevice,
+                                c->stream));
+    return PHN_OK;
+}
+
+struct StageTimer {  // CUDA-event timing of one kernel family on the context's stream (profiling only)
+    phn_ctx *c; int fam;
+    StageTimer(phn_ctx *c_, int fam_) : c(c_), fam(fam_) { if (c->profiling) cudaEventRecord(c->ev[2 * fam], c->stream); }
+    ~StageTimer()
+    {
+        if (!c->profiling) return;
+        cudaEventRecord(c->ev[2 * fam + 1], c->stream);
+        cudaEventSynchronize(c->ev[2 * fam + 1]);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, c->ev[2 * fam], c->ev[2 * fam + 1]);
+        c->k_ms[fam] += ms;
+    }
+};
+
+static void reset_timing(phn_ctx *c)
+{
+    for (int i = 0; i < PHN_K_COUNT; ++i) { c->k_ms[i] = 0.f; c->k_launches[i] = 0; }
+}
+
+// mel (device, un-normalised) -> posteriors (device)
+static int run_posteriors(phn_ctx *c)
+{
+    int rc;
+    { StageTimer t(c, PHN_K_MEAN); if ((rc = launch_sentence_mean(c))) return rc; }
+    const bool tc = c->mlp_mode == PHN_MLP_TC_F16;
+    const int64_t F = c->total_frames;
+    int64_t ch = tc ? (int64_t)1 << 18 : (int64_t)1 << 15;
+    if (ch > F) ch = (F + 127) / 128 * 128;
+    if (ch == 0) return PHN_OK;
+    if (tc) {
+        if ((rc = mlp_tc_prepare(c))) return rc;
+        if ((rc = ensure(c, c->d_x0h, sizeof(__half) * ch * c->net[0].k1P))) return rc;
+        if ((rc = ensure(c, c->d_x1h, sizeof(__half) * ch * c->net[1].k1P))) return rc;
+        if ((rc = ensure(c, c->d_xmh, sizeof(__half) * ch * c->net[2].k1P))) return rc;
+    } else {
+        if ((rc = ensure(c, c->d_x0, sizeof(float) * ch * c->net[0].kp))) return rc;
+        if ((rc = ensure(c, c->d_x1, sizeof(float) * ch * c->net[1].kp))) return rc;
+        if ((rc = ensure(c, c->d_xm, sizeof(float) * ch * c->net[2].kp))) return rc;
+        if ((rc = ensure(c, c->d_h, sizeof(float) * ch * c->net[0].ldh))) return rc;
+    }
+    c->chunk_frames = ch;
+    for (int64_t f0 = 0; f0 < F; f0 += ch) {
+        const int64_t nf = F - f0 < ch ? F - f0 : ch;
+        { StageTimer t(c, PHN_K_STC); if ((rc = launch_stc(c, f0, nf))) return rc; }
+        { StageTimer t(c, PHN_K_MLP); if ((rc = tc ? launch_mlp_tc(c, f0, nf) : launch_mlp_exact(c, f0, nf))) return rc; }
+    }
+    return PHN_OK;
+}
+
+static int run_decode(phn_ctx *c, const float *penalties, int n_pen)
+{
+    std::vector<float> pen(n_pen);
+    for (int k = 0; k < n_pen; ++k) pen[k] = penalties ? penalties[k] : c->wpenalty;
+    PHN_CUDA(c, cudaMemcpyAsync(c->d_pen.p, pen.data(), sizeof(float) * n_pen, cudaMemcpyHostToDevice, c->stream));
+    PHN_CUDA(c, cudaStreamSynchronize(c->stream));  // `pen` is a pageable temporary
+    StageTimer t(c, PHN_K_VIT);
+    return launch_viterbi(c, (const float *)c->d_pen.p, n_pen);
+}
+
+}  // namespace phn
+
+using namespace phn;
+
+// ===================================================================== C ABI
+extern "C" {
+
+const char *phn_version(void) { return "phnrec_b200 0.1 (sm_100a)"; }
+
+int phn_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+const char *phn_last_error(const phn_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+
+int phn_create(const char *cfg_dir, int device, phn_ctx **out)
+{
+    if (!cfg_dir || !out) return fail(nullptr, PHN_ERR_ARG, "phn_create: null argument\n");
+    *out = nullptr;
+    phn_ctx *c = new phn_ctx();
+    auto bail = [&](int rc) {
+        g_create_err = c->err;
+        phn_destroy(c);
+        return rc;
+    };
+    c->cfg_dir = cfg_dir;
+    c->device = device;
+    const std::string cfg_file = c->cfg_dir + "/config";
+    int line = 0;
+    int rc = c->cfg.load(cfg_file, &line);
+    if (rc != PHN_OK) {  // messages of SpeechRec::Init, srec.cpp:248-262
+        switch (rc) {
+            case PHN_ERR_CFG_UNKVAR: fail(c, rc, "Unknown variable in configuration file '%s', line %d\n", cfg_file.c_str(), line); break;
+            case PHN_ERR_CFG_BADVAL: fail(c, rc, "Invalid argument for a vatiable in configuration file '%s', line %d\n", cfg_file.c_str(), line); break;
+            case PHN_ERR_CFG_FILE: fail(c, rc, "Can not open configuration file '%s'\n", cfg_file.c_str()); break;
+            default: fail(c, rc, "Invalid notation of variable in configuration file '%s', line %d\n", cfg_file.c_str(), line); break;
+        }
+        return bail(rc);
+    }
+    const Config &C = c->cfg;
+    // ---- what this hot path implements: fbanks -> LCRC -> phndec, offline
+    if (C.str("params", "kind") != "fbanks") return bail(fail(c, PHN_ERR_UNSUPPORTED, "Unsupported parameter kind: %s\n", C.str("params", "kind").c_str()));
+    if (C.str("posteriors", "system") != "LCRC") return bail(fail(c, PHN_ERR_UNSUPPORTED, "Unsupported posterior estimator: %s (only LCRC)\n", C.str("posteriors", "system").c_str()));
+    if (C.str("decoder", "type") != "phndec") return bail(fail(c, PHN_ERR_UNSUPPORTED, "Unsupported decoder type: %s (only phndec)\n", C.str("decoder", "type").c_str()));
+    if (C.i("posteriors", "length") != 31 || !C.b("posteriors", "add_c0") || C.b("posteriors", "hamming"))
+        return bail(fail(c, PHN_ERR_UNSUPPORTED, "Unsupported LCRC set-up (needs length=31, add_c0=true, hamming=false)\n"));
+    if (C.str("posteriors", "softening_func").rfind("none", 0) != 0 || C.str("decoder", "softening_func").rfind("log", 0) != 0)
+        return bail(fail(c, PHN_ERR_UNSUPPORTED, "Unsupported softening functions (needs posteriors none, decoder log)\n"));
+    if (C.b("offlinenorm", "sent_var_norm") || C.b("offlinenorm", "sent_max_norm") || C.b("offlinenorm", "sent_chmax_norm"))
+        return bail(fail(c, PHN_ERR_UNSUPPORTED, "Unsupported offline normalisation (only sent_mean_norm)\n"));
+    if (C.f("source", "noise_level") != 0.0f) return bail(fail(c, PHN_ERR_UNSUPPORTED, "source/noise_level is not supported\n"));
+    if (C.i("decoder", "num_states_per_phn") != 3) return bail(fail(c, PHN_ERR_UNSUPPORTED, "decoder/num_states_per_phn must be 3\n"));
+    const std::string &fmt = C.str("source", "format");
+    if (fmt == "lin16") c->fmt = PHN_WAVE_LIN16;
+    else if (fmt == "alaw") c->fmt = PHN_WAVE_ALAW;
+    else return bail(fail(c, PHN_ERR_UNSUPPORTED, "Unknown waveform format: %s\n", fmt.c_str()));
+    c->fs = C.i("source", "sample_freq");
+    c->scale = C.f("source", "scale");
+    c->dc_shift = C.f("source", "dc_shift");
+    c->nbanks = C.i("melbanks", "nbanks");
+    c->vs = C.i("melbanks", "vector_size");
+    c->step = C.i("melbanks", "vector_step");
+    c->lo = C.f("melbanks", "lower_freq");
+    c->hi = C.f("melbanks", "higher_freq");
+    c->preem = C.f("melbanks", "preem_coef");
+    c->z_mean = C.b("melbanks", "z_mean_source");
+    c->sent_mean_norm = C.b("offlinenorm", "sent_mean_norm");
+    c->frame_shift = C.f("framenorm", "shift");
+    c->frame_floor = C.f("framenorm", "min_floor");
+    c->wpenalty = C.f("decoder", "wpenalty");
+    c->hist = C.i("decoder", "time_pruning");
+    c->S = 3;
+    if (c->nbanks < 1 || c->nbanks > 32 || c->vs < 2 || c->vs > 4096 || c->step < 1 || c->hist < 1)
+        return bail(fail(c, PHN_ERR_CFG_BADVAL, "Front-end sizes out of range in '%s'\n", cfg_file.c_str()));
+    {   // mkdir <tmp> is attempted and its failure ignored, as in srec.cpp:270-279
+        std::string tmp = C.str("dirs", "tmp");
+        size_t p = tmp.find("$C");
+        if (p != std::string::npos) tmp.replace(p, 2, c->cfg_dir);
+        mkdir(tmp.c_str(), 0777);
+    }
+    // ---- nets (traps.cpp:139-166: .nbin tried first; it is the only weight source we read)
+    const char *names[3] = {"band0", "band1", "merger"};
+    for (int i = 0; i < 3; ++i) {
+        const std::string p = c->cfg_dir + "/weights/" + names[i] + ".nbin";
+        rc = c->hnet[i].load(p);
+        if (rc != PHN_OK) return bail(fail(c, rc, "Can not load neural network: %s\n", p.c_str()));
+    }
+    if (c->hnet[0].nin % c->nbanks || c->hnet[0].nin != c->hnet[1].nin || c->hnet[0].nout != c->hnet[1].nout ||
+        c->hnet[2].nin != 2 * c->hnet[0].nout)
+        return bail(fail(c, PHN_ERR_NN_FORMAT, "Inconsistent network sizes in %s/weights\n", cfg_dir));
+    c->ncoef = c->hnet[0].nin / c->nbanks;
+    if (c->ncoef != 11) return bail(fail(c, PHN_ERR_UNSUPPORTED, "band nets must take 11 coefficients per band\n"));
+    for (int w = 0; w < 2; ++w) {  // traps.cpp:549-570
+        const std::string p = c->cfg_dir + "/windows/band" + std::to_string(w) + ".window";
+        FILE *f = fopen(p.c_str(), "r");
+        if (!f) return bail(fail(c, PHN_ERR_DEC_INPUT, "Can not open window file: %s\n", p.c_str()));
+        for (int i = 0; i < 16; ++i)
+            if (fscanf(f, "%f", &c->win[w * 16 + i]) != 1) { fclose(f); return bail(fail(c, PHN_ERR_DEC_INPUT, "Invalid window file: %s\n", p.c_str())); }
+        fclose(f);
+    }
+    {   // phoneme list (phndec.cpp:305-350); $C substitution as srec.cpp:219-233
+        std::string p = C.str("dicts", "phoneme_list");
+        if (p.empty()) p = "$C/dicts/phonemes";
+        size_t q = p.find("$C");
+        if (q != std::string::npos) p.replace(q, 2, c->cfg_dir);
+        FILE *f = fopen(p.c_str(), "r");
+        if (!f) return bail(fail(c, PHN_ERR_DEC_INPUT, "Can not open the phoneme list: %s\n", p.c_str()));
+        char buf[256];
+        while (fgets(buf, 255, f)) {
+            buf[strcspn(buf, "\r\n")] = 0;
+            c->phonemes.push_back(buf);
+        }
+        fclose(f);
+        c->P = (int)c->phonemes.size();
+        if (c->P < 1 || c->P * 3 > c->hnet[2].nout)
+            return bail(fail(c, PHN_ERR_DEC_INPUT, "Phoneme list %s does not fit the %d network outputs\n", p.c_str(), c->hnet[2].nout));
+    }
+    c->mt.build(c->nbanks, c->vs, c->step, c->fs, c->lo, c->hi);
+
+    // ---- device
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return bail(fail(c, PHN_ERR_CUDA, "no CUDA device available (this library has no CPU path)\n"));
+    if (device < 0 || device >= ndev) return bail(fail(c, PHN_ERR_ARG, "device %d out of range (0..%d)\n", device, ndev - 1));
+    auto cu = [&](cudaError_t e, const char *what) -> int {
+        if (e == cudaSuccess) return PHN_OK;
+        return fail(c, PHN_ERR_CUDA, "CUDA failure in %s: %s\n", what, cudaGetErrorString(e));
+    };
+    if ((rc = cu(cudaSetDevice(device), "cudaSetDevice"))) return bail(rc);
+    cudaDeviceProp prop;
+    if ((rc = cu(cudaGetDeviceProperties(&prop, device), "cudaGetDeviceProperties"))) return bail(rc);
+    if (prop.major != 10)
+        return bail(fail(c, PHN_ERR_CUDA, "device %d is sm_%d%d; this library carries sm_100a code only\n", device, prop.major, prop.minor));
+    c->num_sms = prop.multiProcessorCount;
+    if ((rc = cu(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking), "cudaStreamCreate"))) return bail(rc);
+    for (int i = 0; i < 2 * PHN_K_COUNT; ++i)
+        if ((rc = cu(cudaEventCreate(&c->ev[i]), "cudaEventCreate"))) return bail(rc);
+    for (int i = 0; i < 3; ++i)
+        if ((rc = upload_net(c, i))) return bail(rc);
+    const MelTables &mt = c->mt;
+    std::vector<double2> tw((size_t)mt.N);
+    for (int i = 0; i < mt.N - 1; ++i) tw[i] = make_double2(mt.tw[2 * i], mt.tw[2 * i + 1]);
+    std::vector<float> dct(160);
+    {   // sDCT's cosine arguments (dspc.h:206-221), evaluated with the host libm like the reference
+        const float PiByN = (float)M_PI / 16.0f;
+        for (int k = 0; k < 10; ++k) {
+            const float v = PiByN * (float)(k + 1);
+            for (int j = 0; j < 16; ++j) dct[k * 16 + j] = cosf(v * ((float)j + 0.5f));
+        }
+    }
+    if ((rc = upload(c, &c->tab.hamming, mt.hamming.data(), mt.hamming.size()))) return bail(rc);
+    if ((rc = upload(c, &c->tab.coeffs, mt.coeffs.data(), mt.coeffs.size()))) return bail(rc);
+    if ((rc = upload(c, &c->tab.banks, mt.banks.data(), mt.banks.size()))) return bail(rc);
+    if ((rc = upload(c, &c->tab.bank_klo, mt.bank_klo.data(), mt.bank_klo.size()))) return bail(rc);
+    if ((rc = upload(c, &c->tab.bank_khi, mt.bank_khi.data(), mt.bank_khi.size()))) return bail(rc);
+    if ((rc = upload(c, &c->tab.tw, tw.data(), tw.size()))) return bail(rc);
+    if ((rc = upload(c, &c->tab.win, c->win, 32))) return bail(rc);
+    if ((rc = upload(c, &c->tab.dct, dct.data(), dct.size()))) return bail(rc);
+    *out = c;
+    return PHN_OK;
+}
+
+void phn_destroy(phn_ctx *c)
+{
+    if (!c) return;
+    if (c->stream) {
+        cudaSetDevice(c->device);
+        cudaStreamSynchronize(c->stream);
+    }
+    phn_ctx::Buf *bufs[] = {&c->d_audio, &c->d_byte_off, &c->d_frame_off, &c->d_lab_off, &c->d_mel, &c->d_mean, &c->d_post,
+                            &c->d_rec, &c->d_labels, &c->d_nlab, &c->d_pen, &c->d_x0, &c->d_x1, &c->d_h, &c->d_xm,
+                            &c->d_x0h, &c->d_x1h, &c->d_xmh, &c->d_tile_ctr, &c->d_coff, &c->d_labels_c};
+    for (auto *b : bufs)
+        if (b->p) cudaFree(b->p);
+    for (int i = 0; i < 3; ++i) {
+        DevNet &d = c->net[i];
+        void *ps[] = {d.w1, d.w2, d.b1, d.b2, d.mean, d.dev, d.w1h, d.w2h};
+        for (void *p : ps)
+            if (p) cudaFree(p);
+    }
+    void *ts[] = {c->tab.hamming, c->tab.coeffs, c->tab.banks, c->tab.bank_klo, c->tab.bank_khi, c->tab.tw, c->tab.win, c->tab.dct};
+    for (void *p : ts)
+        if (p) cudaFree(p);
+    for (auto &e : c->ev)
+        if (e) cudaEventDestroy(e);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int phn_get_info(const phn_ctx *c, phn_info *o)
+{
+    if (!c || !o) return PHN_ERR_ARG;
+    o->sample_freq = c->fs; o->wave_format = c->fmt; o->nbanks = c->nbanks; o->vector_size = c->vs;
+    o->vector_step = c->step; o->fft_size = c->mt.N; o->n_phonemes = c->P; o->n_states = c->S;
+    o->n_outputs = c->hnet[2].nout; o->band_inputs = c->hnet[0].nin; o->merger_inputs = c->hnet[2].nin;
+    o->hidden = c->hnet[0].nhid; o->sent_mean_norm = c->sent_mean_norm; o->time_pruning = c->hist;
+    o->mlp_mode = c->mlp_mode; o->device = c->device; o->wpenalty = c->wpenalty;
+    return PHN_OK;
+}
+
+const char *phn_phoneme(const phn_ctx *c, int i) { return (c && i >= 0 && i < c->P) ? c->phonemes[i].c_str() : nullptr; }
+
+int phn_set_penalty(phn_ctx *c, float wp)
+{
+    if (!c) return PHN_ERR_ARG;
+    c->wpenalty = wp;
+    return PHN_OK;
+}
+int phn_set_wave_format(phn_ctx *c, int fmt)
+{
+    if (!c) return PHN_ERR_ARG;
+    if (fmt != PHN_WAVE_LIN16 && fmt != PHN_WAVE_ALAW) return fail(c, PHN_ERR_ARG, "Unknown waveform format\n");
+    c->fmt = fmt;
+    return PHN_OK;
+}
+int phn_set_mlp_mode(phn_ctx *c, int mode)
+{
+    if (!c) return PHN_ERR_ARG;
+    if (mode != PHN_MLP_EXACT_FP32 && mode != PHN_MLP_TC_F16) return fail(c, PHN_ERR_ARG, "Unknown MLP mode\n");
+    c->mlp_mode = mode;
+    return PHN_OK;
+}
+int phn_set_profiling(phn_ctx *c, int on)
+{
+    if (!c) return PHN_ERR_ARG;
+    c->profiling = on;
+    return PHN_OK;
+}
+int phn_last_timing(phn_ctx *c, float ms[PHN_K_COUNT], int64_t launches[PHN_K_COUNT])
+{
+    if (!c) return PHN_ERR_ARG;
+    for (int i = 0; i < PHN_K_COUNT; ++i) {
+        if (ms) ms[i] = c->k_ms[i];
+        if (launches) launches[i] = c->k_launches[i];
+    }
+    return PHN_OK;
+}
+
+int64_t phn_num_frames(const phn_ctx *c, int64_t nbytes) { return c ? frames_of(c, nbytes) : -1; }
+
+int64_t phn_label_capacity(const phn_ctx *c, const int64_t *frame_off, int n_utt)
+{
+    if (!c || !frame_off || n_utt < 0) return -1;
+    return frame_off[n_utt] + (int64_t)48 * n_utt;
+}
+
+void *phn_stream(phn_ctx *c) { return c ? (void *)c->stream : nullptr; }
+int phn_sync(phn_ctx *c)
+{
+    if (!c) return PHN_ERR_ARG;
+    PHN_CUDA(c, cudaSetDevice(c->device));
+    PHN_CUDA(c, cudaStreamSynchronize(c->stream));
+    return PHN_OK;
+}
+void *phn_device_alloc(phn_ctx *c, int64_t n)
+{
+    void *p = nullptr;
+    if (!c || cudaSetDevice(c->device) != cudaSuccess || cudaMalloc(&p, (size_t)(n > 0 ? n : 1)) != cudaSuccess) return nullptr;
+    return p;
+}
+void phn_device_free(phn_ctx *c, void *p)
+{
+    if (c && p) { cudaSetDevice(c->device); cudaFree(p); }
+}
+void *phn_host_alloc_pinned(int64_t n)
+{
+    void *p = nullptr;
+    if (cudaMallocHost(&p, (size_t)(n > 0 ? n : 1)) != cudaSuccess) return nullptr;
+    return p;
+}
+void phn_host_free_pinned(void *p) { if (p) cudaFreeHost(p); }
+int phn_memcpy_h2d(phn_ctx *c, void *dst, const void *src, int64_t n)
+{
+    if (!c) return PHN_ERR_ARG;
+    PHN_CUDA(c, cudaSetDevice(c->device));
+    PHN_CUDA(c, cudaMemcpyAsync(dst, src, (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    return PHN_OK;
+}
+int phn_memcpy_d2h(phn_ctx *c, void *dst, const void *src, int64_t n)
+{
+    if (!c) return PHN_ERR_ARG;
+    PHN_CUDA(c, cudaSetDevice(c->device));
+    PHN_CUDA(c, cudaMemcpyAsync(dst, src, (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+    PHN_CUDA(c, cudaStreamSynchronize(c->stream));
+    return PHN_OK;
+}
+int phn_synth_audio_device(phn_ctx *c, void *d_audio, int64_t bytes_per_utt, int n_utt, uint64_t seed)
+{
+    if (!c || !d_audio) return PHN_ERR_ARG;
+    PHN_CUDA(c, cudaSetDevice(c->device));
+    return launch_synth(c, d_audio, bytes_per_utt, n_utt, seed);
+}
+
+// --------------------------------------------------------------------- stages
+int phn_recognize_device(phn_ctx *c, const void *d_audio, const int64_t *byte_off, int n_utt)
+{
+    if (!c || !d_audio) return PHN_ERR_ARG;
+    PHN_CUDA(c, cudaSetDevice(c->device));
+    reset_timing(c);
+    int rc;
+    if ((rc = plan_audio(c, byte_off, n_utt))) return rc;
+    { StageTimer t(c, PHN_K_WAVE); if ((rc = launch_wave(c, d_audio))) return rc; }
+    if ((rc = run_posteriors(c))) return rc;
+    return run_decode(c, nullptr, 1);
+}
+
+int phn_fetch_mel(phn_ctx *c, float *mel_out)
+{
+    if (!c || !mel_out) return PHN_ERR_ARG;
+    PHN_CUDA(c, cudaSetDevice(c->device));
+    PHN_CUDA(c, cudaMemcpyAsync(mel_out, c->d_mel.p, sizeof(float) * c->total_frames * c->nbanks, cudaMemcpyDeviceToHost, c->stream));
+    PHN_CUDA(c, cudaStreamSynchronize(c->stream));
+    return PHN_OK;
+}
+int phn_fetch_posteriors(phn_ctx *c, float *post_out)
+{
+    if (!c || !post_out) return PHN_ERR_ARG;
+    PHN_CUDA(c, cudaSetDevice(c->device));
+    PHN_CUDA(c, cudaMemcpyAsync(post_out, c->d_post.p, sizeof(float) * c->total_frames * c->net[2].nout, cudaMemcpyDeviceToHost, c->stream));
+    PHN_CUDA(c, cudaStreamSynchronize(c->stream));
+    return PHN_OK;
+}
+
+int phn_fetch_labels(phn_ctx *c, phn_label *labels, int64_t label_cap, int64_t *label_off)
+{
+    if (!c) return PHN_ERR_ARG;
+    PHN_CUDA(c, cudaSetDevice(c->device));
+    const int nseg = c->n_utt * c->n_pen;
+    c->h_nlab.resize((size_t)nseg);
+    if (nseg)
+        PHN_CUDA(c, cudaMemcpyAsync(c->h_nlab.data(), c->d_nlab.p, sizeof(int) * nseg, cudaMemcpyDeviceToHost, c->stream));
+    PHN_CUDA(c, cudaStreamSynchronize(c->stream));
+    int64_t total = 0;
+    std::vector<int64_t> off((size_t)nseg + 1, 0);
+    for (int s = 0; s < nseg; ++s) {
+        const int64_t cap = c->h_lab_off[s + 1] - c->h_lab_off[s];
+        if (c->h_nlab[s] > cap) return fail(c, PHN_ERR_CAPACITY, "internal label capacity exceeded (segment %d)\n", s);
+        total += c->h_nlab[s];
+        off[s + 1] = total;
+    }
+    if (label_off) memcpy(label_off, off.data(), sizeof(int64_t) * (nseg + 1));
+    if (!labels) return PHN_OK;
+    if (label_cap < total) return fail(c, PHN_ERR_CAPACITY, "label buffer too small: %lld needed\n", (long long)total);
+    if (total == 0) return PHN_OK;
+    // gather the produced labels into one contiguous run on the device, then a single D2H copy
+    int rc;
+    if ((rc = ensure(c, c->d_coff, sizeof(int64_t) * (nseg + 1)))) return rc;
+    if ((rc = ensure(c, c->d_labels_c, sizeof(phn_label) * (size_t)total))) return rc;
+    PHN_CUDA(c, cudaMemcpyAsync(c->d_coff.p, off.data(), sizeof(int64_t) * (nseg + 1), cudaMemcpyHostToDevice, c->stream));
+    if ((rc = launch_compact_labels(c, nseg))) return rc;
+    PHN_CUDA(c, cudaMemcpyAsync(labels, c->d_labels_c.p, sizeof(phn_label) * (size_t)total, cudaMemcpyDeviceToHost, c->stream));
+    PHN_CUDA(c, cudaStreamSynchronize(c->stream));
+    return PHN_OK;
+}
+
+int phn_mel(phn_ctx *c, const void *audio, const int64_t *byte_off, int n_utt, float *mel_out, int64_t *frame_off)
+{
+    if (!c || !byte_off || (!audio && n_utt > 0 && byte_off[n_utt] > 0)) return PHN_ERR_ARG;
+    PHN_CUDA(c, cudaSetDevice(c->device));
+    reset_timing(c);
+    int rc;
+    if ((rc = plan_audio(c, byte_off, n_utt))) return rc;
+    if (frame_off) memcpy(frame_off, c->h_frame_off.data(), sizeof(int64_t) * (n_utt + 1));
+    if (!mel_out) return PHN_OK;
+    if ((rc = ensure(c, c->d_audio, (size_t)c->total_bytes + 16))) return rc;
+    if (c->total_bytes)
+        PHN_CUDA(c, cudaMemcpyAsync(c->d_audio.p, audio, (size_t)c->total_bytes, cudaMemcpyHostToDevice, c->stream));
+    { StageTimer t(c, PHN_K_WAVE); if ((rc = launch_wave(c, c->d_audio.p))) return rc; }
+    return phn_fetch_mel(c, mel_out);
+}
+
+int phn_posteriors(phn_ctx *c, const float *mel, const int64_t *frame_off, int n_utt, float *post_out)
+{
+    if (!c || !mel || !frame_off || !post_out) return PHN_ERR_ARG;
+    PHN_CUDA(c, cudaSetDevice(c->device));
+    reset_timing(c);
+    int rc;
+    if ((rc = plan_frames(c, frame_off, n_utt, 1))) return rc;
+    PHN_CUDA(c, cudaMemcpyAsync(c->d_mel.p, mel, sizeof(float) * c->total_frames * c->nbanks, cudaMemcpyHostToDevice, c->stream));
+    if ((rc = run_posteriors(c))) return rc;
+    return phn_fetch_posteriors(c, post_out);
+}
+
+int phn_decode(phn_ctx *c, const float *post, const int64_t *frame_off, int n_utt, const float *penalties, int n_pen,
+               phn_label *labels, int64_t label_cap, int64_t *label_off)
+{
+    if (!c || !post || !frame_off) return PHN_ERR_ARG;
+    if (!penalties) n_pen = 1;
+    PHN_CUDA(c, cudaSetDevice(c->device));
+    reset_timing(c);
+    int rc;
+    if ((rc = plan_frames(c, frame_off, n_utt, n_pen))) return rc;
+    PHN_CUDA(c, cudaMemcpyAsync(c->d_post.p, post, sizeof(float) * c->total_frames * c->net[2].nout, cudaMemcpyHostToDevice, c->stream));
+    if ((rc = run_decode(c, penalties, n_pen))) return rc;
+    return phn_fetch_labels(c, labels, label_cap, label_off);
+}
+
+int phn_recognize(phn_ctx *c, const void *audio, const int64_t *byte_off, int n_utt, phn_label *labels, int64_t label_cap,
+                  int64_t *label_off, int64_t *frame_off_out)
+{
+    if (!c || !byte_off || (!audio && n_utt > 0 && byte_off[n_utt] > 0)) return PHN_ERR_ARG;
+    PHN_CUDA(c, cudaSetDevice(c->device));
+    int rc;
+    if ((rc = ensure(c, c->d_audio, (size_t)byte_off[n_utt] + 16))) return rc;
+    if (byte_off[n_utt])
+        PHN_CUDA(c, cudaMemcpyAsync(c->d_audio.p, audio, (size_t)byte_off[n_utt], cudaMemcpyHostToDevice, c->stream));
+    if ((rc = phn_recognize_device(c, c->d_audio.p, byte_off, n_utt))) return rc;
+    if (frame_off_out) memcpy(frame_off_out, c->h_frame_off.data(), sizeof(int64_t) * (n_utt + 1));
+    return phn_fetch_labels(c, labels, label_cap, label_off);
+}
+
+int phn_online_norm(phn_ctx *c, float *x, int64_t frames, int nbanks, int interval, int mean_norm, int var_norm)
+{
+    if (!c || !x || frames < 0 || nbanks < 1) return PHN_ERR_ARG;
+    PHN_CUDA(c, cudaSetDevice(c->device));
+    int rc;
+    phn_ctx::Buf tmp;
+    if ((rc = ensure(c, tmp, sizeof(float) * frames * nbanks))) return rc;
+    PHN_CUDA(c, cudaMemcpyAsync(tmp.p, x, sizeof(float) * frames * nbanks, cudaMemcpyHostToDevice, c->stream));
+    rc = launch_online_norm(c, (float *)tmp.p, frames, nbanks, interval, mean_norm, var_norm);
+    if (rc == PHN_OK) {
+        cudaMemcpyAsync(x, tmp.p, sizeof(float) * frames * nbanks, cudaMemcpyDeviceToHost, c->stream);
+        cudaStreamSynchronize(c->stream);
+    }
+    cudaFree(tmp.p);
+    return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,108 @@
+// host_model.cpp — model artefacts read from a PHN_* directory and the front-end tables.
+// Everything here runs once at phn_create(); tables are built with the same single-precision
+// expressions (and the same libm) the reference uses, so the device kernels that consume them
+// reproduce the reference's numbers bit for bit.  Compile with -ffp-contract=off.
+#include "internal.h"
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+
+namespace phn {
+
+// .nbin layout (nn.cpp:464-531; padding rule nn.cpp:633-682): int32 nlayers(=2), nIn, nHid, nOut;
+// then W1 [nHid4][nIn4], W2 [nOut4][nHid4], b1, b2, mean, dev with X4 = X rounded up to 4 floats.
+int HostNet::load(const std::string &path)
+{
+    FILE *f = fopen(path.c_str(), "rb");
+    if (!f) return PHN_ERR_NN_FILE;
+    int32_t hdr[4];
+    if (fread(hdr, sizeof(int32_t), 4, f) != 4) { fclose(f); return PHN_ERR_NN_FILE; }
+    if (hdr[0] != 2 || hdr[1] <= 0 || hdr[2] <= 0 || hdr[3] <= 0) { fclose(f); return PHN_ERR_NN_FORMAT; }
+    nin = hdr[1]; nhid = hdr[2]; nout = hdr[3];
+    auto up4 = [](int n) { return (n + 3) / 4 * 4; };
+    nin4 = up4(nin); nhid4 = up4(nhid); nout4 = up4(nout);
+    struct { std::vector<float> *v; size_t n; } parts[] = {
+        {&w1, (size_t)nhid4 * nin4}, {&w2, (size_t)nout4 * nhid4}, {&b1, (size_t)nhid4},
+        {&b2, (size_t)nout4},        {&mean, (size_t)nin4},        {&dev, (size_t)nin4}};
+    for (auto &p : parts) {
+        p.v->resize(p.n);
+        if (fread(p.v->data(), sizeof(float), p.n, f) != p.n) { fclose(f); return PHN_ERR_NN_FILE; }
+    }
+    fclose(f);
+    return PHN_OK;
+}
+
+static float mel_scale(float hz) { return 1127.0f * logf(1.0f + hz / 700.0f); }  // dspc.h:169-177
+
+void MelTables::build(int nbanks_, int vs_, int step_, int fs_, float lo, float hi)
+{
+    nbanks = nbanks_; vs = vs_; step = step_; fs = fs_;
+    N = 1; logN = 0;
+    while (N < vs) { N <<= 1; ++logN; }  // melbanks.cpp:44-46
+    N2 = N / 2;
+
+    // Hamming window as the reference obtains it: sWindow_Hamming applied to ones (dspc.h:162-167)
+    hamming.resize(vs);
+    for (int i = 0; i < vs; ++i) hamming[i] = 1.0f * (0.54f - 0.46f * cosf(2.0f * (float)M_PI * i / (vs - 1)));
+
+    // triangular filters on the mel axis (dspc.cpp:80-225)
+    if (lo < 0.0f) lo = 0.0f;
+    if (hi > (float)fs / 2.0f) hi = (float)fs / 2.0f;
+    const float bin_hz = (float)fs / (float)N;
+    const float mlo = mel_scale(lo), mhi = mel_scale(hi);
+    fftlo = (int)(lo / bin_hz + 1.5f);
+    ffthi = (int)(hi / bin_hz - 0.5f);
+    if (fftlo < 1) fftlo = 1;
+    if (ffthi >= N2) ffthi = N2 - 1;
+    std::vector<float> centre(nbanks + 2);
+    const float dmel = (mhi - mlo) / (nbanks + 1);
+    float acc = mlo;
+    for (int i = 0; i <= nbanks; ++i) { acc = acc + dmel; centre[i] = acc; }  // repeated addition, dspc.cpp:156-162
+    centre[nbanks + 1] = INFINITY;
+    banks.assign(N2, -1);
+    coeffs.assign(N2, 0.0f);
+    int ch = 0;
+    for (int k = fftlo; k <= ffthi; ++k) {
+        const float m = mel_scale((float)k * bin_hz);
+        while (m > centre[ch] && ch <= nbanks) ++ch;
+        banks[k] = ch;
+        const float below = ch == 0 ? mlo : centre[ch - 1];
+        coeffs[k] = (centre[ch] - m) / (centre[ch] - below);
+    }
+    // bank b collects (1-c)P[k] from bins assigned to b and cP[k] from bins assigned to b+1, in
+    // ascending k (dspc.cpp:236-269); Banks[] is non-decreasing so that is one contiguous range.
+    bank_klo.assign(nbanks, 0);
+    bank_khi.assign(nbanks, -1);
+    for (int b = 0; b < nbanks; ++b) {
+        int lo_k = -1, hi_k = -2;
+        for (int k = fftlo; k <= ffthi; ++k)
+            if (banks[k] == b || banks[k] == b + 1) {
+                if (lo_k < 0) lo_k = k;
+                hi_k = k;
+            }
+        bank_klo[b] = lo_k < 0 ? 0 : lo_k;
+        bank_khi[b] = hi_k;
+    }
+
+    // FFT twiddles exactly as the Numerical-Recipes recurrence in cFour1 produces them
+    // (dspc.cpp:24-78, isign = -1): per stage a double-precision rotation started at (1, 0).
+    tw.assign((size_t)2 * (N - 1), 0.0);
+    for (int h = 1; h < N; h <<= 1) {
+        const unsigned mmax = 2u * (unsigned)h;  // NR counts floats
+        const double theta = -1 * (6.28318530717959 / mmax);
+        double wtemp = sin(0.5 * theta);
+        const double wpr = -2.0 * wtemp * wtemp;
+        const double wpi = sin(theta);
+        double wr = 1.0, wi = 0.0;
+        for (int m = 0; m < h; ++m) {
+            tw[2 * (size_t)(h - 1 + m)] = wr;
+            tw[2 * (size_t)(h - 1 + m) + 1] = wi;
+            wtemp = wr;
+            wr = wtemp * wpr - wi * wpi + wr;
+            wi = wi * wpr + wtemp * wpi + wi;
+        }
+    }
+}
+
+}  // namespace phn

@@ -1,0 +1,124 @@
+// internal.h — shared declarations of libphnrec_b200 (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include <map>
+
+#include "../../include/phnrec_b200.h"
+
+namespace phn {
+
+// ---------------------------------------------------------------- host: config
+// The INI dialect of configz.cpp:102-165 with the typed variable table of srec.cpp:34-110.
+struct Config {
+    std::map<std::string, std::string> kv;  // "section/variable" -> value
+    int load(const std::string &file, int *err_line);  // PHN_OK or PHN_ERR_CFG_*
+    const std::string &str(const char *sec, const char *var) const;
+    int i(const char *sec, const char *var) const;
+    float f(const char *sec, const char *var) const;
+    bool b(const char *sec, const char *var) const;
+};
+
+// ---------------------------------------------------------------- host: model
+struct HostNet {  // .nbin image, nn.cpp:464-531
+    int nin = 0, nhid = 0, nout = 0, nin4 = 0, nhid4 = 0, nout4 = 0;
+    std::vector<float> w1, w2, b1, b2, mean, dev;
+    int load(const std::string &path);  // PHN_OK / PHN_ERR_NN_*
+};
+
+struct MelTables {  // melbanks.cpp:38-70, dspc.cpp:80-225, dspc.h:162-167
+    int nbanks, vs, step, fs, N, logN, N2, fftlo, ffthi;
+    std::vector<float> hamming, coeffs;
+    std::vector<int> banks;
+    std::vector<int> bank_klo, bank_khi;  // per bank: contiguous bin range that feeds it
+    std::vector<double> tw;               // (wr, wi) pairs: stage h=1,2,4..N/2, index m<h at [2*(h-1+m)]
+    void build(int nbanks, int vs, int step, int fs, float lo, float hi);
+};
+
+// ---------------------------------------------------------------- device: model
+struct DevNet {
+    int nin, nhid, nout, nin4, nhid4, nout4;
+    int kp;    // layer-1 K rounded up to 16  (row stride of the fp32 input matrix)
+    int ldh;   // hidden row stride: nhid4 rounded up to 16
+    float *w1, *w2, *b1, *b2, *mean, *dev;  // fp32 images exactly as in the .nbin
+    // fp16 tensor-core images (K-major, zero padded): w1h [nhidP][k1P], w2h [noutP][nhidP]
+    __half *w1h, *w2h;
+    int k1P, nhidP, noutP;
+};
+
+struct DevTables {
+    float *hamming, *coeffs;
+    int *banks, *bank_klo, *bank_khi;
+    double2 *tw;
+    float *win;   // [32] band0 then band1 window
+    float *dct;   // [10][16] cosf table (dspc.h:206-221)
+};
+
+}  // namespace phn
+
+// ---------------------------------------------------------------- the context
+struct phn_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    std::string cfg_dir;
+    phn::Config cfg;
+    // config-derived
+    int fs = 8000, fmt = 0, nbanks = 15, vs = 200, step = 80, S = 3, P = 0, hist = 40;
+    int sent_mean_norm = 0, z_mean = 0;
+    float lo = 0, hi = 4000, preem = 0, wpenalty = -2.f, frame_shift = 0.f, frame_floor = -9999.9f, scale = 1.f, dc_shift = 0.f;
+    int mlp_mode = PHN_MLP_EXACT_FP32;
+    std::vector<std::string> phonemes;
+    float win[32];
+    phn::HostNet hnet[3];
+    phn::MelTables mt;
+    phn::DevNet net[3];
+    phn::DevTables tab{};
+    int ncoef = 11;
+    int num_sms = 148;
+
+    // ---- batch state (grow-only device buffers)
+    int n_utt = 0, n_pen = 1;
+    int64_t total_bytes = 0, total_frames = 0, label_cap = 0;
+    std::vector<int64_t> h_byte_off, h_frame_off, h_lab_off;
+    struct Buf { void *p = nullptr; size_t cap = 0; };
+    Buf d_audio, d_byte_off, d_frame_off, d_lab_off, d_mel, d_mean, d_post, d_rec, d_labels, d_nlab, d_pen;
+    Buf d_x0, d_x1, d_h, d_xm, d_x0h, d_x1h, d_xmh;  // MLP workspace (per frame chunk)
+    Buf d_tile_ctr, d_coff, d_labels_c;
+    std::vector<int32_t> h_nlab;
+    int64_t chunk_frames = 0;
+    // profiling
+    int profiling = 0;
+    float k_ms[PHN_K_COUNT] = {0};
+    int64_t k_launches[PHN_K_COUNT] = {0};
+    cudaEvent_t ev[2 * PHN_K_COUNT] = {nullptr};
+};
+
+namespace phn {
+// ---- error helpers
+int fail(phn_ctx *c, int code, const char *fmt, ...);
+#define PHN_CUDA(c, expr)                                                                        \
+    do {                                                                                         \
+        cudaError_t e__ = (expr);                                                                \
+        if (e__ != cudaSuccess)                                                                  \
+            return phn::fail((c), PHN_ERR_CUDA, "CUDA failure: %s (%s) at %s:%d\n", cudaGetErrorString(e__), #expr, \
+                             __FILE__, __LINE__);                                                \
+    } while (0)
+
+int ensure(phn_ctx *c, phn_ctx::Buf &b, size_t bytes);
+
+// ---- kernel launchers (each in its own .cu)
+int launch_wave(phn_ctx *c, const void *d_audio);                          // k_wave.cu
+int launch_sentence_mean(phn_ctx *c);                                      // k_norm.cu
+int launch_online_norm(phn_ctx *c, float *d_x, int64_t frames, int nb, int interval, int mean_norm, int var_norm);
+int launch_stc(phn_ctx *c, int64_t f0, int64_t nf);                        // k_stc.cu
+int launch_mlp_exact(phn_ctx *c, int64_t f0, int64_t nf);                  // k_mlp_exact.cu
+int launch_mlp_tc(phn_ctx *c, int64_t f0, int64_t nf);                     // k_mlp_tc.cu
+int launch_viterbi(phn_ctx *c, const float *d_pen, int n_pen);             // k_vit.cu
+int launch_compact_labels(phn_ctx *c, int nseg);                           // k_vit.cu
+int launch_synth(phn_ctx *c, void *d_audio, int64_t bytes_per_utt, int n_utt, uint64_t seed);  // k_synth.cu
+int mlp_tc_prepare(phn_ctx *c);                                            // fp16 weight images + tensor maps
+}  // namespace phn

@@ -1,0 +1,314 @@
+// k_vit.cu — K-vit + K-trace: the phone-loop token-passing decoder, one warp (one CTA) per
+// (utterance, penalty).
+//
+// Replaces the decoder soft function decSoftFunc=log (srec.h:192-195, srec.cpp:1088-1097) and
+// PhnDec::{Init, PropagateInModels, PropagateInNetwork, AddHistory, GetBestToken, TimePruning,
+// Done} (phndec.cpp:44-302).  All comparisons are the reference's strict fp32 `>` with
+// first-index tie breaking; additions are single fp32 adds in the written order; log is the
+// glibc logf port, so labels, boundaries AND scores are bit-identical to the reference when both
+// are fed the same posteriors.
+//
+// Phase 1 (sequential in time): lane l owns phones l, l+32, ... with their 3 emitting states in
+//   registers.  Per frame: state update, then redux.sync max/min over the warp for the best
+//   phone-end token (mx, mi) and for the best token overall; the winners' (prev, len) go to a
+//   per-frame record in global memory instead of the reference's 41-slot shift register.
+// Phase 2 (parallel over frames): the partial traceback of TimePruning is an independent walk
+//   for every frame n > H over those records (SURVEY §8a "verified restatement notes"); emitted
+//   labels are compacted in time order with ballots, scores are differences of consecutive
+//   commit alphas; lane 0 appends the final traceback of Done.
+#include "internal.h"
+#include "device_math.cuh"
+
+#include <cfloat>
+
+namespace phn {
+
+struct VitArgs {
+    const float *post;       // [total_frames][ncols] linear posteriors
+    int ncols;
+    const int64_t *frame_off;
+    int n_utt, P, H;
+    int64_t total_frames;
+    const float *pen;        // [n_pen]
+    int *r_hphn, *r_hlen, *r_bp, *r_bl;  // [n_pen * total_frames]
+    float *r_halpha;
+    phn_label *labels;
+    const int64_t *lab_off;  // [n_pen*n_utt + 1] capacity offsets
+    int *nlab;               // [n_pen*n_utt]
+};
+
+#define PHN_LN05 (-0.69314718055994530941723212145818f) /* phndec.cpp:9 */
+
+__device__ __forceinline__ unsigned f2ord(float v)
+{
+    const unsigned u = __float_as_uint(v);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ord2f(unsigned o)
+{
+    return __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o);
+}
+
+template <int PPL>
+__global__ void __launch_bounds__(32) k_viterbi(VitArgs a)
+{
+    const int seg = blockIdx.x;
+    const int kpen = seg / a.n_utt, u = seg - kpen * a.n_utt;
+    const int lane = threadIdx.x;
+    const int64_t f0 = a.frame_off[u];
+    const int T = (int)(a.frame_off[u + 1] - f0);
+    const float wp = a.pen[kpen];
+    const int H = a.H;
+    const int64_t rbase = (int64_t)kpen * a.total_frames + f0;
+    int *hphn = a.r_hphn + rbase, *hlen = a.r_hlen + rbase, *rbp = a.r_bp + rbase, *rbl = a.r_bl + rbase;
+    float *halpha = a.r_halpha + rbase;
+    const unsigned FULL = 0xffffffffu;
+    const unsigned ORD_FLOOR = f2ord(-FLT_MAX);
+
+    float al[PPL][4];
+    int pv[PPL][4], ln[PPL][4];
+    bool valid[PPL];
+#pragma unroll
+    for (int r = 0; r < PPL; ++r) {
+        valid[r] = lane + 32 * r < a.P;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { al[r][j] = -FLT_MAX; pv[r][j] = -1; ln[r][j] = 0; }
+        al[r][0] = wp;
+    }
+    int last_mi = -1;  // prev[0][0] after the last frame (phndec.cpp:240)
+
+    constexpr int FB = 4;  // frames whose observations are fetched and logged ahead of the recurrence
+    for (int tb = 0; tb < T; tb += FB) {
+        float obs[FB][PPL][3];
+#pragma unroll
+        for (int q = 0; q < FB; ++q)
+#pragma unroll
+            for (int r = 0; r < PPL; ++r)
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    const int i = lane + 32 * r;
+                    obs[q][r][j] = (valid[r] && tb + q < T) ? a.post[(f0 + tb + q) * a.ncols + 3 * i + j] : 1.0f;
+                }
+#pragma unroll
+        for (int q = 0; q < FB; ++q)
+#pragma unroll
+            for (int r = 0; r < PPL; ++r)
+#pragma unroll
+                for (int j = 0; j < 3; ++j) obs[q][r][j] = logf_glibc(obs[q][r][j]);  // SoftLog, no guard
+
+#pragma unroll
+        for (int q = 0; q < FB; ++q) {
+            const int t = tb + q;
+            if (t >= T) break;
+            // ---- PropagateInModels (phndec.cpp:96-119): descending j, in place
+#pragma unroll
+            for (int r = 0; r < PPL; ++r) {
+                if (!valid[r]) continue;
+#pragma unroll
+                for (int j = 3; j > 0; --j) {
+                    const float cur = __fadd_rn(al[r][j], PHN_LN05);
+                    const float prv = __fadd_rn(al[r][j - 1], PHN_LN05);
+                    if (cur > prv) {
+                        al[r][j] = __fadd_rn(cur, obs[q][r][j - 1]);
+                        ln[r][j] += 1;
+                    } else {
+                        al[r][j] = __fadd_rn(prv, obs[q][r][j - 1]);
+                        pv[r][j] = pv[r][j - 1];
+                        ln[r][j] = ln[r][j - 1] + 1;
+                    }
+                }
+            }
+            // ---- PropagateInNetwork (phndec.cpp:121-144): first strict max of alpha[i][3] from (-FLT_MAX, 0)
+            unsigned bo = ORD_FLOOR;
+            int bi = 0;
+#pragma unroll
+            for (int r = 0; r < PPL; ++r) {
+                const float v = al[r][3];
+                if (valid[r] && v > -FLT_MAX) {
+                    const unsigned o = f2ord(v + 0.0f);
+                    if (o > bo) { bo = o; bi = lane + 32 * r; }
+                }
+            }
+            const unsigned mo = __reduce_max_sync(FULL, bo);
+            const int mi = (int)__reduce_min_sync(FULL, bo == mo ? (unsigned)bi : 0x7fffffffu);
+            const float mx = mo == ORD_FLOOR ? -FLT_MAX : ord2f(mo);
+            // AddHistory (phndec.cpp:146-158): record of frame t+1
+            if ((mi & 31) == lane) {
+#pragma unroll
+                for (int r = 0; r < PPL; ++r)
+                    if (r == (mi >> 5)) { hphn[t] = pv[r][3]; hlen[t] = ln[r][3]; halpha[t] = mx; }
+            }
+            const float entry = __fadd_rn(mx, wp);
+#pragma unroll
+            for (int r = 0; r < PPL; ++r) { al[r][0] = entry; pv[r][0] = mi; ln[r][0] = 0; }
+            last_mi = mi;
+            // ---- GetBestToken (phndec.cpp:169-189), only consumed by TimePruning when n >= H+1
+            if (t + 1 >= H + 1) {
+                unsigned co = ORD_FLOOR;
+                int ci = 0x7fffffff;
+#pragma unroll
+                for (int r = 0; r < PPL; ++r)
+#pragma unroll
+                    for (int j = 1; j <= 3; ++j) {
+                        const float v = al[r][j];
+                        if (valid[r] && v > -FLT_MAX) {
+                            const unsigned o = f2ord(v + 0.0f);
+                            if (o > co) { co = o; ci = (lane + 32 * r) * 3 + (j - 1); }
+                        }
+                    }
+                const unsigned to = __reduce_max_sync(FULL, co);
+                const int ti = (int)__reduce_min_sync(FULL, (co == to && ci != 0x7fffffff) ? (unsigned)ci : 0x7fffffffu);
+                if (ti == 0x7fffffff) {  // nothing above -FLT_MAX: the scan's initial (len 1, prev 0)
+                    if (lane == 0) { rbl[t] = 1; rbp[t] = 0; }
+                } else {
+                    const int wi = ti / 3, wj = ti - wi * 3 + 1;
+                    if ((wi & 31) == lane) {
+#pragma unroll
+                        for (int r = 0; r < PPL; ++r)
+#pragma unroll
+                            for (int j = 1; j <= 3; ++j)
+                                if (r == (wi >> 5) && j == wj) { rbl[t] = ln[r][j]; rbp[t] = pv[r][j]; }
+                    }
+                }
+            }
+        }
+    }
+    __syncwarp();
+    __threadfence_block();
+
+    // ------------------------------------------------------------------ phase 2: traceback
+    // record of frame number n (1-based) lives at index n-1; n <= 0 is the initial shift-register
+    // content (phndec.cpp:71-78): phn -1, len -1, alpha -1.0f
+    auto Hphn = [&](int n) { return n >= 1 ? hphn[n - 1] : -1; };
+    auto Hlen = [&](int n) { return n >= 1 ? hlen[n - 1] : -1; };
+    auto Halpha = [&](int n) { return n >= 1 ? halpha[n - 1] : -1.0f; };
+
+    phn_label *out = a.labels + a.lab_off[seg];
+    const int cap = (int)(a.lab_off[seg + 1] - a.lab_off[seg]);
+    int count = 0;
+    // TimePruning (phndec.cpp:191-234) for every n in [H+1, T]
+    for (int nb = H + 1; nb <= T; nb += 32) {
+        const int n = nb + lane;
+        bool emit = false;
+        int q = 0;
+        if (n <= T) {
+            int o = H - rbl[n - 1];
+            q = rbp[n - 1];
+            while (o > 0) {
+                const int uu = n - H + o;
+                q = Hphn(uu);
+                o -= Hlen(uu);
+            }
+            emit = o == 0;
+        }
+        const unsigned m = __ballot_sync(FULL, emit);
+        if (emit) {
+            const int pos = count + __popc(m & ((1u << lane) - 1u));
+            if (pos < cap) {
+                const int end = n - H;
+                out[pos].phn = q;
+                out[pos].start = end - Hlen(end);
+                out[pos].end = end;
+                out[pos].like = Halpha(end);  // commit alpha; turned into a score below
+            }
+        }
+        count += __popc(m);
+    }
+    __syncwarp();
+    const int n_commit = count < cap ? count : cap;
+    // like_k = alpha_k - alpha_{k-1} (mPrevAlpha chain, phndec.cpp:226-232), alpha_{-1} = 0.
+    // Chunks are rewritten from the end so that alpha_{k-1} is still intact when chunk k reads it.
+    float prev_alpha = n_commit > 0 ? out[n_commit - 1].like : 0.0f;
+    for (int kb = ((n_commit - 1) / 32) * 32; kb >= 0 && n_commit > 0; kb -= 32) {
+        const int k = kb + lane;
+        float ak = 0.0f, ap = 0.0f;
+        if (k < n_commit) { ak = out[k].like; ap = k > 0 ? out[k - 1].like : 0.0f; }
+        __syncwarp();
+        if (k < n_commit) out[k].like = __fsub_rn(ak, ap);
+        __syncwarp();
+    }
+
+    // Done (phndec.cpp:236-302): final traceback, lane 0, at most H labels
+    if (lane == 0) {
+        int cnt = 0;
+        {
+            int o = H, q = T > 0 ? last_mi : -1;
+            while (o > 0 && q != -1) {
+                const int uu = T - H + o;
+                q = Hphn(uu);
+                o -= Hlen(uu);
+                ++cnt;
+            }
+        }
+        int o = H, end = T, q = T > 0 ? last_mi : -1, idx = 0;
+        while (o > 0 && q != -1) {
+            const int uu = T - H + o;
+            const int l = Hlen(uu);
+            const float av = Halpha(uu);
+            const int qq = Hphn(uu);
+            o -= l;
+            const float like = o > 0 ? __fsub_rn(av, Halpha(T - H + o)) : __fsub_rn(av, prev_alpha);
+            const int pos = count + (cnt - 1 - idx);
+            if (pos < cap) { out[pos].phn = q; out[pos].start = end - l; out[pos].end = end; out[pos].like = like; }
+            end -= l;
+            q = qq;
+            ++idx;
+        }
+        a.nlab[seg] = count + cnt;
+    }
+}
+
+int launch_viterbi(phn_ctx *c, const float *d_pen, int n_pen)
+{
+    const int nseg = c->n_utt * n_pen;
+    if (nseg == 0) return PHN_OK;
+    VitArgs a;
+    a.post = (const float *)c->d_post.p;
+    a.ncols = c->net[2].nout;
+    a.frame_off = (const int64_t *)c->d_frame_off.p;
+    a.n_utt = c->n_utt; a.P = c->P; a.H = c->hist;
+    a.total_frames = c->total_frames;
+    a.pen = d_pen;
+    const size_t R = (size_t)n_pen * (size_t)c->total_frames;
+    int *rec = (int *)c->d_rec.p;
+    a.r_hphn = rec; a.r_hlen = rec + R; a.r_bp = rec + 2 * R; a.r_bl = rec + 3 * R;
+    a.r_halpha = (float *)(rec + 4 * R);
+    a.labels = (phn_label *)c->d_labels.p;
+    a.lab_off = (const int64_t *)c->d_lab_off.p;
+    a.nlab = (int *)c->d_nlab.p;
+    const int ppl = (c->P + 31) / 32;
+    switch (ppl) {
+        case 1: k_viterbi<1><<<nseg, 32, 0, c->stream>>>(a); break;
+        case 2: k_viterbi<2><<<nseg, 32, 0, c->stream>>>(a); break;
+        case 3: k_viterbi<3><<<nseg, 32, 0, c->stream>>>(a); break;
+        case 4: k_viterbi<4><<<nseg, 32, 0, c->stream>>>(a); break;
+        default: return fail(c, PHN_ERR_UNSUPPORTED, "more than 128 phonemes\n");
+    }
+    PHN_CUDA(c, cudaGetLastError());
+    c->k_launches[PHN_K_VIT] += 1;
+    return PHN_OK;
+}
+
+// Gather each segment's labels (stored at capacity offsets) into one contiguous run.
+__global__ void k_compact_labels(const phn_label *__restrict__ src, const int64_t *__restrict__ cap_off,
+                                 const int64_t *__restrict__ out_off, phn_label *__restrict__ dst)
+{
+    const int seg = blockIdx.x;
+    const int64_t s0 = cap_off[seg], d0 = out_off[seg];
+    const int n = (int)(out_off[seg + 1] - d0);
+    const int4 *s = reinterpret_cast<const int4 *>(src + s0);
+    int4 *d = reinterpret_cast<int4 *>(dst + d0);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) d[i] = s[i];
+}
+
+int launch_compact_labels(phn_ctx *c, int nseg)
+{
+    if (nseg == 0) return PHN_OK;
+    k_compact_labels<<<nseg, 64, 0, c->stream>>>((const phn_label *)c->d_labels.p, (const int64_t *)c->d_lab_off.p,
+                                                 (const int64_t *)c->d_coff.p, (phn_label *)c->d_labels_c.p);
+    PHN_CUDA(c, cudaGetLastError());
+    c->k_launches[PHN_K_VIT] += 1;
+    return PHN_OK;
+}
+
+}  // namespace phn

@@ -1,0 +1,226 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same inputs
+and against the committed reference-built fixtures.  Exact mode bar: BIT-exact mel, posteriors,
+labels, boundaries and scores.  Run on the B200 box:  python -m pytest tests -m gpu"""
+import numpy as np
+import pytest
+
+from conftest import ALL_MODELS, audio_bytes, model_dir, ref_run
+
+import phnrec_b200 as pb
+
+pytestmark = pytest.mark.gpu
+
+RUNS = [("PHN_CZ_SPDAT_LCRC_N1500", "test.raw"), ("PHN_CZ_SPDAT_LCRC_N1500", "8580.wav"),
+        ("PHN_EN_TIMIT_LCRC_N500", "test.raw"), ("PHN_HU_SPDAT_LCRC_N1500", "test.raw"),
+        ("PHN_RU_SPDAT_LCRC_N1500", "test.raw"), ("PHN_ES", "8580.wav"), ("PHN_ES", "es.wav")]
+
+
+@pytest.fixture(scope="module")
+def recs():
+    cache = {}
+
+    def get(name):
+        if name not in cache:
+            cache[name] = pb.Recognizer(model_dir(name), device=0)
+        return cache[name]
+    yield get
+    for r in cache.values():
+        r.close()
+
+
+def bits(a):
+    return np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+
+
+def assert_bits_equal(got, want, what):
+    got = np.asarray(got, dtype=np.float32)
+    want = np.asarray(want, dtype=np.float32)
+    assert got.shape == want.shape, (what, got.shape, want.shape)
+    bad = bits(got) != bits(want)
+    if bad.any():
+        d = np.abs(got.astype(np.float64) - want.astype(np.float64))
+        raise AssertionError(f"{what}: {int(bad.sum())}/{bad.size} values differ bitwise, max abs diff {d.max():.3e}")
+
+
+def labels_equal(a, b):
+    return (len(a) == len(b) and np.array_equal(a["phn"], b["phn"]) and np.array_equal(a["start"], b["start"])
+            and np.array_equal(a["end"], b["end"]) and np.array_equal(bits(a["like"]), bits(b["like"])))
+
+
+# ----------------------------------------------------------------------------- fixtures from the reference build
+@pytest.mark.parametrize("model,audio", RUNS)
+def test_reference_fixtures_end_to_end(recs, model, audio):
+    """audio -> mel -> posteriors -> .rec text, against what the reference's own binary wrote."""
+    r = recs(model)
+    ref = ref_run(model, audio)
+    a = audio_bytes(audio)
+    mel = r.mel([a])[0]
+    assert_bits_equal(mel, ref["mel"], "mel vs reference -t par")
+    post = r.posteriors([mel])[0]
+    assert_bits_equal(post[ref["post_rows"]], ref["post"], "posteriors vs reference -t post")
+    assert pb.format_rec(r.recognize([a])[0], r.phonemes) == str(ref["rec"])
+    assert pb.format_rec(r.decode([post], penalties=[-1.5])[0][0], r.phonemes) == str(ref["rec_p15"])
+
+
+def test_shipped_golden_labels(recs, ref_labels):
+    for g, info in ref_labels.items():
+        r = recs(info["model"])
+        lab = r.recognize([audio_bytes(info["audio"])])[0]
+        got = [(int(l["start"]), int(l["end"]), r.phonemes[int(l["phn"])]) for l in lab]
+        assert got == [(s, e, p) for s, e, p, _ in info["labels"]], g
+
+
+def test_mlf_text_matches_reference_mlf(recs, ref_labels):
+    info = ref_labels["test/test"]
+    r = recs(info["model"])
+    lab = r.recognize([audio_bytes(info["audio"])])[0]
+    got = "#!MLF!#\n" + pb.format_mlf_entry("8580.rec", lab, r.phonemes)
+    want = info["text"]
+    # another build wrote the golden: identical up to the last printed digits of the scores
+    gl, wl = got.splitlines(), want.splitlines()
+    assert len(gl) == len(wl)
+    for a, b in zip(gl, wl):
+        assert a.split()[:3] == b.split()[:3]
+
+
+# ----------------------------------------------------------------------------- against the oracle, stage by stage
+def ragged_audio(rng, fs_bytes, lengths):
+    return [rng.integers(-3000, 3000, size=n, dtype=np.int16).tobytes()[:fs_bytes * n] for n in lengths]
+
+
+@pytest.mark.parametrize("model", ["PHN_CZ_SPDAT_LCRC_N1500", "PHN_EN_TIMIT_LCRC_N500"])
+def test_ragged_batch_every_stage_bit_exact(recs, oracle_models, model):
+    r, o = recs(model), oracle_models(model)
+    rng = np.random.default_rng(5)
+    vs, st = r.vector_size, r.vector_step
+    # edge cases: empty, shorter than one window, exactly one window, one sample short of 2 frames,
+    # fewer frames than the 15-frame context, around the 41-frame decoder horizon, and long ones
+    nsamp = [0, 1, vs - 1, vs, vs + st - 1, vs + st, vs + 5 * st, vs + 13 * st, vs + 14 * st, vs + 39 * st,
+             vs + 40 * st, vs + 41 * st, vs + 200 * st + 7, vs + 997 * st]
+    base = np.frombuffer(audio_bytes("test.raw"), dtype=np.int16)
+    utts = []
+    for i, n in enumerate(nsamp):
+        seg = base[(i * 997) % 20000:][:n].copy()
+        if i % 3 == 0 and n > 50:
+            seg[n // 3: n // 2] = 0          # digital silence: the sLn zero guard
+        utts.append(seg.tobytes())
+    mels = r.mel(utts)
+    for u, m in zip(utts, mels):
+        assert_bits_equal(m, o.mel(u), f"mel, {len(u)} bytes")
+    posts = r.posteriors(mels)
+    for m, p in zip(mels, posts):
+        assert_bits_equal(p, o.posteriors(m), f"posteriors, {m.shape[0]} frames")
+    labs = r.decode(posts)
+    for p, l in zip(posts, labs):
+        assert labels_equal(l, o.decode(p)), f"labels, {p.shape[0]} frames"
+    for u, l in zip(utts, r.recognize(utts)):
+        assert labels_equal(l, o.recognize(u)), f"recognize, {len(u)} bytes"
+
+
+def test_alaw_input_path(recs, oracle_models, orc):
+    r, o = recs("PHN_CZ_SPDAT_LCRC_N1500"), oracle_models("PHN_CZ_SPDAT_LCRC_N1500")
+    rng = np.random.default_rng(11)
+    utts = [rng.integers(0, 256, size=n, dtype=np.uint8).tobytes() for n in (80000, 12345, 199, 200, 201)]
+    utts.append(bytes(range(256)) * 40)     # every A-law code
+    r.set_wave_format("alaw")
+    try:
+        for u, m in zip(utts, r.mel(utts)):
+            assert_bits_equal(m, o.mel(u, fmt="alaw"), f"alaw mel, {len(u)} bytes")
+        lin = np.frombuffer(audio_bytes("test.raw"), dtype=np.int16)
+        t = np.zeros(256, dtype=np.int16)
+        orc.lib().orc_alaw_table(t)
+        inv = {int(v) * 8: i for i, v in enumerate(t)}
+        enc = np.array([inv[int(s)] for s in lin], dtype=np.uint8).tobytes()
+        lab = r.recognize([enc])[0]
+    finally:
+        r.set_wave_format("lin16")
+    assert pb.format_rec(lab, r.phonemes) == str(ref_run("PHN_CZ_SPDAT_LCRC_N1500", "test.raw")["rec"])
+
+
+@pytest.mark.parametrize("model", ALL_MODELS)
+def test_decoder_bit_exact_on_random_posteriors(recs, oracle_models, model):
+    """Flat random posteriors drive the decoder through its odd corners (skipped commits, ties,
+    utterances shorter than the 41-frame horizon, zeros -> log = -inf)."""
+    r, o = recs(model), oracle_models(model)
+    rng = np.random.default_rng(3)
+    posts = []
+    for T in (1, 2, 3, 11, 39, 40, 41, 42, 43, 100, 333, 1200):
+        p = rng.random((T, r.n_outputs)).astype(np.float32) ** 8 + 1e-6
+        p /= p.sum(1, keepdims=True)
+        if T > 50:
+            p[T // 2, :] = 1.0 / r.n_outputs          # exact ties across all states
+            p[T // 3, 5] = 0.0                        # logf(0) = -inf
+        posts.append(p)
+    for wp in (None, 0.0, -10.0):
+        if wp is not None:
+            r.set_penalty(wp)
+        labs = r.decode(posts)
+        for p, l in zip(posts, labs):
+            assert labels_equal(l, o.decode(p, wp=wp)), (model, p.shape[0], wp)
+    r.set_penalty(o.wpenalty)
+
+
+def test_penalty_sweep_from_saved_posteriors(recs, oracle_models):
+    """BASELINE config 4: decode saved posteriors under 14 penalties in one call (-s post -p P)."""
+    model = "PHN_EN_TIMIT_LCRC_N500"
+    r, o = recs(model), oracle_models(model)
+    ref = ref_run(model, "test.raw")
+    post = np.ascontiguousarray(ref["post"])
+    pens = [-6.0 + 0.5 * i for i in range(13)] + [o.wpenalty]
+    out = r.decode([post, post[:100]], penalties=pens)
+    for k, wp in enumerate(pens):
+        assert labels_equal(out[k][0], o.decode(post, wp=wp)), wp
+        assert labels_equal(out[k][1], o.decode(post[:100], wp=wp)), wp
+    assert pb.format_rec(out[-1][0], r.phonemes) == str(ref["rec"])
+
+
+def test_synthetic_alaw_batch_matches_oracle(recs, oracle_models):
+    """BASELINE config 2 in miniature: synthetic 8 kHz A-law utterances generated on the device."""
+    r, o = recs("PHN_CZ_SPDAT_LCRC_N1500"), oracle_models("PHN_CZ_SPDAT_LCRC_N1500")
+    r.set_wave_format("alaw")
+    try:
+        audio = r.synth_audio(80000, 6, seed=1234)
+        assert audio.shape == (6, 80000) and len(np.unique(audio)) > 100
+        assert r.num_frames(80000) == 998
+        utts = [audio[i].tobytes() for i in range(6)]
+        labs = r.recognize(utts)
+        for u, l in zip(utts, labs):
+            want = o.recognize(u, fmt="alaw")
+            assert labels_equal(l, want)
+            assert len(l) > 20
+        again = r.synth_audio(80000, 6, seed=1234)
+        assert np.array_equal(audio, again)
+    finally:
+        r.set_wave_format("lin16")
+
+
+def test_batch_equals_singletons_and_is_order_independent(recs):
+    """Size-independent property: utterances are independent, so batching must not change results."""
+    r = recs("PHN_CZ_SPDAT_LCRC_N1500")
+    base = audio_bytes("test.raw")
+    utts = [base[:30000], base[30000:90000], base[:2000], base]
+    together = r.recognize(utts)
+    rev = r.recognize(utts[::-1])[::-1]
+    for u, a, b in zip(utts, together, rev):
+        c = r.recognize([u])[0]
+        assert labels_equal(a, c) and labels_equal(b, c)
+
+
+def test_online_norm_arithmetic(recs, orc):
+    r = recs("PHN_CZ_SPDAT_LCRC_N1500")
+    x = np.random.default_rng(2).standard_normal((300, 15)).astype(np.float32) * 3 + 11
+    for mn, vn in ((True, False), (True, True), (False, True)):
+        want = x.copy()
+        orc.lib().orc_online_norm(want, 300, 15, 100, int(mn), int(vn))
+        assert_bits_equal(r.online_norm(x, 100, mn, vn), want, f"online norm {mn} {vn}")
+
+
+def test_capacity_error_reports_needed_size(recs):
+    import ctypes as C
+    r = recs("PHN_CZ_SPDAT_LCRC_N1500")
+    a = np.frombuffer(audio_bytes("test.raw"), dtype=np.uint8)
+    boff = np.array([0, a.size], dtype=np.int64)
+    labels = np.zeros(2, dtype=pb.LABEL_DTYPE)
+    loff = np.zeros(2, dtype=np.int64)
+    rc = r._L.phn_recognize(r._h, a.ctypes.data, boff, 1, labels.ctypes.data, 2, loff, None)
+    assert rc == 32 and loff[1] == 50
