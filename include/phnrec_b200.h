@@ -84,6 +84,9 @@ void phn_destroy(phn_ctx *ctx);
 const char *phn_last_error(const phn_ctx *ctx);
 int phn_get_info(const phn_ctx *ctx, phn_info *info);
 const char *phn_phoneme(const phn_ctx *ctx, int index); /* PhnDec::LoadPhnList, phndec.cpp:305 */
+/* Config::GetString (configz.h:87-102) after the $C / $T substitution of srec.cpp:219-233;
+ * NULL for a variable the table does not know. */
+const char *phn_config_get(const phn_ctx *ctx, const char *section, const char *variable);
 
 /* -- knobs ------------------------------------------------------------------------- */
 int phn_set_penalty(phn_ctx *ctx, float wpenalty);   /* Decoder::SetWPenalty, decoder.h:70 / phnrec.cpp:212-221 */

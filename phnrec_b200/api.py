@@ -60,6 +60,7 @@ _SYMS = [
     ("phn_last_error", C.c_char_p, [C.c_void_p]),
     ("phn_get_info", C.c_int, [C.c_void_p, C.POINTER(_Info)]),
     ("phn_phoneme", C.c_char_p, [C.c_void_p, C.c_int]),
+    ("phn_config_get", C.c_char_p, [C.c_void_p, C.c_char_p, C.c_char_p]),
     ("phn_set_penalty", C.c_int, [C.c_void_p, C.c_float]),
     ("phn_set_wave_format", C.c_int, [C.c_void_p, C.c_int]),
     ("phn_set_mlp_mode", C.c_int, [C.c_void_p, C.c_int]),
@@ -145,6 +146,10 @@ class Recognizer:
     def _ck(self, rc: int):
         if rc:
             raise PhnRecError(rc, (self._L.phn_last_error(self._h) or b"").decode())
+
+    def config(self, section: str, variable: str):
+        v = self._L.phn_config_get(self._h, section.encode(), variable.encode())
+        return None if v is None else v.decode()
 
     # -- knobs (Decoder::SetWPenalty, SpeechRec::SetWaveFormat)
     def set_penalty(self, wp: float):

@@ -186,10 +186,9 @@ static int run_posteriors(phn_ctx *c)
 
 static int run_decode(phn_ctx *c, const float *penalties, int n_pen)
 {
-    std::vector<float> pen(n_pen);
-    for (int k = 0; k < n_pen; ++k) pen[k] = penalties ? penalties[k] : c->wpenalty;
-    PHN_CUDA(c, cudaMemcpyAsync(c->d_pen.p, pen.data(), sizeof(float) * n_pen, cudaMemcpyHostToDevice, c->stream));
-    PHN_CUDA(c, cudaStreamSynchronize(c->stream));  // `pen` is a pageable temporary
+    c->h_pen.resize(n_pen);  // member: stays alive until the (staged) copy has been consumed
+    for (int k = 0; k < n_pen; ++k) c->h_pen[k] = penalties ? penalties[k] : c->wpenalty;
+    PHN_CUDA(c, cudaMemcpyAsync(c->d_pen.p, c->h_pen.data(), sizeof(float) * n_pen, cudaMemcpyHostToDevice, c->stream));
     StageTimer t(c, PHN_K_VIT);
     return launch_viterbi(c, (const float *)c->d_pen.p, n_pen);
 }
@@ -236,6 +235,22 @@ int phn_create(const char *cfg_dir, int device, phn_ctx **out)
         }
         return bail(rc);
     }
+    {   // SubstVars (srec.cpp:219-233): $C = config dir, $T = tmp dir, for the path-like variables
+        auto subst = [&](const char *sec, const char *var, const std::string &tdir) {
+            std::string &v = c->cfg.kv[std::string(sec) + "/" + var];
+            size_t p;
+            while ((p = v.find("$C")) != std::string::npos) v.replace(p, 2, c->cfg_dir);
+            while ((p = v.find("$T")) != std::string::npos) v.replace(p, 2, tdir);
+        };
+        subst("dirs", "tmp", "");
+        const std::string tdir = c->cfg.str("dirs", "tmp");
+        const char *paths[][2] = {{"models", "hmm_defs"}, {"dicts", "phoneme_list"}, {"networks", "default"},
+                                  {"dicts", "lexicon1"}, {"dicts", "lexicon2"}, {"dicts", "keyword_list"},
+                                  {"kws", "thresholds_file"}, {"gptransc", "rules"}, {"gptransc", "symbols"},
+                                  {"onlinenorm", "file"}};
+        for (auto &pv : paths) subst(pv[0], pv[1], tdir);
+        mkdir(tdir.c_str(), 0777);  // attempted, failure ignored (srec.cpp:270-279)
+    }
     const Config &C = c->cfg;
     // ---- what this hot path implements: fbanks -> LCRC -> phndec, offline
     if (C.str("params", "kind") != "fbanks") return bail(fail(c, PHN_ERR_UNSUPPORTED, "Unsupported parameter kind: %s\n", C.str("params", "kind").c_str()));
@@ -271,12 +286,6 @@ int phn_create(const char *cfg_dir, int device, phn_ctx **out)
     c->S = 3;
     if (c->nbanks < 1 || c->nbanks > 32 || c->vs < 2 || c->vs > 4096 || c->step < 1 || c->hist < 1)
         return bail(fail(c, PHN_ERR_CFG_BADVAL, "Front-end sizes out of range in '%s'\n", cfg_file.c_str()));
-    {   // mkdir <tmp> is attempted and its failure ignored, as in srec.cpp:270-279
-        std::string tmp = C.str("dirs", "tmp");
-        size_t p = tmp.find("$C");
-        if (p != std::string::npos) tmp.replace(p, 2, c->cfg_dir);
-        mkdir(tmp.c_str(), 0777);
-    }
     // ---- nets (traps.cpp:139-166: .nbin tried first; it is the only weight source we read)
     const char *names[3] = {"band0", "band1", "merger"};
     for (int i = 0; i < 3; ++i) {
@@ -298,10 +307,7 @@ int phn_create(const char *cfg_dir, int device, phn_ctx **out)
         fclose(f);
     }
     {   // phoneme list (phndec.cpp:305-350); $C substitution as srec.cpp:219-233
-        std::string p = C.str("dicts", "phoneme_list");
-        if (p.empty()) p = "$C/dicts/phonemes";
-        size_t q = p.find("$C");
-        if (q != std::string::npos) p.replace(q, 2, c->cfg_dir);
+        const std::string p = C.str("dicts", "phoneme_list");
         FILE *f = fopen(p.c_str(), "r");
         if (!f) return bail(fail(c, PHN_ERR_DEC_INPUT, "Can not open the phoneme list: %s\n", p.c_str()));
         char buf[256];
@@ -398,6 +404,13 @@ int phn_get_info(const phn_ctx *c, phn_info *o)
 }
 
 const char *phn_phoneme(const phn_ctx *c, int i) { return (c && i >= 0 && i < c->P) ? c->phonemes[i].c_str() : nullptr; }
+
+const char *phn_config_get(const phn_ctx *c, const char *sec, const char *var)
+{
+    if (!c || !sec || !var) return nullptr;
+    auto it = c->cfg.kv.find(std::string(sec) + "/" + var);
+    return it == c->cfg.kv.end() ? nullptr : it->second.c_str();
+}
 
 int phn_set_penalty(phn_ctx *c, float wp)
 {

@@ -1,0 +1,420 @@
+// cli_phnrec.cpp — the `phnrec` command, drop-in for the reference CLI on the offline path.
+//
+// Same switches, same config/model directory, same output files (HTK .rec / MLF labels, HTK
+// parameter and posterior matrices) as phnrec.cpp:113-299 + SpeechRec::ProcessFile*
+// (srec.cpp:1113-1291); the work itself is done by libphnrec_b200 through its C ABI, batching
+// the lines of a file list into ragged GPU batches.  `-a` (live soundcard input) is outside the
+// hot path and reports an error.
+#include <cctype>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "phnrec_b200.h"
+
+namespace {
+
+enum DataFmt { dfWaveform = 0, dfParams = 1, dfPosteriors = 2, dfStrings = 3, dfUnknown = 4 };  // srec.h order
+
+bool g_verbose = false;
+
+[[noreturn]] void die(const char *fmt, ...) __attribute__((format(printf, 1, 2)));
+void die(const char *fmt, ...)
+{
+    // SpeechRec::MError (srec.cpp:118-122): "ERROR: <msg>" on stderr, exit(1)
+    va_list ap;
+    va_start(ap, fmt);
+    fputs("ERROR: ", stderr);
+    vfprintf(stderr, fmt, ap);
+    va_end(ap);
+    exit(1);
+}
+
+void logmsg(const char *fmt, ...) __attribute__((format(printf, 1, 2)));
+void logmsg(const char *fmt, ...)
+{
+    if (!g_verbose) return;
+    va_list ap;
+    va_start(ap, fmt);
+    vfprintf(stdout, fmt, ap);
+    va_end(ap);
+}
+
+void help()
+{
+    puts("\nUSAGE: phnrec [options]\n");
+    puts(" -c dir             configuration directory");
+    puts(" -l file            list of files");
+    puts(" -i file            input file");
+    puts(" -o file            output file");
+    puts(" -m file            output MLF");
+    puts(" -a                 live audio input");
+    puts(" -s fmt [waveform]  source format (wf-waveform, par-parameters, post-posteriors)");
+    puts(" -t fmt [strings]   target format (par-parameters, post-posteriors, str-strings)");
+    puts(" -w fmt [lin16]     waveform format (lin16, alaw)");
+    puts(" -f fmt [str]       live output format (str, strlen, lab)");
+    puts(" -p num [-3.8]      phoneme insertion penalty");
+    puts(" -v                 verbose\n");
+}
+
+DataFmt str2fmt(const char *s)
+{
+    if (!strcmp(s, "wf")) return dfWaveform;
+    if (!strcmp(s, "par")) return dfParams;
+    if (!strcmp(s, "post")) return dfPosteriors;
+    if (!strcmp(s, "str")) return dfStrings;
+    die("Invalid data format '%s'. Supported data formats are 'wf', 'mb', 'post' and 'str'.\n", s);
+}
+
+// ---- file-name helpers with the reference's rules (filename.cpp:30-114)
+size_t last_sep(const std::string &s)
+{
+    size_t a = s.rfind('/'), b = s.rfind('\\');
+    if (a == std::string::npos) return b;
+    if (b == std::string::npos) return a;
+    return a > b ? a : b;
+}
+std::string change_suffix(std::string f, const std::string &suf)
+{
+    size_t dot = f.rfind('.'), sep = last_sep(f);
+    if (dot == std::string::npos || (sep != std::string::npos && sep > dot)) return f + "." + suf;
+    return f.substr(0, dot + 1) + suf;
+}
+std::string change_path(const std::string &f, const std::string &path)
+{
+    size_t sep = last_sep(f);
+    if (sep == std::string::npos) return f;  // only when the name has a directory
+    return path + f.substr(sep);
+}
+
+// ---- HTK parameter files (Mat::saveHTK / loadHTK, matrix.h:2506-2573)
+uint32_t bswap32(uint32_t v) { return __builtin_bswap32(v); }
+bool load_htk(const std::string &path, std::vector<float> &m, int &rows, int &cols)
+{
+    FILE *f = fopen(path.c_str(), "rb");
+    if (!f) return false;
+    unsigned char h[12];
+    if (fread(h, 1, 12, f) != 12) { fclose(f); return false; }
+    rows = (int)((uint32_t)h[0] << 24 | (uint32_t)h[1] << 16 | (uint32_t)h[2] << 8 | h[3]);
+    const int samp_size = (int)((uint32_t)h[8] << 8 | h[9]);
+    cols = samp_size / 4;
+    if (rows < 0 || cols <= 0) { fclose(f); return false; }
+    m.resize((size_t)rows * cols);
+    const size_t n = fread(m.data(), 4, m.size(), f);
+    fclose(f);
+    if (n != m.size()) return false;
+    uint32_t *u = reinterpret_cast<uint32_t *>(m.data());
+    for (size_t i = 0; i < m.size(); ++i) u[i] = bswap32(u[i]);
+    return true;
+}
+bool save_htk(const std::string &path, const float *m, int rows, int cols)
+{
+    FILE *f = fopen(path.c_str(), "wb");
+    if (!f) return false;
+    const uint32_t period = 100000;
+    const uint16_t size = (uint16_t)(cols * 4), kind = 6;
+    unsigned char h[12] = {(unsigned char)(rows >> 24), (unsigned char)(rows >> 16), (unsigned char)(rows >> 8), (unsigned char)rows,
+                           (unsigned char)(period >> 24), (unsigned char)(period >> 16), (unsigned char)(period >> 8), (unsigned char)period,
+                           (unsigned char)(size >> 8), (unsigned char)size, (unsigned char)(kind >> 8), (unsigned char)kind};
+    bool ok = fwrite(h, 1, 12, f) == 12;
+    std::vector<uint32_t> be((size_t)rows * cols);
+    const uint32_t *u = reinterpret_cast<const uint32_t *>(m);
+    for (size_t i = 0; i < be.size(); ++i) be[i] = bswap32(u[i]);
+    ok = ok && fwrite(be.data(), 4, be.size(), f) == be.size();
+    fclose(f);
+    return ok;
+}
+
+bool load_bytes(const std::string &path, std::vector<unsigned char> &out)
+{
+    FILE *f = fopen(path.c_str(), "rb");
+    if (!f) return false;
+    fseek(f, 0, SEEK_END);
+    long n = ftell(f);
+    fseek(f, 0, SEEK_SET);
+    const size_t at = out.size();
+    out.resize(at + (size_t)n);
+    const bool ok = n == 0 || fread(out.data() + at, 1, (size_t)n, f) == (size_t)n;
+    fclose(f);
+    return ok;
+}
+
+struct Job { std::string src, dst; };
+
+struct Runner {
+    phn_ctx *ctx = nullptr;
+    phn_info info{};
+    DataFmt inf = dfWaveform, outf = dfStrings;
+    FILE *mlf = nullptr;
+
+    void ck(int rc) { if (rc) die("%s", phn_last_error(ctx)); }
+
+    // label writers: PhnDec's fprintf (phndec.cpp:230,292) and SpeechRec::OnWordMLF (srec.cpp:137-161)
+    void write_rec(FILE *f, const phn_label *l, int64_t n)
+    {
+        for (int64_t i = 0; i < n; ++i) fprintf(f, "%d00000 %d00000 %s %f\n", l[i].start, l[i].end, phn_phoneme(ctx, l[i].phn), l[i].like);
+    }
+    void write_mlf(const std::string &name, const phn_label *l, int64_t n)
+    {
+        fprintf(mlf, "\"%s\"\n", name.c_str());
+        for (int64_t i = 0; i < n; ++i) {
+            if (l[i].start == 0) fprintf(mlf, "0"); else fprintf(mlf, "%u00000", (unsigned)l[i].start);
+            if (l[i].end == 0) fprintf(mlf, " 0"); else fprintf(mlf, " %u00000", (unsigned)l[i].end);
+            fprintf(mlf, " %s %f\n", phn_phoneme(ctx, l[i].phn), l[i].like);
+        }
+        fprintf(mlf, ".\n");
+    }
+
+    // One ragged batch through the GPU.  `pending_error` (if any) is raised after the batch's
+    // outputs are written, like the reference stopping at the first bad list line.
+    void run(const std::vector<Job> &jobs, const std::string &pending_error)
+    {
+        const int n = (int)jobs.size();
+        std::vector<int64_t> off(n + 1, 0), foff(n + 1, 0);
+        std::vector<unsigned char> audio;
+        std::vector<float> mat;  // mel or posteriors, concatenated
+        std::string late_error = pending_error;
+        int good = n;
+        const int want_cols = inf == dfParams ? info.nbanks : info.n_outputs;
+        for (int i = 0; i < n; ++i) {
+            logmsg("%s -> %s\n", jobs[i].src.c_str(), jobs[i].dst.c_str());
+            if (inf == dfWaveform) {
+                if (!load_bytes(jobs[i].src, audio)) { late_error = "Can not open waveform file: " + jobs[i].src + "\n"; good = i; break; }
+                off[i + 1] = (int64_t)audio.size();
+            } else {
+                std::vector<float> m;
+                int rows, cols;
+                if (!load_htk(jobs[i].src, m, rows, cols)) { late_error = "Can not open file: " + jobs[i].src + "\n"; good = i; break; }
+                if (cols < want_cols) { late_error = "Invalid dimensionality of parameter vectors\n"; good = i; break; }
+                for (int r = 0; r < rows; ++r) mat.insert(mat.end(), m.begin() + (size_t)r * cols, m.begin() + (size_t)r * cols + want_cols);
+                foff[i + 1] = foff[i] + rows;  // extra columns are dropped (srec.cpp:983-997)
+            }
+        }
+        if (good > 0) process(jobs, good, audio, off, mat, foff);
+        if (!late_error.empty()) die("%s", late_error.c_str());
+    }
+
+    void process(const std::vector<Job> &jobs, int n, std::vector<unsigned char> &audio, std::vector<int64_t> &off,
+                 std::vector<float> &mat, std::vector<int64_t> &foff)
+    {
+        std::vector<float> mel, post;
+        if (inf == dfWaveform) {
+            if (outf == dfStrings) {  // the fused path: audio -> labels without leaving the GPU
+                ck(phn_mel(ctx, audio.data(), off.data(), n, nullptr, foff.data()));
+                const int64_t cap = phn_label_capacity(ctx, foff.data(), n);
+                std::vector<phn_label> lab((size_t)cap);
+                std::vector<int64_t> loff(n + 1);
+                ck(phn_recognize(ctx, audio.data(), off.data(), n, lab.data(), cap, loff.data(), nullptr));
+                emit_labels(jobs, n, lab, loff);
+                return;
+            }
+            ck(phn_mel(ctx, audio.data(), off.data(), n, nullptr, foff.data()));
+            mel.resize((size_t)foff[n] * info.nbanks);
+            ck(phn_mel(ctx, audio.data(), off.data(), n, mel.data(), foff.data()));
+            if (outf == dfParams) { emit_matrix(jobs, n, mel, foff, info.nbanks); return; }
+        } else if (inf == dfParams) {
+            mel.swap(mat);
+        } else {
+            post.swap(mat);
+        }
+        if (inf != dfPosteriors) {
+            post.resize((size_t)foff[n] * info.n_outputs);
+            ck(phn_posteriors(ctx, mel.data(), foff.data(), n, post.data()));
+            if (outf == dfPosteriors) { emit_matrix(jobs, n, post, foff, info.n_outputs); return; }
+        }
+        const int64_t cap = phn_label_capacity(ctx, foff.data(), n);
+        std::vector<phn_label> lab((size_t)cap);
+        std::vector<int64_t> loff(n + 1);
+        ck(phn_decode(ctx, post.data(), foff.data(), n, nullptr, 1, lab.data(), cap, loff.data()));
+        emit_labels(jobs, n, lab, loff);
+    }
+
+    void emit_labels(const std::vector<Job> &jobs, int n, const std::vector<phn_label> &lab, const std::vector<int64_t> &loff)
+    {
+        for (int i = 0; i < n; ++i) {
+            const phn_label *l = lab.data() + loff[i];
+            const int64_t cnt = loff[i + 1] - loff[i];
+            if (mlf) { write_mlf(jobs[i].dst, l, cnt); continue; }
+            if (jobs[i].dst.empty()) {  // no target: the decoder's default callback prints MLF-style lines to stdout
+                FILE *save = mlf; mlf = stdout;
+                for (int64_t k = 0; k < cnt; ++k) {
+                    if (l[k].start == 0) fprintf(mlf, "0"); else fprintf(mlf, "%u00000", (unsigned)l[k].start);
+                    if (l[k].end == 0) fprintf(mlf, " 0"); else fprintf(mlf, " %u00000", (unsigned)l[k].end);
+                    fprintf(mlf, " %s %f\n", phn_phoneme(ctx, l[k].phn), l[k].like);
+                }
+                mlf = save;
+                continue;
+            }
+            FILE *f = fopen(jobs[i].dst.c_str(), "w");
+            if (!f) die("Can not create the label file: %s\n", jobs[i].dst.c_str());
+            write_rec(f, l, cnt);
+            fclose(f);
+        }
+    }
+
+    void emit_matrix(const std::vector<Job> &jobs, int n, const std::vector<float> &m, const std::vector<int64_t> &foff, int cols)
+    {
+        for (int i = 0; i < n; ++i)
+            if (!save_htk(jobs[i].dst, m.data() + (size_t)foff[i] * cols, (int)(foff[i + 1] - foff[i]), cols))
+                die("Can not create file: %s\n", jobs[i].dst.c_str());
+    }
+};
+
+}  // namespace
+
+
+int main(int argc, char *argv[])
+{
+    const char *config_dir = nullptr, *file_list = nullptr, *input_file = nullptr, *output_file = nullptr;
+    const char *output_mlf = nullptr, *wpenalty = nullptr, *wformat = nullptr;
+    bool live = false;
+    int mlp_mode = PHN_MLP_EXACT_FP32;
+    Runner R;
+
+    if (argc == 1) { help(); return 1; }
+    // the reference's bundled getopt (getopt.cpp:21-41): "-x val" or "-xval", the next argv is
+    // taken verbatim as the argument (so "-p -3.0" works), bare words are ignored
+    const char *opts = "-c:l:i:o:m:as:t:w:f:p:v";
+    for (int i = 1; i < argc; ++i) {
+        const char *a = argv[i];
+        if (!(a[0] == '-' && isalpha((unsigned char)a[1]))) continue;
+        const char *o = strchr(opts, a[1]);
+        if (!o) { fprintf(stderr, "ERROR: Error during command line parsing\n"); return 1; }
+        const char *arg = nullptr;
+        if (o[1] == ':') {
+            if (a[2]) arg = a + 2;
+            else if (++i == argc) { fprintf(stderr, "ERROR: Error during command line parsing\n"); return 1; }
+            else arg = argv[i];
+        }
+        switch (a[1]) {
+            case 'c': config_dir = arg; break;
+            case 'l': file_list = arg; break;
+            case 'i': input_file = arg; break;
+            case 'o': output_file = arg; break;
+            case 'm': output_mlf = arg; break;
+            case 'a': live = true; break;
+            case 's': R.inf = str2fmt(arg); break;
+            case 't': R.outf = str2fmt(arg); break;
+            case 'w':
+                if (strcmp(arg, "lin16") && strcmp(arg, "alaw"))
+                    die("Invalid waveform format '%s'. Supported data formats are 'lin16' and 'alaw'.\n", arg);
+                wformat = arg;
+                break;
+            case 'p': wpenalty = arg; break;
+            case 'f':
+                if (strcmp(arg, "lab") && strcmp(arg, "str") && strcmp(arg, "strlen")) {
+                    fprintf(stderr, "ERROR: Invalid output format: %s. (can be 'lab', 'str', 'strlen')\n", arg);
+                    return 1;
+                }
+                break;
+            case 'v': g_verbose = true; break;
+        }
+    }
+    // PHNREC_MLP=tc selects the tensor-core posterior estimator (not a reference switch)
+    if (const char *e = getenv("PHNREC_MLP")) mlp_mode = !strcmp(e, "tc") ? PHN_MLP_TC_F16 : PHN_MLP_EXACT_FP32;
+    int device = 0;
+    if (const char *e = getenv("PHNREC_DEVICE")) device = atoi(e);
+
+    if (!config_dir) { fprintf(stderr, "ERROR: Configuration directory is not set (-c)\n"); return 1; }
+    logmsg("\nSystem initialization\n");
+    if (phn_create(config_dir, device, &R.ctx)) die("%s", phn_last_error(nullptr));
+    phn_get_info(R.ctx, &R.info);
+    logmsg("  - mel-banks ...\n  - online normalization ...\n  - posteriors (loading NNs) ...\n  - decoder ...\n\n");
+    logmsg("------------------- SUMMARY -------------------\n");
+    logmsg("Dictionary:   %s\n", phn_config_get(R.ctx, "dicts", "phoneme_list"));
+    logmsg("Network file: %s\n", phn_config_get(R.ctx, "networks", "default"));
+    logmsg("HMM file:     %s\n", phn_config_get(R.ctx, "models", "hmm_defs"));
+    logmsg("#States/Phn:  %d\n", atoi(phn_config_get(R.ctx, "models", "nstates")));
+    logmsg("Time pruning: %d\n", R.info.time_pruning);
+    logmsg("Word penalty: %f\n", R.info.wpenalty);
+    logmsg("Soft func:    %s\n", phn_config_get(R.ctx, "decoder", "softening_func"));
+    logmsg("-----------------------------------------------\n\n");
+    R.ck(phn_set_mlp_mode(R.ctx, mlp_mode));
+
+    if (wpenalty) {
+        float v;
+        if (sscanf(wpenalty, "%f", &v) != 1) {
+            fprintf(stderr, "ERROR: Invalid argument for -p switch at command line: %s\n", wpenalty);
+            return 1;
+        }
+        phn_set_penalty(R.ctx, v);
+    }
+    if (wformat) phn_set_wave_format(R.ctx, !strcmp(wformat, "alaw") ? PHN_WAVE_ALAW : PHN_WAVE_LIN16);
+    if (output_file && !input_file) { fprintf(stderr, "ERROR: The input file is not specified (-i)\n"); return 1; }
+    if (!((int)R.outf > (int)R.inf)) { fprintf(stderr, "ERROR: Unsupported data conversion (-s, -t)\n"); return 1; }
+
+    const std::string params_suffix = phn_config_get(R.ctx, "params", "suffix");
+    const std::string labels_suffix = phn_config_get(R.ctx, "labels", "suffix");
+    const bool remove_path = !strcmp(phn_config_get(R.ctx, "labels", "remove_path"), "true");
+
+    // one list line -> a job (SpeechRec::ProcessFileListLine, srec.cpp:1201-1244)
+    auto parse_line = [&](const char *line, bool in_mlf, Job &job, std::string &err) {
+        char f1[1024], sep[256], f2[1024];
+        if (sscanf(line, "%1023[^ \n\r\t]%255[ \t]%1023[^ \n\r\t]", f1, sep, f2) == 3) { job.src = f1; job.dst = f2; return true; }
+        if (sscanf(line, "%1023s", f1) != 1) { err = std::string("Invalid line in file list: ") + line + "\n"; return false; }
+        job.src = f1;
+        switch (R.outf) {
+            case dfParams: job.dst = change_suffix(f1, params_suffix); break;
+            case dfPosteriors:
+                // the reference asks for the unknown variable traps/suffix here and aborts (srec.cpp:1224)
+                err = "Posterior output needs an explicit target file ('source target' list lines or -i/-o)\n";
+                return false;
+            case dfStrings:
+                if (in_mlf) {  // CreateLabelFileNameForMLF, srec.cpp:1424-1436
+                    std::string s = f1;
+                    for (char &ch : s) if (ch == '\\') ch = '/';
+                    s = change_suffix(s, labels_suffix);
+                    job.dst = remove_path ? change_path(s, "*") : s;
+                } else {
+                    job.dst = change_suffix(f1, labels_suffix);
+                }
+                break;
+            default: job.dst = f1; break;
+        }
+        return true;
+    };
+
+    if (input_file) {  // -i [-o]: phnrec.cpp:241-252
+        std::string line = input_file;
+        if (output_file) line += std::string(" ") + output_file;
+        Job j;
+        std::string err;
+        if (!parse_line(line.c_str(), false, j, err)) die("%s", err.c_str());
+        R.run({j}, "");
+    }
+
+    if (file_list) {  // SpeechRec::ProcessFileList, srec.cpp:1246-1291
+        FILE *fl = fopen(file_list, "r");
+        if (!fl) die("Can not open the file list: %s\n", file_list);
+        if (output_mlf) {
+            R.mlf = fopen(output_mlf, "w");
+            if (!R.mlf) die("Can not create the MLF: %s\n", output_mlf);
+            fprintf(R.mlf, "#!MLF!#\n");
+        }
+        size_t max_batch = 2048;
+        if (const char *e = getenv("PHNREC_BATCH")) max_batch = (size_t)atol(e) > 0 ? (size_t)atol(e) : max_batch;
+        std::vector<Job> batch;
+        char line[1024];
+        std::string err;
+        while (fgets(line, 1023, fl)) {
+            Job j;
+            if (!parse_line(line, R.mlf != nullptr, j, err)) break;
+            batch.push_back(j);
+            if (batch.size() >= max_batch) { R.run(batch, ""); batch.clear(); }
+        }
+        if (!batch.empty() || !err.empty()) {
+            if (!batch.empty()) R.run(batch, err);
+            else die("%s", err.c_str());
+        }
+        if (R.mlf) fclose(R.mlf);
+        fclose(fl);
+    }
+
+    if (live) die("Live audio input (-a) is outside the GPU hot path of this build\n");
+    phn_destroy(R.ctx);
+    return 0;
+}

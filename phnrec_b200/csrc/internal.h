@@ -89,6 +89,7 @@ struct phn_ctx {
     Buf d_x0, d_x1, d_h, d_xm, d_x0h, d_x1h, d_xmh;  // MLP workspace (per frame chunk)
     Buf d_tile_ctr, d_coff, d_labels_c;
     std::vector<int32_t> h_nlab;
+    std::vector<float> h_pen;
     int64_t chunk_frames = 0;
     // profiling
     int profiling = 0;
