@@ -377,6 +377,7 @@ void phn_destroy(phn_ctx *c)
                             &c->d_x0h, &c->d_x1h, &c->d_xmh, &c->d_tile_ctr, &c->d_coff, &c->d_labels_c};
     for (auto *b : bufs)
         if (b->p) cudaFree(b->p);
+    mlp_tc_release(c);
     for (int i = 0; i < 3; ++i) {
         DevNet &d = c->net[i];
         void *ps[] = {d.w1, d.w2, d.b1, d.b2, d.mean, d.dev, d.w1h, d.w2h};

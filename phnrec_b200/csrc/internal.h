@@ -71,6 +71,7 @@ struct phn_ctx {
     int sent_mean_norm = 0, z_mean = 0;
     float lo = 0, hi = 4000, preem = 0, wpenalty = -2.f, frame_shift = 0.f, frame_floor = -9999.9f, scale = 1.f, dc_shift = 0.f;
     int mlp_mode = PHN_MLP_EXACT_FP32;
+    void *tc = nullptr;  // tensor-core mode state (k_mlp_tc.cu)
     std::vector<std::string> phonemes;
     float win[32];
     phn::HostNet hnet[3];
@@ -121,5 +122,6 @@ int launch_mlp_tc(phn_ctx *c, int64_t f0, int64_t nf);                     // k_
 int launch_viterbi(phn_ctx *c, const float *d_pen, int n_pen);             // k_vit.cu
 int launch_compact_labels(phn_ctx *c, int nseg);                           // k_vit.cu
 int launch_synth(phn_ctx *c, void *d_audio, int64_t bytes_per_utt, int n_utt, uint64_t seed);  // k_synth.cu
-int mlp_tc_prepare(phn_ctx *c);                                            // fp16 weight images + tensor maps
+int mlp_tc_prepare(phn_ctx *c);                                            // fp16 weight images (k_mlp_tc.cu)
+void mlp_tc_release(phn_ctx *c);
 }  // namespace phn

@@ -1,6 +1,577 @@
-// k_mlp_tc.cu — placeholder until the tcgen05 kernels land (next commit).
+// k_mlp_tc.cu — K-mlp, tensor-core mode: one fused kernel per net,
+//     P = fsoftmax(b2 + fsig(b1 + X W1^T) W2^T)
+// on the 5th-generation tensor cores (tcgen05.mma, fp16 operands, fp32 accumulators in TMEM),
+// operands streamed into shared memory by the TMA engine (cp.async.bulk + mbarrier), the hidden
+// layer never leaving the SM.  Replaces NeuralNet::Forward (nn.cpp:872-950), fexp_sigmoid /
+// fexp_softmax_v (fexp.h:33-78) and Traps::CalcInputFeaturesForMerger (traps.cpp:435-461) in
+// reduced precision; the measured deviation from the exact mode is stated in DESIGN.md.
+//
+// Tiling: a CTA owns 128 frames (UMMA M = 128, cta_group::1) and walks the hidden layer in
+// chunks of 128 units:
+//     G1(c): D1[c&1] (TMEM, 128 cols)  = X[128 x K1] . W1[c]^T          K1/16 MMAs of 128x128x16
+//     E1(c): H = fp16(fsig(D1 + b1))  -> shared memory (K-major, 128B swizzle)     8 epilogue warps
+//     G2(c): D2 (TMEM, N2P cols)     += H[128 x 128] . W2[:, c]^T       8 MMAs of 128xN2Px16
+//     E2   : softmax over D2 + b2, then posteriors (merger) or ln + merger input norm (band nets)
+// Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer + TMEM allocator, warps 2..9 = epilogue
+// (two warps per TMEM lane quarter, each taking half of the columns).
+//
+// All operands live in global memory as ready-made shared-memory images: 16 KB blocks of
+// [128 rows x 64 fp16] in the canonical K-major SWIZZLE_128B layout (16-byte chunk index XOR
+// row%8), so one 1-D bulk copy lands a block exactly as the UMMA descriptor expects it.  The
+// weight images are built once (mlp_tc_prepare); K-stc and the band nets' E2 write activations
+// straight into that layout.
 #include "internal.h"
+#include "device_math.cuh"
+
+#include <cfloat>
+
 namespace phn {
-int mlp_tc_prepare(phn_ctx *c) { return fail(c, PHN_ERR_UNSUPPORTED, "tensor-core MLP mode not built\n"); }
-int launch_mlp_tc(phn_ctx *c, int64_t, int64_t) { return fail(c, PHN_ERR_UNSUPPORTED, "tensor-core MLP mode not built\n"); }
+
+// ------------------------------------------------------------------------------------------------
+// layout helpers (shared by host-side image builders and device writers)
+// ------------------------------------------------------------------------------------------------
+constexpr int TC_M = 128;          // frames per tile
+constexpr int TC_NC = 128;         // hidden units per chunk
+constexpr int TC_KB = 64;          // fp16 elements per 128-byte swizzle row
+constexpr int TC_BLK = 128 * 128;  // bytes of one [128 rows x 64 fp16] block
+
+// byte offset of element (row r < rows, column cc < 64) inside a K-major SW128 block
+__host__ __device__ __forceinline__ uint32_t sw128_off(int r, int cc)
+{
+    return (uint32_t)r * 128u + ((((uint32_t)cc >> 3) ^ ((uint32_t)r & 7u)) << 4) + ((uint32_t)cc & 7u) * 2u;
+}
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "W_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra D_%=;\n\t"
+        "bra W_%=;\n\t"
+        "D_%=:\n\t}"
+        ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t *bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// D[tmem] (+)= A[smem] . B[smem]^T   (both operands K-major)
+__device__ __forceinline__ void umma_f16_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// K-major, SWIZZLE_128B shared-memory matrix descriptor: start address, LBO (unused for swizzled
+// K-major) = 1, SBO = 1024 B between 8-row groups, descriptor version 1 (sm_100), layout type 2.
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t saddr)
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024u >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// instruction descriptor: fp16 x fp16 -> fp32, both K-major, M = 128, N = n
+__host__ __device__ constexpr uint32_t make_idesc(int n)
+{
+    return (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t *v)
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ float rcp_approx(float x)
+{
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ uint32_t pack_half2(float lo, float hi)
+{
+    uint32_t r;
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+// The Quicknet bit-trick exponential in single precision: D(y) ~ float whose bit pattern is
+// trunc(2^23/ln2 * y) + (127*2^23 - 60801*8)  (fexp.h:14-21 scaled from the double's 20-bit to the
+// float's 23-bit mantissa field).  v = A32*y + C32 is formed by one FFMA by the callers.
+constexpr float kA32 = 12102203.161561485f;   // 2^23 / ln 2
+constexpr float kC32 = 1064866808.0f;         // 127 * 2^23 - 60801 * 8
+constexpr float kVmin = 12000000.0f, kVmax = 2118000000.0f;
+__device__ __forceinline__ float fexp_bits(float v)
+{
+    v = fminf(fmaxf(v, kVmin), kVmax);
+    return __int_as_float(__float2int_rz(v));
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernel
+// ------------------------------------------------------------------------------------------------
+struct TcArgs {
+    const uint8_t *x_img;     // [tiles][KB1][16 KB]  activations, SW128 blocks
+    const uint8_t *w1_img;    // [NCH][KB1][16 KB]
+    const uint8_t *w2_img;    // [NCH][2][N2P*128 B]
+    const float *sig_k;       // [NCH*128]  per hidden unit: C32 - A32*b1   (0-weight padding units give fsig(0)*0)
+    const float *b2;          // [N2P]
+    int n_tiles, KB1, NCH, S1;
+    int nks_last;             // k-steps (of 16) actually needed in the last k-block of layer 1
+    int64_t nf;               // frames in this launch
+    int nout;
+    // outputs
+    float *post; int ldpost;                          // merger: posteriors [nf][nout]
+    uint8_t *xm_img; int xm_kb1; int xm_col0;         // band nets: merger input image
+    const float *mmean, *mdev;
+};
+
+template <int N2P>
+__global__ void __launch_bounds__(320, 1) k_mlp_tc(TcArgs a)
+{
+    constexpr int W2_BLK = N2P * 128;       // bytes of one [N2P rows x 64 fp16] block
+    constexpr int NH8 = N2P / 16;           // 8-column groups per column half of D2
+    extern __shared__ uint8_t smem_raw[];
+    // carve-up (all block bases 1024-byte aligned: the swizzle pattern is a function of the address)
+    uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t *sX = smem;                                        // KB1 x 16 KB
+    uint8_t *sW1 = sX + (size_t)a.KB1 * TC_BLK;                // S1 x 16 KB ring
+    uint8_t *sW2 = sW1 + (size_t)a.S1 * TC_BLK;                // 2 x W2_BLK
+    uint8_t *sH = sW2 + 2 * W2_BLK;                            // 2 x 16 KB
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sH + 2 * TC_BLK);
+    uint64_t *x_full = bars;                 // [8]
+    uint64_t *x_empty = bars + 8;            // [1]
+    uint64_t *w1_full = bars + 9;            // [8]
+    uint64_t *w1_empty = bars + 17;          // [8]
+    uint64_t *w2_full = bars + 25, *w2_empty = bars + 26;
+    uint64_t *d1_full = bars + 27;           // [2]
+    uint64_t *d1_empty = bars + 29;          // [2]
+    uint64_t *h_full = bars + 31, *h_empty = bars + 32;
+    uint64_t *d2_full = bars + 33, *d2_empty = bars + 34;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 35);
+    float *s_red = reinterpret_cast<float *>(bars + 36);       // [2][2][128] row max / row sum exchange
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 8; ++i) { mbar_init(&x_full[i], 1); mbar_init(&w1_full[i], 1); mbar_init(&w1_empty[i], 1); }
+        mbar_init(x_empty, 1);
+        mbar_init(w2_full, 1); mbar_init(w2_empty, 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(&d1_full[i], 1); mbar_init(&d1_empty[i], 8); }
+        mbar_init(h_full, 8); mbar_init(h_empty, 1);
+        mbar_init(d2_full, 1); mbar_init(d2_empty, 8);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {  // TMEM: 512 columns (D1 double buffer 2 x 128, D2 up to 192)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t tD1[2] = {tmem, tmem + 128u};
+    const uint32_t tD2 = tmem + 256u;
+
+    if (warp == 0) {
+        // ===================================================================== TMA producer
+        if (lane == 0) {
+            uint32_t ph_x_empty = 0, ph_w2_empty = 0, w1_stage = 0, ph_w1 = 0;
+            bool first_tile = true, first_w2 = true;
+            auto load_w1 = [&](int c) {
+                for (int kb = 0; kb < a.KB1; ++kb) {
+                    mbar_wait(&w1_empty[w1_stage], ph_w1 ^ 1);
+                    mbar_expect_tx(&w1_full[w1_stage], TC_BLK);
+                    tma_load_1d(sW1 + (size_t)w1_stage * TC_BLK, a.w1_img + ((size_t)c * a.KB1 + kb) * TC_BLK, TC_BLK, &w1_full[w1_stage]);
+                    if (++w1_stage == (uint32_t)a.S1) { w1_stage = 0; ph_w1 ^= 1; }
+                }
+            };
+            for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+                // later tiles: the first weight chunk is prefetched while the previous tile still owns X
+                if (!first_tile) { load_w1(0); mbar_wait(x_empty, ph_x_empty); ph_x_empty ^= 1; }
+                for (int kb = 0; kb < a.KB1; ++kb) {
+                    mbar_expect_tx(&x_full[kb], TC_BLK);
+                    tma_load_1d(sX + (size_t)kb * TC_BLK, a.x_img + ((size_t)tile * a.KB1 + kb) * TC_BLK, TC_BLK, &x_full[kb]);
+                }
+                if (first_tile) load_w1(0);
+                first_tile = false;
+                for (int c = 0; c < a.NCH; ++c) {
+                    if (c + 1 < a.NCH) load_w1(c + 1);
+                    if (!first_w2) { mbar_wait(w2_empty, ph_w2_empty); ph_w2_empty ^= 1; }
+                    first_w2 = false;
+                    mbar_expect_tx(w2_full, 2 * W2_BLK);
+                    tma_load_1d(sW2, a.w2_img + (size_t)c * 2 * W2_BLK, 2 * W2_BLK, w2_full);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================================================================== MMA issuer
+        if (lane == 0) {
+            const uint32_t idesc1 = make_idesc(TC_NC), idesc2 = make_idesc(N2P);
+            uint32_t ph_x_full = 0, w1_stage = 0, ph_w1 = 0, ph_w2_full = 0, ph_h_full = 0, ph_d2_empty = 0;
+            uint32_t ph_d1_empty[2] = {0, 0};
+            uint32_t n_d1_use[2] = {0, 0};
+            bool first_d2 = true;
+            const uint32_t sX_a = smem_u32(sX), sW1_a = smem_u32(sW1), sW2_a = smem_u32(sW2), sH_a = smem_u32(sH);
+            for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+                auto g1 = [&](int c) {
+                    const int b = c & 1;
+                    if (n_d1_use[b] > 0) { mbar_wait(&d1_empty[b], ph_d1_empty[b]); ph_d1_empty[b] ^= 1; }
+                    ++n_d1_use[b];
+                    tc_fence_after();
+                    for (int kb = 0; kb < a.KB1; ++kb) {
+                        if (c == 0) mbar_wait(&x_full[kb], ph_x_full);
+                        mbar_wait(&w1_full[w1_stage], ph_w1);
+                        tc_fence_after();
+                        const int nks = kb == a.KB1 - 1 ? a.nks_last : 4;
+                        for (int ks = 0; ks < nks; ++ks) {
+                            const uint64_t ad = make_sw128_desc(sX_a + kb * TC_BLK + ks * 32);
+                            const uint64_t bd = make_sw128_desc(sW1_a + w1_stage * TC_BLK + ks * 32);
+                            umma_f16_ss(tD1[b], ad, bd, idesc1, (kb | ks) ? 1u : 0u);
+                        }
+                        tc_commit(&w1_empty[w1_stage]);
+                        if (++w1_stage == (uint32_t)a.S1) { w1_stage = 0; ph_w1 ^= 1; }
+                    }
+                    tc_commit(&d1_full[b]);
+                    if (c == a.NCH - 1) tc_commit(x_empty);
+                };
+                auto g2 = [&](int c) {
+                    if (c == 0 && !first_d2) { mbar_wait(d2_empty, ph_d2_empty); ph_d2_empty ^= 1; }
+                    first_d2 = false;
+                    mbar_wait(w2_full, ph_w2_full); ph_w2_full ^= 1;
+                    mbar_wait(h_full, ph_h_full); ph_h_full ^= 1;
+                    tc_fence_after();
+                    for (int kb = 0; kb < 2; ++kb)
+                        for (int ks = 0; ks < 4; ++ks) {
+                            const uint64_t ad = make_sw128_desc(sH_a + kb * TC_BLK + ks * 32);
+                            const uint64_t bd = make_sw128_desc(sW2_a + kb * W2_BLK + ks * 32);
+                            umma_f16_ss(tD2, ad, bd, idesc2, (c | kb | ks) ? 1u : 0u);
+                        }
+                    tc_commit(h_empty);
+                    tc_commit(w2_empty);
+                    if (c == a.NCH - 1) tc_commit(d2_full);
+                };
+                g1(0);
+                for (int c = 0; c < a.NCH; ++c) {
+                    if (c + 1 < a.NCH) g1(c + 1);
+                    g2(c);
+                }
+                ph_x_full ^= 1;
+            }
+        }
+    } else {
+        // ===================================================================== epilogue warps
+        const int ew = warp - 2;                 // 0..7
+        const int q = warp & 3;                  // TMEM lane quarter this warp may access
+        const int hh = ew >> 2;                  // column half
+        const int row = q * 32 + lane;           // tile row == TMEM lane
+        const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+        uint32_t ph_d1_full[2] = {0, 0}, ph_h_empty = 0, ph_d2_full = 0;
+        bool first_h = true;
+        for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+            for (int c = 0; c < a.NCH; ++c) {
+                const int b = c & 1;
+                mbar_wait(&d1_full[b], ph_d1_full[b]); ph_d1_full[b] ^= 1;
+                tc_fence_after();
+                uint32_t acc[2][32];
+                tmem_ld32(tD1[b] + lane_addr + hh * 64, acc[0]);
+                tmem_ld32(tD1[b] + lane_addr + hh * 64 + 32, acc[1]);
+                tmem_ld_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&d1_empty[b]);
+                // fsig(x) = 1 / (1 + D(-x)),  D's bit pattern = trunc(-A32*x + C32 - A32*b1)
+                uint32_t hp[32];
+                const float4 *kp = reinterpret_cast<const float4 *>(a.sig_k + c * TC_NC + hh * 64);
+#pragma unroll
+                for (int g = 0; g < 16; ++g) {
+                    const float4 k4 = __ldg(kp + g);
+                    const int j = g * 4;
+                    const float x0 = __uint_as_float(acc[j >> 5][(j + 0) & 31]), x1 = __uint_as_float(acc[j >> 5][(j + 1) & 31]);
+                    const float x2 = __uint_as_float(acc[j >> 5][(j + 2) & 31]), x3 = __uint_as_float(acc[j >> 5][(j + 3) & 31]);
+                    const float h0 = rcp_approx(1.0f + fexp_bits(fmaf(x0, -kA32, k4.x)));
+                    const float h1 = rcp_approx(1.0f + fexp_bits(fmaf(x1, -kA32, k4.y)));
+                    const float h2 = rcp_approx(1.0f + fexp_bits(fmaf(x2, -kA32, k4.z)));
+                    const float h3 = rcp_approx(1.0f + fexp_bits(fmaf(x3, -kA32, k4.w)));
+                    hp[g * 2] = pack_half2(h0, h1);
+                    hp[g * 2 + 1] = pack_half2(h2, h3);
+                }
+                // H[row][hh*64 .. +63] -> k-block hh of the H operand, SW128: 8 x 16-byte chunks
+                if (!first_h) { mbar_wait(h_empty, ph_h_empty); ph_h_empty ^= 1; }
+                first_h = false;
+                uint8_t *hrow = sH + (size_t)hh * TC_BLK + (size_t)row * 128;
+#pragma unroll
+                for (int ch = 0; ch < 8; ++ch) {
+                    uint4 v = make_uint4(hp[ch * 4], hp[ch * 4 + 1], hp[ch * 4 + 2], hp[ch * 4 + 3]);
+                    *reinterpret_cast<uint4 *>(hrow + ((ch ^ (row & 7)) << 4)) = v;
+                }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(h_full);
+            }
+            // ------------------------------------------------------------- E2: softmax + outputs
+            mbar_wait(d2_full, ph_d2_full); ph_d2_full ^= 1;
+            tc_fence_after();
+            float o[NH8 * 8];
+            {
+                uint32_t raw[NH8 * 8];
+#pragma unroll
+                for (int g = 0; g < NH8; ++g) tmem_ld8(tD2 + lane_addr + hh * (N2P / 2) + g * 8, raw + g * 8);
+                tmem_ld_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(d2_empty);
+#pragma unroll
+                for (int i = 0; i < NH8 * 8; ++i) o[i] = __uint_as_float(raw[i]);
+            }
+            const int col0 = hh * (N2P / 2);
+            float mx = -FLT_MAX;
+#pragma unroll
+            for (int i = 0; i < NH8 * 8; ++i) {
+                const int n = col0 + i;
+                o[i] = n < a.nout ? o[i] + __ldg(a.b2 + n) : -FLT_MAX;
+                mx = fmaxf(mx, o[i]);
+            }
+            s_red[(0 * 2 + hh) * 128 + row] = mx;
+            epi_bar_sync();
+            mx = fmaxf(mx, s_red[(0 * 2 + (hh ^ 1)) * 128 + row]);
+            float sum = 0.0f;
+#pragma unroll
+            for (int i = 0; i < NH8 * 8; ++i) {
+                const int n = col0 + i;
+                const float e = n < a.nout ? fexp_bits(fmaf(o[i] - mx, kA32, kC32)) : 0.0f;
+                o[i] = e;
+                sum += e;
+            }
+            s_red[(1 * 2 + hh) * 128 + row] = sum;
+            epi_bar_sync();
+            sum += s_red[(1 * 2 + (hh ^ 1)) * 128 + row];
+            const float sc = 1.0f / sum;
+            const int64_t f = (int64_t)tile * TC_M + row;
+            if (f < a.nf) {
+                if (a.post) {
+                    float *dst = a.post + f * a.ldpost;
+#pragma unroll
+                    for (int i = 0; i < NH8 * 8; ++i)
+                        if (col0 + i < a.nout) dst[col0 + i] = o[i] * sc;
+                } else {
+                    // merger input: sLn(p), merger input normalisation, fp16, straight into the merger's X image
+#pragma unroll
+                    for (int i = 0; i < NH8 * 8; ++i) {
+                        const int n = col0 + i;
+                        if (n < a.nout) {
+                            const float p = o[i] * sc;
+                            const float v = p > 0.0f ? __logf(p) : 0.0f;
+                            const int cm = a.xm_col0 + n;
+                            const float xn = (v - __ldg(a.mmean + cm)) * __ldg(a.mdev + cm);
+                            uint8_t *blk = a.xm_img + ((size_t)tile * a.xm_kb1 + (cm >> 6)) * TC_BLK;
+                            *reinterpret_cast<__half *>(blk + sw128_off(row, cm & 63)) = __float2half_rn(xn);
+                        }
+                    }
+                }
+            }
+            epi_bar_sync();  // s_red is reused by the next tile
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// weight images (built once per context)
+// ------------------------------------------------------------------------------------------------
+struct TcNetImages {
+    uint8_t *w1_img = nullptr, *w2_img = nullptr;
+    float *sig_k = nullptr, *b2 = nullptr;
+    int KB1 = 0, NCH = 0, N2P = 0, nks_last = 4;
+};
+
+__global__ void k_build_w1_img(const float *__restrict__ w1, int nin, int nhid, int nin4, uint8_t *img, int KB1, int NCH)
+{
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t total = (int64_t)NCH * 128 * KB1 * 64;
+    if (idx >= total) return;
+    const int k = (int)(idx % (KB1 * 64));
+    const int n = (int)(idx / (KB1 * 64));
+    const float v = (n < nhid && k < nin) ? w1[(int64_t)n * nin4 + k] : 0.0f;
+    const int c = n >> 7, r = n & 127, kb = k >> 6, cc = k & 63;
+    *reinterpret_cast<__half *>(img + ((size_t)c * KB1 + kb) * TC_BLK + sw128_off(r, cc)) = __float2half_rn(v);
+}
+
+__global__ void k_build_w2_img(const float *__restrict__ w2, int nhid, int nout, int nhid4, uint8_t *img, int N2P, int NCH)
+{
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t total = (int64_t)N2P * NCH * 128;
+    if (idx >= total) return;
+    const int k = (int)(idx % (NCH * 128));
+    const int n = (int)(idx / (NCH * 128));
+    const float v = (n < nout && k < nhid) ? w2[(int64_t)n * nhid4 + k] : 0.0f;
+    const int c = k >> 7, kb = (k >> 6) & 1, cc = k & 63;
+    *reinterpret_cast<__half *>(img + ((size_t)c * 2 + kb) * (N2P * 128) + sw128_off(n, cc)) = __float2half_rn(v);
+}
+
+__global__ void k_build_bias(const float *__restrict__ b1, int nhid, float *sig_k, int nhidP, const float *__restrict__ b2,
+                             int nout, float *b2p, int N2P)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nhidP) sig_k[i] = i < nhid ? (float)((double)kC32 - (double)kA32 * (double)b1[i]) : kC32;
+    if (i < N2P) b2p[i] = i < nout ? b2[i] : 0.0f;
+}
+
+struct TcState {
+    TcNetImages net[3];
+    bool ready = false;
+};
+
+int mlp_tc_prepare(phn_ctx *c)
+{
+    if (!c->tc) c->tc = new TcState();
+    TcState &st = *static_cast<TcState *>(c->tc);
+    if (st.ready) return PHN_OK;
+    for (int i = 0; i < 3; ++i) {
+        DevNet &n = c->net[i];
+        TcNetImages &im = st.net[i];
+        im.KB1 = (n.nin + 63) / 64;
+        im.NCH = (n.nhid + 127) / 128;
+        im.N2P = (n.nout + 15) / 16 * 16;
+        const int rem = n.nin - (im.KB1 - 1) * 64;
+        im.nks_last = (rem + 15) / 16;
+        if (im.KB1 > 8) return fail(c, PHN_ERR_UNSUPPORTED, "tensor-core mode: more than 512 network inputs\n");
+        if (im.N2P != 128 && im.N2P != 144 && im.N2P != 160 && im.N2P != 192)
+            return fail(c, PHN_ERR_UNSUPPORTED, "tensor-core mode: %d network outputs not instantiated\n", n.nout);
+        const size_t w1b = (size_t)im.NCH * im.KB1 * TC_BLK, w2b = (size_t)im.NCH * 2 * im.N2P * 128;
+        PHN_CUDA(c, cudaMalloc((void **)&im.w1_img, w1b));
+        PHN_CUDA(c, cudaMalloc((void **)&im.w2_img, w2b));
+        PHN_CUDA(c, cudaMalloc((void **)&im.sig_k, sizeof(float) * im.NCH * 128));
+        PHN_CUDA(c, cudaMalloc((void **)&im.b2, sizeof(float) * im.N2P));
+        const int64_t t1 = (int64_t)im.NCH * 128 * im.KB1 * 64, t2 = (int64_t)im.N2P * im.NCH * 128;
+        k_build_w1_img<<<(unsigned)((t1 + 255) / 256), 256, 0, c->stream>>>(n.w1, n.nin, n.nhid, n.nin4, im.w1_img, im.KB1, im.NCH);
+        k_build_w2_img<<<(unsigned)((t2 + 255) / 256), 256, 0, c->stream>>>(n.w2, n.nhid, n.nout, n.nhid4, im.w2_img, im.N2P, im.NCH);
+        const int nb = im.NCH * 128 > im.N2P ? im.NCH * 128 : im.N2P;
+        k_build_bias<<<(nb + 255) / 256, 256, 0, c->stream>>>(n.b1, n.nhid, im.sig_k, im.NCH * 128, n.b2, n.nout, im.b2, im.N2P);
+        PHN_CUDA(c, cudaGetLastError());
+        n.w1h = reinterpret_cast<__half *>(im.w1_img);  // owned by the context from here on (freed in phn_destroy)
+        n.w2h = reinterpret_cast<__half *>(im.w2_img);
+        n.nhidP = im.NCH * 128;
+        n.noutP = im.N2P;
+    }
+    st.ready = true;
+    return PHN_OK;
+}
+
+void mlp_tc_release(phn_ctx *c)
+{
+    if (!c->tc) return;
+    TcState *st = static_cast<TcState *>(c->tc);
+    for (auto &im : st->net) {
+        if (im.sig_k) cudaFree(im.sig_k);
+        if (im.b2) cudaFree(im.b2);
+    }
+    delete st;
+    c->tc = nullptr;
+}
+
+template <int N2P>
+static int launch_one(phn_ctx *c, const TcArgs &a, size_t smem_bytes, int grid)
+{
+    PHN_CUDA(c, cudaFuncSetAttribute(k_mlp_tc<N2P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+    k_mlp_tc<N2P><<<grid, 320, smem_bytes, c->stream>>>(a);
+    PHN_CUDA(c, cudaGetLastError());
+    return PHN_OK;
+}
+
+static int run_net_tc(phn_ctx *c, int which, const uint8_t *x_img, int64_t nf, int64_t f0)
+{
+    TcState &st = *static_cast<TcState *>(c->tc);
+    const TcNetImages &im = st.net[which];
+    const DevNet &n = c->net[which];
+    TcArgs a{};
+    a.x_img = x_img; a.w1_img = im.w1_img; a.w2_img = im.w2_img; a.sig_k = im.sig_k; a.b2 = im.b2;
+    a.n_tiles = (int)((nf + TC_M - 1) / TC_M);
+    a.KB1 = im.KB1; a.NCH = im.NCH; a.nks_last = im.nks_last; a.nf = nf; a.nout = n.nout;
+    if (which < 2) {
+        a.post = nullptr;
+        a.xm_img = (uint8_t *)c->d_xmh.p; a.xm_kb1 = st.net[2].KB1; a.xm_col0 = which * n.nout;
+        a.mmean = c->net[2].mean; a.mdev = c->net[2].dev;
+    } else {
+        a.post = (float *)c->d_post.p + f0 * n.nout; a.ldpost = n.nout;
+    }
+    // shared memory plan: X (KB1 blocks) + W2 (2 blocks) + H (2 blocks) + barriers, rest = W1 ring
+    const size_t fixed = (size_t)im.KB1 * TC_BLK + 2 * (size_t)im.N2P * 128 + 2 * TC_BLK + 36 * 8 + 4 * 128 * 4 + 1024;
+    const size_t max_smem = 232448;
+    int S1 = (int)((max_smem - fixed) / TC_BLK);
+    if (S1 > 8) S1 = 8;
+    if (S1 < 2) return fail(c, PHN_ERR_UNSUPPORTED, "tensor-core mode: shared memory plan does not fit\n");
+    a.S1 = S1;
+    const size_t smem_bytes = fixed + (size_t)S1 * TC_BLK;
+    const int grid = a.n_tiles < c->num_sms ? a.n_tiles : c->num_sms;
+    int rc;
+    switch (im.N2P) {
+        case 128: rc = launch_one<128>(c, a, smem_bytes, grid); break;
+        case 144: rc = launch_one<144>(c, a, smem_bytes, grid); break;
+        case 160: rc = launch_one<160>(c, a, smem_bytes, grid); break;
+        default: rc = launch_one<192>(c, a, smem_bytes, grid); break;
+    }
+    c->k_launches[PHN_K_MLP] += 1;
+    return rc;
+}
+
+int launch_mlp_tc(phn_ctx *c, int64_t f0, int64_t nf)
+{
+    if (nf == 0) return PHN_OK;
+    int rc;
+    if ((rc = run_net_tc(c, 0, (const uint8_t *)c->d_x0h.p, nf, f0))) return rc;
+    if ((rc = run_net_tc(c, 1, (const uint8_t *)c->d_x1h.p, nf, f0))) return rc;
+    return run_net_tc(c, 2, (const uint8_t *)c->d_xmh.p, nf, f0);
+}
+
 }  // namespace phn

@@ -21,8 +21,8 @@ struct StcArgs {
     const float *nmean0, *ndev0, *nmean1, *ndev1;
     float normc;
     float *x0, *x1;   // fp32 outputs [nf][ld32]  (exact mode)   or nullptr
-    __half *x0h, *x1h; // fp16 outputs [nf][ld16] (tensor-core mode) or nullptr
-    int ld32, ld16;
+    uint8_t *x0h, *x1h; // fp16 outputs as shared-memory images (tensor-core mode, see k_mlp_tc.cu) or nullptr
+    int ld32, kb1;      // fp32 row stride; 64-column blocks per row of the fp16 image
 };
 
 __device__ __forceinline__ int stc_find_utt(const int64_t *off, int n, int64_t f)
@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(256) k_stc(StcArgs a)
     const float *nd = side ? a.ndev1 : a.ndev0;
     const int col0 = b * a.ncoef;
     float *o32 = side ? a.x1 : a.x0;
-    __half *o16 = side ? a.x1h : a.x0h;
+    uint8_t *o16 = side ? a.x1h : a.x0h;
 
     for (int k = 0; k < a.ncoef; ++k) {
         float s = 0.0f;
@@ -81,7 +81,12 @@ __global__ void __launch_bounds__(256) k_stc(StcArgs a)
         const int col = col0 + k;
         const float xn = __fmul_rn(__fsub_rn(s, nm[col]), nd[col]);  // NeuralNet::Normalize nn.cpp:702-716
         if (o32) o32[fl * a.ld32 + col] = xn;
-        if (o16) o16[fl * a.ld16 + col] = __float2half_rn(xn);
+        if (o16) {  // [tile of 128 frames][64-column block][128 rows x 128 B, 16-byte chunks XOR-swizzled by row%8]
+            const int r = (int)(fl & 127), cc = col & 63;
+            uint8_t *blk = o16 + ((size_t)(fl >> 7) * a.kb1 + (col >> 6)) * 16384;
+            *reinterpret_cast<__half *>(blk + r * 128 + ((((unsigned)cc >> 3) ^ ((unsigned)r & 7u)) << 4) + (cc & 7) * 2) =
+                __float2half_rn(xn);
+        }
     }
 }
 
@@ -101,10 +106,10 @@ int launch_stc(phn_ctx *c, int64_t f0, int64_t nf)
     const bool tc = c->mlp_mode == PHN_MLP_TC_F16;
     a.x0 = tc ? nullptr : (float *)c->d_x0.p;
     a.x1 = tc ? nullptr : (float *)c->d_x1.p;
-    a.x0h = tc ? (__half *)c->d_x0h.p : nullptr;
-    a.x1h = tc ? (__half *)c->d_x1h.p : nullptr;
+    a.x0h = tc ? (uint8_t *)c->d_x0h.p : nullptr;
+    a.x1h = tc ? (uint8_t *)c->d_x1h.p : nullptr;
     a.ld32 = c->net[0].kp;
-    a.ld16 = c->net[0].k1P;
+    a.kb1 = c->net[0].k1P / 64;
     const int64_t items = nf * 2 * c->nbanks;
     k_stc<<<(unsigned)((items + 255) / 256), 256, 0, c->stream>>>(a);
     PHN_CUDA(c, cudaGetLastError());
