@@ -24,6 +24,7 @@
 #include "device_math.cuh"
 
 #include <cfloat>
+#include <cstdlib>
 
 namespace phn {
 
@@ -231,13 +232,17 @@ __global__ void __launch_bounds__(320, 1) k_mlp_tc(TcArgs a)
                 }
             };
             for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
-                // later tiles: the first weight chunk is prefetched while the previous tile still owns X
-                if (!first_tile) { load_w1(0); mbar_wait(x_empty, ph_x_empty); ph_x_empty ^= 1; }
+                // Later tiles: the first weight chunk is prefetched while the previous tile still owns X -
+                // but only when it fits the ring entirely (KB1 <= S1); otherwise the issuer, which waits
+                // for X before it frees a ring stage, and this warp would wait for each other.
+                const bool prefetch_w1 = !first_tile && a.KB1 <= a.S1;
+                if (prefetch_w1) load_w1(0);
+                if (!first_tile) { mbar_wait(x_empty, ph_x_empty); ph_x_empty ^= 1; }
                 for (int kb = 0; kb < a.KB1; ++kb) {
                     mbar_expect_tx(&x_full[kb], TC_BLK);
                     tma_load_1d(sX + (size_t)kb * TC_BLK, a.x_img + ((size_t)tile * a.KB1 + kb) * TC_BLK, TC_BLK, &x_full[kb]);
                 }
-                if (first_tile) load_w1(0);
+                if (!prefetch_w1) load_w1(0);
                 first_tile = false;
                 for (int c = 0; c < a.NCH; ++c) {
                     if (c + 1 < a.NCH) load_w1(c + 1);
@@ -553,7 +558,11 @@ static int run_net_tc(phn_ctx *c, int which, const uint8_t *x_img, int64_t nf, i
     if (S1 < 2) return fail(c, PHN_ERR_UNSUPPORTED, "tensor-core mode: shared memory plan does not fit\n");
     a.S1 = S1;
     const size_t smem_bytes = fixed + (size_t)S1 * TC_BLK;
-    const int grid = a.n_tiles < c->num_sms ? a.n_tiles : c->num_sms;
+    int grid = a.n_tiles < c->num_sms ? a.n_tiles : c->num_sms;
+    if (const char *e = getenv("PHNREC_TC_GRID")) {  // debugging aid: force several tiles per CTA
+        const int g = atoi(e);
+        if (g > 0 && g < grid) grid = g;
+    }
     int rc;
     switch (im.N2P) {
         case 128: rc = launch_one<128>(c, a, smem_bytes, grid); break;
