@@ -59,7 +59,10 @@ static int upload_net(phn_ctx *c, int which)
     d.nin = h.nin; d.nhid = h.nhid; d.nout = h.nout; d.nin4 = h.nin4; d.nhid4 = h.nhid4; d.nout4 = h.nout4;
     d.kp = up16(h.nin4);
     d.ldh = up16(h.nhid4);
-    d.w1h = nullptr; d.w2h = nullptr; d.k1P = (h.nin + 63) / 64 * 64; d.nhidP = 0; d.noutP = 0;
+    d.w1h = nullptr; d.w2h = nullptr; d.nhidP = 0; d.noutP = 0;
+    // fp16 image width: the merger's image keeps its two halves 8-column aligned (k_mlp_tc.cu)
+    const int kin = which == 2 ? (c->hnet[0].nout + 7) / 8 * 8 + c->hnet[0].nout : h.nin;
+    d.k1P = (kin + 63) / 64 * 64;
     int rc;
     if ((rc = upload(c, &d.w1, h.w1.data(), h.w1.size()))) return rc;
     if ((rc = upload(c, &d.w2, h.w2.data(), h.w2.size()))) return rc;
@@ -97,13 +100,12 @@ static int plan_frames(phn_ctx *c, const int64_t *frame_off, int n_utt, int n_pe
         }
     c->label_cap = c->h_lab_off[nseg];
     const int64_t F = c->total_frames;
-    const int nout = c->net[2].nout;
     int rc;
     if ((rc = ensure(c, c->d_frame_off, sizeof(int64_t) * (n_utt + 1)))) return rc;
     if ((rc = ensure(c, c->d_lab_off, sizeof(int64_t) * (nseg + 1)))) return rc;
     if ((rc = ensure(c, c->d_mel, sizeof(float) * F * c->nbanks))) return rc;
     if ((rc = ensure(c, c->d_mean, sizeof(float) * (size_t)n_utt * c->nbanks))) return rc;
-    if ((rc = ensure(c, c->d_post, sizeof(float) * F * nout))) return rc;
+    if ((rc = ensure(c, c->d_post, sizeof(float) * F * c->ldp))) return rc;
     if ((rc = ensure(c, c->d_rec, (size_t)20 * F * n_pen))) return rc;
     if ((rc = ensure(c, c->d_labels, sizeof(phn_label) * (size_t)c->label_cap))) return rc;
     if ((rc = ensure(c, c->d_nlab, sizeof(int) * (size_t)nseg))) return rc;
@@ -296,6 +298,7 @@ int phn_create(const char *cfg_dir, int device, phn_ctx **out)
     if (c->hnet[0].nin % c->nbanks || c->hnet[0].nin != c->hnet[1].nin || c->hnet[0].nout != c->hnet[1].nout ||
         c->hnet[2].nin != 2 * c->hnet[0].nout)
         return bail(fail(c, PHN_ERR_NN_FORMAT, "Inconsistent network sizes in %s/weights\n", cfg_dir));
+    c->ldp = (c->hnet[2].nout + 3) / 4 * 4;  // posterior row stride on the device (16-byte aligned rows)
     c->ncoef = c->hnet[0].nin / c->nbanks;
     if (c->ncoef != 11) return bail(fail(c, PHN_ERR_UNSUPPORTED, "band nets must take 11 coefficients per band\n"));
     for (int w = 0; w < 2; ++w) {  // traps.cpp:549-570
@@ -529,7 +532,9 @@ int phn_fetch_posteriors(phn_ctx *c, float *post_out)
 {
     if (!c || !post_out) return PHN_ERR_ARG;
     PHN_CUDA(c, cudaSetDevice(c->device));
-    PHN_CUDA(c, cudaMemcpyAsync(post_out, c->d_post.p, sizeof(float) * c->total_frames * c->net[2].nout, cudaMemcpyDeviceToHost, c->stream));
+    const size_t rowb = sizeof(float) * c->net[2].nout;
+    if (c->total_frames)
+        PHN_CUDA(c, cudaMemcpy2DAsync(post_out, rowb, c->d_post.p, sizeof(float) * c->ldp, rowb, (size_t)c->total_frames, cudaMemcpyDeviceToHost, c->stream));
     PHN_CUDA(c, cudaStreamSynchronize(c->stream));
     return PHN_OK;
 }
@@ -603,7 +608,9 @@ int phn_decode(phn_ctx *c, const float *post, const int64_t *frame_off, int n_ut
     reset_timing(c);
     int rc;
     if ((rc = plan_frames(c, frame_off, n_utt, n_pen))) return rc;
-    PHN_CUDA(c, cudaMemcpyAsync(c->d_post.p, post, sizeof(float) * c->total_frames * c->net[2].nout, cudaMemcpyHostToDevice, c->stream));
+    const size_t rowb = sizeof(float) * c->net[2].nout;
+    if (c->total_frames)
+        PHN_CUDA(c, cudaMemcpy2DAsync(c->d_post.p, sizeof(float) * c->ldp, post, rowb, rowb, (size_t)c->total_frames, cudaMemcpyHostToDevice, c->stream));
     if ((rc = run_decode(c, penalties, n_pen))) return rc;
     return phn_fetch_labels(c, labels, label_cap, label_off);
 }

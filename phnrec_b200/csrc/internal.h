@@ -79,6 +79,7 @@ struct phn_ctx {
     phn::DevNet net[3];
     phn::DevTables tab{};
     int ncoef = 11;
+    int ldp = 0;  // device row stride of the posterior matrix (n_outputs rounded up to 4)
     int num_sms = 148;
 
     // ---- batch state (grow-only device buffers)

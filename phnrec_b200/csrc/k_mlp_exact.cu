@@ -245,7 +245,7 @@ static int run_net(phn_ctx *c, int which, const float *x, int ldx, int64_t nf, i
         a.xm = (float *)c->d_xm.p; a.ldxm = c->net[2].kp; a.xm_col0 = which * n.nout;
         a.mmean = c->net[2].mean; a.mdev = c->net[2].dev;
     } else {
-        a.post = (float *)c->d_post.p + f0 * n.nout; a.ldpost = n.nout;
+        a.post = (float *)c->d_post.p + f0 * c->ldp; a.ldpost = c->ldp;
     }
     k_l2_exact<<<(unsigned)((nf + L2_BM - 1) / L2_BM), 256, 0, c->stream>>>(a);
     PHN_CUDA(c, cudaGetLastError());

@@ -138,18 +138,21 @@ __device__ __forceinline__ uint32_t pack_half2(float lo, float hi)
     asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
     return r;
 }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
-// The Quicknet bit-trick exponential in single precision: D(y) ~ float whose bit pattern is
-// trunc(2^23/ln2 * y) + (127*2^23 - 60801*8)  (fexp.h:14-21 scaled from the double's 20-bit to the
-// float's 23-bit mantissa field).  v = A32*y + C32 is formed by one FFMA by the callers.
-constexpr float kA32 = 12102203.161561485f;   // 2^23 / ln 2
-constexpr float kC32 = 1064866808.0f;         // 127 * 2^23 - 60801 * 8
-constexpr float kVmin = 12000000.0f, kVmax = 2118000000.0f;
-__device__ __forceinline__ float fexp_bits(float v)
+// The Quicknet bit-trick exponential (fexp.h:14-21) without a float->int conversion (F2I shares the
+// quarter-rate XU pipe with MUFU.RCP, and the epilogue must keep pace with the tensor pipe):
+//   D(y) = float whose exponent field is floor(t) and whose mantissa is frac(t),  t = y/ln2 + Ct,
+//   Ct = 127 - 60801/2^20.  One FFMA forms r = 2^23 + t*2^14 (callers fold Ct, the bias and 2^23
+//   into the addend); in [2^23, 2^24) the float's mantissa field IS round(t*2^14), so
+//   bits(D) = bits(r) << 9.  t keeps 14 fractional bits (2^-14 relative in D; the reference keeps 20).
+constexpr float kK14 = 23637.115549924778f;     // 2^14 / ln 2
+constexpr double kCt = 127.0 - 60801.0 / 1048576.0;
+constexpr float kRmin = 8388608.0f;             // 2^23              (t = 0)
+constexpr float kRmax = 8388608.0f + 4177920.0f; // 2^23 + 255*2^14  (t = 255, D ~ 2^128 -> 1/(1+D) = 0)
+__device__ __forceinline__ float fexp_from_r(float r)
 {
-    v = fminf(fmaxf(v, kVmin), kVmax);
-    return __int_as_float(__float2int_rz(v));
+    r = fminf(fmaxf(r, kRmin), kRmax - 16384.0f);
+    return __uint_as_float(__float_as_uint(r) << 9);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -159,58 +162,68 @@ struct TcArgs {
     const uint8_t *x_img;     // [tiles][KB1][16 KB]  activations, SW128 blocks
     const uint8_t *w1_img;    // [NCH][KB1][16 KB]
     const uint8_t *w2_img;    // [NCH][2][N2P*128 B]
-    const float *sig_k;       // [NCH*128]  per hidden unit: C32 - A32*b1   (0-weight padding units give fsig(0)*0)
+    const float *sig_k;       // [NCH*128]  per hidden unit: 2^23 + round(2^14 (Ct - b1/ln2))
     const float *b2;          // [N2P]
-    int n_tiles, KB1, NCH, S1;
+    int n_tiles, KB1, NCH, S1, S2;
     int nks_last;             // k-steps (of 16) actually needed in the last k-block of layer 1
     int64_t nf;               // frames in this launch
     int nout;
     // outputs
-    float *post; int ldpost;                          // merger: posteriors [nf][nout]
-    uint8_t *xm_img; int xm_kb1; int xm_col0;         // band nets: merger input image
-    const float *mmean, *mdev;
+    float *post; int ldpost;                          // merger: posteriors [nf][ldpost]
+    uint8_t *xm_img; int xm_kb1; int xm_col0;         // band nets: merger input image, first column (multiple of 8)
+    const float *mmean, *mdev;                        // merger input normalisation, indexed by image column
 };
 
+constexpr int TC_EPI_WARPS = 16;
+constexpr int TC_THREADS = (2 + TC_EPI_WARPS) * 32;
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
+
 template <int N2P>
-__global__ void __launch_bounds__(320, 1) k_mlp_tc(TcArgs a)
+__global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs a)
 {
     constexpr int W2_BLK = N2P * 128;       // bytes of one [N2P rows x 64 fp16] block
-    constexpr int NH8 = N2P / 16;           // 8-column groups per column half of D2
+    constexpr int NG = N2P / 8;             // 8-column groups of D2
+    constexpr int MAXG = (NG + 3) / 4;      // groups per column quarter (at most)
     extern __shared__ uint8_t smem_raw[];
     // carve-up (all block bases 1024-byte aligned: the swizzle pattern is a function of the address)
     uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t *sX = smem;                                        // KB1 x 16 KB
     uint8_t *sW1 = sX + (size_t)a.KB1 * TC_BLK;                // S1 x 16 KB ring
-    uint8_t *sW2 = sW1 + (size_t)a.S1 * TC_BLK;                // 2 x W2_BLK
-    uint8_t *sH = sW2 + 2 * W2_BLK;                            // 2 x 16 KB
-    uint64_t *bars = reinterpret_cast<uint64_t *>(sH + 2 * TC_BLK);
+    uint8_t *sW2 = sW1 + (size_t)a.S1 * TC_BLK;                // S2 x W2_BLK ring
+    uint8_t *sH = sW2 + (size_t)a.S2 * W2_BLK;                 // 2 x 16 KB
+    float *s_sigk = reinterpret_cast<float *>(sH + 2 * TC_BLK);  // [NCH*128]
+    float *s_b2 = s_sigk + a.NCH * TC_NC;                      // [N2P]
+    float *s_red = s_b2 + N2P;                                 // [4][128] row max / row sum exchange
+    uint64_t *bars = reinterpret_cast<uint64_t *>(s_red + 4 * 128);
     uint64_t *x_full = bars;                 // [8]
     uint64_t *x_empty = bars + 8;            // [1]
     uint64_t *w1_full = bars + 9;            // [8]
     uint64_t *w1_empty = bars + 17;          // [8]
-    uint64_t *w2_full = bars + 25, *w2_empty = bars + 26;
-    uint64_t *d1_full = bars + 27;           // [2]
-    uint64_t *d1_empty = bars + 29;          // [2]
-    uint64_t *h_full = bars + 31, *h_empty = bars + 32;
-    uint64_t *d2_full = bars + 33, *d2_empty = bars + 34;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 35);
-    float *s_red = reinterpret_cast<float *>(bars + 36);       // [2][2][128] row max / row sum exchange
+    uint64_t *w2_full = bars + 25;           // [4]
+    uint64_t *w2_empty = bars + 29;          // [4]
+    uint64_t *d1_full = bars + 33;           // [2]
+    uint64_t *d1_empty = bars + 35;          // [2]
+    uint64_t *h_full = bars + 37, *h_empty = bars + 38;
+    uint64_t *d2_full = bars + 39, *d2_empty = bars + 40;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 41);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < 8; ++i) { mbar_init(&x_full[i], 1); mbar_init(&w1_full[i], 1); mbar_init(&w1_empty[i], 1); }
+        for (int i = 0; i < 4; ++i) { mbar_init(&w2_full[i], 1); mbar_init(&w2_empty[i], 1); }
         mbar_init(x_empty, 1);
-        mbar_init(w2_full, 1); mbar_init(w2_empty, 1);
-        for (int i = 0; i < 2; ++i) { mbar_init(&d1_full[i], 1); mbar_init(&d1_empty[i], 8); }
-        mbar_init(h_full, 8); mbar_init(h_empty, 1);
-        mbar_init(d2_full, 1); mbar_init(d2_empty, 8);
+        for (int i = 0; i < 2; ++i) { mbar_init(&d1_full[i], 1); mbar_init(&d1_empty[i], TC_EPI_WARPS); }
+        mbar_init(h_full, TC_EPI_WARPS); mbar_init(h_empty, 1);
+        mbar_init(d2_full, 1); mbar_init(d2_empty, TC_EPI_WARPS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {  // TMEM: 512 columns (D1 double buffer 2 x 128, D2 up to 192)
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
+    for (int i = threadIdx.x; i < a.NCH * TC_NC; i += blockDim.x) s_sigk[i] = a.sig_k[i];
+    for (int i = threadIdx.x; i < N2P; i += blockDim.x) s_b2[i] = a.b2[i];
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -221,14 +234,22 @@ __global__ void __launch_bounds__(320, 1) k_mlp_tc(TcArgs a)
     if (warp == 0) {
         // ===================================================================== TMA producer
         if (lane == 0) {
-            uint32_t ph_x_empty = 0, ph_w2_empty = 0, w1_stage = 0, ph_w1 = 0;
-            bool first_tile = true, first_w2 = true;
+            uint32_t ph_x_empty = 0, w1_stage = 0, ph_w1 = 0, w2_stage = 0, ph_w2 = 0;
+            bool first_tile = true;
             auto load_w1 = [&](int c) {
                 for (int kb = 0; kb < a.KB1; ++kb) {
                     mbar_wait(&w1_empty[w1_stage], ph_w1 ^ 1);
                     mbar_expect_tx(&w1_full[w1_stage], TC_BLK);
                     tma_load_1d(sW1 + (size_t)w1_stage * TC_BLK, a.w1_img + ((size_t)c * a.KB1 + kb) * TC_BLK, TC_BLK, &w1_full[w1_stage]);
                     if (++w1_stage == (uint32_t)a.S1) { w1_stage = 0; ph_w1 ^= 1; }
+                }
+            };
+            auto load_w2 = [&](int c) {
+                for (int kb = 0; kb < 2; ++kb) {
+                    mbar_wait(&w2_empty[w2_stage], ph_w2 ^ 1);
+                    mbar_expect_tx(&w2_full[w2_stage], W2_BLK);
+                    tma_load_1d(sW2 + (size_t)w2_stage * W2_BLK, a.w2_img + ((size_t)c * 2 + kb) * W2_BLK, W2_BLK, &w2_full[w2_stage]);
+                    if (++w2_stage == (uint32_t)a.S2) { w2_stage = 0; ph_w2 ^= 1; }
                 }
             };
             for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
@@ -244,12 +265,9 @@ __global__ void __launch_bounds__(320, 1) k_mlp_tc(TcArgs a)
                 }
                 if (!prefetch_w1) load_w1(0);
                 first_tile = false;
-                for (int c = 0; c < a.NCH; ++c) {
+                for (int c = 0; c < a.NCH; ++c) {   // same order as the issuer consumes: G1(c+1) before G2(c)
                     if (c + 1 < a.NCH) load_w1(c + 1);
-                    if (!first_w2) { mbar_wait(w2_empty, ph_w2_empty); ph_w2_empty ^= 1; }
-                    first_w2 = false;
-                    mbar_expect_tx(w2_full, 2 * W2_BLK);
-                    tma_load_1d(sW2, a.w2_img + (size_t)c * 2 * W2_BLK, 2 * W2_BLK, w2_full);
+                    load_w2(c);
                 }
             }
         }
@@ -257,16 +275,20 @@ __global__ void __launch_bounds__(320, 1) k_mlp_tc(TcArgs a)
         // ===================================================================== MMA issuer
         if (lane == 0) {
             const uint32_t idesc1 = make_idesc(TC_NC), idesc2 = make_idesc(N2P);
-            uint32_t ph_x_full = 0, w1_stage = 0, ph_w1 = 0, ph_w2_full = 0, ph_h_full = 0, ph_d2_empty = 0;
-            uint32_t ph_d1_empty[2] = {0, 0};
-            uint32_t n_d1_use[2] = {0, 0};
+            uint32_t ph_x_full = 0, w1_stage = 0, ph_w1 = 0, w2_stage = 0, ph_w2 = 0, ph_h_full = 0, ph_d2_empty = 0;
+            uint32_t ph_d1_empty0 = 0, ph_d1_empty1 = 0, n_d1_use0 = 0, n_d1_use1 = 0;
             bool first_d2 = true;
             const uint32_t sX_a = smem_u32(sX), sW1_a = smem_u32(sW1), sW2_a = smem_u32(sW2), sH_a = smem_u32(sH);
             for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
                 auto g1 = [&](int c) {
                     const int b = c & 1;
-                    if (n_d1_use[b] > 0) { mbar_wait(&d1_empty[b], ph_d1_empty[b]); ph_d1_empty[b] ^= 1; }
-                    ++n_d1_use[b];
+                    if (b == 0) {
+                        if (n_d1_use0 > 0) { mbar_wait(&d1_empty[0], ph_d1_empty0); ph_d1_empty0 ^= 1; }
+                        ++n_d1_use0;
+                    } else {
+                        if (n_d1_use1 > 0) { mbar_wait(&d1_empty[1], ph_d1_empty1); ph_d1_empty1 ^= 1; }
+                        ++n_d1_use1;
+                    }
                     tc_fence_after();
                     for (int kb = 0; kb < a.KB1; ++kb) {
                         if (c == 0) mbar_wait(&x_full[kb], ph_x_full);
@@ -276,7 +298,7 @@ __global__ void __launch_bounds__(320, 1) k_mlp_tc(TcArgs a)
                         for (int ks = 0; ks < nks; ++ks) {
                             const uint64_t ad = make_sw128_desc(sX_a + kb * TC_BLK + ks * 32);
                             const uint64_t bd = make_sw128_desc(sW1_a + w1_stage * TC_BLK + ks * 32);
-                            umma_f16_ss(tD1[b], ad, bd, idesc1, (kb | ks) ? 1u : 0u);
+                            umma_f16_ss(b ? tD1[1] : tD1[0], ad, bd, idesc1, (kb | ks) ? 1u : 0u);
                         }
                         tc_commit(&w1_empty[w1_stage]);
                         if (++w1_stage == (uint32_t)a.S1) { w1_stage = 0; ph_w1 ^= 1; }
@@ -287,17 +309,19 @@ __global__ void __launch_bounds__(320, 1) k_mlp_tc(TcArgs a)
                 auto g2 = [&](int c) {
                     if (c == 0 && !first_d2) { mbar_wait(d2_empty, ph_d2_empty); ph_d2_empty ^= 1; }
                     first_d2 = false;
-                    mbar_wait(w2_full, ph_w2_full); ph_w2_full ^= 1;
                     mbar_wait(h_full, ph_h_full); ph_h_full ^= 1;
-                    tc_fence_after();
-                    for (int kb = 0; kb < 2; ++kb)
+                    for (int kb = 0; kb < 2; ++kb) {
+                        mbar_wait(&w2_full[w2_stage], ph_w2);
+                        tc_fence_after();
                         for (int ks = 0; ks < 4; ++ks) {
                             const uint64_t ad = make_sw128_desc(sH_a + kb * TC_BLK + ks * 32);
-                            const uint64_t bd = make_sw128_desc(sW2_a + kb * W2_BLK + ks * 32);
+                            const uint64_t bd = make_sw128_desc(sW2_a + w2_stage * W2_BLK + ks * 32);
                             umma_f16_ss(tD2, ad, bd, idesc2, (c | kb | ks) ? 1u : 0u);
                         }
+                        tc_commit(&w2_empty[w2_stage]);
+                        if (++w2_stage == (uint32_t)a.S2) { w2_stage = 0; ph_w2 ^= 1; }
+                    }
                     tc_commit(h_empty);
-                    tc_commit(w2_empty);
                     if (c == a.NCH - 1) tc_commit(d2_full);
                 };
                 g1(0);
@@ -310,111 +334,127 @@ __global__ void __launch_bounds__(320, 1) k_mlp_tc(TcArgs a)
         }
     } else {
         // ===================================================================== epilogue warps
-        const int ew = warp - 2;                 // 0..7
         const int q = warp & 3;                  // TMEM lane quarter this warp may access
-        const int hh = ew >> 2;                  // column half
+        const int cq = (warp - 2) >> 2;          // column quarter 0..3
         const int row = q * 32 + lane;           // tile row == TMEM lane
         const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-        uint32_t ph_d1_full[2] = {0, 0}, ph_h_empty = 0, ph_d2_full = 0;
+        uint32_t ph_d1_full0 = 0, ph_d1_full1 = 0, ph_h_empty = 0, ph_d2_full = 0;
         bool first_h = true;
+        // H[row][cq*32 .. +31] lives in k-block cq>>1 of the H operand, 16-byte chunks (cq&1)*4 .. +3
+        uint8_t *hrow = sH + (size_t)(cq >> 1) * TC_BLK + (size_t)row * 128;
+        const int hchunk0 = (cq & 1) * 4;
         for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
             for (int c = 0; c < a.NCH; ++c) {
                 const int b = c & 1;
-                mbar_wait(&d1_full[b], ph_d1_full[b]); ph_d1_full[b] ^= 1;
+                if (b == 0) { mbar_wait(&d1_full[0], ph_d1_full0); ph_d1_full0 ^= 1; }
+                else        { mbar_wait(&d1_full[1], ph_d1_full1); ph_d1_full1 ^= 1; }
                 tc_fence_after();
-                uint32_t acc[2][32];
-                tmem_ld32(tD1[b] + lane_addr + hh * 64, acc[0]);
-                tmem_ld32(tD1[b] + lane_addr + hh * 64 + 32, acc[1]);
+                uint32_t acc[32];
+                tmem_ld32((b ? tD1[1] : tD1[0]) + lane_addr + cq * 32, acc);
                 tmem_ld_wait();
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&d1_empty[b]);
-                // fsig(x) = 1 / (1 + D(-x)),  D's bit pattern = trunc(-A32*x + C32 - A32*b1)
-                uint32_t hp[32];
-                const float4 *kp = reinterpret_cast<const float4 *>(a.sig_k + c * TC_NC + hh * 64);
+                // fsig(x) = 1 / (1 + D(-x - b1))
+                uint32_t hp[16];
+                const float4 *kp = reinterpret_cast<const float4 *>(s_sigk + c * TC_NC + cq * 32);
 #pragma unroll
-                for (int g = 0; g < 16; ++g) {
-                    const float4 k4 = __ldg(kp + g);
-                    const int j = g * 4;
-                    const float x0 = __uint_as_float(acc[j >> 5][(j + 0) & 31]), x1 = __uint_as_float(acc[j >> 5][(j + 1) & 31]);
-                    const float x2 = __uint_as_float(acc[j >> 5][(j + 2) & 31]), x3 = __uint_as_float(acc[j >> 5][(j + 3) & 31]);
-                    const float h0 = rcp_approx(1.0f + fexp_bits(fmaf(x0, -kA32, k4.x)));
-                    const float h1 = rcp_approx(1.0f + fexp_bits(fmaf(x1, -kA32, k4.y)));
-                    const float h2 = rcp_approx(1.0f + fexp_bits(fmaf(x2, -kA32, k4.z)));
-                    const float h3 = rcp_approx(1.0f + fexp_bits(fmaf(x3, -kA32, k4.w)));
+                for (int g = 0; g < 8; ++g) {
+                    const float4 k4 = kp[g];
+                    const float h0 = rcp_approx(1.0f + fexp_from_r(fmaf(__uint_as_float(acc[g * 4 + 0]), -kK14, k4.x)));
+                    const float h1 = rcp_approx(1.0f + fexp_from_r(fmaf(__uint_as_float(acc[g * 4 + 1]), -kK14, k4.y)));
+                    const float h2 = rcp_approx(1.0f + fexp_from_r(fmaf(__uint_as_float(acc[g * 4 + 2]), -kK14, k4.z)));
+                    const float h3 = rcp_approx(1.0f + fexp_from_r(fmaf(__uint_as_float(acc[g * 4 + 3]), -kK14, k4.w)));
                     hp[g * 2] = pack_half2(h0, h1);
                     hp[g * 2 + 1] = pack_half2(h2, h3);
                 }
-                // H[row][hh*64 .. +63] -> k-block hh of the H operand, SW128: 8 x 16-byte chunks
                 if (!first_h) { mbar_wait(h_empty, ph_h_empty); ph_h_empty ^= 1; }
                 first_h = false;
-                uint8_t *hrow = sH + (size_t)hh * TC_BLK + (size_t)row * 128;
 #pragma unroll
-                for (int ch = 0; ch < 8; ++ch) {
-                    uint4 v = make_uint4(hp[ch * 4], hp[ch * 4 + 1], hp[ch * 4 + 2], hp[ch * 4 + 3]);
-                    *reinterpret_cast<uint4 *>(hrow + ((ch ^ (row & 7)) << 4)) = v;
+                for (int ch = 0; ch < 4; ++ch) {
+                    const uint4 v = make_uint4(hp[ch * 4], hp[ch * 4 + 1], hp[ch * 4 + 2], hp[ch * 4 + 3]);
+                    *reinterpret_cast<uint4 *>(hrow + (((hchunk0 + ch) ^ (row & 7)) << 4)) = v;
                 }
                 fence_proxy_async();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(h_full);
             }
             // ------------------------------------------------------------- E2: softmax + outputs
+            // column quarter cq owns the 8-column groups [g_beg, g_end) of D2
+            const int g_beg = (cq * NG) / 4, g_end = ((cq + 1) * NG) / 4;
             mbar_wait(d2_full, ph_d2_full); ph_d2_full ^= 1;
             tc_fence_after();
-            float o[NH8 * 8];
+            float o[MAXG * 8];
             {
-                uint32_t raw[NH8 * 8];
+                uint32_t raw[MAXG][8];
 #pragma unroll
-                for (int g = 0; g < NH8; ++g) tmem_ld8(tD2 + lane_addr + hh * (N2P / 2) + g * 8, raw + g * 8);
+                for (int g = 0; g < MAXG; ++g)
+                    if (g_beg + g < g_end) tmem_ld8(tD2 + lane_addr + (g_beg + g) * 8, raw[g]);
                 tmem_ld_wait();
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(d2_empty);
 #pragma unroll
-                for (int i = 0; i < NH8 * 8; ++i) o[i] = __uint_as_float(raw[i]);
+                for (int g = 0; g < MAXG; ++g)
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) o[g * 8 + i] = __uint_as_float(raw[g][i]);
             }
-            const int col0 = hh * (N2P / 2);
             float mx = -FLT_MAX;
 #pragma unroll
-            for (int i = 0; i < NH8 * 8; ++i) {
-                const int n = col0 + i;
-                o[i] = n < a.nout ? o[i] + __ldg(a.b2 + n) : -FLT_MAX;
-                mx = fmaxf(mx, o[i]);
-            }
-            s_red[(0 * 2 + hh) * 128 + row] = mx;
-            epi_bar_sync();
-            mx = fmaxf(mx, s_red[(0 * 2 + (hh ^ 1)) * 128 + row]);
-            float sum = 0.0f;
+            for (int g = 0; g < MAXG; ++g)
 #pragma unroll
-            for (int i = 0; i < NH8 * 8; ++i) {
-                const int n = col0 + i;
-                const float e = n < a.nout ? fexp_bits(fmaf(o[i] - mx, kA32, kC32)) : 0.0f;
+                for (int i = 0; i < 8; ++i) {
+                    const int n = (g_beg + g) * 8 + i;
+                    const bool ok = g_beg + g < g_end && n < a.nout;
+                    o[g * 8 + i] = ok ? o[g * 8 + i] + s_b2[n < N2P ? n : 0] : -FLT_MAX;
+                    mx = fmaxf(mx, o[g * 8 + i]);
+                }
+            s_red[cq * 128 + row] = mx;
+            epi_bar_sync();
+            mx = fmaxf(fmaxf(s_red[row], s_red[128 + row]), fmaxf(s_red[256 + row], s_red[384 + row]));
+            epi_bar_sync();
+            float sum = 0.0f;
+            const float kexp = (float)(8388608.0 + 16384.0 * kCt);
+#pragma unroll
+            for (int i = 0; i < MAXG * 8; ++i) {
+                const float e = o[i] > -FLT_MAX ? fexp_from_r(fmaf(o[i] - mx, kK14, kexp)) : 0.0f;
                 o[i] = e;
                 sum += e;
             }
-            s_red[(1 * 2 + hh) * 128 + row] = sum;
+            s_red[cq * 128 + row] = sum;
             epi_bar_sync();
-            sum += s_red[(1 * 2 + (hh ^ 1)) * 128 + row];
+            sum = (s_red[row] + s_red[128 + row]) + (s_red[256 + row] + s_red[384 + row]);
             const float sc = 1.0f / sum;
             const int64_t f = (int64_t)tile * TC_M + row;
             if (f < a.nf) {
                 if (a.post) {
                     float *dst = a.post + f * a.ldpost;
 #pragma unroll
-                    for (int i = 0; i < NH8 * 8; ++i)
-                        if (col0 + i < a.nout) dst[col0 + i] = o[i] * sc;
+                    for (int g = 0; g < MAXG; ++g) {
+                        const int n0 = (g_beg + g) * 8;
+                        if (g_beg + g < g_end) {
+                            if (n0 < a.ldpost)
+                                *reinterpret_cast<float4 *>(dst + n0) = make_float4(o[g * 8] * sc, o[g * 8 + 1] * sc, o[g * 8 + 2] * sc, o[g * 8 + 3] * sc);
+                            if (n0 + 4 < a.ldpost)
+                                *reinterpret_cast<float4 *>(dst + n0 + 4) = make_float4(o[g * 8 + 4] * sc, o[g * 8 + 5] * sc, o[g * 8 + 6] * sc, o[g * 8 + 7] * sc);
+                        }
+                    }
                 } else {
-                    // merger input: sLn(p), merger input normalisation, fp16, straight into the merger's X image
+                    // merger input: sLn(p), merger input normalisation, fp16, 16-byte chunks of the merger's X image
 #pragma unroll
-                    for (int i = 0; i < NH8 * 8; ++i) {
-                        const int n = col0 + i;
-                        if (n < a.nout) {
-                            const float p = o[i] * sc;
-                            const float v = p > 0.0f ? __logf(p) : 0.0f;
-                            const int cm = a.xm_col0 + n;
-                            const float xn = (v - __ldg(a.mmean + cm)) * __ldg(a.mdev + cm);
-                            uint8_t *blk = a.xm_img + ((size_t)tile * a.xm_kb1 + (cm >> 6)) * TC_BLK;
-                            *reinterpret_cast<__half *>(blk + sw128_off(row, cm & 63)) = __float2half_rn(xn);
+                    for (int g = 0; g < MAXG; ++g) {
+                        if (g_beg + g < g_end) {
+                            const int cm0 = a.xm_col0 + (g_beg + g) * 8;
+                            float xn[8];
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                const float p = o[g * 8 + i] * sc;
+                                const float v = p > 0.0f ? __logf(p) : 0.0f;
+                                xn[i] = (g_beg + g) * 8 + i < a.nout ? (v - a.mmean[cm0 + i]) * a.mdev[cm0 + i] : 0.0f;
+                            }
+                            uint8_t *blk = a.xm_img + ((size_t)tile * a.xm_kb1 + (cm0 >> 6)) * TC_BLK;
+                            const uint4 v = make_uint4(pack_half2(xn[0], xn[1]), pack_half2(xn[2], xn[3]), pack_half2(xn[4], xn[5]), pack_half2(xn[6], xn[7]));
+                            *reinterpret_cast<uint4 *>(blk + (size_t)row * 128 + ((((cm0 >> 3) & 7) ^ (row & 7)) << 4)) = v;
                         }
                     }
                 }
@@ -437,17 +477,30 @@ __global__ void __launch_bounds__(320, 1) k_mlp_tc(TcArgs a)
 struct TcNetImages {
     uint8_t *w1_img = nullptr, *w2_img = nullptr;
     float *sig_k = nullptr, *b2 = nullptr;
-    int KB1 = 0, NCH = 0, N2P = 0, nks_last = 4;
+    float *mean_img = nullptr, *dev_img = nullptr;   // merger only: input normalisation in image column order
+    int KB1 = 0, NCH = 0, N2P = 0, nks_last = 4, kin = 0;
 };
 
-__global__ void k_build_w1_img(const float *__restrict__ w1, int nin, int nhid, int nin4, uint8_t *img, int KB1, int NCH)
+// Image column k of the merger's layer 1 <- network input: the band-1 half starts at `split8`
+// (= band outputs rounded up to 8) so that both band nets write whole 16-byte chunks.
+__host__ __device__ __forceinline__ int img_col_to_input(int k, int split, int split8)
+{
+    if (split <= 0) return k;                 // band nets: identity
+    if (k < split) return k;
+    if (k < split8) return -1;
+    return k - split8 + split;
+}
+
+__global__ void k_build_w1_img(const float *__restrict__ w1, int nin, int nhid, int nin4, uint8_t *img, int KB1, int NCH,
+                               int split, int split8)
 {
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t total = (int64_t)NCH * 128 * KB1 * 64;
     if (idx >= total) return;
     const int k = (int)(idx % (KB1 * 64));
     const int n = (int)(idx / (KB1 * 64));
-    const float v = (n < nhid && k < nin) ? w1[(int64_t)n * nin4 + k] : 0.0f;
+    const int ki = img_col_to_input(k, split, split8);
+    const float v = (n < nhid && ki >= 0 && ki < nin) ? w1[(int64_t)n * nin4 + ki] : 0.0f;
     const int c = n >> 7, r = n & 127, kb = k >> 6, cc = k & 63;
     *reinterpret_cast<__half *>(img + ((size_t)c * KB1 + kb) * TC_BLK + sw128_off(r, cc)) = __float2half_rn(v);
 }
@@ -464,11 +517,22 @@ __global__ void k_build_w2_img(const float *__restrict__ w2, int nhid, int nout,
     *reinterpret_cast<__half *>(img + ((size_t)c * 2 + kb) * (N2P * 128) + sw128_off(n, cc)) = __float2half_rn(v);
 }
 
+__global__ void k_build_mnorm(const float *__restrict__ mean, const float *__restrict__ dev, int nin, float *mean_img,
+                              float *dev_img, int ncols, int split, int split8)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= ncols) return;
+    const int ki = img_col_to_input(k, split, split8);
+    mean_img[k] = (ki >= 0 && ki < nin) ? mean[ki] : 0.0f;
+    dev_img[k] = (ki >= 0 && ki < nin) ? dev[ki] : 0.0f;
+}
+
 __global__ void k_build_bias(const float *__restrict__ b1, int nhid, float *sig_k, int nhidP, const float *__restrict__ b2,
                              int nout, float *b2p, int N2P)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < nhidP) sig_k[i] = i < nhid ? (float)((double)kC32 - (double)kA32 * (double)b1[i]) : kC32;
+    // r = 2^23 + 2^14 * t,  t = -(x + b1)/ln2 + Ct : the addend must be an integer (ulp is 1 in [2^23, 2^24))
+    if (i < nhidP) sig_k[i] = (float)(8388608.0 + rint(16384.0 * (kCt - (double)(i < nhid ? b1[i] : 0.0f) / 0.69314718055994530942)));
     if (i < N2P) b2p[i] = i < nout ? b2[i] : 0.0f;
 }
 
@@ -485,10 +549,12 @@ int mlp_tc_prepare(phn_ctx *c)
     for (int i = 0; i < 3; ++i) {
         DevNet &n = c->net[i];
         TcNetImages &im = st.net[i];
-        im.KB1 = (n.nin + 63) / 64;
+        const int split = i == 2 ? c->net[0].nout : 0, split8 = (split + 7) / 8 * 8;
+        im.kin = i == 2 ? split8 + split : n.nin;   // image columns that carry data
+        im.KB1 = (im.kin + 63) / 64;
         im.NCH = (n.nhid + 127) / 128;
         im.N2P = (n.nout + 15) / 16 * 16;
-        const int rem = n.nin - (im.KB1 - 1) * 64;
+        const int rem = im.kin - (im.KB1 - 1) * 64;
         im.nks_last = (rem + 15) / 16;
         if (im.KB1 > 8) return fail(c, PHN_ERR_UNSUPPORTED, "tensor-core mode: more than 512 network inputs\n");
         if (im.N2P != 128 && im.N2P != 144 && im.N2P != 160 && im.N2P != 192)
@@ -499,7 +565,12 @@ int mlp_tc_prepare(phn_ctx *c)
         PHN_CUDA(c, cudaMalloc((void **)&im.sig_k, sizeof(float) * im.NCH * 128));
         PHN_CUDA(c, cudaMalloc((void **)&im.b2, sizeof(float) * im.N2P));
         const int64_t t1 = (int64_t)im.NCH * 128 * im.KB1 * 64, t2 = (int64_t)im.N2P * im.NCH * 128;
-        k_build_w1_img<<<(unsigned)((t1 + 255) / 256), 256, 0, c->stream>>>(n.w1, n.nin, n.nhid, n.nin4, im.w1_img, im.KB1, im.NCH);
+        k_build_w1_img<<<(unsigned)((t1 + 255) / 256), 256, 0, c->stream>>>(n.w1, n.nin, n.nhid, n.nin4, im.w1_img, im.KB1, im.NCH, split, split8);
+        if (i == 2) {
+            PHN_CUDA(c, cudaMalloc((void **)&im.mean_img, sizeof(float) * im.KB1 * 64));
+            PHN_CUDA(c, cudaMalloc((void **)&im.dev_img, sizeof(float) * im.KB1 * 64));
+            k_build_mnorm<<<(im.KB1 * 64 + 127) / 128, 128, 0, c->stream>>>(n.mean, n.dev, n.nin, im.mean_img, im.dev_img, im.KB1 * 64, split, split8);
+        }
         k_build_w2_img<<<(unsigned)((t2 + 255) / 256), 256, 0, c->stream>>>(n.w2, n.nhid, n.nout, n.nhid4, im.w2_img, im.N2P, im.NCH);
         const int nb = im.NCH * 128 > im.N2P ? im.NCH * 128 : im.N2P;
         k_build_bias<<<(nb + 255) / 256, 256, 0, c->stream>>>(n.b1, n.nhid, im.sig_k, im.NCH * 128, n.b2, n.nout, im.b2, im.N2P);
@@ -520,6 +591,8 @@ void mlp_tc_release(phn_ctx *c)
     for (auto &im : st->net) {
         if (im.sig_k) cudaFree(im.sig_k);
         if (im.b2) cudaFree(im.b2);
+        if (im.mean_img) cudaFree(im.mean_img);
+        if (im.dev_img) cudaFree(im.dev_img);
     }
     delete st;
     c->tc = nullptr;
@@ -529,7 +602,7 @@ template <int N2P>
 static int launch_one(phn_ctx *c, const TcArgs &a, size_t smem_bytes, int grid)
 {
     PHN_CUDA(c, cudaFuncSetAttribute(k_mlp_tc<N2P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
-    k_mlp_tc<N2P><<<grid, 320, smem_bytes, c->stream>>>(a);
+    k_mlp_tc<N2P><<<grid, TC_THREADS, smem_bytes, c->stream>>>(a);
     PHN_CUDA(c, cudaGetLastError());
     return PHN_OK;
 }
@@ -545,19 +618,26 @@ static int run_net_tc(phn_ctx *c, int which, const uint8_t *x_img, int64_t nf, i
     a.KB1 = im.KB1; a.NCH = im.NCH; a.nks_last = im.nks_last; a.nf = nf; a.nout = n.nout;
     if (which < 2) {
         a.post = nullptr;
-        a.xm_img = (uint8_t *)c->d_xmh.p; a.xm_kb1 = st.net[2].KB1; a.xm_col0 = which * n.nout;
-        a.mmean = c->net[2].mean; a.mdev = c->net[2].dev;
+        a.xm_img = (uint8_t *)c->d_xmh.p; a.xm_kb1 = st.net[2].KB1; a.xm_col0 = which * ((n.nout + 7) / 8 * 8);
+        a.mmean = st.net[2].mean_img; a.mdev = st.net[2].dev_img;
     } else {
-        a.post = (float *)c->d_post.p + f0 * n.nout; a.ldpost = n.nout;
+        a.post = (float *)c->d_post.p + f0 * c->ldp; a.ldpost = c->ldp;
     }
-    // shared memory plan: X (KB1 blocks) + W2 (2 blocks) + H (2 blocks) + barriers, rest = W1 ring
-    const size_t fixed = (size_t)im.KB1 * TC_BLK + 2 * (size_t)im.N2P * 128 + 2 * TC_BLK + 36 * 8 + 4 * 128 * 4 + 1024;
+    // shared memory plan: X (KB1 blocks) + H (2 blocks) + constants + barriers are fixed; the rest is split
+    // between the W2 ring (S2 k-blocks of N2P x 64) and the W1 ring (S1 blocks of 128 x 64)
+    const size_t w2_blk = (size_t)im.N2P * 128;
+    const size_t fixed = (size_t)im.KB1 * TC_BLK + 2 * TC_BLK + sizeof(float) * ((size_t)im.NCH * TC_NC + im.N2P + 4 * 128) + 48 * 8 + 1024;
     const size_t max_smem = 232448;
-    int S1 = (int)((max_smem - fixed) / TC_BLK);
+    int S1 = 0, S2 = 4;
+    for (; S2 >= 2; --S2) {
+        if (fixed + S2 * w2_blk + 2 * (size_t)TC_BLK > max_smem) continue;
+        S1 = (int)((max_smem - fixed - S2 * w2_blk) / TC_BLK);
+        if (S1 >= (S2 == 2 ? 2 : 4)) break;
+    }
+    if (S2 < 2 || S1 < 2) return fail(c, PHN_ERR_UNSUPPORTED, "tensor-core mode: shared memory plan does not fit\n");
     if (S1 > 8) S1 = 8;
-    if (S1 < 2) return fail(c, PHN_ERR_UNSUPPORTED, "tensor-core mode: shared memory plan does not fit\n");
-    a.S1 = S1;
-    const size_t smem_bytes = fixed + (size_t)S1 * TC_BLK;
+    a.S1 = S1; a.S2 = S2;
+    const size_t smem_bytes = fixed + (size_t)S1 * TC_BLK + (size_t)S2 * w2_blk;
     int grid = a.n_tiles < c->num_sms ? a.n_tiles : c->num_sms;
     if (const char *e = getenv("PHNREC_TC_GRID")) {  // debugging aid: force several tiles per CTA
         const int g = atoi(e);

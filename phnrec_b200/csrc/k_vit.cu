@@ -264,7 +264,7 @@ int launch_viterbi(phn_ctx *c, const float *d_pen, int n_pen)
     if (nseg == 0) return PHN_OK;
     VitArgs a;
     a.post = (const float *)c->d_post.p;
-    a.ncols = c->net[2].nout;
+    a.ncols = c->ldp;
     a.frame_off = (const int64_t *)c->d_frame_off.p;
     a.n_utt = c->n_utt; a.P = c->P; a.H = c->hist;
     a.total_frames = c->total_frames;
