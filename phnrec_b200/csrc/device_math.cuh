@@ -32,7 +32,14 @@ __constant__ double kLogfTab[16][2] = {
     {0x1.b2036576afce6p-1, 0x1.526e57720db08p-3},  {0x1.9c2d163a1aa2dp-1, 0x1.bc2860d22477p-3},
     {0x1.886e6037841edp-1, 0x1.1058bc8a07ee1p-2},  {0x1.767dcf5534862p-1, 0x1.4043057b6ee09p-2}};
 
-__device__ __forceinline__ float logf_glibc(float x)
+// The table is indexed per lane; __constant__ memory serialises divergent indices, so kernels on a
+// hot path copy it to shared memory once (logf_table_to_smem) and pass that pointer instead.
+__device__ __forceinline__ void logf_table_to_smem(double *dst /*[32]*/, int tid, int nthreads)
+{
+    for (int i = tid; i < 32; i += nthreads) dst[i] = kLogfTab[i >> 1][i & 1];
+}
+
+__device__ __forceinline__ float logf_glibc(float x, const double *tab /* [16][2] */)
 {
     const double Ln2 = 0x1.62e42fefa39efp-1;
     const double A0 = -0x1.00ea348b88334p-2, A1 = 0x1.5575b0be00b6ap-2, A2 = -0x1.ffffef20a4123p-2;
@@ -49,8 +56,8 @@ __device__ __forceinline__ float logf_glibc(float x)
     const int i = (tmp >> 19) & 15;
     const int k = (int32_t)tmp >> 23;
     const double z = (double)__uint_as_float(ix - (tmp & 0xff800000u));
-    const double r = __dsub_rn(__dmul_rn(z, kLogfTab[i][0]), 1.0);
-    const double y0 = __dadd_rn(kLogfTab[i][1], __dmul_rn((double)k, Ln2));
+    const double r = __dsub_rn(__dmul_rn(z, tab[2 * i]), 1.0);
+    const double y0 = __dadd_rn(tab[2 * i + 1], __dmul_rn((double)k, Ln2));
     const double r2 = __dmul_rn(r, r);
     double y = __dadd_rn(__dmul_rn(A1, r), A2);
     y = __dadd_rn(__dmul_rn(A0, r2), y);
@@ -59,7 +66,7 @@ __device__ __forceinline__ float logf_glibc(float x)
 }
 
 // sLn (dspc.h:155-160): guarded log, digital silence maps to 0.0 (not -inf)
-__device__ __forceinline__ float ln_guarded(float v) { return v > 0.0f ? logf_glibc(v) : 0.0f; }
+__device__ __forceinline__ float ln_guarded(float v, const double *tab) { return v > 0.0f ? logf_glibc(v, tab) : 0.0f; }
 
 // Canonical Quicknet/Schraudolph exp (fexp.h:14-21, low word := 0): a double whose high word is
 // trunc(2^20/ln2 * y) + (1023*2^20 - 60801).

@@ -130,7 +130,9 @@ __global__ void __launch_bounds__(256) k_l2_exact(L2Args a)
     __shared__ __align__(16) float As[L2_BK][L2_LDA];
     __shared__ __align__(16) float Bs[L2_BK][L2_LDB];
     __shared__ float So[L2_BM][L2_LDO];
-    __shared__ float s_max[L2_BM], s_sc[L2_BM];
+    __shared__ float s_sc[L2_BM];
+    __shared__ double s_logtab[32];
+    logf_table_to_smem(s_logtab, threadIdx.x, 256);
     const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
     const int64_t m0 = (int64_t)blockIdx.x * L2_BM;
 
@@ -225,10 +227,9 @@ __global__ void __launch_bounds__(256) k_l2_exact(L2Args a)
             a.post[f * a.ldpost + n] = p;
         } else {  // merger input: sLn then the merger's own input normalisation (traps.cpp:459, nn.cpp:702-716)
             const int c = a.xm_col0 + n;
-            a.xm[f * a.ldxm + c] = __fmul_rn(__fsub_rn(ln_guarded(p), a.mmean[c]), a.mdev[c]);
+            a.xm[f * a.ldxm + c] = __fmul_rn(__fsub_rn(ln_guarded(p, s_logtab), a.mmean[c]), a.mdev[c]);
         }
     }
-    (void)s_max;
 }
 
 static int run_net(phn_ctx *c, int which, const float *x, int ldx, int64_t nf, int64_t f0)

@@ -35,57 +35,101 @@ __device__ __forceinline__ int stc_find_utt(const int64_t *off, int n, int64_t f
     return lo;
 }
 
+constexpr int STC_F = 32;  // frames per CTA
+
+// One CTA = 32 consecutive frames of the chunk, both context sides.  Phase 1: one thread per
+// (frame, side, band) item computes the 11 normalised coefficients into a shared staging tile
+// [side][frame][nin].  Phase 2: the tile is written out coalesced - fp32 rows for the exact MLP,
+// or 16-byte chunks of the fp16 shared-memory image the tensor-core MLP loads by TMA.
 __global__ void __launch_bounds__(256) k_stc(StcArgs a)
 {
+    extern __shared__ float s_val[];          // [2][STC_F][nin]
     __shared__ float s_win[32];
     __shared__ float s_dct[160];
+    __shared__ int64_t s_u0[STC_F];
+    __shared__ int s_T[STC_F], s_u[STC_F];
+    const int nin = a.nb * a.ncoef;
+    const int64_t fl0 = (int64_t)blockIdx.x * STC_F;
     if (threadIdx.x < 32) s_win[threadIdx.x] = a.win[threadIdx.x];
     if (threadIdx.x < 160) s_dct[threadIdx.x] = a.dct[threadIdx.x];
+    if (threadIdx.x < STC_F) {
+        const int64_t fl = fl0 + threadIdx.x;
+        if (fl < a.nf) {
+            const int u = stc_find_utt(a.frame_off, a.n_utt, a.f0 + fl);
+            s_u[threadIdx.x] = u;
+            s_u0[threadIdx.x] = a.frame_off[u];
+            s_T[threadIdx.x] = (int)(a.frame_off[u + 1] - a.frame_off[u]);
+        } else {
+            s_u[threadIdx.x] = -1;
+        }
+    }
     __syncthreads();
 
     const int per_frame = 2 * a.nb;
-    const int64_t item = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (item >= a.nf * per_frame) return;
-    const int64_t fl = item / per_frame;          // frame within the chunk
-    const int rem = (int)(item - fl * per_frame);
-    const int side = rem / a.nb, b = rem - side * a.nb;
-    const int64_t f = a.f0 + fl;
-    const int u = stc_find_utt(a.frame_off, a.n_utt, f);
-    const int64_t u0 = a.frame_off[u], T = a.frame_off[u + 1] - u0, r = f - u0;
-    const float mu = a.mean[u * a.nb + b];
-
-    float x[16];
+    for (int item = threadIdx.x; item < STC_F * per_frame; item += blockDim.x) {
+        const int fi = item / per_frame;
+        const int rem = item - fi * per_frame;
+        const int side = rem / a.nb, b = rem - side * a.nb;
+        const int u = s_u[fi];
+        if (u < 0) continue;
+        const int64_t u0 = s_u0[fi];
+        const int T = s_T[fi];
+        const int r = (int)(a.f0 + fl0 + fi - u0);
+        const float mu = a.mean[u * a.nb + b];
+        float x[16];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-        int64_t t = r - 15 + j + (side ? 15 : 0);
-        t = t < 0 ? 0 : (t > T - 1 ? T - 1 : t);
-        const float v = __fsub_rn(a.mel[(u0 + t) * a.nb + b], mu);   // sentence mean normalisation
-        x[j] = __fmul_rn(v, s_win[side * 16 + j]);                   // traps.cpp:300-313
-    }
-    const float *nm = side ? a.nmean1 : a.nmean0;
-    const float *nd = side ? a.ndev1 : a.ndev0;
-    const int col0 = b * a.ncoef;
-    float *o32 = side ? a.x1 : a.x0;
-    uint8_t *o16 = side ? a.x1h : a.x0h;
-
-    for (int k = 0; k < a.ncoef; ++k) {
-        float s = 0.0f;
-        if (k == 0) {  // CalcC0 (dspc.h:223-233): plain sum, no 1/sqrt2
-#pragma unroll
-            for (int j = 0; j < 16; ++j) s = __fadd_rn(s, x[j]);
-        } else {       // sDCT (dspc.h:206-221): cos table row k-1
-#pragma unroll
-            for (int j = 0; j < 16; ++j) s = __fadd_rn(s, __fmul_rn(x[j], s_dct[(k - 1) * 16 + j]));
+        for (int j = 0; j < 16; ++j) {
+            int t = r - 15 + j + (side ? 15 : 0);
+            t = t < 0 ? 0 : (t > T - 1 ? T - 1 : t);
+            const float v = __fsub_rn(a.mel[(u0 + t) * a.nb + b], mu);   // sentence mean normalisation
+            x[j] = __fmul_rn(v, s_win[side * 16 + j]);                   // traps.cpp:300-313
         }
-        s = __fmul_rn(s, a.normc);
-        const int col = col0 + k;
-        const float xn = __fmul_rn(__fsub_rn(s, nm[col]), nd[col]);  // NeuralNet::Normalize nn.cpp:702-716
-        if (o32) o32[fl * a.ld32 + col] = xn;
-        if (o16) {  // [tile of 128 frames][64-column block][128 rows x 128 B, 16-byte chunks XOR-swizzled by row%8]
-            const int r = (int)(fl & 127), cc = col & 63;
-            uint8_t *blk = o16 + ((size_t)(fl >> 7) * a.kb1 + (col >> 6)) * 16384;
-            *reinterpret_cast<__half *>(blk + r * 128 + ((((unsigned)cc >> 3) ^ ((unsigned)r & 7u)) << 4) + (cc & 7) * 2) =
-                __float2half_rn(xn);
+        const float *nm = side ? a.nmean1 : a.nmean0;
+        const float *nd = side ? a.ndev1 : a.ndev0;
+        float *out = s_val + ((size_t)side * STC_F + fi) * nin + b * a.ncoef;
+        for (int k = 0; k < a.ncoef; ++k) {
+            float s = 0.0f;
+            if (k == 0) {  // CalcC0 (dspc.h:223-233): plain sum, no 1/sqrt2
+#pragma unroll
+                for (int j = 0; j < 16; ++j) s = __fadd_rn(s, x[j]);
+            } else {       // sDCT (dspc.h:206-221): cos table row k-1
+#pragma unroll
+                for (int j = 0; j < 16; ++j) s = __fadd_rn(s, __fmul_rn(x[j], s_dct[(k - 1) * 16 + j]));
+            }
+            s = __fmul_rn(s, a.normc);
+            const int col = b * a.ncoef + k;
+            out[k] = __fmul_rn(__fsub_rn(s, nm[col]), nd[col]);          // NeuralNet::Normalize nn.cpp:702-716
+        }
+    }
+    __syncthreads();
+
+    if (a.x0) {   // fp32 rows [fl][ld32]; padding columns stay zero from allocation
+        for (int q = threadIdx.x; q < 2 * STC_F * nin; q += blockDim.x) {
+            const int side = q / (STC_F * nin);
+            const int rem = q - side * STC_F * nin;
+            const int fi = rem / nin, col = rem - fi * nin;
+            if (fl0 + fi < a.nf) (side ? a.x1 : a.x0)[(fl0 + fi) * a.ld32 + col] = s_val[q];
+        }
+    } else {      // fp16 image: [tile of 128 frames][64-column block][128 rows x 128 B], chunk index XOR row%8
+        const int chunks_per_row = a.kb1 * 8;
+        for (int q = threadIdx.x; q < 2 * STC_F * chunks_per_row; q += blockDim.x) {
+            const int side = q / (STC_F * chunks_per_row);
+            const int rem = q - side * STC_F * chunks_per_row;
+            const int fi = rem / chunks_per_row, ch = rem - fi * chunks_per_row;
+            const int64_t fl = fl0 + fi;
+            if (fl >= a.nf) continue;
+            const float *src = s_val + ((size_t)side * STC_F + fi) * nin;
+            unsigned h[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int c0 = ch * 8 + 2 * i;
+                const __half2 p = __floats2half2_rn(c0 < nin ? src[c0] : 0.0f, c0 + 1 < nin ? src[c0 + 1] : 0.0f);
+                h[i] = *reinterpret_cast<const unsigned *>(&p);
+            }
+            const int r = (int)(fl & 127);
+            uint8_t *blk = (side ? a.x1h : a.x0h) + ((size_t)(fl >> 7) * a.kb1 + (ch >> 3)) * 16384;
+            *reinterpret_cast<uint4 *>(blk + r * 128 + ((((unsigned)ch & 7u) ^ ((unsigned)r & 7u)) << 4)) =
+                make_uint4(h[0], h[1], h[2], h[3]);
         }
     }
 }
@@ -110,8 +154,9 @@ int launch_stc(phn_ctx *c, int64_t f0, int64_t nf)
     a.x1h = tc ? (uint8_t *)c->d_x1h.p : nullptr;
     a.ld32 = c->net[0].kp;
     a.kb1 = c->net[0].k1P / 64;
-    const int64_t items = nf * 2 * c->nbanks;
-    k_stc<<<(unsigned)((items + 255) / 256), 256, 0, c->stream>>>(a);
+    const size_t smem = sizeof(float) * 2 * STC_F * (size_t)c->nbanks * c->ncoef;
+    PHN_CUDA(c, cudaFuncSetAttribute(k_stc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_stc<<<(unsigned)((nf + STC_F - 1) / STC_F), 256, smem, c->stream>>>(a);
     PHN_CUDA(c, cudaGetLastError());
     c->k_launches[PHN_K_STC] += 1;
     return PHN_OK;

@@ -64,6 +64,9 @@ __global__ void __launch_bounds__(32) k_viterbi(VitArgs a)
     float *halpha = a.r_halpha + rbase;
     const unsigned FULL = 0xffffffffu;
     const unsigned ORD_FLOOR = f2ord(-FLT_MAX);
+    __shared__ double s_logtab[32];
+    logf_table_to_smem(s_logtab, lane, 32);
+    __syncwarp();
 
     float al[PPL][4];
     int pv[PPL][4], ln[PPL][4];
@@ -94,7 +97,7 @@ __global__ void __launch_bounds__(32) k_viterbi(VitArgs a)
 #pragma unroll
             for (int r = 0; r < PPL; ++r)
 #pragma unroll
-                for (int j = 0; j < 3; ++j) obs[q][r][j] = logf_glibc(obs[q][r][j]);  // SoftLog, no guard
+                for (int j = 0; j < 3; ++j) obs[q][r][j] = logf_glibc(obs[q][r][j], s_logtab);  // SoftLog, no guard
 
 #pragma unroll
         for (int q = 0; q < FB; ++q) {

@@ -47,7 +47,9 @@ __global__ void __launch_bounds__(kWaveWarps * 32) k_wave(WaveArgs a)
     float *s_ham = reinterpret_cast<float *>(s_tw + N);             // [vs rounded to N]
     float *s_coef = s_ham + N;                                      // [N2]
     int *s_bank = reinterpret_cast<int *>(s_coef + N2);             // [N2]
-    float *s_work = reinterpret_cast<float *>(s_bank + N2);         // per warp: re[N] im[N] pw[N2]
+    double *s_logtab = reinterpret_cast<double *>(s_bank + N2);     // [32] glibc logf table
+    float *s_work = reinterpret_cast<float *>(s_logtab + 32);       // per warp: re[N] im[N] pw[N2]
+    logf_table_to_smem(s_logtab, threadIdx.x, blockDim.x);
 
     for (int i = threadIdx.x; i < N - 1; i += blockDim.x) s_tw[i] = a.tw[i];
     for (int i = threadIdx.x; i < N; i += blockDim.x) s_ham[i] = i < a.vs ? a.hamming[i] : 0.0f;
@@ -149,7 +151,7 @@ __global__ void __launch_bounds__(kWaveWarps * 32) k_wave(WaveArgs a)
                 const float v = __fmul_rn(s_coef[k], p);
                 acc = __fadd_rn(acc, s_bank[k] == lane ? __fsub_rn(p, v) : v);
             }
-            float o = ln_guarded(acc);
+            float o = ln_guarded(acc, s_logtab);
             if (a.frame_shift != 0.0f) o = __fadd_rn(o, a.frame_shift);           // srec.cpp:1594-1620
             if (a.frame_floor != -9999.9f && o < a.frame_floor) o = a.frame_floor;
             a.mel[f * a.nbanks + lane] = o;
@@ -174,7 +176,7 @@ int launch_wave(phn_ctx *c, const void *d_audio)
     a.klo = c->tab.bank_klo; a.khi = c->tab.bank_khi; a.tw = c->tab.tw;
     a.mel = (float *)c->d_mel.p;
     const int N = a.N, N2 = N / 2;
-    const size_t smem = sizeof(double2) * N + sizeof(float) * (N + N2) + sizeof(int) * N2 +
+    const size_t smem = sizeof(double2) * N + sizeof(float) * (N + N2) + sizeof(int) * N2 + sizeof(double) * 32 +
                         sizeof(float) * (size_t)kWaveWarps * (2 * N + N2);
     PHN_CUDA(c, cudaFuncSetAttribute(k_wave, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int64_t blocks = (c->total_frames + kWaveWarps - 1) / kWaveWarps;
