@@ -583,7 +583,10 @@ int phn_mel(phn_ctx *c, const void *audio, const int64_t *byte_off, int n_utt, f
     if ((rc = ensure(c, c->d_audio, (size_t)c->total_bytes + 16))) return rc;
     if (c->total_bytes)
         PHN_CUDA(c, cudaMemcpyAsync(c->d_audio.p, audio, (size_t)c->total_bytes, cudaMemcpyHostToDevice, c->stream));
-    { StageTimer t(c, PHN_K_WAVE); if ((rc = launch_wave(c, c->d_audio.p))) return rc; }
+    c->force_exact_wave = 1;
+    { StageTimer t(c, PHN_K_WAVE); rc = launch_wave(c, c->d_audio.p); }
+    c->force_exact_wave = 0;
+    if (rc) return rc;
     return phn_fetch_mel(c, mel_out);
 }
 

@@ -38,9 +38,13 @@ __device__ __forceinline__ int stc_find_utt(const int64_t *off, int n, int64_t f
 constexpr int STC_F = 32;  // frames per CTA
 
 // One CTA = 32 consecutive frames of the chunk, both context sides.  Phase 1: one thread per
-// (frame, side, band) item computes the 11 normalised coefficients into a shared staging tile
-// [side][frame][nin].  Phase 2: the tile is written out coalesced - fp32 rows for the exact MLP,
-// or 16-byte chunks of the fp16 shared-memory image the tensor-core MLP loads by TMA.
+// (group of 4 frames, side, band) keeps the 4 x 16 windowed samples in registers and walks the
+// 11 output coefficients, so every DCT-table word fetched from shared memory feeds 4 products.
+// EXACT: separately rounded multiply / add in the reference's order (bit-identical features);
+// otherwise FMAs (the tensor-core MLP rounds its inputs to fp16 anyway).
+// Phase 2: the staging tile [side][frame][nin] is written out coalesced - fp32 rows for the exact
+// MLP, or 16-byte chunks of the fp16 shared-memory image the tensor-core MLP loads by TMA.
+template <bool EXACT>
 __global__ void __launch_bounds__(256) k_stc(StcArgs a)
 {
     extern __shared__ float s_val[];          // [2][STC_F][nin]
@@ -65,40 +69,52 @@ __global__ void __launch_bounds__(256) k_stc(StcArgs a)
     }
     __syncthreads();
 
-    const int per_frame = 2 * a.nb;
-    for (int item = threadIdx.x; item < STC_F * per_frame; item += blockDim.x) {
-        const int fi = item / per_frame;
-        const int rem = item - fi * per_frame;
+    const int per_group = 2 * a.nb;
+    for (int item = threadIdx.x; item < (STC_F / 4) * per_group; item += blockDim.x) {
+        const int grp = item / per_group;
+        const int rem = item - grp * per_group;
         const int side = rem / a.nb, b = rem - side * a.nb;
-        const int u = s_u[fi];
-        if (u < 0) continue;
-        const int64_t u0 = s_u0[fi];
-        const int T = s_T[fi];
-        const int r = (int)(a.f0 + fl0 + fi - u0);
-        const float mu = a.mean[u * a.nb + b];
-        float x[16];
+        float x[4][16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            int t = r - 15 + j + (side ? 15 : 0);
-            t = t < 0 ? 0 : (t > T - 1 ? T - 1 : t);
-            const float v = __fsub_rn(a.mel[(u0 + t) * a.nb + b], mu);   // sentence mean normalisation
-            x[j] = __fmul_rn(v, s_win[side * 16 + j]);                   // traps.cpp:300-313
+        for (int f = 0; f < 4; ++f) {
+            const int fi = grp * 4 + f;
+            const int u = s_u[fi];
+            const int64_t u0 = u < 0 ? 0 : s_u0[fi];
+            const int T = u < 0 ? 1 : s_T[fi];
+            const int r = (int)(a.f0 + fl0 + fi - u0);
+            const float mu = u < 0 ? 0.0f : a.mean[u * a.nb + b];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                int t = r - 15 + j + (side ? 15 : 0);
+                t = t < 0 ? 0 : (t > T - 1 ? T - 1 : t);
+                const float v = u < 0 ? 0.0f : __fsub_rn(a.mel[(u0 + t) * a.nb + b], mu);  // sentence mean normalisation
+                x[f][j] = __fmul_rn(v, s_win[side * 16 + j]);                             // traps.cpp:300-313
+            }
         }
         const float *nm = side ? a.nmean1 : a.nmean0;
         const float *nd = side ? a.ndev1 : a.ndev0;
-        float *out = s_val + ((size_t)side * STC_F + fi) * nin + b * a.ncoef;
+        float *out = s_val + ((size_t)side * STC_F + grp * 4) * nin + b * a.ncoef;
         for (int k = 0; k < a.ncoef; ++k) {
-            float s = 0.0f;
+            float s[4] = {0.0f, 0.0f, 0.0f, 0.0f};
             if (k == 0) {  // CalcC0 (dspc.h:223-233): plain sum, no 1/sqrt2
 #pragma unroll
-                for (int j = 0; j < 16; ++j) s = __fadd_rn(s, x[j]);
+                for (int j = 0; j < 16; ++j)
+#pragma unroll
+                    for (int f = 0; f < 4; ++f) s[f] = __fadd_rn(s[f], x[f][j]);
             } else {       // sDCT (dspc.h:206-221): cos table row k-1
 #pragma unroll
-                for (int j = 0; j < 16; ++j) s = __fadd_rn(s, __fmul_rn(x[j], s_dct[(k - 1) * 16 + j]));
+                for (int j = 0; j < 16; ++j) {
+                    const float cs = s_dct[(k - 1) * 16 + j];
+#pragma unroll
+                    for (int f = 0; f < 4; ++f)
+                        s[f] = EXACT ? __fadd_rn(s[f], __fmul_rn(x[f][j], cs)) : fmaf(x[f][j], cs, s[f]);
+                }
             }
-            s = __fmul_rn(s, a.normc);
             const int col = b * a.ncoef + k;
-            out[k] = __fmul_rn(__fsub_rn(s, nm[col]), nd[col]);          // NeuralNet::Normalize nn.cpp:702-716
+            const float m = nm[col], d = nd[col];
+#pragma unroll
+            for (int f = 0; f < 4; ++f)  // NeuralNet::Normalize nn.cpp:702-716
+                out[(size_t)f * nin + k] = __fmul_rn(__fsub_rn(__fmul_rn(s[f], a.normc), m), d);
         }
     }
     __syncthreads();
@@ -155,8 +171,14 @@ int launch_stc(phn_ctx *c, int64_t f0, int64_t nf)
     a.ld32 = c->net[0].kp;
     a.kb1 = c->net[0].k1P / 64;
     const size_t smem = sizeof(float) * 2 * STC_F * (size_t)c->nbanks * c->ncoef;
-    PHN_CUDA(c, cudaFuncSetAttribute(k_stc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_stc<<<(unsigned)((nf + STC_F - 1) / STC_F), 256, smem, c->stream>>>(a);
+    const unsigned grid = (unsigned)((nf + STC_F - 1) / STC_F);
+    if (tc) {
+        PHN_CUDA(c, cudaFuncSetAttribute(k_stc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_stc<false><<<grid, 256, smem, c->stream>>>(a);
+    } else {
+        PHN_CUDA(c, cudaFuncSetAttribute(k_stc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_stc<true><<<grid, 256, smem, c->stream>>>(a);
+    }
     PHN_CUDA(c, cudaGetLastError());
     c->k_launches[PHN_K_STC] += 1;
     return PHN_OK;

@@ -4,10 +4,14 @@
 // (melbanks.cpp:111-204), cFour1 / _mbApply (dspc.cpp:24-78, 236-269), cPower / sLn (dspc.h:141-160)
 // and FrameBasedNormalization (srec.cpp:1594-1620) for a ragged batch of utterances.
 //
-// One warp owns one frame at a time; the frame lives in that warp's shared-memory slice
-// (re[N], im[N]).  The FFT is the reference's radix-2 decimation-in-time with the reference's
-// double-precision twiddles (built on the host by the same recurrence) and the reference's
-// rounding points, so mel values are bit-identical to the CPU implementation.
+// One warp owns one frame at a time.  The N-point FFT is the reference's radix-2
+// decimation-in-time, regrouped into register passes of three stages (radix 8; the last pass is
+// radix N/64) with two shared-memory transposes in between; each lane fetches its own samples
+// straight from the audio in bit-reversed order.  Butterflies are independent within a stage, so
+// regrouping changes no rounding: in the EXACT instantiation (reference twiddles in double, built
+// on the host by the same recurrence, and the reference's rounding points) mel values are
+// bit-identical to the CPU implementation.  The !EXACT instantiation (tensor-core pipeline) uses
+// fp32 FMAs.
 #include "internal.h"
 #include "device_math.cuh"
 
@@ -39,28 +43,78 @@ __device__ __forceinline__ int find_utt(const int64_t *off, int n, int64_t f)
     return lo;
 }
 
+// One radix-2 butterfly of cFour1 (dspc.cpp:55-76) on (lo, up) = (element i, element i+h).
+// EXACT: the reference's arithmetic - twiddle in double, products and their sum/difference rounded
+// in double, one rounding to float, then float add/sub.  Twiddle (1, 0) needs no arithmetic at all:
+// fl32(fl64(1*x) - fl64(0*y)) == x (up to the sign of a zero, which |X|^2 cannot see).
+// !EXACT: plain fp32 FMAs.
+template <bool EXACT>
+__device__ __forceinline__ void bfly(float2 &lo, float2 &up, const double2 w, const bool trivial)
+{
+    float tr, ti;
+    if (trivial) {
+        tr = up.x; ti = up.y;
+    } else if (EXACT) {
+        const double kr = (double)up.x, ki = (double)up.y;
+        tr = __double2float_rn(__dsub_rn(__dmul_rn(w.x, kr), __dmul_rn(w.y, ki)));
+        ti = __double2float_rn(__dadd_rn(__dmul_rn(w.x, ki), __dmul_rn(w.y, kr)));
+    } else {
+        const float wr = (float)w.x, wi = (float)w.y;
+        tr = fmaf(wr, up.x, -wi * up.y);
+        ti = fmaf(wr, up.y, wi * up.x);
+    }
+    up.x = __fsub_rn(lo.x, tr); up.y = __fsub_rn(lo.y, ti);
+    lo.x = __fadd_rn(lo.x, tr); lo.y = __fadd_rn(lo.y, ti);
+}
+
+// LEVELS consecutive radix-2 stages on R = 2^LEVELS elements held in registers.
+// v[r] is element e = base + S*r of the length-N array; stage half-sizes S, 2S, 4S.
+// Twiddle of the pair (e, e+h) is tw[h-1 + (e mod h)], e mod h = base_mod + S*(r mod hh).
+template <bool EXACT, int LEVELS>
+__device__ __forceinline__ void fft_pass(float2 *v, const double2 *s_tw, int S, int base_mod)
+{
+    constexpr int R = 1 << LEVELS;
+#pragma unroll
+    for (int lv = 0; lv < LEVELS; ++lv) {
+        const int hh = 1 << lv;
+        const int h = S * hh;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            if (r & hh) continue;
+            const int m = base_mod + S * (r & (hh - 1));
+            bfly<EXACT>(v[r], v[r + hh], s_tw[h - 1 + m], m == 0);
+        }
+    }
+}
+
+__device__ __forceinline__ int pad_idx(int e) { return e + (e >> 5); }  // breaks the stride-8/64 bank patterns
+
+template <bool EXACT, int LOGN>
 __global__ void __launch_bounds__(kWaveWarps * 32) k_wave(WaveArgs a)
 {
+    constexpr int N = 1 << LOGN, N2 = N / 2;
+    constexpr int OCT = N / 256;            // octets per lane in passes 1 and 2 (1 or 2)
+    constexpr int L3 = LOGN - 6;            // levels of the last pass (2 or 3)
+    constexpr int R3 = 1 << L3;             // its radix (4 or 8); N/R3 = 64 groups -> 2 per lane
+    constexpr int WORK = N + N / 32 + N2 / 2;  // float2 units per warp: padded data[] + pw[N2]
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int N = a.N, N2 = N / 2;
     double2 *s_tw = reinterpret_cast<double2 *>(smem_raw);          // [N-1] (+1 pad)
-    float *s_ham = reinterpret_cast<float *>(s_tw + N);             // [vs rounded to N]
+    float *s_ham = reinterpret_cast<float *>(s_tw + N);             // [N], zero beyond vs
     float *s_coef = s_ham + N;                                      // [N2]
     int *s_bank = reinterpret_cast<int *>(s_coef + N2);             // [N2]
     double *s_logtab = reinterpret_cast<double *>(s_bank + N2);     // [32] glibc logf table
-    float *s_work = reinterpret_cast<float *>(s_logtab + 32);       // per warp: re[N] im[N] pw[N2]
+    float2 *s_work = reinterpret_cast<float2 *>(s_logtab + 32);
     logf_table_to_smem(s_logtab, threadIdx.x, blockDim.x);
-
     for (int i = threadIdx.x; i < N - 1; i += blockDim.x) s_tw[i] = a.tw[i];
     for (int i = threadIdx.x; i < N; i += blockDim.x) s_ham[i] = i < a.vs ? a.hamming[i] : 0.0f;
     for (int i = threadIdx.x; i < N2; i += blockDim.x) { s_coef[i] = a.coeffs[i]; s_bank[i] = a.banks[i]; }
     __syncthreads();
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float *re = s_work + (size_t)warp * (2 * N + N2);
-    float *im = re + N;
-    float *pw = im + N;
+    float2 *data = s_work + (size_t)warp * WORK;
+    float *pw = reinterpret_cast<float *>(data + N + N / 32);
     const int bps = a.fmt == PHN_WAVE_LIN16 ? 2 : 1;
+    const bool plain = !a.z_mean && a.preem == 0.0f;
 
     for (int64_t f = (int64_t)blockIdx.x * kWaveWarps + warp; f < a.total_frames; f += (int64_t)gridDim.x * kWaveWarps) {
         const int u = find_utt(a.frame_off, a.n_utt, f);
@@ -69,8 +123,7 @@ __global__ void __launch_bounds__(kWaveWarps * 32) k_wave(WaveArgs a)
         const int64_t len = (a.byte_off[u + 1] - b0) / bps;  // samples in this utterance
         const int64_t s0 = t * a.step;
 
-        // ---- decode (srec.cpp:742-743 / 768-769), dc shift, scale; zero beyond the signal
-        for (int i = lane; i < N; i += 32) {
+        auto sample = [&](int i) -> float {  // decode (srec.cpp:742-743 / 768-769), dc shift, scale; 0 beyond the signal
             float x = 0.0f;
             if (i < a.vs && s0 + i < len) {
                 if (a.fmt == PHN_WAVE_LIN16) {
@@ -82,64 +135,99 @@ __global__ void __launch_bounds__(kWaveWarps * 32) k_wave(WaveArgs a)
                 if (a.dc_shift != 0.0f) x = __fadd_rn(x, a.dc_shift);
                 if (a.scale != 1.0f) x = __fmul_rn(x, a.scale);
             }
-            if (a.z_mean || a.preem != 0.0f) im[i] = x;  // staging for the optional per-frame ops
-            else re[__brev((unsigned)i) >> (32 - a.logN)] = i < a.vs ? __fmul_rn(x, s_ham[i]) : 0.0f;
-        }
-        if (a.z_mean || a.preem != 0.0f) {
-            // optional sSubtractAverage / sPreemphasis (dspc.h:63-84); not used by the shipped systems
+            return x;
+        };
+
+        float *stage = reinterpret_cast<float *>(data);  // N floats; data[] is free until pass 1 stores
+        if (!plain) {
+            // optional sSubtractAverage / sPreemphasis (dspc.h:63-84), not used by the shipped systems
+            for (int i = lane; i < N; i += 32) stage[i] = sample(i);
             __syncwarp();
             float avg = 0.0f;
             if (a.z_mean) {
                 if (lane == 0) {
                     float s = 0.0f;
-                    for (int i = 0; i < a.vs; ++i) s = __fadd_rn(s, im[i]);
+                    for (int i = 0; i < a.vs; ++i) s = __fadd_rn(s, stage[i]);
                     pw[0] = __fdiv_rn(s, (float)a.vs);
                 }
                 __syncwarp();
                 avg = pw[0];
                 __syncwarp();
             }
-            for (int i = lane; i < N; i += 32) {
+            float y[N / 32];
+#pragma unroll
+            for (int q = 0; q < N / 32; ++q) {
+                const int i = lane + 32 * q;
                 float x = 0.0f;
                 if (i < a.vs) {
-                    x = a.z_mean ? __fsub_rn(im[i], avg) : im[i];
+                    x = a.z_mean ? __fsub_rn(stage[i], avg) : stage[i];
                     if (a.preem != 0.0f) {
                         if (i == 0) x = __fmul_rn(x, __fsub_rn(1.0f, a.preem));
                         else {
-                            const float xp = a.z_mean ? __fsub_rn(im[i - 1], avg) : im[i - 1];
+                            const float xp = a.z_mean ? __fsub_rn(stage[i - 1], avg) : stage[i - 1];
                             x = __fsub_rn(x, __fmul_rn(a.preem, xp));
                         }
                     }
-                    x = __fmul_rn(x, s_ham[i]);
                 }
-                re[__brev((unsigned)i) >> (32 - a.logN)] = x;
+                y[q] = x;
             }
             __syncwarp();
+#pragma unroll
+            for (int q = 0; q < N / 32; ++q) stage[lane + 32 * q] = y[q];
+            __syncwarp();
         }
-        for (int i = lane; i < N; i += 32) im[i] = 0.0f;
+
+        // ---- pass 1 (stages h = 1, 2, 4): elements 8o .. 8o+7 = windowed inputs at bit-reversed positions
+        float2 v[OCT][8];
+#pragma unroll
+        for (int oc = 0; oc < OCT; ++oc) {
+            const int o = lane + 32 * oc;
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                const int i = (int)(__brev((unsigned)(8 * o + r)) >> (32 - LOGN));
+                const float x = plain ? sample(i) : stage[i];
+                v[oc][r] = make_float2(__fmul_rn(x, s_ham[i]), 0.0f);
+            }
+        }
+        if (!plain) __syncwarp();
+#pragma unroll
+        for (int oc = 0; oc < OCT; ++oc) {
+            const int o = lane + 32 * oc;
+            fft_pass<EXACT, 3>(v[oc], s_tw, 1, 0);
+#pragma unroll
+            for (int r = 0; r < 8; ++r) data[pad_idx(8 * o + r)] = v[oc][r];
+        }
         __syncwarp();
-
-        // ---- radix-2 DIT butterflies, stage half-size h = 1 .. N/2 (dspc.cpp:55-76)
-        for (int h = 1; h < N; h <<= 1) {
-            for (int j = lane; j < N2; j += 32) {
-                const int m = j & (h - 1);
-                const int i0 = ((j - m) << 1) + m;
-                const int k0 = i0 + h;
-                const double2 w = s_tw[h - 1 + m];
-                const double kr = (double)re[k0], ki = (double)im[k0];
-                const float tr = __double2float_rn(__dsub_rn(__dmul_rn(w.x, kr), __dmul_rn(w.y, ki)));
-                const float ti = __double2float_rn(__dadd_rn(__dmul_rn(w.x, ki), __dmul_rn(w.y, kr)));
-                const float ir = re[i0], ii = im[i0];
-                re[k0] = __fsub_rn(ir, tr);
-                im[k0] = __fsub_rn(ii, ti);
-                re[i0] = __fadd_rn(ir, tr);
-                im[i0] = __fadd_rn(ii, ti);
-            }
-            __syncwarp();
+        // ---- pass 2 (h = 8, 16, 32): elements low3 + 8r + 64*high
+#pragma unroll
+        for (int oc = 0; oc < OCT; ++oc) {
+            const int o = lane + 32 * oc;
+            const int low3 = o & 7, high = o >> 3;
+#pragma unroll
+            for (int r = 0; r < 8; ++r) v[oc][r] = data[pad_idx(low3 + 8 * r + 64 * high)];
         }
-
-        // ---- power spectrum (dspc.h:141-146), bins 0 .. N/2-1
-        for (int k = lane; k < N2; k += 32) pw[k] = __fadd_rn(__fmul_rn(re[k], re[k]), __fmul_rn(im[k], im[k]));
+        __syncwarp();
+#pragma unroll
+        for (int oc = 0; oc < OCT; ++oc) {
+            const int o = lane + 32 * oc;
+            const int low3 = o & 7, high = o >> 3;
+            fft_pass<EXACT, 3>(v[oc], s_tw, 8, low3);
+#pragma unroll
+            for (int r = 0; r < 8; ++r) data[pad_idx(low3 + 8 * r + 64 * high)] = v[oc][r];
+        }
+        __syncwarp();
+        // ---- pass 3 (h = 64 .. N/2): elements low6 + 64r, two groups per lane; then |X|^2 of bins < N/2
+#pragma unroll
+        for (int gq = 0; gq < 2; ++gq) {
+            const int low6 = lane + 32 * gq;
+            float2 w3[R3];
+#pragma unroll
+            for (int r = 0; r < R3; ++r) w3[r] = data[pad_idx(low6 + 64 * r)];
+            fft_pass<EXACT, L3>(w3, s_tw, 64, low6);
+#pragma unroll
+            for (int r = 0; r < R3 / 2; ++r)   // cPower (dspc.h:141-146)
+                pw[low6 + 64 * r] = __fadd_rn(__fmul_rn(w3[r].x, w3[r].x), __fmul_rn(w3[r].y, w3[r].y));
+        }
         __syncwarp();
 
         // ---- mel filterbank (dspc.cpp:236-269): lane b accumulates bank b in ascending bin order
@@ -148,8 +236,8 @@ __global__ void __launch_bounds__(kWaveWarps * 32) k_wave(WaveArgs a)
             const int hi = a.khi[lane];
             for (int k = a.klo[lane]; k <= hi; ++k) {
                 const float p = pw[k];
-                const float v = __fmul_rn(s_coef[k], p);
-                acc = __fadd_rn(acc, s_bank[k] == lane ? __fsub_rn(p, v) : v);
+                const float v2 = __fmul_rn(s_coef[k], p);
+                acc = __fadd_rn(acc, s_bank[k] == lane ? __fsub_rn(p, v2) : v2);
             }
             float o = ln_guarded(acc, s_logtab);
             if (a.frame_shift != 0.0f) o = __fadd_rn(o, a.frame_shift);           // srec.cpp:1594-1620
@@ -158,6 +246,21 @@ __global__ void __launch_bounds__(kWaveWarps * 32) k_wave(WaveArgs a)
         }
         __syncwarp();
     }
+}
+
+template <bool EXACT, int LOGN>
+static int launch_wave_t(phn_ctx *c, const WaveArgs &a)
+{
+    constexpr int N = 1 << LOGN, N2 = N / 2;
+    const size_t smem = sizeof(double2) * N + sizeof(float) * (N + N2) + sizeof(int) * N2 + sizeof(double) * 32 +
+                        sizeof(float2) * (size_t)kWaveWarps * (N + N / 32 + N2 / 2);
+    PHN_CUDA(c, cudaFuncSetAttribute(k_wave<EXACT, LOGN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int64_t blocks = (c->total_frames + kWaveWarps - 1) / kWaveWarps;
+    const int64_t cap = (int64_t)c->num_sms * 6;
+    if (blocks > cap) blocks = cap;
+    k_wave<EXACT, LOGN><<<(unsigned)blocks, kWaveWarps * 32, smem, c->stream>>>(a);
+    PHN_CUDA(c, cudaGetLastError());
+    return PHN_OK;
 }
 
 int launch_wave(phn_ctx *c, const void *d_audio)
@@ -175,15 +278,17 @@ int launch_wave(phn_ctx *c, const void *d_audio)
     a.hamming = c->tab.hamming; a.coeffs = c->tab.coeffs; a.banks = c->tab.banks;
     a.klo = c->tab.bank_klo; a.khi = c->tab.bank_khi; a.tw = c->tab.tw;
     a.mel = (float *)c->d_mel.p;
-    const int N = a.N, N2 = N / 2;
-    const size_t smem = sizeof(double2) * N + sizeof(float) * (N + N2) + sizeof(int) * N2 + sizeof(double) * 32 +
-                        sizeof(float) * (size_t)kWaveWarps * (2 * N + N2);
-    PHN_CUDA(c, cudaFuncSetAttribute(k_wave, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int64_t blocks = (c->total_frames + kWaveWarps - 1) / kWaveWarps;
-    const int64_t cap = (int64_t)c->num_sms * 8;
-    if (blocks > cap) blocks = cap;
-    k_wave<<<(unsigned)blocks, kWaveWarps * 32, smem, c->stream>>>(a);
-    PHN_CUDA(c, cudaGetLastError());
+    // The exact instantiation always serves the stage-wise API (phn_mel: what `-t par` saves must be
+    // the reference's bits); the fused tensor-core pipeline takes the fp32 one.
+    const bool exact = c->mlp_mode != PHN_MLP_TC_F16 || c->force_exact_wave;
+    int rc;
+    switch (c->mt.logN) {
+        case 8: rc = exact ? launch_wave_t<true, 8>(c, a) : launch_wave_t<false, 8>(c, a); break;
+        case 9: rc = exact ? launch_wave_t<true, 9>(c, a) : launch_wave_t<false, 9>(c, a); break;
+        case 10: rc = exact ? launch_wave_t<true, 10>(c, a) : launch_wave_t<false, 10>(c, a); break;
+        default: return fail(c, PHN_ERR_UNSUPPORTED, "FFT size %d not instantiated (vector_size must be 129..1024)\n", c->mt.N);
+    }
+    if (rc) return rc;
     c->k_launches[PHN_K_WAVE] += 1;
     return PHN_OK;
 }
