@@ -377,7 +377,7 @@ void phn_destroy(phn_ctx *c)
     }
     phn_ctx::Buf *bufs[] = {&c->d_audio, &c->d_byte_off, &c->d_frame_off, &c->d_lab_off, &c->d_mel, &c->d_mean, &c->d_post,
                             &c->d_rec, &c->d_labels, &c->d_nlab, &c->d_pen, &c->d_x0, &c->d_x1, &c->d_h, &c->d_xm,
-                            &c->d_x0h, &c->d_x1h, &c->d_xmh, &c->d_tile_ctr, &c->d_coff, &c->d_labels_c};
+                            &c->d_x0h, &c->d_x1h, &c->d_xmh, &c->d_tile_ctr, &c->d_coff, &c->d_labels_c, &c->d_logp};
     for (auto *b : bufs)
         if (b->p) cudaFree(b->p);
     mlp_tc_release(c);

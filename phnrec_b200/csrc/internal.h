@@ -90,7 +90,7 @@ struct phn_ctx {
     struct Buf { void *p = nullptr; size_t cap = 0; };
     Buf d_audio, d_byte_off, d_frame_off, d_lab_off, d_mel, d_mean, d_post, d_rec, d_labels, d_nlab, d_pen;
     Buf d_x0, d_x1, d_h, d_xm, d_x0h, d_x1h, d_xmh;  // MLP workspace (per frame chunk)
-    Buf d_tile_ctr, d_coff, d_labels_c;
+    Buf d_tile_ctr, d_coff, d_labels_c, d_logp;
     std::vector<int32_t> h_nlab;
     std::vector<float> h_pen;
     int64_t chunk_frames = 0;

@@ -17,6 +17,7 @@ struct StcArgs {
     const int64_t *frame_off;
     int n_utt, nb, ncoef;
     int64_t f0, nf;   // frame chunk [f0, f0+nf)
+    int64_t total_frames;
     const float *win, *dct;
     const float *nmean0, *ndev0, *nmean1, *ndev1;
     float normc;
@@ -52,8 +53,16 @@ __global__ void __launch_bounds__(256) k_stc(StcArgs a)
     __shared__ float s_dct[160];
     __shared__ int64_t s_u0[STC_F];
     __shared__ int s_T[STC_F], s_u[STC_F];
+    __shared__ float s_mel[(STC_F + 30) * 32];   // mel rows G0-15 .. G0+STC_F+14 (nb <= 32)
     const int nin = a.nb * a.ncoef;
     const int64_t fl0 = (int64_t)blockIdx.x * STC_F;
+    // A clamped context index always lies between the frame itself and the unclamped index, so every
+    // row any of the 32 frames needs is inside this window of the global frame axis.
+    const int64_t G0 = a.f0 + fl0 - 15;
+    for (int q = threadIdx.x; q < (STC_F + 30) * a.nb; q += blockDim.x) {
+        const int64_t g = G0 + q / a.nb;
+        s_mel[q] = (g >= 0 && g < a.total_frames) ? a.mel[G0 * a.nb + q] : 0.0f;
+    }
     if (threadIdx.x < 32) s_win[threadIdx.x] = a.win[threadIdx.x];
     if (threadIdx.x < 160) s_dct[threadIdx.x] = a.dct[threadIdx.x];
     if (threadIdx.x < STC_F) {
@@ -87,7 +96,7 @@ __global__ void __launch_bounds__(256) k_stc(StcArgs a)
             for (int j = 0; j < 16; ++j) {
                 int t = r - 15 + j + (side ? 15 : 0);
                 t = t < 0 ? 0 : (t > T - 1 ? T - 1 : t);
-                const float v = u < 0 ? 0.0f : __fsub_rn(a.mel[(u0 + t) * a.nb + b], mu);  // sentence mean normalisation
+                const float v = u < 0 ? 0.0f : __fsub_rn(s_mel[(int)(u0 + t - G0) * a.nb + b], mu);  // sentence mean normalisation
                 x[f][j] = __fmul_rn(v, s_win[side * 16 + j]);                             // traps.cpp:300-313
             }
         }
@@ -158,7 +167,7 @@ int launch_stc(phn_ctx *c, int64_t f0, int64_t nf)
     a.mean = (const float *)c->d_mean.p;
     a.frame_off = (const int64_t *)c->d_frame_off.p;
     a.n_utt = c->n_utt; a.nb = c->nbanks; a.ncoef = c->ncoef;
-    a.f0 = f0; a.nf = nf;
+    a.f0 = f0; a.nf = nf; a.total_frames = c->total_frames;
     a.win = c->tab.win; a.dct = c->tab.dct;
     a.nmean0 = c->net[0].mean; a.ndev0 = c->net[0].dev;
     a.nmean1 = c->net[1].mean; a.ndev1 = c->net[1].dev;

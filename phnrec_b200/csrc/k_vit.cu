@@ -24,7 +24,7 @@
 namespace phn {
 
 struct VitArgs {
-    const float *post;       // [total_frames][ncols] linear posteriors
+    const float *logp;       // [total_frames][ncols] log-posteriors of the 3P decoder-visible columns (K-log)
     int ncols;
     const int64_t *frame_off;
     int n_utt, P, H;
@@ -49,6 +49,22 @@ __device__ __forceinline__ float ord2f(unsigned o)
     return __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o);
 }
 
+// K-log: the decoder soft function SoftLog (srec.h:192-195, applied srec.cpp:1088-1097) = glibc logf,
+// no guard, on the 3P columns the decoder reads.  Fully parallel, so the sequential kernel below is
+// pure token passing; a penalty sweep reuses the same log-posteriors.
+__global__ void __launch_bounds__(256) k_log_post(const float *__restrict__ post, int ldp, int ncols, int64_t total,
+                                                 float *__restrict__ logp)
+{
+    __shared__ double s_logtab[32];
+    logf_table_to_smem(s_logtab, threadIdx.x, blockDim.x);
+    __syncthreads();
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t f = i / ncols;
+        const int cidx = (int)(i - f * ncols);
+        logp[i] = logf_glibc(post[f * ldp + cidx], s_logtab);
+    }
+}
+
 template <int PPL>
 __global__ void __launch_bounds__(32) k_viterbi(VitArgs a)
 {
@@ -64,9 +80,6 @@ __global__ void __launch_bounds__(32) k_viterbi(VitArgs a)
     float *halpha = a.r_halpha + rbase;
     const unsigned FULL = 0xffffffffu;
     const unsigned ORD_FLOOR = f2ord(-FLT_MAX);
-    __shared__ double s_logtab[32];
-    logf_table_to_smem(s_logtab, lane, 32);
-    __syncwarp();
 
     float al[PPL][4];
     int pv[PPL][4], ln[PPL][4];
@@ -80,7 +93,7 @@ __global__ void __launch_bounds__(32) k_viterbi(VitArgs a)
     }
     int last_mi = -1;  // prev[0][0] after the last frame (phndec.cpp:240)
 
-    constexpr int FB = 4;  // frames whose observations are fetched and logged ahead of the recurrence
+    constexpr int FB = 8;  // frames whose observations are fetched ahead of the recurrence
     for (int tb = 0; tb < T; tb += FB) {
         float obs[FB][PPL][3];
 #pragma unroll
@@ -90,14 +103,8 @@ __global__ void __launch_bounds__(32) k_viterbi(VitArgs a)
 #pragma unroll
                 for (int j = 0; j < 3; ++j) {
                     const int i = lane + 32 * r;
-                    obs[q][r][j] = (valid[r] && tb + q < T) ? a.post[(f0 + tb + q) * a.ncols + 3 * i + j] : 1.0f;
+                    obs[q][r][j] = (valid[r] && tb + q < T) ? a.logp[(f0 + tb + q) * a.ncols + 3 * i + j] : 0.0f;
                 }
-#pragma unroll
-        for (int q = 0; q < FB; ++q)
-#pragma unroll
-            for (int r = 0; r < PPL; ++r)
-#pragma unroll
-                for (int j = 0; j < 3; ++j) obs[q][r][j] = logf_glibc(obs[q][r][j], s_logtab);  // SoftLog, no guard
 
 #pragma unroll
         for (int q = 0; q < FB; ++q) {
@@ -265,9 +272,20 @@ int launch_viterbi(phn_ctx *c, const float *d_pen, int n_pen)
 {
     const int nseg = c->n_utt * n_pen;
     if (nseg == 0) return PHN_OK;
+    const int ncols = 3 * c->P;
+    const int64_t total = c->total_frames * ncols;
+    int rc = ensure(c, c->d_logp, sizeof(float) * (size_t)(total ? total : 1));
+    if (rc) return rc;
+    if (total) {
+        int64_t blocks = (total + 255) / 256;
+        if (blocks > (int64_t)c->num_sms * 16) blocks = (int64_t)c->num_sms * 16;
+        k_log_post<<<(unsigned)blocks, 256, 0, c->stream>>>((const float *)c->d_post.p, c->ldp, ncols, total, (float *)c->d_logp.p);
+        PHN_CUDA(c, cudaGetLastError());
+        c->k_launches[PHN_K_VIT] += 1;
+    }
     VitArgs a;
-    a.post = (const float *)c->d_post.p;
-    a.ncols = c->ldp;
+    a.logp = (const float *)c->d_logp.p;
+    a.ncols = ncols;
     a.frame_off = (const int64_t *)c->d_frame_off.p;
     a.n_utt = c->n_utt; a.P = c->P; a.H = c->hist;
     a.total_frames = c->total_frames;
