@@ -45,9 +45,12 @@ constexpr int STC_F = 32;  // frames per CTA
 // otherwise FMAs (the tensor-core MLP rounds its inputs to fp16 anyway).
 // Phase 2: the staging tile [side][frame][nin] is written out coalesced - fp32 rows for the exact
 // MLP, or 16-byte chunks of the fp16 shared-memory image the tensor-core MLP loads by TMA.
-template <bool EXACT>
-__global__ void __launch_bounds__(256) k_stc(StcArgs a)
+template <bool EXACT, int NB>   // NB = banks when known at compile time (15, 23), 0 = read it from the arguments
+__global__ void __launch_bounds__(256) k_stc(StcArgs a_)
 {
+    StcArgs a = a_;
+    if (NB) { a.nb = NB; }
+    a.ncoef = 11;   // enforced at phn_create (add_c0 + 10 DCT coefficients)
     extern __shared__ float s_val[];          // [2][STC_F][nin]
     __shared__ float s_win[32];
     __shared__ float s_dct[160];
@@ -181,13 +184,15 @@ int launch_stc(phn_ctx *c, int64_t f0, int64_t nf)
     a.kb1 = c->net[0].k1P / 64;
     const size_t smem = sizeof(float) * 2 * STC_F * (size_t)c->nbanks * c->ncoef;
     const unsigned grid = (unsigned)((nf + STC_F - 1) / STC_F);
-    if (tc) {
-        PHN_CUDA(c, cudaFuncSetAttribute(k_stc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_stc<false><<<grid, 256, smem, c->stream>>>(a);
-    } else {
-        PHN_CUDA(c, cudaFuncSetAttribute(k_stc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_stc<true><<<grid, 256, smem, c->stream>>>(a);
-    }
+#define PHN_STC_LAUNCH(EX, NBV)                                                                                     \
+    do {                                                                                                            \
+        PHN_CUDA(c, cudaFuncSetAttribute(k_stc<EX, NBV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  \
+        k_stc<EX, NBV><<<grid, 256, smem, c->stream>>>(a);                                                          \
+    } while (0)
+    const int nbv = c->nbanks == 15 ? 15 : (c->nbanks == 23 ? 23 : 0);
+    if (tc) { if (nbv == 15) PHN_STC_LAUNCH(false, 15); else if (nbv == 23) PHN_STC_LAUNCH(false, 23); else PHN_STC_LAUNCH(false, 0); }
+    else    { if (nbv == 15) PHN_STC_LAUNCH(true, 15);  else if (nbv == 23) PHN_STC_LAUNCH(true, 23);  else PHN_STC_LAUNCH(true, 0); }
+#undef PHN_STC_LAUNCH
     PHN_CUDA(c, cudaGetLastError());
     c->k_launches[PHN_K_STC] += 1;
     return PHN_OK;

@@ -58,11 +58,10 @@ __global__ void __launch_bounds__(256) k_log_post(const float *__restrict__ post
     __shared__ double s_logtab[32];
     logf_table_to_smem(s_logtab, threadIdx.x, blockDim.x);
     __syncthreads();
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t f = i / ncols;
-        const int cidx = (int)(i - f * ncols);
-        logp[i] = logf_glibc(post[f * ldp + cidx], s_logtab);
-    }
+    const int64_t frames = total / ncols;
+    const int lane = threadIdx.x & 31;
+    for (int64_t f = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); f < frames; f += (int64_t)gridDim.x * 8)   // one warp per row
+        for (int cidx = lane; cidx < ncols; cidx += 32) logp[f * ncols + cidx] = logf_glibc(post[f * ldp + cidx], s_logtab);
 }
 
 template <int PPL>
@@ -109,7 +108,7 @@ __global__ void __launch_bounds__(32) k_viterbi(VitArgs a)
 #pragma unroll
         for (int q = 0; q < FB; ++q) {
             const int t = tb + q;
-            if (t >= T) break;
+            if (t < T) {   // predicated, not `break`: keeps obs[][][] in registers (fully unrolled indices)
             // ---- PropagateInModels (phndec.cpp:96-119): descending j, in place
 #pragma unroll
             for (int r = 0; r < PPL; ++r) {
@@ -130,24 +129,20 @@ __global__ void __launch_bounds__(32) k_viterbi(VitArgs a)
             }
             // ---- PropagateInNetwork (phndec.cpp:121-144): first strict max of alpha[i][3] from (-FLT_MAX, 0)
             unsigned bo = ORD_FLOOR;
-            int bi = 0;
+            int bi = 0, b_prev = pv[0][3], b_len = ln[0][3];   // payload of the local winner travels with it
 #pragma unroll
             for (int r = 0; r < PPL; ++r) {
                 const float v = al[r][3];
                 if (valid[r] && v > -FLT_MAX) {
                     const unsigned o = f2ord(v + 0.0f);
-                    if (o > bo) { bo = o; bi = lane + 32 * r; }
+                    if (o > bo) { bo = o; bi = lane + 32 * r; b_prev = pv[r][3]; b_len = ln[r][3]; }
                 }
             }
             const unsigned mo = __reduce_max_sync(FULL, bo);
             const int mi = (int)__reduce_min_sync(FULL, bo == mo ? (unsigned)bi : 0x7fffffffu);
             const float mx = mo == ORD_FLOOR ? -FLT_MAX : ord2f(mo);
-            // AddHistory (phndec.cpp:146-158): record of frame t+1
-            if ((mi & 31) == lane) {
-#pragma unroll
-                for (int r = 0; r < PPL; ++r)
-                    if (r == (mi >> 5)) { hphn[t] = pv[r][3]; hlen[t] = ln[r][3]; halpha[t] = mx; }
-            }
+            // AddHistory (phndec.cpp:146-158): record of frame t+1, written by the lane that owns phone mi
+            if ((mi & 31) == lane) { hphn[t] = b_prev; hlen[t] = b_len; halpha[t] = mx; }
             const float entry = __fadd_rn(mx, wp);
 #pragma unroll
             for (int r = 0; r < PPL; ++r) { al[r][0] = entry; pv[r][0] = mi; ln[r][0] = 0; }
@@ -155,7 +150,7 @@ __global__ void __launch_bounds__(32) k_viterbi(VitArgs a)
             // ---- GetBestToken (phndec.cpp:169-189), only consumed by TimePruning when n >= H+1
             if (t + 1 >= H + 1) {
                 unsigned co = ORD_FLOOR;
-                int ci = 0x7fffffff;
+                int ci = 0x7fffffff, c_prev = 0, c_len = 1;
 #pragma unroll
                 for (int r = 0; r < PPL; ++r)
 #pragma unroll
@@ -163,23 +158,17 @@ __global__ void __launch_bounds__(32) k_viterbi(VitArgs a)
                         const float v = al[r][j];
                         if (valid[r] && v > -FLT_MAX) {
                             const unsigned o = f2ord(v + 0.0f);
-                            if (o > co) { co = o; ci = (lane + 32 * r) * 3 + (j - 1); }
+                            if (o > co) { co = o; ci = (lane + 32 * r) * 3 + (j - 1); c_prev = pv[r][j]; c_len = ln[r][j]; }
                         }
                     }
                 const unsigned to = __reduce_max_sync(FULL, co);
                 const int ti = (int)__reduce_min_sync(FULL, (co == to && ci != 0x7fffffff) ? (unsigned)ci : 0x7fffffffu);
                 if (ti == 0x7fffffff) {  // nothing above -FLT_MAX: the scan's initial (len 1, prev 0)
                     if (lane == 0) { rbl[t] = 1; rbp[t] = 0; }
-                } else {
-                    const int wi = ti / 3, wj = ti - wi * 3 + 1;
-                    if ((wi & 31) == lane) {
-#pragma unroll
-                        for (int r = 0; r < PPL; ++r)
-#pragma unroll
-                            for (int j = 1; j <= 3; ++j)
-                                if (r == (wi >> 5) && j == wj) { rbl[t] = ln[r][j]; rbp[t] = pv[r][j]; }
-                    }
+                } else if (ci == ti) {   // exactly one lane holds the winning (phone, state)
+                    rbl[t] = c_len; rbp[t] = c_prev;
                 }
+            }
             }
         }
     }
@@ -277,7 +266,7 @@ int launch_viterbi(phn_ctx *c, const float *d_pen, int n_pen)
     int rc = ensure(c, c->d_logp, sizeof(float) * (size_t)(total ? total : 1));
     if (rc) return rc;
     if (total) {
-        int64_t blocks = (total + 255) / 256;
+        int64_t blocks = (c->total_frames + 7) / 8;
         if (blocks > (int64_t)c->num_sms * 16) blocks = (int64_t)c->num_sms * 16;
         k_log_post<<<(unsigned)blocks, 256, 0, c->stream>>>((const float *)c->d_post.p, c->ldp, ncols, total, (float *)c->d_logp.p);
         PHN_CUDA(c, cudaGetLastError());

@@ -15,6 +15,8 @@
 #include "internal.h"
 #include "device_math.cuh"
 
+#include <type_traits>
+
 namespace phn {
 
 struct WaveArgs {
@@ -48,16 +50,16 @@ __device__ __forceinline__ int find_utt(const int64_t *off, int n, int64_t f)
 // in double, one rounding to float, then float add/sub.  Twiddle (1, 0) needs no arithmetic at all:
 // fl32(fl64(1*x) - fl64(0*y)) == x (up to the sign of a zero, which |X|^2 cannot see).
 // !EXACT: plain fp32 FMAs.
-template <bool EXACT>
-__device__ __forceinline__ void bfly(float2 &lo, float2 &up, const double2 w, const bool trivial)
+template <bool EXACT, typename TW>
+__device__ __forceinline__ void bfly(float2 &lo, float2 &up, const TW w, const bool trivial)
 {
     float tr, ti;
     if (trivial) {
         tr = up.x; ti = up.y;
     } else if (EXACT) {
         const double kr = (double)up.x, ki = (double)up.y;
-        tr = __double2float_rn(__dsub_rn(__dmul_rn(w.x, kr), __dmul_rn(w.y, ki)));
-        ti = __double2float_rn(__dadd_rn(__dmul_rn(w.x, ki), __dmul_rn(w.y, kr)));
+        tr = __double2float_rn(__dsub_rn(__dmul_rn((double)w.x, kr), __dmul_rn((double)w.y, ki)));
+        ti = __double2float_rn(__dadd_rn(__dmul_rn((double)w.x, ki), __dmul_rn((double)w.y, kr)));
     } else {
         const float wr = (float)w.x, wi = (float)w.y;
         tr = fmaf(wr, up.x, -wi * up.y);
@@ -70,8 +72,8 @@ __device__ __forceinline__ void bfly(float2 &lo, float2 &up, const double2 w, co
 // LEVELS consecutive radix-2 stages on R = 2^LEVELS elements held in registers.
 // v[r] is element e = base + S*r of the length-N array; stage half-sizes S, 2S, 4S.
 // Twiddle of the pair (e, e+h) is tw[h-1 + (e mod h)], e mod h = base_mod + S*(r mod hh).
-template <bool EXACT, int LEVELS>
-__device__ __forceinline__ void fft_pass(float2 *v, const double2 *s_tw, int S, int base_mod)
+template <bool EXACT, int LEVELS, typename TW>
+__device__ __forceinline__ void fft_pass(float2 *v, const TW *s_tw, int S, int base_mod)
 {
     constexpr int R = 1 << LEVELS;
 #pragma unroll
@@ -82,7 +84,7 @@ __device__ __forceinline__ void fft_pass(float2 *v, const double2 *s_tw, int S, 
         for (int r = 0; r < R; ++r) {
             if (r & hh) continue;
             const int m = base_mod + S * (r & (hh - 1));
-            bfly<EXACT>(v[r], v[r + hh], s_tw[h - 1 + m], m == 0);
+            bfly<EXACT, TW>(v[r], v[r + hh], s_tw[h - 1 + m], m == 0);
         }
     }
 }
@@ -98,14 +100,19 @@ __global__ void __launch_bounds__(kWaveWarps * 32) k_wave(WaveArgs a)
     constexpr int R3 = 1 << L3;             // its radix (4 or 8); N/R3 = 64 groups -> 2 per lane
     constexpr int WORK = N + N / 32 + N2 / 2;  // float2 units per warp: padded data[] + pw[N2]
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double2 *s_tw = reinterpret_cast<double2 *>(smem_raw);          // [N-1] (+1 pad)
-    float *s_ham = reinterpret_cast<float *>(s_tw + N);             // [N], zero beyond vs
+    using TW = typename std::conditional<EXACT, double2, float2>::type;   // fp32 pipeline: twiddles rounded to float once
+    TW *s_tw = reinterpret_cast<TW *>(smem_raw);                    // [N-1] (+1 pad) in a double2-sized slot each
+    float *s_ham = reinterpret_cast<float *>(smem_raw + sizeof(double2) * N);  // [N], zero beyond vs
     float *s_coef = s_ham + N;                                      // [N2]
     int *s_bank = reinterpret_cast<int *>(s_coef + N2);             // [N2]
     double *s_logtab = reinterpret_cast<double *>(s_bank + N2);     // [32] glibc logf table
     float2 *s_work = reinterpret_cast<float2 *>(s_logtab + 32);
     logf_table_to_smem(s_logtab, threadIdx.x, blockDim.x);
-    for (int i = threadIdx.x; i < N - 1; i += blockDim.x) s_tw[i] = a.tw[i];
+    for (int i = threadIdx.x; i < N - 1; i += blockDim.x) {
+        const double2 w = a.tw[i];
+        if (EXACT) reinterpret_cast<double2 *>(s_tw)[i] = w;
+        else reinterpret_cast<float2 *>(s_tw)[i] = make_float2((float)w.x, (float)w.y);
+    }
     for (int i = threadIdx.x; i < N; i += blockDim.x) s_ham[i] = i < a.vs ? a.hamming[i] : 0.0f;
     for (int i = threadIdx.x; i < N2; i += blockDim.x) { s_coef[i] = a.coeffs[i]; s_bank[i] = a.banks[i]; }
     __syncthreads();
@@ -193,7 +200,7 @@ __global__ void __launch_bounds__(kWaveWarps * 32) k_wave(WaveArgs a)
 #pragma unroll
         for (int oc = 0; oc < OCT; ++oc) {
             const int o = lane + 32 * oc;
-            fft_pass<EXACT, 3>(v[oc], s_tw, 1, 0);
+            fft_pass<EXACT, 3, TW>(v[oc], s_tw, 1, 0);
 #pragma unroll
             for (int r = 0; r < 8; ++r) data[pad_idx(8 * o + r)] = v[oc][r];
         }
@@ -211,7 +218,7 @@ __global__ void __launch_bounds__(kWaveWarps * 32) k_wave(WaveArgs a)
         for (int oc = 0; oc < OCT; ++oc) {
             const int o = lane + 32 * oc;
             const int low3 = o & 7, high = o >> 3;
-            fft_pass<EXACT, 3>(v[oc], s_tw, 8, low3);
+            fft_pass<EXACT, 3, TW>(v[oc], s_tw, 8, low3);
 #pragma unroll
             for (int r = 0; r < 8; ++r) data[pad_idx(low3 + 8 * r + 64 * high)] = v[oc][r];
         }
@@ -223,7 +230,7 @@ __global__ void __launch_bounds__(kWaveWarps * 32) k_wave(WaveArgs a)
             float2 w3[R3];
 #pragma unroll
             for (int r = 0; r < R3; ++r) w3[r] = data[pad_idx(low6 + 64 * r)];
-            fft_pass<EXACT, L3>(w3, s_tw, 64, low6);
+            fft_pass<EXACT, L3, TW>(w3, s_tw, 64, low6);
 #pragma unroll
             for (int r = 0; r < R3 / 2; ++r)   // cPower (dspc.h:141-146)
                 pw[low6 + 64 * r] = __fadd_rn(__fmul_rn(w3[r].x, w3[r].x), __fmul_rn(w3[r].y, w3[r].y));
