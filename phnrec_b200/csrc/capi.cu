@@ -166,8 +166,10 @@ static int run_posteriors(phn_ctx *c)
     int64_t ch = tc ? (int64_t)1 << 18 : (int64_t)1 << 15;
     if (ch > F) ch = (F + 127) / 128 * 128;
     if (ch == 0) return PHN_OK;
+    c->logp_valid = 0;
     if (tc) {
         if ((rc = mlp_tc_prepare(c))) return rc;
+        if (c->fuse_logp && (rc = ensure(c, c->d_logp, sizeof(float) * (size_t)F * c->ldp))) return rc;
         if ((rc = ensure(c, c->d_x0h, sizeof(__half) * ch * c->net[0].k1P))) return rc;
         if ((rc = ensure(c, c->d_x1h, sizeof(__half) * ch * c->net[1].k1P))) return rc;
         if ((rc = ensure(c, c->d_xmh, sizeof(__half) * ch * c->net[2].k1P))) return rc;
@@ -183,6 +185,7 @@ static int run_posteriors(phn_ctx *c)
         { StageTimer t(c, PHN_K_STC); if ((rc = launch_stc(c, f0, nf))) return rc; }
         { StageTimer t(c, PHN_K_MLP); if ((rc = tc ? launch_mlp_tc(c, f0, nf) : launch_mlp_exact(c, f0, nf))) return rc; }
     }
+    c->logp_valid = tc && c->fuse_logp;
     return PHN_OK;
 }
 
@@ -516,8 +519,13 @@ int phn_recognize_device(phn_ctx *c, const void *d_audio, const int64_t *byte_of
     int rc;
     if ((rc = plan_audio(c, byte_off, n_utt))) return rc;
     { StageTimer t(c, PHN_K_WAVE); if ((rc = launch_wave(c, d_audio))) return rc; }
-    if ((rc = run_posteriors(c))) return rc;
-    return run_decode(c, nullptr, 1);
+    c->fuse_logp = 1;
+    rc = run_posteriors(c);
+    c->fuse_logp = 0;
+    if (rc) return rc;
+    rc = run_decode(c, nullptr, 1);
+    c->logp_valid = 0;
+    return rc;
 }
 
 int phn_fetch_mel(phn_ctx *c, float *mel_out)
@@ -614,6 +622,7 @@ int phn_decode(phn_ctx *c, const float *post, const int64_t *frame_off, int n_ut
     const size_t rowb = sizeof(float) * c->net[2].nout;
     if (c->total_frames)
         PHN_CUDA(c, cudaMemcpy2DAsync(c->d_post.p, sizeof(float) * c->ldp, post, rowb, rowb, (size_t)c->total_frames, cudaMemcpyHostToDevice, c->stream));
+    c->logp_valid = 0;
     if ((rc = run_decode(c, penalties, n_pen))) return rc;
     return phn_fetch_labels(c, labels, label_cap, label_off);
 }

@@ -72,7 +72,9 @@ struct phn_ctx {
     float lo = 0, hi = 4000, preem = 0, wpenalty = -2.f, frame_shift = 0.f, frame_floor = -9999.9f, scale = 1.f, dc_shift = 0.f;
     int mlp_mode = PHN_MLP_EXACT_FP32;
     void *tc = nullptr;  // tensor-core mode state (k_mlp_tc.cu)
-    int force_exact_wave = 0;  // phn_mel always returns the reference's bits, whatever the MLP mode
+    int force_exact_wave = 0;
+    int fuse_logp = 0;   // tensor-core merger also writes ln(posteriors) for the decoder (audio -> labels path)
+    int logp_valid = 0;  // d_logp already holds the decoder's input for the current batch  // phn_mel always returns the reference's bits, whatever the MLP mode
     std::vector<std::string> phonemes;
     float win[32];
     phn::HostNet hnet[3];

@@ -107,29 +107,32 @@ __host__ __device__ constexpr uint32_t make_idesc(int n)
 {
     return (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
 }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
-{
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-        : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t *v)
-{
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
-                 : "r"(taddr));
-}
+#define PHN_TMEM_LD(NAME, SHAPE, N, OUTS, ...)                                                        \
+    __device__ __forceinline__ void NAME(uint32_t taddr, uint32_t *v)                                  \
+    {                                                                                                 \
+        asm volatile("tcgen05.ld.sync.aligned.32x32b." SHAPE ".b32 {" OUTS "}, [%" #N "];" : __VA_ARGS__ : "r"(taddr)); \
+    }
+#define R4(b) "=r"(v[b]), "=r"(v[b + 1]), "=r"(v[b + 2]), "=r"(v[b + 3])
+PHN_TMEM_LD(tmem_ld4, "x4", 4, "%0, %1, %2, %3", R4(0))
+PHN_TMEM_LD(tmem_ld8, "x8", 8, "%0, %1, %2, %3, %4, %5, %6, %7", R4(0), R4(4))
+PHN_TMEM_LD(tmem_ld16, "x16", 16, "%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15", R4(0), R4(4), R4(8), R4(12))
+PHN_TMEM_LD(tmem_ld32, "x32", 32,
+            "%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31",
+            R4(0), R4(4), R4(8), R4(12), R4(16), R4(20), R4(24), R4(28))
+#undef R4
+#undef PHN_TMEM_LD
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ float rcp_approx(float x)
 {
     float r;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float fma_sat(float a, float b, float c)
+{
+    float r;
+    asm("fma.rn.sat.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
     return r;
 }
 __device__ __forceinline__ uint32_t pack_half2(float lo, float hi)
@@ -138,20 +141,29 @@ __device__ __forceinline__ uint32_t pack_half2(float lo, float hi)
     asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
     return r;
 }
+// One lane of a converged warp (the same one every time: the lowest); tcgen05.commit tracks the MMAs
+// of the thread that executes it, so the issuer's MMAs and commits must come from one elected lane.
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 
 // The Quicknet bit-trick exponential (fexp.h:14-21) without a float->int conversion (F2I shares the
 // quarter-rate XU pipe with MUFU.RCP, and the epilogue must keep pace with the tensor pipe):
 //   D(y) = float whose exponent field is floor(t) and whose mantissa is frac(t),  t = y/ln2 + Ct,
-//   Ct = 127 - 60801/2^20.  One FFMA forms r = 2^23 + t*2^14 (callers fold Ct, the bias and 2^23
-//   into the addend); in [2^23, 2^24) the float's mantissa field IS round(t*2^14), so
+//   Ct = 127 - 60801/2^20.  The caller forms u = sat(t / TMAX) with one FFMA.SAT (the saturation is
+//   the clamp: t < 0 gives D = 0, t > TMAX gives D = 2^(TMAX-127)); a second FFMA forms
+//   r = 2^23 + u * TMAX * 2^14: in [2^23, 2^24) the float's mantissa field IS round(t*2^14), so
 //   bits(D) = bits(r) << 9.  t keeps 14 fractional bits (2^-14 relative in D; the reference keeps 20).
-constexpr float kK14 = 23637.115549924778f;     // 2^14 / ln 2
+constexpr double kLn2 = 0.69314718055994530942;
 constexpr double kCt = 127.0 - 60801.0 / 1048576.0;
-constexpr float kRmin = 8388608.0f;             // 2^23              (t = 0)
-constexpr float kRmax = 8388608.0f + 4177920.0f; // 2^23 + 255*2^14  (t = 255, D ~ 2^128 -> 1/(1+D) = 0)
-__device__ __forceinline__ float fexp_from_r(float r)
+constexpr float kSigTmax = 158.0f;               // sigmoid: D clamped to 2^31 (1/(1+D) is 0 in fp16 long before)
+constexpr float kSmxTmax = 128.0f;               // softmax: y <= 0, so t <= Ct < 128
+__device__ __forceinline__ float fexp_from_u(float u, float tmax)
 {
-    r = fminf(fmaxf(r, kRmin), kRmax - 16384.0f);
+    const float r = fmaf(u, tmax * 16384.0f, 8388608.0f);
     return __uint_as_float(__float_as_uint(r) << 9);
 }
 
@@ -162,28 +174,32 @@ struct TcArgs {
     const uint8_t *x_img;     // [tiles][KB1][16 KB]  activations, SW128 blocks
     const uint8_t *w1_img;    // [NCH][KB1][16 KB]
     const uint8_t *w2_img;    // [NCH][2][N2P*128 B]
-    const float *sig_k;       // [NCH*128]  per hidden unit: 2^23 + round(2^14 (Ct - b1/ln2))
-    const float *b2;          // [N2P]
+    const float *sig_k;       // [NCH*128]  per hidden unit: (Ct - b1/ln2) / kSigTmax
+    const float *b2;          // [N2P]      output bias; -FLT_MAX in the padding columns
     int n_tiles, KB1, NCH, S1, S2;
     int nks_last;             // k-steps (of 16) actually needed in the last k-block of layer 1
     int64_t nf;               // frames in this launch
     int nout;
     // outputs
     float *post; int ldpost;                          // merger: posteriors [nf][ldpost]
+    float *logp;                                      // merger: ln(posteriors) [nf][ldpost] for the decoder, or nullptr
     uint8_t *xm_img; int xm_kb1; int xm_col0;         // band nets: merger input image, first column (multiple of 8)
     const float *mmean, *mdev;                        // merger input normalisation, indexed by image column
 };
 
-constexpr int TC_EPI_WARPS = 16;
-constexpr int TC_THREADS = (2 + TC_EPI_WARPS) * 32;
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
+constexpr int TC_EPI_WARPS = 16;                     // warps 0..15: epilogue; 16: TMA producer; 17: MMA issuer
+constexpr int TC_THREADS = (TC_EPI_WARPS + 2) * 32;
+// The SM's warp schedulers favour the highest warp id among eligible warps, so the two warps whose
+// instruction streams gate everything else (TMA producer, MMA issuer) get the highest ids.
+__device__ __forceinline__ void quarter_bar_sync(int q) { asm volatile("bar.sync %0, 128;" ::"r"(q + 1) : "memory"); }
 
 template <int N2P>
 __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs a)
 {
     constexpr int W2_BLK = N2P * 128;       // bytes of one [N2P rows x 64 fp16] block
-    constexpr int NG = N2P / 8;             // 8-column groups of D2
-    constexpr int MAXG = (NG + 3) / 4;      // groups per column quarter (at most)
+    constexpr int NQ = N2P / 4;             // D2 columns per epilogue column quarter (32, 36, 40 or 48)
+    constexpr int NR = NQ - 32;             // columns beyond the first 32-column TMEM load (0, 4, 8 or 16)
+    static_assert(NR == 0 || NR == 4 || NR == 8 || NR == 16, "unsupported output width");
     extern __shared__ uint8_t smem_raw[];
     // carve-up (all block bases 1024-byte aligned: the swizzle pattern is a function of the address)
     uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -193,8 +209,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs a)
     uint8_t *sH = sW2 + (size_t)a.S2 * W2_BLK;                 // 2 x 16 KB
     float *s_sigk = reinterpret_cast<float *>(sH + 2 * TC_BLK);  // [NCH*128]
     float *s_b2 = s_sigk + a.NCH * TC_NC;                      // [N2P]
-    float *s_red = s_b2 + N2P;                                 // [4][128] row max / row sum exchange
-    uint64_t *bars = reinterpret_cast<uint64_t *>(s_red + 4 * 128);
+    float *s_mm = s_b2 + N2P;                                  // [N2P] merger input mean  (band nets)
+    float *s_md = s_mm + N2P;                                  // [N2P] merger input 1/std (band nets)
+    float *s_red = s_md + N2P;                                 // [2][4][128] row max / row sum exchange
+    uint64_t *bars = reinterpret_cast<uint64_t *>(s_red + 8 * 128);
     uint64_t *x_full = bars;                 // [8]
     uint64_t *x_empty = bars + 8;            // [1]
     uint64_t *w1_full = bars + 9;            // [8]
@@ -208,6 +226,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs a)
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 41);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int WARP_TMA = TC_EPI_WARPS, WARP_MMA = TC_EPI_WARPS + 1;
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < 8; ++i) { mbar_init(&x_full[i], 1); mbar_init(&w1_full[i], 1); mbar_init(&w1_empty[i], 1); }
@@ -218,12 +237,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs a)
         mbar_init(d2_full, 1); mbar_init(d2_empty, TC_EPI_WARPS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 1) {  // TMEM: 512 columns (D1 double buffer 2 x 128, D2 up to 192)
+    if (warp == WARP_MMA) {  // TMEM: 512 columns (D1 double buffer 2 x 128, D2 up to 192)
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     for (int i = threadIdx.x; i < a.NCH * TC_NC; i += blockDim.x) s_sigk[i] = a.sig_k[i];
-    for (int i = threadIdx.x; i < N2P; i += blockDim.x) s_b2[i] = a.b2[i];
+    for (int i = threadIdx.x; i < N2P; i += blockDim.x) {
+        s_b2[i] = a.b2[i];
+        s_mm[i] = a.mmean ? a.mmean[a.xm_col0 + i] : 0.0f;
+        s_md[i] = a.mdev ? a.mdev[a.xm_col0 + i] : 0.0f;
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -231,111 +254,125 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs a)
     const uint32_t tD1[2] = {tmem, tmem + 128u};
     const uint32_t tD2 = tmem + 256u;
 
-    if (warp == 0) {
+    if (warp == WARP_TMA) {
         // ===================================================================== TMA producer
-        if (lane == 0) {
-            uint32_t ph_x_empty = 0, w1_stage = 0, ph_w1 = 0, w2_stage = 0, ph_w2 = 0;
-            bool first_tile = true;
-            auto load_w1 = [&](int c) {
-                for (int kb = 0; kb < a.KB1; ++kb) {
-                    mbar_wait(&w1_empty[w1_stage], ph_w1 ^ 1);
+        // The whole warp walks the loops (warp-uniform control flow); one elected lane issues.
+        uint32_t ph_x_empty = 0, w1_stage = 0, ph_w1 = 0, w2_stage = 0, ph_w2 = 0;
+        bool first_tile = true;
+        auto load_w1 = [&](int c) {
+            for (int kb = 0; kb < a.KB1; ++kb) {
+                mbar_wait(&w1_empty[w1_stage], ph_w1 ^ 1);
+                if (elect_one()) {
                     mbar_expect_tx(&w1_full[w1_stage], TC_BLK);
                     tma_load_1d(sW1 + (size_t)w1_stage * TC_BLK, a.w1_img + ((size_t)c * a.KB1 + kb) * TC_BLK, TC_BLK, &w1_full[w1_stage]);
-                    if (++w1_stage == (uint32_t)a.S1) { w1_stage = 0; ph_w1 ^= 1; }
                 }
-            };
-            auto load_w2 = [&](int c) {
-                for (int kb = 0; kb < 2; ++kb) {
-                    mbar_wait(&w2_empty[w2_stage], ph_w2 ^ 1);
+                __syncwarp();
+                if (++w1_stage == (uint32_t)a.S1) { w1_stage = 0; ph_w1 ^= 1; }
+            }
+        };
+        auto load_w2 = [&](int c) {
+            for (int kb = 0; kb < 2; ++kb) {
+                mbar_wait(&w2_empty[w2_stage], ph_w2 ^ 1);
+                if (elect_one()) {
                     mbar_expect_tx(&w2_full[w2_stage], W2_BLK);
                     tma_load_1d(sW2 + (size_t)w2_stage * W2_BLK, a.w2_img + ((size_t)c * 2 + kb) * W2_BLK, W2_BLK, &w2_full[w2_stage]);
-                    if (++w2_stage == (uint32_t)a.S2) { w2_stage = 0; ph_w2 ^= 1; }
                 }
-            };
-            for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
-                // Later tiles: the first weight chunk is prefetched while the previous tile still owns X -
-                // but only when it fits the ring entirely (KB1 <= S1); otherwise the issuer, which waits
-                // for X before it frees a ring stage, and this warp would wait for each other.
-                const bool prefetch_w1 = !first_tile && a.KB1 <= a.S1;
-                if (prefetch_w1) load_w1(0);
-                if (!first_tile) { mbar_wait(x_empty, ph_x_empty); ph_x_empty ^= 1; }
+                __syncwarp();
+                if (++w2_stage == (uint32_t)a.S2) { w2_stage = 0; ph_w2 ^= 1; }
+            }
+        };
+        for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+            // Later tiles: the first weight chunk is prefetched while the previous tile still owns X -
+            // but only when it fits the ring entirely (KB1 <= S1); otherwise the issuer, which waits
+            // for X before it frees a ring stage, and this warp would wait for each other.
+            const bool prefetch_w1 = !first_tile && a.KB1 <= a.S1;
+            if (prefetch_w1) load_w1(0);
+            if (!first_tile) { mbar_wait(x_empty, ph_x_empty); ph_x_empty ^= 1; }
+            if (elect_one()) {
                 for (int kb = 0; kb < a.KB1; ++kb) {
                     mbar_expect_tx(&x_full[kb], TC_BLK);
                     tma_load_1d(sX + (size_t)kb * TC_BLK, a.x_img + ((size_t)tile * a.KB1 + kb) * TC_BLK, TC_BLK, &x_full[kb]);
                 }
-                if (!prefetch_w1) load_w1(0);
-                first_tile = false;
-                for (int c = 0; c < a.NCH; ++c) {   // same order as the issuer consumes: G1(c+1) before G2(c)
-                    if (c + 1 < a.NCH) load_w1(c + 1);
-                    load_w2(c);
-                }
+            }
+            __syncwarp();
+            if (!prefetch_w1) load_w1(0);
+            first_tile = false;
+            for (int c = 0; c < a.NCH; ++c) {   // same order as the issuer consumes: G1(c+1) before G2(c)
+                if (c + 1 < a.NCH) load_w1(c + 1);
+                load_w2(c);
             }
         }
-    } else if (warp == 1) {
+    } else if (warp == WARP_MMA) {
         // ===================================================================== MMA issuer
-        if (lane == 0) {
-            const uint32_t idesc1 = make_idesc(TC_NC), idesc2 = make_idesc(N2P);
-            uint32_t ph_x_full = 0, w1_stage = 0, ph_w1 = 0, w2_stage = 0, ph_w2 = 0, ph_h_full = 0, ph_d2_empty = 0;
-            uint32_t ph_d1_empty0 = 0, ph_d1_empty1 = 0, n_d1_use0 = 0, n_d1_use1 = 0;
-            bool first_d2 = true;
-            const uint32_t sX_a = smem_u32(sX), sW1_a = smem_u32(sW1), sW2_a = smem_u32(sW2), sH_a = smem_u32(sH);
-            for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
-                auto g1 = [&](int c) {
-                    const int b = c & 1;
-                    if (b == 0) {
-                        if (n_d1_use0 > 0) { mbar_wait(&d1_empty[0], ph_d1_empty0); ph_d1_empty0 ^= 1; }
-                        ++n_d1_use0;
-                    } else {
-                        if (n_d1_use1 > 0) { mbar_wait(&d1_empty[1], ph_d1_empty1); ph_d1_empty1 ^= 1; }
-                        ++n_d1_use1;
-                    }
-                    tc_fence_after();
-                    for (int kb = 0; kb < a.KB1; ++kb) {
-                        if (c == 0) mbar_wait(&x_full[kb], ph_x_full);
-                        mbar_wait(&w1_full[w1_stage], ph_w1);
-                        tc_fence_after();
-                        const int nks = kb == a.KB1 - 1 ? a.nks_last : 4;
-                        for (int ks = 0; ks < nks; ++ks) {
-                            const uint64_t ad = make_sw128_desc(sX_a + kb * TC_BLK + ks * 32);
-                            const uint64_t bd = make_sw128_desc(sW1_a + w1_stage * TC_BLK + ks * 32);
-                            umma_f16_ss(b ? tD1[1] : tD1[0], ad, bd, idesc1, (kb | ks) ? 1u : 0u);
-                        }
-                        tc_commit(&w1_empty[w1_stage]);
-                        if (++w1_stage == (uint32_t)a.S1) { w1_stage = 0; ph_w1 ^= 1; }
-                    }
-                    tc_commit(&d1_full[b]);
-                    if (c == a.NCH - 1) tc_commit(x_empty);
-                };
-                auto g2 = [&](int c) {
-                    if (c == 0 && !first_d2) { mbar_wait(d2_empty, ph_d2_empty); ph_d2_empty ^= 1; }
-                    first_d2 = false;
-                    mbar_wait(h_full, ph_h_full); ph_h_full ^= 1;
-                    for (int kb = 0; kb < 2; ++kb) {
-                        mbar_wait(&w2_full[w2_stage], ph_w2);
-                        tc_fence_after();
-                        for (int ks = 0; ks < 4; ++ks) {
-                            const uint64_t ad = make_sw128_desc(sH_a + kb * TC_BLK + ks * 32);
-                            const uint64_t bd = make_sw128_desc(sW2_a + w2_stage * W2_BLK + ks * 32);
-                            umma_f16_ss(tD2, ad, bd, idesc2, (c | kb | ks) ? 1u : 0u);
-                        }
-                        tc_commit(&w2_empty[w2_stage]);
-                        if (++w2_stage == (uint32_t)a.S2) { w2_stage = 0; ph_w2 ^= 1; }
-                    }
-                    tc_commit(h_empty);
-                    if (c == a.NCH - 1) tc_commit(d2_full);
-                };
-                g1(0);
-                for (int c = 0; c < a.NCH; ++c) {
-                    if (c + 1 < a.NCH) g1(c + 1);
-                    g2(c);
+        // Warp-uniform loops; the MMAs and commits of one k-block are issued by the elected lane.
+        const uint32_t idesc1 = make_idesc(TC_NC), idesc2 = make_idesc(N2P);
+        uint32_t ph_x_full = 0, w1_stage = 0, ph_w1 = 0, w2_stage = 0, ph_w2 = 0, ph_h_full = 0, ph_d2_empty = 0;
+        uint32_t ph_d1_empty0 = 0, ph_d1_empty1 = 0, n_d1_use0 = 0, n_d1_use1 = 0;
+        bool first_d2 = true;
+        // descriptors differ only in the 14-bit start-address field: base + (byte offset >> 4)
+        const uint64_t dX = make_sw128_desc(smem_u32(sX)), dW1 = make_sw128_desc(smem_u32(sW1));
+        const uint64_t dW2 = make_sw128_desc(smem_u32(sW2)), dH = make_sw128_desc(smem_u32(sH));
+        for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+            auto g1 = [&](int c) {
+                const int b = c & 1;
+                if (b == 0) {
+                    if (n_d1_use0 > 0) { mbar_wait(&d1_empty[0], ph_d1_empty0); ph_d1_empty0 ^= 1; }
+                    ++n_d1_use0;
+                } else {
+                    if (n_d1_use1 > 0) { mbar_wait(&d1_empty[1], ph_d1_empty1); ph_d1_empty1 ^= 1; }
+                    ++n_d1_use1;
                 }
-                ph_x_full ^= 1;
+                const uint32_t td = b ? tD1[1] : tD1[0];
+                for (int kb = 0; kb < a.KB1; ++kb) {
+                    if (c == 0) mbar_wait(&x_full[kb], ph_x_full);
+                    mbar_wait(&w1_full[w1_stage], ph_w1);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const int nks = kb == a.KB1 - 1 ? a.nks_last : 4;
+                        const uint64_t ad = dX + (uint64_t)((kb * TC_BLK) >> 4), bd = dW1 + (uint64_t)((w1_stage * TC_BLK) >> 4);
+                        for (int ks = 0; ks < nks; ++ks) umma_f16_ss(td, ad + 2 * ks, bd + 2 * ks, idesc1, (kb | ks) ? 1u : 0u);
+                        tc_commit(&w1_empty[w1_stage]);
+                        if (kb == a.KB1 - 1) {
+                            tc_commit(&d1_full[b]);
+                            if (c == a.NCH - 1) tc_commit(x_empty);
+                        }
+                    }
+                    __syncwarp();
+                    if (++w1_stage == (uint32_t)a.S1) { w1_stage = 0; ph_w1 ^= 1; }
+                }
+            };
+            auto g2 = [&](int c) {
+                if (c == 0 && !first_d2) { mbar_wait(d2_empty, ph_d2_empty); ph_d2_empty ^= 1; }
+                first_d2 = false;
+                mbar_wait(h_full, ph_h_full); ph_h_full ^= 1;
+                for (int kb = 0; kb < 2; ++kb) {
+                    mbar_wait(&w2_full[w2_stage], ph_w2);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const uint64_t ad = dH + (uint64_t)((kb * TC_BLK) >> 4), bd = dW2 + (uint64_t)((w2_stage * W2_BLK) >> 4);
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks) umma_f16_ss(tD2, ad + 2 * ks, bd + 2 * ks, idesc2, (c | kb | ks) ? 1u : 0u);
+                        tc_commit(&w2_empty[w2_stage]);
+                        if (kb == 1) {
+                            tc_commit(h_empty);
+                            if (c == a.NCH - 1) tc_commit(d2_full);
+                        }
+                    }
+                    __syncwarp();
+                    if (++w2_stage == (uint32_t)a.S2) { w2_stage = 0; ph_w2 ^= 1; }
+                }
+            };
+            g1(0);
+            for (int c = 0; c < a.NCH; ++c) {
+                if (c + 1 < a.NCH) g1(c + 1);
+                g2(c);
             }
+            ph_x_full ^= 1;
         }
     } else {
         // ===================================================================== epilogue warps
         const int q = warp & 3;                  // TMEM lane quarter this warp may access
-        const int cq = (warp - 2) >> 2;          // column quarter 0..3
+        const int cq = warp >> 2;                // column quarter 0..3
         const int row = q * 32 + lane;           // tile row == TMEM lane
         const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
         uint32_t ph_d1_full0 = 0, ph_d1_full1 = 0, ph_h_empty = 0, ph_d2_full = 0;
@@ -343,6 +380,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs a)
         // H[row][cq*32 .. +31] lives in k-block cq>>1 of the H operand, 16-byte chunks (cq&1)*4 .. +3
         uint8_t *hrow = sH + (size_t)(cq >> 1) * TC_BLK + (size_t)row * 128;
         const int hchunk0 = (cq & 1) * 4;
+        const float sigA = (float)(-1.0 / (kLn2 * (double)kSigTmax));
         for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
             for (int c = 0; c < a.NCH; ++c) {
                 const int b = c & 1;
@@ -355,18 +393,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs a)
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&d1_empty[b]);
-                // fsig(x) = 1 / (1 + D(-x - b1))
+                // fsig(x) = 1 / (1 + D(-x - b1)); two reciprocals share one MUFU: 1/a = a' / (a a'), 1/a' = a / (a a')
                 uint32_t hp[16];
                 const float4 *kp = reinterpret_cast<const float4 *>(s_sigk + c * TC_NC + cq * 32);
 #pragma unroll
                 for (int g = 0; g < 8; ++g) {
                     const float4 k4 = kp[g];
-                    const float h0 = rcp_approx(1.0f + fexp_from_r(fmaf(__uint_as_float(acc[g * 4 + 0]), -kK14, k4.x)));
-                    const float h1 = rcp_approx(1.0f + fexp_from_r(fmaf(__uint_as_float(acc[g * 4 + 1]), -kK14, k4.y)));
-                    const float h2 = rcp_approx(1.0f + fexp_from_r(fmaf(__uint_as_float(acc[g * 4 + 2]), -kK14, k4.z)));
-                    const float h3 = rcp_approx(1.0f + fexp_from_r(fmaf(__uint_as_float(acc[g * 4 + 3]), -kK14, k4.w)));
-                    hp[g * 2] = pack_half2(h0, h1);
-                    hp[g * 2 + 1] = pack_half2(h2, h3);
+                    const float a0 = 1.0f + fexp_from_u(fma_sat(__uint_as_float(acc[g * 4 + 0]), sigA, k4.x), kSigTmax);
+                    const float a1 = 1.0f + fexp_from_u(fma_sat(__uint_as_float(acc[g * 4 + 1]), sigA, k4.y), kSigTmax);
+                    const float a2 = 1.0f + fexp_from_u(fma_sat(__uint_as_float(acc[g * 4 + 2]), sigA, k4.z), kSigTmax);
+                    const float a3 = 1.0f + fexp_from_u(fma_sat(__uint_as_float(acc[g * 4 + 3]), sigA, k4.w), kSigTmax);
+                    const float r01 = rcp_approx(a0 * a1), r23 = rcp_approx(a2 * a3);
+                    hp[g * 2] = pack_half2(r01 * a1, r01 * a0);
+                    hp[g * 2 + 1] = pack_half2(r23 * a3, r23 * a2);
                 }
                 if (!first_h) { mbar_wait(h_empty, ph_h_empty); ph_h_empty ^= 1; }
                 first_h = false;
@@ -380,92 +419,95 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs a)
                 if (lane == 0) mbar_arrive(h_full);
             }
             // ------------------------------------------------------------- E2: softmax + outputs
-            // column quarter cq owns the 8-column groups [g_beg, g_end) of D2
-            const int g_beg = (cq * NG) / 4, g_end = ((cq + 1) * NG) / 4;
+            // column quarter cq owns D2 columns [cq*NQ, (cq+1)*NQ); the 4 warps of a row quarter
+            // exchange row max / row sum through shared memory and their own named barrier
+            const int n0 = cq * NQ;
             mbar_wait(d2_full, ph_d2_full); ph_d2_full ^= 1;
             tc_fence_after();
-            float o[MAXG * 8];
+            float o[NQ];
             {
-                uint32_t raw[MAXG][8];
-#pragma unroll
-                for (int g = 0; g < MAXG; ++g)
-                    if (g_beg + g < g_end) tmem_ld8(tD2 + lane_addr + (g_beg + g) * 8, raw[g]);
+                uint32_t raw[NQ];
+                tmem_ld32(tD2 + lane_addr + n0, raw);
+                if (NR == 4) tmem_ld4(tD2 + lane_addr + n0 + 32, raw + 32);
+                if (NR == 8) tmem_ld8(tD2 + lane_addr + n0 + 32, raw + 32);
+                if (NR == 16) tmem_ld16(tD2 + lane_addr + n0 + 32, raw + 32);
                 tmem_ld_wait();
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(d2_empty);
 #pragma unroll
-                for (int g = 0; g < MAXG; ++g)
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) o[g * 8 + i] = __uint_as_float(raw[g][i]);
-            }
-            float mx = -FLT_MAX;
-#pragma unroll
-            for (int g = 0; g < MAXG; ++g)
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int n = (g_beg + g) * 8 + i;
-                    const bool ok = g_beg + g < g_end && n < a.nout;
-                    o[g * 8 + i] = ok ? o[g * 8 + i] + s_b2[n < N2P ? n : 0] : -FLT_MAX;
-                    mx = fmaxf(mx, o[g * 8 + i]);
+                for (int j = 0; j < NQ / 4; ++j) {
+                    const float4 b4 = *reinterpret_cast<const float4 *>(s_b2 + n0 + 4 * j);   // -FLT_MAX in padding columns
+                    o[4 * j + 0] = __uint_as_float(raw[4 * j + 0]) + b4.x;
+                    o[4 * j + 1] = __uint_as_float(raw[4 * j + 1]) + b4.y;
+                    o[4 * j + 2] = __uint_as_float(raw[4 * j + 2]) + b4.z;
+                    o[4 * j + 3] = __uint_as_float(raw[4 * j + 3]) + b4.w;
                 }
-            s_red[cq * 128 + row] = mx;
-            epi_bar_sync();
-            mx = fmaxf(fmaxf(s_red[row], s_red[128 + row]), fmaxf(s_red[256 + row], s_red[384 + row]));
-            epi_bar_sync();
-            float sum = 0.0f;
-            const float kexp = (float)(8388608.0 + 16384.0 * kCt);
+            }
+            float mx = o[0];
 #pragma unroll
-            for (int i = 0; i < MAXG * 8; ++i) {
-                const float e = o[i] > -FLT_MAX ? fexp_from_r(fmaf(o[i] - mx, kK14, kexp)) : 0.0f;
+            for (int i = 1; i < NQ; ++i) mx = fmaxf(mx, o[i]);
+            s_red[cq * 128 + row] = mx;
+            quarter_bar_sync(q);
+            mx = fmaxf(fmaxf(s_red[row], s_red[128 + row]), fmaxf(s_red[256 + row], s_red[384 + row]));
+            float sum = 0.0f;
+            const float smxA = (float)(1.0 / (kLn2 * (double)kSmxTmax)), smxB = (float)(kCt / (double)kSmxTmax);
+#pragma unroll
+            for (int i = 0; i < NQ; ++i) {     // fexp_softmax_v (fexp.h:49-78): e = D(o - max)
+                const float e = fexp_from_u(fma_sat(o[i] - mx, smxA, smxB), kSmxTmax);
                 o[i] = e;
                 sum += e;
             }
-            s_red[cq * 128 + row] = sum;
-            epi_bar_sync();
-            sum = (s_red[row] + s_red[128 + row]) + (s_red[256 + row] + s_red[384 + row]);
+            s_red[512 + cq * 128 + row] = sum;
+            quarter_bar_sync(q);
+            sum = (s_red[512 + row] + s_red[512 + 128 + row]) + (s_red[512 + 256 + row] + s_red[512 + 384 + row]);
             const float sc = 1.0f / sum;
             const int64_t f = (int64_t)tile * TC_M + row;
             if (f < a.nf) {
                 if (a.post) {
-                    float *dst = a.post + f * a.ldpost;
+                    float *dst = a.post + f * a.ldpost + n0;
 #pragma unroll
-                    for (int g = 0; g < MAXG; ++g) {
-                        const int n0 = (g_beg + g) * 8;
-                        if (g_beg + g < g_end) {
-                            if (n0 < a.ldpost)
-                                *reinterpret_cast<float4 *>(dst + n0) = make_float4(o[g * 8] * sc, o[g * 8 + 1] * sc, o[g * 8 + 2] * sc, o[g * 8 + 3] * sc);
-                            if (n0 + 4 < a.ldpost)
-                                *reinterpret_cast<float4 *>(dst + n0 + 4) = make_float4(o[g * 8 + 4] * sc, o[g * 8 + 5] * sc, o[g * 8 + 6] * sc, o[g * 8 + 7] * sc);
-                        }
+                    for (int j = 0; j < NQ / 4; ++j)
+                        if (n0 + 4 * j < a.ldpost)
+                            *reinterpret_cast<float4 *>(dst + 4 * j) = make_float4(o[4 * j] * sc, o[4 * j + 1] * sc, o[4 * j + 2] * sc, o[4 * j + 3] * sc);
+                    if (a.logp) {   // decoder soft function (srec.cpp:1088-1097), fused: ln p for the token passing kernel
+                        float *ldst = a.logp + f * a.ldpost + n0;
+#pragma unroll
+                        for (int j = 0; j < NQ / 4; ++j)
+                            if (n0 + 4 * j < a.ldpost)
+                                *reinterpret_cast<float4 *>(ldst + 4 * j) = make_float4(__logf(o[4 * j] * sc), __logf(o[4 * j + 1] * sc),
+                                                                                       __logf(o[4 * j + 2] * sc), __logf(o[4 * j + 3] * sc));
                     }
                 } else {
-                    // merger input: sLn(p), merger input normalisation, fp16, 16-byte chunks of the merger's X image
+                    // merger input: sLn(p), merger input normalisation, fp16, 8-byte pieces of the merger's X image
+                    const int nlim = (a.nout + 7) & ~7;   // this net's share of the image: nout rounded up to 8 columns
 #pragma unroll
-                    for (int g = 0; g < MAXG; ++g) {
-                        if (g_beg + g < g_end) {
-                            const int cm0 = a.xm_col0 + (g_beg + g) * 8;
-                            float xn[8];
+                    for (int j = 0; j < NQ / 4; ++j) {
+                        const int n = n0 + 4 * j;
+                        if (n < nlim) {
+                            const float4 m4 = *reinterpret_cast<const float4 *>(s_mm + n), d4 = *reinterpret_cast<const float4 *>(s_md + n);
+                            const float mm[4] = {m4.x, m4.y, m4.z, m4.w}, md[4] = {d4.x, d4.y, d4.z, d4.w};
+                            float xn[4];
 #pragma unroll
-                            for (int i = 0; i < 8; ++i) {
-                                const float p = o[g * 8 + i] * sc;
+                            for (int i = 0; i < 4; ++i) {
+                                const float p = o[4 * j + i] * sc;
                                 const float v = p > 0.0f ? __logf(p) : 0.0f;
-                                xn[i] = (g_beg + g) * 8 + i < a.nout ? (v - a.mmean[cm0 + i]) * a.mdev[cm0 + i] : 0.0f;
+                                xn[i] = n + i < a.nout ? (v - mm[i]) * md[i] : 0.0f;
                             }
-                            uint8_t *blk = a.xm_img + ((size_t)tile * a.xm_kb1 + (cm0 >> 6)) * TC_BLK;
-                            const uint4 v = make_uint4(pack_half2(xn[0], xn[1]), pack_half2(xn[2], xn[3]), pack_half2(xn[4], xn[5]), pack_half2(xn[6], xn[7]));
-                            *reinterpret_cast<uint4 *>(blk + (size_t)row * 128 + ((((cm0 >> 3) & 7) ^ (row & 7)) << 4)) = v;
+                            const int cm = a.xm_col0 + n;
+                            uint8_t *blk = a.xm_img + ((size_t)tile * a.xm_kb1 + (cm >> 6)) * TC_BLK;
+                            *reinterpret_cast<uint2 *>(blk + (size_t)row * 128 + ((((cm >> 3) & 7) ^ (row & 7)) << 4) + ((cm & 4) << 1)) =
+                                make_uint2(pack_half2(xn[0], xn[1]), pack_half2(xn[2], xn[3]));
                         }
                     }
                 }
             }
-            epi_bar_sync();  // s_red is reused by the next tile
         }
     }
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) {
+    if (warp == WARP_MMA) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
     }
@@ -531,9 +573,9 @@ __global__ void k_build_bias(const float *__restrict__ b1, int nhid, float *sig_
                              int nout, float *b2p, int N2P)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    // r = 2^23 + 2^14 * t,  t = -(x + b1)/ln2 + Ct : the addend must be an integer (ulp is 1 in [2^23, 2^24))
-    if (i < nhidP) sig_k[i] = (float)(8388608.0 + rint(16384.0 * (kCt - (double)(i < nhid ? b1[i] : 0.0f) / 0.69314718055994530942)));
-    if (i < N2P) b2p[i] = i < nout ? b2[i] : 0.0f;
+    // u = sat(t / TMAX),  t = -(x + b1)/ln2 + Ct : the per-unit addend of the epilogue's FFMA.SAT
+    if (i < nhidP) sig_k[i] = (float)((kCt - (double)(i < nhid ? b1[i] : 0.0f) / kLn2) / (double)kSigTmax);
+    if (i < N2P) b2p[i] = i < nout ? b2[i] : -FLT_MAX;   // padding columns drop out of the softmax (D(-huge) = 0)
 }
 
 struct TcState {
@@ -567,9 +609,11 @@ int mlp_tc_prepare(phn_ctx *c)
         const int64_t t1 = (int64_t)im.NCH * 128 * im.KB1 * 64, t2 = (int64_t)im.N2P * im.NCH * 128;
         k_build_w1_img<<<(unsigned)((t1 + 255) / 256), 256, 0, c->stream>>>(n.w1, n.nin, n.nhid, n.nin4, im.w1_img, im.KB1, im.NCH, split, split8);
         if (i == 2) {
-            PHN_CUDA(c, cudaMalloc((void **)&im.mean_img, sizeof(float) * im.KB1 * 64));
-            PHN_CUDA(c, cudaMalloc((void **)&im.dev_img, sizeof(float) * im.KB1 * 64));
-            k_build_mnorm<<<(im.KB1 * 64 + 127) / 128, 128, 0, c->stream>>>(n.mean, n.dev, n.nin, im.mean_img, im.dev_img, im.KB1 * 64, split, split8);
+            // + 16: a band net reads its N2P (= outputs rounded up to 16) columns starting at its first image column
+            const int ncol = im.KB1 * 64 + 16;
+            PHN_CUDA(c, cudaMalloc((void **)&im.mean_img, sizeof(float) * ncol));
+            PHN_CUDA(c, cudaMalloc((void **)&im.dev_img, sizeof(float) * ncol));
+            k_build_mnorm<<<(ncol + 127) / 128, 128, 0, c->stream>>>(n.mean, n.dev, n.nin, im.mean_img, im.dev_img, ncol, split, split8);
         }
         k_build_w2_img<<<(unsigned)((t2 + 255) / 256), 256, 0, c->stream>>>(n.w2, n.nhid, n.nout, n.nhid4, im.w2_img, im.N2P, im.NCH);
         const int nb = im.NCH * 128 > im.N2P ? im.NCH * 128 : im.N2P;
@@ -622,11 +666,12 @@ static int run_net_tc(phn_ctx *c, int which, const uint8_t *x_img, int64_t nf, i
         a.mmean = st.net[2].mean_img; a.mdev = st.net[2].dev_img;
     } else {
         a.post = (float *)c->d_post.p + f0 * c->ldp; a.ldpost = c->ldp;
+        a.logp = c->fuse_logp ? (float *)c->d_logp.p + f0 * c->ldp : nullptr;
     }
     // shared memory plan: X (KB1 blocks) + H (2 blocks) + constants + barriers are fixed; the rest is split
     // between the W2 ring (S2 k-blocks of N2P x 64) and the W1 ring (S1 blocks of 128 x 64)
     const size_t w2_blk = (size_t)im.N2P * 128;
-    const size_t fixed = (size_t)im.KB1 * TC_BLK + 2 * TC_BLK + sizeof(float) * ((size_t)im.NCH * TC_NC + im.N2P + 4 * 128) + 48 * 8 + 1024;
+    const size_t fixed = (size_t)im.KB1 * TC_BLK + 2 * TC_BLK + sizeof(float) * ((size_t)im.NCH * TC_NC + 3 * im.N2P + 8 * 128) + 48 * 8 + 1024;
     const size_t max_smem = 232448;
     int S1 = 0, S2 = 4;
     for (; S2 >= 2; --S2) {

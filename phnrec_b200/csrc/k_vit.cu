@@ -24,8 +24,8 @@
 namespace phn {
 
 struct VitArgs {
-    const float *logp;       // [total_frames][ncols] log-posteriors of the 3P decoder-visible columns (K-log)
-    int ncols;
+    const float *logp;       // [total_frames][ld] log-posteriors; the decoder reads the first 3P columns of a row
+    int ld;
     const int64_t *frame_off;
     int n_utt, P, H;
     int64_t total_frames;
@@ -52,16 +52,15 @@ __device__ __forceinline__ float ord2f(unsigned o)
 // K-log: the decoder soft function SoftLog (srec.h:192-195, applied srec.cpp:1088-1097) = glibc logf,
 // no guard, on the 3P columns the decoder reads.  Fully parallel, so the sequential kernel below is
 // pure token passing; a penalty sweep reuses the same log-posteriors.
-__global__ void __launch_bounds__(256) k_log_post(const float *__restrict__ post, int ldp, int ncols, int64_t total,
+__global__ void __launch_bounds__(256) k_log_post(const float *__restrict__ post, int ldp, int ncols, int64_t frames,
                                                  float *__restrict__ logp)
 {
     __shared__ double s_logtab[32];
     logf_table_to_smem(s_logtab, threadIdx.x, blockDim.x);
     __syncthreads();
-    const int64_t frames = total / ncols;
     const int lane = threadIdx.x & 31;
     for (int64_t f = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); f < frames; f += (int64_t)gridDim.x * 8)   // one warp per row
-        for (int cidx = lane; cidx < ncols; cidx += 32) logp[f * ncols + cidx] = logf_glibc(post[f * ldp + cidx], s_logtab);
+        for (int cidx = lane; cidx < ncols; cidx += 32) logp[f * ldp + cidx] = logf_glibc(post[f * ldp + cidx], s_logtab);
 }
 
 template <int PPL>
@@ -102,7 +101,7 @@ __global__ void __launch_bounds__(32) k_viterbi(VitArgs a)
 #pragma unroll
                 for (int j = 0; j < 3; ++j) {
                     const int i = lane + 32 * r;
-                    obs[q][r][j] = (valid[r] && tb + q < T) ? a.logp[(f0 + tb + q) * a.ncols + 3 * i + j] : 0.0f;
+                    obs[q][r][j] = (valid[r] && tb + q < T) ? a.logp[(f0 + tb + q) * a.ld + 3 * i + j] : 0.0f;
                 }
 
 #pragma unroll
@@ -262,19 +261,18 @@ int launch_viterbi(phn_ctx *c, const float *d_pen, int n_pen)
     const int nseg = c->n_utt * n_pen;
     if (nseg == 0) return PHN_OK;
     const int ncols = 3 * c->P;
-    const int64_t total = c->total_frames * ncols;
-    int rc = ensure(c, c->d_logp, sizeof(float) * (size_t)(total ? total : 1));
+    int rc = ensure(c, c->d_logp, sizeof(float) * (size_t)(c->total_frames ? c->total_frames : 1) * c->ldp);
     if (rc) return rc;
-    if (total) {
+    if (c->total_frames && !c->logp_valid) {   // (the tensor-core merger writes ln p itself when it feeds the decoder directly)
         int64_t blocks = (c->total_frames + 7) / 8;
         if (blocks > (int64_t)c->num_sms * 16) blocks = (int64_t)c->num_sms * 16;
-        k_log_post<<<(unsigned)blocks, 256, 0, c->stream>>>((const float *)c->d_post.p, c->ldp, ncols, total, (float *)c->d_logp.p);
+        k_log_post<<<(unsigned)blocks, 256, 0, c->stream>>>((const float *)c->d_post.p, c->ldp, ncols, c->total_frames, (float *)c->d_logp.p);
         PHN_CUDA(c, cudaGetLastError());
         c->k_launches[PHN_K_VIT] += 1;
     }
     VitArgs a;
     a.logp = (const float *)c->d_logp.p;
-    a.ncols = ncols;
+    a.ld = c->ldp;
     a.frame_off = (const int64_t *)c->d_frame_off.p;
     a.n_utt = c->n_utt; a.P = c->P; a.H = c->hist;
     a.total_frames = c->total_frames;
