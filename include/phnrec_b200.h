@@ -154,6 +154,10 @@ enum { PHN_K_WAVE = 0, PHN_K_MEAN, PHN_K_STC, PHN_K_MLP, PHN_K_VIT, PHN_K_COUNT 
 int phn_set_profiling(phn_ctx *ctx, int on);
 int phn_last_timing(phn_ctx *ctx, float ms[PHN_K_COUNT], int64_t launches[PHN_K_COUNT]);
 
+/* Kernel-development aid: which >= 0 arms a clock64() timeline of one tile of tensor-core net `which`
+ * (0/1 band nets, 2 merger) for the following calls; which < 0 disarms and copies the 16 x 16 table out. */
+int phn_debug_tc_timeline(phn_ctx *ctx, int which, long long *out);
+
 /* N2: online normaliser arithmetic (Normalization::ProcessFrame, norm.cpp:216-234;
  * ChannelNormParams::{Accum,Update,Norm}, norm.cpp:92-148) on a [frames][nbanks] host
  * matrix, in place on the device: estimate over the first `interval` frames, apply after. */

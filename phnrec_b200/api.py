@@ -9,6 +9,7 @@ Python or CPU fallback.
 from __future__ import annotations
 
 import ctypes as C
+import os
 import struct
 import subprocess
 from pathlib import Path
@@ -37,7 +38,8 @@ class _Info(C.Structure):
 
 
 def lib_path() -> Path:
-    return PKG / "lib" / "libphnrec_b200.so"
+    # PHNREC_B200_LIB: kernel-development aid (A/B runs of two builds on the same GPU box)
+    return Path(os.environ["PHNREC_B200_LIB"]) if os.environ.get("PHNREC_B200_LIB") else PKG / "lib" / "libphnrec_b200.so"
 
 
 def build(verbose: bool = False) -> None:

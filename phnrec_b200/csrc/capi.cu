@@ -62,7 +62,8 @@ static int upload_net(phn_ctx *c, int which)
     d.w1h = nullptr; d.w2h = nullptr; d.nhidP = 0; d.noutP = 0;
     // fp16 image width: the merger's image keeps its two halves 8-column aligned (k_mlp_tc.cu)
     const int kin = which == 2 ? (c->hnet[0].nout + 7) / 8 * 8 + c->hnet[0].nout : h.nin;
-    d.k1P = (kin + 63) / 64 * 64;
+    d.kin = kin;
+    d.k1P = (kin + 2 + 63) / 64 * 64;   // + the two bias columns (k_mlp_tc.cu)
     int rc;
     if ((rc = upload(c, &d.w1, h.w1.data(), h.w1.size()))) return rc;
     if ((rc = upload(c, &d.w2, h.w2.data(), h.w2.size()))) return rc;
@@ -172,7 +173,9 @@ static int run_posteriors(phn_ctx *c)
         if (c->fuse_logp && (rc = ensure(c, c->d_logp, sizeof(float) * (size_t)F * c->ldp))) return rc;
         if ((rc = ensure(c, c->d_x0h, sizeof(__half) * ch * c->net[0].k1P))) return rc;
         if ((rc = ensure(c, c->d_x1h, sizeof(__half) * ch * c->net[1].k1P))) return rc;
+        const void *xm_before = c->d_xmh.p;
         if ((rc = ensure(c, c->d_xmh, sizeof(__half) * ch * c->net[2].k1P))) return rc;
+        if (c->d_xmh.p != xm_before && (rc = mlp_tc_fill_merger_bias(c, (int64_t)(c->d_xmh.cap / (sizeof(__half) * c->net[2].k1P)) / 128 * 128))) return rc;
     } else {
         if ((rc = ensure(c, c->d_x0, sizeof(float) * ch * c->net[0].kp))) return rc;
         if ((rc = ensure(c, c->d_x1, sizeof(float) * ch * c->net[1].kp))) return rc;
@@ -384,6 +387,7 @@ void phn_destroy(phn_ctx *c)
     for (auto *b : bufs)
         if (b->p) cudaFree(b->p);
     mlp_tc_release(c);
+    if (c->tc_dbg) cudaFree(c->tc_dbg);
     for (int i = 0; i < 3; ++i) {
         DevNet &d = c->net[i];
         void *ps[] = {d.w1, d.w2, d.b1, d.b2, d.mean, d.dev, d.w1h, d.w2h};
@@ -639,6 +643,25 @@ int phn_recognize(phn_ctx *c, const void *audio, const int64_t *byte_off, int n_
     if ((rc = phn_recognize_device(c, c->d_audio.p, byte_off, n_utt))) return rc;
     if (frame_off_out) memcpy(frame_off_out, c->h_frame_off.data(), sizeof(int64_t) * (n_utt + 1));
     return phn_fetch_labels(c, labels, label_cap, label_off);
+}
+
+// Debug aid (not part of the stable ABI surface used by the reference binding): the next tensor-core launches of
+// net `which` record clock64() timestamps of CTA 0's second tile into a 16 x 16 table; which < 0 reads it back.
+int phn_debug_tc_timeline(phn_ctx *c, int which, long long *out /*[256]*/)
+{
+    if (!c) return PHN_ERR_ARG;
+    PHN_CUDA(c, cudaSetDevice(c->device));
+    if (which >= 0) {
+        if (!c->tc_dbg) PHN_CUDA(c, cudaMalloc(&c->tc_dbg, 256 * sizeof(long long)));
+        PHN_CUDA(c, cudaMemsetAsync(c->tc_dbg, 0, 256 * sizeof(long long), c->stream));
+        c->tc_dbg_net = which;
+        return PHN_OK;
+    }
+    c->tc_dbg_net = -1;
+    if (!c->tc_dbg || !out) return PHN_ERR_ARG;
+    PHN_CUDA(c, cudaMemcpyAsync(out, c->tc_dbg, 256 * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
+    PHN_CUDA(c, cudaStreamSynchronize(c->stream));
+    return PHN_OK;
 }
 
 int phn_online_norm(phn_ctx *c, float *x, int64_t frames, int nbanks, int interval, int mean_norm, int var_norm)

@@ -47,6 +47,7 @@ struct DevNet {
     // fp16 tensor-core images (K-major, zero padded): w1h [nhidP][k1P], w2h [noutP][nhidP]
     __half *w1h, *w2h;
     int k1P, nhidP, noutP;
+    int kin;   // data columns of the fp16 activation image; columns kin, kin+1 hold the constant 1.0 that multiplies b1
 };
 
 struct DevTables {
@@ -73,6 +74,8 @@ struct phn_ctx {
     int mlp_mode = PHN_MLP_EXACT_FP32;
     void *tc = nullptr;  // tensor-core mode state (k_mlp_tc.cu)
     int force_exact_wave = 0;
+    void *tc_dbg = nullptr;   // device buffer for the tensor-core kernel's debug timeline (phn_debug_tc_timeline)
+    int tc_dbg_net = -1;
     int fuse_logp = 0;   // tensor-core merger also writes ln(posteriors) for the decoder (audio -> labels path)
     int logp_valid = 0;  // d_logp already holds the decoder's input for the current batch  // phn_mel always returns the reference's bits, whatever the MLP mode
     std::vector<std::string> phonemes;
@@ -126,6 +129,7 @@ int launch_mlp_tc(phn_ctx *c, int64_t f0, int64_t nf);                     // k_
 int launch_viterbi(phn_ctx *c, const float *d_pen, int n_pen);             // k_vit.cu
 int launch_compact_labels(phn_ctx *c, int nseg);                           // k_vit.cu
 int launch_synth(phn_ctx *c, void *d_audio, int64_t bytes_per_utt, int n_utt, uint64_t seed);  // k_synth.cu
+int mlp_tc_fill_merger_bias(phn_ctx *c, int64_t rows);                     // constant-1 bias columns of the merger image
 int mlp_tc_prepare(phn_ctx *c);                                            // fp16 weight images (k_mlp_tc.cu)
 void mlp_tc_release(phn_ctx *c);
 }  // namespace phn

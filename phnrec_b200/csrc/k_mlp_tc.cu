@@ -2,18 +2,28 @@
 //     P = fsoftmax(b2 + fsig(b1 + X W1^T) W2^T)
 // on the 5th-generation tensor cores (tcgen05.mma, fp16 operands, fp32 accumulators in TMEM),
 // operands streamed into shared memory by the TMA engine (cp.async.bulk + mbarrier), the hidden
-// layer never leaving the SM.  Replaces NeuralNet::Forward (nn.cpp:872-950), fexp_sigmoid /
+// layer never leaving the SM (TMEM accumulator -> registers -> TMEM operand).  Replaces NeuralNet::Forward (nn.cpp:872-950), fexp_sigmoid /
 // fexp_softmax_v (fexp.h:33-78) and Traps::CalcInputFeaturesForMerger (traps.cpp:435-461) in
 // reduced precision; the measured deviation from the exact mode is stated in DESIGN.md.
 //
-// Tiling: a CTA owns 128 frames (UMMA M = 128, cta_group::1) and walks the hidden layer in
-// chunks of 128 units:
-//     G1(c): D1[c&1] (TMEM, 128 cols)  = X[128 x K1] . W1[c]^T          K1/16 MMAs of 128x128x16
-//     E1(c): H = fp16(fsig(D1 + b1))  -> shared memory (K-major, 128B swizzle)     8 epilogue warps
-//     G2(c): D2 (TMEM, N2P cols)     += H[128 x 128] . W2[:, c]^T       8 MMAs of 128xN2Px16
-//     E2   : softmax over D2 + b2, then posteriors (merger) or ln + merger input norm (band nets)
-// Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer + TMEM allocator, warps 2..9 = epilogue
-// (two warps per TMEM lane quarter, each taking half of the columns).
+// Tiling: a persistent CTA (one per SM) owns 128-frame tiles (UMMA M = 128, cta_group::1) and walks the hidden
+// layer in chunks of 128 units; over the CTA's linear chunk sequence g:
+//     G1(g): D1[g&1] (TMEM, 128 cols)  = X[128 x K1] . W1[c]^T    K1/16 SS MMAs 128x128x16 (A, B in shared memory);
+//                                        b1 rides along as two extra K columns (fp16 hi + lo) against X columns = 1
+//     E1(g): H = fp16(fsig(D1))        -> TMEM (64 cols, fp16 pairs)             16 epilogue warps
+//     G2(g): D2 (TMEM, N2P cols)      += H[128 x 128] . W2[:, c]^T  8 TS MMAs 128xN2Px16 (A = H from TMEM)
+//     E2   : softmax over D2 + b2 once per tile, then posteriors + ln(posteriors) (merger) or
+//            ln + merger input normalisation -> fp16 merger X image (band nets)
+// Warp roles: warps 0..15 = epilogue (warp&3 = TMEM lane quarter, warp>>2 = column quarter), warp 16 = TMA
+// producer, warp 17 = MMA issuer + TMEM allocator.  What shaped the schedule (measured with tools/umma_bench.cu
+// and tools/tc_timeline.py, numbers in DESIGN.md):
+//   * an SS MMA costs ~38 + N/2 clk, a TS MMA ~9 + N/2; interleaved SS/TS streams from ONE thread run at ~N/2,
+//     two issuing threads serialise -> one issuer, burst(g) = G2(g) interleaved block-wise with G1(g+2),
+//     software pipelined across chunks and tiles; E1(g+1) runs on the epilogue warps meanwhile;
+//   * the issuer is instruction-fetch bound (it shares an SMSP and its L0 I-cache with four epilogue warps):
+//     the steady-state burst is a lean single-instance path with chunk-level "full" barriers (3 waits per burst);
+//   * the producer is a non-blocking two-cursor state machine (W1 + X stream, W2 stream), rings sized so that
+//     the next chunk of both streams is resident while the current one is multiplied.
 //
 // All operands live in global memory as ready-made shared-memory images: 16 KB blocks of
 // [128 rows x 64 fp16] in the canonical K-major SWIZZLE_128B layout (16-byte chunk index XOR
@@ -70,6 +80,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
         "D_%=:\n\t}"
         ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
+__device__ __forceinline__ uint32_t mbar_try(uint64_t *bar, uint32_t parity)
+{
+    uint32_t ok;
+    // test_wait, not try_wait: try_wait may suspend the thread for a hardware time-out when the phase is still open
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok;
+}
 __device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar)
 {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -89,6 +107,35 @@ __device__ __forceinline__ void umma_f16_ss(uint32_t tmem_d, uint64_t adesc, uin
         "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// D[tmem] (+)= A[tmem] . B[smem]^T   (A: 128 lanes x K/2 32-bit columns holding fp16 pairs; B K-major)
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// Issue-slot-lean forms for the steady-state path: descriptors travel as their low words (start address field +
+// LBO) plus one shared high word, the accumulate flag is a compile-time constant.
+constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);   // SBO = 1024 B, version 1, SWIZZLE_128B
+template <int ACC>
+__device__ __forceinline__ void umma_ss_lo(uint32_t tmem_d, uint32_t alo, uint32_t blo, uint32_t idesc)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %5, 0;\n\t"
+        "mov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}"
+        ::"r"(tmem_d), "r"(alo), "r"(blo), "r"(kDescHi), "r"(idesc), "n"(ACC) : "memory");
+}
+template <int ACC>
+__device__ __forceinline__ void umma_ts_lo(uint32_t tmem_d, uint32_t tmem_a, uint32_t blo, uint32_t idesc)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 db;\n\tsetp.ne.b32 p, %5, 0;\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "r"(blo), "r"(kDescHi), "r"(idesc), "n"(ACC) : "memory");
 }
 // K-major, SWIZZLE_128B shared-memory matrix descriptor: start address, LBO (unused for swizzled
 // K-major) = 1, SBO = 1024 B between 8-row groups, descriptor version 1 (sm_100), layout type 2.
@@ -122,6 +169,13 @@ PHN_TMEM_LD(tmem_ld32, "x32", 32,
             R4(0), R4(4), R4(8), R4(12), R4(16), R4(20), R4(24), R4(28))
 #undef R4
 #undef PHN_TMEM_LD
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t *v)
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+                 ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
+                   "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ float rcp_approx(float x)
 {
@@ -174,7 +228,6 @@ struct TcArgs {
     const uint8_t *x_img;     // [tiles][KB1][16 KB]  activations, SW128 blocks
     const uint8_t *w1_img;    // [NCH][KB1][16 KB]
     const uint8_t *w2_img;    // [NCH][2][N2P*128 B]
-    const float *sig_k;       // [NCH*128]  per hidden unit: (Ct - b1/ln2) / kSigTmax
     const float *b2;          // [N2P]      output bias; -FLT_MAX in the padding columns
     int n_tiles, KB1, NCH, S1, S2;
     int nks_last;             // k-steps (of 16) actually needed in the last k-block of layer 1
@@ -184,9 +237,17 @@ struct TcArgs {
     float *post; int ldpost;                          // merger: posteriors [nf][ldpost]
     float *logp;                                      // merger: ln(posteriors) [nf][ldpost] for the decoder, or nullptr
     uint8_t *xm_img; int xm_kb1; int xm_col0;         // band nets: merger input image, first column (multiple of 8)
+    long long *dbg;                                   // optional timeline of CTA 0's second tile (tools/tc_timeline.py)
+    int xm_bias;                                      // band 1: its columns nout, nout+1 are the merger's constant-1 bias inputs
     const float *mmean, *mdev;                        // merger input normalisation, indexed by image column
 };
 
+// debug timeline: dbg[(c * 16 + event)] = clock64() for chunk c of CTA 0's second tile
+#define TC_DBG(ev, c)                                                                       \
+    do {                                                                                    \
+        if (a.dbg && blockIdx.x == 0 && tile == (int)gridDim.x) a.dbg[(c) * 16 + (ev)] = clock64(); \
+    } while (0)
+constexpr int TC_MAXS1 = 12;                        // upper bound on W1 ring stages (barrier array size)
 constexpr int TC_EPI_WARPS = 16;                     // warps 0..15: epilogue; 16: TMA producer; 17: MMA issuer
 constexpr int TC_THREADS = (TC_EPI_WARPS + 2) * 32;
 // The SM's warp schedulers favour the highest warp id among eligible warps, so the two warps whose
@@ -206,42 +267,41 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs a)
     uint8_t *sX = smem;                                        // KB1 x 16 KB
     uint8_t *sW1 = sX + (size_t)a.KB1 * TC_BLK;                // S1 x 16 KB ring
     uint8_t *sW2 = sW1 + (size_t)a.S1 * TC_BLK;                // S2 x W2_BLK ring
-    uint8_t *sH = sW2 + (size_t)a.S2 * W2_BLK;                 // 2 x 16 KB
-    float *s_sigk = reinterpret_cast<float *>(sH + 2 * TC_BLK);  // [NCH*128]
-    float *s_b2 = s_sigk + a.NCH * TC_NC;                      // [N2P]
+    float *s_b2 = reinterpret_cast<float *>(sW2 + (size_t)a.S2 * W2_BLK);   // [N2P]
     float *s_mm = s_b2 + N2P;                                  // [N2P] merger input mean  (band nets)
     float *s_md = s_mm + N2P;                                  // [N2P] merger input 1/std (band nets)
     float *s_red = s_md + N2P;                                 // [2][4][128] row max / row sum exchange
     uint64_t *bars = reinterpret_cast<uint64_t *>(s_red + 8 * 128);
     uint64_t *x_full = bars;                 // [8]
     uint64_t *x_empty = bars + 8;            // [1]
-    uint64_t *w1_full = bars + 9;            // [8]
-    uint64_t *w1_empty = bars + 17;          // [8]
-    uint64_t *w2_full = bars + 25;           // [4]
-    uint64_t *w2_empty = bars + 29;          // [4]
-    uint64_t *d1_full = bars + 33;           // [2]
-    uint64_t *d1_empty = bars + 35;          // [2]
-    uint64_t *h_full = bars + 37, *h_empty = bars + 38;
-    uint64_t *d2_full = bars + 39, *d2_empty = bars + 40;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 41);
+    uint64_t *w1_full = bars + 9;            // [TC_MAXS1]
+    uint64_t *w1_empty = w1_full + TC_MAXS1; // [TC_MAXS1]
+    uint64_t *w2_empty = w1_empty + TC_MAXS1; // [4]
+    uint64_t *w1c_full = w2_empty + 4;       // [4] chunk-level: all KB1 k-blocks of layer-1 chunk n have landed (n & 3)
+    uint64_t *w2c_full = w1c_full + 4;       // [2] chunk-level: both k-blocks of layer-2 chunk n have landed (n & 1)
+    uint64_t *d1_full = w2c_full + 2;        // [2]
+    uint64_t *h_full = d1_full + 2, *h_empty = h_full + 1;
+    uint64_t *d2_full = h_empty + 1, *d2_empty = d2_full + 1;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(d2_empty + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    constexpr int WARP_TMA = TC_EPI_WARPS, WARP_MMA = TC_EPI_WARPS + 1;
+    constexpr int WARP_TMA = TC_EPI_WARPS, WARP_MMA = TC_EPI_WARPS + 1, EPI0 = 0;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < 8; ++i) { mbar_init(&x_full[i], 1); mbar_init(&w1_full[i], 1); mbar_init(&w1_empty[i], 1); }
-        for (int i = 0; i < 4; ++i) { mbar_init(&w2_full[i], 1); mbar_init(&w2_empty[i], 1); }
+        for (int i = 0; i < 8; ++i) mbar_init(&x_full[i], 1);
+        for (int i = 0; i < TC_MAXS1; ++i) { mbar_init(&w1_full[i], 1); mbar_init(&w1_empty[i], 1); }
+        for (int i = 0; i < 4; ++i) { mbar_init(&w2_empty[i], 1); mbar_init(&w1c_full[i], a.KB1); }
+        for (int i = 0; i < 2; ++i) mbar_init(&w2c_full[i], 2);
         mbar_init(x_empty, 1);
-        for (int i = 0; i < 2; ++i) { mbar_init(&d1_full[i], 1); mbar_init(&d1_empty[i], TC_EPI_WARPS); }
+        for (int i = 0; i < 2; ++i) mbar_init(&d1_full[i], 1);
         mbar_init(h_full, TC_EPI_WARPS); mbar_init(h_empty, 1);
         mbar_init(d2_full, 1); mbar_init(d2_empty, TC_EPI_WARPS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == WARP_MMA) {  // TMEM: 512 columns (D1 double buffer 2 x 128, D2 up to 192)
+    if (warp == WARP_MMA) {  // TMEM: 512 columns = D1 double buffer 2 x 128 | D2 up to 192 | H 64 (128 fp16 per lane)
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    for (int i = threadIdx.x; i < a.NCH * TC_NC; i += blockDim.x) s_sigk[i] = a.sig_k[i];
     for (int i = threadIdx.x; i < N2P; i += blockDim.x) {
         s_b2[i] = a.b2[i];
         s_mm[i] = a.mmean ? a.mmean[a.xm_col0 + i] : 0.0f;
@@ -253,177 +313,307 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs a)
     const uint32_t tmem = *tmem_slot;
     const uint32_t tD1[2] = {tmem, tmem + 128u};
     const uint32_t tD2 = tmem + 256u;
+    const uint32_t tH = tmem + 448u;
 
     if (warp == WARP_TMA) {
         // ===================================================================== TMA producer
-        // The whole warp walks the loops (warp-uniform control flow); one elected lane issues.
+        // The whole warp walks the loops (warp-uniform control flow); one elected lane issues.  Loads follow the
+        // issuer's consumption order over the CTA's linear chunk sequence g = tile_iter * NCH + c:
+        //   X(tile 0), W1(0), W1(1), then per g:  [X(next tile) if chunk g+2 opens it]  W1(g+2)  W2(g)
         uint32_t ph_x_empty = 0, w1_stage = 0, ph_w1 = 0, w2_stage = 0, ph_w2 = 0;
-        bool first_tile = true;
-        auto load_w1 = [&](int c) {
-            for (int kb = 0; kb < a.KB1; ++kb) {
-                mbar_wait(&w1_empty[w1_stage], ph_w1 ^ 1);
-                if (elect_one()) {
-                    mbar_expect_tx(&w1_full[w1_stage], TC_BLK);
-                    tma_load_1d(sW1 + (size_t)w1_stage * TC_BLK, a.w1_img + ((size_t)c * a.KB1 + kb) * TC_BLK, TC_BLK, &w1_full[w1_stage]);
+        const int my_tiles = blockIdx.x < a.n_tiles ? (a.n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+        const int G = my_tiles * a.NCH;
+        // Normal case (the W1 ring holds a whole chunk): every k-block load of a chunk reports to the chunk's own
+        // "full" barrier, so the issuer waits once per chunk; ring stages are still handed back one by one.
+        // Two independent cursors (layer-1 weights + X, layer-2 weights), each advanced whenever its next ring stage
+        // is free: a blocking in-order producer would sit on the shallow W2 ring and never prefetch W1 ahead.
+        const bool chunk_bar = a.S1 >= a.KB1;
+        uint32_t n1 = 0, n2 = 0;          // chunks fully issued per stream
+        int kb1 = 0, kb2 = 0;             // next k-block inside the current chunk
+        int c1 = 0, c2 = 0, tile1 = blockIdx.x;
+        bool x_done = false, first_x = true;
+        while (n1 < (uint32_t)G || n2 < (uint32_t)G) {
+            if (n1 < (uint32_t)G) {
+                if (c1 == 0 && kb1 == 0 && !x_done) {   // the chunk opens a tile: its X first
+                    if (first_x || mbar_try(x_empty, ph_x_empty)) {
+                        if (!first_x) ph_x_empty ^= 1;
+                        first_x = false;
+                        if (elect_one()) {
+                            for (int kb = 0; kb < a.KB1; ++kb) {
+                                mbar_expect_tx(&x_full[kb], TC_BLK);
+                                tma_load_1d(sX + (size_t)kb * TC_BLK, a.x_img + ((size_t)tile1 * a.KB1 + kb) * TC_BLK, TC_BLK, &x_full[kb]);
+                            }
+                        }
+                        __syncwarp();
+                        x_done = true;
+                    }
+                } else if (mbar_try(&w1_empty[w1_stage], ph_w1 ^ 1)) {
+                    if (elect_one()) {
+                        uint64_t *fb = chunk_bar ? &w1c_full[n1 & 3] : &w1_full[w1_stage];
+                        mbar_expect_tx(fb, TC_BLK);
+                        tma_load_1d(sW1 + (size_t)w1_stage * TC_BLK, a.w1_img + ((size_t)c1 * a.KB1 + kb1) * TC_BLK, TC_BLK, fb);
+                    }
+                    __syncwarp();
+                    if (++w1_stage == (uint32_t)a.S1) { w1_stage = 0; ph_w1 ^= 1; }
+                    if (++kb1 == a.KB1) {
+                        kb1 = 0; ++n1; x_done = false;
+                        if (++c1 == a.NCH) { c1 = 0; tile1 += gridDim.x; }
+                    }
                 }
-                __syncwarp();
-                if (++w1_stage == (uint32_t)a.S1) { w1_stage = 0; ph_w1 ^= 1; }
             }
-        };
-        auto load_w2 = [&](int c) {
-            for (int kb = 0; kb < 2; ++kb) {
-                mbar_wait(&w2_empty[w2_stage], ph_w2 ^ 1);
+            if (n2 < (uint32_t)G && mbar_try(&w2_empty[w2_stage], ph_w2 ^ 1)) {
                 if (elect_one()) {
-                    mbar_expect_tx(&w2_full[w2_stage], W2_BLK);
-                    tma_load_1d(sW2 + (size_t)w2_stage * W2_BLK, a.w2_img + ((size_t)c * 2 + kb) * W2_BLK, W2_BLK, &w2_full[w2_stage]);
+                    mbar_expect_tx(&w2c_full[n2 & 1], W2_BLK);
+                    tma_load_1d(sW2 + (size_t)w2_stage * W2_BLK, a.w2_img + ((size_t)c2 * 2 + kb2) * W2_BLK, W2_BLK, &w2c_full[n2 & 1]);
                 }
                 __syncwarp();
                 if (++w2_stage == (uint32_t)a.S2) { w2_stage = 0; ph_w2 ^= 1; }
-            }
-        };
-        for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
-            // Later tiles: the first weight chunk is prefetched while the previous tile still owns X -
-            // but only when it fits the ring entirely (KB1 <= S1); otherwise the issuer, which waits
-            // for X before it frees a ring stage, and this warp would wait for each other.
-            const bool prefetch_w1 = !first_tile && a.KB1 <= a.S1;
-            if (prefetch_w1) load_w1(0);
-            if (!first_tile) { mbar_wait(x_empty, ph_x_empty); ph_x_empty ^= 1; }
-            if (elect_one()) {
-                for (int kb = 0; kb < a.KB1; ++kb) {
-                    mbar_expect_tx(&x_full[kb], TC_BLK);
-                    tma_load_1d(sX + (size_t)kb * TC_BLK, a.x_img + ((size_t)tile * a.KB1 + kb) * TC_BLK, TC_BLK, &x_full[kb]);
+                if (++kb2 == 2) {
+                    kb2 = 0; ++n2;
+                    if (++c2 == a.NCH) c2 = 0;
                 }
-            }
-            __syncwarp();
-            if (!prefetch_w1) load_w1(0);
-            first_tile = false;
-            for (int c = 0; c < a.NCH; ++c) {   // same order as the issuer consumes: G1(c+1) before G2(c)
-                if (c + 1 < a.NCH) load_w1(c + 1);
-                load_w2(c);
             }
         }
     } else if (warp == WARP_MMA) {
         // ===================================================================== MMA issuer
-        // Warp-uniform loops; the MMAs and commits of one k-block are issued by the elected lane.
+        // One thread issues every MMA of the CTA (two issuing threads serialise in the tensor pipe; measured with
+        // tools/umma_bench.cu).  Layer 1 reads both operands from shared memory (SS, ~38 + N/2 clk each when run
+        // alone), layer 2 takes H from TMEM (TS, ~9 + N/2); interleaved one to one the pair runs at the nominal
+        // N/2 per MMA because the SS operand fetch overlaps the TS math.  So the issue schedule over the CTA's
+        // linear chunk sequence g is software pipelined:   burst(g) = G2(g) interleaved with G1(g+2),
+        // issued as soon as E1(g) has published H(g) - which also means D1[g & 1] has been read and is free for
+        // G1(g+2).  E1(g+1) (whose D1 came from the previous burst) runs on the epilogue warps meanwhile.
         const uint32_t idesc1 = make_idesc(TC_NC), idesc2 = make_idesc(N2P);
-        uint32_t ph_x_full = 0, w1_stage = 0, ph_w1 = 0, w2_stage = 0, ph_w2 = 0, ph_h_full = 0, ph_d2_empty = 0;
-        uint32_t ph_d1_empty0 = 0, ph_d1_empty1 = 0, n_d1_use0 = 0, n_d1_use1 = 0;
-        bool first_d2 = true;
-        // descriptors differ only in the 14-bit start-address field: base + (byte offset >> 4)
+        uint32_t ph_x_full = 0, w1_stage = 0, ph_w1 = 0, w2_stage = 0, ph_h_full = 0, ph_d2_empty = 0;
         const uint64_t dX = make_sw128_desc(smem_u32(sX)), dW1 = make_sw128_desc(smem_u32(sW1));
-        const uint64_t dW2 = make_sw128_desc(smem_u32(sW2)), dH = make_sw128_desc(smem_u32(sH));
-        for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
-            auto g1 = [&](int c) {
-                const int b = c & 1;
-                if (b == 0) {
-                    if (n_d1_use0 > 0) { mbar_wait(&d1_empty[0], ph_d1_empty0); ph_d1_empty0 ^= 1; }
-                    ++n_d1_use0;
-                } else {
-                    if (n_d1_use1 > 0) { mbar_wait(&d1_empty[1], ph_d1_empty1); ph_d1_empty1 ^= 1; }
-                    ++n_d1_use1;
-                }
-                const uint32_t td = b ? tD1[1] : tD1[0];
-                for (int kb = 0; kb < a.KB1; ++kb) {
-                    if (c == 0) mbar_wait(&x_full[kb], ph_x_full);
-                    mbar_wait(&w1_full[w1_stage], ph_w1);
-                    tc_fence_after();
-                    if (elect_one()) {
-                        const int nks = kb == a.KB1 - 1 ? a.nks_last : 4;
-                        const uint64_t ad = dX + (uint64_t)((kb * TC_BLK) >> 4), bd = dW1 + (uint64_t)((w1_stage * TC_BLK) >> 4);
-                        for (int ks = 0; ks < nks; ++ks) umma_f16_ss(td, ad + 2 * ks, bd + 2 * ks, idesc1, (kb | ks) ? 1u : 0u);
-                        tc_commit(&w1_empty[w1_stage]);
-                        if (kb == a.KB1 - 1) {
-                            tc_commit(&d1_full[b]);
-                            if (c == a.NCH - 1) tc_commit(x_empty);
+        const uint64_t dW2 = make_sw128_desc(smem_u32(sW2));
+        const int my_tiles = blockIdx.x < a.n_tiles ? (a.n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+        const int G = my_tiles * a.NCH;
+        // A chunk's layer-1 k-blocks are issued in groups of GK blocks: the whole chunk when the W1 ring can hold
+        // it (S1 >= KB1, the normal case), else half a ring at a time (wide merger nets next to a wide X tile).
+        const int GK = a.S1 >= a.KB1 ? a.KB1 : (a.S1 / 2 > 0 ? a.S1 / 2 : 1);
+        // burst: layer 2 of chunk g2 (g2 < 0: none) interleaved one to one with layer 1 of chunk g1 (g1 < 0: none)
+        // (c2 / c1: the chunks' positions inside their tiles; first2: no D2 has been handed to the epilogue yet)
+        const bool chunk_bar = a.S1 >= a.KB1;
+        uint32_t n1 = 0, n2 = 0;   // running chunk counters of the two weight streams (chunk-level "full" barriers)
+        int c2 = 0, c1 = 0, d1buf = 0;
+        bool first2 = true;
+        int tile = blockIdx.x;   // (only for the debug timeline)
+        auto burst = [&](bool do_g2, bool do_g1) {
+            const int g1 = do_g1 ? d1buf : -1;   // only the D1 buffer index of the layer-1 chunk matters below
+            uint32_t w2b = w2_stage + 1;
+            if (w2b == (uint32_t)a.S2) w2b = 0;
+            const bool opens = do_g1 && c1 == 0;
+            const bool wait_d2 = do_g2 && c2 == 0 && !first2;
+            bool g2_pending = do_g2;
+            for (int kb0 = 0; kb0 < (g1 >= 0 ? a.KB1 : 1); kb0 += GK) {
+                const int nkb = g1 >= 0 ? (a.KB1 - kb0 < GK ? a.KB1 - kb0 : GK) : 0;
+                // operands of this group: weights first (loaded long ago in the steady state), H last (the freshest)
+                if (nkb > 0) {
+                    if (chunk_bar) {
+                        mbar_wait(&w1c_full[n1 & 3], (n1 >> 2) & 1);
+                    } else {
+                        uint32_t st = w1_stage, ph = ph_w1;
+                        for (int k = 0; k < nkb; ++k) {
+                            mbar_wait(&w1_full[st], ph);
+                            if (++st == (uint32_t)a.S1) { st = 0; ph ^= 1; }
                         }
                     }
-                    __syncwarp();
-                    if (++w1_stage == (uint32_t)a.S1) { w1_stage = 0; ph_w1 ^= 1; }
+                    if (opens)
+                        for (int k = 0; k < nkb; ++k) mbar_wait(&x_full[kb0 + k], ph_x_full);
                 }
-            };
-            auto g2 = [&](int c) {
-                if (c == 0 && !first_d2) { mbar_wait(d2_empty, ph_d2_empty); ph_d2_empty ^= 1; }
-                first_d2 = false;
-                mbar_wait(h_full, ph_h_full); ph_h_full ^= 1;
-                for (int kb = 0; kb < 2; ++kb) {
-                    mbar_wait(&w2_full[w2_stage], ph_w2);
-                    tc_fence_after();
-                    if (elect_one()) {
-                        const uint64_t ad = dH + (uint64_t)((kb * TC_BLK) >> 4), bd = dW2 + (uint64_t)((w2_stage * W2_BLK) >> 4);
+                if (g2_pending) {
+                    mbar_wait(&w2c_full[n2 & 1], (n2 >> 1) & 1);
+                    if (wait_d2) mbar_wait(d2_empty, ph_d2_empty);
+                    mbar_wait(h_full, ph_h_full);
+                }
+                tc_fence_after();
+                if (elect_one()) {
+                    // interleave in blocks of four k-steps (one k-block): SS block of layer 1, TS block of layer 2, ...
+                    const int nblk = g2_pending ? (nkb > 2 ? nkb : 2) : nkb;
+                    uint32_t st = w1_stage;
+                    for (int k = 0; k < nblk; ++k) {
+                        if (k < nkb) {
+                            const int kb = kb0 + k;
+                            const int nks = kb == a.KB1 - 1 ? a.nks_last : 4;
+                            const uint64_t ad = dX + (uint64_t)((kb * TC_BLK) >> 4), bd = dW1 + (uint64_t)((st * TC_BLK) >> 4);
 #pragma unroll
-                        for (int ks = 0; ks < 4; ++ks) umma_f16_ss(tD2, ad + 2 * ks, bd + 2 * ks, idesc2, (c | kb | ks) ? 1u : 0u);
-                        tc_commit(&w2_empty[w2_stage]);
-                        if (kb == 1) {
-                            tc_commit(h_empty);
-                            if (c == a.NCH - 1) tc_commit(d2_full);
+                            for (int ks = 0; ks < 4; ++ks)
+                                if (ks < nks) umma_f16_ss(tD1[g1 & 1], ad + 2 * ks, bd + 2 * ks, idesc1, (kb | ks) ? 1u : 0u);
+                            tc_commit(&w1_empty[st]);
+                            if (++st == (uint32_t)a.S1) st = 0;
+                        }
+                        if (g2_pending && k < 2) {   // A = H[:, 64 k + 16 ks .. +15] = 8 TMEM columns per k-step
+                            const uint32_t w2s = k ? w2b : w2_stage;
+                            const uint64_t bd = dW2 + (uint64_t)((w2s * W2_BLK) >> 4);
+#pragma unroll
+                            for (int ks = 0; ks < 4; ++ks)
+                                umma_f16_ts(tD2, tH + (uint32_t)(k * 4 + ks) * 8u, bd + 2 * ks, idesc2, (c2 | k | ks) ? 1u : 0u);
+                            tc_commit(&w2_empty[w2s]);
                         }
                     }
-                    __syncwarp();
-                    if (++w2_stage == (uint32_t)a.S2) { w2_stage = 0; ph_w2 ^= 1; }
+                    if (g2_pending) {
+                        tc_commit(h_empty);
+                        if (c2 == a.NCH - 1) tc_commit(d2_full);
+                    }
+                    if (g1 >= 0 && kb0 + nkb == a.KB1) {
+                        tc_commit(&d1_full[g1 & 1]);
+                        if (c1 == a.NCH - 1) tc_commit(x_empty);
+                    }
                 }
-            };
-            g1(0);
-            for (int c = 0; c < a.NCH; ++c) {
-                if (c + 1 < a.NCH) g1(c + 1);
-                g2(c);
+                __syncwarp();
+                w1_stage += nkb;
+                if (w1_stage >= (uint32_t)a.S1) { w1_stage -= a.S1; ph_w1 ^= 1; }
+                if (g2_pending) {
+                    ph_h_full ^= 1;
+                    if (wait_d2) ph_d2_empty ^= 1;
+                    w2_stage += 2;
+                    if (w2_stage >= (uint32_t)a.S2) w2_stage -= a.S2;
+                    g2_pending = false;
+                }
             }
-            ph_x_full ^= 1;
+            if (opens) ph_x_full ^= 1;
+            if (do_g1) { ++n1; d1buf ^= 1; if (++c1 == a.NCH) c1 = 0; }
+            if (do_g2) { ++n2; first2 = false; if (++c2 == a.NCH) c2 = 0; }
+        };
+        // Steady state (both chunks inside their tiles, W1 chunk resident): the same burst with nothing but the
+        // instructions it needs - this warp shares an SMSP (and its 6 KB L0 instruction cache) with four epilogue
+        // warps, and every instruction-fetch miss of the issuer is a bubble in the tensor pipe.
+        const uint32_t xlo = (uint32_t)dX, w1lo = (uint32_t)dW1, w2lo = (uint32_t)dW2;
+        auto lean = [&]() {
+            if (lane == 0) TC_DBG(3, c2);
+            mbar_wait(&w1c_full[n1 & 3], (n1 >> 2) & 1);
+            mbar_wait(&w2c_full[n2 & 1], (n2 >> 1) & 1);
+            mbar_wait(h_full, ph_h_full);
+            if (lane == 0) TC_DBG(5, c2);   // operands there
+            tc_fence_after();
+            uint32_t w2b = w2_stage + 1;
+            if (w2b == (uint32_t)a.S2) w2b = 0;
+            if (elect_one()) {
+                const uint32_t td1 = tD1[d1buf];
+                uint32_t st = w1_stage, alo = xlo;
+                for (int k = 0; k < a.KB1; ++k) {
+                    const uint32_t blo = w1lo + st * (TC_BLK >> 4);
+                    if (k == 0) umma_ss_lo<0>(td1, alo, blo, idesc1); else umma_ss_lo<1>(td1, alo, blo, idesc1);
+                    if (k < a.KB1 - 1 || a.nks_last > 1) umma_ss_lo<1>(td1, alo + 2, blo + 2, idesc1);
+                    if (k < a.KB1 - 1 || a.nks_last > 2) umma_ss_lo<1>(td1, alo + 4, blo + 4, idesc1);
+                    if (k < a.KB1 - 1 || a.nks_last > 3) umma_ss_lo<1>(td1, alo + 6, blo + 6, idesc1);
+                    tc_commit(&w1_empty[st]);
+                    if (++st == (uint32_t)a.S1) st = 0;
+                    alo += TC_BLK >> 4;
+                    if (k < 2) {   // A = H[:, 64 k + 16 ks .. +15] = 8 TMEM columns per k-step
+                        const uint32_t w2s = k ? w2b : w2_stage;
+                        const uint32_t b2lo = w2lo + w2s * (W2_BLK >> 4);
+                        const uint32_t ta = tH + (uint32_t)k * 32u;
+                        umma_ts_lo<1>(tD2, ta, b2lo, idesc2);
+                        umma_ts_lo<1>(tD2, ta + 8u, b2lo + 2, idesc2);
+                        umma_ts_lo<1>(tD2, ta + 16u, b2lo + 4, idesc2);
+                        umma_ts_lo<1>(tD2, ta + 24u, b2lo + 6, idesc2);
+                        tc_commit(&w2_empty[w2s]);
+                    }
+                }
+                tc_commit(h_empty);
+                if (c2 == a.NCH - 1) tc_commit(d2_full);
+                tc_commit(&d1_full[d1buf]);
+                if (c1 == a.NCH - 1) tc_commit(x_empty);
+                TC_DBG(13, c2);                 // all MMAs and commits issued
+            }
+            __syncwarp();
+            w1_stage += a.KB1;
+            if (w1_stage >= (uint32_t)a.S1) { w1_stage -= a.S1; ph_w1 ^= 1; }
+            ph_h_full ^= 1;
+            w2_stage += 2;
+            if (w2_stage >= (uint32_t)a.S2) w2_stage -= a.S2;
+            ++n1; d1buf ^= 1; if (++c1 == a.NCH) c1 = 0;
+            ++n2; if (++c2 == a.NCH) c2 = 0;
+        };
+        const bool lean_ok = chunk_bar && a.KB1 >= 2;
+        int pro = G > 1 ? 2 : G;   // prologue: layer 1 of the first two chunks on its own
+        for (int g = 0; g < G;) {
+            bool t_g2[2] = {false, false}, t_g1[2] = {true, true};
+            int nt = 1;
+            const int c = c2;
+            if (pro > 0) {
+                --pro;
+            } else {
+                const bool has_g1 = g + 2 < G;
+                if (lane == 0) TC_DBG(2, c);   // burst starts
+                if (has_g1 && c1 != 0 && c2 != 0 && lean_ok) {
+                    lean();
+                    ++g;
+                    if (lane == 0) TC_DBG(4, c);   // burst issued
+                    if (c2 == 0) tile += gridDim.x;
+                    continue;
+                }
+                if (has_g1 && c1 == 0) {
+                    // G1(g+2) opens a tile whose X may still be in flight: do not hold layer 2 of this chunk back for it
+                    nt = 2; t_g2[0] = true; t_g1[0] = false;
+                } else {
+                    t_g2[0] = true; t_g1[0] = has_g1;
+                }
+                ++g;
+            }
+            for (int t = 0; t < nt; ++t) burst(t_g2[t], t_g1[t]);   // (one call site: one copy of the general path)
+            if (c2 == 0 && t_g2[0]) tile += gridDim.x;
         }
     } else {
         // ===================================================================== epilogue warps
         const int q = warp & 3;                  // TMEM lane quarter this warp may access
-        const int cq = warp >> 2;                // column quarter 0..3
+        const int cq = (warp - EPI0) >> 2;       // column quarter 0..3
         const int row = q * 32 + lane;           // tile row == TMEM lane
         const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
         uint32_t ph_d1_full0 = 0, ph_d1_full1 = 0, ph_h_empty = 0, ph_d2_full = 0;
         bool first_h = true;
-        // H[row][cq*32 .. +31] lives in k-block cq>>1 of the H operand, 16-byte chunks (cq&1)*4 .. +3
-        uint8_t *hrow = sH + (size_t)(cq >> 1) * TC_BLK + (size_t)row * 128;
-        const int hchunk0 = (cq & 1) * 4;
-        const float sigA = (float)(-1.0 / (kLn2 * (double)kSigTmax));
+        int g = 0;   // the CTA's linear chunk index: D1 buffer = g & 1 (NCH may be odd)
+        // H[row][cq*32 .. +31] (fp16 pairs) = TMEM lane `row`, columns cq*16 .. +15 of the H operand
+        // u = sat(t / TMAX), t = -(x + b1)/ln2 + Ct; b1 is already inside x (two extra K columns of layer 1)
+        const float sigA = (float)(-1.0 / (kLn2 * (double)kSigTmax)), sigB = (float)(kCt / (double)kSigTmax);
         for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
-            for (int c = 0; c < a.NCH; ++c) {
-                const int b = c & 1;
+            for (int c = 0; c < a.NCH; ++c, ++g) {
+                const int b = g & 1;
+                if (threadIdx.x == EPI0 * 32) TC_DBG(8, c);    // e1: waiting for D1
                 if (b == 0) { mbar_wait(&d1_full[0], ph_d1_full0); ph_d1_full0 ^= 1; }
                 else        { mbar_wait(&d1_full[1], ph_d1_full1); ph_d1_full1 ^= 1; }
                 tc_fence_after();
-                uint32_t acc[32];
-                tmem_ld32((b ? tD1[1] : tD1[0]) + lane_addr + cq * 32, acc);
-                tmem_ld_wait();
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&d1_empty[b]);
+                if (threadIdx.x == EPI0 * 32) TC_DBG(9, c);    // e1: D1 seen
+                // (no "D1 free" signal: the issuer reuses D1[b] only after this chunk's H has been published)
                 // fsig(x) = 1 / (1 + D(-x - b1)); two reciprocals share one MUFU: 1/a = a' / (a a'), 1/a' = a / (a a')
                 uint32_t hp[16];
-                const float4 *kp = reinterpret_cast<const float4 *>(s_sigk + c * TC_NC + cq * 32);
+                {
+                    uint32_t acc[32];
+                    tmem_ld32((b ? tD1[1] : tD1[0]) + lane_addr + cq * 32, acc);
+                    tmem_ld_wait();
 #pragma unroll
-                for (int g = 0; g < 8; ++g) {
-                    const float4 k4 = kp[g];
-                    const float a0 = 1.0f + fexp_from_u(fma_sat(__uint_as_float(acc[g * 4 + 0]), sigA, k4.x), kSigTmax);
-                    const float a1 = 1.0f + fexp_from_u(fma_sat(__uint_as_float(acc[g * 4 + 1]), sigA, k4.y), kSigTmax);
-                    const float a2 = 1.0f + fexp_from_u(fma_sat(__uint_as_float(acc[g * 4 + 2]), sigA, k4.z), kSigTmax);
-                    const float a3 = 1.0f + fexp_from_u(fma_sat(__uint_as_float(acc[g * 4 + 3]), sigA, k4.w), kSigTmax);
-                    const float r01 = rcp_approx(a0 * a1), r23 = rcp_approx(a2 * a3);
-                    hp[g * 2] = pack_half2(r01 * a1, r01 * a0);
-                    hp[g * 2 + 1] = pack_half2(r23 * a3, r23 * a2);
+                    for (int g4 = 0; g4 < 8; ++g4) {
+                        const float a0 = 1.0f + fexp_from_u(fma_sat(__uint_as_float(acc[g4 * 4 + 0]), sigA, sigB), kSigTmax);
+                        const float a1 = 1.0f + fexp_from_u(fma_sat(__uint_as_float(acc[g4 * 4 + 1]), sigA, sigB), kSigTmax);
+                        const float a2 = 1.0f + fexp_from_u(fma_sat(__uint_as_float(acc[g4 * 4 + 2]), sigA, sigB), kSigTmax);
+                        const float a3 = 1.0f + fexp_from_u(fma_sat(__uint_as_float(acc[g4 * 4 + 3]), sigA, sigB), kSigTmax);
+                        const float r01 = rcp_approx(a0 * a1), r23 = rcp_approx(a2 * a3);
+                        hp[g4 * 2] = pack_half2(r01 * a1, r01 * a0);
+                        hp[g4 * 2 + 1] = pack_half2(r23 * a3, r23 * a2);
+                    }
                 }
+                if (threadIdx.x == EPI0 * 32) TC_DBG(10, c);   // e1: math done
                 if (!first_h) { mbar_wait(h_empty, ph_h_empty); ph_h_empty ^= 1; }
                 first_h = false;
-#pragma unroll
-                for (int ch = 0; ch < 4; ++ch) {
-                    const uint4 v = make_uint4(hp[ch * 4], hp[ch * 4 + 1], hp[ch * 4 + 2], hp[ch * 4 + 3]);
-                    *reinterpret_cast<uint4 *>(hrow + (((hchunk0 + ch) ^ (row & 7)) << 4)) = v;
-                }
-                fence_proxy_async();
+                if (threadIdx.x == EPI0 * 32) TC_DBG(11, c);   // e1: H buffer free
+                tc_fence_after();
+                tmem_st16(tH + lane_addr + cq * 16, hp);
+                tmem_st_wait();
+                tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(h_full);
+                if (threadIdx.x == EPI0 * 32) TC_DBG(12, c);   // e1: H published
             }
             // ------------------------------------------------------------- E2: softmax + outputs
             // column quarter cq owns D2 columns [cq*NQ, (cq+1)*NQ); the 4 warps of a row quarter
             // exchange row max / row sum through shared memory and their own named barrier
             const int n0 = cq * NQ;
+            if (threadIdx.x == EPI0 * 32) TC_DBG(13, 0);       // e2: waiting for D2
             mbar_wait(d2_full, ph_d2_full); ph_d2_full ^= 1;
             tc_fence_after();
+            if (threadIdx.x == EPI0 * 32) TC_DBG(14, 0);       // e2: D2 seen
             float o[NQ];
             {
                 uint32_t raw[NQ];
@@ -492,7 +682,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs a)
                             for (int i = 0; i < 4; ++i) {
                                 const float p = o[4 * j + i] * sc;
                                 const float v = p > 0.0f ? __logf(p) : 0.0f;
-                                xn[i] = n + i < a.nout ? (v - mm[i]) * md[i] : 0.0f;
+                                xn[i] = n + i < a.nout ? (v - mm[i]) * md[i] : ((a.xm_bias && n + i < a.nout + 2) ? 1.0f : 0.0f);
                             }
                             const int cm = a.xm_col0 + n;
                             uint8_t *blk = a.xm_img + ((size_t)tile * a.xm_kb1 + (cm >> 6)) * TC_BLK;
@@ -502,6 +692,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs a)
                     }
                 }
             }
+            if (threadIdx.x == EPI0 * 32) TC_DBG(15, 0);       // e2 done
         }
     }
 
@@ -518,7 +709,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs a)
 // ------------------------------------------------------------------------------------------------
 struct TcNetImages {
     uint8_t *w1_img = nullptr, *w2_img = nullptr;
-    float *sig_k = nullptr, *b2 = nullptr;
+    float *b2 = nullptr;
     float *mean_img = nullptr, *dev_img = nullptr;   // merger only: input normalisation in image column order
     int KB1 = 0, NCH = 0, N2P = 0, nks_last = 4, kin = 0;
 };
@@ -533,8 +724,10 @@ __host__ __device__ __forceinline__ int img_col_to_input(int k, int split, int s
     return k - split8 + split;
 }
 
-__global__ void k_build_w1_img(const float *__restrict__ w1, int nin, int nhid, int nin4, uint8_t *img, int KB1, int NCH,
-                               int split, int split8)
+// Layer-1 weight image.  Image columns kin, kin+1 carry the bias: fp16(b1) and fp16(b1 - fp16(b1)); the
+// activations hold 1.0 in both, so the tensor core adds b1 with ~2^-22 relative error.
+__global__ void k_build_w1_img(const float *__restrict__ w1, const float *__restrict__ b1, int nin, int nhid, int nin4,
+                               uint8_t *img, int KB1, int NCH, int split, int split8, int kin)
 {
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t total = (int64_t)NCH * 128 * KB1 * 64;
@@ -542,9 +735,21 @@ __global__ void k_build_w1_img(const float *__restrict__ w1, int nin, int nhid, 
     const int k = (int)(idx % (KB1 * 64));
     const int n = (int)(idx / (KB1 * 64));
     const int ki = img_col_to_input(k, split, split8);
-    const float v = (n < nhid && ki >= 0 && ki < nin) ? w1[(int64_t)n * nin4 + ki] : 0.0f;
+    float v = (n < nhid && k < kin && ki >= 0 && ki < nin) ? w1[(int64_t)n * nin4 + ki] : 0.0f;
+    if (n < nhid && k == kin) v = b1[n];
+    if (n < nhid && k == kin + 1) v = b1[n] - __half2float(__float2half_rn(b1[n]));
     const int c = n >> 7, r = n & 127, kb = k >> 6, cc = k & 63;
     *reinterpret_cast<__half *>(img + ((size_t)c * KB1 + kb) * TC_BLK + sw128_off(r, cc)) = __float2half_rn(v);
+}
+
+// Constant-1 bias inputs of an activation image (columns kin, kin+1 of every row of every tile).
+__global__ void k_fill_bias_cols(uint8_t *img, int64_t rows, int KB1, int kin)
+{
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= rows * 2) return;
+    const int64_t row = idx >> 1;
+    const int k = kin + (int)(idx & 1);
+    *reinterpret_cast<__half *>(img + ((size_t)(row >> 7) * KB1 + (k >> 6)) * TC_BLK + sw128_off((int)(row & 127), k & 63)) = __float2half_rn(1.0f);
 }
 
 __global__ void k_build_w2_img(const float *__restrict__ w2, int nhid, int nout, int nhid4, uint8_t *img, int N2P, int NCH)
@@ -569,12 +774,9 @@ __global__ void k_build_mnorm(const float *__restrict__ mean, const float *__res
     dev_img[k] = (ki >= 0 && ki < nin) ? dev[ki] : 0.0f;
 }
 
-__global__ void k_build_bias(const float *__restrict__ b1, int nhid, float *sig_k, int nhidP, const float *__restrict__ b2,
-                             int nout, float *b2p, int N2P)
+__global__ void k_build_bias(const float *__restrict__ b2, int nout, float *b2p, int N2P)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    // u = sat(t / TMAX),  t = -(x + b1)/ln2 + Ct : the per-unit addend of the epilogue's FFMA.SAT
-    if (i < nhidP) sig_k[i] = (float)((kCt - (double)(i < nhid ? b1[i] : 0.0f) / kLn2) / (double)kSigTmax);
     if (i < N2P) b2p[i] = i < nout ? b2[i] : -FLT_MAX;   // padding columns drop out of the softmax (D(-huge) = 0)
 }
 
@@ -592,11 +794,11 @@ int mlp_tc_prepare(phn_ctx *c)
         DevNet &n = c->net[i];
         TcNetImages &im = st.net[i];
         const int split = i == 2 ? c->net[0].nout : 0, split8 = (split + 7) / 8 * 8;
-        im.kin = i == 2 ? split8 + split : n.nin;   // image columns that carry data
-        im.KB1 = (im.kin + 63) / 64;
+        im.kin = i == 2 ? split8 + split : n.nin;   // image columns that carry data; two bias columns follow
+        im.KB1 = (im.kin + 2 + 63) / 64;
         im.NCH = (n.nhid + 127) / 128;
         im.N2P = (n.nout + 15) / 16 * 16;
-        const int rem = im.kin - (im.KB1 - 1) * 64;
+        const int rem = im.kin + 2 - (im.KB1 - 1) * 64;
         im.nks_last = (rem + 15) / 16;
         if (im.KB1 > 8) return fail(c, PHN_ERR_UNSUPPORTED, "tensor-core mode: more than 512 network inputs\n");
         if (im.N2P != 128 && im.N2P != 144 && im.N2P != 160 && im.N2P != 192)
@@ -604,10 +806,9 @@ int mlp_tc_prepare(phn_ctx *c)
         const size_t w1b = (size_t)im.NCH * im.KB1 * TC_BLK, w2b = (size_t)im.NCH * 2 * im.N2P * 128;
         PHN_CUDA(c, cudaMalloc((void **)&im.w1_img, w1b));
         PHN_CUDA(c, cudaMalloc((void **)&im.w2_img, w2b));
-        PHN_CUDA(c, cudaMalloc((void **)&im.sig_k, sizeof(float) * im.NCH * 128));
         PHN_CUDA(c, cudaMalloc((void **)&im.b2, sizeof(float) * im.N2P));
         const int64_t t1 = (int64_t)im.NCH * 128 * im.KB1 * 64, t2 = (int64_t)im.N2P * im.NCH * 128;
-        k_build_w1_img<<<(unsigned)((t1 + 255) / 256), 256, 0, c->stream>>>(n.w1, n.nin, n.nhid, n.nin4, im.w1_img, im.KB1, im.NCH, split, split8);
+        k_build_w1_img<<<(unsigned)((t1 + 255) / 256), 256, 0, c->stream>>>(n.w1, n.b1, n.nin, n.nhid, n.nin4, im.w1_img, im.KB1, im.NCH, split, split8, im.kin);
         if (i == 2) {
             // + 16: a band net reads its N2P (= outputs rounded up to 16) columns starting at its first image column
             const int ncol = im.KB1 * 64 + 16;
@@ -616,8 +817,7 @@ int mlp_tc_prepare(phn_ctx *c)
             k_build_mnorm<<<(ncol + 127) / 128, 128, 0, c->stream>>>(n.mean, n.dev, n.nin, im.mean_img, im.dev_img, ncol, split, split8);
         }
         k_build_w2_img<<<(unsigned)((t2 + 255) / 256), 256, 0, c->stream>>>(n.w2, n.nhid, n.nout, n.nhid4, im.w2_img, im.N2P, im.NCH);
-        const int nb = im.NCH * 128 > im.N2P ? im.NCH * 128 : im.N2P;
-        k_build_bias<<<(nb + 255) / 256, 256, 0, c->stream>>>(n.b1, n.nhid, im.sig_k, im.NCH * 128, n.b2, n.nout, im.b2, im.N2P);
+        k_build_bias<<<(im.N2P + 255) / 256, 256, 0, c->stream>>>(n.b2, n.nout, im.b2, im.N2P);
         PHN_CUDA(c, cudaGetLastError());
         n.w1h = reinterpret_cast<__half *>(im.w1_img);  // owned by the context from here on (freed in phn_destroy)
         n.w2h = reinterpret_cast<__half *>(im.w2_img);
@@ -633,7 +833,6 @@ void mlp_tc_release(phn_ctx *c)
     if (!c->tc) return;
     TcState *st = static_cast<TcState *>(c->tc);
     for (auto &im : st->net) {
-        if (im.sig_k) cudaFree(im.sig_k);
         if (im.b2) cudaFree(im.b2);
         if (im.mean_img) cudaFree(im.mean_img);
         if (im.dev_img) cudaFree(im.dev_img);
@@ -657,13 +856,15 @@ static int run_net_tc(phn_ctx *c, int which, const uint8_t *x_img, int64_t nf, i
     const TcNetImages &im = st.net[which];
     const DevNet &n = c->net[which];
     TcArgs a{};
-    a.x_img = x_img; a.w1_img = im.w1_img; a.w2_img = im.w2_img; a.sig_k = im.sig_k; a.b2 = im.b2;
+    a.x_img = x_img; a.w1_img = im.w1_img; a.w2_img = im.w2_img; a.b2 = im.b2;
     a.n_tiles = (int)((nf + TC_M - 1) / TC_M);
+    a.dbg = (which == c->tc_dbg_net) ? (long long *)c->tc_dbg : nullptr;
     a.KB1 = im.KB1; a.NCH = im.NCH; a.nks_last = im.nks_last; a.nf = nf; a.nout = n.nout;
     if (which < 2) {
         a.post = nullptr;
         a.xm_img = (uint8_t *)c->d_xmh.p; a.xm_kb1 = st.net[2].KB1; a.xm_col0 = which * ((n.nout + 7) / 8 * 8);
         a.mmean = st.net[2].mean_img; a.mdev = st.net[2].dev_img;
+        a.xm_bias = which == 1;
     } else {
         a.post = (float *)c->d_post.p + f0 * c->ldp; a.ldpost = c->ldp;
         a.logp = c->fuse_logp ? (float *)c->d_logp.p + f0 * c->ldp : nullptr;
@@ -671,16 +872,18 @@ static int run_net_tc(phn_ctx *c, int which, const uint8_t *x_img, int64_t nf, i
     // shared memory plan: X (KB1 blocks) + H (2 blocks) + constants + barriers are fixed; the rest is split
     // between the W2 ring (S2 k-blocks of N2P x 64) and the W1 ring (S1 blocks of 128 x 64)
     const size_t w2_blk = (size_t)im.N2P * 128;
-    const size_t fixed = (size_t)im.KB1 * TC_BLK + 2 * TC_BLK + sizeof(float) * ((size_t)im.NCH * TC_NC + 3 * im.N2P + 8 * 128) + 48 * 8 + 1024;
+    const size_t fixed = (size_t)im.KB1 * TC_BLK + sizeof(float) * (3 * (size_t)im.N2P + 8 * 128) + 64 * 8 + 1024;
     const size_t max_smem = 232448;
-    int S1 = 0, S2 = 4;
-    for (; S2 >= 2; --S2) {
-        if (fixed + S2 * w2_blk + 2 * (size_t)TC_BLK > max_smem) continue;
-        S1 = (int)((max_smem - fixed - S2 * w2_blk) / TC_BLK);
-        if (S1 >= (S2 == 2 ? 2 : 4)) break;
-    }
-    if (S2 < 2 || S1 < 2) return fail(c, PHN_ERR_UNSUPPORTED, "tensor-core mode: shared memory plan does not fit\n");
-    if (S1 > 8) S1 = 8;
+    // Ring plan.  Both weight streams want two chunks resident (the one being multiplied and the one in flight):
+    // W2 ring 4 stages, W1 ring 2 KB1 stages.  When that does not fit (wide merger next to its wide X tile), W2
+    // falls back to 3 and then 2 stages and W1 takes whatever is left (at least 2 stages; the issuer then walks a
+    // chunk in groups, see k_mlp_tc).
+    int S2 = 4;
+    if (fixed + S2 * w2_blk + 2 * (size_t)im.KB1 * TC_BLK > max_smem) S2 = 3;
+    if (fixed + S2 * w2_blk + (size_t)(im.KB1 + 1) * TC_BLK > max_smem) S2 = 2;
+    if (fixed + S2 * w2_blk + 2 * (size_t)TC_BLK > max_smem) return fail(c, PHN_ERR_UNSUPPORTED, "tensor-core mode: shared memory plan does not fit\n");
+    int S1 = (int)((max_smem - fixed - S2 * w2_blk) / TC_BLK);
+    if (S1 > TC_MAXS1) S1 = TC_MAXS1;
     a.S1 = S1; a.S2 = S2;
     const size_t smem_bytes = fixed + (size_t)S1 * TC_BLK + (size_t)S2 * w2_blk;
     int grid = a.n_tiles < c->num_sms ? a.n_tiles : c->num_sms;
@@ -697,6 +900,17 @@ static int run_net_tc(phn_ctx *c, int which, const uint8_t *x_img, int64_t nf, i
     }
     c->k_launches[PHN_K_MLP] += 1;
     return rc;
+}
+
+// The merger's activation image is written by the band nets' epilogues; its constant-1 bias columns that lie
+// outside what those epilogues write are filled once per (re)allocation.
+int mlp_tc_fill_merger_bias(phn_ctx *c, int64_t rows)
+{
+    TcState &st = *static_cast<TcState *>(c->tc);
+    if (rows <= 0) return PHN_OK;
+    k_fill_bias_cols<<<(unsigned)((rows * 2 + 255) / 256), 256, 0, c->stream>>>((uint8_t *)c->d_xmh.p, rows, st.net[2].KB1, st.net[2].kin);
+    PHN_CUDA(c, cudaGetLastError());
+    return PHN_OK;
 }
 
 int launch_mlp_tc(phn_ctx *c, int64_t f0, int64_t nf)

@@ -151,7 +151,9 @@ __global__ void __launch_bounds__(256) k_stc(StcArgs a_)
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const int c0 = ch * 8 + 2 * i;
-                const __half2 p = __floats2half2_rn(c0 < nin ? src[c0] : 0.0f, c0 + 1 < nin ? src[c0 + 1] : 0.0f);
+                // columns nin, nin+1: the constant 1.0 that multiplies the two bias columns of the layer-1 weight image
+                const __half2 p = __floats2half2_rn(c0 < nin ? src[c0] : (c0 < nin + 2 ? 1.0f : 0.0f),
+                                                    c0 + 1 < nin ? src[c0 + 1] : (c0 + 1 < nin + 2 ? 1.0f : 0.0f));
                 h[i] = *reinterpret_cast<const unsigned *>(&p);
             }
             const int r = (int)(fl & 127);
