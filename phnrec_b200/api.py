@@ -88,6 +88,7 @@ _SYMS = [
     ("phn_set_profiling", C.c_int, [C.c_void_p, C.c_int]),
     ("phn_last_timing", C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int64)]),
     ("phn_online_norm", C.c_int, [C.c_void_p, _f32p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int]),
+    ("phn_debug_tc_timeline", C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     ("phn_version", C.c_char_p, []),
     ("phn_device_count", C.c_int, []),
 ]

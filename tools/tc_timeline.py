@@ -23,7 +23,6 @@ for _ in range(2):
     rec.recognize_device(d, boff)
 rec.sync()
 L = rec._L
-L.phn_debug_tc_timeline.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
 L.phn_debug_tc_timeline(rec._h, net, None)
 rec.recognize_device(d, boff)
 rec.sync()
