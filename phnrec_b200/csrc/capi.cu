@@ -170,7 +170,7 @@ static int run_posteriors(phn_ctx *c)
     c->logp_valid = 0;
     if (tc) {
         if ((rc = mlp_tc_prepare(c))) return rc;
-        if (c->fuse_logp && (rc = ensure(c, c->d_logp, sizeof(float) * (size_t)F * c->ldp))) return rc;
+        if (c->fuse_logp && (rc = ensure(c, c->d_logp, sizeof(float) * (size_t)((F + 127) / 128 * 128 + 128) * c->ldp))) return rc;
         if ((rc = ensure(c, c->d_x0h, sizeof(__half) * ch * c->net[0].k1P))) return rc;
         if ((rc = ensure(c, c->d_x1h, sizeof(__half) * ch * c->net[1].k1P))) return rc;
         const void *xm_before = c->d_xmh.p;
@@ -189,6 +189,7 @@ static int run_posteriors(phn_ctx *c)
         { StageTimer t(c, PHN_K_MLP); if ((rc = tc ? launch_mlp_tc(c, f0, nf) : launch_mlp_exact(c, f0, nf))) return rc; }
     }
     c->logp_valid = tc && c->fuse_logp;
+    c->post_valid = !c->logp_valid;
     return PHN_OK;
 }
 
@@ -543,6 +544,9 @@ int phn_fetch_mel(phn_ctx *c, float *mel_out)
 int phn_fetch_posteriors(phn_ctx *c, float *post_out)
 {
     if (!c || !post_out) return PHN_ERR_ARG;
+    if (!c->post_valid)
+        return fail(c, PHN_ERR_ARG, "no posteriors to fetch: the last call was the fused audio -> labels path of the tensor-core mode "
+                                    "(it hands ln p straight to the decoder); use phn_posteriors()\n");
     PHN_CUDA(c, cudaSetDevice(c->device));
     const size_t rowb = sizeof(float) * c->net[2].nout;
     if (c->total_frames)
@@ -627,6 +631,7 @@ int phn_decode(phn_ctx *c, const float *post, const int64_t *frame_off, int n_ut
     if (c->total_frames)
         PHN_CUDA(c, cudaMemcpy2DAsync(c->d_post.p, sizeof(float) * c->ldp, post, rowb, rowb, (size_t)c->total_frames, cudaMemcpyHostToDevice, c->stream));
     c->logp_valid = 0;
+    c->post_valid = 1;
     if ((rc = run_decode(c, penalties, n_pen))) return rc;
     return phn_fetch_labels(c, labels, label_cap, label_off);
 }

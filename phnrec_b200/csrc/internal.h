@@ -77,6 +77,7 @@ struct phn_ctx {
     void *tc_dbg = nullptr;   // device buffer for the tensor-core kernel's debug timeline (phn_debug_tc_timeline)
     int tc_dbg_net = -1;
     int fuse_logp = 0;   // tensor-core merger also writes ln(posteriors) for the decoder (audio -> labels path)
+    int post_valid = 0;  // d_post holds the linear posteriors of the current batch
     int logp_valid = 0;  // d_logp already holds the decoder's input for the current batch  // phn_mel always returns the reference's bits, whatever the MLP mode
     std::vector<std::string> phonemes;
     float win[32];

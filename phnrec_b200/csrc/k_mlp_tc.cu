@@ -52,6 +52,17 @@ __host__ __device__ __forceinline__ uint32_t sw128_off(int r, int cc)
     return (uint32_t)r * 128u + ((((uint32_t)cc >> 3) ^ ((uint32_t)r & 7u)) << 4) + ((uint32_t)cc & 7u) * 2u;
 }
 
+// The merger's activation image is M-major ("MN-major" A operand): its writers are the band nets' epilogues, whose
+// threads own one tile ROW each (TMEM lane = row), so a warp store of one COLUMN must land on consecutive bytes.
+// Canonical UMMA MN-major SWIZZLE_128B layout, per tile: [k / 8][row / 64][k % 8][128 B = 64 rows], 16-byte chunk
+// index XOR k % 8; a 64-column block is 16 KB like the K-major one, one k-step of 16 is 4 KB.
+//   descriptor: LBO = 1024 B (next 64 rows), SBO = 2048 B (next 8 columns)
+__host__ __device__ __forceinline__ uint32_t mn128_off(int r, int k)
+{
+    return ((uint32_t)k >> 3) * 2048u + ((uint32_t)r >> 6) * 1024u + ((uint32_t)k & 7u) * 128u +
+           (((((uint32_t)r & 63u) >> 3) ^ ((uint32_t)k & 7u)) << 4) + ((uint32_t)r & 7u) * 2u;
+}
+
 // ------------------------------------------------------------------------------------------------
 // PTX wrappers
 // ------------------------------------------------------------------------------------------------
@@ -80,6 +91,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
         "D_%=:\n\t}"
         ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
+// Warp-uniform wait: the loop condition is a vote, so the compiler sees uniform control flow around it and may keep
+// warp-uniform values (descriptors, ring positions) in uniform registers across the wait.
+__device__ __forceinline__ void mbar_wait_u(uint64_t *bar, uint32_t parity)
+{
+    uint32_t ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!__all_sync(0xffffffffu, ok));
+}
 __device__ __forceinline__ uint32_t mbar_try(uint64_t *bar, uint32_t parity)
 {
     uint32_t ok;
@@ -93,9 +114,17 @@ __device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ void l2_prefetch(const void *src_gmem, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src_gmem), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit_u(uint32_t bar_saddr)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_saddr) : "memory");
+}
 __device__ __forceinline__ void tc_commit(uint64_t *bar)
 {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -120,13 +149,13 @@ __device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, ui
 // LBO) plus one shared high word, the accumulate flag is a compile-time constant.
 constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);   // SBO = 1024 B, version 1, SWIZZLE_128B
 template <int ACC>
-__device__ __forceinline__ void umma_ss_lo(uint32_t tmem_d, uint32_t alo, uint32_t blo, uint32_t idesc)
+__device__ __forceinline__ void umma_ss_lo(uint32_t tmem_d, uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t idesc)
 {
     asm volatile(
-        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %5, 0;\n\t"
-        "mov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}"
-        ::"r"(tmem_d), "r"(alo), "r"(blo), "r"(kDescHi), "r"(idesc), "n"(ACC) : "memory");
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %6, 0;\n\t"
+        "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+        ::"r"(tmem_d), "r"(alo), "r"(ahi), "r"(blo), "r"(kDescHi), "r"(idesc), "n"(ACC) : "memory");
 }
 template <int ACC>
 __device__ __forceinline__ void umma_ts_lo(uint32_t tmem_d, uint32_t tmem_a, uint32_t blo, uint32_t idesc)
@@ -149,10 +178,21 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t saddr)
     d |= (uint64_t)2 << 61;
     return d;
 }
-// instruction descriptor: fp16 x fp16 -> fp32, both K-major, M = 128, N = n
-__host__ __device__ constexpr uint32_t make_idesc(int n)
+// M-major ("MN-major") SWIZZLE_128B A operand (mn128_off): LBO = 1024 B, SBO = 2048 B
+__device__ __forceinline__ uint64_t make_mn128_desc(uint32_t saddr)
 {
-    return (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)(1024u >> 4) << 16;
+    d |= (uint64_t)(2048u >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// instruction descriptor: fp16 x fp16 -> fp32, B K-major, A K-major or M-major (bit 15), M = 128, N = n
+__host__ __device__ constexpr uint32_t make_idesc(int n, bool a_mn = false)
+{
+    return (1u << 4) | (0u << 7) | (0u << 10) | ((a_mn ? 1u : 0u) << 15) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
 }
 #define PHN_TMEM_LD(NAME, SHAPE, N, OUTS, ...)                                                        \
     __device__ __forceinline__ void NAME(uint32_t taddr, uint32_t *v)                                  \
@@ -235,7 +275,9 @@ struct TcArgs {
     int nout;
     // outputs
     float *post; int ldpost;                          // merger: posteriors [nf][ldpost]
-    float *logp;                                      // merger: ln(posteriors) [nf][ldpost] for the decoder, or nullptr
+    float *logp;                                      // merger: ln(posteriors) for the decoder, TILED [tile][ldpost][128 rows], or nullptr
+    int64_t logp_tile0;                               //         global tile index of this launch's first tile
+    int x_mn;                                         // the activation image is M-major (mn128_off): the merger's
     uint8_t *xm_img; int xm_kb1; int xm_col0;         // band nets: merger input image, first column (multiple of 8)
     long long *dbg;                                   // optional timeline of CTA 0's second tile (tools/tc_timeline.py)
     int xm_bias;                                      // band 1: its columns nout, nout+1 are the merger's constant-1 bias inputs
@@ -247,14 +289,55 @@ struct TcArgs {
     do {                                                                                    \
         if (a.dbg && blockIdx.x == 0 && tile == (int)gridDim.x) a.dbg[(c) * 16 + (ev)] = clock64(); \
     } while (0)
+// E2 stage events of that tile go to row 15: 0 A begins (waits for D2), 1 D2 seen, 2 A done, 3 B begins, 4 B done, 5 C begins, 6 C done
+#define TC_DBG2(ev)                                                                                                   \
+    do {                                                                                                              \
+        if (a.dbg && blockIdx.x == 0 && threadIdx.x == 0 && e2_tile == (int)gridDim.x) a.dbg[15 * 16 + (ev)] = clock64(); \
+    } while (0)
 constexpr int TC_MAXS1 = 12;                        // upper bound on W1 ring stages (barrier array size)
-constexpr int TC_EPI_WARPS = 16;                     // warps 0..15: epilogue; 16: TMA producer; 17: MMA issuer
-constexpr int TC_THREADS = (TC_EPI_WARPS + 2) * 32;
+constexpr int TC_EPI_WARPS = 16;                     // warps 0..15: epilogue; 16: TMA producer; 17, 18: MMA issuers (layer 1, layer 2)
+constexpr int TC_THREADS = (TC_EPI_WARPS + 3) * 32;
 // The SM's warp schedulers favour the highest warp id among eligible warps, so the two warps whose
 // instruction streams gate everything else (TMA producer, MMA issuer) get the highest ids.
 __device__ __forceinline__ void quarter_bar_sync(int q) { asm volatile("bar.sync %0, 128;" ::"r"(q + 1) : "memory"); }
 
-template <int N2P>
+__device__ __forceinline__ float lg2_approx(float x)
+{
+    float r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+// Band nets, E2 stage C: the thread's NQ soft-max numerators e (row `row`, image columns c0 .. c0+NQ-1, c0 % 8 == SH)
+// -> normalised merger inputs, fp16, into the merger's M-major image.  x = lg2(e / sum) * A + B with the per-column
+// constants of the kernel prologue; e == 0 (exponent underflow, padding columns) takes sLn's guard: ln := 0 -> x = B.
+// All address arithmetic is per thread and loop invariant: 8 pointers (one per column % 8), immediates for the rest.
+template <int NQ, int SH>
+__device__ __forceinline__ void band_out(const float (&o)[NQ], float lg2_sc, const float *sA, const float *sB, uint8_t *img,
+                                         int row, int c0, int ncols)
+{
+    uint8_t *ptr[8];
+    const uint32_t rc = ((uint32_t)row & 63u) >> 3;
+    uint8_t *rb = img + (size_t)((c0 - SH) >> 3) * 2048 + ((uint32_t)row >> 6) * 1024u + ((uint32_t)row & 7u) * 2u;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) ptr[t] = rb + t * 128 + ((rc ^ (uint32_t)t) << 4);
+#pragma unroll
+    for (int j = 0; j < NQ / 4; ++j) {
+        if (4 * j < ncols) {   // (the image share of a net ends on a multiple of 8 columns, c0 is a multiple of 4)
+            const float4 a4 = *reinterpret_cast<const float4 *>(sA + 4 * j), b4 = *reinterpret_cast<const float4 *>(sB + 4 * j);
+            const float av[4] = {a4.x, a4.y, a4.z, a4.w}, bv[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int cc = SH + 4 * j + i;
+                const float e = o[4 * j + i];
+                const float x = e > 0.0f ? fmaf(lg2_approx(e), av[i], fmaf(lg2_sc, av[i], bv[i])) : bv[i];
+                *reinterpret_cast<__half *>(ptr[cc & 7] + (cc >> 3) * 2048) = __float2half_rn(x);
+            }
+        }
+    }
+}
+
+template <int N2P, bool XMN>   // XMN: the activation image is M-major (the merger's), else K-major
 __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs a)
 {
     constexpr int W2_BLK = N2P * 128;       // bytes of one [N2P rows x 64 fp16] block
@@ -273,8 +356,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs a)
     float *s_red = s_md + N2P;                                 // [2][4][128] row max / row sum exchange
     uint64_t *bars = reinterpret_cast<uint64_t *>(s_red + 8 * 128);
     uint64_t *x_full = bars;                 // [8]
-    uint64_t *x_empty = bars + 8;            // [1]
-    uint64_t *w1_full = bars + 9;            // [TC_MAXS1]
+    uint64_t *x_empty = bars + 8;            // [8] per k-block: the tile's last layer-1 chunk has consumed it
+    uint64_t *w1_full = bars + 16;           // [TC_MAXS1]
     uint64_t *w1_empty = w1_full + TC_MAXS1; // [TC_MAXS1]
     uint64_t *w2_empty = w1_empty + TC_MAXS1; // [4]
     uint64_t *w1c_full = w2_empty + 4;       // [4] chunk-level: all KB1 k-blocks of layer-1 chunk n have landed (n & 3)
@@ -282,30 +365,34 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs a)
     uint64_t *d1_full = w2c_full + 2;        // [2]
     uint64_t *h_full = d1_full + 2, *h_empty = h_full + 1;
     uint64_t *d2_full = h_empty + 1, *d2_empty = d2_full + 1;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(d2_empty + 1);
+    uint64_t *d1_empty = d2_empty + 1;       // [2] E1 has read the accumulator buffer
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(d1_empty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    constexpr int WARP_TMA = TC_EPI_WARPS, WARP_MMA = TC_EPI_WARPS + 1, EPI0 = 0;
+    constexpr int WARP_TMA = TC_EPI_WARPS, WARP_MMA1 = TC_EPI_WARPS + 1, WARP_MMA2 = TC_EPI_WARPS + 2, EPI0 = 0;
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < 8; ++i) mbar_init(&x_full[i], 1);
         for (int i = 0; i < TC_MAXS1; ++i) { mbar_init(&w1_full[i], 1); mbar_init(&w1_empty[i], 1); }
         for (int i = 0; i < 4; ++i) { mbar_init(&w2_empty[i], 1); mbar_init(&w1c_full[i], a.KB1); }
         for (int i = 0; i < 2; ++i) mbar_init(&w2c_full[i], 2);
-        mbar_init(x_empty, 1);
-        for (int i = 0; i < 2; ++i) mbar_init(&d1_full[i], 1);
+        for (int i = 0; i < 8; ++i) mbar_init(&x_empty[i], 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(&d1_full[i], 1); mbar_init(&d1_empty[i], TC_EPI_WARPS); }
         mbar_init(h_full, TC_EPI_WARPS); mbar_init(h_empty, 1);
         mbar_init(d2_full, 1); mbar_init(d2_empty, TC_EPI_WARPS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == WARP_MMA) {  // TMEM: 512 columns = D1 double buffer 2 x 128 | D2 up to 192 | H 64 (128 fp16 per lane)
+    if (warp == WARP_MMA1) {  // TMEM: 512 columns = D1 double buffer 2 x 128 | D2 up to 192 | H 64 (128 fp16 per lane)
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     for (int i = threadIdx.x; i < N2P; i += blockDim.x) {
         s_b2[i] = a.b2[i];
-        s_mm[i] = a.mmean ? a.mmean[a.xm_col0 + i] : 0.0f;
-        s_md[i] = a.mdev ? a.mdev[a.xm_col0 + i] : 0.0f;
+        // band nets: merger input x = (sLn(p) - mean) * dev = lg2(p) * (ln2 * dev) - mean * dev; beyond the net's outputs
+        // the image holds the two constant-1 bias inputs (band 1) and zeros
+        const bool live = a.mmean && i < a.nout;
+        s_mm[i] = live ? (float)kLn2 * a.mdev[a.xm_col0 + i] : 0.0f;
+        s_md[i] = live ? -a.mmean[a.xm_col0 + i] * a.mdev[a.xm_col0 + i] : ((a.xm_bias && i < a.nout + 2) ? 1.0f : 0.0f);
     }
     tc_fence_before();
     __syncthreads();
@@ -320,45 +407,44 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs a)
         // The whole warp walks the loops (warp-uniform control flow); one elected lane issues.  Loads follow the
         // issuer's consumption order over the CTA's linear chunk sequence g = tile_iter * NCH + c:
         //   X(tile 0), W1(0), W1(1), then per g:  [X(next tile) if chunk g+2 opens it]  W1(g+2)  W2(g)
-        uint32_t ph_x_empty = 0, w1_stage = 0, ph_w1 = 0, w2_stage = 0, ph_w2 = 0;
+        uint32_t w1_stage = 0, ph_w1 = 0, w2_stage = 0, ph_w2 = 0;
         const int my_tiles = blockIdx.x < a.n_tiles ? (a.n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
         const int G = my_tiles * a.NCH;
         // Normal case (the W1 ring holds a whole chunk): every k-block load of a chunk reports to the chunk's own
         // "full" barrier, so the issuer waits once per chunk; ring stages are still handed back one by one.
-        // Two independent cursors (layer-1 weights + X, layer-2 weights), each advanced whenever its next ring stage
-        // is free: a blocking in-order producer would sit on the shallow W2 ring and never prefetch W1 ahead.
+        // Three independent cursors (X tiles, layer-1 weights, layer-2 weights), each advanced whenever its next
+        // buffer is free: a blocking in-order producer would sit on the shallow W2 ring and never prefetch W1 ahead.
+        // X k-blocks are handed back one by one while the tile's last layer-1 chunk is being multiplied, so the next
+        // tile's X (already in L2, see the prefetch) streams in behind it and is there when its first chunk is issued.
         const bool chunk_bar = a.S1 >= a.KB1;
         uint32_t n1 = 0, n2 = 0;          // chunks fully issued per stream
         int kb1 = 0, kb2 = 0;             // next k-block inside the current chunk
-        int c1 = 0, c2 = 0, tile1 = blockIdx.x;
-        bool x_done = false, first_x = true;
-        while (n1 < (uint32_t)G || n2 < (uint32_t)G) {
-            if (n1 < (uint32_t)G) {
-                if (c1 == 0 && kb1 == 0 && !x_done) {   // the chunk opens a tile: its X first
-                    if (first_x || mbar_try(x_empty, ph_x_empty)) {
-                        if (!first_x) ph_x_empty ^= 1;
-                        first_x = false;
-                        if (elect_one()) {
-                            for (int kb = 0; kb < a.KB1; ++kb) {
-                                mbar_expect_tx(&x_full[kb], TC_BLK);
-                                tma_load_1d(sX + (size_t)kb * TC_BLK, a.x_img + ((size_t)tile1 * a.KB1 + kb) * TC_BLK, TC_BLK, &x_full[kb]);
-                            }
-                        }
-                        __syncwarp();
-                        x_done = true;
-                    }
-                } else if (mbar_try(&w1_empty[w1_stage], ph_w1 ^ 1)) {
-                    if (elect_one()) {
-                        uint64_t *fb = chunk_bar ? &w1c_full[n1 & 3] : &w1_full[w1_stage];
-                        mbar_expect_tx(fb, TC_BLK);
-                        tma_load_1d(sW1 + (size_t)w1_stage * TC_BLK, a.w1_img + ((size_t)c1 * a.KB1 + kb1) * TC_BLK, TC_BLK, fb);
-                    }
-                    __syncwarp();
-                    if (++w1_stage == (uint32_t)a.S1) { w1_stage = 0; ph_w1 ^= 1; }
-                    if (++kb1 == a.KB1) {
-                        kb1 = 0; ++n1; x_done = false;
-                        if (++c1 == a.NCH) { c1 = 0; tile1 += gridDim.x; }
-                    }
+        int c1 = 0, c2 = 0;
+        int xt = 0, xk = 0, xtile = blockIdx.x;   // X cursor: tile iteration, k-block, global tile
+        while (n1 < (uint32_t)G || n2 < (uint32_t)G || xt < my_tiles) {
+            if (xt < my_tiles && (xt == 0 || mbar_try(&x_empty[xk], (uint32_t)(xt - 1) & 1u))) {
+                if (elect_one()) {
+                    mbar_expect_tx(&x_full[xk], TC_BLK);
+                    tma_load_1d(sX + (size_t)xk * TC_BLK, a.x_img + ((size_t)xtile * a.KB1 + xk) * TC_BLK, TC_BLK, &x_full[xk]);
+                    // the CTA's next tile goes to L2 now: when its turn comes (one tile time from here) the
+                    // load that sits between two tiles' MMAs is an L2 hit
+                    if (xk == 0 && xtile + (int)gridDim.x < a.n_tiles)
+                        l2_prefetch(a.x_img + (size_t)(xtile + gridDim.x) * a.KB1 * TC_BLK, (uint32_t)a.KB1 * TC_BLK);
+                }
+                __syncwarp();
+                if (++xk == a.KB1) { xk = 0; ++xt; xtile += gridDim.x; }
+            }
+            if (n1 < (uint32_t)G && mbar_try(&w1_empty[w1_stage], ph_w1 ^ 1)) {
+                if (elect_one()) {
+                    uint64_t *fb = chunk_bar ? &w1c_full[n1 & 3] : &w1_full[w1_stage];
+                    mbar_expect_tx(fb, TC_BLK);
+                    tma_load_1d(sW1 + (size_t)w1_stage * TC_BLK, a.w1_img + ((size_t)c1 * a.KB1 + kb1) * TC_BLK, TC_BLK, fb);
+                }
+                __syncwarp();
+                if (++w1_stage == (uint32_t)a.S1) { w1_stage = 0; ph_w1 ^= 1; }
+                if (++kb1 == a.KB1) {
+                    kb1 = 0; ++n1;
+                    if (++c1 == a.NCH) c1 = 0;
                 }
             }
             if (n2 < (uint32_t)G && mbar_try(&w2_empty[w2_stage], ph_w2 ^ 1)) {
@@ -374,226 +460,163 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs a)
                 }
             }
         }
-    } else if (warp == WARP_MMA) {
-        // ===================================================================== MMA issuer
-        // One thread issues every MMA of the CTA (two issuing threads serialise in the tensor pipe; measured with
-        // tools/umma_bench.cu).  Layer 1 reads both operands from shared memory (SS, ~38 + N/2 clk each when run
-        // alone), layer 2 takes H from TMEM (TS, ~9 + N/2); interleaved one to one the pair runs at the nominal
-        // N/2 per MMA because the SS operand fetch overlaps the TS math.  So the issue schedule over the CTA's
-        // linear chunk sequence g is software pipelined:   burst(g) = G2(g) interleaved with G1(g+2),
-        // issued as soon as E1(g) has published H(g) - which also means D1[g & 1] has been read and is free for
-        // G1(g+2).  E1(g+1) (whose D1 came from the previous burst) runs on the epilogue warps meanwhile.
-        const uint32_t idesc1 = make_idesc(TC_NC), idesc2 = make_idesc(N2P);
-        uint32_t ph_x_full = 0, w1_stage = 0, ph_w1 = 0, w2_stage = 0, ph_h_full = 0, ph_d2_empty = 0;
-        const uint64_t dX = make_sw128_desc(smem_u32(sX)), dW1 = make_sw128_desc(smem_u32(sW1));
-        const uint64_t dW2 = make_sw128_desc(smem_u32(sW2));
+    } else if (warp == WARP_MMA1) {
+        // ===================================================================== MMA issuer, layer 1
+        // Two issuer warps, one per layer: an issuing warp is instruction-bound (descriptor arithmetic lives in
+        // ordinary registers and every tcgen05.mma needs them moved to uniform registers: ~12 SASS instructions per
+        // MMA from ONE warp, at single-warp issue latency - measured ~115 clk per MMA against the tensor pipe's
+        // ~64-72), and the two layers' streams are independent: different accumulators, different operand rings,
+        // their own barriers.  The tensor pipe interleaves them (SS operand fetch overlaps the TS math).
+        // This warp: for every chunk g of the CTA's linear sequence, D1[g & 1] = X . W1[c]^T (K1/16 SS MMAs), as
+        // soon as the weights have landed and E1(g - 2) has read the accumulator buffer.
+        constexpr uint32_t idesc1 = make_idesc(TC_NC, XMN);
+        constexpr uint32_t akst = XMN ? (4096u >> 4) : 2u;     // A descriptor advance per k-step of 16 columns
+        const uint64_t dX = XMN ? make_mn128_desc(smem_u32(sX)) : make_sw128_desc(smem_u32(sX));
+        const uint64_t dW1 = make_sw128_desc(smem_u32(sW1));
+        const uint32_t xlo = (uint32_t)dX, xhi = (uint32_t)(dX >> 32), w1lo = (uint32_t)dW1;
+        const uint32_t bar_w1e = smem_u32(w1_empty), bar_xe = smem_u32(x_empty), bar_d1f = smem_u32(d1_full);
         const int my_tiles = blockIdx.x < a.n_tiles ? (a.n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
         const int G = my_tiles * a.NCH;
-        // A chunk's layer-1 k-blocks are issued in groups of GK blocks: the whole chunk when the W1 ring can hold
-        // it (S1 >= KB1, the normal case), else half a ring at a time (wide merger nets next to a wide X tile).
-        const int GK = a.S1 >= a.KB1 ? a.KB1 : (a.S1 / 2 > 0 ? a.S1 / 2 : 1);
-        // burst: layer 2 of chunk g2 (g2 < 0: none) interleaved one to one with layer 1 of chunk g1 (g1 < 0: none)
-        // (c2 / c1: the chunks' positions inside their tiles; first2: no D2 has been handed to the epilogue yet)
-        const bool chunk_bar = a.S1 >= a.KB1;
-        uint32_t n1 = 0, n2 = 0;   // running chunk counters of the two weight streams (chunk-level "full" barriers)
-        int c2 = 0, c1 = 0, d1buf = 0;
-        bool first2 = true;
-        int tile = blockIdx.x;   // (only for the debug timeline)
-        auto burst = [&](bool do_g2, bool do_g1) {
-            const int g1 = do_g1 ? d1buf : -1;   // only the D1 buffer index of the layer-1 chunk matters below
-            uint32_t w2b = w2_stage + 1;
-            if (w2b == (uint32_t)a.S2) w2b = 0;
-            const bool opens = do_g1 && c1 == 0;
-            const bool wait_d2 = do_g2 && c2 == 0 && !first2;
-            bool g2_pending = do_g2;
-            for (int kb0 = 0; kb0 < (g1 >= 0 ? a.KB1 : 1); kb0 += GK) {
-                const int nkb = g1 >= 0 ? (a.KB1 - kb0 < GK ? a.KB1 - kb0 : GK) : 0;
-                // operands of this group: weights first (loaded long ago in the steady state), H last (the freshest)
-                if (nkb > 0) {
-                    if (chunk_bar) {
-                        mbar_wait(&w1c_full[n1 & 3], (n1 >> 2) & 1);
+        const bool chunk_bar = a.S1 >= a.KB1;   // the W1 ring holds a whole chunk: one "full" barrier per chunk
+        uint32_t st = 0, ph_w1 = 0, ph_x_full = 0;
+        int c1 = 0, tile = blockIdx.x;          // (tile: only for the debug timeline)
+        const bool leader = elect_one();
+#pragma unroll 1
+        for (int g = 0; g < G; ++g) {
+            const bool opens = c1 == 0, closes = c1 == a.NCH - 1;
+            const uint32_t td1 = (g & 1) ? tmem + 128u : tmem;
+            if (lane == 0) TC_DBG(2, c1);   // layer 1 of chunk c1: begins
+            if (g >= 2) mbar_wait(&d1_empty[g & 1], (uint32_t)((g >> 1) - 1) & 1u);
+            if (chunk_bar) mbar_wait(&w1c_full[g & 3], (uint32_t)(g >> 2) & 1u);
+            if (lane == 0) TC_DBG(3, c1);   // accumulator + weights there
+            tc_fence_after();
+            uint32_t alo = xlo;
+#pragma unroll 1
+            for (int k = 0; k < a.KB1; ++k) {   // (kept rolled: a small loop body stays in the SMSP's instruction cache)
+                if (!chunk_bar) mbar_wait(&w1_full[st], ph_w1);
+                if (opens) mbar_wait(&x_full[k], ph_x_full);
+                if (!chunk_bar || opens) tc_fence_after();
+                const uint32_t blo = w1lo + st * (TC_BLK >> 4);
+                const uint32_t bw1 = bar_w1e + st * 8u, bxe = bar_xe + (uint32_t)k * 8u;
+                if (leader) {
+                    if (k == 0) umma_ss_lo<0>(td1, alo, xhi, blo, idesc1); else umma_ss_lo<1>(td1, alo, xhi, blo, idesc1);
+                    if (k < a.KB1 - 1 || a.nks_last == 4) {
+                        umma_ss_lo<1>(td1, alo + akst, xhi, blo + 2, idesc1);
+                        umma_ss_lo<1>(td1, alo + 2 * akst, xhi, blo + 4, idesc1);
+                        umma_ss_lo<1>(td1, alo + 3 * akst, xhi, blo + 6, idesc1);
                     } else {
-                        uint32_t st = w1_stage, ph = ph_w1;
-                        for (int k = 0; k < nkb; ++k) {
-                            mbar_wait(&w1_full[st], ph);
-                            if (++st == (uint32_t)a.S1) { st = 0; ph ^= 1; }
-                        }
+                        if (a.nks_last > 1) umma_ss_lo<1>(td1, alo + akst, xhi, blo + 2, idesc1);
+                        if (a.nks_last > 2) umma_ss_lo<1>(td1, alo + 2 * akst, xhi, blo + 4, idesc1);
                     }
-                    if (opens)
-                        for (int k = 0; k < nkb; ++k) mbar_wait(&x_full[kb0 + k], ph_x_full);
-                }
-                if (g2_pending) {
-                    mbar_wait(&w2c_full[n2 & 1], (n2 >> 1) & 1);
-                    if (wait_d2) mbar_wait(d2_empty, ph_d2_empty);
-                    mbar_wait(h_full, ph_h_full);
-                }
-                tc_fence_after();
-                if (elect_one()) {
-                    // interleave in blocks of four k-steps (one k-block): SS block of layer 1, TS block of layer 2, ...
-                    const int nblk = g2_pending ? (nkb > 2 ? nkb : 2) : nkb;
-                    uint32_t st = w1_stage;
-                    for (int k = 0; k < nblk; ++k) {
-                        if (k < nkb) {
-                            const int kb = kb0 + k;
-                            const int nks = kb == a.KB1 - 1 ? a.nks_last : 4;
-                            const uint64_t ad = dX + (uint64_t)((kb * TC_BLK) >> 4), bd = dW1 + (uint64_t)((st * TC_BLK) >> 4);
-#pragma unroll
-                            for (int ks = 0; ks < 4; ++ks)
-                                if (ks < nks) umma_f16_ss(tD1[g1 & 1], ad + 2 * ks, bd + 2 * ks, idesc1, (kb | ks) ? 1u : 0u);
-                            tc_commit(&w1_empty[st]);
-                            if (++st == (uint32_t)a.S1) st = 0;
-                        }
-                        if (g2_pending && k < 2) {   // A = H[:, 64 k + 16 ks .. +15] = 8 TMEM columns per k-step
-                            const uint32_t w2s = k ? w2b : w2_stage;
-                            const uint64_t bd = dW2 + (uint64_t)((w2s * W2_BLK) >> 4);
-#pragma unroll
-                            for (int ks = 0; ks < 4; ++ks)
-                                umma_f16_ts(tD2, tH + (uint32_t)(k * 4 + ks) * 8u, bd + 2 * ks, idesc2, (c2 | k | ks) ? 1u : 0u);
-                            tc_commit(&w2_empty[w2s]);
-                        }
-                    }
-                    if (g2_pending) {
-                        tc_commit(h_empty);
-                        if (c2 == a.NCH - 1) tc_commit(d2_full);
-                    }
-                    if (g1 >= 0 && kb0 + nkb == a.KB1) {
-                        tc_commit(&d1_full[g1 & 1]);
-                        if (c1 == a.NCH - 1) tc_commit(x_empty);
-                    }
+                    tc_commit_u(bw1);
+                    if (closes) tc_commit_u(bxe);
                 }
                 __syncwarp();
-                w1_stage += nkb;
-                if (w1_stage >= (uint32_t)a.S1) { w1_stage -= a.S1; ph_w1 ^= 1; }
-                if (g2_pending) {
-                    ph_h_full ^= 1;
-                    if (wait_d2) ph_d2_empty ^= 1;
-                    w2_stage += 2;
-                    if (w2_stage >= (uint32_t)a.S2) w2_stage -= a.S2;
-                    g2_pending = false;
-                }
+                if (++st == (uint32_t)a.S1) { st = 0; ph_w1 ^= 1; }
+                alo += TC_BLK >> 4;
             }
+            if (leader) tc_commit_u(bar_d1f + (uint32_t)(g & 1) * 8u);
+            __syncwarp();
+            if (lane == 0) TC_DBG(4, c1);   // issued
             if (opens) ph_x_full ^= 1;
-            if (do_g1) { ++n1; d1buf ^= 1; if (++c1 == a.NCH) c1 = 0; }
-            if (do_g2) { ++n2; first2 = false; if (++c2 == a.NCH) c2 = 0; }
-        };
-        // Steady state (both chunks inside their tiles, W1 chunk resident): the same burst with nothing but the
-        // instructions it needs - this warp shares an SMSP (and its 6 KB L0 instruction cache) with four epilogue
-        // warps, and every instruction-fetch miss of the issuer is a bubble in the tensor pipe.
-        const uint32_t xlo = (uint32_t)dX, w1lo = (uint32_t)dW1, w2lo = (uint32_t)dW2;
-        auto lean = [&]() {
-            if (lane == 0) TC_DBG(3, c2);
-            mbar_wait(&w1c_full[n1 & 3], (n1 >> 2) & 1);
-            mbar_wait(&w2c_full[n2 & 1], (n2 >> 1) & 1);
-            mbar_wait(h_full, ph_h_full);
-            if (lane == 0) TC_DBG(5, c2);   // operands there
+            if (++c1 == a.NCH) { c1 = 0; tile += gridDim.x; }
+        }
+    } else if (warp == WARP_MMA2) {
+        // ===================================================================== MMA issuer, layer 2
+        // D2 (+)= H(g) . W2[:, c]^T: 8 TS MMAs per chunk (A = H from TMEM, 8 columns per k-step), as soon as E1(g) has
+        // published H and the chunk's two W2 k-blocks have landed; H goes back to the epilogue warps right behind them.
+        constexpr uint32_t idesc2 = make_idesc(N2P);
+        const uint32_t w2lo = (uint32_t)make_sw128_desc(smem_u32(sW2));
+        const uint32_t bar_w2e = smem_u32(w2_empty), bar_he = smem_u32(h_empty), bar_d2f = smem_u32(d2_full);
+        const int my_tiles = blockIdx.x < a.n_tiles ? (a.n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+        const int G = my_tiles * a.NCH;
+        uint32_t w2s = 0, ph_d2_empty = 0;
+        int c2 = 0, tile = blockIdx.x;
+        const bool leader = elect_one();
+#pragma unroll 1
+        for (int g = 0; g < G; ++g) {
+            if (lane == 0) TC_DBG(5, c2);   // layer 2 of chunk c2: begins
+            mbar_wait(&w2c_full[g & 1], (uint32_t)(g >> 1) & 1u);
+            if (c2 == 0 && g > 0) { mbar_wait(d2_empty, ph_d2_empty); ph_d2_empty ^= 1; }
+            mbar_wait(h_full, (uint32_t)g & 1u);
+            if (lane == 0) TC_DBG(6, c2);   // H + weights there
             tc_fence_after();
-            uint32_t w2b = w2_stage + 1;
-            if (w2b == (uint32_t)a.S2) w2b = 0;
-            if (elect_one()) {
-                const uint32_t td1 = tD1[d1buf];
-                uint32_t st = w1_stage, alo = xlo;
-                for (int k = 0; k < a.KB1; ++k) {
-                    const uint32_t blo = w1lo + st * (TC_BLK >> 4);
-                    if (k == 0) umma_ss_lo<0>(td1, alo, blo, idesc1); else umma_ss_lo<1>(td1, alo, blo, idesc1);
-                    if (k < a.KB1 - 1 || a.nks_last > 1) umma_ss_lo<1>(td1, alo + 2, blo + 2, idesc1);
-                    if (k < a.KB1 - 1 || a.nks_last > 2) umma_ss_lo<1>(td1, alo + 4, blo + 4, idesc1);
-                    if (k < a.KB1 - 1 || a.nks_last > 3) umma_ss_lo<1>(td1, alo + 6, blo + 6, idesc1);
-                    tc_commit(&w1_empty[st]);
-                    if (++st == (uint32_t)a.S1) st = 0;
-                    alo += TC_BLK >> 4;
-                    if (k < 2) {   // A = H[:, 64 k + 16 ks .. +15] = 8 TMEM columns per k-step
-                        const uint32_t w2s = k ? w2b : w2_stage;
-                        const uint32_t b2lo = w2lo + w2s * (W2_BLK >> 4);
-                        const uint32_t ta = tH + (uint32_t)k * 32u;
-                        umma_ts_lo<1>(tD2, ta, b2lo, idesc2);
-                        umma_ts_lo<1>(tD2, ta + 8u, b2lo + 2, idesc2);
-                        umma_ts_lo<1>(tD2, ta + 16u, b2lo + 4, idesc2);
-                        umma_ts_lo<1>(tD2, ta + 24u, b2lo + 6, idesc2);
-                        tc_commit(&w2_empty[w2s]);
-                    }
+#pragma unroll 1
+            for (int k = 0; k < 2; ++k) {
+                const uint32_t b2lo = w2lo + w2s * (W2_BLK >> 4);
+                const uint32_t ta = tH + (uint32_t)k * 32u;
+                const uint32_t bw2 = bar_w2e + w2s * 8u;
+                const uint32_t acc0 = (k | c2) ? 1u : 0u;
+                if (leader) {
+                    umma_f16_ts(tD2, ta, ((uint64_t)kDescHi << 32) | b2lo, idesc2, acc0);
+                    umma_ts_lo<1>(tD2, ta + 8u, b2lo + 2, idesc2);
+                    umma_ts_lo<1>(tD2, ta + 16u, b2lo + 4, idesc2);
+                    umma_ts_lo<1>(tD2, ta + 24u, b2lo + 6, idesc2);
+                    tc_commit_u(bw2);
                 }
-                tc_commit(h_empty);
-                if (c2 == a.NCH - 1) tc_commit(d2_full);
-                tc_commit(&d1_full[d1buf]);
-                if (c1 == a.NCH - 1) tc_commit(x_empty);
-                TC_DBG(13, c2);                 // all MMAs and commits issued
+                __syncwarp();
+                if (++w2s == (uint32_t)a.S2) w2s = 0;
+            }
+            if (leader) {
+                tc_commit_u(bar_he);
+                if (c2 == a.NCH - 1) tc_commit_u(bar_d2f);
             }
             __syncwarp();
-            w1_stage += a.KB1;
-            if (w1_stage >= (uint32_t)a.S1) { w1_stage -= a.S1; ph_w1 ^= 1; }
-            ph_h_full ^= 1;
-            w2_stage += 2;
-            if (w2_stage >= (uint32_t)a.S2) w2_stage -= a.S2;
-            ++n1; d1buf ^= 1; if (++c1 == a.NCH) c1 = 0;
-            ++n2; if (++c2 == a.NCH) c2 = 0;
-        };
-        const bool lean_ok = chunk_bar && a.KB1 >= 2;
-        int pro = G > 1 ? 2 : G;   // prologue: layer 1 of the first two chunks on its own
-        for (int g = 0; g < G;) {
-            bool t_g2[2] = {false, false}, t_g1[2] = {true, true};
-            int nt = 1;
-            const int c = c2;
-            if (pro > 0) {
-                --pro;
-            } else {
-                const bool has_g1 = g + 2 < G;
-                if (lane == 0) TC_DBG(2, c);   // burst starts
-                if (has_g1 && c1 != 0 && c2 != 0 && lean_ok) {
-                    lean();
-                    ++g;
-                    if (lane == 0) TC_DBG(4, c);   // burst issued
-                    if (c2 == 0) tile += gridDim.x;
-                    continue;
-                }
-                if (has_g1 && c1 == 0) {
-                    // G1(g+2) opens a tile whose X may still be in flight: do not hold layer 2 of this chunk back for it
-                    nt = 2; t_g2[0] = true; t_g1[0] = false;
-                } else {
-                    t_g2[0] = true; t_g1[0] = has_g1;
-                }
-                ++g;
-            }
-            for (int t = 0; t < nt; ++t) burst(t_g2[t], t_g1[t]);   // (one call site: one copy of the general path)
-            if (c2 == 0 && t_g2[0]) tile += gridDim.x;
+            if (lane == 0) TC_DBG(7, c2);   // issued
+            if (++c2 == a.NCH) { c2 = 0; tile += gridDim.x; }
         }
     } else {
         // ===================================================================== epilogue warps
+        // E1 runs once per chunk; E2 of a tile is cut into three stages that ride behind the E1s of the NEXT tile's
+        // first chunks (A: drain D2 into registers and hand D2 back, row max; B: exponentials, row sum; C: outputs),
+        // so the tensor pipe never waits for a soft-max.  After the CTA's last chunk the stages run back to back.
         const int q = warp & 3;                  // TMEM lane quarter this warp may access
         const int cq = (warp - EPI0) >> 2;       // column quarter 0..3
         const int row = q * 32 + lane;           // tile row == TMEM lane
         const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
         uint32_t ph_d1_full0 = 0, ph_d1_full1 = 0, ph_h_empty = 0, ph_d2_full = 0;
         bool first_h = true;
-        int g = 0;   // the CTA's linear chunk index: D1 buffer = g & 1 (NCH may be odd)
         // H[row][cq*32 .. +31] (fp16 pairs) = TMEM lane `row`, columns cq*16 .. +15 of the H operand
         // u = sat(t / TMAX), t = -(x + b1)/ln2 + Ct; b1 is already inside x (two extra K columns of layer 1)
         const float sigA = (float)(-1.0 / (kLn2 * (double)kSigTmax)), sigB = (float)(kCt / (double)kSigTmax);
-        for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
-            for (int c = 0; c < a.NCH; ++c, ++g) {
-                const int b = g & 1;
+        const float smxA = (float)(1.0 / (kLn2 * (double)kSmxTmax)), smxB = (float)(kCt / (double)kSmxTmax);
+        const int my_tiles = blockIdx.x < a.n_tiles ? (a.n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+        const int G = my_tiles * a.NCH;
+        const int n0 = cq * NQ;                  // column quarter cq owns D2 columns [cq*NQ, (cq+1)*NQ)
+        float o[NQ];
+        float mx = 0.0f;
+        int e2_stage = 3, e2_tile = 0;           // 3: no soft-max pending; 0..2: next stage of tile e2_tile
+        int c = 0, tile = blockIdx.x;
+        for (int g = 0; g <= G; ++g) {           // g == G: drain iteration (no E1)
+            const bool drain = g == G;
+            if (!drain) {
+                const int b = g & 1;             // D1 buffer = linear chunk index & 1 (NCH may be odd)
                 if (threadIdx.x == EPI0 * 32) TC_DBG(8, c);    // e1: waiting for D1
                 if (b == 0) { mbar_wait(&d1_full[0], ph_d1_full0); ph_d1_full0 ^= 1; }
                 else        { mbar_wait(&d1_full[1], ph_d1_full1); ph_d1_full1 ^= 1; }
                 tc_fence_after();
                 if (threadIdx.x == EPI0 * 32) TC_DBG(9, c);    // e1: D1 seen
-                // (no "D1 free" signal: the issuer reuses D1[b] only after this chunk's H has been published)
                 // fsig(x) = 1 / (1 + D(-x - b1)); two reciprocals share one MUFU: 1/a = a' / (a a'), 1/a' = a / (a a')
                 uint32_t hp[16];
-                {
-                    uint32_t acc[32];
-                    tmem_ld32((b ? tD1[1] : tD1[0]) + lane_addr + cq * 32, acc);
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    uint32_t acc[16];
+                    tmem_ld16((b ? tD1[1] : tD1[0]) + lane_addr + cq * 32 + half * 16, acc);
                     tmem_ld_wait();
 #pragma unroll
-                    for (int g4 = 0; g4 < 8; ++g4) {
+                    for (int g4 = 0; g4 < 4; ++g4) {
                         const float a0 = 1.0f + fexp_from_u(fma_sat(__uint_as_float(acc[g4 * 4 + 0]), sigA, sigB), kSigTmax);
                         const float a1 = 1.0f + fexp_from_u(fma_sat(__uint_as_float(acc[g4 * 4 + 1]), sigA, sigB), kSigTmax);
                         const float a2 = 1.0f + fexp_from_u(fma_sat(__uint_as_float(acc[g4 * 4 + 2]), sigA, sigB), kSigTmax);
                         const float a3 = 1.0f + fexp_from_u(fma_sat(__uint_as_float(acc[g4 * 4 + 3]), sigA, sigB), kSigTmax);
                         const float r01 = rcp_approx(a0 * a1), r23 = rcp_approx(a2 * a3);
-                        hp[g4 * 2] = pack_half2(r01 * a1, r01 * a0);
-                        hp[g4 * 2 + 1] = pack_half2(r23 * a3, r23 * a2);
+                        hp[half * 8 + g4 * 2] = pack_half2(r01 * a1, r01 * a0);
+                        hp[half * 8 + g4 * 2 + 1] = pack_half2(r23 * a3, r23 * a2);
                     }
                 }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&d1_empty[b]);      // (the layer-1 issuer may overwrite this accumulator buffer)
                 if (threadIdx.x == EPI0 * 32) TC_DBG(10, c);   // e1: math done
                 if (!first_h) { mbar_wait(h_empty, ph_h_empty); ph_h_empty ^= 1; }
                 first_h = false;
@@ -606,99 +629,102 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs a)
                 if (lane == 0) mbar_arrive(h_full);
                 if (threadIdx.x == EPI0 * 32) TC_DBG(12, c);   // e1: H published
             }
-            // ------------------------------------------------------------- E2: softmax + outputs
-            // column quarter cq owns D2 columns [cq*NQ, (cq+1)*NQ); the 4 warps of a row quarter
-            // exchange row max / row sum through shared memory and their own named barrier
-            const int n0 = cq * NQ;
-            if (threadIdx.x == EPI0 * 32) TC_DBG(13, 0);       // e2: waiting for D2
-            mbar_wait(d2_full, ph_d2_full); ph_d2_full ^= 1;
-            tc_fence_after();
-            if (threadIdx.x == EPI0 * 32) TC_DBG(14, 0);       // e2: D2 seen
-            float o[NQ];
-            {
-                uint32_t raw[NQ];
-                tmem_ld32(tD2 + lane_addr + n0, raw);
-                if (NR == 4) tmem_ld4(tD2 + lane_addr + n0 + 32, raw + 32);
-                if (NR == 8) tmem_ld8(tD2 + lane_addr + n0 + 32, raw + 32);
-                if (NR == 16) tmem_ld16(tD2 + lane_addr + n0 + 32, raw + 32);
-                tmem_ld_wait();
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(d2_empty);
-#pragma unroll
-                for (int j = 0; j < NQ / 4; ++j) {
-                    const float4 b4 = *reinterpret_cast<const float4 *>(s_b2 + n0 + 4 * j);   // -FLT_MAX in padding columns
-                    o[4 * j + 0] = __uint_as_float(raw[4 * j + 0]) + b4.x;
-                    o[4 * j + 1] = __uint_as_float(raw[4 * j + 1]) + b4.y;
-                    o[4 * j + 2] = __uint_as_float(raw[4 * j + 2]) + b4.z;
-                    o[4 * j + 3] = __uint_as_float(raw[4 * j + 3]) + b4.w;
-                }
-            }
-            float mx = o[0];
-#pragma unroll
-            for (int i = 1; i < NQ; ++i) mx = fmaxf(mx, o[i]);
-            s_red[cq * 128 + row] = mx;
-            quarter_bar_sync(q);
-            mx = fmaxf(fmaxf(s_red[row], s_red[128 + row]), fmaxf(s_red[256 + row], s_red[384 + row]));
-            float sum = 0.0f;
-            const float smxA = (float)(1.0 / (kLn2 * (double)kSmxTmax)), smxB = (float)(kCt / (double)kSmxTmax);
-#pragma unroll
-            for (int i = 0; i < NQ; ++i) {     // fexp_softmax_v (fexp.h:49-78): e = D(o - max)
-                const float e = fexp_from_u(fma_sat(o[i] - mx, smxA, smxB), kSmxTmax);
-                o[i] = e;
-                sum += e;
-            }
-            s_red[512 + cq * 128 + row] = sum;
-            quarter_bar_sync(q);
-            sum = (s_red[512 + row] + s_red[512 + 128 + row]) + (s_red[512 + 256 + row] + s_red[512 + 384 + row]);
-            const float sc = 1.0f / sum;
-            const int64_t f = (int64_t)tile * TC_M + row;
-            if (f < a.nf) {
-                if (a.post) {
-                    float *dst = a.post + f * a.ldpost + n0;
-#pragma unroll
-                    for (int j = 0; j < NQ / 4; ++j)
-                        if (n0 + 4 * j < a.ldpost)
-                            *reinterpret_cast<float4 *>(dst + 4 * j) = make_float4(o[4 * j] * sc, o[4 * j + 1] * sc, o[4 * j + 2] * sc, o[4 * j + 3] * sc);
-                    if (a.logp) {   // decoder soft function (srec.cpp:1088-1097), fused: ln p for the token passing kernel
-                        float *ldst = a.logp + f * a.ldpost + n0;
-#pragma unroll
-                        for (int j = 0; j < NQ / 4; ++j)
-                            if (n0 + 4 * j < a.ldpost)
-                                *reinterpret_cast<float4 *>(ldst + 4 * j) = make_float4(__logf(o[4 * j] * sc), __logf(o[4 * j + 1] * sc),
-                                                                                       __logf(o[4 * j + 2] * sc), __logf(o[4 * j + 3] * sc));
-                    }
-                } else {
-                    // merger input: sLn(p), merger input normalisation, fp16, 8-byte pieces of the merger's X image
-                    const int nlim = (a.nout + 7) & ~7;   // this net's share of the image: nout rounded up to 8 columns
+            // ------------------------------------------------------------- E2 stages: soft-max + outputs of tile e2_tile
+            // one stage per chunk; everything that is left when a tile ends or in the drain iteration
+            int budget = (drain || c == a.NCH - 1) ? 3 : 1;
+            while (e2_stage < 3 && budget-- > 0) {
+                if (e2_stage == 0) {
+                    // A: D2 -> registers (+ b2), D2 handed back to the issuer, row max of this warp's columns
+                    TC_DBG2(0);
+                    mbar_wait(d2_full, ph_d2_full); ph_d2_full ^= 1;
+                    tc_fence_after();
+                    TC_DBG2(1);
+                    uint32_t raw[NQ];
+                    tmem_ld32(tD2 + lane_addr + n0, raw);
+                    if (NR == 4) tmem_ld4(tD2 + lane_addr + n0 + 32, raw + 32);
+                    if (NR == 8) tmem_ld8(tD2 + lane_addr + n0 + 32, raw + 32);
+                    if (NR == 16) tmem_ld16(tD2 + lane_addr + n0 + 32, raw + 32);
+                    tmem_ld_wait();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(d2_empty);
 #pragma unroll
                     for (int j = 0; j < NQ / 4; ++j) {
-                        const int n = n0 + 4 * j;
-                        if (n < nlim) {
-                            const float4 m4 = *reinterpret_cast<const float4 *>(s_mm + n), d4 = *reinterpret_cast<const float4 *>(s_md + n);
-                            const float mm[4] = {m4.x, m4.y, m4.z, m4.w}, md[4] = {d4.x, d4.y, d4.z, d4.w};
-                            float xn[4];
+                        const float4 b4 = *reinterpret_cast<const float4 *>(s_b2 + n0 + 4 * j);   // -FLT_MAX in padding columns
+                        o[4 * j + 0] = __uint_as_float(raw[4 * j + 0]) + b4.x;
+                        o[4 * j + 1] = __uint_as_float(raw[4 * j + 1]) + b4.y;
+                        o[4 * j + 2] = __uint_as_float(raw[4 * j + 2]) + b4.z;
+                        o[4 * j + 3] = __uint_as_float(raw[4 * j + 3]) + b4.w;
+                    }
+                    mx = o[0];
 #pragma unroll
-                            for (int i = 0; i < 4; ++i) {
-                                const float p = o[4 * j + i] * sc;
-                                const float v = p > 0.0f ? __logf(p) : 0.0f;
-                                xn[i] = n + i < a.nout ? (v - mm[i]) * md[i] : ((a.xm_bias && n + i < a.nout + 2) ? 1.0f : 0.0f);
+                    for (int i = 1; i < NQ; ++i) mx = fmaxf(mx, o[i]);
+                    s_red[cq * 128 + row] = mx;
+                    TC_DBG2(2);
+                } else if (e2_stage == 1) {
+                    // B: row max across the 4 column-quarter warps of this lane quarter, e = D(o - max) (fexp.h:49-78), row sum
+                    TC_DBG2(3);
+                    quarter_bar_sync(q);
+                    mx = fmaxf(fmaxf(s_red[row], s_red[128 + row]), fmaxf(s_red[256 + row], s_red[384 + row]));
+                    float sum = 0.0f;
+#pragma unroll
+                    for (int i = 0; i < NQ; ++i) {
+                        const float e = fexp_from_u(fma_sat(o[i] - mx, smxA, smxB), kSmxTmax);
+                        o[i] = e;
+                        sum += e;
+                    }
+                    s_red[512 + cq * 128 + row] = sum;
+                    TC_DBG2(4);
+                } else {
+                    // C: normalise, outputs
+                    TC_DBG2(5);
+                    quarter_bar_sync(q);
+                    const float sum = (s_red[512 + row] + s_red[512 + 128 + row]) + (s_red[512 + 256 + row] + s_red[512 + 384 + row]);
+                    const int64_t f = (int64_t)e2_tile * TC_M + row;
+                    if (f < a.nf) {
+                        if (!a.xm_img) {
+                            if (a.post) {
+                                const float sc = 1.0f / sum;
+                                float *dst = a.post + f * a.ldpost + n0;
+#pragma unroll
+                                for (int j = 0; j < NQ / 4; ++j)
+                                    if (n0 + 4 * j < a.ldpost)
+                                        *reinterpret_cast<float4 *>(dst + 4 * j) = make_float4(o[4 * j] * sc, o[4 * j + 1] * sc, o[4 * j + 2] * sc, o[4 * j + 3] * sc);
                             }
-                            const int cm = a.xm_col0 + n;
-                            uint8_t *blk = a.xm_img + ((size_t)tile * a.xm_kb1 + (cm >> 6)) * TC_BLK;
-                            *reinterpret_cast<uint2 *>(blk + (size_t)row * 128 + ((((cm >> 3) & 7) ^ (row & 7)) << 4) + ((cm & 4) << 1)) =
-                                make_uint2(pack_half2(xn[0], xn[1]), pack_half2(xn[2], xn[3]));
+                            if (a.logp) {   // decoder soft function (srec.cpp:1088-1097), fused: ln p for the token passing kernel,
+                                            // column-major inside the tile so that a warp's store of one column is one 128-byte line
+                                float *ldst = a.logp + ((a.logp_tile0 + e2_tile) * a.ldpost + n0) * TC_M + row;
+                                const float ln_sc = -__logf(sum);
+#pragma unroll
+                                for (int i = 0; i < NQ; ++i)
+                                    if (n0 + i < a.ldpost) ldst[i * TC_M] = fmaf(lg2_approx(o[i]), (float)kLn2, ln_sc);
+                            }
+                        } else {
+                            // merger input: sLn(p), merger input normalisation, fp16, into the merger's M-major X image: a warp's
+                            // store of one column is 64 consecutive bytes
+                            const int nlim = (a.nout + 7) & ~7;   // this net's share of the image: nout rounded up to 8 columns
+                            uint8_t *img = a.xm_img + (size_t)e2_tile * a.xm_kb1 * TC_BLK;
+                            const float lg2_sc = -lg2_approx(sum);
+                            const int c0 = a.xm_col0 + n0;
+                            if (c0 & 4) band_out<NQ, 4>(o, lg2_sc, s_mm + n0, s_md + n0, img, row, c0, nlim - n0);
+                            else        band_out<NQ, 0>(o, lg2_sc, s_mm + n0, s_md + n0, img, row, c0, nlim - n0);
                         }
                     }
+                    TC_DBG2(6);
                 }
+                ++e2_stage;
             }
-            if (threadIdx.x == EPI0 * 32) TC_DBG(15, 0);       // e2 done
+            if (!drain && ++c == a.NCH) {        // the tile's last H is on its way: its soft-max becomes pending
+                c = 0;
+                e2_stage = 0; e2_tile = tile;
+                tile += gridDim.x;
+            }
         }
     }
 
     tc_fence_before();
     __syncthreads();
-    if (warp == WARP_MMA) {
+    if (warp == WARP_MMA1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
     }
@@ -749,7 +775,8 @@ __global__ void k_fill_bias_cols(uint8_t *img, int64_t rows, int KB1, int kin)
     if (idx >= rows * 2) return;
     const int64_t row = idx >> 1;
     const int k = kin + (int)(idx & 1);
-    *reinterpret_cast<__half *>(img + ((size_t)(row >> 7) * KB1 + (k >> 6)) * TC_BLK + sw128_off((int)(row & 127), k & 63)) = __float2half_rn(1.0f);
+    // (only the merger's image is filled this way, and the merger's image is M-major)
+    *reinterpret_cast<__half *>(img + (size_t)(row >> 7) * KB1 * TC_BLK + mn128_off((int)(row & 127), k)) = __float2half_rn(1.0f);
 }
 
 __global__ void k_build_w2_img(const float *__restrict__ w2, int nhid, int nout, int nhid4, uint8_t *img, int N2P, int NCH)
@@ -844,8 +871,13 @@ void mlp_tc_release(phn_ctx *c)
 template <int N2P>
 static int launch_one(phn_ctx *c, const TcArgs &a, size_t smem_bytes, int grid)
 {
-    PHN_CUDA(c, cudaFuncSetAttribute(k_mlp_tc<N2P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
-    k_mlp_tc<N2P><<<grid, TC_THREADS, smem_bytes, c->stream>>>(a);
+    if (a.x_mn) {
+        PHN_CUDA(c, cudaFuncSetAttribute(k_mlp_tc<N2P, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+        k_mlp_tc<N2P, true><<<grid, TC_THREADS, smem_bytes, c->stream>>>(a);
+    } else {
+        PHN_CUDA(c, cudaFuncSetAttribute(k_mlp_tc<N2P, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+        k_mlp_tc<N2P, false><<<grid, TC_THREADS, smem_bytes, c->stream>>>(a);
+    }
     PHN_CUDA(c, cudaGetLastError());
     return PHN_OK;
 }
@@ -866,8 +898,11 @@ static int run_net_tc(phn_ctx *c, int which, const uint8_t *x_img, int64_t nf, i
         a.mmean = st.net[2].mean_img; a.mdev = st.net[2].dev_img;
         a.xm_bias = which == 1;
     } else {
-        a.post = (float *)c->d_post.p + f0 * c->ldp; a.ldpost = c->ldp;
-        a.logp = c->fuse_logp ? (float *)c->d_logp.p + f0 * c->ldp : nullptr;
+        // audio -> labels path: the decoder only needs ln p, so the linear posteriors are not written at all
+        a.post = c->fuse_logp ? nullptr : (float *)c->d_post.p + f0 * c->ldp; a.ldpost = c->ldp;
+        a.logp = c->fuse_logp ? (float *)c->d_logp.p : nullptr;
+        a.logp_tile0 = f0 / TC_M;
+        a.x_mn = 1;
     }
     // shared memory plan: X (KB1 blocks) + H (2 blocks) + constants + barriers are fixed; the rest is split
     // between the W2 ring (S2 k-blocks of N2P x 64) and the W1 ring (S1 blocks of 128 x 64)

@@ -24,8 +24,8 @@
 namespace phn {
 
 struct VitArgs {
-    const float *logp;       // [total_frames][ld] log-posteriors; the decoder reads the first 3P columns of a row
-    int ld;
+    const float *logp;       // log-posteriors, row-major [total_frames][ld] (K-log) or TILED [frame / 128][ld][128] (written
+    int ld;                  // by the tensor-core merger's epilogue); the decoder reads the first 3P columns of a row
     const int64_t *frame_off;
     int n_utt, P, H;
     int64_t total_frames;
@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(256) k_log_post(const float *__restrict__ post
         for (int cidx = lane; cidx < ncols; cidx += 32) logp[f * ldp + cidx] = logf_glibc(post[f * ldp + cidx], s_logtab);
 }
 
-template <int PPL>
+template <int PPL, bool TILED>
 __global__ void __launch_bounds__(32) k_viterbi(VitArgs a)
 {
     const int seg = blockIdx.x;
@@ -101,7 +101,9 @@ __global__ void __launch_bounds__(32) k_viterbi(VitArgs a)
 #pragma unroll
                 for (int j = 0; j < 3; ++j) {
                     const int i = lane + 32 * r;
-                    obs[q][r][j] = (valid[r] && tb + q < T) ? a.logp[(f0 + tb + q) * a.ld + 3 * i + j] : 0.0f;
+                    const int64_t f = f0 + tb + q;
+                    const int64_t at = TILED ? ((f >> 7) * a.ld + 3 * i + j) * 128 + (f & 127) : f * a.ld + 3 * i + j;
+                    obs[q][r][j] = (valid[r] && tb + q < T) ? a.logp[at] : 0.0f;
                 }
 
 #pragma unroll
@@ -261,7 +263,7 @@ int launch_viterbi(phn_ctx *c, const float *d_pen, int n_pen)
     const int nseg = c->n_utt * n_pen;
     if (nseg == 0) return PHN_OK;
     const int ncols = 3 * c->P;
-    int rc = ensure(c, c->d_logp, sizeof(float) * (size_t)(c->total_frames ? c->total_frames : 1) * c->ldp);
+    int rc = ensure(c, c->d_logp, sizeof(float) * (size_t)((c->total_frames + 127) / 128 * 128 + 128) * c->ldp);
     if (rc) return rc;
     if (c->total_frames && !c->logp_valid) {   // (the tensor-core merger writes ln p itself when it feeds the decoder directly)
         int64_t blocks = (c->total_frames + 7) / 8;
@@ -285,13 +287,20 @@ int launch_viterbi(phn_ctx *c, const float *d_pen, int n_pen)
     a.lab_off = (const int64_t *)c->d_lab_off.p;
     a.nlab = (int *)c->d_nlab.p;
     const int ppl = (c->P + 31) / 32;
+    const bool tiled = c->logp_valid != 0;   // ln p came from the tensor-core merger's epilogue (tiled layout)
+#define PHN_VIT(N)                                                          \
+    do {                                                                    \
+        if (tiled) k_viterbi<N, true><<<nseg, 32, 0, c->stream>>>(a);       \
+        else k_viterbi<N, false><<<nseg, 32, 0, c->stream>>>(a);            \
+    } while (0)
     switch (ppl) {
-        case 1: k_viterbi<1><<<nseg, 32, 0, c->stream>>>(a); break;
-        case 2: k_viterbi<2><<<nseg, 32, 0, c->stream>>>(a); break;
-        case 3: k_viterbi<3><<<nseg, 32, 0, c->stream>>>(a); break;
-        case 4: k_viterbi<4><<<nseg, 32, 0, c->stream>>>(a); break;
+        case 1: PHN_VIT(1); break;
+        case 2: PHN_VIT(2); break;
+        case 3: PHN_VIT(3); break;
+        case 4: PHN_VIT(4); break;
         default: return fail(c, PHN_ERR_UNSUPPORTED, "more than 128 phonemes\n");
     }
+#undef PHN_VIT
     PHN_CUDA(c, cudaGetLastError());
     c->k_launches[PHN_K_VIT] += 1;
     return PHN_OK;

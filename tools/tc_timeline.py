@@ -30,12 +30,9 @@ out = np.zeros(256, dtype=np.int64)
 L.phn_debug_tc_timeline(rec._h, -1, out.ctypes.data)
 t = out.reshape(16, 16)
 t0 = t[t > 0].min()
-names = {2: "burst.beg", 3: "entered", 5: "operands", 13: "issued", 4: "burst.end", 8: "e1.wait", 9: "e1.D1", 10: "e1.math", 11: "e1.Hfree", 12: "e1.pub"}
+names = {2: "L1.beg", 3: "L1.ready", 4: "L1.issued", 5: "L2.beg", 6: "L2.ready", 7: "L2.issued", 8: "e1.wait", 9: "e1.D1", 10: "e1.math", 11: "e1.Hfree", 12: "e1.pub"}
 print("chunk " + " ".join(f"{names[k]:>9s}" for k in sorted(names)))
 for c in range(12):
     print(f"{c:5d} " + " ".join(f"{(t[c, k] - t0) if t[c, k] else -1:9d}" for k in sorted(names)))
-print("burst detail (relative to burst start): entered, operands there, all MMAs + commits issued, burst end")
-for c in range(1, 11):
-    b = t[c, 2]
-    print(f"{c:5d} " + " ".join(f"{t[c, k] - b:7d}" for k in (3, 5, 13, 4)))
-print("e2: wait", t[0, 13] - t0, "D2 seen", t[0, 14] - t0, "done", t[0, 15] - t0)
+e2 = ["A.begin", "A.D2seen", "A.end", "B.begin", "B.end", "C.begin", "C.end"]
+print("e2 stages of that tile (they run during the next tile):", ", ".join(f"{n} {t[15, i] - t0}" for i, n in enumerate(e2) if t[15, i]))
