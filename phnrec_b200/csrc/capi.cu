@@ -348,6 +348,10 @@ int phn_create(const char *cfg_dir, int device, phn_ctx **out)
         return bail(fail(c, PHN_ERR_CUDA, "device %d is sm_%d%d; this library carries sm_100a code only\n", device, prop.major, prop.minor));
     c->num_sms = prop.multiProcessorCount;
     if ((rc = cu(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking), "cudaStreamCreate"))) return bail(rc);
+    if ((rc = cu(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking), "cudaStreamCreate"))) return bail(rc);
+    for (auto &e : c->ev_copy)
+        if ((rc = cu(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "cudaEventCreate"))) return bail(rc);
+    if ((rc = cu(cudaEventCreateWithFlags(&c->ev_free, cudaEventDisableTiming), "cudaEventCreate"))) return bail(rc);
     for (int i = 0; i < 2 * PHN_K_COUNT; ++i)
         if ((rc = cu(cudaEventCreate(&c->ev[i]), "cudaEventCreate"))) return bail(rc);
     for (int i = 0; i < 3; ++i)
@@ -400,6 +404,10 @@ void phn_destroy(phn_ctx *c)
         if (p) cudaFree(p);
     for (auto &e : c->ev)
         if (e) cudaEventDestroy(e);
+    for (auto &e : c->ev_copy)
+        if (e) cudaEventDestroy(e);
+    if (c->ev_free) cudaEventDestroy(c->ev_free);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -516,6 +524,18 @@ int phn_synth_audio_device(phn_ctx *c, void *d_audio, int64_t bytes_per_utt, int
 }
 
 // --------------------------------------------------------------------- stages
+// mel (device) -> labels (device): everything behind K-wave on the audio -> labels path
+static int recognize_after_wave(phn_ctx *c)
+{
+    c->fuse_logp = 1;
+    int rc = run_posteriors(c);
+    c->fuse_logp = 0;
+    if (rc) return rc;
+    rc = run_decode(c, nullptr, 1);
+    c->logp_valid = 0;
+    return rc;
+}
+
 int phn_recognize_device(phn_ctx *c, const void *d_audio, const int64_t *byte_off, int n_utt)
 {
     if (!c || !d_audio) return PHN_ERR_ARG;
@@ -524,13 +544,7 @@ int phn_recognize_device(phn_ctx *c, const void *d_audio, const int64_t *byte_of
     int rc;
     if ((rc = plan_audio(c, byte_off, n_utt))) return rc;
     { StageTimer t(c, PHN_K_WAVE); if ((rc = launch_wave(c, d_audio))) return rc; }
-    c->fuse_logp = 1;
-    rc = run_posteriors(c);
-    c->fuse_logp = 0;
-    if (rc) return rc;
-    rc = run_decode(c, nullptr, 1);
-    c->logp_valid = 0;
-    return rc;
+    return recognize_after_wave(c);
 }
 
 int phn_fetch_mel(phn_ctx *c, float *mel_out)
@@ -643,9 +657,34 @@ int phn_recognize(phn_ctx *c, const void *audio, const int64_t *byte_off, int n_
     PHN_CUDA(c, cudaSetDevice(c->device));
     int rc;
     if ((rc = ensure(c, c->d_audio, (size_t)byte_off[n_utt] + 16))) return rc;
-    if (byte_off[n_utt])
-        PHN_CUDA(c, cudaMemcpyAsync(c->d_audio.p, audio, (size_t)byte_off[n_utt], cudaMemcpyHostToDevice, c->stream));
-    if ((rc = phn_recognize_device(c, c->d_audio.p, byte_off, n_utt))) return rc;
+    reset_timing(c);
+    if ((rc = plan_audio(c, byte_off, n_utt))) return rc;
+    // The audio goes up in groups of whole utterances on a copy stream; K-wave of group g starts as soon as the
+    // group has landed and runs under the copy of group g+1, so only the first group's transfer is exposed.
+    const int64_t total = byte_off[n_utt];
+    int ng = (int)(total / ((int64_t)8 << 20));
+    ng = ng < 1 ? 1 : (ng > 16 ? 16 : ng);
+    PHN_CUDA(c, cudaEventRecord(c->ev_free, c->stream));             // (buffer growth and its zero fill are stream work)
+    PHN_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->ev_free, 0));
+    {
+        StageTimer t(c, PHN_K_WAVE);
+        int u0 = 0;
+        for (int g = 0; g < ng; ++g) {
+            int u1 = u0;
+            const int64_t want = total * (g + 1) / ng;
+            while (u1 < n_utt && (byte_off[u1 + 1] <= want || g == ng - 1)) ++u1;
+            if (g == ng - 1) u1 = n_utt;
+            if (u1 == u0) continue;
+            const int64_t b0 = byte_off[u0], nb = byte_off[u1] - b0;
+            if (nb)
+                PHN_CUDA(c, cudaMemcpyAsync((uint8_t *)c->d_audio.p + b0, (const uint8_t *)audio + b0, (size_t)nb, cudaMemcpyHostToDevice, c->copy_stream));
+            PHN_CUDA(c, cudaEventRecord(c->ev_copy[g], c->copy_stream));
+            PHN_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_copy[g], 0));
+            if ((rc = launch_wave(c, c->d_audio.p, c->h_frame_off[u0], c->h_frame_off[u1]))) return rc;
+            u0 = u1;
+        }
+    }
+    if ((rc = recognize_after_wave(c))) return rc;
     if (frame_off_out) memcpy(frame_off_out, c->h_frame_off.data(), sizeof(int64_t) * (n_utt + 1));
     return phn_fetch_labels(c, labels, label_cap, label_off);
 }

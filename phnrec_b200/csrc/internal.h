@@ -64,6 +64,9 @@ struct DevTables {
 struct phn_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;      // H2D of audio groups, overlapped with K-wave of the previous group (phn_recognize)
+    cudaEvent_t ev_copy[16] = {nullptr};     // group g has landed
+    cudaEvent_t ev_free = nullptr;           // the audio buffer's previous readers are done
     std::string err;
     std::string cfg_dir;
     phn::Config cfg;
@@ -121,7 +124,7 @@ int fail(phn_ctx *c, int code, const char *fmt, ...);
 int ensure(phn_ctx *c, phn_ctx::Buf &b, size_t bytes);
 
 // ---- kernel launchers (each in its own .cu)
-int launch_wave(phn_ctx *c, const void *d_audio);                          // k_wave.cu
+int launch_wave(phn_ctx *c, const void *d_audio, int64_t f_begin = 0, int64_t f_end = -1);   // k_wave.cu (frame range)
 int launch_sentence_mean(phn_ctx *c);                                      // k_norm.cu
 int launch_online_norm(phn_ctx *c, float *d_x, int64_t frames, int nb, int interval, int mean_norm, int var_norm);
 int launch_stc(phn_ctx *c, int64_t f0, int64_t nf);                        // k_stc.cu

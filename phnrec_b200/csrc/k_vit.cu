@@ -92,8 +92,39 @@ __global__ void __launch_bounds__(32) k_viterbi(VitArgs a)
     int last_mi = -1;  // prev[0][0] after the last frame (phndec.cpp:240)
 
     constexpr int FB = 8;  // frames whose observations are fetched ahead of the recurrence
+    // TILED input (column-major inside 128-frame tiles): a warp's row read would touch one 128-byte line per
+    // column, so 16-frame panels [16 frames][3P columns] are staged through shared memory with 4-byte cp.async
+    // (two columns x 16 consecutive frames = 2 x 64 contiguous bytes per instruction), a ring of three panels
+    // indexed by global frame number, the next panel in flight while the recurrence consumes the current ones.
+    extern __shared__ float s_panel[];                 // [48][pstride]
+    const int ncol = 3 * a.P;
+    const int pstride = ncol | 1;                      // odd row stride: conflict-free panel writes
+    int64_t next_blk = f0 >> 4;                        // next 16-frame panel (global numbering) to request
+    const int64_t last_blk = T > 0 ? (f0 + T - 1) >> 4 : -1;
+    auto request_panel = [&](int64_t blk) {
+        const int64_t F = blk * 16 + (lane & 15);
+        const float *src = a.logp + ((F >> 7) * a.ld) * 128 + (F & 127);
+        float *dst = s_panel + (size_t)(F % 48) * pstride;
+        for (int cc = lane >> 4; cc < ncol; cc += 2)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(dst + cc)), "l"(__cvta_generic_to_global(src + (size_t)cc * 128)) : "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
     for (int tb = 0; tb < T; tb += FB) {
         float obs[FB][PPL][3];
+        if (TILED) {
+            int64_t need = (f0 + tb + FB - 1) >> 4;    // last panel this group of frames reads
+            if (need > last_blk) need = last_blk;
+            while (next_blk <= need) request_panel(next_blk++);
+            if (next_blk <= last_blk && next_blk == need + 1) {   // one panel ahead
+                request_panel(next_blk++);
+                asm volatile("cp.async.wait_group 1;" ::: "memory");
+            } else if (next_blk == need + 2) {
+                asm volatile("cp.async.wait_group 1;" ::: "memory");
+            } else {
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
+            }
+            __syncwarp();
+        }
 #pragma unroll
         for (int q = 0; q < FB; ++q)
 #pragma unroll
@@ -102,9 +133,10 @@ __global__ void __launch_bounds__(32) k_viterbi(VitArgs a)
                 for (int j = 0; j < 3; ++j) {
                     const int i = lane + 32 * r;
                     const int64_t f = f0 + tb + q;
-                    const int64_t at = TILED ? ((f >> 7) * a.ld + 3 * i + j) * 128 + (f & 127) : f * a.ld + 3 * i + j;
-                    obs[q][r][j] = (valid[r] && tb + q < T) ? a.logp[at] : 0.0f;
+                    if (TILED) obs[q][r][j] = (valid[r] && tb + q < T) ? s_panel[(size_t)(f % 48) * pstride + 3 * i + j] : 0.0f;
+                    else obs[q][r][j] = (valid[r] && tb + q < T) ? a.logp[f * a.ld + 3 * i + j] : 0.0f;
                 }
+        if (TILED) __syncwarp();   // (all lanes have their observations before a later request reuses a panel slot)
 
 #pragma unroll
         for (int q = 0; q < FB; ++q) {
@@ -288,9 +320,10 @@ int launch_viterbi(phn_ctx *c, const float *d_pen, int n_pen)
     a.nlab = (int *)c->d_nlab.p;
     const int ppl = (c->P + 31) / 32;
     const bool tiled = c->logp_valid != 0;   // ln p came from the tensor-core merger's epilogue (tiled layout)
+    const size_t vsmem = sizeof(float) * 48 * (size_t)((3 * c->P) | 1);
 #define PHN_VIT(N)                                                          \
     do {                                                                    \
-        if (tiled) k_viterbi<N, true><<<nseg, 32, 0, c->stream>>>(a);       \
+        if (tiled) k_viterbi<N, true><<<nseg, 32, vsmem, c->stream>>>(a);   \
         else k_viterbi<N, false><<<nseg, 32, 0, c->stream>>>(a);            \
     } while (0)
     switch (ppl) {

@@ -24,6 +24,7 @@ struct WaveArgs {
     const int64_t *byte_off, *frame_off;
     int n_utt;
     int64_t total_frames;
+    int64_t f_begin, f_end;   // frame range of this launch (a group of whole utterances)
     int fmt, vs, step, N, logN, nbanks;
     float scale, dc_shift, frame_shift, frame_floor, preem;
     int z_mean;
@@ -123,7 +124,7 @@ __global__ void __launch_bounds__(kWaveWarps * 32) k_wave(WaveArgs a)
     const int bps = a.fmt == PHN_WAVE_LIN16 ? 2 : 1;
     const bool plain = !a.z_mean && a.preem == 0.0f;
 
-    for (int64_t f = (int64_t)blockIdx.x * kWaveWarps + warp; f < a.total_frames; f += (int64_t)gridDim.x * kWaveWarps) {
+    for (int64_t f = a.f_begin + (int64_t)blockIdx.x * kWaveWarps + warp; f < a.f_end; f += (int64_t)gridDim.x * kWaveWarps) {
         const int u = find_utt(a.frame_off, a.n_utt, f);
         const int64_t t = f - a.frame_off[u];
         const int64_t b0 = a.byte_off[u];
@@ -262,7 +263,7 @@ static int launch_wave_t(phn_ctx *c, const WaveArgs &a)
     const size_t smem = sizeof(double2) * N + sizeof(float) * (N + N2) + sizeof(int) * N2 + sizeof(double) * 32 +
                         sizeof(float2) * (size_t)kWaveWarps * (N + N / 32 + N2 / 2);
     PHN_CUDA(c, cudaFuncSetAttribute(k_wave<EXACT, LOGN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int64_t blocks = (c->total_frames + kWaveWarps - 1) / kWaveWarps;
+    int64_t blocks = (a.f_end - a.f_begin + kWaveWarps - 1) / kWaveWarps;
     const int64_t cap = (int64_t)c->num_sms * 6;
     if (blocks > cap) blocks = cap;
     k_wave<EXACT, LOGN><<<(unsigned)blocks, kWaveWarps * 32, smem, c->stream>>>(a);
@@ -270,15 +271,17 @@ static int launch_wave_t(phn_ctx *c, const WaveArgs &a)
     return PHN_OK;
 }
 
-int launch_wave(phn_ctx *c, const void *d_audio)
+int launch_wave(phn_ctx *c, const void *d_audio, int64_t f_begin, int64_t f_end)
 {
-    if (c->total_frames == 0) return PHN_OK;
+    if (f_end < 0) f_end = c->total_frames;
+    if (f_end <= f_begin) return PHN_OK;
     WaveArgs a;
     a.audio = (const uint8_t *)d_audio;
     a.byte_off = (const int64_t *)c->d_byte_off.p;
     a.frame_off = (const int64_t *)c->d_frame_off.p;
     a.n_utt = c->n_utt;
     a.total_frames = c->total_frames;
+    a.f_begin = f_begin; a.f_end = f_end;
     a.fmt = c->fmt; a.vs = c->vs; a.step = c->step; a.N = c->mt.N; a.logN = c->mt.logN; a.nbanks = c->nbanks;
     a.scale = c->scale; a.dc_shift = c->dc_shift; a.frame_shift = c->frame_shift; a.frame_floor = c->frame_floor;
     a.preem = c->preem; a.z_mean = c->z_mean;
