@@ -76,6 +76,7 @@ struct phn_ctx {
     float lo = 0, hi = 4000, preem = 0, wpenalty = -2.f, frame_shift = 0.f, frame_floor = -9999.9f, scale = 1.f, dc_shift = 0.f;
     int mlp_mode = PHN_MLP_EXACT_FP32;
     void *tc = nullptr;  // tensor-core mode state (k_mlp_tc.cu)
+    void *stc_btab = nullptr, *stc_bias = nullptr;   // K-stc tensor-core formulation: constant matrices (k_stc.cu)
     int force_exact_wave = 0;
     void *tc_dbg = nullptr;   // device buffer for the tensor-core kernel's debug timeline (phn_debug_tc_timeline)
     int tc_dbg_net = -1;

@@ -10,6 +10,9 @@
 // (C0 + 10 DCT coefficients), sums in the reference's order with separately rounded mul/add.
 #include "internal.h"
 
+#include <cmath>
+#include <vector>
+
 namespace phn {
 
 struct StcArgs {
@@ -164,6 +167,224 @@ __global__ void __launch_bounds__(256) k_stc(StcArgs a_)
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Tensor-core pipeline: the same features as 16 x 16 x 16 matrix products on mma.sync.
+// x[frame][11 b + n] = sum_j (mel[c(frame, j)][b] - mean[b]) * Bm[s][b][j][n] - bias,
+//     Bm = window[s][j] * basis[n][j] * sqrt(2/16) * dev[s][11 b + n],  bias = nn_mean * dev
+// (window, C0/DCT basis, the sqrt(2/16) factor and NeuralNet::Normalize folded into one constant matrix per
+// (side, band)).  A = 16 frames x 16 taps, B = 16 taps x 16 (11 used) coefficients, both split into fp16 hi + lo,
+// three products (hi.hi + lo.hi + hi.lo) accumulated in fp32: 2^-22 relative, i.e. fp32-grade features for the
+// price of 6 MMAs per (16 frames, side, band) instead of 2816 FMAs.
+// CTA = one 128-frame tile of the fp16 activation images (8 warps x 16 frames), persistent over tiles.
+struct StcMmaArgs {
+    const float *mel, *mean;
+    const int64_t *frame_off;
+    int n_utt, nb;
+    int64_t f0, nf, total_frames;
+    const uint4 *btab;     // [2][nb][2 n-tiles][32 lanes] B fragments {hi k0-7, hi k8-15, lo k0-7, lo k8-15}
+    const float *bias;     // [2][nb * 11]
+    uint8_t *x0h, *x1h;
+    int kb1, n_tiles;
+};
+
+__device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1)
+{
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void split_half2(float x, float y, uint32_t &hi, uint32_t &lo)
+{
+    const __half2 h = __floats2half2_rn(x, y);
+    const float2 hf = __half22float2(h);
+    const __half2 l = __floats2half2_rn(x - hf.x, y - hf.y);
+    hi = *reinterpret_cast<const uint32_t *>(&h);
+    lo = *reinterpret_cast<const uint32_t *>(&l);
+}
+
+constexpr int STCM_F = 128;     // frames per CTA pass = one image tile
+
+template <int NB>
+__global__ void __launch_bounds__(256, 2) k_stc_mma(StcMmaArgs a)
+{
+    constexpr int NIN = NB * 11;
+    constexpr int COLS = (NIN + 2 + 63) / 64 * 64;   // image columns (64-column blocks), = 64 * kb1
+    constexpr int STCM_LD = COLS + 8;                // staging row stride in halves (16-byte aligned rows, conflict-free)
+    extern __shared__ __align__(16) uint8_t stc_smem[];
+    uint4 *s_b = reinterpret_cast<uint4 *>(stc_smem);                                   // [2][NB][2][32]
+    float *s_bias = reinterpret_cast<float *>(s_b + 2 * NB * 2 * 32);                   // [2][NIN]
+    float *s_mel = s_bias + 2 * NIN;                                                    // [(128 + 30)][NB]
+    __half *s_out = reinterpret_cast<__half *>(s_mel + (STCM_F + 30) * NB + ((STCM_F + 30) * NB & 1) + 2);   // [8][16][STCM_LD]
+    __shared__ int64_t s_u0[STCM_F];
+    __shared__ int s_T[STCM_F], s_u[STCM_F];
+    s_out = reinterpret_cast<__half *>((reinterpret_cast<uintptr_t>(s_out) + 15) & ~(uintptr_t)15);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    for (int i = threadIdx.x; i < 2 * NB * 2 * 32; i += blockDim.x) s_b[i] = a.btab[i];
+    for (int i = threadIdx.x; i < 2 * NIN; i += blockDim.x) s_bias[i] = a.bias[i];
+    // image columns beyond the features: the two constant-1 inputs that multiply the bias columns of the layer-1
+    // weight image (k_mlp_tc.cu), then zeros; never overwritten below
+    __half *my_out = s_out + (size_t)warp * 16 * STCM_LD;
+    for (int i = lane; i < 16 * (COLS - NIN); i += 32) {
+        const int r = i / (COLS - NIN), cidx = NIN + i % (COLS - NIN);
+        my_out[r * STCM_LD + cidx] = __float2half_rn(cidx < NIN + 2 ? 1.0f : 0.0f);
+    }
+    for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+        const int64_t fl0 = (int64_t)tile * STCM_F;
+        const int64_t G0 = a.f0 + fl0 - 15;
+        __syncthreads();   // (previous tile's readers of s_mel / s_u are done)
+        for (int q = threadIdx.x; q < (STCM_F + 30) * NB; q += blockDim.x) {
+            const int64_t gr = G0 + q / NB;
+            s_mel[q] = (gr >= 0 && gr < a.total_frames) ? a.mel[G0 * NB + q] : 0.0f;
+        }
+        if (threadIdx.x < STCM_F) {
+            const int64_t fl = fl0 + threadIdx.x;
+            if (fl < a.nf) {
+                const int u = stc_find_utt(a.frame_off, a.n_utt, a.f0 + fl);
+                s_u[threadIdx.x] = u;
+                s_u0[threadIdx.x] = a.frame_off[u];
+                s_T[threadIdx.x] = (int)(a.frame_off[u + 1] - a.frame_off[u]);
+            } else {
+                s_u[threadIdx.x] = -1;
+            }
+        }
+        __syncthreads();
+        // this thread's two frames (fragment rows g and g + 8 of the warp's 16)
+        const int fa = warp * 16 + g, fb = fa + 8;
+        const int ua = s_u[fa], ub = s_u[fb];
+        const int Ta = ua < 0 ? 1 : s_T[fa], Tb = ub < 0 ? 1 : s_T[fb];
+        const int64_t u0a = ua < 0 ? 0 : s_u0[fa], u0b = ub < 0 ? 0 : s_u0[fb];
+        const int ra = (int)(a.f0 + fl0 + fa - u0a), rb = (int)(a.f0 + fl0 + fb - u0b);
+        const float *mean_a = a.mean + (size_t)(ua < 0 ? 0 : ua) * NB, *mean_b = a.mean + (size_t)(ub < 0 ? 0 : ub) * NB;
+#pragma unroll 1
+        for (int side = 0; side < 2; ++side) {
+            // shared-memory row offsets of the 4 taps (2t, 2t+1, 2t+8, 2t+9) of both frames; clamped inside the utterance
+            int oa[4], ob[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int j = 2 * t + (i & 1) + (i >> 1) * 8;
+                int ta = ra - 15 + j + side * 15, tb = rb - 15 + j + side * 15;
+                ta = ta < 0 ? 0 : (ta > Ta - 1 ? Ta - 1 : ta);
+                tb = tb < 0 ? 0 : (tb > Tb - 1 ? Tb - 1 : tb);
+                oa[i] = (int)(u0a + ta - G0) * NB;
+                ob[i] = (int)(u0b + tb - G0) * NB;
+            }
+            const uint4 *bt = s_b + (size_t)side * NB * 64 + lane;
+            const float *bias = s_bias + side * NIN;
+#pragma unroll 3
+            for (int b = 0; b < NB; ++b) {
+                const float ma = ua < 0 ? 0.0f : __ldg(mean_a + b), mb = ub < 0 ? 0.0f : __ldg(mean_b + b);
+                uint32_t ah[4], al[4];   // A fragment: {row g k 2t..}, {row g+8 k 2t..}, {row g k 2t+8..}, {row g+8 k 2t+8..}
+                split_half2(ua < 0 ? 0.0f : s_mel[oa[0] + b] - ma, ua < 0 ? 0.0f : s_mel[oa[1] + b] - ma, ah[0], al[0]);
+                split_half2(ub < 0 ? 0.0f : s_mel[ob[0] + b] - mb, ub < 0 ? 0.0f : s_mel[ob[1] + b] - mb, ah[1], al[1]);
+                split_half2(ua < 0 ? 0.0f : s_mel[oa[2] + b] - ma, ua < 0 ? 0.0f : s_mel[oa[3] + b] - ma, ah[2], al[2]);
+                split_half2(ub < 0 ? 0.0f : s_mel[ob[2] + b] - mb, ub < 0 ? 0.0f : s_mel[ob[3] + b] - mb, ah[3], al[3]);
+#pragma unroll
+                for (int nt = 0; nt < 2; ++nt) {
+                    const uint4 bf = bt[(b * 2 + nt) * 32];
+                    float d[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+                    mma16816(d, al, bf.x, bf.y);     // small terms first
+                    mma16816(d, ah, bf.z, bf.w);
+                    mma16816(d, ah, bf.x, bf.y);
+                    const int n = nt * 8 + 2 * t;    // coefficient of d[0] / d[2]; d[1] / d[3] are n + 1
+                    if (n < 11) {
+                        const int col = b * 11 + n;
+                        my_out[g * STCM_LD + col] = __float2half_rn(ua < 0 ? 0.0f : d[0] - bias[col]);
+                        my_out[(g + 8) * STCM_LD + col] = __float2half_rn(ub < 0 ? 0.0f : d[2] - bias[col]);
+                        if (n + 1 < 11) {
+                            my_out[g * STCM_LD + col + 1] = __float2half_rn(ua < 0 ? 0.0f : d[1] - bias[col + 1]);
+                            my_out[(g + 8) * STCM_LD + col + 1] = __float2half_rn(ub < 0 ? 0.0f : d[3] - bias[col + 1]);
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+            // the warp's 16 rows x 24 chunks of 16 bytes -> image (K-major SW128 blocks, k_mlp_tc.cu)
+            uint8_t *img = (side ? a.x1h : a.x0h) + (size_t)tile * a.kb1 * 16384;
+            for (int q = lane; q < 16 * (COLS / 8); q += 32) {
+                const int r16 = q / (COLS / 8), ch = q - r16 * (COLS / 8);
+                const int r = warp * 16 + r16;
+                if (fl0 + r < a.nf)
+                    *reinterpret_cast<uint4 *>(img + (size_t)(ch >> 3) * 16384 + r * 128 + ((((unsigned)ch & 7u) ^ ((unsigned)r & 7u)) << 4)) =
+                        *reinterpret_cast<const uint4 *>(my_out + r16 * STCM_LD + ch * 8);
+            }
+            __syncwarp();
+        }
+    }
+}
+
+
+// constant matrices of the tensor-core formulation, built once per context on the host (fp16 hi + lo fragments)
+static int stc_mma_prepare(phn_ctx *c)
+{
+    if (c->stc_btab) return PHN_OK;
+    const int nb = c->nbanks, nin = nb * 11;
+    std::vector<uint32_t> tab((size_t)2 * nb * 2 * 32 * 4);
+    std::vector<float> bias((size_t)2 * nin);
+    const double normc = (double)sqrtf(2.0f / 16.0f);
+    const float PiByN = (float)M_PI / 16.0f;
+    auto coef = [&](int s, int b, int j, int n) -> double {   // Bm[s][b][j][n]
+        if (n >= 11) return 0.0;
+        const double basis = n == 0 ? 1.0 : (double)cosf(PiByN * (float)n * ((float)j + 0.5f));   // CalcC0 / sDCT, dspc.h:206-233
+        return (double)c->win[s * 16 + j] * basis * normc * (double)c->hnet[s].dev[b * 11 + n];
+    };
+    auto pack = [&](double v0, double v1, uint32_t &hi, uint32_t &lo) {
+        const __half h0 = __float2half_rn((float)v0), h1 = __float2half_rn((float)v1);
+        const __half l0 = __float2half_rn((float)(v0 - (double)__half2float(h0))), l1 = __float2half_rn((float)(v1 - (double)__half2float(h1)));
+        hi = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+        lo = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+    };
+    for (int s = 0; s < 2; ++s)
+        for (int b = 0; b < nb; ++b) {
+            for (int nt = 0; nt < 2; ++nt)
+                for (int lane = 0; lane < 32; ++lane) {
+                    const int g = lane >> 2, t = lane & 3, n = nt * 8 + g;
+                    uint32_t *o = &tab[((((size_t)s * nb + b) * 2 + nt) * 32 + lane) * 4];
+                    pack(coef(s, b, 2 * t, n), coef(s, b, 2 * t + 1, n), o[0], o[2]);          // k = 2t, 2t+1
+                    pack(coef(s, b, 2 * t + 8, n), coef(s, b, 2 * t + 9, n), o[1], o[3]);      // k = 2t+8, 2t+9
+                }
+            for (int n = 0; n < 11; ++n) bias[(size_t)s * nin + b * 11 + n] = c->hnet[s].mean[b * 11 + n] * c->hnet[s].dev[b * 11 + n];
+        }
+    PHN_CUDA(c, cudaMalloc(&c->stc_btab, tab.size() * 4));
+    PHN_CUDA(c, cudaMalloc(&c->stc_bias, bias.size() * 4));
+    PHN_CUDA(c, cudaMemcpy(c->stc_btab, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice));
+    PHN_CUDA(c, cudaMemcpy(c->stc_bias, bias.data(), bias.size() * 4, cudaMemcpyHostToDevice));
+    return PHN_OK;
+}
+
+template <int NB>
+static int launch_stc_mma_t(phn_ctx *c, const StcMmaArgs &a)
+{
+    constexpr int NIN = NB * 11, COLS = (NIN + 2 + 63) / 64 * 64;
+    const size_t smem = (size_t)2 * NB * 2 * 32 * 16 + sizeof(float) * 2 * NIN + sizeof(float) * ((STCM_F + 30) * NB + 4) +
+                        (size_t)8 * 16 * (COLS + 8) * 2 + 32;
+    PHN_CUDA(c, cudaFuncSetAttribute(k_stc_mma<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int grid = a.n_tiles < 2 * c->num_sms ? a.n_tiles : 2 * c->num_sms;
+    k_stc_mma<NB><<<grid, 256, smem, c->stream>>>(a);
+    PHN_CUDA(c, cudaGetLastError());
+    return PHN_OK;
+}
+
+static int launch_stc_mma(phn_ctx *c, int64_t f0, int64_t nf)
+{
+    int rc;
+    if ((rc = stc_mma_prepare(c))) return rc;
+    StcMmaArgs a;
+    a.mel = (const float *)c->d_mel.p;
+    a.mean = (const float *)c->d_mean.p;
+    a.frame_off = (const int64_t *)c->d_frame_off.p;
+    a.n_utt = c->n_utt; a.nb = c->nbanks;
+    a.f0 = f0; a.nf = nf; a.total_frames = c->total_frames;
+    a.btab = (const uint4 *)c->stc_btab; a.bias = (const float *)c->stc_bias;
+    a.x0h = (uint8_t *)c->d_x0h.p; a.x1h = (uint8_t *)c->d_x1h.p;
+    a.kb1 = c->net[0].k1P / 64;
+    a.n_tiles = (int)((nf + STCM_F - 1) / STCM_F);
+    rc = c->nbanks == 15 ? launch_stc_mma_t<15>(c, a) : launch_stc_mma_t<23>(c, a);
+    if (rc) return rc;
+    c->k_launches[PHN_K_STC] += 1;
+    return PHN_OK;
+}
+
 int launch_stc(phn_ctx *c, int64_t f0, int64_t nf)
 {
     if (nf == 0) return PHN_OK;
@@ -178,6 +399,7 @@ int launch_stc(phn_ctx *c, int64_t f0, int64_t nf)
     a.nmean1 = c->net[1].mean; a.ndev1 = c->net[1].dev;
     a.normc = sqrtf(2.0f / 16.0f);
     const bool tc = c->mlp_mode == PHN_MLP_TC_F16;
+    if (tc && (c->nbanks == 15 || c->nbanks == 23) && c->net[0].k1P / 64 == (c->nbanks * 11 + 2 + 63) / 64) return launch_stc_mma(c, f0, nf);
     a.x0 = tc ? nullptr : (float *)c->d_x0.p;
     a.x1 = tc ? nullptr : (float *)c->d_x1.p;
     a.x0h = tc ? (uint8_t *)c->d_x0h.p : nullptr;
