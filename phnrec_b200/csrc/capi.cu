@@ -164,7 +164,7 @@ static int run_posteriors(phn_ctx *c)
     { StageTimer t(c, PHN_K_MEAN); if ((rc = launch_sentence_mean(c))) return rc; }
     const bool tc = c->mlp_mode == PHN_MLP_TC_F16;
     const int64_t F = c->total_frames;
-    int64_t ch = tc ? (int64_t)1 << 18 : (int64_t)1 << 15;
+    int64_t ch = tc ? (int64_t)1 << 20 : (int64_t)1 << 15;   // frames per pass of the MLP workspace (tensor-core: 1.4 KB per frame)
     if (ch > F) ch = (F + 127) / 128 * 128;
     if (ch == 0) return PHN_OK;
     c->logp_valid = 0;
