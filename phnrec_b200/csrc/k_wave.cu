@@ -256,6 +256,184 @@ __global__ void __launch_bounds__(kWaveWarps * 32) k_wave(WaveArgs a)
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Tensor-core pipeline (fp32 front end): TWO real frames per complex FFT.  z = a + i b; by linearity and the
+// conjugate symmetry of real signals  A[k] = (Z[k] + conj Z[N-k]) / 2,  B[k] = (Z[k] - conj Z[N-k]) / 2i,  so
+// |A[k]|^2 = ((Zr[k] + Zr[N-k])^2 + (Zi[k] - Zi[N-k])^2) / 4,  |B[k]|^2 = ((Zr[k] - Zr[N-k])^2 + (Zi[k] + Zi[N-k])^2) / 4.
+// Half the butterflies per frame; the price is fp32 cross-talk between the two frames at the 1e-7 level of the
+// louder one.  An all-zero frame (digital silence) is detected on load and keeps the reference's exact answer
+// (sLn's guard: mel = 0), whatever its partner holds.  Only for the plain front end (no z_mean / pre-emphasis).
+template <int LOGN>
+__global__ void __launch_bounds__(kWaveWarps * 32) k_wave_pair(WaveArgs a)
+{
+    constexpr int N = 1 << LOGN, N2 = N / 2;
+    constexpr int OCT = N / 256;
+    constexpr int L3 = LOGN - 6;
+    constexpr int R3 = 1 << L3;
+    constexpr int WORK = N + N / 32 + N2 / 2;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    using TW = float2;
+    TW *s_tw = reinterpret_cast<TW *>(smem_raw);
+    float *s_ham = reinterpret_cast<float *>(smem_raw + sizeof(double2) * N);
+    float *s_coef = s_ham + N;
+    int *s_bank = reinterpret_cast<int *>(s_coef + N2);
+    double *s_logtab = reinterpret_cast<double *>(s_bank + N2);
+    float2 *s_work = reinterpret_cast<float2 *>(s_logtab + 32);
+    logf_table_to_smem(s_logtab, threadIdx.x, blockDim.x);
+    for (int i = threadIdx.x; i < N - 1; i += blockDim.x) {
+        const double2 w = a.tw[i];
+        s_tw[i] = make_float2((float)w.x, (float)w.y);
+    }
+    for (int i = threadIdx.x; i < N; i += blockDim.x) s_ham[i] = i < a.vs ? a.hamming[i] : 0.0f;
+    for (int i = threadIdx.x; i < N2; i += blockDim.x) { s_coef[i] = a.coeffs[i]; s_bank[i] = a.banks[i]; }
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float2 *data = s_work + (size_t)warp * WORK;
+    float *pwA = reinterpret_cast<float *>(data + N + N / 32);   // [N2] power spectrum of the first frame
+    float *pwB = reinterpret_cast<float *>(data);                // [N2] second frame (aliases data[], free by then)
+    const int bps = a.fmt == PHN_WAVE_LIN16 ? 2 : 1;
+    const int64_t n_pairs = (a.f_end - a.f_begin + 1) / 2;
+
+    for (int64_t p = (int64_t)blockIdx.x * kWaveWarps + warp; p < n_pairs; p += (int64_t)gridDim.x * kWaveWarps) {
+        const int64_t fA = a.f_begin + 2 * p, fB = fA + 1;
+        const bool haveB = fB < a.f_end;
+        int64_t b0[2], len[2], s0[2];
+#pragma unroll
+        for (int w = 0; w < 2; ++w) {
+            const int64_t f = w ? (haveB ? fB : fA) : fA;
+            const int u = find_utt(a.frame_off, a.n_utt, f);
+            b0[w] = a.byte_off[u];
+            len[w] = (a.byte_off[u + 1] - b0[w]) / bps;
+            s0[w] = (f - a.frame_off[u]) * a.step;
+        }
+        auto sample = [&](int w, int i) -> float {  // decode (srec.cpp:742-743 / 768-769), dc shift, scale; 0 beyond the signal
+            float x = 0.0f;
+            if (i < a.vs && s0[w] + i < len[w]) {
+                if (a.fmt == PHN_WAVE_LIN16) {
+                    const uint8_t *q = a.audio + b0[w] + 2 * (s0[w] + i);
+                    x = (float)(short)((unsigned)q[0] | ((unsigned)q[1] << 8));
+                } else {
+                    x = 8.0f * (float)alaw_d5(a.audio[b0[w] + s0[w] + i]);
+                }
+                if (a.dc_shift != 0.0f) x += a.dc_shift;
+                if (a.scale != 1.0f) x *= a.scale;
+            }
+            return x;
+        };
+
+        // ---- pass 1 (stages h = 1, 2, 4): elements 8o .. 8o+7 = windowed inputs at bit-reversed positions
+        float2 v[OCT][8];
+        bool nzA = false, nzB = false;
+#pragma unroll
+        for (int oc = 0; oc < OCT; ++oc) {
+            const int o = lane + 32 * oc;
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                const int i = (int)(__brev((unsigned)(8 * o + r)) >> (32 - LOGN));
+                const float xa = sample(0, i), xb = haveB ? sample(1, i) : 0.0f;
+                nzA |= xa != 0.0f; nzB |= xb != 0.0f;
+                const float hm = s_ham[i];
+                v[oc][r] = make_float2(xa * hm, xb * hm);
+            }
+        }
+        const bool liveA = __any_sync(0xffffffffu, nzA), liveB = __any_sync(0xffffffffu, nzB);
+#pragma unroll
+        for (int oc = 0; oc < OCT; ++oc) {
+            const int o = lane + 32 * oc;
+            fft_pass<false, 3, TW>(v[oc], s_tw, 1, 0);
+#pragma unroll
+            for (int r = 0; r < 8; ++r) data[pad_idx(8 * o + r)] = v[oc][r];
+        }
+        __syncwarp();
+        // ---- pass 2 (h = 8, 16, 32)
+#pragma unroll
+        for (int oc = 0; oc < OCT; ++oc) {
+            const int o = lane + 32 * oc;
+            const int low3 = o & 7, high = o >> 3;
+#pragma unroll
+            for (int r = 0; r < 8; ++r) v[oc][r] = data[pad_idx(low3 + 8 * r + 64 * high)];
+        }
+        __syncwarp();
+#pragma unroll
+        for (int oc = 0; oc < OCT; ++oc) {
+            const int o = lane + 32 * oc;
+            const int low3 = o & 7, high = o >> 3;
+            fft_pass<false, 3, TW>(v[oc], s_tw, 8, low3);
+#pragma unroll
+            for (int r = 0; r < 8; ++r) data[pad_idx(low3 + 8 * r + 64 * high)] = v[oc][r];
+        }
+        __syncwarp();
+        // ---- pass 3 (h = 64 .. N/2): elements low6 + 64r, two groups per lane; all N bins are needed now
+        float2 w3[2][R3];
+#pragma unroll
+        for (int gq = 0; gq < 2; ++gq) {
+            const int low6 = lane + 32 * gq;
+#pragma unroll
+            for (int r = 0; r < R3; ++r) w3[gq][r] = data[pad_idx(low6 + 64 * r)];
+        }
+        __syncwarp();
+#pragma unroll
+        for (int gq = 0; gq < 2; ++gq) {
+            const int low6 = lane + 32 * gq;
+            fft_pass<false, L3, TW>(w3[gq], s_tw, 64, low6);
+#pragma unroll
+            for (int r = 0; r < R3; ++r) data[pad_idx(low6 + 64 * r)] = w3[gq][r];
+        }
+        __syncwarp();
+        // ---- separate the two spectra: bin k = low6 + 64r (r < R3/2) pairs with bin N - k
+        float pa[2][R3 / 2], pb[2][R3 / 2];
+#pragma unroll
+        for (int gq = 0; gq < 2; ++gq) {
+            const int low6 = lane + 32 * gq;
+#pragma unroll
+            for (int r = 0; r < R3 / 2; ++r) {
+                const int k = low6 + 64 * r;
+                const float2 z = w3[gq][r];
+                const float2 y = data[pad_idx((N - k) & (N - 1))];   // k = 0 pairs with itself
+                const float sr = z.x + y.x, di = z.y - y.y, dr = z.x - y.x, si = z.y + y.y;
+                pa[gq][r] = 0.25f * fmaf(sr, sr, di * di);           // cPower (dspc.h:141-146) of frame A
+                pb[gq][r] = 0.25f * fmaf(dr, dr, si * si);           //                          frame B
+            }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int gq = 0; gq < 2; ++gq)
+#pragma unroll
+            for (int r = 0; r < R3 / 2; ++r) {
+                const int k = lane + 32 * gq + 64 * r;
+                pwA[k] = pa[gq][r];
+                pwB[k] = pb[gq][r];
+            }
+        __syncwarp();
+
+        // ---- mel filterbank (dspc.cpp:236-269): bank b of frame A on lane b, of frame B on lane 16 + b when both fit
+        // a warp, else one frame after the other
+        const bool both = a.nbanks <= 16;
+#pragma unroll 1
+        for (int pass = 0; pass < (both ? 1 : 2); ++pass) {
+            const int w = both ? (lane >> 4) : pass;
+            const int bk = both ? (lane & 15) : lane;
+            if (bk < a.nbanks && (w == 0 || haveB)) {
+                const float *pw = w ? pwB : pwA;
+                float acc = 0.0f;
+                const int hi = a.khi[bk];
+                for (int k = a.klo[bk]; k <= hi; ++k) {
+                    const float pk = pw[k];
+                    const float v2 = s_coef[k] * pk;
+                    acc += s_bank[k] == bk ? pk - v2 : v2;
+                }
+                if (!(w ? liveB : liveA)) acc = 0.0f;                // digital silence stays exactly silent
+                float o = ln_guarded(acc, s_logtab);
+                if (a.frame_shift != 0.0f) o += a.frame_shift;                        // srec.cpp:1594-1620
+                if (a.frame_floor != -9999.9f && o < a.frame_floor) o = a.frame_floor;
+                a.mel[(w ? fB : fA) * a.nbanks + bk] = o;
+            }
+        }
+        __syncwarp();
+    }
+}
+
 template <bool EXACT, int LOGN>
 static int launch_wave_t(phn_ctx *c, const WaveArgs &a)
 {
@@ -263,9 +441,15 @@ static int launch_wave_t(phn_ctx *c, const WaveArgs &a)
     const size_t smem = sizeof(double2) * N + sizeof(float) * (N + N2) + sizeof(int) * N2 + sizeof(double) * 32 +
                         sizeof(float2) * (size_t)kWaveWarps * (N + N / 32 + N2 / 2);
     PHN_CUDA(c, cudaFuncSetAttribute(k_wave<EXACT, LOGN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int64_t blocks = (a.f_end - a.f_begin + kWaveWarps - 1) / kWaveWarps;
+    const bool pair = !EXACT && !a.z_mean && a.preem == 0.0f;
+    const int64_t units = pair ? (a.f_end - a.f_begin + 1) / 2 : a.f_end - a.f_begin;
+    int64_t blocks = (units + kWaveWarps - 1) / kWaveWarps;
     const int64_t cap = (int64_t)c->num_sms * 6;
     if (blocks > cap) blocks = cap;
+    if (pair) {
+        PHN_CUDA(c, cudaFuncSetAttribute(k_wave_pair<LOGN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_wave_pair<LOGN><<<(unsigned)blocks, kWaveWarps * 32, smem, c->stream>>>(a);
+    } else
     k_wave<EXACT, LOGN><<<(unsigned)blocks, kWaveWarps * 32, smem, c->stream>>>(a);
     PHN_CUDA(c, cudaGetLastError());
     return PHN_OK;

@@ -123,3 +123,31 @@ def test_tc_synthetic_batch_labels_close_to_exact_mode(recs):
     finally:
         r.set_wave_format("lin16")
         r.set_mlp_mode(pb.MLP_TC_F16)
+
+
+TC_MEL_ABS = 1e-3   # fast front end (two real frames per complex fp32 FFT) vs the reference's bits; observed <= 1e-4
+
+
+@pytest.mark.parametrize("model,fmt", [("PHN_CZ_SPDAT_LCRC_N1500", "alaw"), ("PHN_EN_TIMIT_LCRC_N500", "lin16")])
+def test_tc_front_end_mel_close_to_exact_and_silence_exact(recs, model, fmt):
+    """The fused path's K-wave (fp32 FMAs, frame pairs share one complex FFT) against phn_mel (the reference's bits):
+    stated absolute bound on ln mel-bank energies; frames of digital silence must stay EXACTLY 0 (sLn's guard,
+    dspc.h:155-160), whatever frame they were paired with.  Odd frame counts and 1-frame utterances included."""
+    r = recs(model)
+    r.set_wave_format(fmt)
+    try:
+        a = r.synth_audio(80000, 3, seed=7).copy()
+        if fmt == "lin16":
+            a[0, 20000:36001] = 0                                 # digital silence (A-law has no zero code)
+            a[2, :5000] = 0
+        utts = [a[0].tobytes(), a[1].tobytes()[:30001 * (2 if fmt == "lin16" else 1)], a[2].tobytes()[:700], a[2].tobytes()]
+        exact = np.concatenate(r.mel(utts))
+        r.recognize(utts)
+        fast = r.fetch_mel(exact.shape[0])
+        assert np.isfinite(fast).all()
+        silent = (exact == 0.0).all(axis=1)
+        assert silent.any() == (fmt == "lin16")
+        assert (fast[silent] == 0.0).all()
+        assert np.abs(fast - exact).max() <= TC_MEL_ABS, np.abs(fast - exact).max()
+    finally:
+        r.set_wave_format("lin16")
