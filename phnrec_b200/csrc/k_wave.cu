@@ -263,9 +263,10 @@ __global__ void __launch_bounds__(kWaveWarps * 32) k_wave(WaveArgs a)
 // Half the butterflies per frame; the price is fp32 cross-talk between the two frames at the 1e-7 level of the
 // louder one.  An all-zero frame (digital silence) is detected on load and keeps the reference's exact answer
 // (sLn's guard: mel = 0), whatever its partner holds.  Only for the plain front end (no z_mean / pre-emphasis).
-template <int LOGN>
+template <int LOGN, bool ALAW>
 __global__ void __launch_bounds__(kWaveWarps * 32) k_wave_pair(WaveArgs a)
 {
+    __shared__ float s_lut[256];   // A-law byte -> sample, dc shift and scale applied in the reference's order (srec.cpp:768-788)
     constexpr int N = 1 << LOGN, N2 = N / 2;
     constexpr int OCT = N / 256;
     constexpr int L3 = LOGN - 6;
@@ -286,73 +287,79 @@ __global__ void __launch_bounds__(kWaveWarps * 32) k_wave_pair(WaveArgs a)
     }
     for (int i = threadIdx.x; i < N; i += blockDim.x) s_ham[i] = i < a.vs ? a.hamming[i] : 0.0f;
     for (int i = threadIdx.x; i < N2; i += blockDim.x) { s_coef[i] = a.coeffs[i]; s_bank[i] = a.banks[i]; }
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_lut[i] = __fmul_rn(__fadd_rn(__fmul_rn(8.0f, (float)alaw_d5((unsigned)i)), a.dc_shift), a.scale);
     __syncthreads();
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float2 *data = s_work + (size_t)warp * WORK;
     float *pwA = reinterpret_cast<float *>(data + N + N / 32);   // [N2] power spectrum of the first frame
     float *pwB = reinterpret_cast<float *>(data);                // [N2] second frame (aliases data[], free by then)
-    const int bps = a.fmt == PHN_WAVE_LIN16 ? 2 : 1;
+    constexpr int bps = ALAW ? 1 : 2;
     const int64_t n_pairs = (a.f_end - a.f_begin + 1) / 2;
 
     for (int64_t p = (int64_t)blockIdx.x * kWaveWarps + warp; p < n_pairs; p += (int64_t)gridDim.x * kWaveWarps) {
         const int64_t fA = a.f_begin + 2 * p, fB = fA + 1;
         const bool haveB = fB < a.f_end;
-        int64_t b0[2], len[2], s0[2];
+        // per frame: pointer to its first sample and the number of samples the window may read (0 beyond the signal)
+        const uint8_t *src[2];
+        int lim[2];
 #pragma unroll
         for (int w = 0; w < 2; ++w) {
             const int64_t f = w ? (haveB ? fB : fA) : fA;
             const int u = find_utt(a.frame_off, a.n_utt, f);
-            b0[w] = a.byte_off[u];
-            len[w] = (a.byte_off[u + 1] - b0[w]) / bps;
-            s0[w] = (f - a.frame_off[u]) * a.step;
+            const int64_t b0 = a.byte_off[u];
+            const int64_t len = (a.byte_off[u + 1] - b0) / bps;
+            const int64_t s0 = (f - a.frame_off[u]) * a.step;
+            src[w] = a.audio + b0 + bps * s0;
+            const int64_t left = len - s0;
+            lim[w] = (w && !haveB) ? 0 : (int)(left < a.vs ? (left < 0 ? 0 : left) : a.vs);
         }
-        auto sample = [&](int w, int i) -> float {  // decode (srec.cpp:742-743 / 768-769), dc shift, scale; 0 beyond the signal
-            float x = 0.0f;
-            if (i < a.vs && s0[w] + i < len[w]) {
-                if (a.fmt == PHN_WAVE_LIN16) {
-                    const uint8_t *q = a.audio + b0[w] + 2 * (s0[w] + i);
-                    x = (float)(short)((unsigned)q[0] | ((unsigned)q[1] << 8));
-                } else {
-                    x = 8.0f * (float)alaw_d5(a.audio[b0[w] + s0[w] + i]);
-                }
-                if (a.dc_shift != 0.0f) x += a.dc_shift;
-                if (a.scale != 1.0f) x *= a.scale;
-            }
-            return x;
+        const float dc = a.dc_shift, sc = a.scale;
+        auto decode = [&](const uint8_t *q) -> float {  // srec.cpp:742-743 / 768-769, dc shift, scale ((x + 0) * 1 == x)
+            if (ALAW) return s_lut[q[0]];
+            return __fmul_rn(__fadd_rn((float)(short)((unsigned)q[0] | ((unsigned)q[1] << 8)), dc), sc);
         };
 
-        // ---- pass 1 (stages h = 1, 2, 4): elements 8o .. 8o+7 = windowed inputs at bit-reversed positions
+        // ---- pass 1 (stages h = 1, 2, 4): elements 8o .. 8o+7 = windowed inputs at bit-reversed positions.
+        // brev(8o + r) = brev(o) + (brev3(r) << (LOGN - 3)): one lane-dependent base, compile-time offsets.
         float2 v[OCT][8];
         bool nzA = false, nzB = false;
 #pragma unroll
         for (int oc = 0; oc < OCT; ++oc) {
             const int o = lane + 32 * oc;
+            const int ib = (int)(__brev((unsigned)o) >> (32 - (LOGN - 3)));
+            const uint8_t *qa = src[0] + bps * ib, *qb = src[1] + bps * ib;
+            const float *hm = s_ham + ib;
 #pragma unroll
             for (int r = 0; r < 8; ++r) {
-                const int i = (int)(__brev((unsigned)(8 * o + r)) >> (32 - LOGN));
-                const float xa = sample(0, i), xb = haveB ? sample(1, i) : 0.0f;
+                constexpr int dummy = 0; (void)dummy;
+                const int off = (((r & 1) << 2) | (r & 2) | ((r >> 2) & 1)) << (LOGN - 3);   // brev3(r) << (LOGN-3)
+                const float xa = ib + off < lim[0] ? decode(qa + bps * off) : 0.0f;
+                const float xb = ib + off < lim[1] ? decode(qb + bps * off) : 0.0f;
                 nzA |= xa != 0.0f; nzB |= xb != 0.0f;
-                const float hm = s_ham[i];
-                v[oc][r] = make_float2(xa * hm, xb * hm);
+                v[oc][r] = make_float2(xa * hm[off], xb * hm[off]);
             }
         }
         const bool liveA = __any_sync(0xffffffffu, nzA), liveB = __any_sync(0xffffffffu, nzB);
+        // padded index of element e is e + (e >> 5); for the three access patterns the pad term is a lane-dependent
+        // base plus a compile-time offset
 #pragma unroll
         for (int oc = 0; oc < OCT; ++oc) {
             const int o = lane + 32 * oc;
             fft_pass<false, 3, TW>(v[oc], s_tw, 1, 0);
+            float2 *d1 = data + 8 * o + (o >> 2);                      // (8o + r) >> 5 == o >> 2
 #pragma unroll
-            for (int r = 0; r < 8; ++r) data[pad_idx(8 * o + r)] = v[oc][r];
+            for (int r = 0; r < 8; ++r) d1[r] = v[oc][r];
         }
         __syncwarp();
-        // ---- pass 2 (h = 8, 16, 32)
+        // ---- pass 2 (h = 8, 16, 32): elements low3 + 8r + 64*high
 #pragma unroll
         for (int oc = 0; oc < OCT; ++oc) {
             const int o = lane + 32 * oc;
             const int low3 = o & 7, high = o >> 3;
+            const float2 *d2 = data + low3 + 66 * high;              // (low3 + 8r + 64 high) >> 5 == 2 high + (r >> 2)
 #pragma unroll
-            for (int r = 0; r < 8; ++r) v[oc][r] = data[pad_idx(low3 + 8 * r + 64 * high)];
+            for (int r = 0; r < 8; ++r) v[oc][r] = d2[8 * r + (r >> 2)];
         }
         __syncwarp();
 #pragma unroll
@@ -360,25 +367,27 @@ __global__ void __launch_bounds__(kWaveWarps * 32) k_wave_pair(WaveArgs a)
             const int o = lane + 32 * oc;
             const int low3 = o & 7, high = o >> 3;
             fft_pass<false, 3, TW>(v[oc], s_tw, 8, low3);
+            float2 *d2 = data + low3 + 66 * high;
 #pragma unroll
-            for (int r = 0; r < 8; ++r) data[pad_idx(low3 + 8 * r + 64 * high)] = v[oc][r];
+            for (int r = 0; r < 8; ++r) d2[8 * r + (r >> 2)] = v[oc][r];
         }
         __syncwarp();
         // ---- pass 3 (h = 64 .. N/2): elements low6 + 64r, two groups per lane; all N bins are needed now
         float2 w3[2][R3];
 #pragma unroll
         for (int gq = 0; gq < 2; ++gq) {
-            const int low6 = lane + 32 * gq;
+            const float2 *d3 = data + lane + 33 * gq;                  // (low6 + 64 r) >> 5 == 2 r + gq
 #pragma unroll
-            for (int r = 0; r < R3; ++r) w3[gq][r] = data[pad_idx(low6 + 64 * r)];
+            for (int r = 0; r < R3; ++r) w3[gq][r] = d3[66 * r];
         }
         __syncwarp();
 #pragma unroll
         for (int gq = 0; gq < 2; ++gq) {
             const int low6 = lane + 32 * gq;
             fft_pass<false, L3, TW>(w3[gq], s_tw, 64, low6);
+            float2 *d3 = data + lane + 33 * gq;
 #pragma unroll
-            for (int r = 0; r < R3; ++r) data[pad_idx(low6 + 64 * r)] = w3[gq][r];
+            for (int r = 0; r < R3; ++r) d3[66 * r] = w3[gq][r];
         }
         __syncwarp();
         // ---- separate the two spectra: bin k = low6 + 64r (r < R3/2) pairs with bin N - k
@@ -446,9 +455,12 @@ static int launch_wave_t(phn_ctx *c, const WaveArgs &a)
     int64_t blocks = (units + kWaveWarps - 1) / kWaveWarps;
     const int64_t cap = (int64_t)c->num_sms * 6;
     if (blocks > cap) blocks = cap;
-    if (pair) {
-        PHN_CUDA(c, cudaFuncSetAttribute(k_wave_pair<LOGN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_wave_pair<LOGN><<<(unsigned)blocks, kWaveWarps * 32, smem, c->stream>>>(a);
+    if (pair && a.fmt == PHN_WAVE_ALAW) {
+        PHN_CUDA(c, cudaFuncSetAttribute(k_wave_pair<LOGN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_wave_pair<LOGN, true><<<(unsigned)blocks, kWaveWarps * 32, smem, c->stream>>>(a);
+    } else if (pair) {
+        PHN_CUDA(c, cudaFuncSetAttribute(k_wave_pair<LOGN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_wave_pair<LOGN, false><<<(unsigned)blocks, kWaveWarps * 32, smem, c->stream>>>(a);
     } else
     k_wave<EXACT, LOGN><<<(unsigned)blocks, kWaveWarps * 32, smem, c->stream>>>(a);
     PHN_CUDA(c, cudaGetLastError());
