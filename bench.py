@@ -110,6 +110,18 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(self.rows)}
 
 
+def measured_traffic(frames):
+    """DRAM bytes of the MLP launches of one step from the committed ncu --set full capture (same workload), or None."""
+    p = ROOT / "profiles" / "r1_mlp_traffic.json"
+    try:
+        j = json.loads(p.read_text())
+        if int(j.get("frames", -1)) == int(frames):
+            return int(j["k_mlp_per_step"])
+    except Exception:
+        pass
+    return None
+
+
 def measured_peaks():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -355,7 +367,9 @@ def main():
             "gpu_launches": int(launches_per_step * args.steps),
             "clocks": clocks,
             "roofline": {"bound": "tensor", "kernel": "K-mlp (3 MLPs per frame)", "achieved": achieved_tflops, "peak": peaks["tflops"],
-                         "unit": "TFLOP/s", "frac": achieved_tflops / peaks["tflops"], "traffic": None,
+                         "unit": "TFLOP/s", "frac": achieved_tflops / peaks["tflops"], "traffic": measured_traffic(frames) if mode == "tc" else None,
+                         "traffic_note": "DRAM bytes of the 3 MLP launches of one step (ncu --set full, profiles/r1_mlp_traffic.json); "
+                                         "the bound is the tensor pipe, HBM traffic is ~10 % of peak",
                          "algorithmic": f"{FLOP_PER_FRAME} FLOP/frame x {frames} frames", "peak_source": peaks["source"],
                          "kernel_ms_per_step": mlp_ms, "launches_per_step": fam["mlp"][1]},
             "kernel_ms": {k: round(v[0], 4) for k, v in fam.items()},
