@@ -166,6 +166,59 @@ __device__ __forceinline__ void umma_ts_lo(uint32_t tmem_d, uint32_t tmem_a, uin
         "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n\t}"
         ::"r"(tmem_d), "r"(tmem_a), "r"(blo), "r"(kDescHi), "r"(idesc), "n"(ACC) : "memory");
 }
+// ---- CTA-pair forms (cta_group::2, M = 256: 128 rows per CTA, every B tile split across the two CTAs)
+template <int ACC>
+__device__ __forceinline__ void umma2_ss_lo(uint32_t tmem_d, uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t idesc)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %6, 0;\n\t"
+        "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, p;\n\t}"
+        ::"r"(tmem_d), "r"(alo), "r"(ahi), "r"(blo), "r"(kDescHi), "r"(idesc), "n"(ACC) : "memory");
+}
+__device__ __forceinline__ void umma2_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+template <int ACC>
+__device__ __forceinline__ void umma2_ts_lo(uint32_t tmem_d, uint32_t tmem_a, uint32_t blo, uint32_t idesc)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 db;\n\tsetp.ne.b32 p, %5, 0;\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], db, %4, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "r"(blo), "r"(kDescHi), "r"(idesc), "n"(ACC) : "memory");
+}
+// completion of this thread's MMAs -> the mbarrier at the same shared-memory offset in BOTH CTAs of the pair
+__device__ __forceinline__ void tc_commit2_u(uint32_t bar_saddr)
+{
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar_saddr), "h"((uint16_t)3) : "memory");
+}
+// arrive on the mbarrier at this shared-memory offset in CTA `cta` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t *bar, uint32_t cta)
+{
+    asm volatile("{\n\t.reg .b32 ra;\n\tmapa.shared::cluster.u32 ra, %0, %1;\n\t"
+                 "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}" ::"r"(smem_u32(bar)), "r"(cta) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t *bar, uint32_t parity)   // (a barrier other CTAs arrive on; same wait as CUTLASS' ClusterBarrier)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "W_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra D_%=;\n\t"
+        "bra W_%=;\n\t"
+        "D_%=:\n\t}"
+        ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 // K-major, SWIZZLE_128B shared-memory matrix descriptor: start address, LBO (unused for swizzled
 // K-major) = 1, SBO = 1024 B between 8-row groups, descriptor version 1 (sm_100), layout type 2.
 __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t saddr)
@@ -190,9 +243,9 @@ __device__ __forceinline__ uint64_t make_mn128_desc(uint32_t saddr)
     return d;
 }
 // instruction descriptor: fp16 x fp16 -> fp32, B K-major, A K-major or M-major (bit 15), M = 128, N = n
-__host__ __device__ constexpr uint32_t make_idesc(int n, bool a_mn = false)
+__host__ __device__ constexpr uint32_t make_idesc(int n, bool a_mn = false, int m = TC_M)
 {
-    return (1u << 4) | (0u << 7) | (0u << 10) | ((a_mn ? 1u : 0u) << 15) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+    return (1u << 4) | (0u << 7) | (0u << 10) | ((a_mn ? 1u : 0u) << 15) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 #define PHN_TMEM_LD(NAME, SHAPE, N, OUTS, ...)                                                        \
     __device__ __forceinline__ void NAME(uint32_t taddr, uint32_t *v)                                  \
@@ -287,14 +340,15 @@ struct TcArgs {
 // debug timeline: dbg[(c * 16 + event)] = clock64() for chunk c of CTA 0's second tile
 #define TC_DBG(ev, c)                                                                       \
     do {                                                                                    \
-        if (a.dbg && blockIdx.x == 0 && tile == (int)gridDim.x) a.dbg[(c) * 16 + (ev)] = clock64(); \
+        if (a.dbg && blockIdx.x == 0 && tile == tile0 + tstep) a.dbg[(c) * 16 + (ev)] = clock64(); \
     } while (0)
 // E2 stage events of that tile go to row 15: 0 A begins (waits for D2), 1 D2 seen, 2 A done, 3 B begins, 4 B done, 5 C begins, 6 C done
 #define TC_DBG2(ev)                                                                                                   \
     do {                                                                                                              \
-        if (a.dbg && blockIdx.x == 0 && threadIdx.x == 0 && e2_tile == (int)gridDim.x) a.dbg[15 * 16 + (ev)] = clock64(); \
+        if (a.dbg && blockIdx.x == 0 && threadIdx.x == 0 && e2_tile == tile0 + tstep) a.dbg[15 * 16 + (ev)] = clock64(); \
     } while (0)
-constexpr int TC_MAXS1 = 12;                        // upper bound on W1 ring stages (barrier array size)
+constexpr int TC_MAXS1 = 24;                        // upper bound on W1 ring stages (barrier array size)
+constexpr int TC_MAXS2 = 8;                         // ... W2 ring stages (4 chunks)
 constexpr int TC_EPI_WARPS = 16;                     // warps 0..15: epilogue; 16: TMA producer; 17, 18: MMA issuers (layer 1, layer 2)
 constexpr int TC_THREADS = (TC_EPI_WARPS + 3) * 32;
 // The SM's warp schedulers favour the highest warp id among eligible warps, so the two warps whose
@@ -337,10 +391,25 @@ __device__ __forceinline__ void band_out(const float (&o)[NQ], float lg2_sc, con
     }
 }
 
-template <int N2P, bool XMN>   // XMN: the activation image is M-major (the merger's), else K-major
+// XMN: the activation image is M-major (the merger's), else K-major.
+// PAIR: the kernel runs as clusters of two CTAs driving cta_group::2 MMAs (M = 256): each CTA owns one 128-frame tile
+// and keeps only HALF of every weight block in its shared memory (W1: 64 of the chunk's 128 hidden rows, W2: N2P/2
+// output rows) - half the TMA weight stream and 6 KB instead of 8 KB of shared-memory operand reads per layer-1 MMA,
+// which is what bounds the single-CTA kernel.  CTA 0 of the pair issues every MMA; its completion signals are
+// multicast to both CTAs; CTA 1's issuer warps only relay "my operands have landed" to CTA 0, and its epilogue warps
+// arrive on CTA 0's barriers.  Everything else (producer, epilogues) is per CTA and unchanged.
+template <int N2P, bool XMN, bool PAIR>
 __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs a)
 {
-    constexpr int W2_BLK = N2P * 128;       // bytes of one [N2P rows x 64 fp16] block
+    constexpr int W2_BLK = N2P * 128;       // bytes of one [N2P rows x 64 fp16] block of the weight image
+    constexpr int W1_ST = PAIR ? TC_BLK / 2 : TC_BLK;      // bytes of one W1 ring stage in this CTA's shared memory
+    constexpr int W2_ST = PAIR ? W2_BLK / 2 : W2_BLK;      // ... W2 ring stage
+    const uint32_t rank = PAIR ? (blockIdx.x & 1u) : 0u;   // CTA rank in the pair (cluster dims (2,1,1))
+    // tile sequence of this CTA: tile0, tile0 + tstep, ... (n_my of them; a pair's two CTAs run in lock step)
+    const int n_units = PAIR ? (a.n_tiles + 1) / 2 : a.n_tiles, unit0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int ustep = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    const int n_my = unit0 < n_units ? (n_units - 1 - unit0) / ustep + 1 : 0;
+    const int tile0 = PAIR ? 2 * unit0 + (int)rank : unit0, tstep = PAIR ? 2 * ustep : ustep;
     constexpr int NQ = N2P / 4;             // D2 columns per epilogue column quarter (32, 36, 40 or 48)
     constexpr int NR = NQ - 32;             // columns beyond the first 32-column TMEM load (0, 4, 8 or 16)
     static_assert(NR == 0 || NR == 4 || NR == 8 || NR == 16, "unsupported output width");
@@ -349,8 +418,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs a)
     uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t *sX = smem;                                        // KB1 x 16 KB
     uint8_t *sW1 = sX + (size_t)a.KB1 * TC_BLK;                // S1 x 16 KB ring
-    uint8_t *sW2 = sW1 + (size_t)a.S1 * TC_BLK;                // S2 x W2_BLK ring
-    float *s_b2 = reinterpret_cast<float *>(sW2 + (size_t)a.S2 * W2_BLK);   // [N2P]
+    uint8_t *sW2 = sW1 + (size_t)a.S1 * W1_ST;                 // S2 x W2_ST ring
+    float *s_b2 = reinterpret_cast<float *>(sW2 + (size_t)a.S2 * W2_ST);    // [N2P]
     float *s_mm = s_b2 + N2P;                                  // [N2P] merger input mean  (band nets)
     float *s_md = s_mm + N2P;                                  // [N2P] merger input 1/std (band nets)
     float *s_red = s_md + N2P;                                 // [2][4][128] row max / row sum exchange
@@ -359,14 +428,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs a)
     uint64_t *x_empty = bars + 8;            // [8] per k-block: the tile's last layer-1 chunk has consumed it
     uint64_t *w1_full = bars + 16;           // [TC_MAXS1]
     uint64_t *w1_empty = w1_full + TC_MAXS1; // [TC_MAXS1]
-    uint64_t *w2_empty = w1_empty + TC_MAXS1; // [4]
-    uint64_t *w1c_full = w2_empty + 4;       // [4] chunk-level: all KB1 k-blocks of layer-1 chunk n have landed (n & 3)
-    uint64_t *w2c_full = w1c_full + 4;       // [2] chunk-level: both k-blocks of layer-2 chunk n have landed (n & 1)
-    uint64_t *d1_full = w2c_full + 2;        // [2]
+    uint64_t *w2_empty = w1_empty + TC_MAXS1; // [TC_MAXS2]
+    uint64_t *w1c_full = w2_empty + TC_MAXS2;       // [4] chunk-level: all KB1 k-blocks of layer-1 chunk n have landed (n & 3)
+    uint64_t *w2c_full = w1c_full + 4;       // [4] chunk-level: both k-blocks of layer-2 chunk n have landed (n & 3)
+    uint64_t *d1_full = w2c_full + 4;        // [2]
     uint64_t *h_full = d1_full + 2, *h_empty = h_full + 1;
     uint64_t *d2_full = h_empty + 1, *d2_empty = d2_full + 1;
     uint64_t *d1_empty = d2_empty + 1;       // [2] E1 has read the accumulator buffer
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(d1_empty + 2);
+    uint64_t *pw1_full = d1_empty + 2;       // [4] PAIR, CTA 0: the peer's layer-1 operands of chunk n have landed (n & 3)
+    uint64_t *pw2_full = pw1_full + 4;       // [4] PAIR, CTA 0: the peer's layer-2 weights of chunk n have landed (n & 3)
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(pw2_full + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr int WARP_TMA = TC_EPI_WARPS, WARP_MMA1 = TC_EPI_WARPS + 1, WARP_MMA2 = TC_EPI_WARPS + 2, EPI0 = 0;
@@ -374,17 +445,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs a)
     if (threadIdx.x == 0) {
         for (int i = 0; i < 8; ++i) mbar_init(&x_full[i], 1);
         for (int i = 0; i < TC_MAXS1; ++i) { mbar_init(&w1_full[i], 1); mbar_init(&w1_empty[i], 1); }
-        for (int i = 0; i < 4; ++i) { mbar_init(&w2_empty[i], 1); mbar_init(&w1c_full[i], a.KB1); }
-        for (int i = 0; i < 2; ++i) mbar_init(&w2c_full[i], 2);
+        for (int i = 0; i < TC_MAXS2; ++i) mbar_init(&w2_empty[i], 1);
+        for (int i = 0; i < 4; ++i) { mbar_init(&w1c_full[i], a.KB1); mbar_init(&w2c_full[i], 2); }
         for (int i = 0; i < 8; ++i) mbar_init(&x_empty[i], 1);
-        for (int i = 0; i < 2; ++i) { mbar_init(&d1_full[i], 1); mbar_init(&d1_empty[i], TC_EPI_WARPS); }
-        mbar_init(h_full, TC_EPI_WARPS); mbar_init(h_empty, 1);
-        mbar_init(d2_full, 1); mbar_init(d2_empty, TC_EPI_WARPS);
+        constexpr uint32_t EPI_ARRIVALS = PAIR ? 2 * TC_EPI_WARPS : TC_EPI_WARPS;   // PAIR: both CTAs' epilogue warps arrive on CTA 0
+        for (int i = 0; i < 2; ++i) { mbar_init(&d1_full[i], 1); mbar_init(&d1_empty[i], EPI_ARRIVALS); }
+        mbar_init(h_full, EPI_ARRIVALS); mbar_init(h_empty, 1);
+        mbar_init(d2_full, 1); mbar_init(d2_empty, EPI_ARRIVALS);
+        for (int i = 0; i < 4; ++i) mbar_init(&pw1_full[i], 1);
+        for (int i = 0; i < 4; ++i) mbar_init(&pw2_full[i], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == WARP_MMA1) {  // TMEM: 512 columns = D1 double buffer 2 x 128 | D2 up to 192 | H 64 (128 fp16 per lane)
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (PAIR) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     for (int i = threadIdx.x; i < N2P; i += blockDim.x) {
         s_b2[i] = a.b2[i];
@@ -396,6 +475,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs a)
     }
     tc_fence_before();
     __syncthreads();
+    if (PAIR) cluster_sync_all();   // both CTAs' barriers are initialised before anything arrives on them remotely
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
     const uint32_t tD1[2] = {tmem, tmem + 128u};
@@ -408,7 +488,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs a)
         // issuer's consumption order over the CTA's linear chunk sequence g = tile_iter * NCH + c:
         //   X(tile 0), W1(0), W1(1), then per g:  [X(next tile) if chunk g+2 opens it]  W1(g+2)  W2(g)
         uint32_t w1_stage = 0, ph_w1 = 0, w2_stage = 0, ph_w2 = 0;
-        const int my_tiles = blockIdx.x < a.n_tiles ? (a.n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+        const int my_tiles = n_my;
         const int G = my_tiles * a.NCH;
         // Normal case (the W1 ring holds a whole chunk): every k-block load of a chunk reports to the chunk's own
         // "full" barrier, so the issuer waits once per chunk; ring stages are still handed back one by one.
@@ -420,25 +500,29 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs a)
         uint32_t n1 = 0, n2 = 0;          // chunks fully issued per stream
         int kb1 = 0, kb2 = 0;             // next k-block inside the current chunk
         int c1 = 0, c2 = 0;
-        int xt = 0, xk = 0, xtile = blockIdx.x;   // X cursor: tile iteration, k-block, global tile
+        int xt = 0, xk = 0, xtile = tile0;   // X cursor: tile iteration, k-block, global tile
         while (n1 < (uint32_t)G || n2 < (uint32_t)G || xt < my_tiles) {
             if (xt < my_tiles && (xt == 0 || mbar_try(&x_empty[xk], (uint32_t)(xt - 1) & 1u))) {
                 if (elect_one()) {
+                    // (PAIR: the odd CTA of the last pair may own a tile past the end; it multiplies the last real tile again
+                    // and writes nothing)
+                    const int xsrc = xtile < a.n_tiles ? xtile : a.n_tiles - 1;
                     mbar_expect_tx(&x_full[xk], TC_BLK);
-                    tma_load_1d(sX + (size_t)xk * TC_BLK, a.x_img + ((size_t)xtile * a.KB1 + xk) * TC_BLK, TC_BLK, &x_full[xk]);
+                    tma_load_1d(sX + (size_t)xk * TC_BLK, a.x_img + ((size_t)xsrc * a.KB1 + xk) * TC_BLK, TC_BLK, &x_full[xk]);
                     // the CTA's next tile goes to L2 now: when its turn comes (one tile time from here) the
                     // load that sits between two tiles' MMAs is an L2 hit
-                    if (xk == 0 && xtile + (int)gridDim.x < a.n_tiles)
-                        l2_prefetch(a.x_img + (size_t)(xtile + gridDim.x) * a.KB1 * TC_BLK, (uint32_t)a.KB1 * TC_BLK);
+                    if (xk == 0 && xtile + tstep < a.n_tiles)
+                        l2_prefetch(a.x_img + (size_t)(xtile + tstep) * a.KB1 * TC_BLK, (uint32_t)a.KB1 * TC_BLK);
                 }
                 __syncwarp();
-                if (++xk == a.KB1) { xk = 0; ++xt; xtile += gridDim.x; }
+                if (++xk == a.KB1) { xk = 0; ++xt; xtile += tstep; }
             }
             if (n1 < (uint32_t)G && mbar_try(&w1_empty[w1_stage], ph_w1 ^ 1)) {
                 if (elect_one()) {
                     uint64_t *fb = chunk_bar ? &w1c_full[n1 & 3] : &w1_full[w1_stage];
-                    mbar_expect_tx(fb, TC_BLK);
-                    tma_load_1d(sW1 + (size_t)w1_stage * TC_BLK, a.w1_img + ((size_t)c1 * a.KB1 + kb1) * TC_BLK, TC_BLK, fb);
+                    // (PAIR: this CTA's half of the block = 64 of the chunk's 128 hidden rows, contiguous in the K-major image)
+                    mbar_expect_tx(fb, W1_ST);
+                    tma_load_1d(sW1 + (size_t)w1_stage * W1_ST, a.w1_img + ((size_t)c1 * a.KB1 + kb1) * TC_BLK + (size_t)rank * W1_ST, W1_ST, fb);
                 }
                 __syncwarp();
                 if (++w1_stage == (uint32_t)a.S1) { w1_stage = 0; ph_w1 ^= 1; }
@@ -449,8 +533,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs a)
             }
             if (n2 < (uint32_t)G && mbar_try(&w2_empty[w2_stage], ph_w2 ^ 1)) {
                 if (elect_one()) {
-                    mbar_expect_tx(&w2c_full[n2 & 1], W2_BLK);
-                    tma_load_1d(sW2 + (size_t)w2_stage * W2_BLK, a.w2_img + ((size_t)c2 * 2 + kb2) * W2_BLK, W2_BLK, &w2c_full[n2 & 1]);
+                    mbar_expect_tx(&w2c_full[n2 & 3], W2_ST);
+                    tma_load_1d(sW2 + (size_t)w2_stage * W2_ST, a.w2_img + ((size_t)c2 * 2 + kb2) * W2_BLK + (size_t)rank * W2_ST, W2_ST, &w2c_full[n2 & 3]);
                 }
                 __syncwarp();
                 if (++w2_stage == (uint32_t)a.S2) { w2_stage = 0; ph_w2 ^= 1; }
@@ -469,25 +553,41 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs a)
         // their own barriers.  The tensor pipe interleaves them (SS operand fetch overlaps the TS math).
         // This warp: for every chunk g of the CTA's linear sequence, D1[g & 1] = X . W1[c]^T (K1/16 SS MMAs), as
         // soon as the weights have landed and E1(g - 2) has read the accumulator buffer.
-        constexpr uint32_t idesc1 = make_idesc(TC_NC, XMN);
+        constexpr uint32_t idesc1 = make_idesc(TC_NC, XMN, PAIR ? 2 * TC_M : TC_M);
         constexpr uint32_t akst = XMN ? (4096u >> 4) : 2u;     // A descriptor advance per k-step of 16 columns
         const uint64_t dX = XMN ? make_mn128_desc(smem_u32(sX)) : make_sw128_desc(smem_u32(sX));
         const uint64_t dW1 = make_sw128_desc(smem_u32(sW1));
         const uint32_t xlo = (uint32_t)dX, xhi = (uint32_t)(dX >> 32), w1lo = (uint32_t)dW1;
         const uint32_t bar_w1e = smem_u32(w1_empty), bar_xe = smem_u32(x_empty), bar_d1f = smem_u32(d1_full);
-        const int my_tiles = blockIdx.x < a.n_tiles ? (a.n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+        const int my_tiles = n_my;
         const int G = my_tiles * a.NCH;
-        const bool chunk_bar = a.S1 >= a.KB1;   // the W1 ring holds a whole chunk: one "full" barrier per chunk
+        const bool chunk_bar = a.S1 >= a.KB1;   // the W1 ring holds a whole chunk: one "full" barrier per chunk (PAIR: always)
         uint32_t st = 0, ph_w1 = 0, ph_x_full = 0;
-        int c1 = 0, tile = blockIdx.x;          // (tile: only for the debug timeline)
+        int c1 = 0, tile = tile0;               // (tile: only for the debug timeline)
         const bool leader = elect_one();
+        if (PAIR && rank != 0) {
+            // CTA 1 of a pair issues nothing: this warp tells CTA 0 when the layer-1 operands of chunk g (its half of the
+            // W1 chunk, and its X tile when the chunk opens one) have landed in THIS CTA's shared memory
+#pragma unroll 1
+            for (int g = 0; g < G; ++g) {
+                mbar_wait(&w1c_full[g & 3], (uint32_t)(g >> 2) & 1u);
+                if (c1 == 0) {
+                    for (int k = 0; k < a.KB1; ++k) mbar_wait(&x_full[k], ph_x_full);
+                    ph_x_full ^= 1;
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(&pw1_full[g & 3], 0);
+                if (++c1 == a.NCH) c1 = 0;
+            }
+        } else
 #pragma unroll 1
         for (int g = 0; g < G; ++g) {
             const bool opens = c1 == 0, closes = c1 == a.NCH - 1;
             const uint32_t td1 = (g & 1) ? tmem + 128u : tmem;
             if (lane == 0) TC_DBG(2, c1);   // layer 1 of chunk c1: begins
-            if (g >= 2) mbar_wait(&d1_empty[g & 1], (uint32_t)((g >> 1) - 1) & 1u);
+            if (g >= 2) { if (PAIR) mbar_wait_cluster(&d1_empty[g & 1], (uint32_t)((g >> 1) - 1) & 1u); else mbar_wait(&d1_empty[g & 1], (uint32_t)((g >> 1) - 1) & 1u); }
             if (chunk_bar) mbar_wait(&w1c_full[g & 3], (uint32_t)(g >> 2) & 1u);
+            if (PAIR) mbar_wait_cluster(&pw1_full[g & 3], (uint32_t)(g >> 2) & 1u);
             if (lane == 0) TC_DBG(3, c1);   // accumulator + weights there
             tc_fence_after();
             uint32_t alo = xlo;
@@ -496,74 +596,106 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs a)
                 if (!chunk_bar) mbar_wait(&w1_full[st], ph_w1);
                 if (opens) mbar_wait(&x_full[k], ph_x_full);
                 if (!chunk_bar || opens) tc_fence_after();
-                const uint32_t blo = w1lo + st * (TC_BLK >> 4);
+                const uint32_t blo = w1lo + st * (W1_ST >> 4);
                 const uint32_t bw1 = bar_w1e + st * 8u, bxe = bar_xe + (uint32_t)k * 8u;
                 if (leader) {
-                    if (k == 0) umma_ss_lo<0>(td1, alo, xhi, blo, idesc1); else umma_ss_lo<1>(td1, alo, xhi, blo, idesc1);
-                    if (k < a.KB1 - 1 || a.nks_last == 4) {
-                        umma_ss_lo<1>(td1, alo + akst, xhi, blo + 2, idesc1);
-                        umma_ss_lo<1>(td1, alo + 2 * akst, xhi, blo + 4, idesc1);
-                        umma_ss_lo<1>(td1, alo + 3 * akst, xhi, blo + 6, idesc1);
+                    if (PAIR) {
+                        if (k == 0) umma2_ss_lo<0>(td1, alo, xhi, blo, idesc1); else umma2_ss_lo<1>(td1, alo, xhi, blo, idesc1);
+                        if (k < a.KB1 - 1 || a.nks_last == 4) {
+                            umma2_ss_lo<1>(td1, alo + akst, xhi, blo + 2, idesc1);
+                            umma2_ss_lo<1>(td1, alo + 2 * akst, xhi, blo + 4, idesc1);
+                            umma2_ss_lo<1>(td1, alo + 3 * akst, xhi, blo + 6, idesc1);
+                        } else {
+                            if (a.nks_last > 1) umma2_ss_lo<1>(td1, alo + akst, xhi, blo + 2, idesc1);
+                            if (a.nks_last > 2) umma2_ss_lo<1>(td1, alo + 2 * akst, xhi, blo + 4, idesc1);
+                        }
+                        tc_commit2_u(bw1);
+                        if (closes) tc_commit2_u(bxe);
                     } else {
-                        if (a.nks_last > 1) umma_ss_lo<1>(td1, alo + akst, xhi, blo + 2, idesc1);
-                        if (a.nks_last > 2) umma_ss_lo<1>(td1, alo + 2 * akst, xhi, blo + 4, idesc1);
+                        if (k == 0) umma_ss_lo<0>(td1, alo, xhi, blo, idesc1); else umma_ss_lo<1>(td1, alo, xhi, blo, idesc1);
+                        if (k < a.KB1 - 1 || a.nks_last == 4) {
+                            umma_ss_lo<1>(td1, alo + akst, xhi, blo + 2, idesc1);
+                            umma_ss_lo<1>(td1, alo + 2 * akst, xhi, blo + 4, idesc1);
+                            umma_ss_lo<1>(td1, alo + 3 * akst, xhi, blo + 6, idesc1);
+                        } else {
+                            if (a.nks_last > 1) umma_ss_lo<1>(td1, alo + akst, xhi, blo + 2, idesc1);
+                            if (a.nks_last > 2) umma_ss_lo<1>(td1, alo + 2 * akst, xhi, blo + 4, idesc1);
+                        }
+                        tc_commit_u(bw1);
+                        if (closes) tc_commit_u(bxe);
                     }
-                    tc_commit_u(bw1);
-                    if (closes) tc_commit_u(bxe);
                 }
                 __syncwarp();
                 if (++st == (uint32_t)a.S1) { st = 0; ph_w1 ^= 1; }
                 alo += TC_BLK >> 4;
             }
-            if (leader) tc_commit_u(bar_d1f + (uint32_t)(g & 1) * 8u);
+            if (leader) { if (PAIR) tc_commit2_u(bar_d1f + (uint32_t)(g & 1) * 8u); else tc_commit_u(bar_d1f + (uint32_t)(g & 1) * 8u); }
             __syncwarp();
             if (lane == 0) TC_DBG(4, c1);   // issued
             if (opens) ph_x_full ^= 1;
-            if (++c1 == a.NCH) { c1 = 0; tile += gridDim.x; }
+            if (++c1 == a.NCH) { c1 = 0; tile += tstep; }
         }
     } else if (warp == WARP_MMA2) {
         // ===================================================================== MMA issuer, layer 2
         // D2 (+)= H(g) . W2[:, c]^T: 8 TS MMAs per chunk (A = H from TMEM, 8 columns per k-step), as soon as E1(g) has
         // published H and the chunk's two W2 k-blocks have landed; H goes back to the epilogue warps right behind them.
-        constexpr uint32_t idesc2 = make_idesc(N2P);
+        constexpr uint32_t idesc2 = make_idesc(N2P, false, PAIR ? 2 * TC_M : TC_M);
         const uint32_t w2lo = (uint32_t)make_sw128_desc(smem_u32(sW2));
         const uint32_t bar_w2e = smem_u32(w2_empty), bar_he = smem_u32(h_empty), bar_d2f = smem_u32(d2_full);
-        const int my_tiles = blockIdx.x < a.n_tiles ? (a.n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+        const int my_tiles = n_my;
         const int G = my_tiles * a.NCH;
         uint32_t w2s = 0, ph_d2_empty = 0;
-        int c2 = 0, tile = blockIdx.x;
+        int c2 = 0, tile = tile0;
         const bool leader = elect_one();
+        if (PAIR && rank != 0) {
+            // CTA 1 of a pair: relay "my half of the chunk's W2 blocks has landed" to CTA 0
+#pragma unroll 1
+            for (int g = 0; g < G; ++g) {
+                mbar_wait(&w2c_full[g & 3], (uint32_t)(g >> 2) & 1u);
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(&pw2_full[g & 3], 0);
+            }
+        } else
 #pragma unroll 1
         for (int g = 0; g < G; ++g) {
             if (lane == 0) TC_DBG(5, c2);   // layer 2 of chunk c2: begins
-            mbar_wait(&w2c_full[g & 1], (uint32_t)(g >> 1) & 1u);
-            if (c2 == 0 && g > 0) { mbar_wait(d2_empty, ph_d2_empty); ph_d2_empty ^= 1; }
-            mbar_wait(h_full, (uint32_t)g & 1u);
+            mbar_wait(&w2c_full[g & 3], (uint32_t)(g >> 2) & 1u);
+            if (PAIR) mbar_wait_cluster(&pw2_full[g & 3], (uint32_t)(g >> 2) & 1u);
+            if (c2 == 0 && g > 0) { if (PAIR) mbar_wait_cluster(d2_empty, ph_d2_empty); else mbar_wait(d2_empty, ph_d2_empty); ph_d2_empty ^= 1; }
+            if (PAIR) mbar_wait_cluster(h_full, (uint32_t)g & 1u); else mbar_wait(h_full, (uint32_t)g & 1u);
             if (lane == 0) TC_DBG(6, c2);   // H + weights there
             tc_fence_after();
 #pragma unroll 1
             for (int k = 0; k < 2; ++k) {
-                const uint32_t b2lo = w2lo + w2s * (W2_BLK >> 4);
+                const uint32_t b2lo = w2lo + w2s * (W2_ST >> 4);
                 const uint32_t ta = tH + (uint32_t)k * 32u;
                 const uint32_t bw2 = bar_w2e + w2s * 8u;
                 const uint32_t acc0 = (k | c2) ? 1u : 0u;
                 if (leader) {
-                    umma_f16_ts(tD2, ta, ((uint64_t)kDescHi << 32) | b2lo, idesc2, acc0);
-                    umma_ts_lo<1>(tD2, ta + 8u, b2lo + 2, idesc2);
-                    umma_ts_lo<1>(tD2, ta + 16u, b2lo + 4, idesc2);
-                    umma_ts_lo<1>(tD2, ta + 24u, b2lo + 6, idesc2);
-                    tc_commit_u(bw2);
+                    if (PAIR) {
+                        umma2_f16_ts(tD2, ta, ((uint64_t)kDescHi << 32) | b2lo, idesc2, acc0);
+                        umma2_ts_lo<1>(tD2, ta + 8u, b2lo + 2, idesc2);
+                        umma2_ts_lo<1>(tD2, ta + 16u, b2lo + 4, idesc2);
+                        umma2_ts_lo<1>(tD2, ta + 24u, b2lo + 6, idesc2);
+                        tc_commit2_u(bw2);
+                    } else {
+                        umma_f16_ts(tD2, ta, ((uint64_t)kDescHi << 32) | b2lo, idesc2, acc0);
+                        umma_ts_lo<1>(tD2, ta + 8u, b2lo + 2, idesc2);
+                        umma_ts_lo<1>(tD2, ta + 16u, b2lo + 4, idesc2);
+                        umma_ts_lo<1>(tD2, ta + 24u, b2lo + 6, idesc2);
+                        tc_commit_u(bw2);
+                    }
                 }
                 __syncwarp();
                 if (++w2s == (uint32_t)a.S2) w2s = 0;
             }
             if (leader) {
-                tc_commit_u(bar_he);
-                if (c2 == a.NCH - 1) tc_commit_u(bar_d2f);
+                if (PAIR) { tc_commit2_u(bar_he); if (c2 == a.NCH - 1) tc_commit2_u(bar_d2f); }
+                else      { tc_commit_u(bar_he);  if (c2 == a.NCH - 1) tc_commit_u(bar_d2f); }
             }
             __syncwarp();
             if (lane == 0) TC_DBG(7, c2);   // issued
-            if (++c2 == a.NCH) { c2 = 0; tile += gridDim.x; }
+            if (++c2 == a.NCH) { c2 = 0; tile += tstep; }
         }
     } else {
         // ===================================================================== epilogue warps
@@ -580,13 +712,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs a)
         // u = sat(t / TMAX), t = -(x + b1)/ln2 + Ct; b1 is already inside x (two extra K columns of layer 1)
         const float sigA = (float)(-1.0 / (kLn2 * (double)kSigTmax)), sigB = (float)(kCt / (double)kSigTmax);
         const float smxA = (float)(1.0 / (kLn2 * (double)kSmxTmax)), smxB = (float)(kCt / (double)kSmxTmax);
-        const int my_tiles = blockIdx.x < a.n_tiles ? (a.n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+        const int my_tiles = n_my;
         const int G = my_tiles * a.NCH;
+        // the consumers of these three signals are the issuer warps: this CTA's, or (PAIR) CTA 0's for both CTAs
+        auto signal = [&](uint64_t *bar) { if (PAIR) mbar_arrive_cluster(bar, 0); else mbar_arrive(bar); };
         const int n0 = cq * NQ;                  // column quarter cq owns D2 columns [cq*NQ, (cq+1)*NQ)
         float o[NQ];
         float mx = 0.0f;
         int e2_stage = 3, e2_tile = 0;           // 3: no soft-max pending; 0..2: next stage of tile e2_tile
-        int c = 0, tile = blockIdx.x;
+        int c = 0, tile = tile0;
         for (int g = 0; g <= G; ++g) {           // g == G: drain iteration (no E1)
             const bool drain = g == G;
             if (!drain) {
@@ -616,7 +750,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs a)
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&d1_empty[b]);      // (the layer-1 issuer may overwrite this accumulator buffer)
+                if (lane == 0) signal(&d1_empty[b]);      // (the layer-1 issuer may overwrite this accumulator buffer)
                 if (threadIdx.x == EPI0 * 32) TC_DBG(10, c);   // e1: math done
                 if (!first_h) { mbar_wait(h_empty, ph_h_empty); ph_h_empty ^= 1; }
                 first_h = false;
@@ -626,7 +760,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs a)
                 tmem_st_wait();
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(h_full);
+                if (lane == 0) signal(h_full);
                 if (threadIdx.x == EPI0 * 32) TC_DBG(12, c);   // e1: H published
             }
             // ------------------------------------------------------------- E2 stages: soft-max + outputs of tile e2_tile
@@ -647,7 +781,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs a)
                     tmem_ld_wait();
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(d2_empty);
+                    if (lane == 0) signal(d2_empty);
 #pragma unroll
                     for (int j = 0; j < NQ / 4; ++j) {
                         const float4 b4 = *reinterpret_cast<const float4 *>(s_b2 + n0 + 4 * j);   // -FLT_MAX in padding columns
@@ -717,16 +851,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs a)
             if (!drain && ++c == a.NCH) {        // the tile's last H is on its way: its soft-max becomes pending
                 c = 0;
                 e2_stage = 0; e2_tile = tile;
-                tile += gridDim.x;
+                tile += tstep;
             }
         }
     }
 
     tc_fence_before();
     __syncthreads();
+    if (PAIR) cluster_sync_all();   // the peer is done with this CTA's barriers, shared memory and tensor memory
     if (warp == WARP_MMA1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+        if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
     }
 }
 
@@ -868,16 +1004,27 @@ void mlp_tc_release(phn_ctx *c)
     c->tc = nullptr;
 }
 
-template <int N2P>
-static int launch_one(phn_ctx *c, const TcArgs &a, size_t smem_bytes, int grid)
+template <int N2P, bool XMN, bool PAIR>
+static int launch_inst(phn_ctx *c, const TcArgs &a, size_t smem_bytes, int grid)
 {
-    if (a.x_mn) {
-        PHN_CUDA(c, cudaFuncSetAttribute(k_mlp_tc<N2P, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
-        k_mlp_tc<N2P, true><<<grid, TC_THREADS, smem_bytes, c->stream>>>(a);
-    } else {
-        PHN_CUDA(c, cudaFuncSetAttribute(k_mlp_tc<N2P, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
-        k_mlp_tc<N2P, false><<<grid, TC_THREADS, smem_bytes, c->stream>>>(a);
-    }
+    PHN_CUDA(c, cudaFuncSetAttribute(k_mlp_tc<N2P, XMN, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = smem_bytes; cfg.stream = c->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = PAIR ? 2 : 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    PHN_CUDA(c, cudaLaunchKernelEx(&cfg, k_mlp_tc<N2P, XMN, PAIR>, a));
+    return PHN_OK;
+}
+
+template <int N2P>
+static int launch_one(phn_ctx *c, const TcArgs &a, size_t smem_bytes, int grid, bool pair)
+{
+    int rc;
+    if (pair) rc = a.x_mn ? launch_inst<N2P, true, true>(c, a, smem_bytes, grid) : launch_inst<N2P, false, true>(c, a, smem_bytes, grid);
+    else      rc = a.x_mn ? launch_inst<N2P, true, false>(c, a, smem_bytes, grid) : launch_inst<N2P, false, false>(c, a, smem_bytes, grid);
+    if (rc) return rc;
     PHN_CUDA(c, cudaGetLastError());
     return PHN_OK;
 }
@@ -906,32 +1053,47 @@ static int run_net_tc(phn_ctx *c, int which, const uint8_t *x_img, int64_t nf, i
     }
     // shared memory plan: X (KB1 blocks) + H (2 blocks) + constants + barriers are fixed; the rest is split
     // between the W2 ring (S2 k-blocks of N2P x 64) and the W1 ring (S1 blocks of 128 x 64)
-    const size_t w2_blk = (size_t)im.N2P * 128;
-    const size_t fixed = (size_t)im.KB1 * TC_BLK + sizeof(float) * (3 * (size_t)im.N2P + 8 * 128) + 64 * 8 + 1024;
+    // CTA pairs (cta_group::2): each CTA keeps half of every weight block.  PHNREC_TC_PAIR=0 selects the single-CTA kernel.
+    bool pair = a.n_tiles >= 2;
+    if (const char *e = getenv("PHNREC_TC_PAIR")) pair = pair && atoi(e) != 0;
+    const size_t w1_blk = pair ? TC_BLK / 2 : TC_BLK;
+    const size_t w2_blk = (size_t)im.N2P * 128 / (pair ? 2 : 1);
+    const size_t fixed = (size_t)im.KB1 * TC_BLK + sizeof(float) * (3 * (size_t)im.N2P + 8 * 128) + 112 * 8 + 1024;
     const size_t max_smem = 232448;
     // Ring plan.  Both weight streams want two chunks resident (the one being multiplied and the one in flight):
     // W2 ring 4 stages, W1 ring 2 KB1 stages.  When that does not fit (wide merger next to its wide X tile), W2
     // falls back to 3 and then 2 stages and W1 takes whatever is left (at least 2 stages; the issuer then walks a
     // chunk in groups, see k_mlp_tc).
-    int S2 = 4;
-    if (fixed + S2 * w2_blk + 2 * (size_t)im.KB1 * TC_BLK > max_smem) S2 = 3;
-    if (fixed + S2 * w2_blk + (size_t)(im.KB1 + 1) * TC_BLK > max_smem) S2 = 2;
-    if (fixed + S2 * w2_blk + 2 * (size_t)TC_BLK > max_smem) return fail(c, PHN_ERR_UNSUPPORTED, "tensor-core mode: shared memory plan does not fit\n");
-    int S1 = (int)((max_smem - fixed - S2 * w2_blk) / TC_BLK);
+    // Pairs have the room for deeper rings: a weight block arrives ~3000 clk after its request when every SM streams
+    // the whole net out of L2, more than one chunk time - so up to four chunks are kept in flight.
+    int S2 = pair ? TC_MAXS2 : 4;
+    if (pair && fixed + S2 * w2_blk + 3 * (size_t)im.KB1 * w1_blk > max_smem) S2 = 6;
+    if (pair && fixed + S2 * w2_blk + 2 * (size_t)im.KB1 * w1_blk > max_smem) S2 = 4;
+    if (fixed + S2 * w2_blk + 2 * (size_t)im.KB1 * w1_blk > max_smem) S2 = 3;
+    if (fixed + S2 * w2_blk + (size_t)(im.KB1 + 1) * w1_blk > max_smem) S2 = 2;
+    if (fixed + S2 * w2_blk + 2 * (size_t)w1_blk > max_smem) return fail(c, PHN_ERR_UNSUPPORTED, "tensor-core mode: shared memory plan does not fit\n");
+    int S1 = (int)((max_smem - fixed - S2 * w2_blk) / w1_blk);
     if (S1 > TC_MAXS1) S1 = TC_MAXS1;
+    if (S1 > 4 * im.KB1) S1 = 4 * im.KB1;   // (four chunk-level "full" barriers)
+    if (pair && S1 < im.KB1) return fail(c, PHN_ERR_UNSUPPORTED, "tensor-core mode: shared memory plan does not fit (pair)\n");
     a.S1 = S1; a.S2 = S2;
-    const size_t smem_bytes = fixed + (size_t)S1 * TC_BLK + (size_t)S2 * w2_blk;
+    const size_t smem_bytes = fixed + (size_t)S1 * w1_blk + (size_t)S2 * w2_blk;
     int grid = a.n_tiles < c->num_sms ? a.n_tiles : c->num_sms;
+    if (pair) {
+        const int npairs = (a.n_tiles + 1) / 2, maxp = c->num_sms / 2;
+        grid = 2 * (npairs < maxp ? npairs : maxp);
+    }
     if (const char *e = getenv("PHNREC_TC_GRID")) {  // debugging aid: force several tiles per CTA
         const int g = atoi(e);
         if (g > 0 && g < grid) grid = g;
+        if (pair) grid = grid < 2 ? 2 : (grid & ~1);
     }
     int rc;
     switch (im.N2P) {
-        case 128: rc = launch_one<128>(c, a, smem_bytes, grid); break;
-        case 144: rc = launch_one<144>(c, a, smem_bytes, grid); break;
-        case 160: rc = launch_one<160>(c, a, smem_bytes, grid); break;
-        default: rc = launch_one<192>(c, a, smem_bytes, grid); break;
+        case 128: rc = launch_one<128>(c, a, smem_bytes, grid, pair); break;
+        case 144: rc = launch_one<144>(c, a, smem_bytes, grid, pair); break;
+        case 160: rc = launch_one<160>(c, a, smem_bytes, grid, pair); break;
+        default: rc = launch_one<192>(c, a, smem_bytes, grid, pair); break;
     }
     c->k_launches[PHN_K_MLP] += 1;
     return rc;
