@@ -44,7 +44,52 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 //       3 = SS, commit after every 4 MMAs, 4 = SS same accumulator but k-steps walk 4 slices of 4 smem blocks
 __global__ void __launch_bounds__(128, 1) k_bench(int n, int mode_, int reps, long long *out_)
 {
-    const int mode = mode_ >= 10 ? 7 : mode_;          // mode 10 = mode 7 on every SM of the chip
+    const int mode = mode_ == 10 ? 7 : mode_;          // mode 10 = mode 7 on every SM of the chip
+    if (mode == 11) {                                   // mode 11: the two streams of mode 7 issued by TWO warps (warp 0: SS, warp 1: TS)
+        extern __shared__ uint8_t raw2[];
+        uint8_t *smem2 = raw2 + ((1024u - (smem_u32(raw2) & 1023u)) & 1023u);
+        __shared__ uint64_t bar2[2];
+        __shared__ uint32_t slot2;
+        for (int i = threadIdx.x; i < (4 * 16384 + 4 * 32768) / 4; i += blockDim.x) reinterpret_cast<uint32_t *>(smem2)[i] = 0x3c003c00u;
+        if (threadIdx.x == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar2[0])));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar2[1])));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        if (threadIdx.x < 32) {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&slot2)), "r"(512u) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t tm = slot2;
+        const int w = threadIdx.x >> 5;
+        if (w < 2) {
+            const uint64_t dB2 = make_sw128_desc(smem_u32(smem2 + 4 * 16384)), dA2 = make_sw128_desc(smem_u32(smem2));
+            const uint32_t i1 = make_idesc(128), i2 = make_idesc(144);
+            uint32_t pred;
+            asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+            if (pred) {
+                const int mine = w == 0 ? reps * 11 / 19 : reps * 8 / 19;
+                const long long t0 = clock64();
+                for (int r = 0; r < mine; ++r) {
+                    if (w == 0) umma_ss(tm, dA2 + 2 * (r & 3), dB2 + 2 * (r & 3), i1, r > 0);
+                    else umma_ts(tm + 256u, tm + 448u + 8u * (r & 3), dB2 + 2 * (r & 3), i2, r > 0);
+                }
+                const long long t1 = clock64();
+                commit(&bar2[w]); mbar_wait(&bar2[w], 0);
+                const long long t2 = clock64();
+                out_[4 * blockIdx.x + 2 * w] = (t1 - t0) * 1000 / mine;
+                out_[4 * blockIdx.x + 2 * w + 1] = (t2 - t0) * 1000 / mine;
+            }
+            __syncwarp();
+        }
+        __syncthreads();
+        if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tm), "r"(512u) : "memory");
+        return;
+    }
     long long *out = out_ + 4 * blockIdx.x;
     extern __shared__ uint8_t raw[];
     uint8_t *smem = raw + ((1024u - (smem_u32(raw) & 1023u)) & 1023u);
@@ -142,6 +187,13 @@ int main()
     const int reps = 19 * 16;
     const char *names[] = {"SS same acc", "SS 2 accs", "TS same acc", "SS commit/4", "SS walk blocks", "L1/L2 alt 1", "L1/L2 alt 4",
                            "L1/L2 alt 11/8", "alt 11/8 + LDTM", "alt 11/8 + ALU", "alt 11/8 x148 SMs"};
+    {   // two issuing warps
+        for (int it = 0; it < 2; ++it) { k_bench<<<1, 128, smem>>>(128, 11, reps, d_out); cudaDeviceSynchronize(); }
+        long long h4[4];
+        cudaMemcpy(h4, d_out, 32, cudaMemcpyDeviceToHost);
+        printf("two issuers      SS warp: issue %6.1f complete %6.1f clk/MMA | TS warp: issue %6.1f complete %6.1f clk/MMA\n",
+               h4[0] / 1000.0, h4[1] / 1000.0, h4[2] / 1000.0, h4[3] / 1000.0);
+    }
     for (int mode = 0; mode < 11; ++mode)
         for (int n : {64, 128, 144, 256}) {
             if (mode >= 5 && n != 128) continue;
