@@ -120,7 +120,9 @@ int phn_decode(phn_ctx *ctx, const float *post, const int64_t *frame_off, int n_
                phn_label *labels, int64_t label_cap, int64_t *label_off);
 
 /* audio -> labels with no host round trip in between; replaces SpeechRec::ProcessOffline
- * (srec.cpp:929-1111) for dfWaveform -> dfStrings.  frame_off_out may be NULL. */
+ * (srec.cpp:929-1111) for dfWaveform -> dfStrings.  frame_off_out may be NULL.
+ * The audio is copied in groups of whole utterances on a second stream while K-wave of the
+ * previous group runs (pass page-locked memory, phn_host_alloc_pinned, for the overlap). */
 int phn_recognize(phn_ctx *ctx, const void *audio, const int64_t *byte_off, int n_utt, phn_label *labels,
                   int64_t label_cap, int64_t *label_off, int64_t *frame_off_out);
 
@@ -131,7 +133,10 @@ int phn_recognize(phn_ctx *ctx, const void *audio, const int64_t *byte_off, int 
  * call phn_sync() or a phn_fetch_* before reading results. */
 int phn_recognize_device(phn_ctx *ctx, const void *d_audio, const int64_t *byte_off, int n_utt);
 int phn_sync(phn_ctx *ctx);
-/* Copy results of the last *_device / host call back. Any output may be NULL. */
+/* Copy results of the last *_device / host call back. Any output may be NULL.
+ * phn_fetch_posteriors: in PHN_MLP_TC_F16 mode the audio -> labels calls (phn_recognize*) hand
+ * ln p straight from the merger's epilogue to the decoder and never materialise the linear
+ * posteriors; the fetch then returns PHN_ERR_ARG - use phn_posteriors() for the `-t post` data. */
 int phn_fetch_labels(phn_ctx *ctx, phn_label *labels, int64_t label_cap, int64_t *label_off);
 int phn_fetch_mel(phn_ctx *ctx, float *mel_out);
 int phn_fetch_posteriors(phn_ctx *ctx, float *post_out);
