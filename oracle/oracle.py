@@ -248,6 +248,18 @@ def format_rec(labels: np.ndarray, phonemes) -> str:
                    for l in labels)
 
 
+def format_vad(labels: np.ndarray, phonemes) -> str:
+    """`.rec` text of the fork's `vadalize` tool (phndecalize.cpp:227-239, 299-314): "%.2f %.2f speech" in seconds
+    (float arithmetic) for every segment whose phoneme is not pau / int / spk."""
+    out = []
+    for l in labels:
+        if phonemes[int(l["phn"])] in ("pau", "int", "spk"):
+            continue
+        s, e = np.float32(int(l["start"])) / np.float32(100), np.float32(int(l["end"])) / np.float32(100)
+        out.append("%.2f %.2f speech\n" % (float(s), float(e)))
+    return "".join(out)
+
+
 def parse_rec(text: str):
     """-> list of (start_frame, end_frame, phoneme, score) from .rec / MLF body lines."""
     out = []

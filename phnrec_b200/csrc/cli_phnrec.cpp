@@ -46,7 +46,11 @@ void logmsg(const char *fmt, ...)
 
 void help()
 {
+#ifdef PHN_VADALIZE
+    puts("\nUSAGE: vadalize [options]\n");   // vadalize.cpp:28
+#else
     puts("\nUSAGE: phnrec [options]\n");
+#endif
     puts(" -c dir             configuration directory");
     puts(" -l file            list of files");
     puts(" -i file            input file");
@@ -156,7 +160,18 @@ struct Runner {
     // label writers: PhnDec's fprintf (phndec.cpp:230,292) and SpeechRec::OnWordMLF (srec.cpp:137-161)
     void write_rec(FILE *f, const phn_label *l, int64_t n)
     {
+#ifdef PHN_VADALIZE
+        // the `vadalize` personality (phndecalize.cpp:227-239, 299-314): one "start end speech" line, in seconds, for every
+        // segment that is not pau / int / spk; float arithmetic as in the reference (float / int, printed with %.2f)
+        for (int64_t i = 0; i < n; ++i) {
+            const std::string ph = phn_phoneme(ctx, l[i].phn);
+            if (ph == "pau" || ph == "int" || ph == "spk") continue;
+            const float alizeStart = (float)l[i].start, alizeEnd = (float)l[i].end;
+            fprintf(f, "%.2f %.2f speech\n", alizeStart / 100, alizeEnd / 100);
+        }
+#else
         for (int64_t i = 0; i < n; ++i) fprintf(f, "%d00000 %d00000 %s %f\n", l[i].start, l[i].end, phn_phoneme(ctx, l[i].phn), l[i].like);
+#endif
     }
     void write_mlf(const std::string &name, const phn_label *l, int64_t n)
     {

@@ -9,6 +9,7 @@ Outputs
   ref_labels.json   the 7 golden label files the reference ships (parsed verbatim:
                     start/end frame, phoneme, printed score) + which model/audio
                     produced each.
+  ref_vad.json      .rec output of the reference's `vadalize` tool (oracle/_ref/vadalize_ref) on three model/audio pairs.
   ref_run_*.npz     outputs of oracle/_ref/phnrec_ref on the reference's own test
                     audio: un-normalised log-mel (`-t par`), linear posteriors
                     (`-t post`, float32, full matrix for CZ / EN, every 8th row for
@@ -49,6 +50,16 @@ def main():
         labels[g] = {"model": model, "audio": audio, "mlf": mlf, "text": txt,
                      "labels": [list(x) for x in orc.parse_rec(txt)]}
     (OUT / "ref_labels.json").write_text(json.dumps(labels, indent=1))
+
+    # the fork's `vadalize` tool (vadalize.cpp + phndecalize.cpp, built as oracle/_ref/vadalize_ref): its .rec output
+    vad = {}
+    with tempfile.TemporaryDirectory() as td:
+        for model, audio in (("PHN_CZ_SPDAT_LCRC_N1500", "test.raw"), ("PHN_EN_TIMIT_LCRC_N500", "test.raw"), ("PHN_ES", "es.wav")):
+            out = Path(td) / "v.rec"
+            subprocess.run([str(orc.REF_BIN.parent / "vadalize_ref"), "-c", str(orc.REF_MODELS / model), "-i", str(orc.REF_AUDIO / audio),
+                            "-o", str(out)], check=True, capture_output=True)
+            vad[f"{model}/{audio}"] = out.read_text()
+    (OUT / "ref_vad.json").write_text(json.dumps(vad, indent=1))
 
     runs = sorted({(m, a) for _, m, a, _ in GOLDENS})
     with tempfile.TemporaryDirectory() as td:

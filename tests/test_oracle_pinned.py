@@ -113,3 +113,16 @@ def test_all_models_load(oracle_models):
         m = oracle_models(name)
         assert m.net_dims(0) == dims[name] and m.net_dims(1) == dims[name]
         assert m.net_dims(2) == (2 * dims[name][2], dims[name][1], dims[name][2])
+
+
+@pytest.mark.parametrize("key", ["PHN_CZ_SPDAT_LCRC_N1500/test.raw", "PHN_EN_TIMIT_LCRC_N500/test.raw", "PHN_ES/es.wav"])
+def test_vadalize_output_matches_reference_tool(orc, oracle_models, key):
+    """the fork's `vadalize` tool (vadalize.cpp + phndecalize.cpp, built as oracle/_ref/vadalize_ref):
+    "start end speech" lines for every non-{pau,int,spk} segment.  The oracle's formatter on the oracle's labels must
+    reproduce the reference tool's output byte for byte (fixture tests/golden/ref_vad.json)."""
+    import json
+    from conftest import GOLDEN, audio_bytes
+    want = json.loads((GOLDEN / "ref_vad.json").read_text())[key]
+    model, audio = key.split("/")
+    om = oracle_models(model)
+    assert orc.format_vad(om.recognize(audio_bytes(audio)), om.phonemes) == want
