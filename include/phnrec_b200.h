@@ -168,6 +168,12 @@ int phn_debug_tc_timeline(phn_ctx *ctx, int which, long long *out);
  * matrix, in place on the device: estimate over the first `interval` frames, apply after. */
 int phn_online_norm(phn_ctx *ctx, float *x, int64_t frames, int nbanks, int interval, int mean_norm, int var_norm);
 
+/* ASCII model files -> the binary .nbin cache (host only, no GPU needed): NeuralNet::LoadAscii + SaveBinary
+ * (nn.cpp:199-462, 533-592).  `weights`: "weigvec N" x2 then "biasvec N" x2; `norms` (may be NULL): "vec N" x2 =
+ * input means and inverse standard deviations.  phn_create() does the same on its own when a net has no .nbin
+ * (NeuralNet::Load, nn.cpp:594-621). */
+int phn_convert_weights(const char *weights_path, const char *norms_path, const char *nbin_out);
+
 /* Library / build identification. */
 const char *phn_version(void);
 int phn_device_count(void);

@@ -75,6 +75,7 @@ _SYMS = [
     ("phn_recognize_device", C.c_int, [C.c_void_p, C.c_void_p, _i64p, C.c_int]),
     ("phn_sync", C.c_int, [C.c_void_p]),
     ("phn_fetch_labels", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    ("phn_convert_weights", C.c_int, [C.c_char_p, C.c_char_p, C.c_char_p]),
     ("phn_fetch_mel", C.c_int, [C.c_void_p, _f32p]),
     ("phn_fetch_posteriors", C.c_int, [C.c_void_p, _f32p]),
     ("phn_stream", C.c_void_p, [C.c_void_p]),

@@ -211,6 +211,15 @@ extern "C" {
 
 const char *phn_version(void) { return "phnrec_b200 0.1 (sm_100a)"; }
 
+int phn_convert_weights(const char *weights_path, const char *norms_path, const char *nbin_out)
+{
+    if (!weights_path || !nbin_out) return PHN_ERR_ARG;
+    HostNet n;
+    int rc = n.load_ascii(weights_path, norms_path ? norms_path : "");
+    if (rc != PHN_OK) return rc;
+    return n.save_nbin(nbin_out);
+}
+
 int phn_device_count(void)
 {
     int n = 0;
@@ -298,8 +307,14 @@ int phn_create(const char *cfg_dir, int device, phn_ctx **out)
     // ---- nets (traps.cpp:139-166: .nbin tried first; it is the only weight source we read)
     const char *names[3] = {"band0", "band1", "merger"};
     for (int i = 0; i < 3; ++i) {
+        // NeuralNet::Load (nn.cpp:594-621): the binary cache first, else the ASCII pair, then the cache is written
         const std::string p = c->cfg_dir + "/weights/" + names[i] + ".nbin";
         rc = c->hnet[i].load(p);
+        if (rc != PHN_OK) {
+            const std::string w = c->cfg_dir + "/weights/" + names[i] + ".weights", nr = c->cfg_dir + "/norms/" + names[i] + ".norms";
+            rc = c->hnet[i].load_ascii(w, nr);
+            if (rc == PHN_OK) c->hnet[i].save_nbin(p);   // (failure to write the cache is ignored, as in the reference)
+        }
         if (rc != PHN_OK) return bail(fail(c, rc, "Can not load neural network: %s\n", p.c_str()));
     }
     if (c->hnet[0].nin % c->nbanks || c->hnet[0].nin != c->hnet[1].nin || c->hnet[0].nout != c->hnet[1].nout ||

@@ -33,6 +33,90 @@ int HostNet::load(const std::string &path)
     return PHN_OK;
 }
 
+// ---- ASCII weights / norms (NeuralNet::LoadAscii, GetInfo, ParseWeights, ParseNorms: nn.cpp:113-462)
+namespace {
+struct Tok {   // whitespace-separated tokens, numbers read with sscanf("%e") / ("%d") like GetFloatValue / GetIntValue (nn.cpp:952-982)
+    const char *p;
+    explicit Tok(const char *s) : p(s) {}
+    bool next(char *buf, size_t cap)
+    {
+        while (*p && strchr(" \t\n\r", *p)) ++p;
+        if (!*p) return false;
+        size_t i = 0;
+        while (*p && !strchr(" \t\n\r", *p)) { if (i + 1 < cap) buf[i++] = *p; ++p; }
+        buf[i] = 0;
+        return true;
+    }
+    bool word(const char *w) { char b[100]; return next(b, sizeof b) && !strcmp(b, w); }
+    bool integer(int *v) { char b[100]; return next(b, sizeof b) && sscanf(b, "%d", v) == 1; }
+    bool real(float *v) { char b[100]; return next(b, sizeof b) && sscanf(b, "%e", v) == 1; }
+};
+bool read_text(const std::string &path, std::string &out)
+{
+    FILE *f = fopen(path.c_str(), "rb");
+    if (!f) return false;
+    char buf[1 << 16];
+    size_t n;
+    out.clear();
+    while ((n = fread(buf, 1, sizeof buf, f)) > 0) out.append(buf, n);
+    fclose(f);
+    return true;
+}
+}  // namespace
+
+int HostNet::load_ascii(const std::string &weights_path, const std::string &norms_path)
+{
+    std::string txt;
+    if (!read_text(weights_path, txt)) return PHN_ERR_NN_FILE;
+    // sizes (GetInfo): nOut / nHid from the bias vectors, nIn = |W1| / nHid
+    std::vector<float> v[4];
+    const char *tags[4] = {"weigvec", "weigvec", "biasvec", "biasvec"};
+    Tok t(txt.c_str());
+    for (int k = 0; k < 4; ++k) {
+        int n = 0;
+        if (!t.word(tags[k]) || !t.integer(&n) || n <= 0) return PHN_ERR_NN_FORMAT;
+        v[k].resize((size_t)n);
+        for (int i = 0; i < n; ++i)
+            if (!t.real(&v[k][i])) return PHN_ERR_NN_FORMAT;
+    }
+    nhid = (int)v[2].size(); nout = (int)v[3].size();
+    nin = (int)(v[0].size() / (size_t)nhid);
+    if (nin <= 0 || (size_t)nin * nhid != v[0].size() || (size_t)nhid * nout != v[1].size()) return PHN_ERR_NN_FORMAT;
+    auto up4 = [](int n) { return (n + 3) / 4 * 4; };
+    nin4 = up4(nin); nhid4 = up4(nhid); nout4 = up4(nout);
+    w1.assign((size_t)nhid4 * nin4, 0.0f); w2.assign((size_t)nout4 * nhid4, 0.0f);
+    b1.assign((size_t)nhid4, 0.0f); b2.assign((size_t)nout4, 0.0f);
+    mean.assign((size_t)nin4, 0.0f); dev.assign((size_t)nin4, 1.0f);
+    for (int j = 0; j < nhid; ++j) memcpy(&w1[(size_t)j * nin4], &v[0][(size_t)j * nin], sizeof(float) * nin);     // row = hidden unit
+    for (int k = 0; k < nout; ++k) memcpy(&w2[(size_t)k * nhid4], &v[1][(size_t)k * nhid], sizeof(float) * nhid);  // row = output
+    memcpy(b1.data(), v[2].data(), sizeof(float) * nhid);
+    memcpy(b2.data(), v[3].data(), sizeof(float) * nout);
+    if (!norms_path.empty()) {
+        if (!read_text(norms_path, txt)) return PHN_ERR_NN_FILE;
+        Tok u(txt.c_str());
+        for (int k = 0; k < 2; ++k) {
+            int n = 0;
+            if (!u.word("vec") || !u.integer(&n)) return PHN_ERR_NN_FORMAT;
+            float *dst = k ? dev.data() : mean.data();
+            for (int i = 0; i < nin; ++i)
+                if (!u.real(&dst[i])) return PHN_ERR_NN_FORMAT;
+        }
+    }
+    return PHN_OK;
+}
+
+int HostNet::save_nbin(const std::string &path) const
+{
+    FILE *f = fopen(path.c_str(), "wb");
+    if (!f) return PHN_ERR_NN_FILE;
+    const int32_t hdr[4] = {2, nin, nhid, nout};
+    bool ok = fwrite(hdr, sizeof(int32_t), 4, f) == 4;
+    const std::vector<float> *parts[] = {&w1, &w2, &b1, &b2, &mean, &dev};
+    for (auto *p : parts) ok = ok && fwrite(p->data(), sizeof(float), p->size(), f) == p->size();
+    ok = (fclose(f) == 0) && ok;
+    return ok ? PHN_OK : PHN_ERR_NN_FILE;
+}
+
 static float mel_scale(float hz) { return 1127.0f * logf(1.0f + hz / 700.0f); }  // dspc.h:169-177
 
 void MelTables::build(int nbanks_, int vs_, int step_, int fs_, float lo, float hi)

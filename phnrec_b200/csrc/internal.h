@@ -27,6 +27,10 @@ struct HostNet {  // .nbin image, nn.cpp:464-531
     int nin = 0, nhid = 0, nout = 0, nin4 = 0, nhid4 = 0, nout4 = 0;
     std::vector<float> w1, w2, b1, b2, mean, dev;
     int load(const std::string &path);  // PHN_OK / PHN_ERR_NN_*
+    // ASCII model files (nn.cpp:199-462): `weigvec N` x2, `biasvec N` x2; norms `vec N` x2 (means, inverse std devs;
+    // norms_path empty -> means 0, devs 1).  save_nbin writes the reference's binary cache (nn.cpp:533-592).
+    int load_ascii(const std::string &weights_path, const std::string &norms_path);
+    int save_nbin(const std::string &path) const;
 };
 
 struct MelTables {  // melbanks.cpp:38-70, dspc.cpp:80-225, dspc.h:162-167

@@ -166,3 +166,30 @@ def test_two_rank_gather_restores_list_order(tmp_path):
     full = json.loads(out.read_text())
     frames = [int(x) for x in np.random.default_rng(7).integers(1, 2000, size=37)]
     assert full == [["utt%d" % u, frames[u] * 3 + 1] for u in range(37)]
+
+
+def test_ascii_weights_give_the_shipped_nbin_byte_for_byte(tmp_path):
+    """SURVEY §8(f) rank 3: NeuralNet::LoadAscii + SaveBinary (nn.cpp:199-462, 533-592).  The EN system ships both the ASCII
+    .weights/.norms and the .nbin cache the reference wrote from them: converting the ASCII pair must reproduce the
+    cache exactly (sizes from the bias vectors, rows padded to 4 floats, means 0 / devs 1 in the padding)."""
+    from phnrec_b200.api import load_library
+    L = load_library()
+    d = model_dir("PHN_EN_TIMIT_LCRC_N500")
+    if not (d / "weights" / "band0.weights").exists():
+        pytest.skip("ASCII model files not staged")
+    for n in ("band0", "band1", "merger"):
+        out = tmp_path / f"{n}.nbin"
+        rc = L.phn_convert_weights(str(d / "weights" / f"{n}.weights").encode(), str(d / "norms" / f"{n}.norms").encode(), str(out).encode())
+        assert rc == 0
+        assert out.read_bytes() == (d / "weights" / f"{n}.nbin").read_bytes()
+    # without a norms file: means 0, inverse devs 1 (NeuralNet::Alloc defaults, nn.cpp:633-682)
+    out = tmp_path / "nonorm.nbin"
+    assert L.phn_convert_weights(str(d / "weights" / "band0.weights").encode(), None, str(out).encode()) == 0
+    raw = np.frombuffer(out.read_bytes(), dtype=np.float32)
+    nin4 = 256
+    assert (raw[-2 * nin4:-nin4] == 0).all() and (raw[-nin4:] == 1).all()
+    # error codes: missing file, malformed file (NN_NOWEIGHTS / NN_BADWEIGHTS, nn.h:35-42)
+    assert L.phn_convert_weights(str(tmp_path / "absent.weights").encode(), None, str(out).encode()) != 0
+    bad = tmp_path / "bad.weights"
+    bad.write_text("weigvec 4\n1\n2\n3\n")
+    assert L.phn_convert_weights(str(bad).encode(), None, str(out).encode()) != 0

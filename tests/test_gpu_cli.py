@@ -97,3 +97,22 @@ def test_phnrec_tensor_core_mode_switch(tmp_path):
     got = [ln.split()[:3] for ln in out.read_text().splitlines()]
     want = [ln.split()[:3] for ln in str(ref_run(model, audio)["rec"]).splitlines()]
     assert sum(g == w for g, w in zip(got, want)) >= 0.9 * len(want)
+
+
+def test_model_directory_with_ascii_weights_only(tmp_path):
+    """NeuralNet::Load (nn.cpp:594-621): no .nbin -> the ASCII .weights/.norms are parsed and the .nbin cache is written
+    next to them; results are those of the shipped cache (EN is the system that ships the ASCII files)."""
+    import shutil
+    src = model_dir("PHN_EN_TIMIT_LCRC_N500")
+    if not (src / "weights" / "band0.weights").exists():
+        pytest.skip("ASCII model files not staged")
+    dst = tmp_path / "PHN_EN"
+    shutil.copytree(src, dst)
+    for f in (dst / "weights").glob("*.nbin"):
+        f.unlink()
+    out = tmp_path / "o.rec"
+    r = run("phnrec", "-c", dst, "-i", AUDIO / "test.raw", "-o", out)
+    assert r.returncode == 0, r.stderr
+    assert out.read_text() == str(ref_run("PHN_EN_TIMIT_LCRC_N500", "test.raw")["rec"])
+    for n in ("band0", "band1", "merger"):
+        assert (dst / "weights" / f"{n}.nbin").read_bytes() == (src / "weights" / f"{n}.nbin").read_bytes()
