@@ -545,8 +545,10 @@ int phn_synth_audio_device(phn_ctx *c, void *d_audio, int64_t bytes_per_utt, int
 static int recognize_after_wave(phn_ctx *c)
 {
     c->fuse_logp = 1;
+    c->fast_front = 1;
     int rc = run_posteriors(c);
     c->fuse_logp = 0;
+    c->fast_front = 0;
     if (rc) return rc;
     rc = run_decode(c, nullptr, 1);
     c->logp_valid = 0;

@@ -82,6 +82,7 @@ struct phn_ctx {
     void *tc = nullptr;  // tensor-core mode state (k_mlp_tc.cu)
     void *stc_btab = nullptr, *stc_bias = nullptr;   // K-stc tensor-core formulation: constant matrices (k_stc.cu)
     int force_exact_wave = 0;
+    int fast_front = 0;   // audio -> labels path of the tensor-core mode: fp32-tolerance front end (K-wave pairs, parallel sentence mean)
     void *tc_dbg = nullptr;   // device buffer for the tensor-core kernel's debug timeline (phn_debug_tc_timeline)
     int tc_dbg_net = -1;
     int fuse_logp = 0;   // tensor-core merger also writes ln(posteriors) for the decoder (audio -> labels path)

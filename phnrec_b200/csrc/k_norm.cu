@@ -34,6 +34,31 @@ __global__ void k_sentence_mean(const float *__restrict__ mel, const int64_t *__
     mean[idx] = T > 0 ? __fmul_rn(s, __fdiv_rn(1.0f, (float)T)) : 0.0f;  // Mat::div(v) == mul(1/v), matrix.h:245
 }
 
+// Tensor-core pipeline: the same mean with a fixed-shape parallel sum (deterministic and batch-invariant, but not the
+// reference's sequential order): one CTA per utterance; thread t owns band t % nb and every (240 / nb)-th frame, so the
+// CTA reads the utterance's [T][nb] block as one coalesced stream; partial sums meet in shared memory in a fixed order.
+__global__ void __launch_bounds__(256) k_sentence_mean_fast(const float *__restrict__ mel, const int64_t *__restrict__ frame_off, int nb,
+                                                            float *__restrict__ mean)
+{
+    __shared__ float s_part[256];
+    const int u = blockIdx.x;
+    const int64_t f0 = frame_off[u], T = frame_off[u + 1] - f0;
+    const int rows = 256 / nb, used = rows * nb;          // frames in flight per pass, active threads
+    const int b = threadIdx.x % nb, r = threadIdx.x / nb;
+    float s = 0.0f;
+    if (threadIdx.x < used) {
+        const float *p = mel + f0 * nb;
+        for (int64_t t = r; t < T; t += rows) s += p[t * nb + b];
+    }
+    s_part[threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.x < nb) {
+        float tot = 0.0f;
+        for (int k = 0; k < rows; ++k) tot += s_part[k * nb + threadIdx.x];
+        mean[(size_t)u * nb + threadIdx.x] = T > 0 ? tot * (1.0f / (float)T) : 0.0f;
+    }
+}
+
 int launch_sentence_mean(phn_ctx *c)
 {
     const int n = c->n_utt * c->nbanks;
@@ -42,6 +67,10 @@ int launch_sentence_mean(phn_ctx *c)
         PHN_CUDA(c, cudaMemsetAsync(c->d_mean.p, 0, sizeof(float) * n, c->stream));
         return PHN_OK;
     }
+    if (c->mlp_mode == PHN_MLP_TC_F16 && !c->force_exact_wave && c->fast_front)
+        k_sentence_mean_fast<<<c->n_utt, 256, 0, c->stream>>>((const float *)c->d_mel.p, (const int64_t *)c->d_frame_off.p, c->nbanks,
+                                                              (float *)c->d_mean.p);
+    else
     k_sentence_mean<<<(n + 127) / 128, 128, 0, c->stream>>>((const float *)c->d_mel.p, (const int64_t *)c->d_frame_off.p,
                                                             c->n_utt, c->nbanks, (float *)c->d_mean.p);
     PHN_CUDA(c, cudaGetLastError());

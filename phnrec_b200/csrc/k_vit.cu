@@ -101,10 +101,13 @@ __global__ void __launch_bounds__(32) k_viterbi(VitArgs a)
     const int pstride = ncol | 1;                      // odd row stride: conflict-free panel writes
     int64_t next_blk = f0 >> 4;                        // next 16-frame panel (global numbering) to request
     const int64_t last_blk = T > 0 ? (f0 + T - 1) >> 4 : -1;
+    int next_slot = (int)(next_blk % 3);                // ring slot of that panel (= panel number mod 3)
+    int row0 = (int)(f0 % 48);                          // ring row of the utterance's frame tb (kept incrementally)
     auto request_panel = [&](int64_t blk) {
         const int64_t F = blk * 16 + (lane & 15);
         const float *src = a.logp + ((F >> 7) * a.ld) * 128 + (F & 127);
-        float *dst = s_panel + (size_t)(F % 48) * pstride;
+        float *dst = s_panel + (size_t)(next_slot * 16 + (lane & 15)) * pstride;
+        if (++next_slot == 3) next_slot = 0;
         for (int cc = lane >> 4; cc < ncol; cc += 2)
             asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(dst + cc)), "l"(__cvta_generic_to_global(src + (size_t)cc * 128)) : "memory");
         asm volatile("cp.async.commit_group;" ::: "memory");
@@ -133,10 +136,14 @@ __global__ void __launch_bounds__(32) k_viterbi(VitArgs a)
                 for (int j = 0; j < 3; ++j) {
                     const int i = lane + 32 * r;
                     const int64_t f = f0 + tb + q;
-                    if (TILED) obs[q][r][j] = (valid[r] && tb + q < T) ? s_panel[(size_t)(f % 48) * pstride + 3 * i + j] : 0.0f;
+                    int rr = row0 + q;
+                    if (rr >= 48) rr -= 48;
+                    if (TILED) obs[q][r][j] = (valid[r] && tb + q < T) ? s_panel[rr * pstride + 3 * i + j] : 0.0f;
                     else obs[q][r][j] = (valid[r] && tb + q < T) ? a.logp[f * a.ld + 3 * i + j] : 0.0f;
                 }
         if (TILED) __syncwarp();   // (all lanes have their observations before a later request reuses a panel slot)
+        row0 += FB;
+        if (row0 >= 48) row0 -= 48;
 
 #pragma unroll
         for (int q = 0; q < FB; ++q) {
@@ -161,16 +168,16 @@ __global__ void __launch_bounds__(32) k_viterbi(VitArgs a)
                 }
             }
             // ---- PropagateInNetwork (phndec.cpp:121-144): first strict max of alpha[i][3] from (-FLT_MAX, 0)
-            unsigned bo = ORD_FLOOR;
+            // (inside a lane the candidates are visited in index order, so the reference's strict `>` on floats picks the
+            // lane's first maximum; one order-preserving key per lane then goes into the warp reduction)
+            float bv = -FLT_MAX;
             int bi = 0, b_prev = pv[0][3], b_len = ln[0][3];   // payload of the local winner travels with it
 #pragma unroll
             for (int r = 0; r < PPL; ++r) {
                 const float v = al[r][3];
-                if (valid[r] && v > -FLT_MAX) {
-                    const unsigned o = f2ord(v + 0.0f);
-                    if (o > bo) { bo = o; bi = lane + 32 * r; b_prev = pv[r][3]; b_len = ln[r][3]; }
-                }
+                if (valid[r] && v > bv) { bv = v; bi = lane + 32 * r; b_prev = pv[r][3]; b_len = ln[r][3]; }
             }
+            const unsigned bo = bv > -FLT_MAX ? f2ord(bv + 0.0f) : ORD_FLOOR;
             const unsigned mo = __reduce_max_sync(FULL, bo);
             const int mi = (int)__reduce_min_sync(FULL, bo == mo ? (unsigned)bi : 0x7fffffffu);
             const float mx = mo == ORD_FLOOR ? -FLT_MAX : ord2f(mo);
@@ -182,18 +189,16 @@ __global__ void __launch_bounds__(32) k_viterbi(VitArgs a)
             last_mi = mi;
             // ---- GetBestToken (phndec.cpp:169-189), only consumed by TimePruning when n >= H+1
             if (t + 1 >= H + 1) {
-                unsigned co = ORD_FLOOR;
+                float cv = -FLT_MAX;
                 int ci = 0x7fffffff, c_prev = 0, c_len = 1;
 #pragma unroll
                 for (int r = 0; r < PPL; ++r)
 #pragma unroll
                     for (int j = 1; j <= 3; ++j) {
                         const float v = al[r][j];
-                        if (valid[r] && v > -FLT_MAX) {
-                            const unsigned o = f2ord(v + 0.0f);
-                            if (o > co) { co = o; ci = (lane + 32 * r) * 3 + (j - 1); c_prev = pv[r][j]; c_len = ln[r][j]; }
-                        }
+                        if (valid[r] && v > cv) { cv = v; ci = (lane + 32 * r) * 3 + (j - 1); c_prev = pv[r][j]; c_len = ln[r][j]; }
                     }
+                const unsigned co = cv > -FLT_MAX ? f2ord(cv + 0.0f) : ORD_FLOOR;
                 const unsigned to = __reduce_max_sync(FULL, co);
                 const int ti = (int)__reduce_min_sync(FULL, (co == to && ci != 0x7fffffff) ? (unsigned)ci : 0x7fffffffu);
                 if (ti == 0x7fffffff) {  // nothing above -FLT_MAX: the scan's initial (len 1, prev 0)

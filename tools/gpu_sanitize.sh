@@ -1,0 +1,19 @@
+# memcheck of the fused path on a small ragged batch (both MLP modes)
+mkdir -p gpurun_out
+cat > /tmp/san.py <<'PY'
+import sys
+sys.path.insert(0, '.')
+import numpy as np
+import phnrec_b200 as pb
+rec = pb.Recognizer('oracle/_ref/models/PHN_CZ_SPDAT_LCRC_N1500', device=0)
+rec.set_wave_format('alaw')
+a = rec.synth_audio(24000, 5, seed=3)
+utts = [a[0].tobytes(), a[1].tobytes()[:9001], a[2].tobytes()[:300], a[3].tobytes(), a[4].tobytes()[:16000]]
+for mode in (pb.MLP_TC_F16, pb.MLP_EXACT_FP32):
+    rec.set_mlp_mode(mode)
+    lab = rec.recognize(utts)
+    print(mode, [len(l) for l in lab])
+rec.close()
+PY
+timeout 900 compute-sanitizer --tool memcheck --error-exitcode 7 python /tmp/san.py > gpurun_out/sanitize_memcheck.log 2>&1; echo "memcheck rc=$?"
+tail -8 gpurun_out/sanitize_memcheck.log
