@@ -158,16 +158,16 @@ static void reset_timing(phn_ctx *c)
 }
 
 // mel (device, un-normalised) -> posteriors (device)
-static int run_posteriors(phn_ctx *c)
+// workspace of the posterior estimator for the planned batch; returns the frames per MLP pass in c->chunk_frames
+static int prepare_posteriors(phn_ctx *c)
 {
     int rc;
-    { StageTimer t(c, PHN_K_MEAN); if ((rc = launch_sentence_mean(c))) return rc; }
     const bool tc = c->mlp_mode == PHN_MLP_TC_F16;
     const int64_t F = c->total_frames;
     int64_t ch = tc ? (int64_t)1 << 20 : (int64_t)1 << 15;   // frames per pass of the MLP workspace (tensor-core: 1.4 KB per frame)
     if (ch > F) ch = (F + 127) / 128 * 128;
+    c->chunk_frames = ch;
     if (ch == 0) return PHN_OK;
-    c->logp_valid = 0;
     if (tc) {
         if ((rc = mlp_tc_prepare(c))) return rc;
         if (c->fuse_logp && (rc = ensure(c, c->d_logp, sizeof(float) * (size_t)((F + 127) / 128 * 128 + 128) * c->ldp))) return rc;
@@ -182,10 +182,26 @@ static int run_posteriors(phn_ctx *c)
         if ((rc = ensure(c, c->d_xm, sizeof(float) * ch * c->net[2].kp))) return rc;
         if ((rc = ensure(c, c->d_h, sizeof(float) * ch * c->net[0].ldh))) return rc;
     }
-    c->chunk_frames = ch;
+    return PHN_OK;
+}
+
+// mel (device, un-normalised) -> posteriors (device).  front_done: the caller has already run K-mean and K-stc for
+// the whole batch (phn_recognize does so group by group under the audio copy; only when the batch is one MLP pass).
+static int run_posteriors(phn_ctx *c, bool front_done = false)
+{
+    int rc;
+    if (!front_done) {
+        if ((rc = prepare_posteriors(c))) return rc;
+        StageTimer t(c, PHN_K_MEAN);
+        if ((rc = launch_sentence_mean(c))) return rc;
+    }
+    const bool tc = c->mlp_mode == PHN_MLP_TC_F16;
+    const int64_t F = c->total_frames, ch = c->chunk_frames;
+    if (ch == 0) return PHN_OK;
+    c->logp_valid = 0;
     for (int64_t f0 = 0; f0 < F; f0 += ch) {
         const int64_t nf = F - f0 < ch ? F - f0 : ch;
-        { StageTimer t(c, PHN_K_STC); if ((rc = launch_stc(c, f0, nf))) return rc; }
+        if (!front_done) { StageTimer t(c, PHN_K_STC); if ((rc = launch_stc(c, f0, nf))) return rc; }
         { StageTimer t(c, PHN_K_MLP); if ((rc = tc ? launch_mlp_tc(c, f0, nf) : launch_mlp_exact(c, f0, nf))) return rc; }
     }
     c->logp_valid = tc && c->fuse_logp;
@@ -542,11 +558,11 @@ int phn_synth_audio_device(phn_ctx *c, void *d_audio, int64_t bytes_per_utt, int
 
 // --------------------------------------------------------------------- stages
 // mel (device) -> labels (device): everything behind K-wave on the audio -> labels path
-static int recognize_after_wave(phn_ctx *c)
+static int recognize_after_wave(phn_ctx *c, bool front_done = false)
 {
     c->fuse_logp = 1;
     c->fast_front = 1;
-    int rc = run_posteriors(c);
+    int rc = run_posteriors(c, front_done);
     c->fuse_logp = 0;
     c->fast_front = 0;
     if (rc) return rc;
@@ -683,6 +699,14 @@ int phn_recognize(phn_ctx *c, const void *audio, const int64_t *byte_off, int n_
     const int64_t total = byte_off[n_utt];
     int ng = (int)(total / ((int64_t)8 << 20));
     ng = ng < 1 ? 1 : (ng > 16 ? 16 : ng);
+    // When the batch is one pass of the tensor-core MLP, the sentence mean and the STC features of a group follow its
+    // K-wave at once, so the whole front end runs under the copy and the MLP starts when the last group has landed.
+    c->fuse_logp = 1; c->fast_front = 1;
+    rc = prepare_posteriors(c);
+    const bool front = rc == PHN_OK && c->mlp_mode == PHN_MLP_TC_F16 && c->chunk_frames >= c->total_frames && c->total_frames > 0 &&
+                       (c->nbanks == 15 || c->nbanks == 23);   // (the row-range form of K-stc exists for the shipped bank counts)
+    c->fuse_logp = 0; c->fast_front = 0;
+    if (rc) return rc;
     PHN_CUDA(c, cudaEventRecord(c->ev_free, c->stream));             // (buffer growth and its zero fill are stream work)
     PHN_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->ev_free, 0));
     {
@@ -700,10 +724,17 @@ int phn_recognize(phn_ctx *c, const void *audio, const int64_t *byte_off, int n_
             PHN_CUDA(c, cudaEventRecord(c->ev_copy[g], c->copy_stream));
             PHN_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_copy[g], 0));
             if ((rc = launch_wave(c, c->d_audio.p, c->h_frame_off[u0], c->h_frame_off[u1]))) return rc;
+            if (front) {
+                c->fast_front = 1;
+                rc = launch_sentence_mean(c, u0, u1);
+                if (!rc) rc = launch_stc(c, 0, c->total_frames, c->h_frame_off[u0], c->h_frame_off[u1]);
+                c->fast_front = 0;
+                if (rc) return rc;
+            }
             u0 = u1;
         }
     }
-    if ((rc = recognize_after_wave(c))) return rc;
+    if ((rc = recognize_after_wave(c, front))) return rc;
     if (frame_off_out) memcpy(frame_off_out, c->h_frame_off.data(), sizeof(int64_t) * (n_utt + 1));
     return phn_fetch_labels(c, labels, label_cap, label_off);
 }

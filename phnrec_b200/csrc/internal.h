@@ -131,9 +131,10 @@ int ensure(phn_ctx *c, phn_ctx::Buf &b, size_t bytes);
 
 // ---- kernel launchers (each in its own .cu)
 int launch_wave(phn_ctx *c, const void *d_audio, int64_t f_begin = 0, int64_t f_end = -1);   // k_wave.cu (frame range)
-int launch_sentence_mean(phn_ctx *c);                                      // k_norm.cu
+int launch_sentence_mean(phn_ctx *c, int u0 = 0, int u1 = -1);             // k_norm.cu (utterance range)
 int launch_online_norm(phn_ctx *c, float *d_x, int64_t frames, int nb, int interval, int mean_norm, int var_norm);
-int launch_stc(phn_ctx *c, int64_t f0, int64_t nf);                        // k_stc.cu
+int launch_stc(phn_ctx *c, int64_t f0, int64_t nf, int64_t row_lo = 0, int64_t row_hi = -1);   // k_stc.cu: frames [f0, f0+nf) of the pass;
+                                                                                                  // only rows row_lo <= frame < row_hi are produced
 int launch_mlp_exact(phn_ctx *c, int64_t f0, int64_t nf);                  // k_mlp_exact.cu
 int launch_mlp_tc(phn_ctx *c, int64_t f0, int64_t nf);                     // k_mlp_tc.cu
 int launch_viterbi(phn_ctx *c, const float *d_pen, int n_pen);             // k_vit.cu

@@ -59,20 +59,21 @@ __global__ void __launch_bounds__(256) k_sentence_mean_fast(const float *__restr
     }
 }
 
-int launch_sentence_mean(phn_ctx *c)
+int launch_sentence_mean(phn_ctx *c, int u0, int u1)
 {
-    const int n = c->n_utt * c->nbanks;
-    if (n == 0) return PHN_OK;
+    if (u1 < 0) u1 = c->n_utt;
+    const int nu = u1 - u0, n = nu * c->nbanks;
+    if (n <= 0) return PHN_OK;
+    float *mean = (float *)c->d_mean.p + (size_t)u0 * c->nbanks;
+    const int64_t *foff = (const int64_t *)c->d_frame_off.p + u0;
     if (!c->sent_mean_norm) {  // EN system: nothing is subtracted (x - 0.0f == x)
-        PHN_CUDA(c, cudaMemsetAsync(c->d_mean.p, 0, sizeof(float) * n, c->stream));
+        PHN_CUDA(c, cudaMemsetAsync(mean, 0, sizeof(float) * n, c->stream));
         return PHN_OK;
     }
     if (c->mlp_mode == PHN_MLP_TC_F16 && !c->force_exact_wave && c->fast_front)
-        k_sentence_mean_fast<<<c->n_utt, 256, 0, c->stream>>>((const float *)c->d_mel.p, (const int64_t *)c->d_frame_off.p, c->nbanks,
-                                                              (float *)c->d_mean.p);
+        k_sentence_mean_fast<<<nu, 256, 0, c->stream>>>((const float *)c->d_mel.p, foff, c->nbanks, mean);
     else
-    k_sentence_mean<<<(n + 127) / 128, 128, 0, c->stream>>>((const float *)c->d_mel.p, (const int64_t *)c->d_frame_off.p,
-                                                            c->n_utt, c->nbanks, (float *)c->d_mean.p);
+    k_sentence_mean<<<(n + 127) / 128, 128, 0, c->stream>>>((const float *)c->d_mel.p, foff, nu, c->nbanks, mean);
     PHN_CUDA(c, cudaGetLastError());
     c->k_launches[PHN_K_MEAN] += 1;
     return PHN_OK;

@@ -185,7 +185,8 @@ struct StcMmaArgs {
     const uint4 *btab;     // [2][nb][2 n-tiles][32 lanes] B fragments {hi k0-7, hi k8-15, lo k0-7, lo k8-15}
     const float *bias;     // [2][nb * 11]
     uint8_t *x0h, *x1h;
-    int kb1, n_tiles;
+    int kb1, n_tiles, tile_lo;   // tiles [tile_lo, tile_lo + n_tiles) of the pass
+    int64_t row_lo, row_hi;      // only frames row_lo <= f0 + fl < row_hi are produced (a group of whole utterances)
 };
 
 __device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1)
@@ -229,7 +230,7 @@ __global__ void __launch_bounds__(256, 2) k_stc_mma(StcMmaArgs a)
         const int r = i / (COLS - NIN), cidx = NIN + i % (COLS - NIN);
         my_out[r * STCM_LD + cidx] = __float2half_rn(cidx < NIN + 2 ? 1.0f : 0.0f);
     }
-    for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+    for (int tile = a.tile_lo + blockIdx.x; tile < a.tile_lo + a.n_tiles; tile += gridDim.x) {
         const int64_t fl0 = (int64_t)tile * STCM_F;
         const int64_t G0 = a.f0 + fl0 - 15;
         __syncthreads();   // (previous tile's readers of s_mel / s_u are done)
@@ -239,7 +240,7 @@ __global__ void __launch_bounds__(256, 2) k_stc_mma(StcMmaArgs a)
         }
         if (threadIdx.x < STCM_F) {
             const int64_t fl = fl0 + threadIdx.x;
-            if (fl < a.nf) {
+            if (fl < a.nf && a.f0 + fl >= a.row_lo && a.f0 + fl < a.row_hi) {
                 const int u = stc_find_utt(a.frame_off, a.n_utt, a.f0 + fl);
                 s_u[threadIdx.x] = u;
                 s_u0[threadIdx.x] = a.frame_off[u];
@@ -304,7 +305,7 @@ __global__ void __launch_bounds__(256, 2) k_stc_mma(StcMmaArgs a)
             for (int q = lane; q < 16 * (COLS / 8); q += 32) {
                 const int r16 = q / (COLS / 8), ch = q - r16 * (COLS / 8);
                 const int r = warp * 16 + r16;
-                if (fl0 + r < a.nf)
+                if (s_u[r] >= 0)   // (inside the pass and inside this launch's row range)
                     *reinterpret_cast<uint4 *>(img + (size_t)(ch >> 3) * 16384 + r * 128 + ((((unsigned)ch & 7u) ^ ((unsigned)r & 7u)) << 4)) =
                         *reinterpret_cast<const uint4 *>(my_out + r16 * STCM_LD + ch * 8);
             }
@@ -365,7 +366,7 @@ static int launch_stc_mma_t(phn_ctx *c, const StcMmaArgs &a)
     return PHN_OK;
 }
 
-static int launch_stc_mma(phn_ctx *c, int64_t f0, int64_t nf)
+static int launch_stc_mma(phn_ctx *c, int64_t f0, int64_t nf, int64_t row_lo, int64_t row_hi)
 {
     int rc;
     if ((rc = stc_mma_prepare(c))) return rc;
@@ -378,16 +379,22 @@ static int launch_stc_mma(phn_ctx *c, int64_t f0, int64_t nf)
     a.btab = (const uint4 *)c->stc_btab; a.bias = (const float *)c->stc_bias;
     a.x0h = (uint8_t *)c->d_x0h.p; a.x1h = (uint8_t *)c->d_x1h.p;
     a.kb1 = c->net[0].k1P / 64;
-    a.n_tiles = (int)((nf + STCM_F - 1) / STCM_F);
+    if (row_lo < f0) row_lo = f0;
+    if (row_hi > f0 + nf) row_hi = f0 + nf;
+    if (row_hi <= row_lo) return PHN_OK;
+    a.row_lo = row_lo; a.row_hi = row_hi;
+    a.tile_lo = (int)((row_lo - f0) / STCM_F);
+    a.n_tiles = (int)((row_hi - f0 + STCM_F - 1) / STCM_F) - a.tile_lo;
     rc = c->nbanks == 15 ? launch_stc_mma_t<15>(c, a) : launch_stc_mma_t<23>(c, a);
     if (rc) return rc;
     c->k_launches[PHN_K_STC] += 1;
     return PHN_OK;
 }
 
-int launch_stc(phn_ctx *c, int64_t f0, int64_t nf)
+int launch_stc(phn_ctx *c, int64_t f0, int64_t nf, int64_t row_lo, int64_t row_hi)
 {
     if (nf == 0) return PHN_OK;
+    if (row_hi < 0) row_hi = f0 + nf;
     StcArgs a;
     a.mel = (const float *)c->d_mel.p;
     a.mean = (const float *)c->d_mean.p;
@@ -399,7 +406,7 @@ int launch_stc(phn_ctx *c, int64_t f0, int64_t nf)
     a.nmean1 = c->net[1].mean; a.ndev1 = c->net[1].dev;
     a.normc = sqrtf(2.0f / 16.0f);
     const bool tc = c->mlp_mode == PHN_MLP_TC_F16;
-    if (tc && (c->nbanks == 15 || c->nbanks == 23) && c->net[0].k1P / 64 == (c->nbanks * 11 + 2 + 63) / 64) return launch_stc_mma(c, f0, nf);
+    if (tc && (c->nbanks == 15 || c->nbanks == 23) && c->net[0].k1P / 64 == (c->nbanks * 11 + 2 + 63) / 64) return launch_stc_mma(c, f0, nf, row_lo, row_hi);
     a.x0 = tc ? nullptr : (float *)c->d_x0.p;
     a.x1 = tc ? nullptr : (float *)c->d_x1.p;
     a.x0h = tc ? (uint8_t *)c->d_x0h.p : nullptr;

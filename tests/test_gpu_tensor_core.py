@@ -151,3 +151,30 @@ def test_tc_front_end_mel_close_to_exact_and_silence_exact(recs, model, fmt):
         assert np.abs(fast - exact).max() <= TC_MEL_ABS, np.abs(fast - exact).max()
     finally:
         r.set_wave_format("lin16")
+
+
+def test_tc_grouped_host_path_equals_device_path(recs):
+    """phn_recognize() copies the audio in groups of whole utterances and runs K-wave / K-mean / K-stc group by group under
+    the copy; phn_recognize_device() runs every stage once over the whole batch.  Same kernels, same numbers: the
+    labels must be identical (ragged utterance lengths so that group boundaries fall inside 128-frame tiles)."""
+    r = recs("PHN_CZ_SPDAT_LCRC_N1500")
+    r.set_wave_format("alaw")
+    try:
+        n = 330
+        a = r.synth_audio(80000, n, seed=11)
+        lens = [80000 - 137 * (i % 7) - 3 * i for i in range(n)]            # ~26 MB -> 3 copy groups
+        utts = [a[i].tobytes()[:lens[i]] for i in range(n)]
+        host = r.recognize(utts)
+        boff = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+        flat = np.frombuffer(b"".join(utts), dtype=np.uint8)
+        d = r.device_alloc(flat.size)
+        r.memcpy_h2d(d, flat.ctypes.data, flat.size)
+        r.recognize_device(d, boff)
+        frames = sum(r.num_frames(x) for x in lens)
+        dev = r.fetch_labels(n, frames + 48 * n)
+        r.device_free(d)
+        assert len(dev) == n
+        for h, g in zip(host, dev):
+            assert np.array_equal(h.view(np.uint8), g.view(np.uint8))
+    finally:
+        r.set_wave_format("lin16")
