@@ -267,34 +267,38 @@ __global__ void __launch_bounds__(256, 2) k_stc_mma(StcMmaArgs a)
                 int ta = ra - 15 + j + side * 15, tb = rb - 15 + j + side * 15;
                 ta = ta < 0 ? 0 : (ta > Ta - 1 ? Ta - 1 : ta);
                 tb = tb < 0 ? 0 : (tb > Tb - 1 ? Tb - 1 : tb);
-                oa[i] = (int)(u0a + ta - G0) * NB;
-                ob[i] = (int)(u0b + tb - G0) * NB;
+                oa[i] = ua < 0 ? 0 : (int)(u0a + ta - G0) * NB;
+                ob[i] = ub < 0 ? 0 : (int)(u0b + tb - G0) * NB;
             }
             const uint4 *bt = s_b + (size_t)side * NB * 64 + lane;
             const float *bias = s_bias + side * NIN;
 #pragma unroll 3
             for (int b = 0; b < NB; ++b) {
-                const float ma = ua < 0 ? 0.0f : __ldg(mean_a + b), mb = ub < 0 ? 0.0f : __ldg(mean_b + b);
+                // (rows outside the pass or outside this launch's row range read window row 0 and utterance 0's mean: finite
+                // numbers that are never written out)
+                const float ma = __ldg(mean_a + b), mb = __ldg(mean_b + b);
                 uint32_t ah[4], al[4];   // A fragment: {row g k 2t..}, {row g+8 k 2t..}, {row g k 2t+8..}, {row g+8 k 2t+8..}
-                split_half2(ua < 0 ? 0.0f : s_mel[oa[0] + b] - ma, ua < 0 ? 0.0f : s_mel[oa[1] + b] - ma, ah[0], al[0]);
-                split_half2(ub < 0 ? 0.0f : s_mel[ob[0] + b] - mb, ub < 0 ? 0.0f : s_mel[ob[1] + b] - mb, ah[1], al[1]);
-                split_half2(ua < 0 ? 0.0f : s_mel[oa[2] + b] - ma, ua < 0 ? 0.0f : s_mel[oa[3] + b] - ma, ah[2], al[2]);
-                split_half2(ub < 0 ? 0.0f : s_mel[ob[2] + b] - mb, ub < 0 ? 0.0f : s_mel[ob[3] + b] - mb, ah[3], al[3]);
+                split_half2(s_mel[oa[0] + b] - ma, s_mel[oa[1] + b] - ma, ah[0], al[0]);
+                split_half2(s_mel[ob[0] + b] - mb, s_mel[ob[1] + b] - mb, ah[1], al[1]);
+                split_half2(s_mel[oa[2] + b] - ma, s_mel[oa[3] + b] - ma, ah[2], al[2]);
+                split_half2(s_mel[ob[2] + b] - mb, s_mel[ob[3] + b] - mb, ah[3], al[3]);
 #pragma unroll
                 for (int nt = 0; nt < 2; ++nt) {
                     const uint4 bf = bt[(b * 2 + nt) * 32];
-                    float d[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+                    const int n = nt * 8 + 2 * t;    // coefficient of d[0] / d[2]; d[1] / d[3] are n + 1
+                    const int col = b * 11 + n;
+                    // the accumulator starts at -mean * dev of its column (NeuralNet::Normalize folded in)
+                    const float nb0 = n < 11 ? -bias[col] : 0.0f, nb1 = n + 1 < 11 ? -bias[col + 1] : 0.0f;
+                    float d[4] = {nb0, nb1, nb0, nb1};
                     mma16816(d, al, bf.x, bf.y);     // small terms first
                     mma16816(d, ah, bf.z, bf.w);
                     mma16816(d, ah, bf.x, bf.y);
-                    const int n = nt * 8 + 2 * t;    // coefficient of d[0] / d[2]; d[1] / d[3] are n + 1
                     if (n < 11) {
-                        const int col = b * 11 + n;
-                        my_out[g * STCM_LD + col] = __float2half_rn(ua < 0 ? 0.0f : d[0] - bias[col]);
-                        my_out[(g + 8) * STCM_LD + col] = __float2half_rn(ub < 0 ? 0.0f : d[2] - bias[col]);
+                        my_out[g * STCM_LD + col] = __float2half_rn(d[0]);
+                        my_out[(g + 8) * STCM_LD + col] = __float2half_rn(d[2]);
                         if (n + 1 < 11) {
-                            my_out[g * STCM_LD + col + 1] = __float2half_rn(ua < 0 ? 0.0f : d[1] - bias[col + 1]);
-                            my_out[(g + 8) * STCM_LD + col + 1] = __float2half_rn(ub < 0 ? 0.0f : d[3] - bias[col + 1]);
+                            my_out[g * STCM_LD + col + 1] = __float2half_rn(d[1]);
+                            my_out[(g + 8) * STCM_LD + col + 1] = __float2half_rn(d[3]);
                         }
                     }
                 }
@@ -302,8 +306,9 @@ __global__ void __launch_bounds__(256, 2) k_stc_mma(StcMmaArgs a)
             __syncwarp();
             // the warp's 16 rows x 24 chunks of 16 bytes -> image (K-major SW128 blocks, k_mlp_tc.cu)
             uint8_t *img = (side ? a.x1h : a.x0h) + (size_t)tile * a.kb1 * 16384;
+#pragma unroll 4
             for (int q = lane; q < 16 * (COLS / 8); q += 32) {
-                const int r16 = q / (COLS / 8), ch = q - r16 * (COLS / 8);
+                const int r16 = q / (COLS / 8), ch = q - r16 * (COLS / 8);   // (division by a compile-time constant)
                 const int r = warp * 16 + r16;
                 if (s_u[r] >= 0)   // (inside the pass and inside this launch's row range)
                     *reinterpret_cast<uint4 *>(img + (size_t)(ch >> 3) * 16384 + r * 128 + ((((unsigned)ch & 7u) ^ ((unsigned)r & 7u)) << 4)) =
