@@ -5,6 +5,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <sys/stat.h>
 
@@ -165,6 +166,10 @@ static int prepare_posteriors(phn_ctx *c)
     const bool tc = c->mlp_mode == PHN_MLP_TC_F16;
     const int64_t F = c->total_frames;
     int64_t ch = tc ? (int64_t)1 << 20 : (int64_t)1 << 15;   // frames per pass of the MLP workspace (tensor-core: 1.4 KB per frame)
+    if (const char *e = getenv("PHNREC_PASS_FRAMES")) {      // testing aid: force several passes on small batches (multiple of 128)
+        const int64_t v = atoll(e) / 128 * 128;
+        if (v >= 128) ch = v;
+    }
     if (ch > F) ch = (F + 127) / 128 * 128;
     c->chunk_frames = ch;
     if (ch == 0) return PHN_OK;

@@ -224,3 +224,15 @@ def test_capacity_error_reports_needed_size(recs):
     loff = np.zeros(2, dtype=np.int64)
     rc = r._L.phn_recognize(r._h, a.ctypes.data, boff, 1, labels.ctypes.data, 2, loff, None)
     assert rc == 32 and loff[1] == 50
+
+
+def test_exact_several_mlp_passes_equal_reference(monkeypatch):
+    """The exact mode with forced small passes (PHNREC_PASS_FRAMES): still the reference's bits."""
+    monkeypatch.setenv("PHNREC_PASS_FRAMES", "256")
+    r = pb.Recognizer(model_dir("PHN_CZ_SPDAT_LCRC_N1500"), device=0)
+    try:
+        ref = ref_run("PHN_CZ_SPDAT_LCRC_N1500", "test.raw")
+        lab = r.recognize([audio_bytes("test.raw")])[0]
+        assert pb.format_rec(lab, r.phonemes) == str(ref["rec"])
+    finally:
+        r.close()

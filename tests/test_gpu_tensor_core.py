@@ -178,3 +178,23 @@ def test_tc_grouped_host_path_equals_device_path(recs):
             assert np.array_equal(h.view(np.uint8), g.view(np.uint8))
     finally:
         r.set_wave_format("lin16")
+
+
+def test_tc_several_mlp_passes_equal_one_pass(recs, monkeypatch):
+    """Batches beyond 2^20 frames (BASELINE config 5: 1000 h) run the posterior estimator in several passes over the same
+    workspace.  Forced here on a small ragged batch (PHNREC_PASS_FRAMES): labels and posteriors must be bitwise those of
+    the single pass (pass boundaries fall inside utterances)."""
+    r = recs("PHN_CZ_SPDAT_LCRC_N1500")
+    a = audio_bytes("test.raw")
+    utts = [a, a[:50000], a[3000:90000], a[:398], a[20000:]]
+    one = r.recognize(utts)
+    mels = r.mel(utts)
+    post_one = r.posteriors(mels)
+    monkeypatch.setenv("PHNREC_PASS_FRAMES", "512")
+    many = r.recognize(utts)
+    post_many = r.posteriors(mels)
+    monkeypatch.delenv("PHNREC_PASS_FRAMES")
+    for x, y in zip(one, many):
+        assert np.array_equal(x.view(np.uint8), y.view(np.uint8))
+    for x, y in zip(post_one, post_many):
+        assert np.array_equal(x.view(np.uint32), y.view(np.uint32))
