@@ -236,3 +236,25 @@ def test_exact_several_mlp_passes_equal_reference(monkeypatch):
         assert pb.format_rec(lab, r.phonemes) == str(ref["rec"])
     finally:
         r.close()
+
+
+@pytest.mark.parametrize("mode", [pb.MLP_EXACT_FP32, pb.MLP_TC_F16])
+def test_degenerate_batches(oracle_models, mode):
+    """Edge cases of the batch interface: an empty batch, empty utterances (0 bytes: the reference still makes ONE frame,
+    srec.cpp:945, and decodes it), an utterance shorter than a window, all in one call."""
+    r = pb.Recognizer(model_dir("PHN_CZ_SPDAT_LCRC_N1500"), device=0)
+    try:
+        r.set_mlp_mode(mode)
+        assert r.recognize([]) == []
+        a = audio_bytes("test.raw")
+        utts = [b"", a[:100], a[:398], b"", a[:4000]]
+        got = r.recognize(utts)
+        assert len(got) == 5
+        om = oracle_models("PHN_CZ_SPDAT_LCRC_N1500")
+        for u, g in zip(utts, got):
+            want = om.recognize(u)
+            assert [(int(x["start"]), int(x["end"])) for x in g] == [(int(x["start"]), int(x["end"])) for x in want]
+            if mode == pb.MLP_EXACT_FP32:
+                assert pb.format_rec(g, r.phonemes) == pb.format_rec(want, om.phonemes)
+    finally:
+        r.close()
