@@ -136,6 +136,12 @@ static int plan_audio(phn_ctx *c, const int64_t *byte_off, int n_utt)
     if ((rc = ensure(c, c->d_byte_off, sizeof(int64_t) * (n_utt + 1)))) return rc;
     PHN_CUDA(c, cudaMemcpyAsync(c->d_byte_off.p, c->h_byte_off.data(), sizeof(int64_t) * (n_utt + 1), cudaMemcpyHostToDevice,
                                 c->stream));
+    // frame pairs of the fp32 front end never straddle utterances (results must not depend on the batch around them)
+    c->h_pair_off.assign((size_t)n_utt + 1, 0);
+    for (int u = 0; u < n_utt; ++u) c->h_pair_off[u + 1] = c->h_pair_off[u] + (fo[u + 1] - fo[u] + 1) / 2;
+    if ((rc = ensure(c, c->d_pair_off, sizeof(int64_t) * (n_utt + 1)))) return rc;
+    PHN_CUDA(c, cudaMemcpyAsync(c->d_pair_off.p, c->h_pair_off.data(), sizeof(int64_t) * (n_utt + 1), cudaMemcpyHostToDevice,
+                                c->stream));
     return PHN_OK;
 }
 
@@ -424,7 +430,7 @@ void phn_destroy(phn_ctx *c)
     }
     phn_ctx::Buf *bufs[] = {&c->d_audio, &c->d_byte_off, &c->d_frame_off, &c->d_lab_off, &c->d_mel, &c->d_mean, &c->d_post,
                             &c->d_rec, &c->d_labels, &c->d_nlab, &c->d_pen, &c->d_x0, &c->d_x1, &c->d_h, &c->d_xm,
-                            &c->d_x0h, &c->d_x1h, &c->d_xmh, &c->d_tile_ctr, &c->d_coff, &c->d_labels_c, &c->d_logp};
+                            &c->d_x0h, &c->d_x1h, &c->d_xmh, &c->d_tile_ctr, &c->d_coff, &c->d_labels_c, &c->d_logp, &c->d_pair_off};
     for (auto *b : bufs)
         if (b->p) cudaFree(b->p);
     mlp_tc_release(c);
@@ -728,7 +734,7 @@ int phn_recognize(phn_ctx *c, const void *audio, const int64_t *byte_off, int n_
                 PHN_CUDA(c, cudaMemcpyAsync((uint8_t *)c->d_audio.p + b0, (const uint8_t *)audio + b0, (size_t)nb, cudaMemcpyHostToDevice, c->copy_stream));
             PHN_CUDA(c, cudaEventRecord(c->ev_copy[g], c->copy_stream));
             PHN_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_copy[g], 0));
-            if ((rc = launch_wave(c, c->d_audio.p, c->h_frame_off[u0], c->h_frame_off[u1]))) return rc;
+            if ((rc = launch_wave(c, c->d_audio.p, u0, u1))) return rc;
             if (front) {
                 c->fast_front = 1;
                 rc = launch_sentence_mean(c, u0, u1);

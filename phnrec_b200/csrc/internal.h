@@ -106,6 +106,8 @@ struct phn_ctx {
     Buf d_audio, d_byte_off, d_frame_off, d_lab_off, d_mel, d_mean, d_post, d_rec, d_labels, d_nlab, d_pen;
     Buf d_x0, d_x1, d_h, d_xm, d_x0h, d_x1h, d_xmh;  // MLP workspace (per frame chunk)
     Buf d_tile_ctr, d_coff, d_labels_c, d_logp;
+    Buf d_pair_off;                          // [n_utt + 1] prefix sums of ceil(T_u / 2): work units of the frame-pair K-wave
+    std::vector<int64_t> h_pair_off;
     std::vector<int32_t> h_nlab;
     std::vector<float> h_pen;
     int64_t chunk_frames = 0;
@@ -130,7 +132,7 @@ int fail(phn_ctx *c, int code, const char *fmt, ...);
 int ensure(phn_ctx *c, phn_ctx::Buf &b, size_t bytes);
 
 // ---- kernel launchers (each in its own .cu)
-int launch_wave(phn_ctx *c, const void *d_audio, int64_t f_begin = 0, int64_t f_end = -1);   // k_wave.cu (frame range)
+int launch_wave(phn_ctx *c, const void *d_audio, int u0 = 0, int u1 = -1);   // k_wave.cu (utterance range)
 int launch_sentence_mean(phn_ctx *c, int u0 = 0, int u1 = -1);             // k_norm.cu (utterance range)
 int launch_online_norm(phn_ctx *c, float *d_x, int64_t frames, int nb, int interval, int mean_norm, int var_norm);
 int launch_stc(phn_ctx *c, int64_t f0, int64_t nf, int64_t row_lo = 0, int64_t row_hi = -1);   // k_stc.cu: frames [f0, f0+nf) of the pass;

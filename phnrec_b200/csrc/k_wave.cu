@@ -21,10 +21,11 @@ namespace phn {
 
 struct WaveArgs {
     const uint8_t *audio;
-    const int64_t *byte_off, *frame_off;
+    const int64_t *byte_off, *frame_off, *pair_off;
     int n_utt;
     int64_t total_frames;
     int64_t f_begin, f_end;   // frame range of this launch (a group of whole utterances)
+    int64_t p_begin, p_end;   // the same range in frame pairs (k_wave_pair)
     int fmt, vs, step, N, logN, nbanks;
     float scale, dc_shift, frame_shift, frame_floor, preem;
     int z_mean;
@@ -257,7 +258,7 @@ __global__ void __launch_bounds__(kWaveWarps * 32) k_wave(WaveArgs a)
 }
 
 // ------------------------------------------------------------------------------------------------
-// Tensor-core pipeline (fp32 front end): TWO real frames per complex FFT.  z = a + i b; by linearity and the
+// Tensor-core pipeline (fp32 front end): TWO real frames (2i, 2i + 1 of one utterance) per complex FFT.  z = a + i b; by linearity and the
 // conjugate symmetry of real signals  A[k] = (Z[k] + conj Z[N-k]) / 2,  B[k] = (Z[k] - conj Z[N-k]) / 2i,  so
 // |A[k]|^2 = ((Zr[k] + Zr[N-k])^2 + (Zi[k] - Zi[N-k])^2) / 4,  |B[k]|^2 = ((Zr[k] - Zr[N-k])^2 + (Zi[k] + Zi[N-k])^2) / 4.
 // Half the butterflies per frame; the price is fp32 cross-talk between the two frames at the 1e-7 level of the
@@ -295,24 +296,26 @@ __global__ void __launch_bounds__(kWaveWarps * 32) k_wave_pair(WaveArgs a)
     float *pwA = reinterpret_cast<float *>(data + N + N / 32);   // [N2] power spectrum of the first frame
     float *pwB = reinterpret_cast<float *>(data);                // [N2] second frame (aliases data[], free by then)
     constexpr int bps = ALAW ? 1 : 2;
-    const int64_t n_pairs = (a.f_end - a.f_begin + 1) / 2;
-
-    for (int64_t p = (int64_t)blockIdx.x * kWaveWarps + warp; p < n_pairs; p += (int64_t)gridDim.x * kWaveWarps) {
-        const int64_t fA = a.f_begin + 2 * p, fB = fA + 1;
-        const bool haveB = fB < a.f_end;
+    // work unit = frames (2i, 2i + 1) of ONE utterance (an odd last frame goes alone): which frames share an FFT does not
+    // depend on what else is in the batch or on how the batch was cut into launches
+    for (int64_t p = a.p_begin + (int64_t)blockIdx.x * kWaveWarps + warp; p < a.p_end; p += (int64_t)gridDim.x * kWaveWarps) {
+        const int u = find_utt(a.pair_off, a.n_utt, p);
+        const int64_t t0 = 2 * (p - a.pair_off[u]), T = a.frame_off[u + 1] - a.frame_off[u];
+        const int64_t fA = a.frame_off[u] + t0, fB = fA + 1;
+        const bool haveB = t0 + 1 < T;
         // per frame: pointer to its first sample and the number of samples the window may read (0 beyond the signal)
         const uint8_t *src[2];
         int lim[2];
-#pragma unroll
-        for (int w = 0; w < 2; ++w) {
-            const int64_t f = w ? (haveB ? fB : fA) : fA;
-            const int u = find_utt(a.frame_off, a.n_utt, f);
+        {
             const int64_t b0 = a.byte_off[u];
             const int64_t len = (a.byte_off[u + 1] - b0) / bps;
-            const int64_t s0 = (f - a.frame_off[u]) * a.step;
-            src[w] = a.audio + b0 + bps * s0;
-            const int64_t left = len - s0;
-            lim[w] = (w && !haveB) ? 0 : (int)(left < a.vs ? (left < 0 ? 0 : left) : a.vs);
+#pragma unroll
+            for (int w = 0; w < 2; ++w) {
+                const int64_t s0 = (t0 + (w && haveB ? 1 : 0)) * a.step;
+                src[w] = a.audio + b0 + bps * s0;
+                const int64_t left = len - s0;
+                lim[w] = (w && !haveB) ? 0 : (int)(left < a.vs ? (left < 0 ? 0 : left) : a.vs);
+            }
         }
         const float dc = a.dc_shift, sc = a.scale;
         auto decode = [&](const uint8_t *q) -> float {  // srec.cpp:742-743 / 768-769, dc shift, scale ((x + 0) * 1 == x)
@@ -451,7 +454,7 @@ static int launch_wave_t(phn_ctx *c, const WaveArgs &a)
                         sizeof(float2) * (size_t)kWaveWarps * (N + N / 32 + N2 / 2);
     PHN_CUDA(c, cudaFuncSetAttribute(k_wave<EXACT, LOGN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const bool pair = !EXACT && !a.z_mean && a.preem == 0.0f;
-    const int64_t units = pair ? (a.f_end - a.f_begin + 1) / 2 : a.f_end - a.f_begin;
+    const int64_t units = pair ? a.p_end - a.p_begin : a.f_end - a.f_begin;
     int64_t blocks = (units + kWaveWarps - 1) / kWaveWarps;
     const int64_t cap = (int64_t)c->num_sms * 6;
     if (blocks > cap) blocks = cap;
@@ -467,9 +470,11 @@ static int launch_wave_t(phn_ctx *c, const WaveArgs &a)
     return PHN_OK;
 }
 
-int launch_wave(phn_ctx *c, const void *d_audio, int64_t f_begin, int64_t f_end)
+int launch_wave(phn_ctx *c, const void *d_audio, int u0, int u1)
 {
-    if (f_end < 0) f_end = c->total_frames;
+    if (u1 < 0) u1 = c->n_utt;
+    if (u1 <= u0) return PHN_OK;
+    const int64_t f_begin = c->h_frame_off[u0], f_end = c->h_frame_off[u1];
     if (f_end <= f_begin) return PHN_OK;
     WaveArgs a;
     a.audio = (const uint8_t *)d_audio;
@@ -478,6 +483,8 @@ int launch_wave(phn_ctx *c, const void *d_audio, int64_t f_begin, int64_t f_end)
     a.n_utt = c->n_utt;
     a.total_frames = c->total_frames;
     a.f_begin = f_begin; a.f_end = f_end;
+    a.pair_off = (const int64_t *)c->d_pair_off.p;
+    a.p_begin = c->h_pair_off[u0]; a.p_end = c->h_pair_off[u1];
     a.fmt = c->fmt; a.vs = c->vs; a.step = c->step; a.N = c->mt.N; a.logN = c->mt.logN; a.nbanks = c->nbanks;
     a.scale = c->scale; a.dc_shift = c->dc_shift; a.frame_shift = c->frame_shift; a.frame_floor = c->frame_floor;
     a.preem = c->preem; a.z_mean = c->z_mean;

@@ -198,3 +198,18 @@ def test_tc_several_mlp_passes_equal_one_pass(recs, monkeypatch):
         assert np.array_equal(x.view(np.uint8), y.view(np.uint8))
     for x, y in zip(post_one, post_many):
         assert np.array_equal(x.view(np.uint32), y.view(np.uint32))
+
+
+def test_tc_fused_path_is_batch_invariant(recs):
+    """audio -> labels of the fast path must not depend on the batch an utterance travels in: frame pairs of the fp32
+    front end never straddle utterances, the sentence mean is a fixed-shape sum, tiles and soft-max rows are per frame.
+    Odd and even frame counts, so that utterances start at odd global frame numbers inside the batch."""
+    r = recs("PHN_CZ_SPDAT_LCRC_N1500")
+    a = audio_bytes("test.raw")
+    utts = [a[:40001 * 2], a[:16161 * 2], a, a[1000:30000], a[:398]]
+    batch = r.recognize(utts)
+    rev = r.recognize(utts[::-1])[::-1]
+    for u, b, v in zip(utts, batch, rev):
+        single = r.recognize([u])[0]
+        assert np.array_equal(single.view(np.uint8), b.view(np.uint8))
+        assert np.array_equal(single.view(np.uint8), v.view(np.uint8))
