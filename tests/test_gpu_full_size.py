@@ -1,0 +1,77 @@
+"""GPU tests at BASELINE.json's full sizes, through size-independent properties of the domain (the oracle needs seconds
+per utterance, so it only checks a sample):
+  * a decoder output covers its utterance in order: the first segment starts at 0, the last one ends at T, segments are
+    non-empty and never overlap (the reference's decoder occasionally leaves a gap of a few frames between two segments
+    -- utterance 49 of the seed below has one at frames 419..422, and the compiled reference, the oracle and both CUDA
+    modes all print it -- so contiguity is NOT a property of the domain);
+  * utterances are independent: a batch equals the same utterances recognised in two halves, bit for bit;
+  * the penalty sweep from saved posteriors is consistent: the multi-penalty call equals single-penalty calls, and a
+    larger (less negative) insertion penalty never yields fewer segments in total."""
+import numpy as np
+import pytest
+
+from conftest import model_dir
+
+import phnrec_b200 as pb
+
+pytestmark = pytest.mark.gpu
+
+
+def tiles(lab, T):
+    if len(lab) == 0:
+        return False
+    s, e = lab["start"].astype(np.int64), lab["end"].astype(np.int64)
+    return s[0] == 0 and e[-1] == T and (s[1:] >= e[:-1]).all() and (e > s).all()
+
+
+def test_config2_cz_1000_utterances_properties(oracle_models):
+    """BASELINE configs[1]: PHN_CZ_SPDAT_LCRC_N1500, 8 kHz A-law, 1000 synthetic 10 s utterances (998 000 frames)."""
+    r = pb.Recognizer(model_dir("PHN_CZ_SPDAT_LCRC_N1500"), device=0)
+    try:
+        r.set_wave_format("alaw")
+        r.set_mlp_mode(pb.MLP_TC_F16)
+        n = 1000
+        a = r.synth_audio(80000, n, seed=2024)
+        utts = [a[i].tobytes() for i in range(n)]
+        full = r.recognize(utts)
+        assert len(full) == n and all(tiles(l, 998) for l in full)
+        halves = r.recognize(utts[:500]) + r.recognize(utts[500:])
+        assert all(np.array_equal(x.view(np.uint8), y.view(np.uint8)) for x, y in zip(full, halves))
+        assert 20 < np.mean([len(l) for l in full]) < 400
+        # a sample against the oracle through the exact mode (bit-identical to the reference by the parity tests)
+        r.set_mlp_mode(pb.MLP_EXACT_FP32)
+        om = oracle_models("PHN_CZ_SPDAT_LCRC_N1500")
+        idx = [0, 49, 999]
+        exact = r.recognize([utts[i] for i in idx])
+        for i, e in zip(idx, exact):
+            want = om.recognize(utts[i], fmt="alaw")
+            assert pb.format_rec(e, r.phonemes) == pb.format_rec(want, om.phonemes)
+            seg = lambda l: {(int(x["start"]), int(x["end"]), int(x["phn"])) for x in l}
+            assert len(seg(full[i]) & seg(e)) >= 0.85 * len(e)      # the fast path on the same utterance
+    finally:
+        r.close()
+
+
+def test_config4_en_penalty_sweep_from_saved_posteriors_properties():
+    """BASELINE configs[3] scaled to 600 utterances (100 min of 16 kHz lin16 audio): posteriors once, then the decoder
+    under 14 insertion penalties from the saved posteriors."""
+    r = pb.Recognizer(model_dir("PHN_EN_TIMIT_LCRC_N500"), device=0)
+    try:
+        r.set_mlp_mode(pb.MLP_TC_F16)
+        n = 600
+        a = r.synth_audio(320000, n, seed=7)                      # 10 s of 16 kHz lin16 = 320 000 bytes -> 998 frames
+        utts = [a[i].tobytes() for i in range(n)]
+        posts = r.posteriors(r.mel(utts))
+        assert all(p.shape == (998, r.n_outputs) for p in posts)
+        pens = [-6.0 + 0.5 * i for i in range(13)] + [r.wpenalty]
+        sweep = r.decode(posts, penalties=pens)
+        assert len(sweep) == 14 and all(len(s) == n for s in sweep)
+        assert all(tiles(l, 998) for s in sweep for l in s)
+        counts = [sum(len(l) for l in s) for s in sweep[:13]]
+        assert all(c1 >= c0 for c0, c1 in zip(counts, counts[1:])), counts   # fewer insertions penalised -> no fewer segments
+        for k in (0, 7, 13):                                               # the sweep equals single-penalty decodes
+            r.set_penalty(pens[k])
+            single = r.decode(posts)
+            assert all(np.array_equal(x.view(np.uint8), y.view(np.uint8)) for x, y in zip(sweep[k], single))
+    finally:
+        r.close()
