@@ -14,6 +14,15 @@ for mode in (pb.MLP_TC_F16, pb.MLP_EXACT_FP32):
     lab = rec.recognize(utts)
     print(mode, [len(l) for l in lab])
 rec.close()
+# 16 kHz lin16 system (512-point FFT, 23 banks: the two-pass filterbank of the fast front end)
+rec = pb.Recognizer('oracle/_ref/models/PHN_EN_TIMIT_LCRC_N500', device=0)
+a = rec.synth_audio(48000, 3, seed=5)
+utts = [a[0].tobytes(), a[1].tobytes()[:9002], a[2].tobytes()[:700]]
+rec.set_mlp_mode(pb.MLP_TC_F16)
+print('EN', [len(l) for l in rec.recognize(utts)])
+rec.close()
 PY
-timeout 900 compute-sanitizer --tool memcheck --error-exitcode 7 python /tmp/san.py > gpurun_out/sanitize_memcheck.log 2>&1; echo "memcheck rc=$?"
+timeout 600 compute-sanitizer --tool memcheck --error-exitcode 7 python /tmp/san.py > gpurun_out/sanitize_memcheck.log 2>&1; echo "memcheck rc=$?"
 tail -8 gpurun_out/sanitize_memcheck.log
+timeout 400 compute-sanitizer --tool racecheck --error-exitcode 7 --kernel-regex kns=k_wave_pair python /tmp/san.py > gpurun_out/sanitize_racecheck_wave.log 2>&1; echo "racecheck rc=$?"
+tail -5 gpurun_out/sanitize_racecheck_wave.log
