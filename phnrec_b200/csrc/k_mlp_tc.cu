@@ -323,6 +323,8 @@ struct TcArgs {
     const uint8_t *w2_img;    // [NCH][2][N2P*128 B]
     const float *b2;          // [N2P]      output bias; -FLT_MAX in the padding columns
     int n_tiles, KB1, NCH, S1, S2;
+    int XR;                   // slots of the X ring: KB1 (the tile's blocks, reloaded in place) or KB1 + 1 (one spare slot: the
+                              // next tile's first block is already there when the last layer-1 chunk of this tile ends)
     int nks_last;             // k-steps (of 16) actually needed in the last k-block of layer 1
     int64_t nf;               // frames in this launch
     int nout;
@@ -416,8 +418,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs a)
     extern __shared__ uint8_t smem_raw[];
     // carve-up (all block bases 1024-byte aligned: the swizzle pattern is a function of the address)
     uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    uint8_t *sX = smem;                                        // KB1 x 16 KB
-    uint8_t *sW1 = sX + (size_t)a.KB1 * TC_BLK;                // S1 x 16 KB ring
+    uint8_t *sX = smem;                                        // XR x 16 KB: block k of the CTA's tile i sits in slot (i KB1 + k) mod XR
+    uint8_t *sW1 = sX + (size_t)a.XR * TC_BLK;                 // S1 x 16 KB ring
     uint8_t *sW2 = sW1 + (size_t)a.S1 * W1_ST;                 // S2 x W2_ST ring
     float *s_b2 = reinterpret_cast<float *>(sW2 + (size_t)a.S2 * W2_ST);    // [N2P]
     float *s_mm = s_b2 + N2P;                                  // [N2P] merger input mean  (band nets)
@@ -501,14 +503,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs a)
         int kb1 = 0, kb2 = 0;             // next k-block inside the current chunk
         int c1 = 0, c2 = 0;
         int xt = 0, xk = 0, xtile = tile0;   // X cursor: tile iteration, k-block, global tile
+        int xs = 0; uint32_t xwrap = 0;      //           ring slot of that block and how often the ring has wrapped (= uses of the slot so far)
         while (n1 < (uint32_t)G || n2 < (uint32_t)G || xt < my_tiles) {
-            if (xt < my_tiles && (xt == 0 || mbar_try(&x_empty[xk], (uint32_t)(xt - 1) & 1u))) {
+            if (xt < my_tiles && (xwrap == 0 || mbar_try(&x_empty[xs], (xwrap - 1) & 1u))) {
                 if (elect_one()) {
                     // (PAIR: the odd CTA of the last pair may own a tile past the end; it multiplies the last real tile again
                     // and writes nothing)
                     const int xsrc = xtile < a.n_tiles ? xtile : a.n_tiles - 1;
-                    mbar_expect_tx(&x_full[xk], TC_BLK);
-                    tma_load_1d(sX + (size_t)xk * TC_BLK, a.x_img + ((size_t)xsrc * a.KB1 + xk) * TC_BLK, TC_BLK, &x_full[xk]);
+                    mbar_expect_tx(&x_full[xs], TC_BLK);
+                    tma_load_1d(sX + (size_t)xs * TC_BLK, a.x_img + ((size_t)xsrc * a.KB1 + xk) * TC_BLK, TC_BLK, &x_full[xs]);
                     // the CTA's next tile goes to L2 now: when its turn comes (one tile time from here) the
                     // load that sits between two tiles' MMAs is an L2 hit
                     if (xk == 0 && xtile + tstep < a.n_tiles)
@@ -516,6 +519,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs a)
                 }
                 __syncwarp();
                 if (++xk == a.KB1) { xk = 0; ++xt; xtile += tstep; }
+                if (++xs == a.XR) { xs = 0; ++xwrap; }
             }
             if (n1 < (uint32_t)G && mbar_try(&w1_empty[w1_stage], ph_w1 ^ 1)) {
                 if (elect_one()) {
@@ -562,7 +566,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs a)
         const int my_tiles = n_my;
         const int G = my_tiles * a.NCH;
         const bool chunk_bar = a.S1 >= a.KB1;   // the W1 ring holds a whole chunk: one "full" barrier per chunk (PAIR: always)
-        uint32_t st = 0, ph_w1 = 0, ph_x_full = 0;
+        uint32_t st = 0, ph_w1 = 0;
+        int xs0 = 0; uint32_t xw0 = 0;          // ring slot of the current tile's block 0, wrap count of the ring at that block
         int c1 = 0, tile = tile0;               // (tile: only for the debug timeline)
         const bool leader = elect_one();
         if (PAIR && rank != 0) {
@@ -572,12 +577,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs a)
             for (int g = 0; g < G; ++g) {
                 mbar_wait(&w1c_full[g & 3], (uint32_t)(g >> 2) & 1u);
                 if (c1 == 0) {
-                    for (int k = 0; k < a.KB1; ++k) mbar_wait(&x_full[k], ph_x_full);
-                    ph_x_full ^= 1;
+                    int s = xs0; uint32_t w = xw0;
+                    for (int k = 0; k < a.KB1; ++k) {
+                        mbar_wait(&x_full[s], w & 1u);
+                        if (++s == a.XR) { s = 0; ++w; }
+                    }
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive_cluster(&pw1_full[g & 3], 0);
-                if (++c1 == a.NCH) c1 = 0;
+                if (++c1 == a.NCH) {
+                    c1 = 0;
+                    xs0 += a.KB1;
+                    if (xs0 >= a.XR) { xs0 -= a.XR; ++xw0; }
+                }
             }
         } else
 #pragma unroll 1
@@ -590,14 +602,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs a)
             if (PAIR) mbar_wait_cluster(&pw1_full[g & 3], (uint32_t)(g >> 2) & 1u);
             if (lane == 0) TC_DBG(3, c1);   // accumulator + weights there
             tc_fence_after();
-            uint32_t alo = xlo;
+            int xs = xs0; uint32_t xw = xw0;
+            uint32_t alo = xlo + (uint32_t)xs0 * (TC_BLK >> 4);
 #pragma unroll 1
             for (int k = 0; k < a.KB1; ++k) {   // (kept rolled: a small loop body stays in the SMSP's instruction cache)
                 if (!chunk_bar) mbar_wait(&w1_full[st], ph_w1);
-                if (opens) mbar_wait(&x_full[k], ph_x_full);
+                if (opens) mbar_wait(&x_full[xs], xw & 1u);
                 if (!chunk_bar || opens) tc_fence_after();
                 const uint32_t blo = w1lo + st * (W1_ST >> 4);
-                const uint32_t bw1 = bar_w1e + st * 8u, bxe = bar_xe + (uint32_t)k * 8u;
+                const uint32_t bw1 = bar_w1e + st * 8u, bxe = bar_xe + (uint32_t)xs * 8u;
                 if (leader) {
                     if (PAIR) {
                         if (k == 0) umma2_ss_lo<0>(td1, alo, xhi, blo, idesc1); else umma2_ss_lo<1>(td1, alo, xhi, blo, idesc1);
@@ -628,12 +641,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs a)
                 __syncwarp();
                 if (++st == (uint32_t)a.S1) { st = 0; ph_w1 ^= 1; }
                 alo += TC_BLK >> 4;
+                if (++xs == a.XR) { xs = 0; ++xw; alo = xlo; }
             }
             if (leader) { if (PAIR) tc_commit2_u(bar_d1f + (uint32_t)(g & 1) * 8u); else tc_commit_u(bar_d1f + (uint32_t)(g & 1) * 8u); }
             __syncwarp();
             if (lane == 0) TC_DBG(4, c1);   // issued
-            if (opens) ph_x_full ^= 1;
-            if (++c1 == a.NCH) { c1 = 0; tile += tstep; }
+            if (++c1 == a.NCH) {
+                c1 = 0; tile += tstep;
+                xs0 += a.KB1;
+                if (xs0 >= a.XR) { xs0 -= a.XR; ++xw0; }
+            }
         }
     } else if (warp == WARP_MMA2) {
         // ===================================================================== MMA issuer, layer 2
@@ -1058,7 +1075,12 @@ static int run_net_tc(phn_ctx *c, int which, const uint8_t *x_img, int64_t nf, i
     if (const char *e = getenv("PHNREC_TC_PAIR")) pair = pair && atoi(e) != 0;
     const size_t w1_blk = pair ? TC_BLK / 2 : TC_BLK;
     const size_t w2_blk = (size_t)im.N2P * 128 / (pair ? 2 : 1);
-    const size_t fixed = (size_t)im.KB1 * TC_BLK + sizeof(float) * (3 * (size_t)im.N2P + 8 * 128) + 112 * 8 + 1024;
+    // X ring: a spare slot where it is cheap (narrow nets: 16 KB out of >= 3 chunks of weight ring), none for the merger,
+    // whose ring is short already.  PHNREC_TC_XSPARE=0/1 overrides (kernel development).
+    int xspare = pair && im.KB1 <= 3;
+    if (const char *e = getenv("PHNREC_TC_XSPARE")) xspare = atoi(e) != 0 && im.KB1 < 8;
+    a.XR = im.KB1 + (xspare ? 1 : 0);
+    const size_t fixed = (size_t)a.XR * TC_BLK + sizeof(float) * (3 * (size_t)im.N2P + 8 * 128) + 112 * 8 + 1024;
     const size_t max_smem = 232448;
     // Ring plan.  Both weight streams want two chunks resident (the one being multiplied and the one in flight):
     // W2 ring 4 stages, W1 ring 2 KB1 stages.  When that does not fit (wide merger next to its wide X tile), W2
