@@ -1,6 +1,7 @@
 // capi.cu — the C ABI (include/phnrec_b200.h): context lifetime, batch planning, stage sequencing
 // on one CUDA stream, host<->device copies.  No computation happens on the host.
 #include "internal.h"
+#include <chrono>
 
 #include <cmath>
 #include <cstdarg>
@@ -702,13 +703,22 @@ int phn_recognize(phn_ctx *c, const void *audio, const int64_t *byte_off, int n_
     if (!c || !byte_off || (!audio && n_utt > 0 && byte_off[n_utt] > 0)) return PHN_ERR_ARG;
     PHN_CUDA(c, cudaSetDevice(c->device));
     int rc;
+    const bool trace = getenv("PHNREC_TRACE") != nullptr;
+    auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double tt0 = now();
+    cudaEvent_t tev[4];
+    if (trace) for (auto &e : tev) cudaEventCreate(&e);
     if ((rc = ensure(c, c->d_audio, (size_t)byte_off[n_utt] + 16))) return rc;
     reset_timing(c);
     if ((rc = plan_audio(c, byte_off, n_utt))) return rc;
+    const double tt1 = now();
+    if (trace) cudaEventRecord(tev[0], c->stream);
     // The audio goes up in groups of whole utterances on a copy stream; K-wave of group g starts as soon as the
     // group has landed and runs under the copy of group g+1, so only the first group's transfer is exposed.
     const int64_t total = byte_off[n_utt];
-    int ng = (int)(total / ((int64_t)8 << 20));
+    int64_t group_mb = 8;
+    if (const char *e = getenv("PHNREC_COPY_GROUP_MB")) group_mb = atoll(e) > 0 ? atoll(e) : group_mb;   // (kernel development)
+    int ng = (int)(total / (group_mb << 20));
     ng = ng < 1 ? 1 : (ng > 16 ? 16 : ng);
     // When the batch is one pass of the tensor-core MLP, the sentence mean and the STC features of a group follow its
     // K-wave at once, so the whole front end runs under the copy and the MLP starts when the last group has landed.
@@ -745,9 +755,26 @@ int phn_recognize(phn_ctx *c, const void *audio, const int64_t *byte_off, int n_
             u0 = u1;
         }
     }
+    const double tt2 = now();
+    if (trace) cudaEventRecord(tev[1], c->stream);
     if ((rc = recognize_after_wave(c, front))) return rc;
+    const double tt3 = now();
+    if (trace) { cudaEventRecord(tev[2], c->stream); cudaStreamSynchronize(c->stream); }
+    const double tt4 = now();
     if (frame_off_out) memcpy(frame_off_out, c->h_frame_off.data(), sizeof(int64_t) * (n_utt + 1));
-    return phn_fetch_labels(c, labels, label_cap, label_off);
+    rc = phn_fetch_labels(c, labels, label_cap, label_off);
+    const double tt5 = now();
+    if (trace) {
+        float e01 = 0, e12 = 0, ec = 0;
+        cudaEventElapsedTime(&e01, tev[0], tev[1]); cudaEventElapsedTime(&e12, tev[1], tev[2]);
+        (void)ng;
+        FILE *tf = fopen(getenv("PHNREC_TRACE"), "a");
+        if (tf) fprintf(tf, "[trace] n_utt %d host: plan %.3f enqueue-front %.3f enqueue-rest %.3f wait-gpu %.3f fetch %.3f total %.3f | gpu: front-end span %.3f (last copy landed at %.3f) mlp+vit %.3f\n",
+                n_utt, tt1 - tt0, tt2 - tt1, tt3 - tt2, tt4 - tt3, tt5 - tt4, tt5 - tt0, e01, ec, e12);
+        if (tf) fclose(tf);
+        for (auto &e : tev) cudaEventDestroy(e);
+    }
+    return rc;
 }
 
 // Debug aid (not part of the stable ABI surface used by the reference binding): the next tensor-core launches of
