@@ -215,11 +215,24 @@ def run_reference(args, rank, world):
             "cpu_baseline": {"value": value, "unit": "xRT", "cores": cores, "kind": kind,
                              "sample": f"{per_step} utterances x 10 s per step, {cores} phnrec processes"},
             "e2e": {"value": value, "unit": "xRT", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_OUT, flush=True)
 
 
 # ------------------------------------------------------------------------------------------ GPU arm
+_OUT = sys.stdout
+
+
+def _one_line_stdout():
+    """stdout carries exactly ONE line, the JSON result: everything else a library may print there (NCCL's version
+    banner under torchrun, for instance) goes to stderr."""
+    global _OUT
+    sys.stdout.flush()
+    _OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
 def main():
+    _one_line_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -386,7 +399,7 @@ def main():
             line["cpu_baseline"] = {"value": v, "unit": "xRT", "cores": cores, "kind": kind,
                                     "sample": f"{n_cpu} of the same synthetic utterances ({n_cpu * 10} s audio), {cores} single-threaded "
                                               f"phnrec processes, {dt:.1f} s wall"}
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=_OUT, flush=True)
 
     rec._L.phn_host_free_pinned(h_audio)
     rec.device_free(d_audio)
