@@ -1,7 +1,7 @@
 # K-wave build variants (blocks per SM / warps per block), timed through bench.py's kernel_ms
 mkdir -p gpurun_out
 cd phnrec_b200/csrc
-for v in "4 4" "5 4" "3 4" "2 8"; do
+for v in "4 4" "5 4" "6 4" "3 8" "10 2"; do
   set -- $v
   /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC,-ffp-contract=off,-Wall -Xptxas -v --fmad=false -DPHN_PAIR_MINB=$1 -DPHN_PAIR_WARPS=$2 -c k_wave.cu -o build/k_wave.o 2> /tmp/ptx.log || { tail -5 /tmp/ptx.log; continue; }
   grep -A2 "Compiling.*k_wave_pairILi8ELb1" /tmp/ptx.log | grep -E "Used|spill" | tr '\n' ' '
