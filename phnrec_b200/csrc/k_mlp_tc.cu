@@ -342,12 +342,12 @@ struct TcArgs {
 // debug timeline: dbg[(c * 16 + event)] = clock64() for chunk c of CTA 0's second tile
 #define TC_DBG(ev, c)                                                                       \
     do {                                                                                    \
-        if (a.dbg && blockIdx.x == 0 && tile == tile0 + tstep) a.dbg[(c) * 16 + (ev)] = clock64(); \
+        if (DBG && a.dbg && blockIdx.x == 0 && tile == tile0 + tstep) a.dbg[(c) * 16 + (ev)] = clock64(); \
     } while (0)
 // E2 stage events of that tile go to row 15: 0 A begins (waits for D2), 1 D2 seen, 2 A done, 3 B begins, 4 B done, 5 C begins, 6 C done
 #define TC_DBG2(ev)                                                                                                   \
     do {                                                                                                              \
-        if (a.dbg && blockIdx.x == 0 && threadIdx.x == 0 && e2_tile == tile0 + tstep) a.dbg[15 * 16 + (ev)] = clock64(); \
+        if (DBG && a.dbg && blockIdx.x == 0 && threadIdx.x == 0 && e2_tile == tile0 + tstep) a.dbg[15 * 16 + (ev)] = clock64(); \
     } while (0)
 constexpr int TC_MAXS1 = 24;                        // upper bound on W1 ring stages (barrier array size)
 constexpr int TC_MAXS2 = 8;                         // ... W2 ring stages (4 chunks)
@@ -400,7 +400,8 @@ __device__ __forceinline__ void band_out(const float (&o)[NQ], float lg2_sc, con
 // which is what bounds the single-CTA kernel.  CTA 0 of the pair issues every MMA; its completion signals are
 // multicast to both CTAs; CTA 1's issuer warps only relay "my operands have landed" to CTA 0, and its epilogue warps
 // arrive on CTA 0's barriers.  Everything else (producer, epilogues) is per CTA and unchanged.
-template <int N2P, bool XMN, bool PAIR>
+// DBG: the instantiation with the clock64() timeline hooks (tools/tc_timeline.py); the product kernels carry none.
+template <int N2P, bool XMN, bool PAIR, bool DBG>
 __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs a)
 {
     constexpr int W2_BLK = N2P * 128;       // bytes of one [N2P rows x 64 fp16] block of the weight image
@@ -1021,18 +1022,25 @@ void mlp_tc_release(phn_ctx *c)
     c->tc = nullptr;
 }
 
-template <int N2P, bool XMN, bool PAIR>
-static int launch_inst(phn_ctx *c, const TcArgs &a, size_t smem_bytes, int grid)
+template <int N2P, bool XMN, bool PAIR, bool DBG>
+static int launch_inst_k(phn_ctx *c, const TcArgs &a, size_t smem_bytes, int grid)
 {
-    PHN_CUDA(c, cudaFuncSetAttribute(k_mlp_tc<N2P, XMN, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+    PHN_CUDA(c, cudaFuncSetAttribute(k_mlp_tc<N2P, XMN, PAIR, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = smem_bytes; cfg.stream = c->stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = PAIR ? 2 : 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    PHN_CUDA(c, cudaLaunchKernelEx(&cfg, k_mlp_tc<N2P, XMN, PAIR>, a));
+    PHN_CUDA(c, cudaLaunchKernelEx(&cfg, k_mlp_tc<N2P, XMN, PAIR, DBG>, a));
     return PHN_OK;
+}
+
+template <int N2P, bool XMN, bool PAIR>
+static int launch_inst(phn_ctx *c, const TcArgs &a, size_t smem_bytes, int grid)
+{
+    // (the timeline instantiation only when tools/tc_timeline.py asked for one on this net)
+    return a.dbg ? launch_inst_k<N2P, XMN, PAIR, true>(c, a, smem_bytes, grid) : launch_inst_k<N2P, XMN, PAIR, false>(c, a, smem_bytes, grid);
 }
 
 template <int N2P>
