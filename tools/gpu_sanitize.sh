@@ -26,3 +26,6 @@ timeout 600 compute-sanitizer --tool memcheck --error-exitcode 7 python /tmp/san
 tail -8 gpurun_out/sanitize_memcheck.log
 timeout 400 compute-sanitizer --tool racecheck --error-exitcode 7 --kernel-regex kns=k_wave_pair python /tmp/san.py > gpurun_out/sanitize_racecheck_wave.log 2>&1; echo "racecheck rc=$?"
 tail -5 gpurun_out/sanitize_racecheck_wave.log
+# the same batch with one CTA pair for all tiles: several tiles per CTA, so the activation ring of the MLP kernel wraps
+PHNREC_TC_GRID=2 timeout 600 compute-sanitizer --tool memcheck --error-exitcode 7 python /tmp/san.py > gpurun_out/sanitize_memcheck_grid2.log 2>&1; echo "memcheck (one pair) rc=$?"
+tail -6 gpurun_out/sanitize_memcheck_grid2.log
