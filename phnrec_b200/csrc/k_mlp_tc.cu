@@ -441,6 +441,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs a)
     uint64_t *pw1_full = d1_empty + 2;       // [4] PAIR, CTA 0: the peer's layer-1 operands of chunk n have landed (n & 3)
     uint64_t *pw2_full = pw1_full + 4;       // [4] PAIR, CTA 0: the peer's layer-2 weights of chunk n have landed (n & 3)
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(pw2_full + 4);
+    volatile int *s_par = reinterpret_cast<volatile int *>(bars + 100);   // [8] loop bounds for the issuer warps (see there)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr int WARP_TMA = TC_EPI_WARPS, WARP_MMA1 = TC_EPI_WARPS + 1, WARP_MMA2 = TC_EPI_WARPS + 2, EPI0 = 0;
@@ -458,6 +459,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs a)
         for (int i = 0; i < 4; ++i) mbar_init(&pw1_full[i], 1);
         for (int i = 0; i < 4; ++i) mbar_init(&pw2_full[i], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        s_par[0] = a.KB1; s_par[1] = a.XR; s_par[2] = a.S1; s_par[3] = a.NCH; s_par[4] = a.nks_last; s_par[5] = a.S2;
     }
     if (warp == WARP_MMA1) {  // TMEM: 512 columns = D1 double buffer 2 x 128 | D2 up to 192 | H 64 (128 fp16 per lane)
         if (PAIR) {
@@ -564,9 +566,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs a)
         const uint64_t dW1 = make_sw128_desc(smem_u32(sW1));
         const uint32_t xlo = (uint32_t)dX, xhi = (uint32_t)(dX >> 32), w1lo = (uint32_t)dW1;
         const uint32_t bar_w1e = smem_u32(w1_empty), bar_xe = smem_u32(x_empty), bar_d1f = smem_u32(d1_full);
+        // (loop bounds read once through volatile shared memory, which pins them in registers: kernel parameters are
+        // re-read from the constant bank inside the issuing loop, and every such load is a dependent stall between two
+        // MMAs of the warp that feeds the tensor pipe)
+        const int p_kb1 = s_par[0], p_xr = s_par[1], p_s1 = s_par[2], p_nch = s_par[3], p_nksl = s_par[4];
         const int my_tiles = n_my;
-        const int G = my_tiles * a.NCH;
-        const bool chunk_bar = a.S1 >= a.KB1;   // the W1 ring holds a whole chunk: one "full" barrier per chunk (PAIR: always)
+        const int G = my_tiles * p_nch;
+        const bool chunk_bar = p_s1 >= p_kb1;   // the W1 ring holds a whole chunk: one "full" barrier per chunk (PAIR: always)
         uint32_t st = 0, ph_w1 = 0;
         int xs0 = 0; uint32_t xw0 = 0;          // ring slot of the current tile's block 0, wrap count of the ring at that block
         int c1 = 0, tile = tile0;               // (tile: only for the debug timeline)
@@ -579,34 +585,36 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs a)
                 mbar_wait(&w1c_full[g & 3], (uint32_t)(g >> 2) & 1u);
                 if (c1 == 0) {
                     int s = xs0; uint32_t w = xw0;
-                    for (int k = 0; k < a.KB1; ++k) {
+                    for (int k = 0; k < p_kb1; ++k) {
                         mbar_wait(&x_full[s], w & 1u);
-                        if (++s == a.XR) { s = 0; ++w; }
+                        if (++s == p_xr) { s = 0; ++w; }
                     }
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive_cluster(&pw1_full[g & 3], 0);
-                if (++c1 == a.NCH) {
+                if (++c1 == p_nch) {
                     c1 = 0;
-                    xs0 += a.KB1;
-                    if (xs0 >= a.XR) { xs0 -= a.XR; ++xw0; }
+                    xs0 += p_kb1;
+                    if (xs0 >= p_xr) { xs0 -= p_xr; ++xw0; }
                 }
             }
         } else
 #pragma unroll 1
         for (int g = 0; g < G; ++g) {
-            const bool opens = c1 == 0, closes = c1 == a.NCH - 1;
+            const bool opens = c1 == 0, closes = c1 == p_nch - 1;
             const uint32_t td1 = (g & 1) ? tmem + 128u : tmem;
             if (lane == 0) TC_DBG(2, c1);   // layer 1 of chunk c1: begins
-            if (g >= 2) { if (PAIR) mbar_wait_cluster(&d1_empty[g & 1], (uint32_t)((g >> 1) - 1) & 1u); else mbar_wait(&d1_empty[g & 1], (uint32_t)((g >> 1) - 1) & 1u); }
+            // (the weights are normally there long before the accumulator buffer is handed back: the barrier that really gates
+            // the chunk is waited for last, so nothing stands between its completion and the first MMA)
             if (chunk_bar) mbar_wait(&w1c_full[g & 3], (uint32_t)(g >> 2) & 1u);
             if (PAIR) mbar_wait_cluster(&pw1_full[g & 3], (uint32_t)(g >> 2) & 1u);
+            if (g >= 2) { if (PAIR) mbar_wait_cluster(&d1_empty[g & 1], (uint32_t)((g >> 1) - 1) & 1u); else mbar_wait(&d1_empty[g & 1], (uint32_t)((g >> 1) - 1) & 1u); }
             if (lane == 0) TC_DBG(3, c1);   // accumulator + weights there
             tc_fence_after();
             int xs = xs0; uint32_t xw = xw0;
             uint32_t alo = xlo + (uint32_t)xs0 * (TC_BLK >> 4);
 #pragma unroll 1
-            for (int k = 0; k < a.KB1; ++k) {   // (kept rolled: a small loop body stays in the SMSP's instruction cache)
+            for (int k = 0; k < p_kb1; ++k) {   // (kept rolled: a small loop body stays in the SMSP's instruction cache)
                 if (!chunk_bar) mbar_wait(&w1_full[st], ph_w1);
                 if (opens) mbar_wait(&x_full[xs], xw & 1u);
                 if (!chunk_bar || opens) tc_fence_after();
@@ -615,42 +623,42 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs a)
                 if (leader) {
                     if (PAIR) {
                         if (k == 0) umma2_ss_lo<0>(td1, alo, xhi, blo, idesc1); else umma2_ss_lo<1>(td1, alo, xhi, blo, idesc1);
-                        if (k < a.KB1 - 1 || a.nks_last == 4) {
+                        if (k < p_kb1 - 1 || p_nksl == 4) {
                             umma2_ss_lo<1>(td1, alo + akst, xhi, blo + 2, idesc1);
                             umma2_ss_lo<1>(td1, alo + 2 * akst, xhi, blo + 4, idesc1);
                             umma2_ss_lo<1>(td1, alo + 3 * akst, xhi, blo + 6, idesc1);
                         } else {
-                            if (a.nks_last > 1) umma2_ss_lo<1>(td1, alo + akst, xhi, blo + 2, idesc1);
-                            if (a.nks_last > 2) umma2_ss_lo<1>(td1, alo + 2 * akst, xhi, blo + 4, idesc1);
+                            if (p_nksl > 1) umma2_ss_lo<1>(td1, alo + akst, xhi, blo + 2, idesc1);
+                            if (p_nksl > 2) umma2_ss_lo<1>(td1, alo + 2 * akst, xhi, blo + 4, idesc1);
                         }
                         tc_commit2_u(bw1);
                         if (closes) tc_commit2_u(bxe);
                     } else {
                         if (k == 0) umma_ss_lo<0>(td1, alo, xhi, blo, idesc1); else umma_ss_lo<1>(td1, alo, xhi, blo, idesc1);
-                        if (k < a.KB1 - 1 || a.nks_last == 4) {
+                        if (k < p_kb1 - 1 || p_nksl == 4) {
                             umma_ss_lo<1>(td1, alo + akst, xhi, blo + 2, idesc1);
                             umma_ss_lo<1>(td1, alo + 2 * akst, xhi, blo + 4, idesc1);
                             umma_ss_lo<1>(td1, alo + 3 * akst, xhi, blo + 6, idesc1);
                         } else {
-                            if (a.nks_last > 1) umma_ss_lo<1>(td1, alo + akst, xhi, blo + 2, idesc1);
-                            if (a.nks_last > 2) umma_ss_lo<1>(td1, alo + 2 * akst, xhi, blo + 4, idesc1);
+                            if (p_nksl > 1) umma_ss_lo<1>(td1, alo + akst, xhi, blo + 2, idesc1);
+                            if (p_nksl > 2) umma_ss_lo<1>(td1, alo + 2 * akst, xhi, blo + 4, idesc1);
                         }
                         tc_commit_u(bw1);
                         if (closes) tc_commit_u(bxe);
                     }
                 }
                 __syncwarp();
-                if (++st == (uint32_t)a.S1) { st = 0; ph_w1 ^= 1; }
+                if (++st == (uint32_t)p_s1) { st = 0; ph_w1 ^= 1; }
                 alo += TC_BLK >> 4;
-                if (++xs == a.XR) { xs = 0; ++xw; alo = xlo; }
+                if (++xs == p_xr) { xs = 0; ++xw; alo = xlo; }
             }
             if (leader) { if (PAIR) tc_commit2_u(bar_d1f + (uint32_t)(g & 1) * 8u); else tc_commit_u(bar_d1f + (uint32_t)(g & 1) * 8u); }
             __syncwarp();
             if (lane == 0) TC_DBG(4, c1);   // issued
-            if (++c1 == a.NCH) {
+            if (++c1 == p_nch) {
                 c1 = 0; tile += tstep;
-                xs0 += a.KB1;
-                if (xs0 >= a.XR) { xs0 -= a.XR; ++xw0; }
+                xs0 += p_kb1;
+                if (xs0 >= p_xr) { xs0 -= p_xr; ++xw0; }
             }
         }
     } else if (warp == WARP_MMA2) {
@@ -660,8 +668,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs a)
         constexpr uint32_t idesc2 = make_idesc(N2P, false, PAIR ? 2 * TC_M : TC_M);
         const uint32_t w2lo = (uint32_t)make_sw128_desc(smem_u32(sW2));
         const uint32_t bar_w2e = smem_u32(w2_empty), bar_he = smem_u32(h_empty), bar_d2f = smem_u32(d2_full);
+        const int p_s2 = s_par[5], p_nch = s_par[3];
         const int my_tiles = n_my;
-        const int G = my_tiles * a.NCH;
+        const int G = my_tiles * p_nch;
         uint32_t w2s = 0, ph_d2_empty = 0;
         int c2 = 0, tile = tile0;
         const bool leader = elect_one();
@@ -705,15 +714,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs a)
                     }
                 }
                 __syncwarp();
-                if (++w2s == (uint32_t)a.S2) w2s = 0;
+                if (++w2s == (uint32_t)p_s2) w2s = 0;
             }
             if (leader) {
-                if (PAIR) { tc_commit2_u(bar_he); if (c2 == a.NCH - 1) tc_commit2_u(bar_d2f); }
-                else      { tc_commit_u(bar_he);  if (c2 == a.NCH - 1) tc_commit_u(bar_d2f); }
+                if (PAIR) { tc_commit2_u(bar_he); if (c2 == p_nch - 1) tc_commit2_u(bar_d2f); }
+                else      { tc_commit_u(bar_he);  if (c2 == p_nch - 1) tc_commit_u(bar_d2f); }
             }
             __syncwarp();
             if (lane == 0) TC_DBG(7, c2);   // issued
-            if (++c2 == a.NCH) { c2 = 0; tile += tstep; }
+            if (++c2 == p_nch) { c2 = 0; tile += tstep; }
         }
     } else {
         // ===================================================================== epilogue warps
