@@ -34,6 +34,7 @@
 #include "device_math.cuh"
 
 #include <cfloat>
+#include <type_traits>
 #include <cstdlib>
 
 namespace phn {
@@ -572,7 +573,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs a)
         const int p_kb1 = s_par[0], p_xr = s_par[1], p_s1 = s_par[2], p_nch = s_par[3], p_nksl = s_par[4];
         const int my_tiles = n_my;
         const int G = my_tiles * p_nch;
-        const bool chunk_bar = p_s1 >= p_kb1;   // the W1 ring holds a whole chunk: one "full" barrier per chunk (PAIR: always)
+        const bool chunk_bar = PAIR || p_s1 >= p_kb1;   // the W1 ring holds a whole chunk: one "full" barrier per chunk (PAIR: always, the host plan guarantees it)
         uint32_t st = 0, ph_w1 = 0;
         int xs0 = 0; uint32_t xw0 = 0;          // ring slot of the current tile's block 0, wrap count of the ring at that block
         int c1 = 0, tile = tile0;               // (tile: only for the debug timeline)
@@ -613,6 +614,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs a)
             tc_fence_after();
             int xs = xs0; uint32_t xw = xw0;
             uint32_t alo = xlo + (uint32_t)xs0 * (TC_BLK >> 4);
+            // The k-block loop exists in four instances (chunk opens / closes a tile or not, compile-time): the steady-state
+            // one - ten chunks out of twelve - contains no barrier wait and no conditional commit.
+            auto kloop = [&](auto opens_c, auto closes_c) {
+            constexpr bool opens = decltype(opens_c)::value, closes = decltype(closes_c)::value;
 #pragma unroll 1
             for (int k = 0; k < p_kb1; ++k) {   // (kept rolled: a small loop body stays in the SMSP's instruction cache)
                 if (!chunk_bar) mbar_wait(&w1_full[st], ph_w1);
@@ -652,6 +657,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs a)
                 alo += TC_BLK >> 4;
                 if (++xs == p_xr) { xs = 0; ++xw; alo = xlo; }
             }
+            };
+            using T_ = std::true_type; using F_ = std::false_type;
+            if (opens) { if (closes) kloop(T_{}, T_{}); else kloop(T_{}, F_{}); }
+            else       { if (closes) kloop(F_{}, T_{}); else kloop(F_{}, F_{}); }
             if (leader) { if (PAIR) tc_commit2_u(bar_d1f + (uint32_t)(g & 1) * 8u); else tc_commit_u(bar_d1f + (uint32_t)(g & 1) * 8u); }
             __syncwarp();
             if (lane == 0) TC_DBG(4, c1);   // issued
