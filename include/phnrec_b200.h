@@ -163,9 +163,17 @@ int phn_last_timing(phn_ctx *ctx, float ms[PHN_K_COUNT], int64_t launches[PHN_K_
  * (0/1 band nets, 2 merger) for the following calls; which < 0 disarms and copies the 16 x 16 table out. */
 int phn_debug_tc_timeline(phn_ctx *ctx, int which, long long *out);
 
+/* Verification aid: logf as the device computes it (port of glibc 2.39 logf, the libm function behind the reference's
+ * SoftLog srec.h:192-195 and sLn dspc.h:155-160) on the n consecutive float bit patterns starting at first_bits. */
+int phn_debug_logf(phn_ctx *ctx, uint32_t first_bits, int64_t n, float *out);
+
 /* N2: online normaliser arithmetic (Normalization::ProcessFrame, norm.cpp:216-234;
  * ChannelNormParams::{Accum,Update,Norm}, norm.cpp:92-148) on a [frames][nbanks] host
- * matrix, in place on the device: estimate over the first `interval` frames, apply after. */
+ * matrix, in place on the device: sums over the first `interval` frames; the frame that
+ * completes the estimate (index interval-1) and every later one get `x -= mean` (mean_norm)
+ * then `x *= invstd` (var_norm); earlier frames pass through (mean 0, inverse std 1).
+ * var_norm without mean_norm -> PHN_ERR_ARG (the reference asserts, norm.cpp:150-155).
+ * Pinned to the reference's own object by oracle/_ref/online_ref (tests/golden/ref_online_norm.npz). */
 int phn_online_norm(phn_ctx *ctx, float *x, int64_t frames, int nbanks, int interval, int mean_norm, int var_norm);
 
 /* ASCII model files -> the binary .nbin cache (host only, no GPU needed): NeuralNet::LoadAscii + SaveBinary

@@ -302,6 +302,12 @@ void orc_sentence_mean_norm(float *mel, int T, int nb)
  * offline hot path never calls it (srec.cpp:806 is ProcessOnline only). */
 void orc_online_norm(float *x, int T, int nb, int interval, int mean_norm, int var_norm)
 {
+    /* ProcessFrame (norm.cpp:216-234) per frame: Accum while fewer than `interval` frames were seen
+     * (norm.cpp:92-110); Update() the moment the count reaches `interval` (norm.cpp:139-148) - BEFORE Norm(), so the
+     * frame that completes the estimate (index interval-1) is already normalised with it; Norm() on every frame
+     * (norm.cpp:112-137): `if(mean) x -= mean; if(var) x *= invstd;`.  Until the estimate exists the parameters are
+     * Null()'s mean 0 / inverse std 1 (norm.cpp:59-70), i.e. the earlier frames pass through unchanged.
+     * SetNorm asserts that var_norm implies mean_norm (norm.cpp:150-155); callers reject that combination. */
     if (interval <= 0 || T < interval) return;
     for (int b = 0; b < nb; ++b) {
         float s = 0.0f, s2 = 0.0f;
@@ -312,11 +318,10 @@ void orc_online_norm(float *x, int T, int nb, int interval, int mean_norm, int v
         }
         float mean = s / (float)interval;
         float inv = 1.0f / sqrtf(s2 / (float)interval - mean * mean);
-        for (int t = interval; t < T; ++t) {
+        for (int t = interval - 1; t < T; ++t) {
             float v = x[(size_t)t * nb + b];
-            if (mean_norm || var_norm) v -= mean;
+            if (mean_norm) v -= mean;
             if (var_norm) v *= inv;
-            if (var_norm && !mean_norm) v += mean;
             x[(size_t)t * nb + b] = v;
         }
     }

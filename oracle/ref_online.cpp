@@ -1,0 +1,114 @@
+// ref_online.cpp — a small DRIVER over the reference's own objects (TEST INFRASTRUCTURE ONLY).
+//
+// The reference reaches its online path (SpeechRec::ProcessOnline, srec.cpp:793-927; Normalization::ProcessFrame,
+// norm.cpp:216-234) only from a sound card (RunLive, srec.cpp:1438-1490).  This driver feeds FILES through the very
+// same objects so that their output can pin the restatement in oracle/phn_oracle.c and the CUDA streaming path.
+// It contains no reference code: it only calls the reference's public classes, compiled where they lie under
+// /root/reference by oracle/Makefile (target `ref`), and is linked with those objects into oracle/_ref/online_ref.
+//
+//   online_ref norm  <in.f32> <rows> <cols> <interval> <mean 0|1> <var 0|1> <out.f32>
+//        Normalization::{StartEstimation, SetMeanNorm, SetVarNorm, ProcessFrame} row by row over a raw float32 matrix.
+//   online_ref stream <config_dir> <audio> <block_bytes> <lin16|alaw> <penalty|-> <out.rec>
+//        SpeechRec::Init + PhnDec::Init(out.rec) + ProcessOnline in blocks of <block_bytes> (last block flagged), Done.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+#include <unistd.h>
+
+#include <cstdarg>
+
+#include "srec.h"
+#include "norm.h"
+
+// Linked with -Wl,--wrap=sprintf (oracle/Makefile): Normalization::Save (norm.cpp:339,353) prints " %e" into a char[10];
+// for that format at most 9 characters are stored, every other call is the plain sprintf.
+extern "C" int __wrap_sprintf(char *dst, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    int n;
+    if (!strcmp(fmt, " %e")) {
+        char tmp[64];
+        n = vsnprintf(tmp, sizeof tmp, fmt, ap);
+        strncpy(dst, tmp, 9);
+        dst[9] = 0;
+    } else {
+        n = vsprintf(dst, fmt, ap);
+    }
+    va_end(ap);
+    return n;
+}
+
+static int run_norm(int argc, char **argv)
+{
+    if (argc != 9) return 2;
+    const int rows = atoi(argv[3]), cols = atoi(argv[4]), interval = atoi(argv[5]);
+    const bool mean = atoi(argv[6]) != 0, var = atoi(argv[7]) != 0;
+    std::vector<float> m((size_t)rows * cols);
+    FILE *f = fopen(argv[2], "rb");
+    if (!f || fread(m.data(), sizeof(float), m.size(), f) != m.size()) return 3;
+    fclose(f);
+    FILE *fo = fopen(argv[8], "wb");   // (opened before the chdir below: the path may be relative)
+    if (!fo) return 5;
+    // (Normalization::Save writes its XML to the configured file name when the estimate completes - default "none",
+    // norm.cpp:216-234,309; run from a scratch directory so that side effect lands there)
+    char tmpl[] = "/tmp/online_ref.XXXXXX";
+    const char *td = mkdtemp(tmpl);
+    if (!td || chdir(td) != 0) return 4;
+    {
+        Normalization N;
+        if (interval != 0) N.StartEstimation(interval);   // srec.cpp:594-601
+        N.SetSignalEstimEnd(false);
+        N.SetMeanNorm(mean);
+        N.SetVarNorm(var);
+        N.SetScaleToGVar(false);
+        for (int r = 0; r < rows; ++r) N.ProcessFrame(cols, m.data() + (size_t)r * cols);
+    }
+    unlink("none");
+    rmdir(td);
+    if (fwrite(m.data(), sizeof(float), m.size(), fo) != m.size()) return 5;
+    fclose(fo);
+    return 0;
+}
+
+static int run_stream(int argc, char **argv)
+{
+    if (argc != 8) return 2;
+    SpeechRec SR;
+    char cfg[2048];
+    snprintf(cfg, sizeof cfg, "%s/config", argv[2]);
+    if (!SR.Init(cfg)) return 3;
+    if (strcmp(argv[6], "-") != 0) SR.DE->SetWPenalty((float)atof(argv[6]));   // phnrec.cpp:212-221
+    const SpeechRec::wave_format wf = SR.Str2WaveFormat(argv[5]);
+    if (wf == SpeechRec::wfUnknown) return 4;
+    SR.SetWaveFormat(wf);
+    void *wave = 0;
+    int nbytes = 0;
+    if (!SR.LoadWaveform(argv[3], &wave, &nbytes)) return 5;
+    const int block = atoi(argv[4]);
+    if (block <= 0) return 6;
+    // what RunLive does around ProcessOnline (srec.cpp:1438-1490): reset the streaming objects, open the decoder
+    SR.MB.Reset();
+    SR.TR.Reset();
+    SR.ResetBunchBuff();
+    if (SR.DE->Init(argv[7]) != DECERR_NONE) return 7;
+    int pos = 0;
+    do {
+        const int n = nbytes - pos < block ? nbytes - pos : block;
+        const bool last = pos + n >= nbytes;
+        if (!SR.ProcessOnline((char *)wave + pos, n, last)) return 8;
+        pos += n;
+    } while (pos < nbytes);
+    SR.DE->Done();
+    free(wave);
+    return 0;
+}
+
+int main(int argc, char **argv)
+{
+    if (argc >= 2 && !strcmp(argv[1], "norm")) return run_norm(argc, argv);
+    if (argc >= 2 && !strcmp(argv[1], "stream")) return run_stream(argc, argv);
+    fprintf(stderr, "usage: online_ref norm|stream ...\n");
+    return 2;
+}

@@ -90,6 +90,7 @@ _SYMS = [
     ("phn_last_timing", C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int64)]),
     ("phn_online_norm", C.c_int, [C.c_void_p, _f32p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int]),
     ("phn_debug_tc_timeline", C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    ("phn_debug_logf", C.c_int, [C.c_void_p, C.c_uint32, C.c_int64, _f32p]),
     ("phn_version", C.c_char_p, []),
     ("phn_device_count", C.c_int, []),
 ]
@@ -297,6 +298,12 @@ class Recognizer:
         finally:
             self.device_free(d)
         return out.reshape(n_utt, bytes_per_utt)
+
+    def debug_logf(self, first_bits: int, n: int) -> np.ndarray:
+        """The device's logf on the n consecutive float bit patterns from first_bits (verification aid)."""
+        out = np.zeros(n, dtype=np.float32)
+        self._ck(self._L.phn_debug_logf(self._h, int(first_bits), int(n), out))
+        return out
 
     def online_norm(self, x: np.ndarray, interval: int, mean_norm: bool, var_norm: bool) -> np.ndarray:
         y = np.array(x, dtype=np.float32, copy=True, order="C")

@@ -86,7 +86,8 @@ static int64_t frames_of(const phn_ctx *c, int64_t nbytes)
 // ---- batch planning: offsets + device buffers for `n_pen` decoder passes
 static int plan_frames(phn_ctx *c, const int64_t *frame_off, int n_utt, int n_pen)
 {
-    if (n_utt < 0 || n_pen < 1) return fail(c, PHN_ERR_ARG, "invalid batch\n");
+    if (n_utt < 0 || n_pen < 1 || !frame_off) return fail(c, PHN_ERR_ARG, "invalid batch\n");
+    c->post_valid = 0; c->logp_valid = 0;   // (whatever an earlier batch left in d_post / d_logp is not this batch's)
     c->n_utt = n_utt; c->n_pen = n_pen;
     c->h_frame_off.assign(frame_off, frame_off + n_utt + 1);
     if (c->h_frame_off[0] != 0) return fail(c, PHN_ERR_ARG, "offsets must start at 0\n");
@@ -650,11 +651,13 @@ int phn_fetch_labels(phn_ctx *c, phn_label *labels, int64_t label_cap, int64_t *
 
 int phn_mel(phn_ctx *c, const void *audio, const int64_t *byte_off, int n_utt, float *mel_out, int64_t *frame_off)
 {
-    if (!c || !byte_off || (!audio && n_utt > 0 && byte_off[n_utt] > 0)) return PHN_ERR_ARG;
+    if (!c) return PHN_ERR_ARG;
+    if (!byte_off || n_utt < 0) return fail(c, PHN_ERR_ARG, "invalid batch\n");
     PHN_CUDA(c, cudaSetDevice(c->device));
     reset_timing(c);
     int rc;
     if ((rc = plan_audio(c, byte_off, n_utt))) return rc;
+    if (!audio && mel_out && c->total_bytes > 0) return fail(c, PHN_ERR_ARG, "null audio buffer\n");
     if (frame_off) memcpy(frame_off, c->h_frame_off.data(), sizeof(int64_t) * (n_utt + 1));
     if (!mel_out) return PHN_OK;
     if ((rc = ensure(c, c->d_audio, (size_t)c->total_bytes + 16))) return rc;
@@ -700,17 +703,25 @@ int phn_decode(phn_ctx *c, const float *post, const int64_t *frame_off, int n_ut
 int phn_recognize(phn_ctx *c, const void *audio, const int64_t *byte_off, int n_utt, phn_label *labels, int64_t label_cap,
                   int64_t *label_off, int64_t *frame_off_out)
 {
-    if (!c || !byte_off || (!audio && n_utt > 0 && byte_off[n_utt] > 0)) return PHN_ERR_ARG;
+    if (!c) return PHN_ERR_ARG;
+    if (!byte_off || n_utt < 0) return fail(c, PHN_ERR_ARG, "invalid batch\n");
     PHN_CUDA(c, cudaSetDevice(c->device));
     int rc;
     const bool trace = getenv("PHNREC_TRACE") != nullptr;
     auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     const double tt0 = now();
-    cudaEvent_t tev[4];
-    if (trace) for (auto &e : tev) cudaEventCreate(&e);
-    if ((rc = ensure(c, c->d_audio, (size_t)byte_off[n_utt] + 16))) return rc;
+    struct TraceEvents {   // (destroyed on every exit path)
+        cudaEvent_t e[4] = {nullptr, nullptr, nullptr, nullptr};
+        bool on;
+        explicit TraceEvents(bool on_) : on(on_) { if (on) for (auto &x : e) cudaEventCreate(&x); }
+        ~TraceEvents() { if (on) for (auto &x : e) if (x) cudaEventDestroy(x); }
+    } tev_holder(trace);
+    cudaEvent_t *tev = tev_holder.e;
     reset_timing(c);
+    // offsets are validated (start at 0, non-decreasing) before anything is sized by them or read through them
     if ((rc = plan_audio(c, byte_off, n_utt))) return rc;
+    if (!audio && c->total_bytes > 0) return fail(c, PHN_ERR_ARG, "null audio buffer\n");
+    if ((rc = ensure(c, c->d_audio, (size_t)c->total_bytes + 16))) return rc;
     const double tt1 = now();
     if (trace) cudaEventRecord(tev[0], c->stream);
     // The audio goes up in groups of whole utterances on a copy stream; K-wave of group g starts as soon as the
@@ -772,7 +783,6 @@ int phn_recognize(phn_ctx *c, const void *audio, const int64_t *byte_off, int n_
         if (tf) fprintf(tf, "[trace] n_utt %d host: plan %.3f enqueue-front %.3f enqueue-rest %.3f wait-gpu %.3f fetch %.3f total %.3f | gpu: front-end span %.3f (last copy landed at %.3f) mlp+vit %.3f\n",
                 n_utt, tt1 - tt0, tt2 - tt1, tt3 - tt2, tt4 - tt3, tt5 - tt4, tt5 - tt0, e01, ec, e12);
         if (tf) fclose(tf);
-        for (auto &e : tev) cudaEventDestroy(e);
     }
     return rc;
 }
@@ -794,6 +804,24 @@ int phn_debug_tc_timeline(phn_ctx *c, int which, long long *out /*[256]*/)
     PHN_CUDA(c, cudaMemcpyAsync(out, c->tc_dbg, 256 * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
     PHN_CUDA(c, cudaStreamSynchronize(c->stream));
     return PHN_OK;
+}
+
+// Verification aid: the device's logf (the glibc port every ln on the exact path goes through) on the n consecutive float
+// bit patterns starting at first_bits.
+int phn_debug_logf(phn_ctx *c, uint32_t first_bits, int64_t n, float *out)
+{
+    if (!c || !out || n < 0) return PHN_ERR_ARG;
+    PHN_CUDA(c, cudaSetDevice(c->device));
+    int rc;
+    phn_ctx::Buf tmp;
+    if ((rc = ensure(c, tmp, sizeof(float) * (size_t)n))) return rc;
+    rc = launch_logf_range(c, first_bits, n, (float *)tmp.p);
+    if (rc == PHN_OK && n) {
+        cudaMemcpyAsync(out, tmp.p, sizeof(float) * (size_t)n, cudaMemcpyDeviceToHost, c->stream);
+        if (cudaStreamSynchronize(c->stream) != cudaSuccess) rc = fail(c, PHN_ERR_CUDA, "CUDA failure in phn_debug_logf\n");
+    }
+    cudaFree(tmp.p);
+    return rc;
 }
 
 int phn_online_norm(phn_ctx *c, float *x, int64_t frames, int nbanks, int interval, int mean_norm, int var_norm)

@@ -19,9 +19,19 @@ int HostNet::load(const std::string &path)
     int32_t hdr[4];
     if (fread(hdr, sizeof(int32_t), 4, f) != 4) { fclose(f); return PHN_ERR_NN_FILE; }
     if (hdr[0] != 2 || hdr[1] <= 0 || hdr[2] <= 0 || hdr[3] <= 0) { fclose(f); return PHN_ERR_NN_FORMAT; }
+    // the header is not trusted beyond what the file can hold (a corrupt size must not turn into a huge allocation)
+    if (hdr[1] > (1 << 20) || hdr[2] > (1 << 20) || hdr[3] > (1 << 20)) { fclose(f); return PHN_ERR_NN_FORMAT; }
     nin = hdr[1]; nhid = hdr[2]; nout = hdr[3];
     auto up4 = [](int n) { return (n + 3) / 4 * 4; };
     nin4 = up4(nin); nhid4 = up4(nhid); nout4 = up4(nout);
+    {
+        const long at = ftell(f);
+        fseek(f, 0, SEEK_END);
+        const long fsize = ftell(f);
+        fseek(f, at, SEEK_SET);
+        const unsigned long long need = 4ull * ((unsigned long long)nhid4 * nin4 + (unsigned long long)nout4 * nhid4 + nhid4 + nout4 + 2ull * nin4);
+        if (at < 0 || fsize < 0 || (unsigned long long)(fsize - at) < need) { fclose(f); return PHN_ERR_NN_FILE; }   // NN_READERR: truncated
+    }
     struct { std::vector<float> *v; size_t n; } parts[] = {
         {&w1, (size_t)nhid4 * nin4}, {&w2, (size_t)nout4 * nhid4}, {&b1, (size_t)nhid4},
         {&b2, (size_t)nout4},        {&mean, (size_t)nin4},        {&dev, (size_t)nin4}};

@@ -141,6 +141,7 @@ int launch_mlp_exact(phn_ctx *c, int64_t f0, int64_t nf);                  // k_
 int launch_mlp_tc(phn_ctx *c, int64_t f0, int64_t nf);                     // k_mlp_tc.cu
 int launch_viterbi(phn_ctx *c, const float *d_pen, int n_pen);             // k_vit.cu
 int launch_compact_labels(phn_ctx *c, int nseg);                           // k_vit.cu
+int launch_logf_range(phn_ctx *c, uint32_t first_bits, int64_t n, float *d_out);   // k_vit.cu (verification aid)
 int launch_synth(phn_ctx *c, void *d_audio, int64_t bytes_per_utt, int n_utt, uint64_t seed);  // k_synth.cu
 int mlp_tc_fill_merger_bias(phn_ctx *c, int64_t rows);                     // constant-1 bias columns of the merger image
 int mlp_tc_prepare(phn_ctx *c);                                            // fp16 weight images (k_mlp_tc.cu)

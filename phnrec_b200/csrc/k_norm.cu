@@ -79,6 +79,10 @@ int launch_sentence_mean(phn_ctx *c, int u0, int u1)
     return PHN_OK;
 }
 
+// One thread per band, frames in order: the estimator's sums are the reference's sequential fp32 sums.
+// Normalization::ProcessFrame (norm.cpp:216-234): Accum for the first `interval` frames, Update() when the count reaches
+// `interval` - before Norm(), so frame interval-1 is the first one normalised - then `if(mean) x -= mean; if(var) x *= inv`
+// (ChannelNormParams::Norm, norm.cpp:112-137).  Earlier frames see Null()'s mean 0 / inverse std 1: unchanged.
 __global__ void k_online_norm(float *x, int64_t T, int nb, int interval, int mean_norm, int var_norm)
 {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -91,17 +95,18 @@ __global__ void k_online_norm(float *x, int64_t T, int nb, int interval, int mea
     }
     const float mean = __fdiv_rn(s, (float)interval);
     const float inv = __fdiv_rn(1.0f, __fsqrt_rn(__fsub_rn(__fdiv_rn(s2, (float)interval), __fmul_rn(mean, mean))));
-    for (int64_t t = interval; t < T; ++t) {
+    for (int64_t t = interval - 1; t < T; ++t) {
         float v = x[t * nb + b];
-        if (mean_norm || var_norm) v = __fsub_rn(v, mean);
+        if (mean_norm) v = __fsub_rn(v, mean);
         if (var_norm) v = __fmul_rn(v, inv);
-        if (var_norm && !mean_norm) v = __fadd_rn(v, mean);
         x[t * nb + b] = v;
     }
 }
 
 int launch_online_norm(phn_ctx *c, float *d_x, int64_t frames, int nb, int interval, int mean_norm, int var_norm)
 {
+    // ChannelNormParams::SetNorm (norm.cpp:150-155) asserts that variance normalisation comes with mean normalisation
+    if (var_norm && !mean_norm) return fail(c, PHN_ERR_ARG, "online normalisation: var_norm without mean_norm (the reference asserts, norm.cpp:152)\n");
     if (interval <= 0 || frames < interval) return PHN_OK;
     k_online_norm<<<(nb + 31) / 32, 32, 0, c->stream>>>(d_x, frames, nb, interval, mean_norm, var_norm);
     PHN_CUDA(c, cudaGetLastError());

@@ -63,6 +63,25 @@ __global__ void __launch_bounds__(256) k_log_post(const float *__restrict__ post
         for (int cidx = lane; cidx < ncols; cidx += 32) logp[f * ldp + cidx] = logf_glibc(post[f * ldp + cidx], s_logtab);
 }
 
+// Verification aid (phn_debug_logf): the device logf over a run of consecutive float bit patterns, so that a test can compare
+// it with the host's libm over every float in (0, 1].
+__global__ void __launch_bounds__(256) k_logf_range(uint32_t first_bits, int64_t n, float *__restrict__ out)
+{
+    __shared__ double s_logtab[32];
+    logf_table_to_smem(s_logtab, threadIdx.x, blockDim.x);
+    __syncthreads();
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = logf_glibc(__uint_as_float(first_bits + (uint32_t)i), s_logtab);
+}
+
+int launch_logf_range(phn_ctx *c, uint32_t first_bits, int64_t n, float *d_out)
+{
+    if (n <= 0) return PHN_OK;
+    k_logf_range<<<c->num_sms * 8, 256, 0, c->stream>>>(first_bits, n, d_out);
+    PHN_CUDA(c, cudaGetLastError());
+    return PHN_OK;
+}
+
 template <int PPL, bool TILED>
 __global__ void __launch_bounds__(32) k_viterbi(VitArgs a)
 {
@@ -326,10 +345,13 @@ int launch_viterbi(phn_ctx *c, const float *d_pen, int n_pen)
     const int ppl = (c->P + 31) / 32;
     const bool tiled = c->logp_valid != 0;   // ln p came from the tensor-core merger's epilogue (tiled layout)
     const size_t vsmem = sizeof(float) * 48 * (size_t)((3 * c->P) | 1);
+    // (the panel ring of the tiled form exceeds the 48 KB default from 86 phonemes on)
 #define PHN_VIT(N)                                                          \
     do {                                                                    \
-        if (tiled) k_viterbi<N, true><<<nseg, 32, vsmem, c->stream>>>(a);   \
-        else k_viterbi<N, false><<<nseg, 32, 0, c->stream>>>(a);            \
+        if (tiled) {                                                        \
+            PHN_CUDA(c, cudaFuncSetAttribute(k_viterbi<N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vsmem)); \
+            k_viterbi<N, true><<<nseg, 32, vsmem, c->stream>>>(a);          \
+        } else k_viterbi<N, false><<<nseg, 32, 0, c->stream>>>(a);          \
     } while (0)
     switch (ppl) {
         case 1: PHN_VIT(1); break;

@@ -70,3 +70,51 @@ def oracle_models(orc):
             cache[name] = orc.Model(model_dir(name))
         return cache[name]
     return get
+
+
+def patch_config(text: str, edits: dict) -> str:
+    """`edits` = {"section/variable": "value"}: replace the variable's line inside its [section], or add it right behind
+    the section header (a new section is appended)."""
+    lines = text.splitlines()
+    for key, val in edits.items():
+        sec, var = key.split("/")
+        out, in_sec, done, seen_sec = [], False, False, False
+        for ln in lines:
+            st = ln.strip()
+            if st.startswith("["):
+                if in_sec and not done:
+                    out.append(f"{var}={val}")
+                    done = True
+                in_sec = st == f"[{sec}]"
+                seen_sec = seen_sec or in_sec
+            elif in_sec and not done and st.split("=")[0].strip() == var:
+                ln = f"{var}={val}"
+                done = True
+            out.append(ln)
+        if not done:
+            if not (in_sec and seen_sec):
+                out.append(f"[{sec}]")
+            out.append(f"{var}={val}")
+        lines = out
+    return "\n".join(lines) + "\n"
+
+
+def variant_model_dir(tmp_path, name: str, edits: dict) -> Path:
+    """A copy of a staged model directory (weights, windows, dictionary symlinked) whose config carries `edits`."""
+    src = model_dir(name)
+    dst = Path(tmp_path) / (name + "_variant")
+    dst.mkdir(parents=True, exist_ok=True)
+    for sub in ("weights", "windows", "dicts", "norms"):
+        if (src / sub).exists() and not (dst / sub).exists():
+            (dst / sub).symlink_to(src / sub)
+    (dst / "config").write_text(patch_config((src / "config").read_text(), edits))
+    return dst
+
+
+def front_end_variants():
+    """Fixture tests/golden/ref_front_variants.npz: the reference binary on edited copies of shipped model directories
+    (srec.cpp:780-788 dc_shift / scale, melbanks.cpp:111-149 z_mean_source / preem_coef, srec.cpp:1594-1620 framenorm)."""
+    z = np.load(GOLDEN / "ref_front_variants.npz")
+    meta = json.loads(str(z["meta"]))
+    for i, m in enumerate(meta):
+        yield m["name"], m["model"], m["audio"], m["nbytes"], m["edits"], z[f"mel{i}"], str(z[f"rec{i}"])

@@ -10,6 +10,12 @@ Outputs
                     start/end frame, phoneme, printed score) + which model/audio
                     produced each.
   ref_vad.json      .rec output of the reference's `vadalize` tool (oracle/_ref/vadalize_ref) on three model/audio pairs.
+  ref_online_norm.npz  Normalization::ProcessFrame (norm.cpp:216-234) run row by row over random matrices by
+                    oracle/_ref/online_ref (oracle/ref_online.cpp linked with the reference's own norm.o):
+                    inputs, (interval, mean_norm, var_norm) cases and the outputs.
+  ref_front_variants.npz  oracle/_ref/phnrec_ref on EDITED copies of shipped model directories: the optional front-end
+                    arithmetic no shipped config switches on (source/dc_shift, source/scale, melbanks/z_mean_source,
+                    melbanks/preem_coef, framenorm/shift, framenorm/min_floor): `-t par` mel + the .rec text.
   ref_run_*.npz     outputs of oracle/_ref/phnrec_ref on the reference's own test
                     audio: un-normalised log-mel (`-t par`), linear posteriors
                     (`-t post`, float32, full matrix for CZ / EN, every 8th row for
@@ -60,6 +66,51 @@ def main():
                             "-o", str(out)], check=True, capture_output=True)
             vad[f"{model}/{audio}"] = out.read_text()
     (OUT / "ref_vad.json").write_text(json.dumps(vad, indent=1))
+
+    # the online normaliser (row N2): the reference's own Normalization object, driven by oracle/_ref/online_ref
+    online_ref = orc.REF_BIN.parent / "online_ref"
+    rng = np.random.default_rng(2)
+    norm = {}
+    with tempfile.TemporaryDirectory() as td:
+        td = Path(td)
+        for cols in (15, 23):
+            x = (rng.standard_normal((300, cols)) * 3 + 11).astype(np.float32)
+            x[7] = 0.0                                        # a frame of digital silence (ln energy 0)
+            norm[f"x{cols}"] = x
+            x.tofile(td / "in.f32")
+            for interval, mean, var in ((100, 1, 0), (100, 1, 1), (100, 0, 0), (1, 1, 0), (300, 1, 1), (301, 1, 1), (0, 1, 1), (5, 1, 1)):
+                subprocess.run([str(online_ref), "norm", str(td / "in.f32"), "300", str(cols), str(interval), str(mean), str(var),
+                                str(td / "out.f32")], check=True, capture_output=True)
+                norm[f"y{cols}_{interval}_{mean}_{var}"] = np.fromfile(td / "out.f32", dtype=np.float32).reshape(300, cols)
+    np.savez_compressed(OUT / "ref_online_norm.npz", **norm)
+    print("ref_online_norm.npz", len(norm), "arrays")
+
+    # optional front-end arithmetic (srec.cpp:780-788, 1594-1620; melbanks.cpp:111-149) on edited model directories
+    sys.path.insert(0, str(ROOT / "tests"))
+    from conftest import variant_model_dir  # noqa: E402
+    variants = [
+        ("dc_scale", "PHN_CZ_SPDAT_LCRC_N1500", {"source/dc_shift": "-37.5", "source/scale": "0.5"}),
+        ("preem", "PHN_CZ_SPDAT_LCRC_N1500", {"melbanks/preem_coef": "0.97"}),
+        ("zmean", "PHN_CZ_SPDAT_LCRC_N1500", {"melbanks/z_mean_source": "true"}),
+        ("framenorm", "PHN_CZ_SPDAT_LCRC_N1500", {"framenorm/shift": "1.25", "framenorm/min_floor": "12.5"}),
+        ("all_cz", "PHN_CZ_SPDAT_LCRC_N1500", {"source/dc_shift": "11", "source/scale": "1.5", "melbanks/preem_coef": "0.95",
+                                               "melbanks/z_mean_source": "true", "framenorm/shift": "-0.5", "framenorm/min_floor": "9"}),
+        ("en_zmean_preem", "PHN_EN_TIMIT_LCRC_N500", {"melbanks/z_mean_source": "true", "melbanks/preem_coef": "0.9"}),
+    ]
+    fv, meta = {}, []
+    with tempfile.TemporaryDirectory() as td:
+        td = Path(td)
+        nbytes = 48000
+        (td / "a.raw").write_bytes((orc.REF_AUDIO / "test.raw").read_bytes()[:nbytes])
+        for i, (name, model, edits) in enumerate(variants):
+            cfg = variant_model_dir(td / name, model, edits)
+            orc.run_ref(["-c", cfg, "-t", "par", "-i", td / "a.raw", "-o", td / "o.par"])
+            orc.run_ref(["-c", cfg, "-i", td / "a.raw", "-o", td / "o.rec"])
+            fv[f"mel{i}"] = orc.read_htk(td / "o.par")
+            fv[f"rec{i}"] = np.array((td / "o.rec").read_text())
+            meta.append({"name": name, "model": model, "audio": "test.raw", "nbytes": nbytes, "edits": edits})
+            print("variant", name, fv[f"mel{i}"].shape, len(str(fv[f"rec{i}"]).splitlines()), "labels")
+    np.savez_compressed(OUT / "ref_front_variants.npz", meta=np.array(json.dumps(meta)), **fv)
 
     runs = sorted({(m, a) for _, m, a, _ in GOLDENS})
     with tempfile.TemporaryDirectory() as td:

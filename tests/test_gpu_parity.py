@@ -206,13 +206,81 @@ def test_batch_equals_singletons_and_is_order_independent(recs):
         assert labels_equal(a, c) and labels_equal(b, c)
 
 
-def test_online_norm_arithmetic(recs, orc):
+def test_optional_front_end_arithmetic_equals_reference_binary(tmp_path, oracle_models):
+    """dc_shift / scale (srec.cpp:780-788), z_mean_source / preem_coef (melbanks.cpp:111-149), framenorm shift / min_floor
+    (srec.cpp:1594-1620): the CUDA path on an edited copy of the model directory against what the reference binary made of
+    the same directory (tests/golden/ref_front_variants.npz) - mel bit-identical, .rec text identical; and the fast
+    (tensor-core pipeline) front end stays within its stated bound of the exact one under the same switches."""
+    from conftest import front_end_variants, variant_model_dir
+    for name, model, audio, nbytes, edits, mel, rec in front_end_variants():
+        a = audio_bytes(audio)[:nbytes]
+        r = pb.Recognizer(variant_model_dir(tmp_path / name, model, edits), device=0)
+        try:
+            got = r.mel([a])[0]
+            assert_bits_equal(got, mel, f"mel, variant {name}")
+            assert pb.format_rec(r.recognize([a])[0], r.phonemes) == rec, name
+            r.set_mlp_mode(pb.MLP_TC_F16)
+            r.recognize([a])
+            fast = r.fetch_mel(mel.shape[0])
+            assert np.abs(fast - mel).max() <= 1e-3, (name, np.abs(fast - mel).max())
+        finally:
+            r.close()
+
+
+def test_batch_arguments_are_validated_before_use(recs):
+    """A negative utterance count, offsets that do not start at 0 or decrease, a null audio pointer: PHN_ERR_ARG, nothing is
+    read through them (capi.cu: plan_audio runs before any buffer is sized or dereferenced)."""
     r = recs("PHN_CZ_SPDAT_LCRC_N1500")
-    x = np.random.default_rng(2).standard_normal((300, 15)).astype(np.float32) * 3 + 11
-    for mn, vn in ((True, False), (True, True), (False, True)):
-        want = x.copy()
-        orc.lib().orc_online_norm(want, 300, 15, 100, int(mn), int(vn))
-        assert_bits_equal(r.online_norm(x, 100, mn, vn), want, f"online norm {mn} {vn}")
+    a = np.frombuffer(audio_bytes("test.raw"), dtype=np.uint8)[:20000].copy()
+    labels = np.zeros(400, dtype=pb.LABEL_DTYPE)
+    loff = np.zeros(3, dtype=np.int64)
+    for boff, n in ((np.array([0, 20000], np.int64), -1), (np.array([4, 20000], np.int64), 1),
+                    (np.array([0, 20000, 10000], np.int64), 2)):
+        assert r._L.phn_recognize(r._h, a.ctypes.data, boff, n, labels.ctypes.data, 400, loff, None) == 31
+    assert r._L.phn_recognize(r._h, None, np.array([0, 20000], np.int64), 1, labels.ctypes.data, 400, loff, None) == 31
+    # and the context is still usable
+    assert len(r.recognize([a.tobytes()])[0]) > 3
+
+
+def test_device_logf_equals_glibc_on_every_float_up_to_one(recs, orc):
+    """the device logf (glibc port, device_math.cuh) against the host's libm logf on EVERY float in (0, 1] -
+    all 1 065 353 216 bit patterns 0x00000001 .. 0x3F800000, subnormals included - plus zero, one-and-above samples,
+    infinity and NaN.  Bit-exact: the decoder's scores are sums of these values."""
+    r = recs("PHN_CZ_SPDAT_LCRC_N1500")
+    first, last = 0x00000001, 0x3F800000
+    step = 1 << 26
+    bad = 0
+    for lo in range(first, last + 1, step):
+        n = min(step, last + 1 - lo)
+        got = r.debug_logf(lo, n)
+        want = np.arange(lo, lo + n, dtype=np.uint32).view(np.float32).copy()
+        orc.lib().orc_log_inplace(want, want.size)
+        bad += int((got.view(np.uint32) != want.view(np.uint32)).sum())
+    assert bad == 0
+    for lo in (0x00000000, 0x3F800001, 0x40000000, 0x7F7FFFF0, 0x7F800000):     # 0, just above 1, 2.0, near FLT_MAX, +inf
+        got = r.debug_logf(lo, 16)
+        want = np.arange(lo, lo + 16, dtype=np.uint32).view(np.float32).copy()
+        orc.lib().orc_log_inplace(want, want.size)
+        nan = np.isnan(want)
+        assert np.array_equal(np.isnan(got), nan)
+        assert np.array_equal(got.view(np.uint32)[~nan], want.view(np.uint32)[~nan])
+
+
+def test_online_norm_equals_reference_object(recs, orc):
+    """Row N2: phn_online_norm against the outputs of the reference's own Normalization object (fixture made by
+    oracle/_ref/online_ref, tests/golden/ref_online_norm.npz) and against the oracle; var_norm without mean_norm is the
+    reference's assert (norm.cpp:150-155) -> PHN_ERR_ARG."""
+    from test_oracle_pinned import online_norm_cases
+    r = recs("PHN_CZ_SPDAT_LCRC_N1500")
+    for cols, interval, mean, var, x, want in online_norm_cases():
+        got = r.online_norm(x, interval, bool(mean), bool(var))
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), (cols, interval, mean, var)
+        chk = x.copy()
+        orc.lib().orc_online_norm(chk, chk.shape[0], cols, interval, mean, var)
+        assert np.array_equal(got.view(np.uint32), chk.view(np.uint32))
+    with pytest.raises(pb.PhnRecError) as e:
+        r.online_norm(np.ones((10, 15), np.float32), 5, False, True)
+    assert e.value.code == 31
 
 
 def test_capacity_error_reports_needed_size(recs):

@@ -86,6 +86,48 @@ def test_stc_clamp_equals_fifo(orc):
         assert np.array_equal(ctx, want)
 
 
+def test_optional_front_end_arithmetic_equals_reference_binary(orc, tmp_path):
+    """Rows W2 / M2 / M3 with the switches no shipped config sets: dc_shift, scale (srec.cpp:780-788), z_mean_source,
+    preem_coef (melbanks.cpp:111-149), framenorm shift / min_floor (srec.cpp:1594-1620).  The oracle on an edited copy of
+    the model directory reproduces, bit for bit, what the reference binary made of the same directory (fixture)."""
+    from conftest import front_end_variants, variant_model_dir, ref_run
+    n = 0
+    for name, model, audio, nbytes, edits, mel, rec in front_end_variants():
+        a = audio_bytes(audio)[:nbytes]
+        m = orc.Model(variant_model_dir(tmp_path / name, model, edits))
+        got = m.mel(a)
+        assert np.array_equal(got.view(np.uint32), mel.view(np.uint32)), name
+        assert orc.format_rec(m.recognize(a), m.phonemes) == rec, name
+        base = np.asarray(ref_run(model, audio)["mel"])[:mel.shape[0]]
+        assert not np.array_equal(base, mel), name      # the switch really changed the features
+        m.close()
+        n += 1
+    assert n == 6
+
+
+def online_norm_cases():
+    """(cols, interval, mean, var, input, reference output) from tests/golden/ref_online_norm.npz: what the reference's own
+    Normalization object (norm.cpp, driven by oracle/_ref/online_ref) made of each input."""
+    from conftest import GOLDEN
+    z = np.load(GOLDEN / "ref_online_norm.npz")
+    for k in z.files:
+        if k.startswith("y"):
+            cols, interval, mean, var = (int(v) for v in k[1:].split("_"))
+            yield cols, interval, mean, var, z[f"x{cols}"], z[k]
+
+
+def test_online_norm_restatement_equals_reference_object(orc):
+    """Row N2 pinned: orc_online_norm == Normalization::ProcessFrame (norm.cpp:216-234) bit for bit, including the frame
+    that completes the estimate (normalised already), estimates that never complete, and NaN/inf from a zero variance."""
+    n = 0
+    for cols, interval, mean, var, x, want in online_norm_cases():
+        got = x.copy()
+        orc.lib().orc_online_norm(got, got.shape[0], cols, interval, mean, var)
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), (cols, interval, mean, var)
+        n += 1
+    assert n >= 16
+
+
 def test_logf_port_equals_glibc(orc):
     # the device logf is a port of orc_logf_port; here: port == libm over a strided sweep of (0, 1]
     bad = orc.lib().orc_logf_port_mismatches(0x00000001, 0x3F800001, 997)
