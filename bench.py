@@ -1,16 +1,18 @@
 #!/usr/bin/env python3
 """bench.py — audio-seconds per second (xRT) of the PhnRec recognition hot path on B200.
 
-Workload (BASELINE.json configs[1], per GPU): PHN_CZ_SPDAT_LCRC_N1500, 8 kHz A-law, 1000 synthetic
-10 s utterances.  A step is one pass of the whole path (wave -> mel -> STC -> 3 MLPs -> Viterbi ->
-labels) over that batch.  N > 1: one process per GPU (torchrun), every rank runs its own 1000
-utterances, no data-path collective (utterances are independent) -> weak scaling.
+Default workload = BASELINE.json configs[1], per GPU: PHN_CZ_SPDAT_LCRC_N1500, 8 kHz A-law, 1000 synthetic 10 s
+utterances.  A step is one pass of the whole path (wave -> mel -> STC -> 3 MLPs -> Viterbi -> labels) over that batch.
+N > 1: one process per GPU (torchrun), every rank runs its own 1000 utterances, no data-path collective (utterances are
+independent) -> weak scaling.
 
   value : inputs resident in HBM when the timed region starts, labels left on the device
-  e2e   : the reference-facing C-ABI call phn_recognize() with HOST buffers (pinned audio in,
-          label arrays out), H2D and D2H copies inside the timed region
-  --impl reference : the reference's own CPU implementation (oracle/_ref/phnrec_ref, the
-          reference sources compiled by oracle/Makefile) on all host cores, bounded sample.
+  e2e   : the reference-facing C-ABI call (phn_recognize / phn_decode) with HOST buffers (pinned audio in, label arrays
+          out), H2D and D2H copies inside the timed region
+  --config cz|hu|ru|en : the other shipped systems (BASELINE configs[2], [3]) on the same kind of batch
+  --config en_sweep    : BASELINE configs[3], the 14-penalty decode from saved posteriors (srec.cpp:1080-1104 with -p)
+  --impl reference     : the reference's own CPU implementation (oracle/_ref/phnrec_ref*, the reference sources compiled
+                         by oracle/Makefile) on all host cores, bounded sample of the same utterances.
 """
 import argparse
 import json
@@ -28,23 +30,31 @@ import numpy as np
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
-MODEL = "PHN_CZ_SPDAT_LCRC_N1500"
-FS = 8000
 UTT_SECONDS = 10.0
-BYTES_PER_UTT = 80000           # 10 s of 8 kHz A-law
-FRAMES_PER_UTT = 998            # (80000 - 200) / 80 + 1, srec.cpp:945
-FLOP_PER_FRAME = 2 * 1530000    # 3 MLPs, from the .nbin header sizes
+FRAMES_PER_UTT = 998            # (80000 - 200) / 80 + 1 = (160000 - 400) / 160 + 1, srec.cpp:945
+SWEEP_PENALTIES = [-6.0 + 0.5 * i for i in range(13)] + [None]   # None = the config's own penalty
+
+CONFIGS = {  # --config -> workload
+    "cz": dict(model="PHN_CZ_SPDAT_LCRC_N1500", fmt="alaw", fs=8000, bytes_per_utt=80000, baseline="configs[1]"),
+    "hu": dict(model="PHN_HU_SPDAT_LCRC_N1500", fmt="alaw", fs=8000, bytes_per_utt=80000, baseline="configs[2]"),
+    "ru": dict(model="PHN_RU_SPDAT_LCRC_N1500", fmt="alaw", fs=8000, bytes_per_utt=80000, baseline="configs[2]"),
+    "en": dict(model="PHN_EN_TIMIT_LCRC_N500", fmt="lin16", fs=16000, bytes_per_utt=320000, baseline="configs[3]"),
+    "en_sweep": dict(model="PHN_EN_TIMIT_LCRC_N500", fmt="lin16", fs=16000, bytes_per_utt=320000, baseline="configs[3]"),
+}
 
 
-def model_dir() -> Path:
-    p = ROOT / "oracle" / "_ref" / "models" / MODEL
+def model_dir(name: str, allow_random: bool) -> Path:
+    p = ROOT / "oracle" / "_ref" / "models" / name
     if (p / "weights" / "merger.nbin").exists():
         return p
+    if not allow_random or name != "PHN_CZ_SPDAT_LCRC_N1500":
+        raise SystemExit(f"bench.py: the staged model data {p} is missing (run `make -C oracle ref` where /root/reference exists); "
+                         "refusing to measure on substitute weights (--allow-random-weights overrides, config cz only)")
     return synth_model_dir()
 
 
 def synth_model_dir() -> Path:
-    """Random-init weights of the CZ N1500 architecture (used only when the staged model data is absent)."""
+    """Random-init weights of the CZ N1500 architecture (only with --allow-random-weights; the line then says so)."""
     d = Path(tempfile.gettempdir()) / "phnrec_b200_synth_model"
     if (d / "weights" / "merger.nbin").exists():
         return d
@@ -78,11 +88,28 @@ def synth_model_dir() -> Path:
     return d
 
 
+def nbin_dims(mdir: Path):
+    """-> [(nin, nhid, nout)] x 3 from the .nbin headers (nn.cpp:464-531)."""
+    out = []
+    for n in ("band0", "band1", "merger"):
+        h = np.fromfile(mdir / "weights" / f"{n}.nbin", dtype=np.int32, count=4)
+        out.append((int(h[1]), int(h[2]), int(h[3])))
+    return out
+
+
+def workload_text(cfg_name: str, cfg: dict, n_utt: int) -> str:
+    rate = "8 kHz" if cfg["fs"] == 8000 else "16 kHz"
+    txt = f"{cfg['model']}, {rate} {cfg['fmt']}, {n_utt} synthetic 10 s utterances per GPU per step ({n_utt * FRAMES_PER_UTT} frames)"
+    if cfg_name == "en_sweep":
+        txt += f"; step = decoder under {len(SWEEP_PENALTIES)} insertion penalties from saved posteriors"
+    return txt
+
+
 class ClockSampler(threading.Thread):
     """Samples nvidia-smi clocks / throttle reasons of one GPU while the timed region runs."""
 
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
-        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,power.draw"
 
     def __init__(self, index: int):
         super().__init__(daemon=True)
@@ -97,49 +124,66 @@ class ClockSampler(threading.Thread):
                     self.rows.append([x.strip() for x in out.split(",")])
             except Exception:
                 pass
-            self._stop_evt.wait(0.2)
+            self._stop_evt.wait(0.1)
 
     def stop(self):
         self._stop_evt.set()
         self.join(timeout=3)
-        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
+
+        def num(r, i):
+            try:
+                return float(r[i])
+            except Exception:
+                return None
+        sm = [v for v in (num(r, 0) for r in self.rows) if v is not None]
+        mx = [v for v in (num(r, 1) for r in self.rows) if v is not None]
+        pw = [v for v in (num(r, 6) for r in self.rows if len(r) > 6) if v is not None]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(self.rows)}
+                "reasons": reasons, "samples": len(self.rows), "power_w_max": max(pw) if pw else None}
 
 
-def measured_traffic(frames):
+def measured_traffic(frames, mode):
     """DRAM bytes of the MLP launches of one step from the committed ncu --set full capture (same workload), or None."""
-    p = ROOT / "profiles" / "r1_mlp_traffic.json"
-    try:
-        j = json.loads(p.read_text())
-        if int(j.get("frames", -1)) == int(frames):
-            return int(j["k_mlp_per_step"])
-    except Exception:
-        pass
-    return None
+    for name in ("r2_mlp_traffic.json", "r1_mlp_traffic.json"):
+        try:
+            j = json.loads((ROOT / "profiles" / name).read_text())
+            if int(j.get("frames", -1)) == int(frames) and mode == "tc":
+                return int(j["k_mlp_per_step"]), name
+        except Exception:
+            pass
+    return None, None
 
 
 def measured_peaks():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
         j = json.loads(p.read_text())
-        return {"tflops": float(j.get("bf16_tflops_sustained", j.get("bf16_tflops", 1400.0))), "hbm_gbs": float(j["hbm_gbs"]),
-                "source": "MEASURED_PEAKS.json (bf16_tflops_sustained)"}
-    return {"tflops": 1400.0, "hbm_gbs": 6650.0, "source": "fallback of B200_PROFILING.md"}
+        return {"tflops_sustained": float(j.get("bf16_tflops_sustained", j.get("bf16_tflops", 1400.0))),
+                "tflops_burst": float(j.get("bf16_tflops", j.get("bf16_tflops_sustained", 1590.0))),
+                "hbm_gbs": float(j["hbm_gbs"]), "source": "MEASURED_PEAKS.json"}
+    return {"tflops_sustained": 1400.0, "tflops_burst": 1590.0, "hbm_gbs": 6650.0, "source": "fallback of B200_PROFILING.md"}
 
 
 # ------------------------------------------------------------------------------------------ reference CPU arm
-def cpu_reference_run(audio: np.ndarray, mdir: Path, cores: int):
-    """The reference's own implementation on `cores` host cores: the list is split into `cores` slices,
-    one phnrec process each (the reference is single threaded), wall clock first start -> last exit.
-    Uses oracle/_ref/phnrec_ref (kind "reference") when built, else the C restatement (kind "port")."""
-    from oracle import oracle as orc  # checker / baseline only
+def ref_binaries():
+    """-> {"noblas": path | None, "blas": path | None}: the reference's own sources compiled by oracle/Makefile."""
+    d = ROOT / "oracle" / "_ref"
+    out = {}
+    for k, n in (("noblas", "phnrec_ref"), ("blas", "phnrec_ref_blas")):
+        p = d / n
+        out[k] = p if p.exists() and os.access(p, os.X_OK) else None
+    return out
+
+
+def cpu_reference_run(audio: np.ndarray, mdir: Path, cores: int, fmt: str, binary):
+    """The reference's own implementation on `cores` host cores: the list is split into `cores` slices, one phnrec process
+    each (the reference is single threaded), wall clock first start -> last exit.  binary = a compiled reference
+    (kind "reference") or None -> the C restatement (kind "port")."""
     n_utt = audio.shape[0]
     secs = n_utt * UTT_SECONDS
-    if orc.have_ref():
+    if binary is not None:
         td = Path(tempfile.mkdtemp(prefix="phn_cpu_"))
         try:
             lists = []
@@ -154,67 +198,76 @@ def cpu_reference_run(audio: np.ndarray, mdir: Path, cores: int):
                     lines.append(str(f))
                 (td / f"l{k}.scp").write_text("\n".join(lines) + "\n")
                 lists.append(k)
+            env = dict(os.environ, OPENBLAS_NUM_THREADS="1", OMP_NUM_THREADS="1")
             t0 = time.perf_counter()
-            procs = [subprocess.Popen([str(orc.REF_BIN), "-c", str(mdir), "-w", "alaw", "-l", str(td / f"l{k}.scp"),
-                                       "-m", str(td / f"o{k}.mlf")], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+            procs = [subprocess.Popen([str(binary), "-c", str(mdir), "-w", fmt, "-l", str(td / f"l{k}.scp"),
+                                       "-m", str(td / f"o{k}.mlf")], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, env=env)
                      for k in lists]
-            for p in procs:
-                p.wait()
+            rcs = [p.wait() for p in procs]
             dt = time.perf_counter() - t0
+            if any(rcs):
+                raise RuntimeError(f"reference binary {binary} failed: {rcs}")
         finally:
             shutil.rmtree(td, ignore_errors=True)
         return secs / dt, "reference", dt
+    from oracle import oracle as orc  # checker / baseline only
     om = orc.Model(mdir)
     t0 = time.perf_counter()
     for u in range(n_utt):
-        om.recognize(audio[u].tobytes(), fmt="alaw")
+        om.recognize(audio[u].tobytes(), fmt=fmt)
     dt = time.perf_counter() - t0
     return secs / dt, "port", dt
 
 
-def host_synth_audio(n_utt: int, seed: int = 1) -> np.ndarray:
-    """Host-generated A-law bytes for the CPU arm when no GPU generated them (speech-like byte statistics)."""
-    rng = np.random.default_rng(seed)
-    t = np.arange(BYTES_PER_UTT) / FS
-    out = np.zeros((n_utt, BYTES_PER_UTT), np.uint8)
-    for u in range(n_utt):
-        f = rng.uniform(200, 3000, size=3)
-        x = sum(np.sin(2 * np.pi * fi * t) for fi in f) * 2000 * (0.5 - 0.5 * np.cos(2 * np.pi * 4 * t)) + rng.normal(0, 300, t.size)
-        x[int(rng.uniform(0, 8) * FS):][:FS] = 0
-        pcm = np.clip(x, -32768, 32767).astype(np.int16) >> 3
-        sign = np.where(pcm >= 0, 0xD5, 0x55)
-        mag = np.where(pcm >= 0, pcm, -pcm - 1).astype(np.int32)
-        seg = np.zeros_like(mag)
-        for s in range(8):
-            seg = np.where(mag > ((0x20 << s) - 1), s + 1, seg)
-        seg = np.minimum(seg, 7)
-        aval = (seg << 4) | np.where(seg < 2, (mag >> 1) & 0xF, (mag >> np.maximum(seg, 1)) & 0xF)
-        out[u] = (aval ^ sign).astype(np.uint8)
-    return out
-
-
 def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU implementation, all host cores, on a bounded sample of the GPU arm's own
+    utterances (tools/synth_host.py reproduces the device generator's bytes; the CUDA library is not loaded here)."""
     if rank != 0:
         return
+    from tools.synth_host import synth_audio
+    cfg = CONFIGS[args.config]
     cores = os.cpu_count() or 1
-    mdir = model_dir()
+    mdir = model_dir(cfg["model"], args.allow_random_weights)
     per_step = max(cores, 8) * args.ref_utts_per_core
-    audio = host_synth_audio(min(per_step, 64))
+    audio = synth_audio(cfg["bytes_per_utt"], min(per_step, args.utts), seed=1000, fmt=cfg["fmt"], fs=cfg["fs"])
     audio = np.concatenate([audio] * ((per_step + audio.shape[0] - 1) // audio.shape[0]))[:per_step]
-    for _ in range(args.warmup):
-        cpu_reference_run(audio[:cores], mdir, cores)
+    bins = ref_binaries()
+    if args.config == "en_sweep":
+        raise SystemExit("bench.py: --impl reference is defined for the audio -> labels configs (cz, hu, ru, en)")
+    # The headline of this arm is the FASTER of the two flavours the reference offers, measured here on the full sample:
+    # its BLAS build (north_star: "ATLAS-BLAS CPU build"; ATLAS is not installable offline, OpenBLAS from the image stands
+    # in) or the plain-loops build.  The other flavour's single pass is reported beside it.
+    probe = {}
+    for fl in ("blas", "noblas"):
+        if bins[fl] is not None:
+            probe[fl] = cpu_reference_run(audio, mdir, cores, cfg["fmt"], bins[fl])
+    flavour = max(probe, key=lambda k: probe[k][0]) if probe else "noblas"
+    binary = bins.get(flavour)
+    for _ in range(max(args.warmup - len(probe), 0)):
+        cpu_reference_run(audio[:cores], mdir, cores, cfg["fmt"], binary)
     t_tot, kind = 0.0, "reference"
     for _ in range(args.steps):
-        v, kind, dt = cpu_reference_run(audio, mdir, cores)
+        v, kind, dt = cpu_reference_run(audio, mdir, cores, cfg["fmt"], binary)
         t_tot += dt
     value = per_step * UTT_SECONDS * args.steps / t_tot
+    other = None
+    names = {"blas": "USE_BLAS build, sgemv per frame (nn.cpp:760) on OpenBLAS 0.3.15, 1 thread per process: substitute for ATLAS, "
+                     "which is not installable offline", "noblas": "no-BLAS loops (nn.cpp:771-793)"}
+    for fl, (v2, _, dt2) in probe.items():
+        if fl != flavour:
+            other = {"value": v2, "unit": "xRT", "cores": cores, "kind": "reference", "flavour": names[fl],
+                     "sample": f"{per_step} utterances x 10 s, one pass, {dt2:.1f} s wall"}
+    flav_txt = names[flavour]
     line = {"impl": "reference", "metric": "audio-sec/sec", "value": value, "unit": "xRT", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1000 * t_tot / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{MODEL}, 8 kHz alaw, {per_step} synthetic 10 s utterances per step (bounded sample)"},
-            "cpu_baseline": {"value": value, "unit": "xRT", "cores": cores, "kind": kind,
-                             "sample": f"{per_step} utterances x 10 s per step, {cores} phnrec processes"},
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic (same generator and seed as the GPU arm; tools/synth_host.py)",
+            "config": {"workload": workload_text(args.config, cfg, args.utts)},
+            "cpu_baseline": {"value": value, "unit": "xRT", "cores": cores, "kind": kind, "flavour": flav_txt,
+                             "sample": f"the first {min(per_step, args.utts)} utterances of that workload ({per_step} x 10 s per step), "
+                                       f"{cores} single-threaded phnrec processes over disjoint list slices"},
             "e2e": {"value": value, "unit": "xRT", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    if other:
+        line["cpu_baseline_other_flavour"] = other
     print(json.dumps(line), file=_OUT, flush=True)
 
 
@@ -238,10 +291,14 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--mode", default="auto", choices=["auto", "tc", "exact"], help="MLP mode: tcgen05 fp16 or exact fp32")
+    ap.add_argument("--config", default="cz", choices=sorted(CONFIGS))
+    ap.add_argument("--mode", default="tc", choices=["tc", "exact"], help="MLP mode: tcgen05 fp16 or exact fp32")
     ap.add_argument("--utts", type=int, default=1000, help="utterances per GPU per step")
     ap.add_argument("--ref-utts-per-core", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--profile-seconds", type=float, default=2.0, help="length of the per-kernel profiling pass")
+    ap.add_argument("--allow-random-weights", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -250,6 +307,8 @@ def main():
         run_reference(args, rank, world)
         return
     args.warmup = max(args.warmup, 3)
+    cfg = CONFIGS[args.config]
+    sweep = args.config == "en_sweep"
 
     import torch
     import torch.distributed as dist
@@ -262,29 +321,21 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
 
-    mdir = model_dir()
+    mdir = model_dir(cfg["model"], args.allow_random_weights)
     rec = pb.Recognizer(mdir, device=local)
-    rec.set_wave_format("alaw")
+    rec.set_wave_format(cfg["fmt"])
     mode = args.mode
-    if mode in ("auto", "tc"):
-        try:
-            rec.set_mlp_mode(pb.MLP_TC_F16)
-            a = rec.synth_audio(BYTES_PER_UTT, 2, seed=5)
-            rec.recognize([a[0].tobytes(), a[1].tobytes()])
-            mode = "tc"
-        except pb.PhnRecError as e:
-            if args.mode == "tc":
-                raise
-            mode = "exact"
-    if mode == "exact":
-        rec.set_mlp_mode(pb.MLP_EXACT_FP32)
+    rec.set_mlp_mode(pb.MLP_TC_F16 if mode == "tc" else pb.MLP_EXACT_FP32)   # (a missing kernel image raises: no fallback)
 
     n_utt = args.utts
-    total_bytes = n_utt * BYTES_PER_UTT
-    frames = n_utt * rec.num_frames(BYTES_PER_UTT)
-    byte_off = (np.arange(n_utt + 1, dtype=np.int64) * BYTES_PER_UTT)
+    bpu = cfg["bytes_per_utt"]
+    total_bytes = n_utt * bpu
+    fpu = rec.num_frames(bpu)
+    frames = n_utt * fpu
+    byte_off = (np.arange(n_utt + 1, dtype=np.int64) * bpu)
+    frame_off = (np.arange(n_utt + 1, dtype=np.int64) * fpu)
     d_audio = rec.device_alloc(total_bytes)
-    rec.synth_audio_device(d_audio, BYTES_PER_UTT, n_utt, seed=1000 + rank)
+    rec.synth_audio_device(d_audio, bpu, n_utt, seed=1000 + rank)
     rec.sync()
 
     stream = torch.cuda.ExternalStream(rec._L.phn_stream(rec._h), device=dev)
@@ -318,9 +369,24 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    # ---- value: device-resident inputs, labels stay on the device
-    def step_device():
-        rec.recognize_device(d_audio, byte_off)
+    import ctypes  # noqa: F401
+    h_audio = rec._L.phn_host_alloc_pinned(total_bytes)
+    rec.memcpy_d2h(h_audio, d_audio, total_bytes)
+    pens = np.array([rec.wpenalty if p is None else p for p in SWEEP_PENALTIES], dtype=np.float32)
+    n_pass = len(pens) if sweep else 1
+
+    if sweep:
+        # posteriors once (tensor-core or exact nets), resident in HBM; the step is the decoder under 14 penalties
+        audio_np = np.ctypeslib.as_array((ctypes.c_uint8 * total_bytes).from_address(h_audio))
+        utts = [audio_np[i * bpu:(i + 1) * bpu] for i in range(n_utt)]
+        posts = np.concatenate(rec.posteriors(rec.mel(utts)))   # [frames, n_outputs]: host copy for the e2e leg; phn_posteriors
+                                                                # also leaves them resident in HBM for phn_decode_device
+
+        def step_device():
+            rec.decode_device(pens)
+    else:
+        def step_device():
+            rec.recognize_device(d_audio, byte_off)
 
     sampler = ClockSampler(local)
     sampler.start()
@@ -328,77 +394,151 @@ def main():
     clocks = sampler.stop()
     launches_per_step = sum(n for _, n in rec.last_timing().values())
 
-    # ---- e2e: host buffers through phn_recognize (pinned audio -> H2D -> kernels -> labels D2H)
-    import ctypes
-    h_audio = rec._L.phn_host_alloc_pinned(total_bytes)
-    rec.memcpy_d2h(h_audio, d_audio, total_bytes)
-    cap = frames + 48 * n_utt
+    # ---- e2e: host buffers through the C ABI (pinned audio -> H2D -> kernels -> labels D2H)
+    cap = (frames + 48 * n_utt) * n_pass
     labels = np.zeros(cap, dtype=pb.LABEL_DTYPE)
-    loff = np.zeros(n_utt + 1, dtype=np.int64)
+    loff = np.zeros(n_utt * n_pass + 1, dtype=np.int64)
     nlab = [0]
-
-    def step_host():
-        nlab[0] = rec.recognize_raw(h_audio, byte_off, labels, loff)
-
+    if sweep:
+        def step_host():
+            rec._ck(rec._L.phn_decode(rec._h, posts.reshape(-1), frame_off, n_utt, pens.ctypes.data, len(pens), labels.ctypes.data, cap, loff))
+            nlab[0] = int(loff[-1])
+        h2d_bytes = posts.nbytes + 2 * 8 * (n_utt + 1) + 4 * len(pens)
+    else:
+        def step_host():
+            nlab[0] = rec.recognize_raw(h_audio, byte_off, labels, loff)
+        h2d_bytes = total_bytes + 3 * 8 * (n_utt + 1) + 4
     ms_e2e = timed_loop(step_host, args.steps, 2)
-    d2h_bytes = nlab[0] * 16 + 4 * n_utt
-    h2d_bytes = total_bytes + 3 * 8 * (n_utt + 1) + 4
+    d2h_bytes = nlab[0] * 16 + 4 * n_utt * n_pass
 
-    # ---- per-kernel-family device time (CUDA events on the launching stream, separate pass, not part of `value`)
+    # ---- per-kernel-family device time: CUDA events on the launching stream, a separate pass of >= profile-seconds so that
+    # the GPU is in its sustained state (clocks under the power cap), not part of `value`
     rec.set_profiling(True)
     fam = {}
-    reps = 2
+    reps = max(2, int(np.ceil(args.profile_seconds * 1000.0 / max(ms_dev / args.steps, 1e-3))))
+    psampler = ClockSampler(local)
+    psampler.start()
+    t_prof0 = time.perf_counter()
     for _ in range(reps):
-        rec.recognize_device(d_audio, byte_off)
+        step_device()
         rec.sync()
         for k, (ms, n) in rec.last_timing().items():
             a = fam.setdefault(k, [0.0, 0])
             a[0] += ms / reps
             a[1] = n
+    t_prof = time.perf_counter() - t_prof0
+    pclocks = psampler.stop()
     rec.set_profiling(False)
     peaks = measured_peaks()
-    mlp_ms = fam["mlp"][0]
-    achieved_tflops = frames * FLOP_PER_FRAME / (mlp_ms * 1e-3) / 1e12 if mlp_ms > 0 else 0.0
+
+    dims = nbin_dims(mdir)
+    flop_per_frame = 2 * sum(i * h + h * o for i, h, o in dims)          # 3 MLPs, from the .nbin header sizes
+    bps = 2 if cfg["fmt"] == "lin16" else 1
+    step_samples = 80 if cfg["fs"] == 8000 else 160
+    nb, nin, P3 = rec.nbanks, dims[0][0], 3 * rec.n_phonemes
+    alg = {  # algorithmic work per frame: bytes for the streaming kernels, FLOP for the nets
+        "wave": ("hbm", step_samples * bps + 4 * nb, "audio in + log-mel out"),
+        "mean": ("hbm", 4 * nb, "log-mel in"),
+        "stc": ("hbm", 4 * nb + (2 * nin * 2 if mode == "tc" else 2 * nin * 4), "log-mel in + 2 x band-net inputs out (fp16 | fp32)"),
+        "mlp": ("tensor" if mode == "tc" else "fp32", flop_per_frame, "3 MLPs"),
+        "vit": ("hbm", 4 * P3 * n_pass, "ln p in (per penalty pass)"),
+    }
+    kernels = []
+    for k, (ms, nl) in fam.items():
+        if ms <= 0:
+            continue
+        bound, per_frame, what = alg[k]
+        if bound == "hbm":
+            ach = frames * per_frame / (ms * 1e-3) / 1e9
+            kernels.append({"kernel": f"K-{k}", "bound": "hbm", "algorithmic_per_frame": per_frame, "what": what, "ms": round(ms, 4),
+                            "launches": nl, "achieved": round(ach, 1), "unit": "GB/s", "peak": peaks["hbm_gbs"], "frac": round(ach / peaks["hbm_gbs"], 4)})
+        else:
+            ach = frames * per_frame / (ms * 1e-3) / 1e12
+            pk = peaks["tflops_sustained"] if bound == "tensor" else 74.4
+            kernels.append({"kernel": f"K-{k}", "bound": bound, "algorithmic_per_frame": per_frame, "what": what, "ms": round(ms, 4),
+                            "launches": nl, "achieved": round(ach, 1), "unit": "TFLOP/s", "peak": pk, "frac": round(ach / pk, 4)})
+    mlp_ms = fam.get("mlp", [0.0, 0])[0]
     fam_total = sum(v[0] for v in fam.values()) or 1.0
 
-    audio_seconds = n_utt * UTT_SECONDS * world * args.steps
+    audio_seconds = n_utt * UTT_SECONDS * world * args.steps * n_pass
     value = audio_seconds / (ms_dev * 1e-3)
     e2e = audio_seconds / (ms_e2e * 1e-3)
 
     if rank == 0:
+        workload = workload_text(args.config, cfg, n_utt)
         line = {
             "metric": "audio-sec/sec", "value": value, "unit": "xRT", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f16" if mode == "tc" else "f32", "data": "synthetic",
-            "config": {"workload": f"{MODEL}, 8 kHz alaw, {n_utt} synthetic 10 s utterances per GPU per step "
-                                   f"({frames} frames)", "mlp_mode": "tcgen05 fp16 operands, fp32 accumulate" if mode == "tc"
-                                   else "exact fp32 (CUDA cores, reference summation order)",
-                       "l2": "256 MB buffer written between timed iterations", "model_data": str(mdir.relative_to(ROOT)) if str(mdir).startswith(str(ROOT)) else "random-init CZ N1500 architecture",
+            "config": {"workload": workload, "baseline_config": cfg["baseline"],
+                       "mlp_mode": "tcgen05 fp16 operands, fp32 accumulate" if mode == "tc" else "exact fp32 (CUDA cores, reference summation order)",
+                       "l2": "256 MB buffer written between timed iterations",
+                       "model_data": str(mdir.relative_to(ROOT)) if str(mdir).startswith(str(ROOT)) else "RANDOM-INIT CZ N1500 architecture (--allow-random-weights)",
                        "parallelism": f"{world} x independent utterance shards, no collective"},
             "e2e": {"value": e2e, "unit": "xRT", "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(d2h_bytes),
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches_per_step * args.steps),
             "clocks": clocks,
-            "roofline": {"bound": "tensor", "kernel": "K-mlp (3 MLPs per frame)", "achieved": achieved_tflops, "peak": peaks["tflops"],
-                         "unit": "TFLOP/s", "frac": achieved_tflops / peaks["tflops"], "traffic": measured_traffic(frames) if mode == "tc" else None,
-                         "traffic_note": "DRAM bytes of the 3 MLP launches of one step (ncu --set full, profiles/r1_mlp_traffic.json); "
-                                         "the bound is the tensor pipe, HBM traffic is ~10 % of peak",
-                         "algorithmic": f"{FLOP_PER_FRAME} FLOP/frame x {frames} frames", "peak_source": peaks["source"],
-                         "kernel_ms_per_step": mlp_ms, "launches_per_step": fam["mlp"][1]},
-            "kernel_ms": {k: round(v[0], 4) for k, v in fam.items()},
-            "kernel_share": {k: round(v[0] / fam_total, 4) for k, v in fam.items()},
         }
-        if world == 1 and not args.no_cpu_baseline:
+        if sweep:
+            line["config"]["value_counts"] = f"audio seconds x {n_pass} decoder passes"
+        if mlp_ms > 0:
+            ach = frames * flop_per_frame / (mlp_ms * 1e-3) / 1e12
+            traffic, tfile = measured_traffic(frames, mode)
+            pk = peaks["tflops_sustained"] if mode == "tc" else 74.4
+            line["roofline"] = {
+                "bound": "tensor" if mode == "tc" else "fp32", "kernel": "K-mlp (3 MLPs per frame)", "achieved": ach, "peak": pk,
+                "unit": "TFLOP/s", "frac": ach / pk, "traffic": traffic,
+                "frac_burst": ach / peaks["tflops_burst"] if mode == "tc" else None,
+                "peak_burst": peaks["tflops_burst"] if mode == "tc" else None,
+                "peak_applies": f"sustained: kernel times are CUDA-event averages over a profiling pass of {reps} steps spanning {t_prof:.1f} s "
+                                f"(SM clock median {pclocks['sm_mhz']} MHz, reasons {pclocks['reasons']}); frac_burst = the same achieved rate "
+                                "over the burst peak, for comparison with a kernel timed alone",
+                "traffic_note": (f"DRAM bytes of the MLP launches of one step (ncu --set full, profiles/{tfile})" if tfile else None),
+                "algorithmic": f"{flop_per_frame} FLOP/frame x {frames} frames", "peak_source": peaks["source"],
+                "kernel_ms_per_step": mlp_ms, "launches_per_step": fam["mlp"][1],
+                "kernels": kernels}
+        else:   # decoder-only step (en_sweep): the dominant kernel is K-vit, latency bound; reported against HBM like the others
+            kv = next((k for k in kernels if k["kernel"] == "K-vit"), None)
+            line["roofline"] = {"bound": "hbm", "kernel": "K-vit (K-log + token passing, per penalty pass)", "achieved": kv["achieved"] if kv else None,
+                                "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": kv["frac"] if kv else None, "traffic": None,
+                                "peak_source": peaks["source"], "kernels": kernels}
+        line["kernel_ms"] = {k: round(v[0], 4) for k, v in fam.items()}
+        line["kernel_share"] = {k: round(v[0] / fam_total, 4) for k, v in fam.items()}
+        if mode == "tc" and not sweep and not args.no_parity:
+            # the precision of the benchmarked mode on the benchmarked audio, outside the timed region: the first 256
+            # utterances through both modes (tools/tc_bound.py has the full-set figures under profiles/)
+            from tools.tc_bound import measure
+            n_par = min(256, n_utt)
+            audio_np = np.ctypeslib.as_array((ctypes.c_uint8 * (n_par * bpu)).from_address(h_audio))
+            pr = measure(rec, pb, [audio_np[i * bpu:(i + 1) * bpu].tobytes() for i in range(n_par)], chunk=128)
+            rec.set_mlp_mode(pb.MLP_TC_F16)
+            line["parity"] = {"vs": "exact fp32 mode of this library (bit-identical to the reference binary)", "utterances": n_par,
+                              "seg_agree": round(pr["seg_agree"], 5), "utt_identical": round(pr["utt_identical"], 4),
+                              "frame_argmax_agree": round(pr["frame_argmax_agree"], 5),
+                              "logp_rel_max": pr["rel_logp_max"], "logp_rel_p999": pr["rel_logp_p999"], "logp_rel_mean": pr["rel_logp_mean"],
+                              "measure": "|ln p_tc - ln p_exact| / max(1, |ln p_exact|) on the 3P decoder columns, every frame"}
+        if world == 1 and not args.no_cpu_baseline and not sweep:
+            from tools.synth_host import synth_audio
             cores = os.cpu_count() or 1
             n_cpu = max(cores, 8) * args.ref_utts_per_core
             n_gen = min(n_cpu, n_utt)
-            sample = np.zeros((n_gen, BYTES_PER_UTT), dtype=np.uint8)
-            rec.memcpy_d2h(sample.ctypes.data, d_audio, n_gen * BYTES_PER_UTT)
+            sample = np.zeros((n_gen, bpu), dtype=np.uint8)
+            rec.memcpy_d2h(sample.ctypes.data, d_audio, n_gen * bpu)
+            host = synth_audio(bpu, min(n_gen, 4), seed=1000 + rank, fmt=cfg["fmt"], fs=cfg["fs"])
+            same = bool(np.array_equal(host, sample[:host.shape[0]]))
             sample = np.concatenate([sample] * ((n_cpu + n_gen - 1) // n_gen))[:n_cpu]
-            v, kind, dt = cpu_reference_run(sample, mdir, cores)
-            line["cpu_baseline"] = {"value": v, "unit": "xRT", "cores": cores, "kind": kind,
+            bins = ref_binaries()
+            v, kind, dt = cpu_reference_run(sample, mdir, cores, cfg["fmt"], bins["noblas"])
+            line["cpu_baseline"] = {"value": v, "unit": "xRT", "cores": cores, "kind": kind, "flavour": "no-BLAS loops (nn.cpp:771-793)",
                                     "sample": f"{n_cpu} of the same synthetic utterances ({n_cpu * 10} s audio), {cores} single-threaded "
-                                              f"phnrec processes, {dt:.1f} s wall"}
+                                              f"phnrec processes, {dt:.1f} s wall; host generator reproduces the device bytes: {same}"}
+            if bins["blas"] is not None:
+                v2, kind2, dt2 = cpu_reference_run(sample, mdir, cores, cfg["fmt"], bins["blas"])
+                line["cpu_baseline_blas"] = {"value": v2, "unit": "xRT", "cores": cores, "kind": kind2,
+                                             "flavour": "USE_BLAS build, sgemv per frame (nn.cpp:760) on OpenBLAS 0.3.15, 1 thread per process: "
+                                                        "substitute for ATLAS (not installable offline)",
+                                             "sample": f"same {n_cpu} utterances, {dt2:.1f} s wall"}
         print(json.dumps(line), file=_OUT, flush=True)
 
     rec._L.phn_host_free_pinned(h_audio)

@@ -132,6 +132,9 @@ int phn_recognize(phn_ctx *ctx, const void *audio, const int64_t *byte_off, int 
  * leaves mel / posteriors / labels in the context's device buffers.  Asynchronous:
  * call phn_sync() or a phn_fetch_* before reading results. */
 int phn_recognize_device(phn_ctx *ctx, const void *d_audio, const int64_t *byte_off, int n_utt);
+/* Penalty sweep from posteriors already resident in the context (after phn_posteriors): decSoftFunc = log once, then the
+ * decoder once per penalty (srec.cpp:1080-1104 with -p); asynchronous, results through phn_fetch_labels (penalty-major). */
+int phn_decode_device(phn_ctx *ctx, const float *penalties, int n_pen);
 int phn_sync(phn_ctx *ctx);
 /* Copy results of the last *_device / host call back. Any output may be NULL.
  * phn_fetch_posteriors: in PHN_MLP_TC_F16 mode the audio -> labels calls (phn_recognize*) hand
@@ -140,6 +143,9 @@ int phn_sync(phn_ctx *ctx);
 int phn_fetch_labels(phn_ctx *ctx, phn_label *labels, int64_t label_cap, int64_t *label_off);
 int phn_fetch_mel(phn_ctx *ctx, float *mel_out);
 int phn_fetch_posteriors(phn_ctx *ctx, float *post_out);
+/* ln p as the decoder of the last call consumed it (decSoftFunc = log, srec.cpp:1088-1097): [frames][3 * n_phonemes].
+ * Works after every decoding call, including the fused tensor-core path that never materialises linear posteriors. */
+int phn_fetch_logp(phn_ctx *ctx, float *logp_out);
 /* Raw CUDA handles for callers that share the device (opaque integers/pointers). */
 void *phn_stream(phn_ctx *ctx);          /* cudaStream_t */
 void *phn_device_alloc(phn_ctx *ctx, int64_t nbytes);

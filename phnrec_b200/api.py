@@ -73,11 +73,13 @@ _SYMS = [
     ("phn_decode", C.c_int, [C.c_void_p, _f32p, _i64p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int64, _i64p]),
     ("phn_recognize", C.c_int, [C.c_void_p, C.c_void_p, _i64p, C.c_int, C.c_void_p, C.c_int64, _i64p, C.c_void_p]),
     ("phn_recognize_device", C.c_int, [C.c_void_p, C.c_void_p, _i64p, C.c_int]),
+    ("phn_decode_device", C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     ("phn_sync", C.c_int, [C.c_void_p]),
     ("phn_fetch_labels", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     ("phn_convert_weights", C.c_int, [C.c_char_p, C.c_char_p, C.c_char_p]),
     ("phn_fetch_mel", C.c_int, [C.c_void_p, _f32p]),
     ("phn_fetch_posteriors", C.c_int, [C.c_void_p, _f32p]),
+    ("phn_fetch_logp", C.c_int, [C.c_void_p, _f32p]),
     ("phn_stream", C.c_void_p, [C.c_void_p]),
     ("phn_device_alloc", C.c_void_p, [C.c_void_p, C.c_int64]),
     ("phn_device_free", None, [C.c_void_p, C.c_void_p]),
@@ -251,6 +253,12 @@ class Recognizer:
     def recognize_device(self, d_audio: int, byte_off: np.ndarray):
         self._ck(self._L.phn_recognize_device(self._h, d_audio, byte_off, len(byte_off) - 1))
 
+    def decode_device(self, penalties=None):
+        """Penalty sweep from the posteriors resident in the context (after posteriors()); fetch with fetch_labels()."""
+        pen = None if penalties is None else np.ascontiguousarray(penalties, dtype=np.float32)
+        self._pen_keepalive = pen
+        self._ck(self._L.phn_decode_device(self._h, None if pen is None else pen.ctypes.data, 1 if pen is None else int(pen.size)))
+
     def sync(self):
         self._ck(self._L.phn_sync(self._h))
 
@@ -268,6 +276,12 @@ class Recognizer:
     def fetch_posteriors(self, total_frames: int):
         out = np.zeros((total_frames, self.n_outputs), dtype=np.float32)
         self._ck(self._L.phn_fetch_posteriors(self._h, out.reshape(-1)))
+        return out
+
+    def fetch_logp(self, total_frames: int):
+        """ln p as the decoder of the last call consumed it: [total_frames, 3 * n_phonemes]."""
+        out = np.zeros((total_frames, 3 * self.n_phonemes), dtype=np.float32)
+        self._ck(self._L.phn_fetch_logp(self._h, out.reshape(-1)))
         return out
 
     def device_alloc(self, nbytes: int) -> int:

@@ -87,7 +87,7 @@ static int64_t frames_of(const phn_ctx *c, int64_t nbytes)
 static int plan_frames(phn_ctx *c, const int64_t *frame_off, int n_utt, int n_pen)
 {
     if (n_utt < 0 || n_pen < 1 || !frame_off) return fail(c, PHN_ERR_ARG, "invalid batch\n");
-    c->post_valid = 0; c->logp_valid = 0;   // (whatever an earlier batch left in d_post / d_logp is not this batch's)
+    c->post_valid = 0; c->logp_valid = 0; c->logp_layout = 0;   // (whatever an earlier batch left in d_post / d_logp is not this batch's)
     c->n_utt = n_utt; c->n_pen = n_pen;
     c->h_frame_off.assign(frame_off, frame_off + n_utt + 1);
     if (c->h_frame_off[0] != 0) return fail(c, PHN_ERR_ARG, "offsets must start at 0\n");
@@ -617,6 +617,32 @@ int phn_fetch_posteriors(phn_ctx *c, float *post_out)
     return PHN_OK;
 }
 
+// ln p exactly as the decoder of the last call consumed it (the first 3P columns of every frame), whichever kernel
+// produced it: K-log (glibc logf of the linear posteriors) or the tensor-core merger's epilogue (tiled in HBM).
+int phn_fetch_logp(phn_ctx *c, float *logp_out)
+{
+    if (!c || !logp_out) return PHN_ERR_ARG;
+    if (!c->logp_layout) return fail(c, PHN_ERR_ARG, "no log-posteriors to fetch: no decode has run on the current batch\n");
+    PHN_CUDA(c, cudaSetDevice(c->device));
+    const int64_t F = c->total_frames;
+    const int nc = 3 * c->P, ld = c->ldp;
+    if (F == 0) return PHN_OK;
+    if (c->logp_layout == 1) {
+        PHN_CUDA(c, cudaMemcpy2DAsync(logp_out, sizeof(float) * nc, c->d_logp.p, sizeof(float) * ld, sizeof(float) * nc, (size_t)F, cudaMemcpyDeviceToHost, c->stream));
+        PHN_CUDA(c, cudaStreamSynchronize(c->stream));
+        return PHN_OK;
+    }
+    const int64_t tiles = (F + 127) / 128;
+    std::vector<float> raw((size_t)tiles * ld * 128);
+    PHN_CUDA(c, cudaMemcpyAsync(raw.data(), c->d_logp.p, sizeof(float) * raw.size(), cudaMemcpyDeviceToHost, c->stream));
+    PHN_CUDA(c, cudaStreamSynchronize(c->stream));
+    for (int64_t f = 0; f < F; ++f) {
+        const float *src = raw.data() + ((f >> 7) * ld) * 128 + (f & 127);
+        for (int k = 0; k < nc; ++k) logp_out[f * nc + k] = src[(size_t)k * 128];
+    }
+    return PHN_OK;
+}
+
 int phn_fetch_labels(phn_ctx *c, phn_label *labels, int64_t label_cap, int64_t *label_off)
 {
     if (!c) return PHN_ERR_ARG;
@@ -698,6 +724,22 @@ int phn_decode(phn_ctx *c, const float *post, const int64_t *frame_off, int n_ut
     c->post_valid = 1;
     if ((rc = run_decode(c, penalties, n_pen))) return rc;
     return phn_fetch_labels(c, labels, label_cap, label_off);
+}
+
+// The penalty sweep on posteriors that are already in HBM (left there by phn_posteriors / a staged call): K-log once,
+// then one decoder pass per penalty; labels stay on the device until phn_fetch_labels.
+int phn_decode_device(phn_ctx *c, const float *penalties, int n_pen)
+{
+    if (!c) return PHN_ERR_ARG;
+    if (!penalties) n_pen = 1;
+    if (!c->post_valid) return fail(c, PHN_ERR_ARG, "no posteriors resident on the device (call phn_posteriors first)\n");
+    PHN_CUDA(c, cudaSetDevice(c->device));
+    reset_timing(c);
+    int rc;
+    const std::vector<int64_t> foff = c->h_frame_off;   // (plan_frames reassigns the member)
+    if ((rc = plan_frames(c, foff.data(), c->n_utt, n_pen))) return rc;
+    c->post_valid = 1;                                   // same frames, same buffer: nothing moved
+    return run_decode(c, penalties, n_pen);
 }
 
 int phn_recognize(phn_ctx *c, const void *audio, const int64_t *byte_off, int n_utt, phn_label *labels, int64_t label_cap,

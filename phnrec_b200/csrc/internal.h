@@ -87,6 +87,7 @@ struct phn_ctx {
     int tc_dbg_net = -1;
     int fuse_logp = 0;   // tensor-core merger also writes ln(posteriors) for the decoder (audio -> labels path)
     int post_valid = 0;  // d_post holds the linear posteriors of the current batch
+    int logp_layout = 0; // what the last decode left in d_logp: 0 nothing, 1 row-major [F][ldp] (K-log), 2 tiled [F/128][ldp][128] (merger epilogue)
     int logp_valid = 0;  // d_logp already holds the decoder's input for the current batch  // phn_mel always returns the reference's bits, whatever the MLP mode
     std::vector<std::string> phonemes;
     float win[32];

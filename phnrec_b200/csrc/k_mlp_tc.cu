@@ -289,6 +289,44 @@ __device__ __forceinline__ uint32_t pack_half2(float lo, float hi)
     asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
     return r;
 }
+// Packed fp32 pairs (sm_100 FFMA2 / FADD2 / FMUL2: one issue slot for two lanes of fp32 work).  The epilogues are bound by
+// the SM's issue slots (a sigmoid per hidden unit and frame: ~6.5 instructions each in scalar form), so every pair of
+// scalar FFMA / FADD / FMUL that can travel as one packed instruction is a direct gain.
+#ifndef PHN_TC_PACKED
+#define PHN_TC_PACKED 1
+#endif
+struct f2 { float x, y; };
+__device__ __forceinline__ uint64_t pk2(float lo, float hi)
+{
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ f2 up2(uint64_t v)
+{
+    f2 r;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+    return r;
+}
+__device__ __forceinline__ f2 ffma2(f2 a, f2 b, f2 c)
+{
+    uint64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(pk2(a.x, a.y)), "l"(pk2(b.x, b.y)), "l"(pk2(c.x, c.y)));
+    return up2(d);
+}
+__device__ __forceinline__ f2 fadd2(f2 a, f2 b)
+{
+    uint64_t d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(pk2(a.x, a.y)), "l"(pk2(b.x, b.y)));
+    return up2(d);
+}
+__device__ __forceinline__ f2 fmul2(f2 a, f2 b)
+{
+    uint64_t d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(pk2(a.x, a.y)), "l"(pk2(b.x, b.y)));
+    return up2(d);
+}
+
 // One lane of a converged warp (the same one every time: the lowest); tcgen05.commit tracks the MMAs
 // of the thread that executes it, so the issuer's MMAs and commits must come from one elected lane.
 __device__ __forceinline__ bool elect_one()
@@ -775,6 +813,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs a)
                     tmem_ld_wait();
 #pragma unroll
                     for (int g4 = 0; g4 < 4; ++g4) {
+#if PHN_TC_PACKED
+                        // four sigmoids: elements (0, 2) and (1, 3) travel as packed pairs; 1/a0 = a1 / (a0 a1), 1/a1 = a0 / (a0 a1)
+                        const f2 uA = {fma_sat(__uint_as_float(acc[g4 * 4 + 0]), sigA, sigB), fma_sat(__uint_as_float(acc[g4 * 4 + 2]), sigA, sigB)};
+                        const f2 uB = {fma_sat(__uint_as_float(acc[g4 * 4 + 1]), sigA, sigB), fma_sat(__uint_as_float(acc[g4 * 4 + 3]), sigA, sigB)};
+                        const f2 kk = {kSigTmax * 16384.0f, kSigTmax * 16384.0f}, mg = {8388608.0f, 8388608.0f}, one = {1.0f, 1.0f};
+                        const f2 rA = ffma2(uA, kk, mg), rB = ffma2(uB, kk, mg);
+                        const f2 dA = {__uint_as_float(__float_as_uint(rA.x) << 9), __uint_as_float(__float_as_uint(rA.y) << 9)};
+                        const f2 dB = {__uint_as_float(__float_as_uint(rB.x) << 9), __uint_as_float(__float_as_uint(rB.y) << 9)};
+                        const f2 aA = fadd2(dA, one), aB = fadd2(dB, one);
+                        const f2 pr = fmul2(aA, aB);
+                        const f2 rc = {rcp_approx(pr.x), rcp_approx(pr.y)};
+                        const f2 hA = fmul2(rc, aB), hB = fmul2(rc, aA);          // (h0, h2), (h1, h3)
+                        hp[half * 8 + g4 * 2] = pack_half2(hA.x, hB.x);
+                        hp[half * 8 + g4 * 2 + 1] = pack_half2(hA.y, hB.y);
+#else
                         const float a0 = 1.0f + fexp_from_u(fma_sat(__uint_as_float(acc[g4 * 4 + 0]), sigA, sigB), kSigTmax);
                         const float a1 = 1.0f + fexp_from_u(fma_sat(__uint_as_float(acc[g4 * 4 + 1]), sigA, sigB), kSigTmax);
                         const float a2 = 1.0f + fexp_from_u(fma_sat(__uint_as_float(acc[g4 * 4 + 2]), sigA, sigB), kSigTmax);
@@ -782,6 +835,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs a)
                         const float r01 = rcp_approx(a0 * a1), r23 = rcp_approx(a2 * a3);
                         hp[half * 8 + g4 * 2] = pack_half2(r01 * a1, r01 * a0);
                         hp[half * 8 + g4 * 2 + 1] = pack_half2(r23 * a3, r23 * a2);
+#endif
                     }
                 }
                 tc_fence_before();
@@ -821,10 +875,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs a)
 #pragma unroll
                     for (int j = 0; j < NQ / 4; ++j) {
                         const float4 b4 = *reinterpret_cast<const float4 *>(s_b2 + n0 + 4 * j);   // -FLT_MAX in padding columns
+#if PHN_TC_PACKED
+                        const f2 s01 = fadd2(f2{__uint_as_float(raw[4 * j + 0]), __uint_as_float(raw[4 * j + 1])}, f2{b4.x, b4.y});
+                        const f2 s23 = fadd2(f2{__uint_as_float(raw[4 * j + 2]), __uint_as_float(raw[4 * j + 3])}, f2{b4.z, b4.w});
+                        o[4 * j + 0] = s01.x; o[4 * j + 1] = s01.y; o[4 * j + 2] = s23.x; o[4 * j + 3] = s23.y;
+#else
                         o[4 * j + 0] = __uint_as_float(raw[4 * j + 0]) + b4.x;
                         o[4 * j + 1] = __uint_as_float(raw[4 * j + 1]) + b4.y;
                         o[4 * j + 2] = __uint_as_float(raw[4 * j + 2]) + b4.z;
                         o[4 * j + 3] = __uint_as_float(raw[4 * j + 3]) + b4.w;
+#endif
                     }
                     mx = o[0];
 #pragma unroll
@@ -836,6 +896,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs a)
                     TC_DBG2(3);
                     quarter_bar_sync(q);
                     mx = fmaxf(fmaxf(s_red[row], s_red[128 + row]), fmaxf(s_red[256 + row], s_red[384 + row]));
+#if PHN_TC_PACKED
+                    f2 sum2 = {0.0f, 0.0f};
+                    const f2 nmx = {-mx, -mx}, kk = {kSmxTmax * 16384.0f, kSmxTmax * 16384.0f}, mg = {8388608.0f, 8388608.0f};
+#pragma unroll
+                    for (int i = 0; i < NQ; i += 2) {
+                        const f2 d = fadd2(f2{o[i], o[i + 1]}, nmx);
+                        const f2 u = {fma_sat(d.x, smxA, smxB), fma_sat(d.y, smxA, smxB)};
+                        const f2 r = ffma2(u, kk, mg);
+                        const f2 e = {__uint_as_float(__float_as_uint(r.x) << 9), __uint_as_float(__float_as_uint(r.y) << 9)};
+                        o[i] = e.x; o[i + 1] = e.y;
+                        sum2 = fadd2(sum2, e);
+                    }
+                    const float sum = sum2.x + sum2.y;
+#else
                     float sum = 0.0f;
 #pragma unroll
                     for (int i = 0; i < NQ; ++i) {
@@ -843,6 +917,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs a)
                         o[i] = e;
                         sum += e;
                     }
+#endif
                     s_red[512 + cq * 128 + row] = sum;
                     TC_DBG2(4);
                 } else {

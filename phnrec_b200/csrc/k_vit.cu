@@ -344,6 +344,7 @@ int launch_viterbi(phn_ctx *c, const float *d_pen, int n_pen)
     a.nlab = (int *)c->d_nlab.p;
     const int ppl = (c->P + 31) / 32;
     const bool tiled = c->logp_valid != 0;   // ln p came from the tensor-core merger's epilogue (tiled layout)
+    c->logp_layout = tiled ? 2 : 1;
     const size_t vsmem = sizeof(float) * 48 * (size_t)((3 * c->P) | 1);
     // (the panel ring of the tiled form exceeds the 48 KB default from 86 phonemes on)
 #define PHN_VIT(N)                                                          \

@@ -194,6 +194,25 @@ def test_synthetic_alaw_batch_matches_oracle(recs, oracle_models):
         r.set_wave_format("lin16")
 
 
+@pytest.mark.parametrize("model,fmt,nbytes", [("PHN_CZ_SPDAT_LCRC_N1500", "alaw", 80000), ("PHN_EN_TIMIT_LCRC_N500", "lin16", 320000)])
+def test_synthetic_audio_host_port(model, fmt, nbytes):
+    """tools/synth_host.py (what bench.py's CPU reference arm recognises) reproduces the device generator byte for byte, so
+    both arms of the benchmark see the same utterances."""
+    import sys
+    from conftest import ROOT
+    sys.path.insert(0, str(ROOT))
+    from tools.synth_host import synth_audio
+    r = pb.Recognizer(model_dir(model), device=0)
+    try:
+        r.set_wave_format(fmt)
+        dev = r.synth_audio(nbytes, 5, seed=1000)
+        host = synth_audio(nbytes, 5, seed=1000, fmt=fmt, fs=r.sample_freq)
+        assert np.array_equal(dev, host)
+        assert np.array_equal(r.synth_audio(nbytes, 7, seed=77)[4:], synth_audio(nbytes, 3, seed=77, fmt=fmt, fs=r.sample_freq, first_utt=4))
+    finally:
+        r.close()
+
+
 def test_batch_equals_singletons_and_is_order_independent(recs):
     """Size-independent property: utterances are independent, so batching must not change results."""
     r = recs("PHN_CZ_SPDAT_LCRC_N1500")

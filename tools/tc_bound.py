@@ -1,0 +1,128 @@
+#!/usr/bin/env python3
+"""Measures the precision bound of the tensor-core mode ON THE BENCHMARKED WORKLOAD.
+
+Same synthetic audio as bench.py (device generator, seed 1000 + rank 0), whole utterances through BOTH modes of the library:
+  exact  : fp32 CUDA-core path, bit-identical to the reference binary (tests/test_gpu_parity.py)
+  tc     : the fused audio -> labels path bench.py times (fp32 pair-FFT front end, tensor-core K-stc features, tcgen05
+           fp16 nets, ln p from the merger's epilogue)
+and compares, over EVERY frame,
+  * ln p as the decoder consumed it (phn_fetch_logp, the 3P decoder-visible columns):
+        m = |ln p_tc - ln p_exact| / max(1, |ln p_exact|)      -> max, p99.9, p99, mean;   frame arg-max agreement
+  * the decoded segments: utterances with identical output, share of exact segments (start, end, phone) found in the tc
+    output, share of utterances with the same phone sequence, histogram of boundary shifts (frames) inside those.
+
+    python tools/tc_bound.py --config cz --utts 1000 --out gpurun_out/tc_bound_cz.json
+"""
+import argparse
+import json
+import sys
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT))
+
+CONFIGS = {  # name -> (model dir, wave format, bytes per 10 s utterance)
+    "cz": ("PHN_CZ_SPDAT_LCRC_N1500", "alaw", 80000),
+    "hu": ("PHN_HU_SPDAT_LCRC_N1500", "alaw", 80000),
+    "ru": ("PHN_RU_SPDAT_LCRC_N1500", "alaw", 80000),
+    "en": ("PHN_EN_TIMIT_LCRC_N500", "lin16", 320000),
+}
+
+
+def seg(labels):
+    return [(int(x["start"]), int(x["end"]), int(x["phn"])) for x in labels]
+
+
+def measure(rec, pb, utts, chunk=250):
+    """-> dict of the figures above for the list of audio byte strings `utts`."""
+    P3 = 3 * rec.n_phonemes
+    n_val = 0
+    s_sum = 0.0
+    mx = 0.0
+    hist_edges = np.concatenate([[0.0], np.logspace(-7, 1, 161)])
+    hist = np.zeros(len(hist_edges) - 1, dtype=np.int64)
+    inf_mismatch = 0
+    argmax_same = frames = 0
+    utt_same = utt_seq_same = 0
+    seg_total = seg_found = 0
+    shifts = {}
+    for c0 in range(0, len(utts), chunk):
+        part = utts[c0:c0 + chunk]
+        F = sum(rec.num_frames(len(u)) for u in part)
+        rec.set_mlp_mode(pb.MLP_EXACT_FP32)
+        lab_ex = rec.recognize(part)
+        lp_ex = rec.fetch_logp(F)
+        rec.set_mlp_mode(pb.MLP_TC_F16)
+        lab_tc = rec.recognize(part)
+        lp_tc = rec.fetch_logp(F)
+        assert lp_ex.shape == lp_tc.shape == (F, P3)
+        fin = np.isfinite(lp_ex) & np.isfinite(lp_tc)
+        inf_mismatch += int((np.isfinite(lp_ex) != np.isfinite(lp_tc)).sum())
+        a, b = lp_ex[fin].astype(np.float64), lp_tc[fin].astype(np.float64)
+        m = np.abs(b - a) / np.maximum(1.0, np.abs(a))
+        n_val += m.size
+        s_sum += float(m.sum())
+        mx = max(mx, float(m.max()) if m.size else 0.0)
+        hist += np.histogram(m, bins=hist_edges)[0]
+        argmax_same += int((lp_ex.argmax(1) == lp_tc.argmax(1)).sum())
+        frames += F
+        for e, t in zip(lab_ex, lab_tc):
+            se, st = seg(e), seg(t)
+            utt_same += se == st
+            seg_total += len(se)
+            sset = set(st)
+            seg_found += sum(x in sset for x in se)
+            if [x[2] for x in se] == [x[2] for x in st]:
+                utt_seq_same += 1
+                for x, y in zip(se[:-1], st[:-1]):
+                    d = y[1] - x[1]
+                    shifts[d] = shifts.get(d, 0) + 1
+    cum = np.cumsum(hist)
+
+    def quant(q):
+        i = int(np.searchsorted(cum, q * n_val))
+        return float(hist_edges[min(i + 1, len(hist_edges) - 1)])   # upper edge of the bin: a bound, not an estimate
+
+    n_utt = len(utts)
+    return {
+        "utterances": n_utt, "frames": int(frames), "values": int(n_val),
+        "rel_logp_max": mx, "rel_logp_p999": quant(0.999), "rel_logp_p99": quant(0.99), "rel_logp_mean": s_sum / max(n_val, 1),
+        "inf_mismatch": inf_mismatch,
+        "frame_argmax_agree": argmax_same / max(frames, 1),
+        "utt_identical": utt_same / max(n_utt, 1),
+        "seg_agree": seg_found / max(seg_total, 1), "segments_exact": int(seg_total),
+        "utt_same_phone_sequence": utt_seq_same / max(n_utt, 1),
+        "boundary_shift_hist": {str(k): int(v) for k, v in sorted(shifts.items())},
+    }
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--config", default="cz", choices=sorted(CONFIGS))
+    ap.add_argument("--utts", type=int, default=1000)
+    ap.add_argument("--seed", type=int, default=1000)
+    ap.add_argument("--out", default=None)
+    args = ap.parse_args()
+    import phnrec_b200 as pb
+
+    model, fmt, nbytes = CONFIGS[args.config]
+    mdir = ROOT / "oracle" / "_ref" / "models" / model
+    rec = pb.Recognizer(mdir, device=0)
+    rec.set_wave_format(fmt)
+    audio = rec.synth_audio(nbytes, args.utts, seed=args.seed)
+    utts = [audio[i].tobytes() for i in range(args.utts)]
+    res = measure(rec, pb, utts)
+    res.update({"config": args.config, "model": model, "wave_format": fmt, "seed": args.seed,
+                "reference_side": "exact fp32 mode of this library (bit-identical to the reference binary, tests/test_gpu_parity.py)"})
+    rec.close()
+    txt = json.dumps(res, indent=1)
+    print(txt)
+    if args.out:
+        Path(args.out).parent.mkdir(parents=True, exist_ok=True)
+        Path(args.out).write_text(txt + "\n")
+
+
+if __name__ == "__main__":
+    main()
