@@ -439,6 +439,8 @@ void phn_destroy(phn_ctx *c)
     if (c->tc_dbg) cudaFree(c->tc_dbg);
     if (c->stc_btab) cudaFree(c->stc_btab);
     if (c->stc_bias) cudaFree(c->stc_bias);
+    if (c->stc_cf) cudaFree(c->stc_cf);
+    if (c->stc_sb) cudaFree(c->stc_sb);
     for (int i = 0; i < 3; ++i) {
         DevNet &d = c->net[i];
         void *ps[] = {d.w1, d.w2, d.b1, d.b2, d.mean, d.dev, d.w1h, d.w2h};

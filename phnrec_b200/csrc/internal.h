@@ -81,6 +81,7 @@ struct phn_ctx {
     int mlp_mode = PHN_MLP_EXACT_FP32;
     void *tc = nullptr;  // tensor-core mode state (k_mlp_tc.cu)
     void *stc_btab = nullptr, *stc_bias = nullptr;   // K-stc tensor-core formulation: constant matrices (k_stc.cu)
+    void *stc_cf = nullptr, *stc_sb = nullptr;       // K-stc fp32 (FFMA2) form: window x basis table, per-column scale / bias pairs
     int force_exact_wave = 0;
     int fast_front = 0;   // audio -> labels path of the tensor-core mode: fp32-tolerance front end (K-wave pairs, parallel sentence mean)
     void *tc_dbg = nullptr;   // device buffer for the tensor-core kernel's debug timeline (phn_debug_tc_timeline)

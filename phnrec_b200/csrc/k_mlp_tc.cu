@@ -269,6 +269,11 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t *v)
                  ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
                    "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]) : "memory");
 }
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t *v)
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ float rcp_approx(float x)
@@ -294,6 +299,15 @@ __device__ __forceinline__ uint32_t pack_half2(float lo, float hi)
 // scalar FFMA / FADD / FMUL that can travel as one packed instruction is a direct gain.
 #ifndef PHN_TC_PACKED
 #define PHN_TC_PACKED 1
+#endif
+#ifndef PHN_TC_E1_LD32       // (kernel development switches, A/B'd on the GPU; the defaults are what measured best)
+#define PHN_TC_E1_LD32 0
+#endif
+#ifndef PHN_TC_RCP4
+#define PHN_TC_RCP4 0
+#endif
+#ifndef PHN_TC_PSLEEP
+#define PHN_TC_PSLEEP 0
 #endif
 struct f2 { float x, y; };
 __device__ __forceinline__ uint64_t pk2(float lo, float hi)
@@ -346,11 +360,40 @@ __device__ __forceinline__ bool elect_one()
 constexpr double kLn2 = 0.69314718055994530942;
 constexpr double kCt = 127.0 - 60801.0 / 1048576.0;
 constexpr float kSigTmax = 158.0f;               // sigmoid: D clamped to 2^31 (1/(1+D) is 0 in fp16 long before)
-constexpr float kSmxTmax = 128.0f;               // softmax: y <= 0, so t <= Ct < 128
+// softmax: y = o - max <= 0.  The numerators are scaled by 2^24 (it cancels against the row sum) and t is kept in
+// [1, 152]: e' = 2^24 D(y) stays a NORMAL float down to y/ln2 = -150, where the reference's own float D(y) runs out of
+// denormals and becomes 0 (fexp.h:14-21 cast to float).  Without the shift every y < -88 gave e = 0, i.e. sLn's guard
+// ln := 0 (dspc.h:155-160) instead of ln p ~ -90: one frame in ~10^5 of the merger's input was then far off.
+// u = sat((t - 1) / (TMAX - 1)); r = 2^23 + 2^14 (1 + u (TMAX - 1)); bits(e') = bits(r) << 9.  u == 0 <=> e' == 2^-126: "zero".
+constexpr float kSmxTmax = 152.0f;
+constexpr double kSmxOff = 24.0;
+constexpr float kSmxZero = 1.17549435e-38f;      // 2^-126: the clamp value, treated as the reference's exact 0
 __device__ __forceinline__ float fexp_from_u(float u, float tmax)
 {
     const float r = fmaf(u, tmax * 16384.0f, 8388608.0f);
     return __uint_as_float(__float_as_uint(r) << 9);
+}
+
+// 16 hidden pre-activations (b1 already inside, fp32 bit patterns from the accumulator) -> 16 fp16 activations as 8 pairs:
+// fsig(x) = 1 / (1 + D(-x)) with the conversion-free bit-trick exponential above; elements (0, 2) and (1, 3) of every four
+// travel as packed fp32 pairs, and two reciprocals share one MUFU: 1/a0 = a1 / (a0 a1), 1/a1 = a0 / (a0 a1).
+__device__ __forceinline__ void sigmoid16(const uint32_t *acc, uint32_t *hp, float sigA, float sigB)
+{
+#pragma unroll
+    for (int g4 = 0; g4 < 4; ++g4) {
+        const f2 uA = {fma_sat(__uint_as_float(acc[g4 * 4 + 0]), sigA, sigB), fma_sat(__uint_as_float(acc[g4 * 4 + 2]), sigA, sigB)};
+        const f2 uB = {fma_sat(__uint_as_float(acc[g4 * 4 + 1]), sigA, sigB), fma_sat(__uint_as_float(acc[g4 * 4 + 3]), sigA, sigB)};
+        const f2 kk = {kSigTmax * 16384.0f, kSigTmax * 16384.0f}, mg = {8388608.0f, 8388608.0f}, one = {1.0f, 1.0f};
+        const f2 rA = ffma2(uA, kk, mg), rB = ffma2(uB, kk, mg);
+        const f2 dA = {__uint_as_float(__float_as_uint(rA.x) << 9), __uint_as_float(__float_as_uint(rA.y) << 9)};
+        const f2 dB = {__uint_as_float(__float_as_uint(rB.x) << 9), __uint_as_float(__float_as_uint(rB.y) << 9)};
+        const f2 aA = fadd2(dA, one), aB = fadd2(dB, one);
+        const f2 pr = fmul2(aA, aB);
+        const f2 rc = {rcp_approx(pr.x), rcp_approx(pr.y)};
+        const f2 hA = fmul2(rc, aB), hB = fmul2(rc, aA);          // (h0, h2), (h1, h3)
+        hp[g4 * 2] = pack_half2(hA.x, hB.x);
+        hp[g4 * 2 + 1] = pack_half2(hA.y, hB.y);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -425,7 +468,7 @@ __device__ __forceinline__ void band_out(const float (&o)[NQ], float lg2_sc, con
             for (int i = 0; i < 4; ++i) {
                 const int cc = SH + 4 * j + i;
                 const float e = o[4 * j + i];
-                const float x = e > 0.0f ? fmaf(lg2_approx(e), av[i], fmaf(lg2_sc, av[i], bv[i])) : bv[i];
+                const float x = e > kSmxZero ? fmaf(lg2_approx(e), av[i], fmaf(lg2_sc, av[i], bv[i])) : bv[i];
                 *reinterpret_cast<__half *>(ptr[cc & 7] + (cc >> 3) * 2048) = __float2half_rn(x);
             }
         }
@@ -440,7 +483,11 @@ __device__ __forceinline__ void band_out(const float (&o)[NQ], float lg2_sc, con
 // multicast to both CTAs; CTA 1's issuer warps only relay "my operands have landed" to CTA 0, and its epilogue warps
 // arrive on CTA 0's barriers.  Everything else (producer, epilogues) is per CTA and unchanged.
 // DBG: the instantiation with the clock64() timeline hooks (tools/tc_timeline.py); the product kernels carry none.
-template <int N2P, bool XMN, bool PAIR, bool DBG>
+// V6: the schedule of round 2 (see "epilogue warps, V6" below): H is written IN PLACE over the layer-1 accumulator it came
+// from (no separate H buffer, no h_empty hand-off: the accumulator buffer returns to the layer-1 issuer when the layer-2
+// MMAs that read H have completed), and the 16 epilogue warps work as two groups of 8 on alternate chunks, each with time
+// to spare, so the soft-max of the previous tile runs in their idle time instead of between two chunks of the next tile.
+template <int N2P, bool XMN, bool PAIR, bool DBG, bool V6>
 __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs a)
 {
     constexpr int W2_BLK = N2P * 128;       // bytes of one [N2P rows x 64 fp16] block of the weight image
@@ -481,6 +528,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs a)
     uint64_t *pw2_full = pw1_full + 4;       // [4] PAIR, CTA 0: the peer's layer-2 weights of chunk n have landed (n & 3)
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(pw2_full + 4);
     volatile int *s_par = reinterpret_cast<volatile int *>(bars + 100);   // [8] loop bounds for the issuer warps (see there)
+    // V6 reuses three slots and adds two groups of four:
+    uint64_t *h_full2 = h_full;              // [2] = {h_full, h_empty}: H of chunk g is published in accumulator buffer g & 1
+    uint64_t *d1_free = d1_empty;            // [2] the layer-2 MMAs that read H out of the buffer have completed
+    uint64_t *max_ready = bars + 104;        // [4] per lane quarter: the four column-quarter warps have published their row maxima
+    uint64_t *sum_ready = bars + 108;        // [4] ... their row sums
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr int WARP_TMA = TC_EPI_WARPS, WARP_MMA1 = TC_EPI_WARPS + 1, WARP_MMA2 = TC_EPI_WARPS + 2, EPI0 = 0;
@@ -492,8 +544,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs a)
         for (int i = 0; i < 4; ++i) { mbar_init(&w1c_full[i], a.KB1); mbar_init(&w2c_full[i], 2); }
         for (int i = 0; i < 8; ++i) mbar_init(&x_empty[i], 1);
         constexpr uint32_t EPI_ARRIVALS = PAIR ? 2 * TC_EPI_WARPS : TC_EPI_WARPS;   // PAIR: both CTAs' epilogue warps arrive on CTA 0
-        for (int i = 0; i < 2; ++i) { mbar_init(&d1_full[i], 1); mbar_init(&d1_empty[i], EPI_ARRIVALS); }
-        mbar_init(h_full, EPI_ARRIVALS); mbar_init(h_empty, 1);
+        if (V6) {
+            for (int i = 0; i < 2; ++i) { mbar_init(&d1_full[i], 1); mbar_init(&d1_free[i], 1); mbar_init(&h_full2[i], EPI_ARRIVALS / 2); }
+            for (int i = 0; i < 4; ++i) { mbar_init(&max_ready[i], 4); mbar_init(&sum_ready[i], 4); }
+        } else {
+            for (int i = 0; i < 2; ++i) { mbar_init(&d1_full[i], 1); mbar_init(&d1_empty[i], EPI_ARRIVALS); }
+            mbar_init(h_full, EPI_ARRIVALS); mbar_init(h_empty, 1);
+        }
         mbar_init(d2_full, 1); mbar_init(d2_empty, EPI_ARRIVALS);
         for (int i = 0; i < 4; ++i) mbar_init(&pw1_full[i], 1);
         for (int i = 0; i < 4; ++i) mbar_init(&pw2_full[i], 1);
@@ -547,7 +604,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs a)
         int xt = 0, xk = 0, xtile = tile0;   // X cursor: tile iteration, k-block, global tile
         int xs = 0; uint32_t xwrap = 0;      //           ring slot of that block and how often the ring has wrapped (= uses of the slot so far)
         while (n1 < (uint32_t)G || n2 < (uint32_t)G || xt < my_tiles) {
+#if PHN_TC_PSLEEP
+            bool progress = false;
+#endif
             if (xt < my_tiles && (xwrap == 0 || mbar_try(&x_empty[xs], (xwrap - 1) & 1u))) {
+#if PHN_TC_PSLEEP
+                progress = true;
+#endif
                 if (elect_one()) {
                     // (PAIR: the odd CTA of the last pair may own a tile past the end; it multiplies the last real tile again
                     // and writes nothing)
@@ -564,6 +627,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs a)
                 if (++xs == a.XR) { xs = 0; ++xwrap; }
             }
             if (n1 < (uint32_t)G && mbar_try(&w1_empty[w1_stage], ph_w1 ^ 1)) {
+#if PHN_TC_PSLEEP
+                progress = true;
+#endif
                 if (elect_one()) {
                     uint64_t *fb = chunk_bar ? &w1c_full[n1 & 3] : &w1_full[w1_stage];
                     // (PAIR: this CTA's half of the block = 64 of the chunk's 128 hidden rows, contiguous in the K-major image)
@@ -578,6 +644,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs a)
                 }
             }
             if (n2 < (uint32_t)G && mbar_try(&w2_empty[w2_stage], ph_w2 ^ 1)) {
+#if PHN_TC_PSLEEP
+                progress = true;
+#endif
                 if (elect_one()) {
                     mbar_expect_tx(&w2c_full[n2 & 3], W2_ST);
                     tma_load_1d(sW2 + (size_t)w2_stage * W2_ST, a.w2_img + ((size_t)c2 * 2 + kb2) * W2_BLK + (size_t)rank * W2_ST, W2_ST, &w2c_full[n2 & 3]);
@@ -589,6 +658,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs a)
                     if (++c2 == a.NCH) c2 = 0;
                 }
             }
+#if PHN_TC_PSLEEP
+            // nothing to load right now: this warp has the highest scheduling priority of its SM sub-partition, and a polling
+            // loop there starves the four epilogue warps it shares the issue port with
+            if (!progress) __nanosleep(PHN_TC_PSLEEP);
+#endif
         }
     } else if (warp == WARP_MMA1) {
         // ===================================================================== MMA issuer, layer 1
@@ -647,7 +721,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs a)
             // the chunk is waited for last, so nothing stands between its completion and the first MMA)
             if (chunk_bar) mbar_wait(&w1c_full[g & 3], (uint32_t)(g >> 2) & 1u);
             if (PAIR) mbar_wait_cluster(&pw1_full[g & 3], (uint32_t)(g >> 2) & 1u);
-            if (g >= 2) { if (PAIR) mbar_wait_cluster(&d1_empty[g & 1], (uint32_t)((g >> 1) - 1) & 1u); else mbar_wait(&d1_empty[g & 1], (uint32_t)((g >> 1) - 1) & 1u); }
+            if (g >= 2) {
+                if (V6) mbar_wait(&d1_free[g & 1], (uint32_t)((g >> 1) - 1) & 1u);   // (committed by this CTA's layer-2 issuer)
+                else if (PAIR) mbar_wait_cluster(&d1_empty[g & 1], (uint32_t)((g >> 1) - 1) & 1u);
+                else mbar_wait(&d1_empty[g & 1], (uint32_t)((g >> 1) - 1) & 1u);
+            }
             if (lane == 0) TC_DBG(3, c1);   // accumulator + weights there
             tc_fence_after();
             int xs = xs0; uint32_t xw = xw0;
@@ -736,13 +814,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs a)
             mbar_wait(&w2c_full[g & 3], (uint32_t)(g >> 2) & 1u);
             if (PAIR) mbar_wait_cluster(&pw2_full[g & 3], (uint32_t)(g >> 2) & 1u);
             if (c2 == 0 && g > 0) { if (PAIR) mbar_wait_cluster(d2_empty, ph_d2_empty); else mbar_wait(d2_empty, ph_d2_empty); ph_d2_empty ^= 1; }
-            if (PAIR) mbar_wait_cluster(h_full, (uint32_t)g & 1u); else mbar_wait(h_full, (uint32_t)g & 1u);
+            if (V6) { if (PAIR) mbar_wait_cluster(&h_full2[g & 1], (uint32_t)(g >> 1) & 1u); else mbar_wait(&h_full2[g & 1], (uint32_t)(g >> 1) & 1u); }
+            else if (PAIR) mbar_wait_cluster(h_full, (uint32_t)g & 1u); else mbar_wait(h_full, (uint32_t)g & 1u);
             if (lane == 0) TC_DBG(6, c2);   // H + weights there
             tc_fence_after();
 #pragma unroll 1
             for (int k = 0; k < 2; ++k) {
                 const uint32_t b2lo = w2lo + w2s * (W2_ST >> 4);
-                const uint32_t ta = tH + (uint32_t)k * 32u;
+                // V6: H(g) lives in accumulator buffer g & 1, k-step j = 4 k + i at columns 64 k + 8 i (written by the epilogue
+                // warp that owns D1 columns 64 k .. 64 k + 63 of that lane quarter)
+                const uint32_t ta = V6 ? ((g & 1) ? tmem + 128u : tmem) + (uint32_t)k * 64u : tH + (uint32_t)k * 32u;
                 const uint32_t bw2 = bar_w2e + w2s * 8u;
                 const uint32_t acc0 = (k | c2) ? 1u : 0u;
                 if (leader) {
@@ -764,12 +845,173 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs a)
                 if (++w2s == (uint32_t)p_s2) w2s = 0;
             }
             if (leader) {
-                if (PAIR) { tc_commit2_u(bar_he); if (c2 == p_nch - 1) tc_commit2_u(bar_d2f); }
-                else      { tc_commit_u(bar_he);  if (c2 == p_nch - 1) tc_commit_u(bar_d2f); }
+                const uint32_t bar_back = V6 ? smem_u32(&d1_free[g & 1]) : bar_he;   // H's buffer goes back: to the layer-1 issuer (V6) / the epilogue
+                if (PAIR) { tc_commit2_u(bar_back); if (c2 == p_nch - 1) tc_commit2_u(bar_d2f); }
+                else      { tc_commit_u(bar_back);  if (c2 == p_nch - 1) tc_commit_u(bar_d2f); }
             }
             __syncwarp();
             if (lane == 0) TC_DBG(7, c2);   // issued
             if (++c2 == p_nch) { c2 = 0; tile += tstep; }
+        }
+    } else if (V6) {
+        // ===================================================================== epilogue warps, V6
+        // Warp = (lane quarter q, column quarter cq).  For E1 the column quarters pair up into two GROUPS (grp = cq >> 1) that
+        // take alternate chunks: group g & 1 turns accumulator buffer g & 1 into H(g), each of its 8 warps owning 64
+        // accumulator columns of its lane quarter (ch = cq & 1), in four sub-blocks of 16: TMEM load -> sigmoid -> fp16 pairs
+        // stored IN PLACE over columns the warp itself has already read (sub-block s lands on columns 8 s .. 8 s + 7 of the
+        // warp's 64: k-step 4 ch + s of the layer-2 MMAs).  A group has two chunk periods per chunk, about half of it idle;
+        // that is where the soft-max of the previous tile runs (same three stages as before, every warp its own 36 columns),
+        // picked up whenever its input is there while the warp polls for its next accumulator - nothing ever blocks on it,
+        // so the tensor pipe sees an epilogue that always answers within one E1.
+        const int q = warp & 3, cq = warp >> 2, grp = cq >> 1, ch = cq & 1;
+        const int row = q * 32 + lane;
+        const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+        const float sigA = (float)(-1.0 / (kLn2 * (double)kSigTmax)), sigB = (float)(kCt / (double)kSigTmax);
+        const float smxA = (float)(1.0 / (kLn2 * ((double)kSmxTmax - 1.0))), smxB = (float)((kCt + kSmxOff - 1.0) / ((double)kSmxTmax - 1.0));
+        const float smxK = (kSmxTmax - 1.0f) * 16384.0f, smxM = 8388608.0f + 16384.0f;
+        const int G = n_my * a.NCH;
+        auto signal = [&](uint64_t *bar) { if (PAIR) mbar_arrive_cluster(bar, 0); else mbar_arrive(bar); };
+        const int n0 = cq * NQ;
+        float o[NQ];
+        float mx = 0.0f;
+        int e2_i = 0, e2_stage = 0;              // next soft-max stage this warp owes: stage e2_stage of the CTA's e2_i-th tile
+        // one soft-max stage if its input is there (or, block = true, waiting for it); false: nothing was done
+        auto e2_step = [&](bool block) -> bool {
+            if (e2_i >= n_my) return false;
+            const uint32_t par = (uint32_t)e2_i & 1u;
+            const bool stamp2 = DBG && a.dbg && blockIdx.x == 0 && threadIdx.x == 0 && e2_i == 1;   // row 15: 1 A begins, 2 A done, 3 B begins, 4 B done, 5 C begins, 6 C done
+            if (e2_stage == 0) {
+                // A: D2 -> registers (+ b2), D2 handed back to the issuer, row max of this warp's columns
+                if (block) mbar_wait(d2_full, par); else if (!mbar_try(d2_full, par)) return false;
+                tc_fence_after();
+                if (stamp2) a.dbg[15 * 16 + 1] = clock64();
+                uint32_t raw[NQ];
+                tmem_ld32(tD2 + lane_addr + n0, raw);
+                if (NR == 4) tmem_ld4(tD2 + lane_addr + n0 + 32, raw + 32);
+                if (NR == 8) tmem_ld8(tD2 + lane_addr + n0 + 32, raw + 32);
+                if (NR == 16) tmem_ld16(tD2 + lane_addr + n0 + 32, raw + 32);
+                tmem_ld_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) signal(d2_empty);
+#pragma unroll
+                for (int j = 0; j < NQ / 4; ++j) {
+                    const float4 b4 = *reinterpret_cast<const float4 *>(s_b2 + n0 + 4 * j);   // -FLT_MAX in padding columns
+                    const f2 s01 = fadd2(f2{__uint_as_float(raw[4 * j + 0]), __uint_as_float(raw[4 * j + 1])}, f2{b4.x, b4.y});
+                    const f2 s23 = fadd2(f2{__uint_as_float(raw[4 * j + 2]), __uint_as_float(raw[4 * j + 3])}, f2{b4.z, b4.w});
+                    o[4 * j + 0] = s01.x; o[4 * j + 1] = s01.y; o[4 * j + 2] = s23.x; o[4 * j + 3] = s23.y;
+                }
+                mx = o[0];
+#pragma unroll
+                for (int i = 1; i < NQ; ++i) mx = fmaxf(mx, o[i]);
+                s_red[cq * 128 + row] = mx;
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&max_ready[q]);       // (release: the maxima above are visible to whoever sees the phase)
+                if (stamp2) a.dbg[15 * 16 + 2] = clock64();
+                e2_stage = 1;
+                return true;
+            }
+            if (e2_stage == 1) {
+                // B: row max across the 4 column-quarter warps of this lane quarter, e = D(o - max) (fexp.h:49-78), row sum
+                if (block) mbar_wait(&max_ready[q], par); else if (!mbar_try(&max_ready[q], par)) return false;
+                if (stamp2) a.dbg[15 * 16 + 3] = clock64();
+                mx = fmaxf(fmaxf(s_red[row], s_red[128 + row]), fmaxf(s_red[256 + row], s_red[384 + row]));
+                f2 sum2 = {0.0f, 0.0f};
+                const f2 nmx = {-mx, -mx}, kk = {smxK, smxK}, mg = {smxM, smxM};
+#pragma unroll
+                for (int i = 0; i < NQ; i += 2) {
+                    const f2 d = fadd2(f2{o[i], o[i + 1]}, nmx);
+                    const f2 u = {fma_sat(d.x, smxA, smxB), fma_sat(d.y, smxA, smxB)};
+                    const f2 r = ffma2(u, kk, mg);
+                    const f2 e = {__uint_as_float(__float_as_uint(r.x) << 9), __uint_as_float(__float_as_uint(r.y) << 9)};
+                    o[i] = e.x; o[i + 1] = e.y;
+                    sum2 = fadd2(sum2, e);
+                }
+                s_red[512 + cq * 128 + row] = sum2.x + sum2.y;
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&sum_ready[q]);
+                if (stamp2) a.dbg[15 * 16 + 4] = clock64();
+                e2_stage = 2;
+                return true;
+            }
+            // C: normalise, outputs
+            if (block) mbar_wait(&sum_ready[q], par); else if (!mbar_try(&sum_ready[q], par)) return false;
+            if (stamp2) a.dbg[15 * 16 + 5] = clock64();
+            {
+                const float sum = (s_red[512 + row] + s_red[512 + 128 + row]) + (s_red[512 + 256 + row] + s_red[512 + 384 + row]);
+                const int e2_tile = tile0 + e2_i * tstep;
+                const int64_t f = (int64_t)e2_tile * TC_M + row;
+                if (f < a.nf) {
+                    if (!a.xm_img) {
+                        if (a.post) {
+                            const float sc = 1.0f / sum;
+                            float *dst = a.post + f * a.ldpost + n0;
+#pragma unroll
+                            for (int j = 0; j < NQ / 4; ++j)
+                                if (n0 + 4 * j < a.ldpost)
+                                    *reinterpret_cast<float4 *>(dst + 4 * j) = make_float4(o[4 * j] * sc, o[4 * j + 1] * sc, o[4 * j + 2] * sc, o[4 * j + 3] * sc);
+                        }
+                        if (a.logp) {   // decoder soft function (srec.cpp:1088-1097), fused; column-major inside the tile
+                            float *ldst = a.logp + ((a.logp_tile0 + e2_tile) * a.ldpost + n0) * TC_M + row;
+                            const float ln_sc = -__logf(sum);
+#pragma unroll
+                            for (int i = 0; i < NQ; ++i)
+                                if (n0 + i < a.ldpost) ldst[i * TC_M] = fmaf(lg2_approx(o[i]), (float)kLn2, ln_sc);
+                        }
+                    } else {
+                        const int nlim = (a.nout + 7) & ~7;   // this net's share of the image: nout rounded up to 8 columns
+                        uint8_t *img = a.xm_img + (size_t)e2_tile * a.xm_kb1 * TC_BLK;
+                        const float lg2_sc = -lg2_approx(sum);
+                        const int c0 = a.xm_col0 + n0;
+                        if (c0 & 4) band_out<NQ, 4>(o, lg2_sc, s_mm + n0, s_md + n0, img, row, c0, nlim - n0);
+                        else        band_out<NQ, 0>(o, lg2_sc, s_mm + n0, s_md + n0, img, row, c0, nlim - n0);
+                    }
+                }
+            }
+            if (stamp2) a.dbg[15 * 16 + 6] = clock64();
+            e2_stage = 0;
+            ++e2_i;
+            return true;
+        };
+        // One loop, one site for each piece of code (the soft-max is ~7 KB of unrolled instructions: it must exist once).
+        // Priority: stage A of a finished tile (it hands D2 back: the next tile's layer 2 waits for it), then E1, then the
+        // soft-max stages B and C; with nothing left to convert the remaining stages are waited for.
+        uint32_t ph_d1 = 0;
+        int g = grp;
+        for (;;) {
+            const bool want_a = e2_i < n_my && e2_stage == 0 && mbar_try(d2_full, (uint32_t)e2_i & 1u);
+            if (!want_a && g < G && mbar_try(&d1_full[grp], ph_d1)) {
+                ph_d1 ^= 1;
+                tc_fence_after();
+                // timeline of the CTA's second tile: warp 0 (group 0) and warp 8 (group 1) stamp their own chunks
+                const bool stamp = DBG && a.dbg && blockIdx.x == 0 && lane == 0 && q == 0 && ch == 0 && g >= a.NCH && g < 2 * a.NCH;
+                if (stamp) a.dbg[(g - a.NCH) * 16 + 9] = clock64();    // e1: D1 seen
+                const uint32_t tbase = (grp ? tD1[1] : tD1[0]) + lane_addr + (uint32_t)ch * 64u;
+                uint32_t acc[2][16];
+                tmem_ld16(tbase, acc[0]);
+#pragma unroll
+                for (int sb = 0; sb < 4; ++sb) {
+                    tmem_ld_wait();                                       // sub-block sb is in registers
+                    if (sb < 3) tmem_ld16(tbase + 16u * (sb + 1), acc[(sb + 1) & 1]);   // the next one travels under this one's arithmetic
+                    uint32_t hp[8];
+                    sigmoid16(acc[sb & 1], hp, sigA, sigB);
+                    tmem_st8(tbase + 8u * sb, hp);                        // columns 8 sb .. 8 sb + 7: read two sub-blocks ago at the latest
+                }
+                if (stamp) a.dbg[(g - a.NCH) * 16 + 10] = clock64();   // e1: arithmetic done, stores issued
+                tmem_st_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) signal(&h_full2[grp]);
+                if (stamp) a.dbg[(g - a.NCH) * 16 + 12] = clock64();   // e1: H published
+                g += 2;
+                continue;
+            }
+            if (e2_i < n_my) {
+                if (!e2_step(g >= G)) __nanosleep(32);
+                continue;
+            }
+            if (g >= G) break;
+            __nanosleep(32);
         }
     } else {
         // ===================================================================== epilogue warps
@@ -785,7 +1027,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs a)
         // H[row][cq*32 .. +31] (fp16 pairs) = TMEM lane `row`, columns cq*16 .. +15 of the H operand
         // u = sat(t / TMAX), t = -(x + b1)/ln2 + Ct; b1 is already inside x (two extra K columns of layer 1)
         const float sigA = (float)(-1.0 / (kLn2 * (double)kSigTmax)), sigB = (float)(kCt / (double)kSigTmax);
-        const float smxA = (float)(1.0 / (kLn2 * (double)kSmxTmax)), smxB = (float)(kCt / (double)kSmxTmax);
+        const float smxA = (float)(1.0 / (kLn2 * ((double)kSmxTmax - 1.0))), smxB = (float)((kCt + kSmxOff - 1.0) / ((double)kSmxTmax - 1.0));
+        const float smxK = (kSmxTmax - 1.0f) * 16384.0f, smxM = 8388608.0f + 16384.0f;
         const int my_tiles = n_my;
         const int G = my_tiles * a.NCH;
         // the consumers of these three signals are the issuer warps: this CTA's, or (PAIR) CTA 0's for both CTAs
@@ -806,11 +1049,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs a)
                 if (threadIdx.x == EPI0 * 32) TC_DBG(9, c);    // e1: D1 seen
                 // fsig(x) = 1 / (1 + D(-x - b1)); two reciprocals share one MUFU: 1/a = a' / (a a'), 1/a' = a / (a a')
                 uint32_t hp[16];
+#if PHN_TC_E1_LD32
+                // both halves of the warp's 32 accumulator columns in one TMEM load; the accumulator buffer goes back to the
+                // layer-1 issuer before the arithmetic starts
+                uint32_t acc32[32];
+                tmem_ld32((b ? tD1[1] : tD1[0]) + lane_addr + cq * 32, acc32);
+                tmem_ld_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) signal(&d1_empty[b]);
+#endif
 #pragma unroll
                 for (int half = 0; half < 2; ++half) {
+#if PHN_TC_E1_LD32
+                    const uint32_t *acc = acc32 + 16 * half;
+#else
                     uint32_t acc[16];
                     tmem_ld16((b ? tD1[1] : tD1[0]) + lane_addr + cq * 32 + half * 16, acc);
                     tmem_ld_wait();
+#endif
 #pragma unroll
                     for (int g4 = 0; g4 < 4; ++g4) {
 #if PHN_TC_PACKED
@@ -823,7 +1080,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs a)
                         const f2 dB = {__uint_as_float(__float_as_uint(rB.x) << 9), __uint_as_float(__float_as_uint(rB.y) << 9)};
                         const f2 aA = fadd2(dA, one), aB = fadd2(dB, one);
                         const f2 pr = fmul2(aA, aB);
+#if PHN_TC_RCP4
+                        // one reciprocal for all four: 1 / (a0 a1) = (a2 a3) / (a0 a1 a2 a3)   (a <= 1 + 2^31: the product stays finite)
+                        const float r4 = rcp_approx(pr.x * pr.y);
+                        const f2 rc = fmul2(f2{r4, r4}, f2{pr.y, pr.x});
+#else
                         const f2 rc = {rcp_approx(pr.x), rcp_approx(pr.y)};
+#endif
                         const f2 hA = fmul2(rc, aB), hB = fmul2(rc, aA);          // (h0, h2), (h1, h3)
                         hp[half * 8 + g4 * 2] = pack_half2(hA.x, hB.x);
                         hp[half * 8 + g4 * 2 + 1] = pack_half2(hA.y, hB.y);
@@ -838,9 +1101,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs a)
 #endif
                     }
                 }
+#if !PHN_TC_E1_LD32
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) signal(&d1_empty[b]);      // (the layer-1 issuer may overwrite this accumulator buffer)
+#endif
                 if (threadIdx.x == EPI0 * 32) TC_DBG(10, c);   // e1: math done
                 if (!first_h) { mbar_wait(h_empty, ph_h_empty); ph_h_empty ^= 1; }
                 first_h = false;
@@ -898,7 +1163,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs a)
                     mx = fmaxf(fmaxf(s_red[row], s_red[128 + row]), fmaxf(s_red[256 + row], s_red[384 + row]));
 #if PHN_TC_PACKED
                     f2 sum2 = {0.0f, 0.0f};
-                    const f2 nmx = {-mx, -mx}, kk = {kSmxTmax * 16384.0f, kSmxTmax * 16384.0f}, mg = {8388608.0f, 8388608.0f};
+                    const f2 nmx = {-mx, -mx}, kk = {smxK, smxK}, mg = {smxM, smxM};
 #pragma unroll
                     for (int i = 0; i < NQ; i += 2) {
                         const f2 d = fadd2(f2{o[i], o[i + 1]}, nmx);
@@ -913,7 +1178,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs a)
                     float sum = 0.0f;
 #pragma unroll
                     for (int i = 0; i < NQ; ++i) {
-                        const float e = fexp_from_u(fma_sat(o[i] - mx, smxA, smxB), kSmxTmax);
+                        const float e = __uint_as_float(__float_as_uint(fmaf(fma_sat(o[i] - mx, smxA, smxB), smxK, smxM)) << 9);
                         o[i] = e;
                         sum += e;
                     }
@@ -1115,17 +1380,17 @@ void mlp_tc_release(phn_ctx *c)
     c->tc = nullptr;
 }
 
-template <int N2P, bool XMN, bool PAIR, bool DBG>
+template <int N2P, bool XMN, bool PAIR, bool DBG, bool V6>
 static int launch_inst_k(phn_ctx *c, const TcArgs &a, size_t smem_bytes, int grid)
 {
-    PHN_CUDA(c, cudaFuncSetAttribute(k_mlp_tc<N2P, XMN, PAIR, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+    PHN_CUDA(c, cudaFuncSetAttribute(k_mlp_tc<N2P, XMN, PAIR, DBG, V6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = smem_bytes; cfg.stream = c->stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = PAIR ? 2 : 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    PHN_CUDA(c, cudaLaunchKernelEx(&cfg, k_mlp_tc<N2P, XMN, PAIR, DBG>, a));
+    PHN_CUDA(c, cudaLaunchKernelEx(&cfg, k_mlp_tc<N2P, XMN, PAIR, DBG, V6>, a));
     return PHN_OK;
 }
 
@@ -1133,7 +1398,11 @@ template <int N2P, bool XMN, bool PAIR>
 static int launch_inst(phn_ctx *c, const TcArgs &a, size_t smem_bytes, int grid)
 {
     // (the timeline instantiation only when tools/tc_timeline.py asked for one on this net)
-    return a.dbg ? launch_inst_k<N2P, XMN, PAIR, true>(c, a, smem_bytes, grid) : launch_inst_k<N2P, XMN, PAIR, false>(c, a, smem_bytes, grid);
+    // PHNREC_TC_V6=1 selects the in-place-H / two-epilogue-group schedule (measured slower: 3.27 vs 3.10 ms per step on
+    // the same box, profiles/r2_*; kept as an experiment).  Default: separate H buffer, all 16 epilogue warps on every chunk.
+    static const bool v5 = !(getenv("PHNREC_TC_V6") && atoi(getenv("PHNREC_TC_V6")) != 0);
+    if (a.dbg) return v5 ? launch_inst_k<N2P, XMN, PAIR, true, false>(c, a, smem_bytes, grid) : launch_inst_k<N2P, XMN, PAIR, true, true>(c, a, smem_bytes, grid);
+    return v5 ? launch_inst_k<N2P, XMN, PAIR, false, false>(c, a, smem_bytes, grid) : launch_inst_k<N2P, XMN, PAIR, false, true>(c, a, smem_bytes, grid);
 }
 
 template <int N2P>

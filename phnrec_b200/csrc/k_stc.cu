@@ -11,6 +11,8 @@
 #include "internal.h"
 
 #include <cmath>
+#include <cstdlib>
+#include <cstring>
 #include <vector>
 
 namespace phn {
@@ -320,6 +322,295 @@ __global__ void __launch_bounds__(256, 2) k_stc_mma(StcMmaArgs a)
 }
 
 
+// ------------------------------------------------------------------------------------------------
+// Tensor-core pipeline, fp32 form (default): the same features on the CUDA cores with packed fp32 pairs (sm_100 FFMA2).
+//     x[frame][11 b + n] = (sum_j (mel[c(frame, j)][b] - mean[b]) * Cf[s][n][j]) * dev[s][11 b + n] - nn_mean * dev
+//     Cf[s][n][j] = window[s][j] * basis[n][j] * sqrt(2/16)        (one table for all bands)
+// One thread = (4 consecutive frames, 2 adjacent bands, one side): the 19 log-mel rows its frames' 16-tap windows cover
+// sit in registers as (band b, band b+1) pairs - adjacent floats of a row of the shared-memory tile, one 64-bit load
+// each - and every FFMA2 does two bands' worth of one tap against a scalar (broadcast) coefficient.  704 FFMA2 per thread
+// and side against ~300 instructions of loads, index arithmetic, conversions and stores: ~130 warp-instructions per frame
+// where the mma.sync formulation above (three hi/lo products + the splits of A) needs ~330.  fp32 throughout: the only
+// rounding to fp16 is the final one into the activation image.
+// CTA = one 128-frame image tile, persistent; the staging tile [128 rows][COLS] goes out as 16-byte chunks of the
+// K-major SWIZZLE_128B image exactly like the mma.sync kernel's.
+struct StcF2Args {
+    const float *mel, *mean;
+    const int64_t *frame_off;
+    int n_utt;
+    int64_t f0, nf, total_frames;
+    const float *cf;       // [2][11][16]
+    const float4 *sb;      // [2][11][NBP] {dev(b0), dev(b1), -mean*dev(b0), -mean*dev(b1)}
+    uint8_t *x0h, *x1h;
+    int kb1, n_tiles, tile_lo;
+    int64_t row_lo, row_hi;
+};
+
+struct sf2 { float x, y; };
+__device__ __forceinline__ uint64_t s_pk2(float lo, float hi)
+{
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ sf2 s_up2(uint64_t v)
+{
+    sf2 r;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+    return r;
+}
+#ifndef PHN_STC_SCALAR      // (kernel development: 1 = two scalar FFMAs in place of every FFMA2)
+#define PHN_STC_SCALAR 0
+#endif
+__device__ __forceinline__ sf2 s_ffma2(sf2 a, sf2 b, sf2 c)
+{
+#if PHN_STC_SCALAR
+    return sf2{fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)};
+#endif
+    uint64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(s_pk2(a.x, a.y)), "l"(s_pk2(b.x, b.y)), "l"(s_pk2(c.x, c.y)));
+    return s_up2(d);
+}
+__device__ __forceinline__ sf2 s_fadd2(sf2 a, sf2 b)
+{
+    uint64_t d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(s_pk2(a.x, a.y)), "l"(s_pk2(b.x, b.y)));
+    return s_up2(d);
+}
+__device__ __forceinline__ uint32_t s_h2(float lo, float hi)
+{
+    uint32_t r;
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+
+// one frame of a unit that is not 4 frames of one utterance (utterance boundary inside it, end of the batch): rare
+template <int PITCH, int NBP>
+__device__ __noinline__ void stc_f2_one_frame(const float *s_mel, const float *cf, const float4 *sb, sf2 nmean, int base, int t0, int T,
+                                              int bp, bool has_b1, __half *orow)
+{
+    sf2 w[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        int t = t0 + j;
+        t = t < 0 ? 0 : (t > T - 1 ? T - 1 : t);
+        const float2 v = *reinterpret_cast<const float2 *>(s_mel + (base + t) * PITCH + 2 * bp);
+        w[j] = s_fadd2(sf2{v.x, v.y}, nmean);
+    }
+#pragma unroll 1
+    for (int n = 0; n < 11; ++n) {
+        sf2 acc = {0.0f, 0.0f};
+#pragma unroll
+        for (int j = 0; j < 16; ++j) { const float c = cf[n * 16 + j]; acc = s_ffma2(w[j], sf2{c, c}, acc); }
+        const float4 k4 = sb[n * NBP];
+        const sf2 x = s_ffma2(acc, sf2{k4.x, k4.y}, sf2{k4.z, k4.w});
+        orow[n] = __float2half_rn(x.x);
+        if (has_b1) orow[11 + n] = __float2half_rn(x.y);
+    }
+}
+
+template <int NB>
+__global__ void __launch_bounds__(256, 2) k_stc_f2(StcF2Args a)
+{
+    constexpr int NBP = (NB + 1) / 2;                 // band pairs (the last one is half empty when NB is odd)
+    constexpr int NIN = NB * 11;
+    constexpr int COLS = (NIN + 2 + 63) / 64 * 64;    // image columns = 64 * kb1
+    constexpr int LD = COLS + 8;                      // staging row stride in halves (16-byte aligned rows)
+    constexpr int PITCH = (2 * NBP + 7) / 8 * 8 + 4;  // floats per log-mel row in shared memory: 4 rows = 64 B mod 128 B
+    constexpr int ROWS = STCM_F + 30;
+    constexpr int UNITS = 32 * NBP;                   // (frame group, band pair) units of one side
+    extern __shared__ __align__(16) uint8_t stc_smem[];
+    float *s_cf = reinterpret_cast<float *>(stc_smem);                          // [2][11][16]
+    float4 *s_sb = reinterpret_cast<float4 *>(s_cf + 2 * 11 * 16);              // [2][11][NBP]
+    float *s_mel = reinterpret_cast<float *>(s_sb + 2 * 11 * NBP);              // [ROWS][PITCH]
+    __half *s_out = reinterpret_cast<__half *>(s_mel + ROWS * PITCH);           // [128][LD]
+    __shared__ int64_t s_u0[STCM_F];
+    __shared__ int s_T[STCM_F], s_u[STCM_F];
+    for (int i = threadIdx.x; i < 2 * 11 * 16; i += blockDim.x) s_cf[i] = a.cf[i];
+    for (int i = threadIdx.x; i < 2 * 11 * NBP; i += blockDim.x) s_sb[i] = a.sb[i];
+    // image columns beyond the features: the two constant-1 inputs that multiply the bias columns of the layer-1 weight
+    // image (k_mlp_tc.cu), then zeros; only column NIN is ever rewritten below (with the same 1.0)
+    for (int i = threadIdx.x; i < STCM_F * (COLS - NIN); i += blockDim.x) {
+        const int r = i / (COLS - NIN), cidx = NIN + i % (COLS - NIN);
+        s_out[r * LD + cidx] = __float2half_rn(cidx < NIN + 2 ? 1.0f : 0.0f);
+    }
+    for (int i = threadIdx.x; i < ROWS * (PITCH - NB); i += blockDim.x)   // padding columns of the tile (the half-empty pair)
+        s_mel[(i / (PITCH - NB)) * PITCH + NB + i % (PITCH - NB)] = 0.0f;
+    for (int tile = a.tile_lo + blockIdx.x; tile < a.tile_lo + a.n_tiles; tile += gridDim.x) {
+        const int64_t fl0 = (int64_t)tile * STCM_F;
+        const int64_t G0 = a.f0 + fl0 - 15;
+        __syncthreads();   // (previous tile's readers of s_mel / s_u / s_out are done)
+        for (int q = threadIdx.x; q < ROWS * NB; q += blockDim.x) {
+            const int r = q / NB, b = q - r * NB;
+            const int64_t gr = G0 + r;
+            s_mel[r * PITCH + b] = (gr >= 0 && gr < a.total_frames) ? a.mel[G0 * NB + q] : 0.0f;
+        }
+        if (threadIdx.x < STCM_F) {
+            const int64_t fl = fl0 + threadIdx.x;
+            if (fl < a.nf && a.f0 + fl >= a.row_lo && a.f0 + fl < a.row_hi) {
+                const int u = stc_find_utt(a.frame_off, a.n_utt, a.f0 + fl);
+                s_u[threadIdx.x] = u;
+                s_u0[threadIdx.x] = a.frame_off[u];
+                s_T[threadIdx.x] = (int)(a.frame_off[u + 1] - a.frame_off[u]);
+            } else {
+                s_u[threadIdx.x] = -1;
+            }
+        }
+        __syncthreads();
+#pragma unroll 1
+        for (int side = 0; side < 2; ++side) {
+            const float *cf = s_cf + side * 176;
+#pragma unroll 1
+            for (int q = threadIdx.x; q < UNITS; q += blockDim.x) {
+                const int fg = q / NBP, bp = q - fg * NBP;
+                const int fr = 4 * fg;                          // first of the unit's 4 tile rows
+                const int u = s_u[fr];
+                const bool has_b1 = 2 * bp + 1 < NB;
+                const float4 *sb = s_sb + side * 11 * NBP + bp;
+                __half *orow = s_out + (size_t)fr * LD + 22 * bp;
+                if (u >= 0 && s_u[fr + 3] == u) {               // 4 valid frames of one utterance (the common case)
+                    const int T = s_T[fr];
+                    const int base = (int)(s_u0[fr] - G0);
+                    const int t0 = (int)(a.f0 + fl0 + fr - s_u0[fr]) - 15 + 15 * side;
+                    const float *mp = a.mean + (size_t)u * NB + 2 * bp;
+                    const sf2 nmean = {-__ldg(mp), has_b1 ? -__ldg(mp + 1) : 0.0f};
+                    // the 19 rows the four 16-tap windows cover, clamped inside the utterance (S1: c(t, j) = clamp(t - 15 + j))
+                    sf2 w[19];
+#pragma unroll
+                    for (int i = 0; i < 19; ++i) {
+                        int t = t0 + i;
+                        t = t < 0 ? 0 : (t > T - 1 ? T - 1 : t);
+                        const float2 v = *reinterpret_cast<const float2 *>(s_mel + (base + t) * PITCH + 2 * bp);
+                        w[i] = s_fadd2(sf2{v.x, v.y}, nmean);
+                    }
+                    // Coefficient n of both bands for the 4 frames.  The unit's 22 image columns go out as 11 pairs of halves:
+                    // band b0 = 2 bp starts at an even column, so its pairs are (0,1) .. (8,9) and (10 | b1's 0); b1's are
+                    // (1,2) .. (9,10).  When b1 does not exist (NB odd, last pair) its first column is the constant 1.0.
+                    float holdA[4], holdB[4], holdB0[4];
+#pragma unroll
+                    for (int n = 0; n < 11; ++n) {
+                        float c[16];
+#pragma unroll
+                        for (int j4 = 0; j4 < 4; ++j4) {
+                            const float4 cc = *reinterpret_cast<const float4 *>(cf + n * 16 + 4 * j4);
+                            c[4 * j4] = cc.x; c[4 * j4 + 1] = cc.y; c[4 * j4 + 2] = cc.z; c[4 * j4 + 3] = cc.w;
+                        }
+                        sf2 acc[4] = {{0.0f, 0.0f}, {0.0f, 0.0f}, {0.0f, 0.0f}, {0.0f, 0.0f}};
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+#pragma unroll
+                            for (int d = 0; d < 4; ++d) acc[d] = s_ffma2(w[d + j], sf2{c[j], c[j]}, acc[d]);
+                        const float4 k4 = sb[n * NBP];
+#pragma unroll
+                        for (int d = 0; d < 4; ++d) {
+                            const sf2 x = s_ffma2(acc[d], sf2{k4.x, k4.y}, sf2{k4.z, k4.w});   // NeuralNet::Normalize folded in
+                            uint32_t *o32 = reinterpret_cast<uint32_t *>(orow + d * LD);
+                            if (n == 10) o32[5] = s_h2(x.x, has_b1 ? holdB0[d] : 1.0f);
+                            else if ((n & 1) == 0) holdA[d] = x.x;
+                            else o32[(n - 1) / 2] = s_h2(holdA[d], x.x);
+                            if (n == 0) holdB0[d] = x.y;
+                            else if (n & 1) holdB[d] = x.y;
+                            else if (has_b1) o32[(10 + n) / 2] = s_h2(holdB[d], x.y);
+                        }
+                    }
+                } else {
+#pragma unroll 1
+                    for (int d = 0; d < 4; ++d) {
+                        const int ud = s_u[fr + d];
+                        if (ud < 0) continue;                   // (outside the pass or this launch's row range: never written out)
+                        const float *mp = a.mean + (size_t)ud * NB + 2 * bp;
+                        const sf2 nmean = {-__ldg(mp), has_b1 ? -__ldg(mp + 1) : 0.0f};
+                        stc_f2_one_frame<PITCH, NBP>(s_mel, cf, sb, nmean, (int)(s_u0[fr + d] - G0),
+                                                     (int)(a.f0 + fl0 + fr + d - s_u0[fr + d]) - 15 + 15 * side, s_T[fr + d], bp, has_b1,
+                                                     orow + d * LD);
+                    }
+                }
+            }
+            __syncthreads();
+            // the tile's 128 rows x COLS / 8 chunks of 16 bytes -> image (K-major SW128 blocks, k_mlp_tc.cu)
+            uint8_t *img = (side ? a.x1h : a.x0h) + (size_t)tile * a.kb1 * 16384;
+#pragma unroll 4
+            for (int q = threadIdx.x; q < STCM_F * (COLS / 8); q += blockDim.x) {
+                const int r = q / (COLS / 8), ch = q - r * (COLS / 8);   // (division by a compile-time constant)
+                if (s_u[r] >= 0)   // (inside the pass and inside this launch's row range)
+                    *reinterpret_cast<uint4 *>(img + (size_t)(ch >> 3) * 16384 + r * 128 + ((((unsigned)ch & 7u) ^ ((unsigned)r & 7u)) << 4)) =
+                        *reinterpret_cast<const uint4 *>(s_out + r * LD + ch * 8);
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// tables of the fp32 form, built once per context on the host
+static int stc_f2_prepare(phn_ctx *c)
+{
+    if (c->stc_cf) return PHN_OK;
+    const int nb = c->nbanks, nbp = (nb + 1) / 2, nin = nb * 11;
+    std::vector<float> cf((size_t)2 * 11 * 16);
+    std::vector<float> sb((size_t)2 * 11 * nbp * 4);
+    const double normc = (double)sqrtf(2.0f / 16.0f);
+    const float PiByN = (float)M_PI / 16.0f;
+    for (int s = 0; s < 2; ++s)
+        for (int n = 0; n < 11; ++n) {
+            for (int j = 0; j < 16; ++j) {
+                const double basis = n == 0 ? 1.0 : (double)cosf(PiByN * (float)n * ((float)j + 0.5f));   // CalcC0 / sDCT, dspc.h:206-233
+                cf[((size_t)s * 11 + n) * 16 + j] = (float)((double)c->win[s * 16 + j] * basis * normc);
+            }
+            for (int bp = 0; bp < nbp; ++bp) {
+                float *o = &sb[(((size_t)s * 11 + n) * nbp + bp) * 4];
+                for (int h = 0; h < 2; ++h) {
+                    const int b = 2 * bp + h;
+                    const float dev = b < nb ? c->hnet[s].dev[b * 11 + n] : 0.0f, mean = b < nb ? c->hnet[s].mean[b * 11 + n] : 0.0f;
+                    o[h] = dev;
+                    o[2 + h] = -mean * dev;
+                }
+            }
+        }
+    (void)nin;
+    PHN_CUDA(c, cudaMalloc(&c->stc_cf, cf.size() * 4));
+    PHN_CUDA(c, cudaMalloc(&c->stc_sb, sb.size() * 4));
+    PHN_CUDA(c, cudaMemcpy(c->stc_cf, cf.data(), cf.size() * 4, cudaMemcpyHostToDevice));
+    PHN_CUDA(c, cudaMemcpy(c->stc_sb, sb.data(), sb.size() * 4, cudaMemcpyHostToDevice));
+    return PHN_OK;
+}
+
+template <int NB>
+static int launch_stc_f2_t(phn_ctx *c, const StcF2Args &a)
+{
+    constexpr int NBP = (NB + 1) / 2, NIN = NB * 11, COLS = (NIN + 2 + 63) / 64 * 64, LD = COLS + 8, PITCH = (2 * NBP + 7) / 8 * 8 + 4;
+    const size_t smem = sizeof(float) * 2 * 11 * 16 + sizeof(float4) * 2 * 11 * NBP + sizeof(float) * (STCM_F + 30) * PITCH + (size_t)STCM_F * LD * 2;
+    PHN_CUDA(c, cudaFuncSetAttribute(k_stc_f2<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int grid = a.n_tiles < 2 * c->num_sms ? a.n_tiles : 2 * c->num_sms;
+    k_stc_f2<NB><<<grid, 256, smem, c->stream>>>(a);
+    PHN_CUDA(c, cudaGetLastError());
+    return PHN_OK;
+}
+
+static int launch_stc_f2(phn_ctx *c, int64_t f0, int64_t nf, int64_t row_lo, int64_t row_hi)
+{
+    int rc;
+    if ((rc = stc_f2_prepare(c))) return rc;
+    StcF2Args a;
+    a.mel = (const float *)c->d_mel.p;
+    a.mean = (const float *)c->d_mean.p;
+    a.frame_off = (const int64_t *)c->d_frame_off.p;
+    a.n_utt = c->n_utt;
+    a.f0 = f0; a.nf = nf; a.total_frames = c->total_frames;
+    a.cf = (const float *)c->stc_cf; a.sb = (const float4 *)c->stc_sb;
+    a.x0h = (uint8_t *)c->d_x0h.p; a.x1h = (uint8_t *)c->d_x1h.p;
+    a.kb1 = c->net[0].k1P / 64;
+    if (row_lo < f0) row_lo = f0;
+    if (row_hi > f0 + nf) row_hi = f0 + nf;
+    if (row_hi <= row_lo) return PHN_OK;
+    a.row_lo = row_lo; a.row_hi = row_hi;
+    a.tile_lo = (int)((row_lo - f0) / STCM_F);
+    a.n_tiles = (int)((row_hi - f0 + STCM_F - 1) / STCM_F) - a.tile_lo;
+    rc = c->nbanks == 15 ? launch_stc_f2_t<15>(c, a) : launch_stc_f2_t<23>(c, a);
+    if (rc) return rc;
+    c->k_launches[PHN_K_STC] += 1;
+    return PHN_OK;
+}
+
 // constant matrices of the tensor-core formulation, built once per context on the host (fp16 hi + lo fragments)
 static int stc_mma_prepare(phn_ctx *c)
 {
@@ -411,7 +702,10 @@ int launch_stc(phn_ctx *c, int64_t f0, int64_t nf, int64_t row_lo, int64_t row_h
     a.nmean1 = c->net[1].mean; a.ndev1 = c->net[1].dev;
     a.normc = sqrtf(2.0f / 16.0f);
     const bool tc = c->mlp_mode == PHN_MLP_TC_F16;
-    if (tc && (c->nbanks == 15 || c->nbanks == 23) && c->net[0].k1P / 64 == (c->nbanks * 11 + 2 + 63) / 64) return launch_stc_mma(c, f0, nf, row_lo, row_hi);
+    if (tc && (c->nbanks == 15 || c->nbanks == 23) && c->net[0].k1P / 64 == (c->nbanks * 11 + 2 + 63) / 64) {
+        static const bool use_mma = getenv("PHNREC_STC") && !strcmp(getenv("PHNREC_STC"), "mma");   // (kernel development: the mma.sync form)
+        return use_mma ? launch_stc_mma(c, f0, nf, row_lo, row_hi) : launch_stc_f2(c, f0, nf, row_lo, row_hi);
+    }
     a.x0 = tc ? nullptr : (float *)c->d_x0.p;
     a.x1 = tc ? nullptr : (float *)c->d_x1.p;
     a.x0h = tc ? (uint8_t *)c->d_x0h.p : nullptr;

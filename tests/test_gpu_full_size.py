@@ -1,9 +1,10 @@
 """GPU tests at BASELINE.json's full sizes, through size-independent properties of the domain (the oracle needs seconds
 per utterance, so it only checks a sample):
   * a decoder output covers its utterance in order: the first segment starts at 0, the last one ends at T, segments are
-    non-empty and never overlap (the reference's decoder occasionally leaves a gap of a few frames between two segments
-    -- utterance 49 of the seed below has one at frames 419..422, and the compiled reference, the oracle and both CUDA
-    modes all print it -- so contiguity is NOT a property of the domain);
+    non-empty, starts and ends never decrease.  Neither contiguity nor disjointness is a property of the domain: the
+    reference's partial traceback (phndec.cpp:191-234) occasionally leaves a gap of a few frames between two segments, and
+    occasionally commits a phone twice with two end points -- utterance 7 of the seed below prints "798 809 e", "798 810 e",
+    "809 839 int"; the compiled reference, the oracle and both CUDA modes all print exactly that;
   * utterances are independent: a batch equals the same utterances recognised in two halves, bit for bit;
   * the penalty sweep from saved posteriors is consistent: the multi-penalty call equals single-penalty calls, and a
     larger (less negative) insertion penalty never yields fewer segments in total."""
@@ -21,7 +22,7 @@ def tiles(lab, T):
     if len(lab) == 0:
         return False
     s, e = lab["start"].astype(np.int64), lab["end"].astype(np.int64)
-    return s[0] == 0 and e[-1] == T and (s[1:] >= e[:-1]).all() and (e > s).all()
+    return s[0] == 0 and e[-1] == T and (s[1:] >= s[:-1]).all() and (e[1:] >= e[:-1]).all() and (e > s).all()
 
 
 def test_config2_cz_1000_utterances_properties(oracle_models):
@@ -41,13 +42,18 @@ def test_config2_cz_1000_utterances_properties(oracle_models):
         # a sample against the oracle through the exact mode (bit-identical to the reference by the parity tests)
         r.set_mlp_mode(pb.MLP_EXACT_FP32)
         om = oracle_models("PHN_CZ_SPDAT_LCRC_N1500")
-        idx = [0, 49, 999]
+        idx = [0, 7, 49, 999]
         exact = r.recognize([utts[i] for i in idx])
         for i, e in zip(idx, exact):
             want = om.recognize(utts[i], fmt="alaw")
             assert pb.format_rec(e, r.phonemes) == pb.format_rec(want, om.phonemes)
-            seg = lambda l: {(int(x["start"]), int(x["end"]), int(x["phn"])) for x in l}
-            assert len(seg(full[i]) & seg(e)) >= 0.85 * len(e)      # the fast path on the same utterance
+        # the fast path against the exact one on the first 200 utterances: segment agreement (start, end, phone) at the
+        # level tools/tc_bound.py measures on the whole set (0.9973; the bound enforced here is twice that error)
+        seg = lambda l: {(int(x["start"]), int(x["end"]), int(x["phn"])) for x in l}
+        ex200 = r.recognize(utts[:200])
+        tot = sum(len(e) for e in ex200)
+        hit = sum(len(seg(f) & seg(e)) for f, e in zip(full[:200], ex200))
+        assert hit / tot >= 0.9945, (hit, tot)
     finally:
         r.close()
 

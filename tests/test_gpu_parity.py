@@ -213,6 +213,32 @@ def test_synthetic_audio_host_port(model, fmt, nbytes):
         r.close()
 
 
+def test_exact_mode_inside_the_bit_trick_exponentials_overflow_zone(recs, oracle_models):
+    """fexp.h:14-21 adds an int32 constant to (int)(2^20/ln2 * y): for |y| > 710.5 the sum overflows (undefined behaviour in
+    the reference; x86 wraps, the hidden activation becomes NaN and the net's soft-max degenerates to the uniform
+    distribution).  Utterance 99 of the RU synthetic set (seed 1000) has such a frame (783: a band-1 pre-activation of
+    822).  The exact mode must still give what the x86 reference gives: posteriors of that neighbourhood bit for bit, and
+    the same labels for the whole utterance."""
+    import sys
+    from conftest import ROOT
+    sys.path.insert(0, str(ROOT))
+    from tools.synth_host import synth_audio
+    r, o = recs("PHN_RU_SPDAT_LCRC_N1500"), oracle_models("PHN_RU_SPDAT_LCRC_N1500")
+    a = synth_audio(80000, 1, seed=1000, fmt="alaw", fs=8000, first_utt=99)[0].tobytes()
+    r.set_wave_format("alaw")
+    try:
+        mel = r.mel([a])[0]
+        want_mel = o.mel(a, fmt="alaw")
+        assert_bits_equal(mel, want_mel, "mel")
+        post = r.posteriors([mel])[0]
+        want = o.posteriors(want_mel)
+        assert np.isfinite(want[783]).all() and np.ptp(want[783, :10]) < 0.2      # (the degenerate frame is finite)
+        assert_bits_equal(post[760:800], want[760:800], "posteriors around the overflow frame")
+        assert labels_equal(r.recognize([a])[0], o.recognize(a, fmt="alaw"))
+    finally:
+        r.set_wave_format("lin16")
+
+
 def test_batch_equals_singletons_and_is_order_independent(recs):
     """Size-independent property: utterances are independent, so batching must not change results."""
     r = recs("PHN_CZ_SPDAT_LCRC_N1500")

@@ -2,10 +2,11 @@
 
 The exact fp32 mode is bit-identical to the reference (tests/test_gpu_parity.py); this mode is the fast path and
 carries a STATED, MEASURED bound instead (DESIGN.md "Precision of the tensor-core mode"):
-    |ln p_tc - ln p_ref| <= 0.15 * max(1, |ln p_ref|)      on the 3P decoder-visible columns, every frame
-    99.9 % of all values within 1e-2 of that same measure, frame arg-max agreement >= 97 %
-and, end to end, the decoded phone sequence must agree with the reference's on >= 90 % of the segments
-(labels + boundaries) of the golden utterances.  The reference side is the fixture built from the reference's own
+    |ln p_tc - ln p_ref| <= 0.08 * max(1, |ln p_ref|)      on the 3P decoder-visible columns, every frame
+    99.9 % of all values within 7e-3 of that same measure, frame arg-max agreement >= 99 %
+(twice what tools/tc_bound.py measures over all 998 000 frames of the benchmark's own synthetic set: max 3.5e-2,
+p99.9 3.6e-3, arg-max 99.9 %; profiles/r2_tc_bound_*.json) and, end to end, the decoded segments of the golden utterances
+must be the reference's (labels + boundaries), with at most one segment of an utterance differing.  The reference side is the fixture built from the reference's own
 binary (tests/golden), not a run of this library."""
 import numpy as np
 import pytest
@@ -16,8 +17,8 @@ import phnrec_b200 as pb
 
 pytestmark = pytest.mark.gpu
 
-TC_REL_LOGP_MAX = 0.15     # worst single value observed on the fixtures: 4.0e-2
-TC_REL_LOGP_P999 = 1e-2    # observed: 3.5e-3
+TC_REL_LOGP_MAX = 0.08     # worst single value observed: 4.0e-2 (fixtures), 3.7e-2 (synthetic sets, tools/tc_bound.py)
+TC_REL_LOGP_P999 = 7e-3    # observed: 3.5e-3 (fixtures), 2.8e-3 .. 5.6e-3 (synthetic sets)
 RUNS = [("PHN_CZ_SPDAT_LCRC_N1500", "test.raw"), ("PHN_EN_TIMIT_LCRC_N500", "test.raw"),
         ("PHN_HU_SPDAT_LCRC_N1500", "test.raw"), ("PHN_RU_SPDAT_LCRC_N1500", "test.raw"), ("PHN_ES", "es.wav")]
 
@@ -57,7 +58,7 @@ def test_tc_posteriors_within_stated_bound_of_reference(recs, model, audio):
     m = np.abs(lg - lw) / np.maximum(1.0, np.abs(lw))
     assert m.max() <= TC_REL_LOGP_MAX, m.max()
     assert np.quantile(m, 0.999) <= TC_REL_LOGP_P999, np.quantile(m, 0.999)
-    assert (got.argmax(1) == want.argmax(1)).mean() >= 0.97    # (the fixtures keep ~100 rows: one flip = 1 %)
+    assert (got.argmax(1) == want.argmax(1)).mean() >= 0.99    # (the subsampled fixtures keep ~100 rows: one flip = 1 %)
 
 
 @pytest.mark.parametrize("model,audio", RUNS)
@@ -70,7 +71,7 @@ def test_tc_end_to_end_labels_agree_with_reference(recs, model, audio):
     got = [l.split()[:3] for l in pb.format_rec(lab, r.phonemes).splitlines()]
     want = [l.split()[:3] for l in str(ref["rec"]).splitlines()]
     common = len(set(map(tuple, got)) & set(map(tuple, want)))
-    assert common / max(len(want), 1) >= 0.90, (common, len(want))
+    assert len(got) == len(want) and common >= len(want) - 1, (common, len(want))
 
 
 def test_tc_fused_path_equals_staged_path(recs):
@@ -119,7 +120,7 @@ def test_tc_synthetic_batch_labels_close_to_exact_mode(recs):
             sf, se = set(seg(f)), seg(e)
             tot += len(se)
             same += sum(x in sf for x in se)
-        assert same / tot >= 0.90, (same, tot)
+        assert same / tot >= 0.985, (same, tot)      # tools/tc_bound.py: 0.9973 over 1000 utterances
     finally:
         r.set_wave_format("lin16")
         r.set_mlp_mode(pb.MLP_TC_F16)

@@ -34,5 +34,5 @@ names = {2: "L1.beg", 3: "L1.ready", 4: "L1.issued", 5: "L2.beg", 6: "L2.ready",
 print("chunk " + " ".join(f"{names[k]:>9s}" for k in sorted(names)))
 for c in range(12):
     print(f"{c:5d} " + " ".join(f"{(t[c, k] - t0) if t[c, k] else -1:9d}" for k in sorted(names)))
-e2 = ["A.begin", "A.D2seen", "A.end", "B.begin", "B.end", "C.begin", "C.end"]
+e2 = ["A.begin", "A.D2seen", "A.end", "B.begin", "B.end", "C.begin", "C.end"]   # (V6 stamps 1..6 only)
 print("e2 stages of that tile (they run during the next tile):", ", ".join(f"{n} {t[15, i] - t0}" for i, n in enumerate(e2) if t[15, i]))
