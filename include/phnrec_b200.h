@@ -126,11 +126,24 @@ int phn_decode(phn_ctx *ctx, const float *post, const int64_t *frame_off, int n_
 int phn_recognize(phn_ctx *ctx, const void *audio, const int64_t *byte_off, int n_utt, phn_label *labels,
                   int64_t label_cap, int64_t *label_off, int64_t *frame_off_out);
 
+/* Asynchronous pair of phn_recognize for callers that keep the GPU busy (the CLI's list mode, servers): the reference
+ * processes a list strictly one file after the other (SpeechRec::ProcessFileList, srec.cpp:1246-1291); here batch k+1 is
+ * enqueued while batch k is still on the device - its audio goes up under batch k's nets, and batch k's decoder and label
+ * read-back run under batch k+1's front end.  phn_recognize_async enqueues everything and returns; `audio` must stay
+ * valid and unchanged until the matching phn_wait has returned (page-locked memory keeps the copy asynchronous).
+ * phn_wait returns the OLDEST batch not yet waited for, exactly as phn_recognize would have (labels, label_off with
+ * n_utt+1 entries, optional frame_off_out).  At most two batches may be in flight; results are independent of how calls
+ * are interleaved.  On PHN_ERR_CAPACITY the batch stays queued (label_off holds the counts) and phn_wait may be repeated. */
+int phn_recognize_async(phn_ctx *ctx, const void *audio, const int64_t *byte_off, int n_utt);
+int phn_wait(phn_ctx *ctx, phn_label *labels, int64_t label_cap, int64_t *label_off, int64_t *frame_off_out);
+int phn_pending(const phn_ctx *ctx);     /* batches enqueued by phn_recognize_async and not yet returned by phn_wait */
+
 /* -- device-resident variants (inputs already in HBM; used by bench.py and servers) -- */
 /* d_audio is a DEVICE pointer on the context's device; byte_off stays a host array.
- * Runs wave -> mean -> STC -> MLPs -> Viterbi -> traceback on the context's stream and
+ * Runs wave -> mean -> STC -> MLPs on the context's stream and Viterbi + traceback on the context's
+ * decoder stream (so that the decoder of one call runs under the front end of the next), and
  * leaves mel / posteriors / labels in the context's device buffers.  Asynchronous:
- * call phn_sync() or a phn_fetch_* before reading results. */
+ * call phn_sync() (joins both streams) or a phn_fetch_* before reading results. */
 int phn_recognize_device(phn_ctx *ctx, const void *d_audio, const int64_t *byte_off, int n_utt);
 /* Penalty sweep from posteriors already resident in the context (after phn_posteriors): decSoftFunc = log once, then the
  * decoder once per penalty (srec.cpp:1080-1104 with -p); asynchronous, results through phn_fetch_labels (penalty-major). */

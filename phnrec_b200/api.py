@@ -72,6 +72,9 @@ _SYMS = [
     ("phn_posteriors", C.c_int, [C.c_void_p, _f32p, _i64p, C.c_int, _f32p]),
     ("phn_decode", C.c_int, [C.c_void_p, _f32p, _i64p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int64, _i64p]),
     ("phn_recognize", C.c_int, [C.c_void_p, C.c_void_p, _i64p, C.c_int, C.c_void_p, C.c_int64, _i64p, C.c_void_p]),
+    ("phn_recognize_async", C.c_int, [C.c_void_p, C.c_void_p, _i64p, C.c_int]),
+    ("phn_wait", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, _i64p, C.c_void_p]),
+    ("phn_pending", C.c_int, [C.c_void_p]),
     ("phn_recognize_device", C.c_int, [C.c_void_p, C.c_void_p, _i64p, C.c_int]),
     ("phn_decode_device", C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     ("phn_sync", C.c_int, [C.c_void_p]),
@@ -249,6 +252,40 @@ class Recognizer:
         self._ck(self._L.phn_recognize(self._h, audio_ptr, byte_off, len(byte_off) - 1, labels.ctypes.data, labels.size,
                                        label_off, None))
         return int(label_off[-1])
+
+    def recognize_async_raw(self, audio_ptr: int, byte_off: np.ndarray):
+        """Enqueue a batch (phn_recognize_async); the audio must stay valid until the matching wait_raw()."""
+        self._ck(self._L.phn_recognize_async(self._h, audio_ptr, byte_off, len(byte_off) - 1))
+
+    def wait_raw(self, labels: np.ndarray, label_off: np.ndarray) -> int:
+        """Labels of the oldest batch in flight (phn_wait)."""
+        self._ck(self._L.phn_wait(self._h, labels.ctypes.data, labels.size, label_off, None))
+        return int(label_off[-1])
+
+    def pending(self) -> int:
+        return int(self._L.phn_pending(self._h))
+
+    def recognize_pipelined(self, batches):
+        """list of batches (each a list of audio byte strings) -> list of lists of label arrays, two batches in flight."""
+        out, keep = [], []
+        for utts in batches:
+            audio, boff = self._concat_audio(utts)
+            n = len(utts)
+            foff = np.zeros(n + 1, dtype=np.int64)
+            self._ck(self._L.phn_mel(self._h, audio.ctypes.data, boff, n, None, foff))
+            keep.append((audio, boff, n, int(self._L.phn_label_capacity(self._h, foff, n))))
+        done = 0
+        for k, (audio, boff, n, cap) in enumerate(keep):
+            self.recognize_async_raw(audio.ctypes.data, boff)
+            if self.pending() == 2 or k == len(keep) - 1:
+                while self.pending() and (self.pending() == 2 or k == len(keep) - 1):
+                    _, _, nd, capd = keep[done]
+                    labels = np.zeros(capd, dtype=LABEL_DTYPE)
+                    loff = np.zeros(nd + 1, dtype=np.int64)
+                    self.wait_raw(labels, loff)
+                    out.append(self._split_labels(labels, loff))
+                    done += 1
+        return out
 
     def recognize_device(self, d_audio: int, byte_off: np.ndarray):
         self._ck(self._L.phn_recognize_device(self._h, d_audio, byte_off, len(byte_off) - 1))

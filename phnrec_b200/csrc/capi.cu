@@ -30,6 +30,7 @@ int ensure(phn_ctx *c, phn_ctx::Buf &b, size_t bytes)
     if (bytes <= b.cap) return PHN_OK;
     if (b.p) {
         PHN_CUDA(c, cudaStreamSynchronize(c->stream));
+        if (c->vit_stream) PHN_CUDA(c, cudaStreamSynchronize(c->vit_stream));
         PHN_CUDA(c, cudaFree(b.p));
         b.p = nullptr; b.cap = 0;
     }
@@ -111,8 +112,6 @@ static int plan_frames(phn_ctx *c, const int64_t *frame_off, int n_utt, int n_pe
     if ((rc = ensure(c, c->d_mean, sizeof(float) * (size_t)n_utt * c->nbanks))) return rc;
     if ((rc = ensure(c, c->d_post, sizeof(float) * F * c->ldp))) return rc;
     if ((rc = ensure(c, c->d_rec, (size_t)20 * F * n_pen))) return rc;
-    if ((rc = ensure(c, c->d_labels, sizeof(phn_label) * (size_t)c->label_cap))) return rc;
-    if ((rc = ensure(c, c->d_nlab, sizeof(int) * (size_t)nseg))) return rc;
     if ((rc = ensure(c, c->d_pen, sizeof(float) * n_pen))) return rc;
     PHN_CUDA(c, cudaMemcpyAsync(c->d_frame_off.p, c->h_frame_off.data(), sizeof(int64_t) * (n_utt + 1),
                                 cudaMemcpyHostToDevice, c->stream));
@@ -147,13 +146,13 @@ static int plan_audio(phn_ctx *c, const int64_t *byte_off, int n_utt)
     return PHN_OK;
 }
 
-struct StageTimer {  // CUDA-event timing of one kernel family on the context's stream (profiling only)
-    phn_ctx *c; int fam;
-    StageTimer(phn_ctx *c_, int fam_) : c(c_), fam(fam_) { if (c->profiling) cudaEventRecord(c->ev[2 * fam], c->stream); }
+struct StageTimer {  // CUDA-event timing of one kernel family on the stream it is launched on (profiling only)
+    phn_ctx *c; int fam; cudaStream_t s;
+    StageTimer(phn_ctx *c_, int fam_, cudaStream_t s_ = nullptr) : c(c_), fam(fam_), s(s_ ? s_ : c_->stream) { if (c->profiling) cudaEventRecord(c->ev[2 * fam], s); }
     ~StageTimer()
     {
         if (!c->profiling) return;
-        cudaEventRecord(c->ev[2 * fam + 1], c->stream);
+        cudaEventRecord(c->ev[2 * fam + 1], s);
         cudaEventSynchronize(c->ev[2 * fam + 1]);
         float ms = 0.f;
         cudaEventElapsedTime(&ms, c->ev[2 * fam], c->ev[2 * fam + 1]);
@@ -212,6 +211,10 @@ static int run_posteriors(phn_ctx *c, bool front_done = false)
     const int64_t F = c->total_frames, ch = c->chunk_frames;
     if (ch == 0) return PHN_OK;
     c->logp_valid = 0;
+    if (c->vit_pending) {   // the previous batch's decoder (side stream) still owns d_logp and its offset copies
+        PHN_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_vit_done, 0));
+        c->vit_pending = 0;
+    }
     for (int64_t f0 = 0; f0 < F; f0 += ch) {
         const int64_t nf = F - f0 < ch ? F - f0 : ch;
         if (!front_done) { StageTimer t(c, PHN_K_STC); if ((rc = launch_stc(c, f0, nf))) return rc; }
@@ -222,13 +225,83 @@ static int run_posteriors(phn_ctx *c, bool front_done = false)
     return PHN_OK;
 }
 
-static int run_decode(phn_ctx *c, const float *penalties, int n_pen)
+// Runs the decoder for the planned batch into the next result slot.
+// side: on the context's decoder stream (audio -> labels path), so that the next call's front end may start while this
+// decoder is still running; `stream` waits for ev_vit_done before its nets touch d_logp again (run_posteriors).  Everything
+// the decoder reads that the NEXT batch's planning rewrites (frame and capacity offsets) is the slot's own copy.
+static int run_decode(phn_ctx *c, const float *penalties, int n_pen, bool side = false)
 {
     c->h_pen.resize(n_pen);  // member: stays alive until the (staged) copy has been consumed
     for (int k = 0; k < n_pen; ++k) c->h_pen[k] = penalties ? penalties[k] : c->wpenalty;
+    if (c->vit_pending) {   // (a decode that does not follow run_posteriors, e.g. phn_decode_device after phn_recognize_device)
+        PHN_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_vit_done, 0));
+        c->vit_pending = 0;
+    }
     PHN_CUDA(c, cudaMemcpyAsync(c->d_pen.p, c->h_pen.data(), sizeof(float) * n_pen, cudaMemcpyHostToDevice, c->stream));
-    StageTimer t(c, PHN_K_VIT);
-    return launch_viterbi(c, (const float *)c->d_pen.p, n_pen);
+    if (getenv("PHNREC_VIT_INLINE")) side = false;   // (kernel development: decoder on the main stream)
+    const int nseg = c->n_utt * n_pen;
+    for (int i = 0; i < c->n_pend; ++i)
+        if (c->pend[i] == c->slot_w) return fail(c, PHN_ERR_ARG, "both result slots hold asynchronous batches that have not been waited for (phn_wait)\n");
+    phn_ctx::DecSlot &sl = c->slot[c->slot_w];
+    c->slot_last = c->slot_w;
+    c->slot_w ^= 1;
+    int rc;
+    if ((rc = ensure(c, sl.d_labels, sizeof(phn_label) * (size_t)c->label_cap))) return rc;
+    if ((rc = ensure(c, sl.d_nlab, sizeof(int) * (size_t)nseg))) return rc;
+    if ((rc = ensure(c, sl.d_frame_off, sizeof(int64_t) * (c->n_utt + 1)))) return rc;
+    if ((rc = ensure(c, sl.d_lab_off, sizeof(int64_t) * (nseg + 1)))) return rc;
+    sl.h_lab_off = c->h_lab_off; sl.h_frame_off = c->h_frame_off;
+    sl.n_utt = c->n_utt; sl.n_pen = n_pen;
+    PHN_CUDA(c, cudaMemcpyAsync(sl.d_frame_off.p, c->d_frame_off.p, sizeof(int64_t) * (c->n_utt + 1), cudaMemcpyDeviceToDevice, c->stream));
+    PHN_CUDA(c, cudaMemcpyAsync(sl.d_lab_off.p, c->d_lab_off.p, sizeof(int64_t) * (nseg + 1), cudaMemcpyDeviceToDevice, c->stream));
+    if (!side) {
+        sl.s = c->stream;
+        StageTimer t(c, PHN_K_VIT);
+        return launch_viterbi(c, (const float *)c->d_pen.p, n_pen, c->stream, sl);
+    }
+    PHN_CUDA(c, cudaEventRecord(c->ev_mlp_done, c->stream));
+    PHN_CUDA(c, cudaStreamWaitEvent(c->vit_stream, c->ev_mlp_done, 0));
+    sl.s = c->vit_stream;
+    {
+        StageTimer t(c, PHN_K_VIT, c->vit_stream);
+        rc = launch_viterbi(c, (const float *)c->d_pen.p, n_pen, c->vit_stream, sl);
+    }
+    if (rc) return rc;
+    PHN_CUDA(c, cudaEventRecord(c->ev_vit_done, c->vit_stream));
+    c->vit_pending = 1;
+    return PHN_OK;
+}
+
+// Labels of one result slot -> host (penalty-major segments).  Follows the stream the slot's decoder ran on.
+static int fetch_slot(phn_ctx *c, phn_ctx::DecSlot &sl, phn_label *labels, int64_t label_cap, int64_t *label_off)
+{
+    const int nseg = sl.n_utt * sl.n_pen;
+    cudaStream_t s = sl.s ? sl.s : c->stream;
+    sl.h_nlab.resize((size_t)nseg);
+    if (nseg)
+        PHN_CUDA(c, cudaMemcpyAsync(sl.h_nlab.data(), sl.d_nlab.p, sizeof(int) * nseg, cudaMemcpyDeviceToHost, s));
+    PHN_CUDA(c, cudaStreamSynchronize(s));
+    int64_t total = 0;
+    std::vector<int64_t> off((size_t)nseg + 1, 0);
+    for (int k = 0; k < nseg; ++k) {
+        const int64_t cap = sl.h_lab_off[k + 1] - sl.h_lab_off[k];
+        if (sl.h_nlab[k] > cap) return fail(c, PHN_ERR_CAPACITY, "internal label capacity exceeded (segment %d)\n", k);
+        total += sl.h_nlab[k];
+        off[k + 1] = total;
+    }
+    if (label_off) memcpy(label_off, off.data(), sizeof(int64_t) * (nseg + 1));
+    if (!labels) return PHN_OK;
+    if (label_cap < total) return fail(c, PHN_ERR_CAPACITY, "label buffer too small: %lld needed\n", (long long)total);
+    if (total == 0) return PHN_OK;
+    // gather the produced labels into one contiguous run on the device, then a single D2H copy
+    int rc;
+    if ((rc = ensure(c, sl.d_coff, sizeof(int64_t) * (nseg + 1)))) return rc;
+    if ((rc = ensure(c, sl.d_labels_c, sizeof(phn_label) * (size_t)total))) return rc;
+    PHN_CUDA(c, cudaMemcpyAsync(sl.d_coff.p, off.data(), sizeof(int64_t) * (nseg + 1), cudaMemcpyHostToDevice, s));
+    if ((rc = launch_compact_labels(c, nseg, sl))) return rc;
+    PHN_CUDA(c, cudaMemcpyAsync(labels, sl.d_labels_c.p, sizeof(phn_label) * (size_t)total, cudaMemcpyDeviceToHost, s));
+    PHN_CUDA(c, cudaStreamSynchronize(s));
+    return PHN_OK;
 }
 
 }  // namespace phn
@@ -396,6 +469,10 @@ int phn_create(const char *cfg_dir, int device, phn_ctx **out)
     for (auto &e : c->ev_copy)
         if ((rc = cu(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "cudaEventCreate"))) return bail(rc);
     if ((rc = cu(cudaEventCreateWithFlags(&c->ev_free, cudaEventDisableTiming), "cudaEventCreate"))) return bail(rc);
+    if ((rc = cu(cudaStreamCreateWithFlags(&c->vit_stream, cudaStreamNonBlocking), "cudaStreamCreate"))) return bail(rc);
+    if ((rc = cu(cudaEventCreateWithFlags(&c->ev_mlp_done, cudaEventDisableTiming), "cudaEventCreate"))) return bail(rc);
+    if ((rc = cu(cudaEventCreateWithFlags(&c->ev_vit_done, cudaEventDisableTiming), "cudaEventCreate"))) return bail(rc);
+    if ((rc = cu(cudaEventCreateWithFlags(&c->ev_audio_free, cudaEventDisableTiming), "cudaEventCreate"))) return bail(rc);
     for (int i = 0; i < 2 * PHN_K_COUNT; ++i)
         if ((rc = cu(cudaEventCreate(&c->ev[i]), "cudaEventCreate"))) return bail(rc);
     for (int i = 0; i < 3; ++i)
@@ -429,10 +506,13 @@ void phn_destroy(phn_ctx *c)
     if (c->stream) {
         cudaSetDevice(c->device);
         cudaStreamSynchronize(c->stream);
+        if (c->vit_stream) cudaStreamSynchronize(c->vit_stream);
     }
     phn_ctx::Buf *bufs[] = {&c->d_audio, &c->d_byte_off, &c->d_frame_off, &c->d_lab_off, &c->d_mel, &c->d_mean, &c->d_post,
-                            &c->d_rec, &c->d_labels, &c->d_nlab, &c->d_pen, &c->d_x0, &c->d_x1, &c->d_h, &c->d_xm,
-                            &c->d_x0h, &c->d_x1h, &c->d_xmh, &c->d_tile_ctr, &c->d_coff, &c->d_labels_c, &c->d_logp, &c->d_pair_off};
+                            &c->d_rec, &c->d_pen, &c->d_x0, &c->d_x1, &c->d_h, &c->d_xm,
+                            &c->d_x0h, &c->d_x1h, &c->d_xmh, &c->d_tile_ctr, &c->d_logp, &c->d_pair_off,
+                            &c->slot[0].d_labels, &c->slot[0].d_nlab, &c->slot[0].d_lab_off, &c->slot[0].d_frame_off, &c->slot[0].d_coff, &c->slot[0].d_labels_c,
+                            &c->slot[1].d_labels, &c->slot[1].d_nlab, &c->slot[1].d_lab_off, &c->slot[1].d_frame_off, &c->slot[1].d_coff, &c->slot[1].d_labels_c};
     for (auto *b : bufs)
         if (b->p) cudaFree(b->p);
     mlp_tc_release(c);
@@ -456,6 +536,10 @@ void phn_destroy(phn_ctx *c)
         if (e) cudaEventDestroy(e);
     if (c->ev_free) cudaEventDestroy(c->ev_free);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    if (c->ev_mlp_done) cudaEventDestroy(c->ev_mlp_done);
+    if (c->ev_vit_done) cudaEventDestroy(c->ev_vit_done);
+    if (c->ev_audio_free) cudaEventDestroy(c->ev_audio_free);
+    if (c->vit_stream) cudaStreamDestroy(c->vit_stream);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -530,6 +614,7 @@ int phn_sync(phn_ctx *c)
     if (!c) return PHN_ERR_ARG;
     PHN_CUDA(c, cudaSetDevice(c->device));
     PHN_CUDA(c, cudaStreamSynchronize(c->stream));
+    PHN_CUDA(c, cudaStreamSynchronize(c->vit_stream));
     return PHN_OK;
 }
 void *phn_device_alloc(phn_ctx *c, int64_t n)
@@ -581,7 +666,7 @@ static int recognize_after_wave(phn_ctx *c, bool front_done = false)
     c->fuse_logp = 0;
     c->fast_front = 0;
     if (rc) return rc;
-    rc = run_decode(c, nullptr, 1);
+    rc = run_decode(c, nullptr, 1, true);
     c->logp_valid = 0;
     return rc;
 }
@@ -649,32 +734,11 @@ int phn_fetch_labels(phn_ctx *c, phn_label *labels, int64_t label_cap, int64_t *
 {
     if (!c) return PHN_ERR_ARG;
     PHN_CUDA(c, cudaSetDevice(c->device));
-    const int nseg = c->n_utt * c->n_pen;
-    c->h_nlab.resize((size_t)nseg);
-    if (nseg)
-        PHN_CUDA(c, cudaMemcpyAsync(c->h_nlab.data(), c->d_nlab.p, sizeof(int) * nseg, cudaMemcpyDeviceToHost, c->stream));
-    PHN_CUDA(c, cudaStreamSynchronize(c->stream));
-    int64_t total = 0;
-    std::vector<int64_t> off((size_t)nseg + 1, 0);
-    for (int s = 0; s < nseg; ++s) {
-        const int64_t cap = c->h_lab_off[s + 1] - c->h_lab_off[s];
-        if (c->h_nlab[s] > cap) return fail(c, PHN_ERR_CAPACITY, "internal label capacity exceeded (segment %d)\n", s);
-        total += c->h_nlab[s];
-        off[s + 1] = total;
+    if (c->slot_last < 0) {   // nothing decoded yet: an empty result
+        if (label_off) label_off[0] = 0;
+        return PHN_OK;
     }
-    if (label_off) memcpy(label_off, off.data(), sizeof(int64_t) * (nseg + 1));
-    if (!labels) return PHN_OK;
-    if (label_cap < total) return fail(c, PHN_ERR_CAPACITY, "label buffer too small: %lld needed\n", (long long)total);
-    if (total == 0) return PHN_OK;
-    // gather the produced labels into one contiguous run on the device, then a single D2H copy
-    int rc;
-    if ((rc = ensure(c, c->d_coff, sizeof(int64_t) * (nseg + 1)))) return rc;
-    if ((rc = ensure(c, c->d_labels_c, sizeof(phn_label) * (size_t)total))) return rc;
-    PHN_CUDA(c, cudaMemcpyAsync(c->d_coff.p, off.data(), sizeof(int64_t) * (nseg + 1), cudaMemcpyHostToDevice, c->stream));
-    if ((rc = launch_compact_labels(c, nseg))) return rc;
-    PHN_CUDA(c, cudaMemcpyAsync(labels, c->d_labels_c.p, sizeof(phn_label) * (size_t)total, cudaMemcpyDeviceToHost, c->stream));
-    PHN_CUDA(c, cudaStreamSynchronize(c->stream));
-    return PHN_OK;
+    return fetch_slot(c, c->slot[c->slot_last], labels, label_cap, label_off);
 }
 
 int phn_mel(phn_ctx *c, const void *audio, const int64_t *byte_off, int n_utt, float *mel_out, int64_t *frame_off)
@@ -744,14 +808,17 @@ int phn_decode_device(phn_ctx *c, const float *penalties, int n_pen)
     return run_decode(c, penalties, n_pen);
 }
 
-int phn_recognize(phn_ctx *c, const void *audio, const int64_t *byte_off, int n_utt, phn_label *labels, int64_t label_cap,
-                  int64_t *label_off, int64_t *frame_off_out)
+// audio (host) -> labels, everything enqueued, nothing waited for.  wait = false: the result slot is queued for phn_wait.
+static int recognize_host(phn_ctx *c, const void *audio, const int64_t *byte_off, int n_utt, phn_label *labels, int64_t label_cap,
+                          int64_t *label_off, int64_t *frame_off_out, bool wait)
 {
     if (!c) return PHN_ERR_ARG;
     if (!byte_off || n_utt < 0) return fail(c, PHN_ERR_ARG, "invalid batch\n");
+    if (wait && c->n_pend) return fail(c, PHN_ERR_ARG, "asynchronous batches are in flight: phn_wait for them first\n");
+    if (!wait && c->n_pend >= 2) return fail(c, PHN_ERR_ARG, "two asynchronous batches are already in flight: phn_wait first\n");
     PHN_CUDA(c, cudaSetDevice(c->device));
     int rc;
-    const bool trace = getenv("PHNREC_TRACE") != nullptr;
+    const bool trace = wait && getenv("PHNREC_TRACE") != nullptr;
     auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     const double tt0 = now();
     struct TraceEvents {   // (destroyed on every exit path)
@@ -765,6 +832,7 @@ int phn_recognize(phn_ctx *c, const void *audio, const int64_t *byte_off, int n_
     // offsets are validated (start at 0, non-decreasing) before anything is sized by them or read through them
     if ((rc = plan_audio(c, byte_off, n_utt))) return rc;
     if (!audio && c->total_bytes > 0) return fail(c, PHN_ERR_ARG, "null audio buffer\n");
+    const void *audio_before = c->d_audio.p;
     if ((rc = ensure(c, c->d_audio, (size_t)c->total_bytes + 16))) return rc;
     const double tt1 = now();
     if (trace) cudaEventRecord(tev[0], c->stream);
@@ -783,8 +851,14 @@ int phn_recognize(phn_ctx *c, const void *audio, const int64_t *byte_off, int n_
                        (c->nbanks == 15 || c->nbanks == 23);   // (the row-range form of K-stc exists for the shipped bank counts)
     c->fuse_logp = 0; c->fast_front = 0;
     if (rc) return rc;
-    PHN_CUDA(c, cudaEventRecord(c->ev_free, c->stream));             // (buffer growth and its zero fill are stream work)
-    PHN_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->ev_free, 0));
+    // The copy may start as soon as the previous call's K-wave has read the buffer - while that call's nets are still
+    // running (asynchronous calls) - unless the buffer was just regrown (its zero fill is work of `stream`).
+    if (c->audio_free_valid && c->d_audio.p == audio_before) {
+        PHN_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->ev_audio_free, 0));
+    } else {
+        PHN_CUDA(c, cudaEventRecord(c->ev_free, c->stream));
+        PHN_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->ev_free, 0));
+    }
     {
         StageTimer t(c, PHN_K_WAVE);
         int u0 = 0;
@@ -800,6 +874,10 @@ int phn_recognize(phn_ctx *c, const void *audio, const int64_t *byte_off, int n_
             PHN_CUDA(c, cudaEventRecord(c->ev_copy[g], c->copy_stream));
             PHN_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_copy[g], 0));
             if ((rc = launch_wave(c, c->d_audio.p, u0, u1))) return rc;
+            if (g == ng - 1) {   // the audio buffer has been consumed
+                PHN_CUDA(c, cudaEventRecord(c->ev_audio_free, c->stream));
+                c->audio_free_valid = 1;
+            }
             if (front) {
                 c->fast_front = 1;
                 rc = launch_sentence_mean(c, u0, u1);
@@ -813,6 +891,10 @@ int phn_recognize(phn_ctx *c, const void *audio, const int64_t *byte_off, int n_
     const double tt2 = now();
     if (trace) cudaEventRecord(tev[1], c->stream);
     if ((rc = recognize_after_wave(c, front))) return rc;
+    if (!wait) {
+        c->pend[c->n_pend++] = c->slot_last;
+        return PHN_OK;
+    }
     const double tt3 = now();
     if (trace) { cudaEventRecord(tev[2], c->stream); cudaStreamSynchronize(c->stream); }
     const double tt4 = now();
@@ -824,12 +906,41 @@ int phn_recognize(phn_ctx *c, const void *audio, const int64_t *byte_off, int n_
         cudaEventElapsedTime(&e01, tev[0], tev[1]); cudaEventElapsedTime(&e12, tev[1], tev[2]);
         (void)ng;
         FILE *tf = fopen(getenv("PHNREC_TRACE"), "a");
-        if (tf) fprintf(tf, "[trace] n_utt %d host: plan %.3f enqueue-front %.3f enqueue-rest %.3f wait-gpu %.3f fetch %.3f total %.3f | gpu: front-end span %.3f (last copy landed at %.3f) mlp+vit %.3f\n",
+        if (tf) fprintf(tf, "[trace] n_utt %d host: plan %.3f enqueue-front %.3f enqueue-rest %.3f wait-gpu %.3f fetch %.3f total %.3f | gpu: front-end span %.3f (last copy landed at %.3f) mlp(+vit on its own stream) %.3f\n",
                 n_utt, tt1 - tt0, tt2 - tt1, tt3 - tt2, tt4 - tt3, tt5 - tt4, tt5 - tt0, e01, ec, e12);
         if (tf) fclose(tf);
     }
     return rc;
 }
+
+int phn_recognize(phn_ctx *c, const void *audio, const int64_t *byte_off, int n_utt, phn_label *labels, int64_t label_cap,
+                  int64_t *label_off, int64_t *frame_off_out)
+{
+    return recognize_host(c, audio, byte_off, n_utt, labels, label_cap, label_off, frame_off_out, true);
+}
+
+int phn_recognize_async(phn_ctx *c, const void *audio, const int64_t *byte_off, int n_utt)
+{
+    return recognize_host(c, audio, byte_off, n_utt, nullptr, 0, nullptr, nullptr, false);
+}
+
+int phn_wait(phn_ctx *c, phn_label *labels, int64_t label_cap, int64_t *label_off, int64_t *frame_off_out)
+{
+    if (!c) return PHN_ERR_ARG;
+    if (!c->n_pend) return fail(c, PHN_ERR_ARG, "phn_wait: no asynchronous batch in flight\n");
+    PHN_CUDA(c, cudaSetDevice(c->device));
+    phn_ctx::DecSlot &sl = c->slot[c->pend[0]];
+    if (frame_off_out) memcpy(frame_off_out, sl.h_frame_off.data(), sizeof(int64_t) * (sl.n_utt + 1));
+    const int rc = fetch_slot(c, sl, labels, label_cap, label_off);
+    // a capacity error leaves the batch queued (the caller may come back with a larger buffer); anything else retires it
+    if (rc != PHN_ERR_CAPACITY || !labels) {
+        c->pend[0] = c->pend[1];
+        --c->n_pend;
+    }
+    return rc;
+}
+
+int phn_pending(const phn_ctx *c) { return c ? c->n_pend : 0; }
 
 // Debug aid (not part of the stable ABI surface used by the reference binding): the next tensor-core launches of
 // net `which` record clock64() timestamps of CTA 0's second tile into a 16 x 16 table; which < 0 reads it back.

@@ -71,6 +71,14 @@ struct phn_ctx {
     cudaStream_t copy_stream = nullptr;      // H2D of audio groups, overlapped with K-wave of the previous group (phn_recognize)
     cudaEvent_t ev_copy[16] = {nullptr};     // group g has landed
     cudaEvent_t ev_free = nullptr;           // the audio buffer's previous readers are done
+    // The decoder of the audio -> labels path runs on its own stream: K-vit is one warp per utterance (latency bound, a
+    // fraction of the SMs' issue slots), so the decoder of batch k runs under the front end (K-wave, K-stc) of batch k+1.
+    cudaStream_t vit_stream = nullptr;
+    cudaEvent_t ev_mlp_done = nullptr;       // ln p of the batch is complete (recorded on `stream`)
+    cudaEvent_t ev_vit_done = nullptr;       // the decoder has consumed it (recorded on `vit_stream`)
+    int vit_pending = 0;                     // a decoder launch on vit_stream has not been waited for by `stream` yet
+    cudaEvent_t ev_audio_free = nullptr;     // K-wave of the last host-audio call has consumed d_audio (the next call's copy may start)
+    int audio_free_valid = 0;
     std::string err;
     std::string cfg_dir;
     phn::Config cfg;
@@ -105,12 +113,24 @@ struct phn_ctx {
     int64_t total_bytes = 0, total_frames = 0, label_cap = 0;
     std::vector<int64_t> h_byte_off, h_frame_off, h_lab_off;
     struct Buf { void *p = nullptr; size_t cap = 0; };
-    Buf d_audio, d_byte_off, d_frame_off, d_lab_off, d_mel, d_mean, d_post, d_rec, d_labels, d_nlab, d_pen;
+    Buf d_audio, d_byte_off, d_frame_off, d_lab_off, d_mel, d_mean, d_post, d_rec, d_pen;
     Buf d_x0, d_x1, d_h, d_xm, d_x0h, d_x1h, d_xmh;  // MLP workspace (per frame chunk)
-    Buf d_tile_ctr, d_coff, d_labels_c, d_logp;
+    Buf d_tile_ctr, d_logp;
+    // Results of one decoder launch.  Two slots, used alternately: the labels of batch k can be fetched (phn_wait) while
+    // batch k+1 is already running (phn_recognize_async).  A slot carries its own copies of the frame / capacity offsets:
+    // the next batch's planning rewrites d_frame_off / d_lab_off and the host vectors.
+    struct DecSlot {
+        Buf d_labels, d_nlab, d_lab_off, d_frame_off, d_coff, d_labels_c;
+        std::vector<int64_t> h_lab_off, h_frame_off;
+        std::vector<int32_t> h_nlab;
+        int n_utt = 0, n_pen = 1;
+        cudaStream_t s = nullptr;            // the stream the decoder ran on (fetching follows it)
+    } slot[2];
+    int slot_w = 0;                          // the slot the next decode writes
+    int slot_last = -1;                      // the slot of the most recent decode (phn_fetch_labels)
+    int pend[2] = {0, 0}, n_pend = 0;        // slots of asynchronous batches not yet waited for, oldest first
     Buf d_pair_off;                          // [n_utt + 1] prefix sums of ceil(T_u / 2): work units of the frame-pair K-wave
     std::vector<int64_t> h_pair_off;
-    std::vector<int32_t> h_nlab;
     std::vector<float> h_pen;
     int64_t chunk_frames = 0;
     // profiling
@@ -141,8 +161,8 @@ int launch_stc(phn_ctx *c, int64_t f0, int64_t nf, int64_t row_lo = 0, int64_t r
                                                                                                   // only rows row_lo <= frame < row_hi are produced
 int launch_mlp_exact(phn_ctx *c, int64_t f0, int64_t nf);                  // k_mlp_exact.cu
 int launch_mlp_tc(phn_ctx *c, int64_t f0, int64_t nf);                     // k_mlp_tc.cu
-int launch_viterbi(phn_ctx *c, const float *d_pen, int n_pen);             // k_vit.cu
-int launch_compact_labels(phn_ctx *c, int nseg);                           // k_vit.cu
+int launch_viterbi(phn_ctx *c, const float *d_pen, int n_pen, cudaStream_t s, phn_ctx::DecSlot &sl);   // k_vit.cu
+int launch_compact_labels(phn_ctx *c, int nseg, phn_ctx::DecSlot &sl);     // k_vit.cu
 int launch_logf_range(phn_ctx *c, uint32_t first_bits, int64_t n, float *d_out);   // k_vit.cu (verification aid)
 int launch_synth(phn_ctx *c, void *d_audio, int64_t bytes_per_utt, int n_utt, uint64_t seed);  // k_synth.cu
 int mlp_tc_fill_merger_bias(phn_ctx *c, int64_t rows);                     // constant-1 bias columns of the merger image

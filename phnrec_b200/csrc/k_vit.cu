@@ -314,7 +314,7 @@ __global__ void __launch_bounds__(32) k_viterbi(VitArgs a)
     }
 }
 
-int launch_viterbi(phn_ctx *c, const float *d_pen, int n_pen)
+int launch_viterbi(phn_ctx *c, const float *d_pen, int n_pen, cudaStream_t s, phn_ctx::DecSlot &sl)
 {
     const int nseg = c->n_utt * n_pen;
     if (nseg == 0) return PHN_OK;
@@ -324,14 +324,14 @@ int launch_viterbi(phn_ctx *c, const float *d_pen, int n_pen)
     if (c->total_frames && !c->logp_valid) {   // (the tensor-core merger writes ln p itself when it feeds the decoder directly)
         int64_t blocks = (c->total_frames + 7) / 8;
         if (blocks > (int64_t)c->num_sms * 16) blocks = (int64_t)c->num_sms * 16;
-        k_log_post<<<(unsigned)blocks, 256, 0, c->stream>>>((const float *)c->d_post.p, c->ldp, ncols, c->total_frames, (float *)c->d_logp.p);
+        k_log_post<<<(unsigned)blocks, 256, 0, s>>>((const float *)c->d_post.p, c->ldp, ncols, c->total_frames, (float *)c->d_logp.p);
         PHN_CUDA(c, cudaGetLastError());
         c->k_launches[PHN_K_VIT] += 1;
     }
     VitArgs a;
     a.logp = (const float *)c->d_logp.p;
     a.ld = c->ldp;
-    a.frame_off = (const int64_t *)c->d_frame_off.p;
+    a.frame_off = (const int64_t *)sl.d_frame_off.p;
     a.n_utt = c->n_utt; a.P = c->P; a.H = c->hist;
     a.total_frames = c->total_frames;
     a.pen = d_pen;
@@ -339,9 +339,9 @@ int launch_viterbi(phn_ctx *c, const float *d_pen, int n_pen)
     int *rec = (int *)c->d_rec.p;
     a.r_hphn = rec; a.r_hlen = rec + R; a.r_bp = rec + 2 * R; a.r_bl = rec + 3 * R;
     a.r_halpha = (float *)(rec + 4 * R);
-    a.labels = (phn_label *)c->d_labels.p;
-    a.lab_off = (const int64_t *)c->d_lab_off.p;
-    a.nlab = (int *)c->d_nlab.p;
+    a.labels = (phn_label *)sl.d_labels.p;
+    a.lab_off = (const int64_t *)sl.d_lab_off.p;
+    a.nlab = (int *)sl.d_nlab.p;
     const int ppl = (c->P + 31) / 32;
     const bool tiled = c->logp_valid != 0;   // ln p came from the tensor-core merger's epilogue (tiled layout)
     c->logp_layout = tiled ? 2 : 1;
@@ -351,8 +351,8 @@ int launch_viterbi(phn_ctx *c, const float *d_pen, int n_pen)
     do {                                                                    \
         if (tiled) {                                                        \
             PHN_CUDA(c, cudaFuncSetAttribute(k_viterbi<N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vsmem)); \
-            k_viterbi<N, true><<<nseg, 32, vsmem, c->stream>>>(a);          \
-        } else k_viterbi<N, false><<<nseg, 32, 0, c->stream>>>(a);          \
+            k_viterbi<N, true><<<nseg, 32, vsmem, s>>>(a);          \
+        } else k_viterbi<N, false><<<nseg, 32, 0, s>>>(a);                  \
     } while (0)
     switch (ppl) {
         case 1: PHN_VIT(1); break;
@@ -379,11 +379,11 @@ __global__ void k_compact_labels(const phn_label *__restrict__ src, const int64_
     for (int i = threadIdx.x; i < n; i += blockDim.x) d[i] = s[i];
 }
 
-int launch_compact_labels(phn_ctx *c, int nseg)
+int launch_compact_labels(phn_ctx *c, int nseg, phn_ctx::DecSlot &sl)
 {
     if (nseg == 0) return PHN_OK;
-    k_compact_labels<<<nseg, 64, 0, c->stream>>>((const phn_label *)c->d_labels.p, (const int64_t *)c->d_lab_off.p,
-                                                 (const int64_t *)c->d_coff.p, (phn_label *)c->d_labels_c.p);
+    k_compact_labels<<<nseg, 64, 0, sl.s>>>((const phn_label *)sl.d_labels.p, (const int64_t *)sl.d_lab_off.p,
+                                            (const int64_t *)sl.d_coff.p, (phn_label *)sl.d_labels_c.p);
     PHN_CUDA(c, cudaGetLastError());
     c->k_launches[PHN_K_VIT] += 1;
     return PHN_OK;
