@@ -116,15 +116,34 @@ class ClockSampler(threading.Thread):
         self.index, self.rows, self._stop_evt = index, [], threading.Event()
 
     def run(self):
+        # NVML in-process (the library nvidia-smi itself reads): a query costs microseconds.  Spawning nvidia-smi every
+        # 100 ms stalls the driver for tens of milliseconds per call - invisible to per-kernel events, but inside a span
+        # timed end to end.  nvidia-smi remains the fallback when the NVML binding is missing.
+        h = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+        except Exception:
+            h = None
         while not self._stop_evt.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([x.strip() for x in out.split(",")])
+                if h is not None:
+                    sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+                    mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+                    rs = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h) if hasattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons") \
+                        else pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                    pw = pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0
+                    act = lambda bit: "Active" if rs & bit else "Not Active"
+                    self.rows.append([str(sm), str(mx), act(0x8), act(0x40), act(0x20), act(0x4), f"{pw:.2f}"])
+                else:
+                    out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                         capture_output=True, text=True, timeout=5).stdout.strip()
+                    if out:
+                        self.rows.append([x.strip() for x in out.split(",")])
             except Exception:
                 pass
-            self._stop_evt.wait(0.1)
+            self._stop_evt.wait(0.02 if h is not None else 0.1)
 
     def stop(self):
         self._stop_evt.set()

@@ -45,6 +45,68 @@ int ensure(phn_ctx *c, phn_ctx::Buf &b, size_t bytes)
     return PHN_OK;
 }
 
+// ---- PHNREC_TIMELINE (development aid): per batch, events 0 copy stream released, 1 first K-wave may start, 2 front end
+// enqueued work done, 3 nets done, 4 decoder may start, 5 decoder done; host clock at 0 call entered, 1 call returned,
+// 2 wait entered, 3 wait returned.
+static double tl_now() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+static void tl_begin(phn_ctx *c)
+{
+    if (c->tl_on < 0) c->tl_on = getenv("PHNREC_TIMELINE") != nullptr;
+    c->tl_cur = -1;
+    if (!c->tl_on || c->tl.size() >= 256) return;
+    c->tl.emplace_back();
+    c->tl_cur = (int)c->tl.size() - 1;
+    c->tl[c->tl_cur].h[0] = tl_now();
+}
+static void tl_ev(phn_ctx *c, int i, cudaStream_t s)
+{
+    if (c->tl_cur < 0) return;
+    cudaEvent_t &e = c->tl[c->tl_cur].e[i];
+    if (!e) cudaEventCreate(&e);
+    cudaEventRecord(e, s);
+}
+static void tl_host(phn_ctx *c, int row, int i) { if (row >= 0 && row < (int)c->tl.size()) c->tl[row].h[i] = tl_now(); }
+static void tl_dump(phn_ctx *c)
+{
+    if (c->tl_on <= 0 || c->tl.empty()) return;
+    FILE *f = fopen(getenv("PHNREC_TIMELINE"), "a");
+    cudaEvent_t ref = nullptr;
+    for (auto &r : c->tl) for (int i = 0; i < 6 && !ref; ++i) if (r.e[i]) ref = r.e[i];
+    if (f) fprintf(f, "# batch | device ms since the first event: copy-go wave-go front-done nets-done vit-go vit-done copy0-done copyN-done | host ms since the first call: call-in call-out wait-in wait-out\n");
+    const double h0 = c->tl[0].h[0];
+    int k = 0;
+    for (auto &r : c->tl) {
+        if (f) fprintf(f, "%3d |", k++);
+        for (int i = 0; i < 6; ++i) {
+            float ms = -1.f;
+            if (r.e[i] && ref && cudaEventElapsedTime(&ms, ref, r.e[i]) != cudaSuccess) { ms = -1.f; cudaGetLastError(); }
+            if (f) fprintf(f, " %9.3f", ms);
+        }
+        for (int i = 0; i < 2; ++i) {
+            float ms = -1.f;
+            if (r.cg[i] && ref && cudaEventElapsedTime(&ms, ref, r.cg[i]) != cudaSuccess) { ms = -1.f; cudaGetLastError(); }
+            if (f) fprintf(f, " %9.3f", ms);
+        }
+        if (f) fprintf(f, " |");
+        for (int i = 0; i < 4; ++i) if (f) fprintf(f, " %9.3f", r.h[i] > 0 ? r.h[i] - h0 : -1.0);
+        if (f) fprintf(f, "\n");
+    }
+    if (f) fclose(f);
+    for (auto &r : c->tl) { for (auto &e : r.e) if (e) cudaEventDestroy(e); for (auto &e : r.cg) if (e) cudaEventDestroy(e); }
+    c->tl.clear();
+}
+
+// Small per-batch uploads (offset tables, penalties) from pageable host memory: the driver stages them at call time (the
+// host does not wait for the stream, measured: 0.2 ms per enqueued batch while the previous one runs) and they do not queue
+// behind the audio chunks on the copy engine - page-locked staging + cudaMemcpyAsync was measured to do exactly that
+// (K-wave of the first group then started only when the whole batch had landed).
+int upload_small(phn_ctx *c, void *dst, const void *src, size_t bytes, cudaStream_t s)
+{
+    if (!bytes) return PHN_OK;
+    PHN_CUDA(c, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, s));
+    return PHN_OK;
+}
+
 template <typename T>
 static int upload(phn_ctx *c, T **dst, const T *src, size_t n)
 {
@@ -113,10 +175,8 @@ static int plan_frames(phn_ctx *c, const int64_t *frame_off, int n_utt, int n_pe
     if ((rc = ensure(c, c->d_post, sizeof(float) * F * c->ldp))) return rc;
     if ((rc = ensure(c, c->d_rec, (size_t)20 * F * n_pen))) return rc;
     if ((rc = ensure(c, c->d_pen, sizeof(float) * n_pen))) return rc;
-    PHN_CUDA(c, cudaMemcpyAsync(c->d_frame_off.p, c->h_frame_off.data(), sizeof(int64_t) * (n_utt + 1),
-                                cudaMemcpyHostToDevice, c->stream));
-    PHN_CUDA(c, cudaMemcpyAsync(c->d_lab_off.p, c->h_lab_off.data(), sizeof(int64_t) * (nseg + 1), cudaMemcpyHostToDevice,
-                                c->stream));
+    if ((rc = upload_small(c, c->d_frame_off.p, c->h_frame_off.data(), sizeof(int64_t) * (n_utt + 1), c->stream))) return rc;
+    if ((rc = upload_small(c, c->d_lab_off.p, c->h_lab_off.data(), sizeof(int64_t) * (nseg + 1), c->stream))) return rc;
     return PHN_OK;
 }
 
@@ -135,14 +195,12 @@ static int plan_audio(phn_ctx *c, const int64_t *byte_off, int n_utt)
     int rc;
     if ((rc = plan_frames(c, fo.data(), n_utt, 1))) return rc;
     if ((rc = ensure(c, c->d_byte_off, sizeof(int64_t) * (n_utt + 1)))) return rc;
-    PHN_CUDA(c, cudaMemcpyAsync(c->d_byte_off.p, c->h_byte_off.data(), sizeof(int64_t) * (n_utt + 1), cudaMemcpyHostToDevice,
-                                c->stream));
+    if ((rc = upload_small(c, c->d_byte_off.p, c->h_byte_off.data(), sizeof(int64_t) * (n_utt + 1), c->stream))) return rc;
     // frame pairs of the fp32 front end never straddle utterances (results must not depend on the batch around them)
     c->h_pair_off.assign((size_t)n_utt + 1, 0);
     for (int u = 0; u < n_utt; ++u) c->h_pair_off[u + 1] = c->h_pair_off[u] + (fo[u + 1] - fo[u] + 1) / 2;
     if ((rc = ensure(c, c->d_pair_off, sizeof(int64_t) * (n_utt + 1)))) return rc;
-    PHN_CUDA(c, cudaMemcpyAsync(c->d_pair_off.p, c->h_pair_off.data(), sizeof(int64_t) * (n_utt + 1), cudaMemcpyHostToDevice,
-                                c->stream));
+    if ((rc = upload_small(c, c->d_pair_off.p, c->h_pair_off.data(), sizeof(int64_t) * (n_utt + 1), c->stream))) return rc;
     return PHN_OK;
 }
 
@@ -237,7 +295,7 @@ static int run_decode(phn_ctx *c, const float *penalties, int n_pen, bool side =
         PHN_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_vit_done, 0));
         c->vit_pending = 0;
     }
-    PHN_CUDA(c, cudaMemcpyAsync(c->d_pen.p, c->h_pen.data(), sizeof(float) * n_pen, cudaMemcpyHostToDevice, c->stream));
+    { int rc0; if ((rc0 = upload_small(c, c->d_pen.p, c->h_pen.data(), sizeof(float) * n_pen, c->stream))) return rc0; }
     if (getenv("PHNREC_VIT_INLINE")) side = false;   // (kernel development: decoder on the main stream)
     const int nseg = c->n_utt * n_pen;
     for (int i = 0; i < c->n_pend; ++i)
@@ -250,55 +308,58 @@ static int run_decode(phn_ctx *c, const float *penalties, int n_pen, bool side =
     if ((rc = ensure(c, sl.d_nlab, sizeof(int) * (size_t)nseg))) return rc;
     if ((rc = ensure(c, sl.d_frame_off, sizeof(int64_t) * (c->n_utt + 1)))) return rc;
     if ((rc = ensure(c, sl.d_lab_off, sizeof(int64_t) * (nseg + 1)))) return rc;
+    if ((rc = ensure(c, sl.d_coff, sizeof(int64_t) * (nseg + 2)))) return rc;
+    if ((rc = ensure(c, sl.d_labels_c, sizeof(phn_label) * (size_t)c->label_cap))) return rc;
+    if (!sl.done) PHN_CUDA(c, cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
     sl.h_lab_off = c->h_lab_off; sl.h_frame_off = c->h_frame_off;
     sl.n_utt = c->n_utt; sl.n_pen = n_pen;
     PHN_CUDA(c, cudaMemcpyAsync(sl.d_frame_off.p, c->d_frame_off.p, sizeof(int64_t) * (c->n_utt + 1), cudaMemcpyDeviceToDevice, c->stream));
     PHN_CUDA(c, cudaMemcpyAsync(sl.d_lab_off.p, c->d_lab_off.p, sizeof(int64_t) * (nseg + 1), cudaMemcpyDeviceToDevice, c->stream));
     if (!side) {
         sl.s = c->stream;
-        StageTimer t(c, PHN_K_VIT);
-        return launch_viterbi(c, (const float *)c->d_pen.p, n_pen, c->stream, sl);
+        {
+            StageTimer t(c, PHN_K_VIT);
+            rc = launch_viterbi(c, (const float *)c->d_pen.p, n_pen, c->stream, sl);
+            if (!rc) rc = launch_compact_labels(c, nseg, sl);
+        }
+        if (rc) return rc;
+        PHN_CUDA(c, cudaEventRecord(sl.done, c->stream));
+        return PHN_OK;
     }
+    tl_ev(c, 3, c->stream);
     PHN_CUDA(c, cudaEventRecord(c->ev_mlp_done, c->stream));
     PHN_CUDA(c, cudaStreamWaitEvent(c->vit_stream, c->ev_mlp_done, 0));
     sl.s = c->vit_stream;
+    tl_ev(c, 4, c->vit_stream);
     {
         StageTimer t(c, PHN_K_VIT, c->vit_stream);
         rc = launch_viterbi(c, (const float *)c->d_pen.p, n_pen, c->vit_stream, sl);
+        if (!rc) rc = launch_compact_labels(c, nseg, sl);
     }
     if (rc) return rc;
+    PHN_CUDA(c, cudaEventRecord(sl.done, c->vit_stream));
+    tl_ev(c, 5, c->vit_stream);
     PHN_CUDA(c, cudaEventRecord(c->ev_vit_done, c->vit_stream));
     c->vit_pending = 1;
     return PHN_OK;
 }
 
-// Labels of one result slot -> host (penalty-major segments).  Follows the stream the slot's decoder ran on.
+// Labels of one result slot -> host (penalty-major segments): the compact offsets, then the labels themselves - two D2H
+// copies on the fetch stream behind the slot's `done` event (the decoder's stream may already hold the next batch).
 static int fetch_slot(phn_ctx *c, phn_ctx::DecSlot &sl, phn_label *labels, int64_t label_cap, int64_t *label_off)
 {
     const int nseg = sl.n_utt * sl.n_pen;
-    cudaStream_t s = sl.s ? sl.s : c->stream;
-    sl.h_nlab.resize((size_t)nseg);
-    if (nseg)
-        PHN_CUDA(c, cudaMemcpyAsync(sl.h_nlab.data(), sl.d_nlab.p, sizeof(int) * nseg, cudaMemcpyDeviceToHost, s));
+    cudaStream_t s = c->fetch_stream;
+    std::vector<int64_t> off((size_t)nseg + 2, 0);
+    PHN_CUDA(c, cudaStreamWaitEvent(s, sl.done, 0));
+    PHN_CUDA(c, cudaMemcpyAsync(off.data(), sl.d_coff.p, sizeof(int64_t) * (nseg + 2), cudaMemcpyDeviceToHost, s));
     PHN_CUDA(c, cudaStreamSynchronize(s));
-    int64_t total = 0;
-    std::vector<int64_t> off((size_t)nseg + 1, 0);
-    for (int k = 0; k < nseg; ++k) {
-        const int64_t cap = sl.h_lab_off[k + 1] - sl.h_lab_off[k];
-        if (sl.h_nlab[k] > cap) return fail(c, PHN_ERR_CAPACITY, "internal label capacity exceeded (segment %d)\n", k);
-        total += sl.h_nlab[k];
-        off[k + 1] = total;
-    }
+    if (off[(size_t)nseg + 1]) return fail(c, PHN_ERR_CAPACITY, "internal label capacity exceeded (segment %lld)\n", (long long)off[(size_t)nseg + 1] - 1);
+    const int64_t total = off[nseg];
     if (label_off) memcpy(label_off, off.data(), sizeof(int64_t) * (nseg + 1));
     if (!labels) return PHN_OK;
     if (label_cap < total) return fail(c, PHN_ERR_CAPACITY, "label buffer too small: %lld needed\n", (long long)total);
     if (total == 0) return PHN_OK;
-    // gather the produced labels into one contiguous run on the device, then a single D2H copy
-    int rc;
-    if ((rc = ensure(c, sl.d_coff, sizeof(int64_t) * (nseg + 1)))) return rc;
-    if ((rc = ensure(c, sl.d_labels_c, sizeof(phn_label) * (size_t)total))) return rc;
-    PHN_CUDA(c, cudaMemcpyAsync(sl.d_coff.p, off.data(), sizeof(int64_t) * (nseg + 1), cudaMemcpyHostToDevice, s));
-    if ((rc = launch_compact_labels(c, nseg, sl))) return rc;
     PHN_CUDA(c, cudaMemcpyAsync(labels, sl.d_labels_c.p, sizeof(phn_label) * (size_t)total, cudaMemcpyDeviceToHost, s));
     PHN_CUDA(c, cudaStreamSynchronize(s));
     return PHN_OK;
@@ -470,6 +531,7 @@ int phn_create(const char *cfg_dir, int device, phn_ctx **out)
         if ((rc = cu(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "cudaEventCreate"))) return bail(rc);
     if ((rc = cu(cudaEventCreateWithFlags(&c->ev_free, cudaEventDisableTiming), "cudaEventCreate"))) return bail(rc);
     if ((rc = cu(cudaStreamCreateWithFlags(&c->vit_stream, cudaStreamNonBlocking), "cudaStreamCreate"))) return bail(rc);
+    if ((rc = cu(cudaStreamCreateWithFlags(&c->fetch_stream, cudaStreamNonBlocking), "cudaStreamCreate"))) return bail(rc);
     if ((rc = cu(cudaEventCreateWithFlags(&c->ev_mlp_done, cudaEventDisableTiming), "cudaEventCreate"))) return bail(rc);
     if ((rc = cu(cudaEventCreateWithFlags(&c->ev_vit_done, cudaEventDisableTiming), "cudaEventCreate"))) return bail(rc);
     if ((rc = cu(cudaEventCreateWithFlags(&c->ev_audio_free, cudaEventDisableTiming), "cudaEventCreate"))) return bail(rc);
@@ -507,6 +569,7 @@ void phn_destroy(phn_ctx *c)
         cudaSetDevice(c->device);
         cudaStreamSynchronize(c->stream);
         if (c->vit_stream) cudaStreamSynchronize(c->vit_stream);
+        tl_dump(c);
     }
     phn_ctx::Buf *bufs[] = {&c->d_audio, &c->d_byte_off, &c->d_frame_off, &c->d_lab_off, &c->d_mel, &c->d_mean, &c->d_post,
                             &c->d_rec, &c->d_pen, &c->d_x0, &c->d_x1, &c->d_h, &c->d_xm,
@@ -540,6 +603,8 @@ void phn_destroy(phn_ctx *c)
     if (c->ev_vit_done) cudaEventDestroy(c->ev_vit_done);
     if (c->ev_audio_free) cudaEventDestroy(c->ev_audio_free);
     if (c->vit_stream) cudaStreamDestroy(c->vit_stream);
+    if (c->fetch_stream) cudaStreamDestroy(c->fetch_stream);
+    for (auto &sl : c->slot) if (sl.done) cudaEventDestroy(sl.done);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -677,9 +742,13 @@ int phn_recognize_device(phn_ctx *c, const void *d_audio, const int64_t *byte_of
     PHN_CUDA(c, cudaSetDevice(c->device));
     reset_timing(c);
     int rc;
+    tl_begin(c);
     if ((rc = plan_audio(c, byte_off, n_utt))) return rc;
+    tl_ev(c, 1, c->stream);
     { StageTimer t(c, PHN_K_WAVE); if ((rc = launch_wave(c, d_audio))) return rc; }
-    return recognize_after_wave(c);
+    rc = recognize_after_wave(c);
+    tl_host(c, c->tl_cur, 1);
+    return rc;
 }
 
 int phn_fetch_mel(phn_ctx *c, float *mel_out)
@@ -829,6 +898,7 @@ static int recognize_host(phn_ctx *c, const void *audio, const int64_t *byte_off
     } tev_holder(trace);
     cudaEvent_t *tev = tev_holder.e;
     reset_timing(c);
+    tl_begin(c);
     // offsets are validated (start at 0, non-decreasing) before anything is sized by them or read through them
     if ((rc = plan_audio(c, byte_off, n_utt))) return rc;
     if (!audio && c->total_bytes > 0) return fail(c, PHN_ERR_ARG, "null audio buffer\n");
@@ -859,6 +929,7 @@ static int recognize_host(phn_ctx *c, const void *audio, const int64_t *byte_off
         PHN_CUDA(c, cudaEventRecord(c->ev_free, c->stream));
         PHN_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->ev_free, 0));
     }
+    tl_ev(c, 0, c->copy_stream);
     {
         StageTimer t(c, PHN_K_WAVE);
         int u0 = 0;
@@ -872,7 +943,13 @@ static int recognize_host(phn_ctx *c, const void *audio, const int64_t *byte_off
             if (nb)
                 PHN_CUDA(c, cudaMemcpyAsync((uint8_t *)c->d_audio.p + b0, (const uint8_t *)audio + b0, (size_t)nb, cudaMemcpyHostToDevice, c->copy_stream));
             PHN_CUDA(c, cudaEventRecord(c->ev_copy[g], c->copy_stream));
+            if (c->tl_cur >= 0 && (u0 == 0 || g == ng - 1)) {
+                cudaEvent_t &e = c->tl[c->tl_cur].cg[u0 == 0 ? 0 : 1];
+                if (!e) cudaEventCreate(&e);
+                cudaEventRecord(e, c->copy_stream);
+            }
             PHN_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_copy[g], 0));
+            if (u0 == 0) tl_ev(c, 1, c->stream);
             if ((rc = launch_wave(c, c->d_audio.p, u0, u1))) return rc;
             if (g == ng - 1) {   // the audio buffer has been consumed
                 PHN_CUDA(c, cudaEventRecord(c->ev_audio_free, c->stream));
@@ -890,8 +967,11 @@ static int recognize_host(phn_ctx *c, const void *audio, const int64_t *byte_off
     }
     const double tt2 = now();
     if (trace) cudaEventRecord(tev[1], c->stream);
+    tl_ev(c, 2, c->stream);
     if ((rc = recognize_after_wave(c, front))) return rc;
+    tl_host(c, c->tl_cur, 1);
     if (!wait) {
+        c->pend_tl[c->n_pend] = c->tl_cur;
         c->pend[c->n_pend++] = c->slot_last;
         return PHN_OK;
     }
@@ -931,10 +1011,12 @@ int phn_wait(phn_ctx *c, phn_label *labels, int64_t label_cap, int64_t *label_of
     PHN_CUDA(c, cudaSetDevice(c->device));
     phn_ctx::DecSlot &sl = c->slot[c->pend[0]];
     if (frame_off_out) memcpy(frame_off_out, sl.h_frame_off.data(), sizeof(int64_t) * (sl.n_utt + 1));
+    tl_host(c, c->pend_tl[0], 2);
     const int rc = fetch_slot(c, sl, labels, label_cap, label_off);
+    tl_host(c, c->pend_tl[0], 3);
     // a capacity error leaves the batch queued (the caller may come back with a larger buffer); anything else retires it
     if (rc != PHN_ERR_CAPACITY || !labels) {
-        c->pend[0] = c->pend[1];
+        c->pend[0] = c->pend[1]; c->pend_tl[0] = c->pend_tl[1];
         --c->n_pend;
     }
     return rc;

@@ -74,6 +74,7 @@ struct phn_ctx {
     // The decoder of the audio -> labels path runs on its own stream: K-vit is one warp per utterance (latency bound, a
     // fraction of the SMs' issue slots), so the decoder of batch k runs under the front end (K-wave, K-stc) of batch k+1.
     cudaStream_t vit_stream = nullptr;
+    cudaStream_t fetch_stream = nullptr;     // label read-back: two D2H copies behind the slot's `done` event, never behind a later batch's decoder
     cudaEvent_t ev_mlp_done = nullptr;       // ln p of the batch is complete (recorded on `stream`)
     cudaEvent_t ev_vit_done = nullptr;       // the decoder has consumed it (recorded on `vit_stream`)
     int vit_pending = 0;                     // a decoder launch on vit_stream has not been waited for by `stream` yet
@@ -108,6 +109,12 @@ struct phn_ctx {
     int ldp = 0;  // device row stride of the posterior matrix (n_outputs rounded up to 4)
     int num_sms = 148;
 
+    // ---- PHNREC_TIMELINE=<file>: CUDA events + host clock per batch, dumped by phn_destroy (development aid)
+    struct TlRow { cudaEvent_t e[6] = {nullptr}; cudaEvent_t cg[2] = {nullptr, nullptr}; double h[4] = {0, 0, 0, 0}; };
+    std::vector<TlRow> tl;
+    int tl_on = -1;       // -1: environment not read yet
+    int tl_cur = -1;      // row of the batch being enqueued
+
     // ---- batch state (grow-only device buffers)
     int n_utt = 0, n_pen = 1;
     int64_t total_bytes = 0, total_frames = 0, label_cap = 0;
@@ -124,11 +131,13 @@ struct phn_ctx {
         std::vector<int64_t> h_lab_off, h_frame_off;
         std::vector<int32_t> h_nlab;
         int n_utt = 0, n_pen = 1;
-        cudaStream_t s = nullptr;            // the stream the decoder ran on (fetching follows it)
+        cudaStream_t s = nullptr;            // the stream the decoder ran on
+        cudaEvent_t done = nullptr;          // decoder + label compaction finished (fetching waits for this, on fetch_stream)
     } slot[2];
     int slot_w = 0;                          // the slot the next decode writes
     int slot_last = -1;                      // the slot of the most recent decode (phn_fetch_labels)
     int pend[2] = {0, 0}, n_pend = 0;        // slots of asynchronous batches not yet waited for, oldest first
+    int pend_tl[2] = {-1, -1};               // ... their PHNREC_TIMELINE rows
     Buf d_pair_off;                          // [n_utt + 1] prefix sums of ceil(T_u / 2): work units of the frame-pair K-wave
     std::vector<int64_t> h_pair_off;
     std::vector<float> h_pen;
@@ -152,6 +161,7 @@ int fail(phn_ctx *c, int code, const char *fmt, ...);
     } while (0)
 
 int ensure(phn_ctx *c, phn_ctx::Buf &b, size_t bytes);
+int upload_small(phn_ctx *c, void *dst, const void *src, size_t bytes, cudaStream_t s);   // small per-batch tables (pageable source, staged by the driver)
 
 // ---- kernel launchers (each in its own .cu)
 int launch_wave(phn_ctx *c, const void *d_audio, int u0 = 0, int u1 = -1);   // k_wave.cu (utterance range)

@@ -580,7 +580,10 @@ static int launch_stc_f2_t(phn_ctx *c, const StcF2Args &a)
     constexpr int NBP = (NB + 1) / 2, NIN = NB * 11, COLS = (NIN + 2 + 63) / 64 * 64, LD = COLS + 8, PITCH = (2 * NBP + 7) / 8 * 8 + 4;
     const size_t smem = sizeof(float) * 2 * 11 * 16 + sizeof(float4) * 2 * 11 * NBP + sizeof(float) * (STCM_F + 30) * PITCH + (size_t)STCM_F * LD * 2;
     PHN_CUDA(c, cudaFuncSetAttribute(k_stc_f2<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int grid = a.n_tiles < 2 * c->num_sms ? a.n_tiles : 2 * c->num_sms;
+    // (grid = a few times the resident count: see launch_wave_pair_k)
+    static const int oversub = getenv("PHNREC_FRONT_OVERSUB") ? atoi(getenv("PHNREC_FRONT_OVERSUB")) : 4;
+    const int gcap = 2 * c->num_sms * (oversub > 0 ? oversub : 1);
+    int grid = a.n_tiles < gcap ? a.n_tiles : gcap;
     k_stc_f2<NB><<<grid, 256, smem, c->stream>>>(a);
     PHN_CUDA(c, cudaGetLastError());
     return PHN_OK;

@@ -367,20 +367,57 @@ int launch_viterbi(phn_ctx *c, const float *d_pen, int n_pen, cudaStream_t s, ph
     return PHN_OK;
 }
 
+// Label counts -> compact offsets: out_off[0..nseg] = exclusive prefix sums of nlab, out_off[nseg + 1] = 1 + the first segment
+// whose count exceeds its capacity (0: none).  One block; runs on the decoder's stream right behind K-vit, so that fetching
+// the labels is two plain D2H copies and needs no kernel of its own (the next batch's persistent kernels own the SMs by then).
+__global__ void __launch_bounds__(1024) k_label_scan(const int *__restrict__ nlab, const int64_t *__restrict__ cap_off, int nseg,
+                                                     int64_t *__restrict__ out_off)
+{
+    __shared__ int64_t s_sum[1024];
+    __shared__ int s_bad;
+    const int t = threadIdx.x;
+    if (t == 0) s_bad = 0x7fffffff;
+    __syncthreads();
+    const int per = (nseg + 1023) / 1024;
+    const int lo = t * per, hi = min(nseg, lo + per);
+    int64_t sum = 0;
+    for (int k = lo; k < hi; ++k) {
+        const int n = nlab[k];
+        if ((int64_t)n > cap_off[k + 1] - cap_off[k]) atomicMin(&s_bad, k);
+        sum += n;
+    }
+    s_sum[t] = sum;
+    __syncthreads();
+    for (int d = 1; d < 1024; d <<= 1) {   // inclusive scan of the per-thread sums
+        const int64_t v = t >= d ? s_sum[t - d] : 0;
+        __syncthreads();
+        s_sum[t] += v;
+        __syncthreads();
+    }
+    int64_t run = s_sum[t] - sum;
+    for (int k = lo; k < hi; ++k) { out_off[k] = run; run += nlab[k]; }
+    if (t == 1023) { out_off[nseg] = s_sum[1023]; out_off[nseg + 1] = s_bad == 0x7fffffff ? 0 : (int64_t)s_bad + 1; }
+}
+
 // Gather each segment's labels (stored at capacity offsets) into one contiguous run.
 __global__ void k_compact_labels(const phn_label *__restrict__ src, const int64_t *__restrict__ cap_off,
                                  const int64_t *__restrict__ out_off, phn_label *__restrict__ dst)
 {
     const int seg = blockIdx.x;
     const int64_t s0 = cap_off[seg], d0 = out_off[seg];
-    const int n = (int)(out_off[seg + 1] - d0);
+    int64_t n = out_off[seg + 1] - d0;
+    if (n > cap_off[seg + 1] - s0) n = cap_off[seg + 1] - s0;   // (an overflowing segment is reported by the scan; never read past its run)
     const int4 *s = reinterpret_cast<const int4 *>(src + s0);
     int4 *d = reinterpret_cast<int4 *>(dst + d0);
     for (int i = threadIdx.x; i < n; i += blockDim.x) d[i] = s[i];
 }
 
+// scan + gather on the decoder's stream (sl.s), right behind the decoder
 int launch_compact_labels(phn_ctx *c, int nseg, phn_ctx::DecSlot &sl)
 {
+    k_label_scan<<<1, 1024, 0, sl.s>>>((const int *)sl.d_nlab.p, (const int64_t *)sl.d_lab_off.p, nseg, (int64_t *)sl.d_coff.p);
+    PHN_CUDA(c, cudaGetLastError());
+    c->k_launches[PHN_K_VIT] += 1;
     if (nseg == 0) return PHN_OK;
     k_compact_labels<<<nseg, 64, 0, sl.s>>>((const phn_label *)sl.d_labels.p, (const int64_t *)sl.d_lab_off.p,
                                             (const int64_t *)sl.d_coff.p, (phn_label *)sl.d_labels_c.p);

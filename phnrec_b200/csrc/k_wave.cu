@@ -13,6 +13,7 @@
 // bit-identical to the CPU implementation.  The !EXACT instantiation (tensor-core pipeline) uses
 // fp32 FMAs.
 #include "internal.h"
+#include <cstdlib>
 #include "device_math.cuh"
 
 #include <algorithm>
@@ -562,7 +563,11 @@ static int launch_wave_pair_k(phn_ctx *c, const WaveArgs &a, size_t smem)
     int per_sm = 1;
     PHN_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_wave_pair<LOGN, ALAW>, kPairWarps * 32, smem));
     int64_t blocks = (a.p_end - a.p_begin + kPairWarps - 1) / kPairWarps;
-    const int64_t cap = (int64_t)c->num_sms * (per_sm > 0 ? per_sm : 1);
+    // Grid = a few times what is resident at once: the previous batch's decoder may hold part of the register file when this
+    // kernel starts (it runs on its own stream), and a grid of exactly the resident count would leave the CTAs that did not
+    // fit waiting with a fixed share of the work.  PHNREC_FRONT_OVERSUB overrides the factor (kernel development).
+    static const int oversub = getenv("PHNREC_FRONT_OVERSUB") ? atoi(getenv("PHNREC_FRONT_OVERSUB")) : 4;
+    const int64_t cap = (int64_t)c->num_sms * (per_sm > 0 ? per_sm : 1) * (oversub > 0 ? oversub : 1);
     if (blocks > cap) blocks = cap;
     k_wave_pair<LOGN, ALAW><<<(unsigned)blocks, kPairWarps * 32, smem, c->stream>>>(a);
     PHN_CUDA(c, cudaGetLastError());
