@@ -143,7 +143,7 @@ class ClockSampler(threading.Thread):
                         self.rows.append([x.strip() for x in out.split(",")])
             except Exception:
                 pass
-            self._stop_evt.wait(0.02 if h is not None else 0.1)
+            self._stop_evt.wait(0.05 if h is not None else 0.1)
 
     def stop(self):
         self._stop_evt.set()
@@ -371,7 +371,9 @@ def main():
         step k runs on the context's decoder stream under the front end of step k+1, so per-step event pairs on the main
         stream would miss it.  rec.sync() joins both streams before the closing event is recorded."""
         for _ in range(warmup):
-            step_fn()
+            with torch.cuda.stream(stream):
+                flush.zero_()                          # (also loads torch's fill kernel before the timed span: lazy module
+            step_fn()                                  #  loading inside it costs hundreds of milliseconds)
         if drain_fn:
             drain_fn()
         rec.sync()
@@ -414,9 +416,10 @@ def main():
             rec.recognize_device(d_audio, byte_off)
 
     sampler = ClockSampler(local)
-    sampler.start()
+    if not os.environ.get("PHNREC_BENCH_NO_SAMPLER"):    # (diagnostic: how much the sampling itself costs)
+        sampler.start()
     ms_dev = timed_loop(step_device, args.steps, args.warmup)
-    clocks = sampler.stop()
+    clocks = sampler.stop() if sampler.is_alive() or sampler.rows else {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "power_w_max": None}
     launches_per_step = sum(n for _, n in rec.last_timing().values())
 
     # ---- e2e: host buffers through the C ABI (pinned audio -> H2D -> kernels -> labels D2H)

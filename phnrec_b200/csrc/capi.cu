@@ -913,6 +913,9 @@ static int recognize_host(phn_ctx *c, const void *audio, const int64_t *byte_off
     if (const char *e = getenv("PHNREC_COPY_GROUP_MB")) group_mb = atoll(e) > 0 ? atoll(e) : group_mb;   // (kernel development)
     int ng = (int)(total / (group_mb << 20));
     ng = ng < 1 ? 1 : (ng > 16 ? 16 : ng);
+    // A batch enqueued behind one that is still on the device: its audio lands while that batch's nets run, long before
+    // its own front end gets the SMs - one launch per kernel over the whole batch instead of sixteen small ones.
+    if (!wait && c->n_pend >= 1 && !getenv("PHNREC_ASYNC_GROUPS")) ng = 1;
     // When the batch is one pass of the tensor-core MLP, the sentence mean and the STC features of a group follow its
     // K-wave at once, so the whole front end runs under the copy and the MLP starts when the last group has landed.
     c->fuse_logp = 1; c->fast_front = 1;

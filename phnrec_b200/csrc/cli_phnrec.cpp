@@ -11,8 +11,16 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
+#include <atomic>
+#include <condition_variable>
+#include <deque>
+#include <functional>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
+#include <sys/stat.h>
 
 #include "phnrec_b200.h"
 
@@ -149,11 +157,198 @@ bool load_bytes(const std::string &path, std::vector<unsigned char> &out)
 
 struct Job { std::string src, dst; };
 
+// label text, as strings (the list pipeline formats on its worker threads and writes from one thread, in list order)
+void append_rec(std::string &out, phn_ctx *ctx, const phn_label *l, int64_t n)
+{
+    char buf[256];
+#ifdef PHN_VADALIZE
+    for (int64_t i = 0; i < n; ++i) {   // phndecalize.cpp:227-239, 299-314
+        const std::string ph = phn_phoneme(ctx, l[i].phn);
+        if (ph == "pau" || ph == "int" || ph == "spk") continue;
+        const float alizeStart = (float)l[i].start, alizeEnd = (float)l[i].end;
+        snprintf(buf, sizeof buf, "%.2f %.2f speech\n", alizeStart / 100, alizeEnd / 100);
+        out += buf;
+    }
+#else
+    for (int64_t i = 0; i < n; ++i) {   // phndec.cpp:230,292
+        snprintf(buf, sizeof buf, "%d00000 %d00000 %s %f\n", l[i].start, l[i].end, phn_phoneme(ctx, l[i].phn), l[i].like);
+        out += buf;
+    }
+#endif
+}
+void append_mlf_lines(std::string &out, phn_ctx *ctx, const phn_label *l, int64_t n)
+{
+    char buf[256];
+    for (int64_t i = 0; i < n; ++i) {   // SpeechRec::OnWordMLF, srec.cpp:137-161
+        if (l[i].start == 0) out += "0"; else { snprintf(buf, sizeof buf, "%u00000", (unsigned)l[i].start); out += buf; }
+        if (l[i].end == 0) out += " 0"; else { snprintf(buf, sizeof buf, " %u00000", (unsigned)l[i].end); out += buf; }
+        snprintf(buf, sizeof buf, " %s %f\n", phn_phoneme(ctx, l[i].phn), l[i].like);
+        out += buf;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// List mode, audio -> labels (SpeechRec::ProcessFileList, srec.cpp:1246-1291, for dfWaveform -> dfStrings).
+// The reference walks the list one file after the other; utterances are independent (fresh decoder, per-utterance mean,
+// clamped context: srec.cpp:1148-1167), so the list is cut into contiguous batches that are handed out to one host
+// thread + one phn_ctx per GPU (PHNREC_DEVICES).  A worker keeps two batches in flight (phn_recognize_async / phn_wait):
+// it reads the files of batch k+1 into page-locked memory while batch k is on its GPU.  Label text is formatted on the
+// workers and written by the calling thread strictly in list order - the output (MLF or .rec files) is byte-identical
+// whatever the number of GPUs.  No data moves between GPUs; the only gather is this ordered write on the host.
+struct ListPipeline {
+    struct Result { std::vector<std::string> text; int n_good = 0; std::string error; bool done = false; };
+    std::vector<Job> jobs;
+    std::vector<std::pair<size_t, size_t>> batches;
+    std::vector<Result> results;
+    std::vector<phn_ctx *> ctxs;
+    bool to_mlf = false;
+    int readers = 2;
+    std::mutex mu;
+    std::condition_variable cv;
+    std::atomic<size_t> next{0};
+
+    struct Stage {
+        unsigned char *pinned = nullptr;
+        size_t cap = 0;
+        std::vector<int64_t> off;
+        size_t b = 0;
+        int n = 0;
+        int64_t frames = 0;
+        std::string error;
+    };
+
+    static void parallel_for(int n, int threads, const std::function<void(int)> &fn)
+    {
+        if (threads <= 1 || n < 2 * threads) { for (int i = 0; i < n; ++i) fn(i); return; }
+        std::atomic<int> at{0};
+        auto body = [&] { for (int i = at.fetch_add(16); i < n; i = at.fetch_add(16)) for (int k = i; k < n && k < i + 16; ++k) fn(k); };
+        std::vector<std::thread> th;
+        for (int t = 1; t < threads; ++t) th.emplace_back(body);
+        body();
+        for (auto &t : th) t.join();
+    }
+
+    // files of batch b -> one page-locked buffer (whole files as raw bytes, SpeechRec::LoadWaveform, srec.cpp:1384-1422);
+    // the first file that cannot be read ends the batch there, like the reference stopping at it
+    void load(Stage &st, size_t b, phn_ctx *ctx)
+    {
+        const size_t j0 = batches[b].first, n = batches[b].second - j0;
+        st.b = b; st.error.clear();
+        std::vector<int64_t> size(n, -1);
+        parallel_for((int)n, readers, [&](int i) {
+            struct stat sb;
+            if (stat(jobs[j0 + i].src.c_str(), &sb) == 0 && S_ISREG(sb.st_mode)) size[i] = (int64_t)sb.st_size;
+        });
+        size_t good = n;
+        for (size_t i = 0; i < n; ++i) if (size[i] < 0) { good = i; break; }
+        st.off.assign(good + 1, 0);
+        for (size_t i = 0; i < good; ++i) st.off[i + 1] = st.off[i] + size[i];
+        const size_t total = (size_t)st.off[good];
+        if (total + 16 > st.cap) {
+            if (st.pinned) phn_host_free_pinned(st.pinned);
+            st.cap = total + total / 2 + 4096;
+            st.pinned = (unsigned char *)phn_host_alloc_pinned((int64_t)st.cap);
+            if (!st.pinned) die("Can not allocate %zu bytes of page-locked memory\n", st.cap);
+        }
+        std::atomic<int> first_bad{(int)good};
+        parallel_for((int)good, readers, [&](int i) {
+            FILE *f = fopen(jobs[j0 + i].src.c_str(), "rb");
+            bool ok = f != nullptr;
+            if (ok) ok = size[i] == 0 || fread(st.pinned + st.off[i], 1, (size_t)size[i], f) == (size_t)size[i];
+            if (f) fclose(f);
+            if (!ok) { int cur = first_bad.load(); while (i < cur && !first_bad.compare_exchange_weak(cur, i)) {} }
+        });
+        if ((size_t)first_bad.load() < good) good = (size_t)first_bad.load();
+        if (good < n) st.error = "Can not open waveform file: " + jobs[j0 + good].src + "\n";
+        st.off.resize(good + 1);
+        st.n = (int)good;
+        st.frames = 0;
+        for (size_t i = 0; i < good; ++i) st.frames += phn_num_frames(ctx, st.off[i + 1] - st.off[i]);
+    }
+
+    void finish(Stage &st, phn_ctx *ctx, bool waited)
+    {
+        Result r;
+        r.n_good = st.n;
+        r.error = st.error;
+        if (st.n > 0 && waited) {
+            const int64_t cap = st.frames + (int64_t)48 * st.n;
+            std::vector<phn_label> lab((size_t)cap);
+            std::vector<int64_t> loff((size_t)st.n + 1);
+            if (phn_wait(ctx, lab.data(), cap, loff.data(), nullptr)) die("%s", phn_last_error(ctx));
+            r.text.resize((size_t)st.n);
+            for (int i = 0; i < st.n; ++i) {
+                if (to_mlf) append_mlf_lines(r.text[i], ctx, lab.data() + loff[i], loff[i + 1] - loff[i]);
+                else if (jobs[batches[st.b].first + i].dst.empty()) append_mlf_lines(r.text[i], ctx, lab.data() + loff[i], loff[i + 1] - loff[i]);
+                else append_rec(r.text[i], ctx, lab.data() + loff[i], loff[i + 1] - loff[i]);
+            }
+        }
+        r.done = true;
+        {
+            std::lock_guard<std::mutex> g(mu);
+            results[st.b] = std::move(r);
+        }
+        cv.notify_all();
+    }
+
+    void worker(phn_ctx *ctx)
+    {
+        Stage st[2];
+        std::deque<int> inflight;   // stage indices, oldest first
+        int k = 0;
+        for (;;) {
+            const size_t b = next.fetch_add(1);
+            if (b >= batches.size()) break;
+            Stage &s = st[k & 1];
+            load(s, b, ctx);
+            if (s.n > 0 && phn_recognize_async(ctx, s.pinned, s.off.data(), s.n)) die("%s", phn_last_error(ctx));
+            inflight.push_back(k & 1);
+            if (inflight.size() == 2) { Stage &o = st[inflight.front()]; inflight.pop_front(); finish(o, ctx, true); }
+            ++k;
+        }
+        while (!inflight.empty()) { Stage &o = st[inflight.front()]; inflight.pop_front(); finish(o, ctx, true); }
+        for (auto &s : st) if (s.pinned) phn_host_free_pinned(s.pinned);
+    }
+
+    // runs the pipeline; writes outputs in list order; returns the first error (empty: none)
+    std::string run(FILE *mlf)
+    {
+        results.assign(batches.size(), Result());
+        std::vector<std::thread> th;
+        for (phn_ctx *c : ctxs) th.emplace_back([this, c] { worker(c); });
+        std::string err;
+        for (size_t b = 0; b < batches.size() && err.empty(); ++b) {
+            Result r;
+            {
+                std::unique_lock<std::mutex> g(mu);
+                cv.wait(g, [&] { return results[b].done; });
+                r = std::move(results[b]);
+            }
+            const size_t j0 = batches[b].first;
+            for (int i = 0; i < r.n_good; ++i) {
+                const Job &j = jobs[j0 + i];
+                logmsg("%s -> %s\n", j.src.c_str(), j.dst.c_str());
+                if (mlf) { fprintf(mlf, "\"%s\"\n", j.dst.c_str()); fputs(r.text[i].c_str(), mlf); fputs(".\n", mlf); continue; }
+                if (j.dst.empty()) { fputs(r.text[i].c_str(), stdout); continue; }
+                FILE *f = fopen(j.dst.c_str(), "w");
+                if (!f) { err = "Can not create the label file: " + j.dst + "\n"; break; }
+                fputs(r.text[i].c_str(), f);
+                fclose(f);
+            }
+            if (err.empty()) err = r.error;
+        }
+        if (!err.empty()) next.store(batches.size());   // stop handing out work
+        for (auto &t : th) t.join();
+        return err;
+    }
+};
+
 struct Runner {
     phn_ctx *ctx = nullptr;
     phn_info info{};
     DataFmt inf = dfWaveform, outf = dfStrings;
     FILE *mlf = nullptr;
+    float info_penalty = 0.f;   // the insertion penalty in force (config value or -p): further devices' contexts get the same
 
     void ck(int rc) { if (rc) die("%s", phn_last_error(ctx)); }
 
@@ -331,8 +526,28 @@ int main(int argc, char *argv[])
     }
     // PHNREC_MLP=tc selects the tensor-core posterior estimator (not a reference switch)
     if (const char *e = getenv("PHNREC_MLP")) mlp_mode = !strcmp(e, "tc") ? PHN_MLP_TC_F16 : PHN_MLP_EXACT_FP32;
-    int device = 0;
-    if (const char *e = getenv("PHNREC_DEVICE")) device = atoi(e);
+    // PHNREC_DEVICES = "all" | "0-7" | "0,2,5" (list mode shards the file list over them); PHNREC_DEVICE = one device
+    std::vector<int> devices;
+    if (const char *e = getenv("PHNREC_DEVICES")) {
+        const int have = phn_device_count();
+        if (!strcmp(e, "all")) { for (int d = 0; d < have; ++d) devices.push_back(d); }
+        else {
+            const char *q = e;
+            while (*q) {
+                char *end;
+                const long a = strtol(q, &end, 10);
+                if (end == q) break;
+                long b = a;
+                if (*end == '-') { q = end + 1; b = strtol(q, &end, 10); }
+                for (long d = a; d <= b; ++d) devices.push_back((int)d);
+                q = *end == ',' ? end + 1 : end;
+                if (*end && *end != ',') break;
+            }
+        }
+        for (int d : devices) if (d < 0 || d >= have) die("PHNREC_DEVICES names device %d; this machine has %d\n", d, have);
+    }
+    if (devices.empty()) devices.push_back(getenv("PHNREC_DEVICE") ? atoi(getenv("PHNREC_DEVICE")) : 0);
+    const int device = devices[0];
 
     if (!config_dir) { fprintf(stderr, "ERROR: Configuration directory is not set (-c)\n"); return 1; }
     logmsg("\nSystem initialization\n");
@@ -349,6 +564,7 @@ int main(int argc, char *argv[])
     logmsg("Soft func:    %s\n", phn_config_get(R.ctx, "decoder", "softening_func"));
     logmsg("-----------------------------------------------\n\n");
     R.ck(phn_set_mlp_mode(R.ctx, mlp_mode));
+    R.info_penalty = R.info.wpenalty;
 
     if (wpenalty) {
         float v;
@@ -357,6 +573,7 @@ int main(int argc, char *argv[])
             return 1;
         }
         phn_set_penalty(R.ctx, v);
+        R.info_penalty = v;
     }
     if (wformat) phn_set_wave_format(R.ctx, !strcmp(wformat, "alaw") ? PHN_WAVE_ALAW : PHN_WAVE_LIN16);
     if (output_file && !input_file) { fprintf(stderr, "ERROR: The input file is not specified (-i)\n"); return 1; }
@@ -412,9 +629,49 @@ int main(int argc, char *argv[])
         }
         size_t max_batch = 2048;
         if (const char *e = getenv("PHNREC_BATCH")) max_batch = (size_t)atol(e) > 0 ? (size_t)atol(e) : max_batch;
-        std::vector<Job> batch;
         char line[1024];
         std::string err;
+        if (R.inf == dfWaveform && R.outf == dfStrings) {
+            // audio -> labels: the multi-GPU list pipeline (one host thread and context per device, ordered gather)
+            ListPipeline P;
+            P.to_mlf = R.mlf != nullptr;
+            while (fgets(line, 1023, fl)) {
+                Job j;
+                if (!parse_line(line, R.mlf != nullptr, j, err)) break;   // (the reference stops at the first bad line)
+                P.jobs.push_back(j);
+            }
+            P.ctxs.push_back(R.ctx);
+            {   // further devices: same model, same settings, created side by side
+                std::vector<std::thread> th;
+                std::vector<phn_ctx *> more(devices.size(), nullptr);
+                std::vector<std::string> cerr_(devices.size());
+                for (size_t d = 1; d < devices.size(); ++d)
+                    th.emplace_back([&, d] {
+                        if (phn_create(config_dir, devices[d], &more[d])) { cerr_[d] = phn_last_error(nullptr); more[d] = nullptr; return; }
+                        phn_set_mlp_mode(more[d], mlp_mode);
+                        phn_set_penalty(more[d], R.info_penalty);
+                        if (wformat) phn_set_wave_format(more[d], !strcmp(wformat, "alaw") ? PHN_WAVE_ALAW : PHN_WAVE_LIN16);
+                    });
+                for (auto &t : th) t.join();
+                for (size_t d = 1; d < devices.size(); ++d) {
+                    if (!more[d]) die("%s", cerr_[d].empty() ? "Can not create a context on a further device\n" : cerr_[d].c_str());
+                    P.ctxs.push_back(more[d]);
+                }
+            }
+            const size_t nd = P.ctxs.size();
+            size_t per = (P.jobs.size() + 4 * nd - 1) / (4 * nd);   // about four batches per device: file reading overlaps the GPU
+            if (per < 64) per = 64;
+            if (per > max_batch) per = max_batch;
+            for (size_t j0 = 0; j0 < P.jobs.size(); j0 += per) P.batches.emplace_back(j0, std::min(P.jobs.size(), j0 + per));
+            unsigned hw = std::thread::hardware_concurrency();
+            P.readers = (int)std::max<size_t>(1, std::min<size_t>(8, (hw ? hw : 8) / nd));
+            if (const char *e = getenv("PHNREC_READERS")) P.readers = atoi(e) > 0 ? atoi(e) : P.readers;
+            const std::string perr = P.run(R.mlf);
+            for (size_t d = 1; d < P.ctxs.size(); ++d) phn_destroy(P.ctxs[d]);
+            if (!perr.empty()) { if (R.mlf) fflush(R.mlf); die("%s", perr.c_str()); }
+            if (!err.empty()) { if (R.mlf) fflush(R.mlf); die("%s", err.c_str()); }
+        } else {
+        std::vector<Job> batch;
         while (fgets(line, 1023, fl)) {
             Job j;
             if (!parse_line(line, R.mlf != nullptr, j, err)) break;
@@ -424,6 +681,7 @@ int main(int argc, char *argv[])
         if (!batch.empty() || !err.empty()) {
             if (!batch.empty()) R.run(batch, err);
             else die("%s", err.c_str());
+        }
         }
         if (R.mlf) fclose(R.mlf);
         fclose(fl);

@@ -82,8 +82,15 @@ int launch_logf_range(phn_ctx *c, uint32_t first_bits, int64_t n, float *d_out)
     return PHN_OK;
 }
 
+// Register budget (kernel development switch): the decoder of batch k shares the SMs with the front end of batch k+1 (it runs
+// on its own stream).  Capping it at 64 registers (PHN_VIT_MINB=32) so that its 7 warps per SM leave room for three K-wave
+// CTAs was measured and dropped: the decoder alone goes from 0.52 to 0.80 ms (spills, less latency hiding) and the step
+// from 4.74 to 5.02 ms.
+#ifndef PHN_VIT_MINB
+#define PHN_VIT_MINB 1
+#endif
 template <int PPL, bool TILED>
-__global__ void __launch_bounds__(32) k_viterbi(VitArgs a)
+__global__ void __launch_bounds__(32, PPL <= 2 ? PHN_VIT_MINB : 1) k_viterbi(VitArgs a)
 {
     const int seg = blockIdx.x;
     const int kpen = seg / a.n_utt, u = seg - kpen * a.n_utt;

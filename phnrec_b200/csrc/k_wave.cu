@@ -567,6 +567,8 @@ static int launch_wave_pair_k(phn_ctx *c, const WaveArgs &a, size_t smem)
     // kernel starts (it runs on its own stream), and a grid of exactly the resident count would leave the CTAs that did not
     // fit waiting with a fixed share of the work.  PHNREC_FRONT_OVERSUB overrides the factor (kernel development).
     static const int oversub = getenv("PHNREC_FRONT_OVERSUB") ? atoi(getenv("PHNREC_FRONT_OVERSUB")) : 4;
+    static const int cta_cap = getenv("PHNREC_WAVE_CTAS") ? atoi(getenv("PHNREC_WAVE_CTAS")) : 0;   // (kernel development)
+    (void)cta_cap;
     const int64_t cap = (int64_t)c->num_sms * (per_sm > 0 ? per_sm : 1) * (oversub > 0 ? oversub : 1);
     if (blocks > cap) blocks = cap;
     k_wave_pair<LOGN, ALAW><<<(unsigned)blocks, kPairWarps * 32, smem, c->stream>>>(a);

@@ -116,3 +116,81 @@ def test_model_directory_with_ascii_weights_only(tmp_path):
     assert out.read_text() == str(ref_run("PHN_EN_TIMIT_LCRC_N500", "test.raw")["rec"])
     for n in ("band0", "band1", "merger"):
         assert (dst / "weights" / f"{n}.nbin").read_bytes() == (src / "weights" / f"{n}.nbin").read_bytes()
+
+
+# ------------------------------------------------------------------------------------------------ list mode on 1..N GPUs
+REF_BIN = ROOT / "oracle" / "_ref" / "phnrec_ref"
+
+
+def _ragged_list(tmp_path, n, seed, with_targets):
+    """n short synthetic A-law files of ragged length + a list file (the scaling test's input)."""
+    import sys
+    sys.path.insert(0, str(ROOT))
+    from tools.synth_host import synth_audio
+    a = synth_audio(16000, n, seed=seed, fmt="alaw", fs=8000)
+    d = tmp_path / "wav"
+    d.mkdir(exist_ok=True)
+    lines = []
+    for i in range(n):
+        f = d / f"u{i:03d}.raw"
+        f.write_bytes(a[i].tobytes()[: 2400 + ((i * 7919) % 13600)])
+        lines.append(f"{f} {tmp_path / f'u{i:03d}.lab'}" if with_targets else str(f))
+    lst = tmp_path / "list.scp"
+    lst.write_text("\n".join(lines) + "\n")
+    return lst
+
+
+def test_list_mode_mlf_equals_reference_and_does_not_depend_on_gpu_count(tmp_path):
+    """`phnrec -l list -m out.mlf` over a 64-utterance ragged list (SpeechRec::ProcessFileList, srec.cpp:1246-1291): the MLF
+    must be the reference binary's byte for byte (exact mode), whatever the batching (7 files per batch: ten batches, two in
+    flight per GPU, handed out dynamically) and whatever the number of GPUs (all visible ones vs one)."""
+    if not REF_BIN.exists():
+        pytest.skip("reference binary not staged")
+    model = model_dir("PHN_CZ_SPDAT_LCRC_N1500")
+    lst = _ragged_list(tmp_path, 64, 77, with_targets=False)
+    ref_mlf = tmp_path / "ref.mlf"
+    r = subprocess.run([str(REF_BIN), "-c", str(model), "-l", str(lst), "-m", str(ref_mlf), "-w", "alaw"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr
+    outs = {}
+    for tag, env in [("one", {"PHNREC_DEVICES": "0", "PHNREC_BATCH": "7"}), ("all", {"PHNREC_DEVICES": "all", "PHNREC_BATCH": "7"}),
+                     ("big", {"PHNREC_DEVICES": "all"})]:
+        mlf = tmp_path / f"{tag}.mlf"
+        r = run("phnrec", "-c", model, "-l", lst, "-m", mlf, "-w", "alaw", env=env)
+        assert r.returncode == 0, r.stderr
+        outs[tag] = mlf.read_bytes()
+    assert outs["one"] == ref_mlf.read_bytes()
+    assert outs["all"] == outs["one"] and outs["big"] == outs["one"]
+    # the fast path: not the reference's bits, but still independent of batching and of the number of GPUs
+    tc = {}
+    for tag, env in [("one", {"PHNREC_DEVICES": "0", "PHNREC_BATCH": "7"}), ("all", {"PHNREC_DEVICES": "all"})]:
+        mlf = tmp_path / f"tc_{tag}.mlf"
+        r = run("phnrec", "-c", model, "-l", lst, "-m", mlf, "-w", "alaw", env={**env, "PHNREC_MLP": "tc"})
+        assert r.returncode == 0, r.stderr
+        tc[tag] = mlf.read_bytes()
+    assert tc["one"] == tc["all"]
+    a, b = tc["one"].decode().splitlines(), outs["one"].decode().splitlines()
+    same = sum(x.split()[:3] == y.split()[:3] for x, y in zip(a, b))
+    assert len(a) == len(b) or abs(len(a) - len(b)) < 0.02 * len(b)
+    assert same >= 0.9 * len(b) or len(a) != len(b)
+
+
+def test_list_mode_rec_files_and_first_bad_file_like_the_reference(tmp_path):
+    """'source target' list lines write one .rec per file; a file that cannot be read stops the run THERE with the
+    reference's message and exit code 1 - everything before it has been written, nothing after it."""
+    if not REF_BIN.exists():
+        pytest.skip("reference binary not staged")
+    model = model_dir("PHN_CZ_SPDAT_LCRC_N1500")
+    lst = _ragged_list(tmp_path, 24, 78, with_targets=True)
+    lines = lst.read_text().splitlines()
+    lines[17] = f"{tmp_path / 'missing.raw'} {tmp_path / 'missing.lab'}"
+    lst.write_text("\n".join(lines) + "\n")
+    r = run("phnrec", "-c", model, "-l", lst, "-w", "alaw", env={"PHNREC_DEVICES": "all", "PHNREC_BATCH": "5"})
+    assert r.returncode == 1 and r.stderr.startswith("ERROR: Can not open waveform file"), r.stderr
+    got = {p.name: p.read_text() for p in tmp_path.glob("u*.lab")}
+    assert sorted(got) == [f"u{i:03d}.lab" for i in range(17)]
+    for p in tmp_path.glob("u*.lab"):
+        p.unlink()
+    rr = subprocess.run([str(REF_BIN), "-c", str(model), "-l", str(lst), "-w", "alaw"], capture_output=True, text=True, timeout=600)
+    assert rr.returncode == 1 and rr.stderr.startswith("ERROR: Can not open waveform file")
+    want = {p.name: p.read_text() for p in tmp_path.glob("u*.lab")}
+    assert got == want

@@ -27,8 +27,16 @@ rec.memcpy_d2h(h, d, n_utt * nbytes)
 frames = n_utt * rec.num_frames(nbytes)
 labels = np.zeros(frames + 48 * n_utt, dtype=pb.LABEL_DTYPE)
 loff = np.zeros(n_utt + 1, dtype=np.int64)
+flush = None
+if os.environ.get("TL_FLUSH"):
+    import torch
+    stream = torch.cuda.ExternalStream(rec._L.phn_stream(rec._h), device=torch.device("cuda", 0))
+    flush = torch.empty(192 << 20, dtype=torch.uint8, device="cuda:0")
 t0 = time.perf_counter()
 for k in range(steps):
+    if flush is not None:
+        with torch.cuda.stream(stream):
+            flush.zero_()
     if mode == "device":
         rec.recognize_device(d, boff)
     elif mode == "sync":
@@ -42,4 +50,9 @@ while rec.pending():
 rec.sync()
 print(f"{mode}: {(time.perf_counter() - t0) * 1e3 / steps:.3f} ms per step (host clock, {steps} steps incl. the first)")
 rec.close()
-print(open(out).read())
+txt = open(out).read()
+rows = [l.split("|") for l in txt.splitlines() if l and l[0] != "#"]
+go = [float(r[1].split()[1]) for r in rows]
+print("wave-go deltas:", " ".join(f"{b - a:.2f}" for a, b in zip(go, go[1:])))
+if steps <= 12:
+    print(txt)
