@@ -103,6 +103,8 @@ def lib() -> C.CDLL:
     L.orc_model_decode.restype = C.c_int
     L.orc_model_recognize.argtypes = [vp, vp, C.c_int, C.c_int, C.c_float, vp, C.c_int]
     L.orc_model_recognize.restype = C.c_int
+    L.orc_model_recognize_online.argtypes = [vp, vp, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, vp, C.c_int]
+    L.orc_model_recognize_online.restype = C.c_int
     _lib = L
     return L
 
@@ -236,6 +238,18 @@ class Model:
         out = np.zeros(cap, dtype=LABEL_DTYPE)
         w = self.wpenalty if wp is None else wp
         k = lib().orc_model_recognize(self.h, p, n, f, C.c_float(w), out.ctypes.data_as(C.c_void_p), cap)
+        return out[:k].copy()
+
+
+    def recognize_online(self, audio, fmt=None, wp=None, interval=-1, mean_norm=-1, var_norm=-1) -> np.ndarray:
+        """The online path (SpeechRec::ProcessOnline, srec.cpp:793-927) over the whole signal; -1 = the config's [onlinenorm]."""
+        a, p, n = _buf(audio)
+        f = -1 if fmt is None else FMT[fmt]
+        cap = n // 50 + 128
+        out = np.zeros(cap, dtype=LABEL_DTYPE)
+        w = self.wpenalty if wp is None else wp
+        k = lib().orc_model_recognize_online(self.h, p, n, f, C.c_float(w), int(interval), int(mean_norm), int(var_norm),
+                                             out.ctypes.data_as(C.c_void_p), cap)
         return out[:k].copy()
 
 

@@ -737,6 +737,8 @@ typedef struct {
     int fs, nbanks, vs, step, fmt, sent_mean_norm, hist, S, P;
     float lo, hi, preem, wpenalty, frame_shift, frame_floor, scale, dc_shift;
     int z_mean;
+    int on_interval, on_mean, on_var;   /* [onlinenorm] estim_interval, mean_norm, var_norm */
+    int bunch;                          /* [posteriors] bunch_size */
     float win[32];
     orc_nn *b0, *b1, *mg;
     orc_mel *mel;
@@ -797,6 +799,10 @@ orc_model *orc_model_load(const char *dir)
     cfg_get(txt, "offlinenorm", "sent_mean_norm", buf, "false"); m->sent_mean_norm = strcmp(buf, "true") == 0;
     cfg_get(txt, "framenorm", "shift", buf, "0"); sscanf(buf, "%f", &m->frame_shift);
     cfg_get(txt, "framenorm", "min_floor", buf, "-9999.9"); sscanf(buf, "%f", &m->frame_floor);
+    cfg_get(txt, "posteriors", "bunch_size", buf, "1"); m->bunch = atoi(buf) > 0 ? atoi(buf) : 1;
+    cfg_get(txt, "onlinenorm", "estim_interval", buf, "0"); m->on_interval = atoi(buf);          /* srec.cpp:56-61, 594-601 */
+    cfg_get(txt, "onlinenorm", "mean_norm", buf, "false"); m->on_mean = strcmp(buf, "true") == 0;
+    cfg_get(txt, "onlinenorm", "var_norm", buf, "false"); m->on_var = strcmp(buf, "true") == 0;
     cfg_get(txt, "decoder", "wpenalty", buf, "-2.0"); sscanf(buf, "%f", &m->wpenalty);
     cfg_get(txt, "decoder", "time_pruning", buf, "40"); m->hist = atoi(buf);
     cfg_get(txt, "decoder", "num_states_per_phn", buf, "1"); m->S = atoi(buf);
@@ -888,6 +894,50 @@ int orc_model_decode(orc_model *m, const float *post, int T, float wp, orc_label
     int n = orc_decode(lp, T, nc, m->P, m->S, m->hist, wp, out, cap);
     free(lp);
     return n;
+}
+
+/* The ONLINE path, SpeechRec::ProcessOnline + ProcessTail (srec.cpp:793-927) fed block by block: the streaming objects carry
+ * their state across blocks (MelBanks frame buffer, melbanks.cpp:151-204; the 31-frame FIFO of Traps, traps.cpp:180-219; the
+ * decoder), so the result does not depend on the block size and equals this whole-signal restatement:
+ *   frames t = samples [t step, t step + vs) for every full frame (no frame at all below vs samples);
+ *   FrameBasedNormalization, then Normalization::ProcessFrame (orc_online_norm) - NO sentence normalisation;
+ *   the FIFO's warm-up / tail = clamped context (orc_stc); soft functions; PhnDec.
+ * Which posterior rows reach the decoder (srec.cpp:826-831, 865-869, 904-908): a whole bunch is passed on when, AFTER it, the
+ * FIFO's delay (= vectors fed - 1, traps.cpp:199-217) has reached the trap shift (15); the tail's 15 vectors always are.
+ * With bunches of 5 that is exactly rows 0..T-1 for T >= 15; a SHORTER utterance gets max(T, 15) frames decoded - the tail
+ * also carries 15 - T warm-up rows (virtual rows r < 0, context clamp(r-15..r+15, 0, T-1), i.e. rows of a signal with
+ * copies of frame 0 in front), and the label times count those frames.  Bunch sizes that do not divide 15 add up to
+ * bunch - 1 such rows in front of every utterance.
+ * interval / mean_norm / var_norm < 0: the model's [onlinenorm] values.
+ * Pinned against oracle/_ref/online_ref (the reference's own objects driven in blocks) by tests/test_oracle_pinned.py. */
+int orc_model_recognize_online(orc_model *m, const void *audio, int nbytes, int fmt, float wp, int interval, int mean_norm,
+                               int var_norm, orc_label *out, int cap)
+{
+    if (fmt < 0) fmt = m->fmt;
+    if (interval < 0) interval = m->on_interval;
+    if (mean_norm < 0) mean_norm = m->on_mean;
+    if (var_norm < 0) var_norm = m->on_var;
+    const int n = fmt == 0 ? nbytes / 2 : nbytes;
+    if (n < m->vs) return 0;
+    const int T = (n - m->vs) / m->step + 1;
+    /* first row handed to the decoder: the first bunch whose last vector is the 16th or later starts at vector a0 */
+    int a0 = -1;
+    for (int a = 1; a <= T; a += m->bunch) {
+        const int b = a + m->bunch - 1 < T ? a + m->bunch - 1 : T;
+        if (b >= 16) { a0 = a; break; }
+    }
+    const int r_first = a0 > 0 ? a0 - 16 : T - 15;
+    const int P = r_first < 0 ? -r_first : 0;
+    float *mel = (float *)malloc(sizeof(float) * (size_t)(T + P) * m->nbanks);
+    float *post = (float *)malloc(sizeof(float) * (size_t)(T + P) * m->mg->nout);
+    orc_model_mel_from_audio(m, audio, nbytes, fmt, mel + (size_t)P * m->nbanks);
+    orc_online_norm(mel + (size_t)P * m->nbanks, T, m->nbanks, interval, mean_norm, var_norm);
+    for (int p = 0; p < P; ++p) memcpy(mel + (size_t)p * m->nbanks, mel + (size_t)P * m->nbanks, sizeof(float) * m->nbanks);
+    orc_posteriors_from_normed_mel(mel, T + P, m->nbanks, m->win, m->b0, m->b1, m->mg, post);
+    const int k = orc_model_decode(m, post, T + P, wp, out, cap);
+    free(mel);
+    free(post);
+    return k;
 }
 
 int orc_model_recognize(orc_model *m, const void *audio, int nbytes, int fmt, float wp, orc_label *out, int cap)

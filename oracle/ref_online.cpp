@@ -13,6 +13,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <string>
 #include <vector>
 #include <unistd.h>
 
@@ -72,12 +73,28 @@ static int run_norm(int argc, char **argv)
     return 0;
 }
 
+static std::string abs_path(const char *p)
+{
+    if (p[0] == '/') return p;
+    char cwd[2048];
+    if (!getcwd(cwd, sizeof cwd)) return p;
+    return std::string(cwd) + "/" + p;
+}
+
 static int run_stream(int argc, char **argv)
 {
     if (argc != 8) return 2;
+    // Normalization::SetFile (norm.cpp:248-259, called from SpeechRec::Init with the config's default file name "none")
+    // LOADS a file of that name if the working directory has one, and Normalization::Save writes one there the moment an
+    // estimate completes: run from a fresh scratch directory so that no run sees a previous run's estimate.
+    const std::string cfg_dir = abs_path(argv[2]), audio = abs_path(argv[3]), out_rec = abs_path(argv[7]);
+    char tmpl[] = "/tmp/online_ref.XXXXXX";
+    const char *td = mkdtemp(tmpl);
+    if (!td || chdir(td) != 0) return 9;
+    struct Cleanup { std::string d; ~Cleanup() { unlink((d + "/none").c_str()); rmdir(d.c_str()); } } cleanup{td};
     SpeechRec SR;
     char cfg[2048];
-    snprintf(cfg, sizeof cfg, "%s/config", argv[2]);
+    snprintf(cfg, sizeof cfg, "%s/config", cfg_dir.c_str());
     if (!SR.Init(cfg)) return 3;
     if (strcmp(argv[6], "-") != 0) SR.DE->SetWPenalty((float)atof(argv[6]));   // phnrec.cpp:212-221
     const SpeechRec::wave_format wf = SR.Str2WaveFormat(argv[5]);
@@ -85,14 +102,14 @@ static int run_stream(int argc, char **argv)
     SR.SetWaveFormat(wf);
     void *wave = 0;
     int nbytes = 0;
-    if (!SR.LoadWaveform(argv[3], &wave, &nbytes)) return 5;
+    if (!SR.LoadWaveform((char *)audio.c_str(), &wave, &nbytes)) return 5;
     const int block = atoi(argv[4]);
     if (block <= 0) return 6;
     // what RunLive does around ProcessOnline (srec.cpp:1438-1490): reset the streaming objects, open the decoder
     SR.MB.Reset();
     SR.TR.Reset();
     SR.ResetBunchBuff();
-    if (SR.DE->Init(argv[7]) != DECERR_NONE) return 7;
+    if (SR.DE->Init((char *)out_rec.c_str()) != DECERR_NONE) return 7;
     int pos = 0;
     do {
         const int n = nbytes - pos < block ? nbytes - pos : block;

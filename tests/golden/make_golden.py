@@ -20,6 +20,10 @@ Outputs
                     audio: un-normalised log-mel (`-t par`), linear posteriors
                     (`-t post`, float32, full matrix for CZ / EN, every 8th row for
                     the others) and the `.rec` text incl. the %f scores.
+  ref_online_stream.json  the ONLINE path: oracle/_ref/online_ref feeds files block by block through the reference's own
+                    SpeechRec::ProcessOnline / ProcessTail (srec.cpp:793-927) - several block sizes, penalties and
+                    [onlinenorm] settings (on edited copies of model directories); the .rec text of each run.
+                    (`python tests/golden/make_golden.py online` regenerates only this one.)
 Nothing in tests/ reads /root/reference at run time; only these files.
 """
 import json
@@ -49,7 +53,54 @@ GOLDENS = [  # (golden file, model dir under oracle/_ref/models, audio under ora
 ]
 
 
+ONLINE_CASES = [  # (name, model, audio, bytes used, wave format, block bytes, penalty or None, config edits)
+    ("en_4000", "PHN_EN_TIMIT_LCRC_N500", "test.raw", 119846, "lin16", 4000, None, {}),
+    ("en_1000", "PHN_EN_TIMIT_LCRC_N500", "test.raw", 119846, "lin16", 1000, None, {}),
+    ("en_odd_len", "PHN_EN_TIMIT_LCRC_N500", "test.raw", 60001, "lin16", 2500, -3.5, {}),
+    ("cz_2000", "PHN_CZ_SPDAT_LCRC_N1500", "test.raw", 119846, "lin16", 2000, None, {}),
+    ("cz_mean50", "PHN_CZ_SPDAT_LCRC_N1500", "test.raw", 119846, "lin16", 2000, None,
+     {"onlinenorm/estim_interval": "50", "onlinenorm/mean_norm": "true"}),
+    ("cz_meanvar120", "PHN_CZ_SPDAT_LCRC_N1500", "test.raw", 90000, "lin16", 3200, -2.0,
+     {"onlinenorm/estim_interval": "120", "onlinenorm/mean_norm": "true", "onlinenorm/var_norm": "true"}),
+    ("cz_never_estimated", "PHN_CZ_SPDAT_LCRC_N1500", "test.raw", 30000, "lin16", 2000, None,
+     {"onlinenorm/estim_interval": "500", "onlinenorm/mean_norm": "true"}),
+    ("cz_alaw_short", "PHN_CZ_SPDAT_LCRC_N1500", "8580.wav", 3000, "alaw", 700, None, {}),
+    ("cz_alaw_35_frames", "PHN_CZ_SPDAT_LCRC_N1500", "8580.wav", 200 + 34 * 80 + 13, "alaw", 500, None, {}),
+    ("cz_alaw_9_frames", "PHN_CZ_SPDAT_LCRC_N1500", "8580.wav", 200 + 8 * 80, "alaw", 300, None, {}),
+    ("cz_alaw_17_frames", "PHN_CZ_SPDAT_LCRC_N1500", "8580.wav", 200 + 16 * 80, "alaw", 400, None, {}),
+    ("cz_bunch4", "PHN_CZ_SPDAT_LCRC_N1500", "test.raw", 40000, "lin16", 1600, None, {"posteriors/bunch_size": "4"}),
+    ("cz_bunch4_14_frames", "PHN_CZ_SPDAT_LCRC_N1500", "8580.wav", 200 + 13 * 80, "alaw", 400, None, {"posteriors/bunch_size": "4"}),
+    ("hu_framenorm", "PHN_HU_SPDAT_LCRC_N1500", "test.raw", 64000, "lin16", 1600, None,
+     {"framenorm/shift": "0.75", "onlinenorm/estim_interval": "30", "onlinenorm/mean_norm": "true"}),
+]
+
+
+def online_stream():
+    """ref_online_stream.json: the reference's online path, block by block (oracle/_ref/online_ref stream)."""
+    sys.path.insert(0, str(ROOT / "tests"))
+    from conftest import variant_model_dir  # noqa: E402
+    online_ref = orc.REF_BIN.parent / "online_ref"
+    out = []
+    with tempfile.TemporaryDirectory() as td:
+        td = Path(td)
+        for name, model, audio, nbytes, fmt, block, pen, edits in ONLINE_CASES:
+            cfg = variant_model_dir(td / name, model, edits) if edits else orc.REF_MODELS / model
+            (td / "a.raw").write_bytes((orc.REF_AUDIO / audio).read_bytes()[:nbytes])
+            r = subprocess.run([str(online_ref), "stream", str(cfg), str(td / "a.raw"), str(block), fmt, "-" if pen is None else str(pen),
+                                str(td / "o.rec")], capture_output=True, text=True)
+            assert r.returncode == 0, (name, r.returncode, r.stderr[-300:])
+            rec = (td / "o.rec").read_text()
+            out.append({"name": name, "model": model, "audio": audio, "nbytes": nbytes, "fmt": fmt, "block": block, "penalty": pen,
+                        "edits": edits, "rec": rec})
+            print("online", name, len(rec.splitlines()), "labels")
+    (OUT / "ref_online_stream.json").write_text(json.dumps(out, indent=1))
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "online":
+        online_stream()
+        return
+    online_stream()
     labels = {}
     for g, model, audio, mlf in GOLDENS:
         txt = (REF / g).read_text()

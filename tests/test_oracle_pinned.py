@@ -168,3 +168,28 @@ def test_vadalize_output_matches_reference_tool(orc, oracle_models, key):
     model, audio = key.split("/")
     om = oracle_models(model)
     assert orc.format_vad(om.recognize(audio_bytes(audio)), om.phonemes) == want
+
+
+def online_stream_cases():
+    """tests/golden/ref_online_stream.json: the reference's own ProcessOnline / ProcessTail fed block by block by
+    oracle/_ref/online_ref (generated by tests/golden/make_golden.py online)."""
+    import json
+    from conftest import GOLDEN
+    return json.loads((GOLDEN / "ref_online_stream.json").read_text())
+
+
+def test_online_path_restatement_equals_reference_objects(orc, tmp_path):
+    """§8(f) rank 1 pinned: the whole-signal restatement of the online path (orc_model_recognize_online: streaming frame count,
+    FrameBasedNormalization, the live normaliser, clamped context, decoder) prints what the reference's streaming objects
+    print when they are fed in blocks - every block size, penalty and [onlinenorm] setting of the fixture, labels AND scores."""
+    from conftest import audio_bytes, variant_model_dir, model_dir
+    n = 0
+    for c in online_stream_cases():
+        cfg = variant_model_dir(tmp_path / c["name"], c["model"], c["edits"]) if c["edits"] else model_dir(c["model"])
+        m = orc.Model(cfg)
+        a = audio_bytes(c["audio"])[:c["nbytes"]]
+        got = m.recognize_online(a, fmt=c["fmt"], wp=c["penalty"])
+        assert orc.format_rec(got, m.phonemes) == c["rec"], c["name"]
+        m.close()
+        n += 1
+    assert n >= 14
