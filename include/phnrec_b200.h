@@ -138,6 +138,38 @@ int phn_recognize_async(phn_ctx *ctx, const void *audio, const int64_t *byte_off
 int phn_wait(phn_ctx *ctx, phn_label *labels, int64_t label_cap, int64_t *label_off, int64_t *frame_off_out);
 int phn_pending(const phn_ctx *ctx);     /* batches enqueued by phn_recognize_async and not yet returned by phn_wait */
 
+/* -- streaming (online) mode ---------------------------------------------------------
+ * Replaces SpeechRec::ProcessOnline / ProcessLastBunch / ProcessTail (srec.cpp:793-927) with its live
+ * normaliser Normalization::ProcessFrame (norm.cpp:216-234, configured by [onlinenorm] estim_interval /
+ * mean_norm / var_norm, srec.cpp:594-601) - the path the reference drives from a sound card in 125 ms
+ * blocks (RunLive, srec.cpp:1438-1490) - for MANY concurrent streams on one GPU.  A stream is the
+ * reference's set of streaming objects: MelBanks' frame buffer (melbanks.cpp:151-204), the 31-frame FIFO
+ * of Traps (traps.cpp:180-219), PhnDec with its 41-slot history (phndec.cpp:44-302) and the normaliser's
+ * running estimate; their state stays in the context between pushes.
+ *   phn_stream_open(ctx, n)   n streams, all in their initial state (replaces any earlier set).
+ *   phn_stream_reset(ctx, s)  stream s back to its initial state, normaliser included.
+ *   phn_stream_push(ctx, sids, n, audio, byte_off, last, labels, cap, label_off)
+ *       one block of audio for each of the n streams sids[i] (each stream at most once per push): bytes
+ *       [byte_off[i], byte_off[i+1]) of `audio` (host memory, the context's wave format; a lin16 block
+ *       contributes floor(bytes/2) samples, like ConvertWaveformFormat called per block).  Blocks may have
+ *       any length, also 0.  last[i] != 0 ends the utterance on that stream (ProcessTail + Decoder::Done):
+ *       the stream then starts a new utterance with its next block; the normaliser's estimate is kept,
+ *       as the reference's Normalization object outlives MelBanks::Reset / Traps::Reset.  `last` may be NULL.
+ *       Returns the labels that became final during this push (TimePruning commits, phndec.cpp:191-234,
+ *       and, for ending streams, the final traceback) - what the reference hands to the decoder callback
+ *       (decoder.h:30-35) while it runs: labels of pushed stream i are labels[label_off[i] .. label_off[i+1]).
+ *       The concatenation over a stream's pushes is exactly the label sequence of the reference's online
+ *       path on the concatenated audio, whatever the block sizes, and however streams are interleaved.
+ *       An utterance shorter than 15 frames is decoded over 15 frames, like the reference's (the tail of
+ *       15 copies of the last frame also flushes 15 - T warm-up rows through the decoder).
+ *   Needs posteriors/bunch_size to divide 15 (all shipped configs: 5); XML persistence of the estimates
+ *   (onlinenorm/file) and scale_to_gvar are not supported (PHN_ERR_UNSUPPORTED). */
+int phn_stream_open(phn_ctx *ctx, int n_streams);
+int phn_stream_count(const phn_ctx *ctx);
+int phn_stream_reset(phn_ctx *ctx, int sid);
+int phn_stream_push(phn_ctx *ctx, const int *sids, int n, const void *audio, const int64_t *byte_off, const int *last,
+                    phn_label *labels, int64_t label_cap, int64_t *label_off);
+
 /* -- device-resident variants (inputs already in HBM; used by bench.py and servers) -- */
 /* d_audio is a DEVICE pointer on the context's device; byte_off stays a host array.
  * Runs wave -> mean -> STC -> MLPs on the context's stream and Viterbi + traceback on the context's

@@ -75,6 +75,10 @@ _SYMS = [
     ("phn_recognize_async", C.c_int, [C.c_void_p, C.c_void_p, _i64p, C.c_int]),
     ("phn_wait", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, _i64p, C.c_void_p]),
     ("phn_pending", C.c_int, [C.c_void_p]),
+    ("phn_stream_open", C.c_int, [C.c_void_p, C.c_int]),
+    ("phn_stream_count", C.c_int, [C.c_void_p]),
+    ("phn_stream_reset", C.c_int, [C.c_void_p, C.c_int]),
+    ("phn_stream_push", C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, _i64p, C.c_void_p, C.c_void_p, C.c_int64, _i64p]),
     ("phn_recognize_device", C.c_int, [C.c_void_p, C.c_void_p, _i64p, C.c_int]),
     ("phn_decode_device", C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     ("phn_sync", C.c_int, [C.c_void_p]),
@@ -286,6 +290,26 @@ class Recognizer:
                     out.append(self._split_labels(labels, loff))
                     done += 1
         return out
+
+    # -- streaming (online) mode: SpeechRec::ProcessOnline for many concurrent streams
+    def stream_open(self, n_streams: int):
+        self._ck(self._L.phn_stream_open(self._h, int(n_streams)))
+
+    def stream_reset(self, sid: int):
+        self._ck(self._L.phn_stream_reset(self._h, int(sid)))
+
+    def stream_push(self, sids, blocks, last=None):
+        """One block of audio bytes per stream in `sids`; returns the labels that became final, one array per pushed stream."""
+        n = len(sids)
+        audio, boff = self._concat_audio(blocks)
+        sid = np.ascontiguousarray(sids, dtype=np.int32)
+        lst = None if last is None else np.ascontiguousarray([1 if x else 0 for x in last], dtype=np.int32)
+        cap = int(sum(len(b) for b in blocks) // 20 + 64 * n + 64)
+        labels = np.zeros(cap, dtype=LABEL_DTYPE)
+        loff = np.zeros(n + 1, dtype=np.int64)
+        self._ck(self._L.phn_stream_push(self._h, sid.ctypes.data, n, audio.ctypes.data, boff, None if lst is None else lst.ctypes.data,
+                                         labels.ctypes.data, cap, loff))
+        return self._split_labels(labels, loff)
 
     def recognize_device(self, d_audio: int, byte_off: np.ndarray):
         self._ck(self._L.phn_recognize_device(self._h, d_audio, byte_off, len(byte_off) - 1))

@@ -1,6 +1,7 @@
 // capi.cu — the C ABI (include/phnrec_b200.h): context lifetime, batch planning, stage sequencing
 // on one CUDA stream, host<->device copies.  No computation happens on the host.
 #include "internal.h"
+#include <algorithm>
 #include <chrono>
 
 #include <cmath>
@@ -143,6 +144,7 @@ static int upload_net(phn_ctx *c, int which)
 static int64_t frames_of(const phn_ctx *c, int64_t nbytes)
 {
     const int64_t n = c->fmt == PHN_WAVE_LIN16 ? nbytes / 2 : nbytes;
+    if (c->stream_frames) return n >= c->vs ? (n - c->vs) / c->step + 1 : 0;   // MelBanks::GetFeatures fed in blocks: full frames only
     return n > c->vs ? (n - c->vs) / c->step + 1 : 1;
 }
 
@@ -464,6 +466,10 @@ int phn_create(const char *cfg_dir, int device, phn_ctx **out)
     c->frame_floor = C.f("framenorm", "min_floor");
     c->wpenalty = C.f("decoder", "wpenalty");
     c->hist = C.i("decoder", "time_pruning");
+    c->on_interval = C.i("onlinenorm", "estim_interval");   // srec.cpp:594-601 (used by the streaming path only)
+    c->on_mean = C.b("onlinenorm", "mean_norm");
+    c->on_var = C.b("onlinenorm", "var_norm");
+    c->bunch = atoi(C.str("posteriors", "bunch_size").c_str());
     c->S = 3;
     if (c->nbanks < 1 || c->nbanks > 32 || c->vs < 2 || c->vs > 4096 || c->step < 1 || c->hist < 1)
         return bail(fail(c, PHN_ERR_CFG_BADVAL, "Front-end sizes out of range in '%s'\n", cfg_file.c_str()));
@@ -571,7 +577,7 @@ void phn_destroy(phn_ctx *c)
         if (c->vit_stream) cudaStreamSynchronize(c->vit_stream);
         tl_dump(c);
     }
-    phn_ctx::Buf *bufs[] = {&c->d_audio, &c->d_byte_off, &c->d_frame_off, &c->d_lab_off, &c->d_mel, &c->d_mean, &c->d_post,
+    phn_ctx::Buf *bufs[] = {&c->d_st_hist, &c->d_st_norm, &c->d_st_cnt, &c->d_st_vit, &c->d_st_args, &c->d_win, &c->d_st_labels, &c->d_st_nlab, &c->d_audio, &c->d_byte_off, &c->d_frame_off, &c->d_lab_off, &c->d_mel, &c->d_mean, &c->d_post,
                             &c->d_rec, &c->d_pen, &c->d_x0, &c->d_x1, &c->d_h, &c->d_xm,
                             &c->d_x0h, &c->d_x1h, &c->d_xmh, &c->d_tile_ctr, &c->d_logp, &c->d_pair_off,
                             &c->slot[0].d_labels, &c->slot[0].d_nlab, &c->slot[0].d_lab_off, &c->slot[0].d_frame_off, &c->slot[0].d_coff, &c->slot[0].d_labels_c,
@@ -1026,6 +1032,185 @@ int phn_wait(phn_ctx *c, phn_label *labels, int64_t label_cap, int64_t *label_of
 }
 
 int phn_pending(const phn_ctx *c) { return c ? c->n_pend : 0; }
+
+// ===================================================================== streaming (online) path
+// SpeechRec::ProcessOnline / ProcessTail (srec.cpp:793-927) for many concurrent streams: every push hands one block of audio
+// per stream to the GPU; the streams' state lives in the context between pushes (k_stream.cu).
+int phn_stream_open(phn_ctx *c, int n_streams)
+{
+    if (!c || n_streams < 0) return PHN_ERR_ARG;
+    PHN_CUDA(c, cudaSetDevice(c->device));
+    if (c->bunch < 1 || 15 % c->bunch != 0)
+        return fail(c, PHN_ERR_UNSUPPORTED, "streaming needs a posteriors/bunch_size that divides the trap shift 15 (1, 3, 5, 15); it is %d: the reference's online path "
+                                            "then hands warm-up rows to the decoder depending on where bunches fall\n", c->bunch);
+    if (c->hist + 1 > 64) return fail(c, PHN_ERR_UNSUPPORTED, "streaming keeps a 64-slot decoder history; decoder/time_pruning is %d\n", c->hist);
+    if (c->on_var && !c->on_mean) return fail(c, PHN_ERR_ARG, "online normalisation: var_norm without mean_norm (the reference asserts, norm.cpp:152)\n");
+    if (c->cfg.str("onlinenorm", "file") != "none") return fail(c, PHN_ERR_UNSUPPORTED, "onlinenorm/file (XML persistence of the estimates) is not supported\n");
+    if (c->cfg.b("onlinenorm", "scale_to_gvar")) return fail(c, PHN_ERR_UNSUPPORTED, "onlinenorm/scale_to_gvar is not supported\n");
+    int rc;
+    const size_t n = (size_t)n_streams;
+    if ((rc = ensure(c, c->d_st_hist, sizeof(float) * n * 30 * c->nbanks))) return rc;
+    if ((rc = ensure(c, c->d_st_norm, sizeof(float) * n * 4 * c->nbanks))) return rc;
+    if ((rc = ensure(c, c->d_st_cnt, sizeof(unsigned) * n))) return rc;
+    if ((rc = ensure(c, c->d_st_vit, sizeof(VitStreamState) * n))) return rc;
+    c->streams.assign(n, phn_ctx::StreamHost());
+    for (int s = 0; s < n_streams; ++s)
+        if ((rc = phn_stream_reset(c, s))) return rc;
+    return PHN_OK;
+}
+
+int phn_stream_count(const phn_ctx *c) { return c ? (int)c->streams.size() : 0; }
+
+// A stream back to its initial state, the live normaliser included (a fresh Normalization::StartEstimation).
+int phn_stream_reset(phn_ctx *c, int sid)
+{
+    if (!c) return PHN_ERR_ARG;
+    if (sid < 0 || sid >= (int)c->streams.size()) return fail(c, PHN_ERR_ARG, "phn_stream_reset: no stream %d\n", sid);
+    PHN_CUDA(c, cudaSetDevice(c->device));
+    c->streams[sid] = phn_ctx::StreamHost();
+    // ChannelNormParams::Null (norm.cpp:59-70): sums 0, mean 0, inverse std 1; nothing accumulated
+    std::vector<float> z((size_t)4 * c->nbanks, 0.0f);
+    for (int b = 0; b < c->nbanks; ++b) z[(size_t)3 * c->nbanks + b] = 1.0f;
+    PHN_CUDA(c, cudaMemcpyAsync((float *)c->d_st_norm.p + (size_t)sid * 4 * c->nbanks, z.data(), sizeof(float) * z.size(), cudaMemcpyHostToDevice, c->stream));
+    PHN_CUDA(c, cudaMemsetAsync((unsigned *)c->d_st_cnt.p + sid, 0, sizeof(unsigned), c->stream));
+    return PHN_OK;
+}
+
+int phn_stream_push(phn_ctx *c, const int *sids, int n, const void *audio, const int64_t *byte_off, const int *last, phn_label *labels,
+                    int64_t label_cap, int64_t *label_off)
+{
+    if (!c) return PHN_ERR_ARG;
+    if (n < 0 || (n > 0 && (!sids || !byte_off || !label_off))) return fail(c, PHN_ERR_ARG, "phn_stream_push: invalid arguments\n");
+    if (c->n_pend) return fail(c, PHN_ERR_ARG, "asynchronous batches are in flight: phn_wait for them first\n");
+    PHN_CUDA(c, cudaSetDevice(c->device));
+    if (label_off) label_off[0] = 0;
+    if (n == 0) return PHN_OK;
+    const int bps = c->fmt == PHN_WAVE_LIN16 ? 2 : 1;
+    const int nstr = (int)c->streams.size();
+    {   // every stream at most once per push
+        std::vector<char> seen((size_t)nstr, 0);
+        if (byte_off[0] != 0) return fail(c, PHN_ERR_ARG, "offsets must start at 0\n");
+        for (int i = 0; i < n; ++i) {
+            if (sids[i] < 0 || sids[i] >= nstr) return fail(c, PHN_ERR_ARG, "phn_stream_push: no stream %d (phn_stream_open)\n", sids[i]);
+            if (seen[sids[i]]) return fail(c, PHN_ERR_ARG, "phn_stream_push: stream %d appears twice in one push\n", sids[i]);
+            seen[sids[i]] = 1;
+            if (byte_off[i + 1] < byte_off[i]) return fail(c, PHN_ERR_ARG, "offsets must be non-decreasing\n");
+        }
+        if (!audio && byte_off[n] > 0) return fail(c, PHN_ERR_ARG, "null audio buffer\n");
+    }
+    // ---- host: [tail | block] per stream (a lin16 block contributes floor(bytes / 2) samples taken from its start, like
+    //      ConvertWaveformFormat called per block, srec.cpp:709-743), new frame counts, windows, decoder row ranges
+    std::vector<int64_t> boff((size_t)n + 1, 0), noff((size_t)n + 1, 0), woff((size_t)n + 1, 0), row0((size_t)n), loff((size_t)n + 1, 0);
+    std::vector<int> pad((size_t)n), hist((size_t)n), cnt((size_t)n), fresh((size_t)n), lastv((size_t)n);
+    c->h_stage.clear();
+    for (int i = 0; i < n; ++i) {
+        phn_ctx::StreamHost &S = c->streams[sids[i]];
+        const int64_t nb = (byte_off[i + 1] - byte_off[i]) / bps * bps;
+        c->h_stage.insert(c->h_stage.end(), S.tail.begin(), S.tail.end());
+        const uint8_t *src = (const uint8_t *)audio + byte_off[i];
+        c->h_stage.insert(c->h_stage.end(), src, src + nb);
+        boff[i + 1] = (int64_t)c->h_stage.size();
+        const int64_t samples = (boff[i + 1] - boff[i]) / bps;
+        const int64_t nf = samples >= c->vs ? (samples - c->vs) / c->step + 1 : 0;
+        noff[i + 1] = noff[i] + nf;
+        // what stays for the next push: everything from the first sample of the next frame on
+        const int64_t used = nf * c->step * bps;
+        S.tail.assign(c->h_stage.begin() + boff[i] + used, c->h_stage.begin() + boff[i + 1]);
+        const bool is_last = last && last[i];
+        const int64_t T = S.frames + nf;                       // frames of the stream so far
+        const int64_t w0 = S.frames - S.hist;                  // global index of the window's first real frame
+        const int64_t avail = is_last ? T : std::max<int64_t>(S.rows_done, T - 15);
+        int64_t r_lo = S.rows_done;
+        pad[i] = 0;
+        if (is_last && T > 0 && T < 15 && S.rows_done == 0) { pad[i] = (int)(15 - T); r_lo = -(int64_t)pad[i]; }   // the tail's warm-up rows
+        hist[i] = S.hist;
+        woff[i + 1] = woff[i] + pad[i] + S.hist + nf;
+        row0[i] = woff[i] + pad[i] + (r_lo - w0);
+        cnt[i] = (int)(avail - r_lo);
+        fresh[i] = S.fed ? 0 : 1;
+        lastv[i] = is_last ? 1 : 0;
+        loff[i + 1] = loff[i] + cnt[i] + 48;
+        S.fed = S.fed || cnt[i] > 0;
+        S.frames = T;
+        S.rows_done = avail;
+        S.hist = (int)std::min<int64_t>(30, S.hist + nf);
+        if (is_last) {   // the next block starts a new utterance on this stream; the normaliser's estimate stays (it outlives
+            const std::vector<uint8_t> none;   // MelBanks / Traps / decoder resets in the reference as well)
+            S = phn_ctx::StreamHost();
+        }
+    }
+    // ---- audio -> new log-mel frames (streaming frame count), live normaliser
+    int rc;
+    reset_timing(c);
+    c->stream_frames = 1;
+    rc = plan_audio(c, boff.data(), n);
+    c->stream_frames = 0;
+    if (rc) return rc;
+    if ((rc = ensure(c, c->d_audio, (size_t)c->total_bytes + 16))) return rc;
+    if (c->total_bytes)
+        PHN_CUDA(c, cudaMemcpyAsync(c->d_audio.p, c->h_stage.data(), (size_t)c->total_bytes, cudaMemcpyHostToDevice, c->stream));
+    const bool tc = c->mlp_mode == PHN_MLP_TC_F16;
+    c->force_exact_wave = tc ? 0 : 1;
+    c->fast_front = tc ? 1 : 0;
+    { StageTimer t(c, PHN_K_WAVE); rc = launch_wave(c, c->d_audio.p); }
+    c->force_exact_wave = 0;
+    c->fast_front = 0;
+    if (rc) return rc;
+    // per-push argument block: [sids | pad | hist | cnt | fresh | last] ints, then [noff | woff | row0 | loff] int64
+    const size_t ni = (size_t)n;
+    std::vector<int> ia(6 * ni);
+    for (size_t i = 0; i < ni; ++i) { ia[i] = sids[i]; ia[ni + i] = pad[i]; ia[2 * ni + i] = hist[i]; ia[3 * ni + i] = cnt[i]; ia[4 * ni + i] = fresh[i]; ia[5 * ni + i] = lastv[i]; }
+    const size_t ib = (sizeof(int) * 6 * ni + 15) / 16 * 16;
+    std::vector<int64_t> la;
+    la.insert(la.end(), noff.begin(), noff.end());
+    la.insert(la.end(), woff.begin(), woff.end());
+    la.insert(la.end(), row0.begin(), row0.end());
+    la.insert(la.end(), loff.begin(), loff.end());
+    if ((rc = ensure(c, c->d_st_args, ib + sizeof(int64_t) * la.size()))) return rc;
+    uint8_t *dargs = (uint8_t *)c->d_st_args.p;
+    if ((rc = upload_small(c, dargs, ia.data(), sizeof(int) * ia.size(), c->stream))) return rc;
+    if ((rc = upload_small(c, dargs + ib, la.data(), sizeof(int64_t) * la.size(), c->stream))) return rc;
+    const int *d_sid = (const int *)dargs, *d_pad = d_sid + ni, *d_hist = d_sid + 2 * ni, *d_cnt = d_sid + 3 * ni, *d_fresh = d_sid + 4 * ni, *d_last = d_sid + 5 * ni;
+    const int64_t *d_noff = (const int64_t *)(dargs + ib), *d_woff = d_noff + (ni + 1), *d_row0 = d_woff + (ni + 1), *d_loff = d_row0 + ni;
+    if ((rc = launch_stream_norm(c, n, d_sid, (float *)c->d_st_norm.p, (unsigned *)c->d_st_cnt.p, c->on_interval, c->on_mean, c->on_var))) return rc;
+    // ---- windows [warm-up copies | history | new frames] -> the batch posterior estimator, no sentence normalisation
+    const int64_t W = woff[n];
+    if ((rc = ensure(c, c->d_win, sizeof(float) * (size_t)(W + 1) * c->nbanks))) return rc;
+    if ((rc = launch_stream_assemble(c, n, d_noff, d_woff, d_sid, d_pad, d_hist, (float *)c->d_win.p, (float *)c->d_st_hist.p))) return rc;
+    if ((rc = plan_frames(c, woff.data(), n, 1))) return rc;
+    if (W) PHN_CUDA(c, cudaMemcpyAsync(c->d_mel.p, c->d_win.p, sizeof(float) * (size_t)W * c->nbanks, cudaMemcpyDeviceToDevice, c->stream));
+    const int smn = c->sent_mean_norm;
+    c->sent_mean_norm = 0;
+    rc = run_posteriors(c);
+    c->sent_mean_norm = smn;
+    if (rc) return rc;
+    // ---- decoder: ln p, then every stream's machine over its new rows; labels committed by TimePruning (and Done) come back
+    if ((rc = ensure(c, c->d_st_labels, sizeof(phn_label) * (size_t)loff[n]))) return rc;
+    if ((rc = ensure(c, c->d_st_nlab, sizeof(int) * ni))) return rc;
+    {
+        StageTimer t(c, PHN_K_VIT);
+        rc = launch_stream_decode(c, n, W, d_row0, d_cnt, d_sid, d_fresh, d_last, (VitStreamState *)c->d_st_vit.p, (phn_label *)c->d_st_labels.p, d_loff,
+                                  (int *)c->d_st_nlab.p);
+    }
+    if (rc) return rc;
+    std::vector<int> nl(ni);
+    PHN_CUDA(c, cudaMemcpyAsync(nl.data(), c->d_st_nlab.p, sizeof(int) * ni, cudaMemcpyDeviceToHost, c->stream));
+    PHN_CUDA(c, cudaStreamSynchronize(c->stream));
+    int64_t total = 0;
+    for (size_t i = 0; i < ni; ++i) {
+        if (nl[i] > cnt[i] + 48) return fail(c, PHN_ERR_CAPACITY, "internal label capacity exceeded (stream %d)\n", sids[i]);
+        total += nl[i];
+        label_off[i + 1] = total;
+    }
+    if (!labels && total) return fail(c, PHN_ERR_CAPACITY, "label buffer too small: %lld needed\n", (long long)total);
+    if (label_cap < total) return fail(c, PHN_ERR_CAPACITY, "label buffer too small: %lld needed\n", (long long)total);
+    for (size_t i = 0; i < ni; ++i)
+        if (nl[i])
+            PHN_CUDA(c, cudaMemcpyAsync(labels + label_off[i], (const phn_label *)c->d_st_labels.p + loff[i], sizeof(phn_label) * (size_t)nl[i],
+                                        cudaMemcpyDeviceToHost, c->stream));
+    PHN_CUDA(c, cudaStreamSynchronize(c->stream));
+    return PHN_OK;
+}
 
 // Debug aid (not part of the stable ABI surface used by the reference binding): the next tensor-core launches of
 // net `which` record clock64() timestamps of CTA 0's second tile into a 16 x 16 table; which < 0 reads it back.

@@ -54,6 +54,17 @@ struct DevNet {
     int kin;   // data columns of the fp16 activation image; columns kin, kin+1 hold the constant 1.0 that multiplies b1
 };
 
+// Decoder of one stream between two pushes (k_stream.cu): PhnDec's members (phndec.cpp:44-94), the history as a 64-slot ring
+struct VitStreamState {
+    float al[128 * 4];
+    int pv[128 * 4], ln[128 * 4];
+    int hphn[64], hlen[64];
+    float halpha[64];
+    int n, last_mi;
+    float prev_alpha;
+    int pad_;
+};
+
 struct DevTables {
     float *hamming, *coeffs;
     int *banks, *bank_klo, *bank_khi;
@@ -142,6 +153,21 @@ struct phn_ctx {
     std::vector<int64_t> h_pair_off;
     std::vector<float> h_pen;
     int64_t chunk_frames = 0;
+    // ---- streaming (online) path: per-stream state, host side and device side (phn_stream_*)
+    struct StreamHost {
+        std::vector<uint8_t> tail;   // whole samples that have not completed a frame yet (raw bytes)
+        int64_t frames = 0;          // log-mel frames produced so far
+        int64_t rows_done = 0;       // posterior rows handed to the decoder so far
+        int hist = 0;                // frames held in the device history (<= 30)
+        bool fed = false;            // the decoder has consumed at least one row (its state on the device is live)
+    };
+    std::vector<StreamHost> streams;
+    Buf d_st_hist, d_st_norm, d_st_cnt, d_st_vit;     // [n_streams] x {30 x nbanks floats, 4 x nbanks floats, unsigned, VitStreamState}
+    Buf d_st_args, d_win, d_st_labels, d_st_nlab;     // per-push argument block, assembled windows, label output
+    std::vector<uint8_t> h_stage;                     // [tail | block] of every pushed stream
+    int on_interval = 0, on_mean = 0, on_var = 0, bunch = 5;   // [onlinenorm] estim_interval / mean_norm / var_norm, [posteriors] bunch_size
+    int stream_frames = 0;                            // frames_of() counts streaming frames (none below vector_size samples)
+
     // profiling
     int profiling = 0;
     float k_ms[PHN_K_COUNT] = {0};
@@ -174,6 +200,13 @@ int launch_mlp_tc(phn_ctx *c, int64_t f0, int64_t nf);                     // k_
 int launch_viterbi(phn_ctx *c, const float *d_pen, int n_pen, cudaStream_t s, phn_ctx::DecSlot &sl);   // k_vit.cu
 int launch_compact_labels(phn_ctx *c, int nseg, phn_ctx::DecSlot &sl);     // k_vit.cu
 int launch_logf_range(phn_ctx *c, uint32_t first_bits, int64_t n, float *d_out);   // k_vit.cu (verification aid)
+int launch_log_post(phn_ctx *c, int64_t rows);                               // k_vit.cu: d_post -> d_logp (row-major), first `rows` rows
+// k_stream.cu: the state-carrying kernels of the streaming path
+int launch_stream_norm(phn_ctx *c, int n, const int *d_sid, float *d_state, unsigned *d_cnt, int interval, int mean_norm, int var_norm);
+int launch_stream_assemble(phn_ctx *c, int n, const int64_t *d_new_off, const int64_t *d_win_off, const int *d_sid, const int *d_pad,
+                           const int *d_hist, float *d_win, float *d_st_hist);
+int launch_stream_decode(phn_ctx *c, int n, int64_t rows, const int64_t *d_row0, const int *d_count, const int *d_sid, const int *d_fresh,
+                         const int *d_last, phn::VitStreamState *d_st, phn_label *d_labels, const int64_t *d_lab_off, int *d_nlab);
 int launch_synth(phn_ctx *c, void *d_audio, int64_t bytes_per_utt, int n_utt, uint64_t seed);  // k_synth.cu
 int mlp_tc_fill_merger_bias(phn_ctx *c, int64_t rows);                     // constant-1 bias columns of the merger image
 int mlp_tc_prepare(phn_ctx *c);                                            // fp16 weight images (k_mlp_tc.cu)

@@ -89,6 +89,17 @@ int launch_logf_range(phn_ctx *c, uint32_t first_bits, int64_t n, float *d_out)
 #ifndef PHN_VIT_MINB
 #define PHN_VIT_MINB 1
 #endif
+int launch_log_post(phn_ctx *c, int64_t rows)
+{
+    if (rows <= 0) return PHN_OK;
+    int64_t blocks = (rows + 7) / 8;
+    if (blocks > (int64_t)c->num_sms * 16) blocks = (int64_t)c->num_sms * 16;
+    k_log_post<<<(unsigned)blocks, 256, 0, c->stream>>>((const float *)c->d_post.p, c->ldp, 3 * c->P, rows, (float *)c->d_logp.p);
+    PHN_CUDA(c, cudaGetLastError());
+    c->k_launches[PHN_K_VIT] += 1;
+    return PHN_OK;
+}
+
 template <int PPL, bool TILED>
 __global__ void __launch_bounds__(32, PPL <= 2 ? PHN_VIT_MINB : 1) k_viterbi(VitArgs a)
 {
