@@ -11,6 +11,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <algorithm>
 #include <atomic>
 #include <condition_variable>
@@ -29,6 +30,17 @@ namespace {
 enum DataFmt { dfWaveform = 0, dfParams = 1, dfPosteriors = 2, dfStrings = 3, dfUnknown = 4 };  // srec.h order
 
 bool g_verbose = false;
+
+// PHNREC_CLI_TIMING=1: wall-clock of the process's phases on stderr (development aid)
+double wall_ms()
+{
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
+const bool g_timing = getenv("PHNREC_CLI_TIMING") != nullptr;
+const double g_t0 = wall_ms();
+void phase(const char *what) { if (g_timing) fprintf(stderr, "[phnrec timing] %8.1f ms  %s\n", wall_ms() - g_t0, what); }
 
 [[noreturn]] void die(const char *fmt, ...) __attribute__((format(printf, 1, 2)));
 void die(const char *fmt, ...)
@@ -551,7 +563,18 @@ int main(int argc, char *argv[])
 
     if (!config_dir) { fprintf(stderr, "ERROR: Configuration directory is not set (-c)\n"); return 1; }
     logmsg("\nSystem initialization\n");
+    phase("arguments parsed");
+    // contexts on the further devices (list mode, audio -> labels) are created side by side with the first one
+    std::vector<std::thread> more_threads;
+    std::vector<phn_ctx *> more(devices.size(), nullptr);
+    std::vector<std::string> more_err(devices.size());
+    if (file_list && R.inf == dfWaveform && R.outf == dfStrings)
+        for (size_t d = 1; d < devices.size(); ++d)
+            more_threads.emplace_back([&, d] {
+                if (phn_create(config_dir, devices[d], &more[d])) { more_err[d] = phn_last_error(nullptr); more[d] = nullptr; }
+            });
     if (phn_create(config_dir, device, &R.ctx)) die("%s", phn_last_error(nullptr));
+    phase("first context created (CUDA context, model load)");
     phn_get_info(R.ctx, &R.info);
     logmsg("  - mel-banks ...\n  - online normalization ...\n  - posteriors (loading NNs) ...\n  - decoder ...\n\n");
     logmsg("------------------- SUMMARY -------------------\n");
@@ -641,22 +664,15 @@ int main(int argc, char *argv[])
                 P.jobs.push_back(j);
             }
             P.ctxs.push_back(R.ctx);
-            {   // further devices: same model, same settings, created side by side
-                std::vector<std::thread> th;
-                std::vector<phn_ctx *> more(devices.size(), nullptr);
-                std::vector<std::string> cerr_(devices.size());
-                for (size_t d = 1; d < devices.size(); ++d)
-                    th.emplace_back([&, d] {
-                        if (phn_create(config_dir, devices[d], &more[d])) { cerr_[d] = phn_last_error(nullptr); more[d] = nullptr; return; }
-                        phn_set_mlp_mode(more[d], mlp_mode);
-                        phn_set_penalty(more[d], R.info_penalty);
-                        if (wformat) phn_set_wave_format(more[d], !strcmp(wformat, "alaw") ? PHN_WAVE_ALAW : PHN_WAVE_LIN16);
-                    });
-                for (auto &t : th) t.join();
-                for (size_t d = 1; d < devices.size(); ++d) {
-                    if (!more[d]) die("%s", cerr_[d].empty() ? "Can not create a context on a further device\n" : cerr_[d].c_str());
-                    P.ctxs.push_back(more[d]);
-                }
+            for (auto &t : more_threads) t.join();
+            more_threads.clear();
+            phase("further contexts created");
+            for (size_t d = 1; d < devices.size(); ++d) {   // same model, same settings
+                if (!more[d]) die("%s", more_err[d].empty() ? "Can not create a context on a further device\n" : more_err[d].c_str());
+                phn_set_mlp_mode(more[d], mlp_mode);
+                phn_set_penalty(more[d], R.info_penalty);
+                if (wformat) phn_set_wave_format(more[d], !strcmp(wformat, "alaw") ? PHN_WAVE_ALAW : PHN_WAVE_LIN16);
+                P.ctxs.push_back(more[d]);
             }
             const size_t nd = P.ctxs.size();
             size_t per = (P.jobs.size() + 4 * nd - 1) / (4 * nd);   // about four batches per device: file reading overlaps the GPU
@@ -667,7 +683,9 @@ int main(int argc, char *argv[])
             P.readers = (int)std::max<size_t>(1, std::min<size_t>(8, (hw ? hw : 8) / nd));
             if (const char *e = getenv("PHNREC_READERS")) P.readers = atoi(e) > 0 ? atoi(e) : P.readers;
             const std::string perr = P.run(R.mlf);
+            phase("list processed, outputs written");
             for (size_t d = 1; d < P.ctxs.size(); ++d) phn_destroy(P.ctxs[d]);
+            phase("further contexts destroyed");
             if (!perr.empty()) { if (R.mlf) fflush(R.mlf); die("%s", perr.c_str()); }
             if (!err.empty()) { if (R.mlf) fflush(R.mlf); die("%s", err.c_str()); }
         } else {
@@ -687,7 +705,9 @@ int main(int argc, char *argv[])
         fclose(fl);
     }
 
+    for (auto &t : more_threads) t.join();   // (contexts nobody used: -i only)
     if (live) die("Live audio input (-a) is outside the GPU hot path of this build\n");
     phn_destroy(R.ctx);
+    phase("done");
     return 0;
 }

@@ -38,10 +38,11 @@ for tag, env in [("1gpu", {"PHNREC_DEVICES": "0"})] + ([("all", {"PHNREC_DEVICES
         mlf = base / f"out_{tag}.mlf"
         t0 = time.perf_counter()
         r = subprocess.run([str(ROOT / "phnrec_b200/bin/phnrec"), "-c", str(model), "-l", str(lst), "-m", str(mlf), "-w", "alaw"],
-                           env={**os.environ, "PHNREC_MLP": "tc", **env}, capture_output=True, text=True)
+                           env={**os.environ, "PHNREC_MLP": "tc", "PHNREC_CLI_TIMING": "1", **env}, capture_output=True, text=True)
         dt = time.perf_counter() - t0
         assert r.returncode == 0, r.stderr
     outs[tag] = mlf.read_bytes()
+    sys.stderr.write(f"--- {tag}\n{r.stderr}")
     print(json.dumps({"cli": "phnrec -l list -m out.mlf (PHNREC_MLP=tc)", "devices": env["PHNREC_DEVICES"], "n_gpus_visible": ndev, "files": n,
                       "audio_s": n * 10.0, "wall_s": round(dt, 3), "xRT": round(n * 10.0 / dt, 1),
                       "note": "whole process: CUDA context + model load, reading the files, recognition, writing the MLF"}))
