@@ -409,8 +409,11 @@ __device__ __noinline__ void stc_f2_one_frame(const float *s_mel, const float *c
     }
 }
 
+// Resident CTAs per SM the register budget is sized for: 3 (85 registers, a few spilled bytes) where three tiles' shared
+// memory fits (15 banks: 68 KB per CTA; measured 0.444 against 0.468 ms), 2 (124 registers) for the 23-bank system, whose
+// 91 KB per CTA allow two anyway (0.629 against 0.652 ms with the tighter budget).
 template <int NB>
-__global__ void __launch_bounds__(256, 2) k_stc_f2(StcF2Args a)
+__global__ void __launch_bounds__(256, NB <= 15 ? 3 : 2) k_stc_f2(StcF2Args a)
 {
     constexpr int NBP = (NB + 1) / 2;                 // band pairs (the last one is half empty when NB is odd)
     constexpr int NIN = NB * 11;
@@ -582,7 +585,7 @@ static int launch_stc_f2_t(phn_ctx *c, const StcF2Args &a)
     PHN_CUDA(c, cudaFuncSetAttribute(k_stc_f2<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // (grid = a few times the resident count: see launch_wave_pair_k)
     static const int oversub = getenv("PHNREC_FRONT_OVERSUB") ? atoi(getenv("PHNREC_FRONT_OVERSUB")) : 4;
-    const int gcap = 2 * c->num_sms * (oversub > 0 ? oversub : 1);
+    const int gcap = (NB <= 15 ? 3 : 2) * c->num_sms * (oversub > 0 ? oversub : 1);
     int grid = a.n_tiles < gcap ? a.n_tiles : gcap;
     k_stc_f2<NB><<<grid, 256, smem, c->stream>>>(a);
     PHN_CUDA(c, cudaGetLastError());
