@@ -565,6 +565,75 @@ void orc_posteriors_from_normed_mel(const float *mel, int T, int nb, const float
     free(XL); free(XR); free(pl); free(pr); free(mi);
 }
 
+/* The other TRAPS systems: posteriors/system = 1BT, 3BT, 1BT_DCT
+ * (traps.cpp:222-283 CalcInputFeaturesForBandNets, 344-361 ForwardPassBandNets, 405-433 CalcInputFeaturesForMerger).
+ * Every band's trajectory is the FIFO's content = frames clamp(r - S .. r + S, 0, T-1), S = (L-1)/2 (same FIFO and
+ * warm-up / tail driver as LCRC), times the Hamming window when posteriors/hamming is set (traps.cpp:232-241,
+ * sWindow_Hamming dspc.h:162-167 over a vector of ones).
+ *   1BT     one net per band on its L-point trajectory; merger input = -sLn(concatenated band outputs).
+ *   3BT     as executed by the reference: the same, over the first nb - 2 bands (the code copies ONE band's L values per
+ *           net, traps.cpp:249-261; nets with 3 L inputs would read uninitialised memory - refused here).
+ *   1BT_DCT no band nets: merger input = per band [C0, DCT_1 .. DCT_{shift-1}] (add_c0) or [DCT_1 .. DCT_shift],
+ *           shift = merger inputs / bands (traps.cpp:263-283, 170).
+ * system: 1 = 1BT, 2 = 1BT_DCT, 3 = 3BT.  mel must already be (sentence) normalised.  Returns 0, or -1 when the nets do
+ * not fit the system the way the reference needs them. */
+int orc_posteriors_trap_system(const float *mel, int T, int nb, int system, int L, int use_hamming, int add_c0,
+                               orc_nn *const *bands, const orc_nn *mg, float *post)
+{
+    const int S = (L - 1) / 2;
+    const int tb = system == 3 ? nb - 2 : nb;   /* trap_bands, traps.cpp:95-97 */
+    if (L < 3 || L > 255 || tb < 1) return -1;
+    float *ham = (float *)malloc(sizeof(float) * L);
+    for (int i = 0; i < L; ++i) ham[i] = 1.0f * (0.54f - 0.46f * cosf(2.0f * (float)M_PI * i / (L - 1)));
+    float *x = (float *)malloc(sizeof(float) * L);
+    float *mi = (float *)calloc((size_t)mg->nin + 4, sizeof(float));
+    int shift = 0, rc = 0;
+    if (system == 2) {
+        shift = mg->nin / tb;
+        if (shift * tb != mg->nin || shift < 1 || (add_c0 ? shift - 1 : shift) > L) rc = -1;
+    } else {
+        int tot = 0;
+        for (int i = 0; i < tb; ++i) { if (!bands[i] || bands[i]->nin != L) rc = -1; else tot += bands[i]->nout; }
+        if (tot != mg->nin) rc = -1;
+    }
+    const float NormC = sqrtf(2.0f / (float)L), PiByN = (float)M_PI / (float)L;
+    for (int r = 0; r < T && rc == 0; ++r) {
+        float *o = mi;
+        for (int b = 0; b < tb; ++b) {
+            for (int j = 0; j < L; ++j) {
+                int t = r - S + j;
+                if (t < 0) t = 0;
+                if (t > T - 1) t = T - 1;
+                x[j] = mel[(size_t)t * nb + b];
+                if (use_hamming) x[j] = x[j] * ham[j];
+            }
+            if (system == 2) {
+                int nd = add_c0 ? shift - 1 : shift;
+                if (add_c0) {   /* CalcC0, dspc.h:223-233 */
+                    float sum = 0.0f;
+                    for (int j = 0; j < L; ++j) sum += x[j];
+                    sum *= NormC;
+                    *o++ = sum;
+                }
+                for (int k = 0; k < nd; ++k) {   /* sDCT, dspc.h:206-221 */
+                    float acc = 0, v = PiByN * (float)(k + 1);
+                    for (int j = 0; j < L; ++j) acc += x[j] * cosf(v * ((float)j + 0.5f));
+                    acc *= NormC;
+                    *o++ = acc;
+                }
+            } else {
+                orc_nn_forward(bands[b], x, o, 1);
+                o += bands[b]->nout;
+            }
+        }
+        if (system != 2)   /* sLn, then times -1 (traps.cpp:425-427) */
+            for (int i = 0; i < mg->nin; ++i) mi[i] = (mi[i] > 0.0f ? logf(mi[i]) : 0.0f) * -1;
+        orc_nn_forward(mg, mi, post + (size_t)r * mg->nout, 1);
+    }
+    free(ham); free(x); free(mi);
+    return rc;
+}
+
 /* ------------------------------------------------------------------------- */
 /* P1: decoder soft function = glibc logf.  srec.h:192-195, srec.cpp:1088-97  */
 /* ------------------------------------------------------------------------- */
@@ -739,6 +808,8 @@ typedef struct {
     int z_mean;
     int on_interval, on_mean, on_var;   /* [onlinenorm] estim_interval, mean_norm, var_norm */
     int bunch;                          /* [posteriors] bunch_size */
+    int system, trap_len, hamming, add_c0;   /* [posteriors] system (0 LCRC, 1 1BT, 2 1BT_DCT, 3 3BT), length, hamming, add_c0 */
+    orc_nn *bands[32];                  /* 1BT / 3BT: one net per band */
     float win[32];
     orc_nn *b0, *b1, *mg;
     orc_mel *mel;
@@ -800,6 +871,11 @@ orc_model *orc_model_load(const char *dir)
     cfg_get(txt, "framenorm", "shift", buf, "0"); sscanf(buf, "%f", &m->frame_shift);
     cfg_get(txt, "framenorm", "min_floor", buf, "-9999.9"); sscanf(buf, "%f", &m->frame_floor);
     cfg_get(txt, "posteriors", "bunch_size", buf, "1"); m->bunch = atoi(buf) > 0 ? atoi(buf) : 1;
+    cfg_get(txt, "posteriors", "system", buf, "1BT_DCT");
+    m->system = !strcmp(buf, "LCRC") ? 0 : !strcmp(buf, "1BT") ? 1 : !strcmp(buf, "1BT_DCT") ? 2 : !strcmp(buf, "3BT") ? 3 : -1;
+    cfg_get(txt, "posteriors", "length", buf, "31"); m->trap_len = atoi(buf);
+    cfg_get(txt, "posteriors", "hamming", buf, "false"); m->hamming = strcmp(buf, "true") == 0;
+    cfg_get(txt, "posteriors", "add_c0", buf, "true"); m->add_c0 = strcmp(buf, "true") == 0;
     cfg_get(txt, "onlinenorm", "estim_interval", buf, "0"); m->on_interval = atoi(buf);          /* srec.cpp:56-61, 594-601 */
     cfg_get(txt, "onlinenorm", "mean_norm", buf, "false"); m->on_mean = strcmp(buf, "true") == 0;
     cfg_get(txt, "onlinenorm", "var_norm", buf, "false"); m->on_var = strcmp(buf, "true") == 0;
@@ -807,11 +883,21 @@ orc_model *orc_model_load(const char *dir)
     cfg_get(txt, "decoder", "time_pruning", buf, "40"); m->hist = atoi(buf);
     cfg_get(txt, "decoder", "num_states_per_phn", buf, "1"); m->S = atoi(buf);
     free(txt);
+    snprintf(path, sizeof path, "%s/weights/merger.nbin", dir); m->mg = orc_nn_load(path);
+    if (m->system != 0) {   /* the other TRAPS systems: one net per band (1BT, 3BT) or none (1BT_DCT); no windows */
+        const int tb = m->system == 3 ? m->nbanks - 2 : m->nbanks;
+        if (m->system < 0 || !m->mg || tb > 32) { free(m); return NULL; }
+        for (int i = 0; i < tb && m->system != 2; ++i) {
+            snprintf(path, sizeof path, "%s/weights/band%d.nbin", dir, i);
+            m->bands[i] = orc_nn_load(path);
+            if (!m->bands[i]) { free(m); return NULL; }
+        }
+    } else {
     snprintf(path, sizeof path, "%s/weights/band0.nbin", dir); m->b0 = orc_nn_load(path);
     snprintf(path, sizeof path, "%s/weights/band1.nbin", dir); m->b1 = orc_nn_load(path);
-    snprintf(path, sizeof path, "%s/weights/merger.nbin", dir); m->mg = orc_nn_load(path);
     if (!m->b0 || !m->b1 || !m->mg) { free(m); return NULL; }
-    for (int w = 0; w < 2; ++w) { /* traps.cpp:549-570 */
+    }
+    for (int w = 0; w < 2 && m->system == 0; ++w) { /* traps.cpp:549-570 */
         snprintf(path, sizeof path, "%s/windows/band%d.window", dir, w);
         f = fopen(path, "r");
         if (!f) { free(m); return NULL; }
@@ -837,7 +923,9 @@ orc_model *orc_model_load(const char *dir)
 void orc_model_destroy(orc_model *m)
 {
     if (!m) return;
-    orc_nn_destroy(m->b0); orc_nn_destroy(m->b1); orc_nn_destroy(m->mg); orc_mel_destroy(m->mel); free(m);
+    orc_nn_destroy(m->b0); orc_nn_destroy(m->b1); orc_nn_destroy(m->mg); orc_mel_destroy(m->mel);
+    for (int i = 0; i < 32; ++i) orc_nn_destroy(m->bands[i]);
+    free(m);
 }
 
 /* info: fs, nbanks, vs, step, fmt, sent_mean_norm, hist, S, P, nout, nin_band, nhid */
@@ -845,7 +933,7 @@ void orc_model_info(const orc_model *m, int *info, float *wpenalty)
 {
     info[0] = m->fs; info[1] = m->nbanks; info[2] = m->vs; info[3] = m->step; info[4] = m->fmt;
     info[5] = m->sent_mean_norm; info[6] = m->hist; info[7] = m->S; info[8] = m->P;
-    info[9] = m->mg->nout; info[10] = m->b0->nin; info[11] = m->b0->nhid;
+    info[9] = m->mg->nout; info[10] = m->b0 ? m->b0->nin : (m->bands[0] ? m->bands[0]->nin : 0); info[11] = m->b0 ? m->b0->nhid : (m->bands[0] ? m->bands[0]->nhid : 0);
     *wpenalty = m->wpenalty;
 }
 const char *orc_model_phoneme(const orc_model *m, int i) { return m->phn[i]; }
@@ -880,7 +968,8 @@ void orc_model_posteriors(orc_model *m, const float *mel, int T, float *post)
     float *mm = (float *)malloc(sizeof(float) * (size_t)T * m->nbanks);
     memcpy(mm, mel, sizeof(float) * (size_t)T * m->nbanks);
     if (m->sent_mean_norm) orc_sentence_mean_norm(mm, T, m->nbanks);
-    orc_posteriors_from_normed_mel(mm, T, m->nbanks, m->win, m->b0, m->b1, m->mg, post);
+    if (m->system == 0) orc_posteriors_from_normed_mel(mm, T, m->nbanks, m->win, m->b0, m->b1, m->mg, post);
+    else orc_posteriors_trap_system(mm, T, m->nbanks, m->system, m->trap_len, m->hamming, m->add_c0, m->bands, m->mg, post);
     free(mm);
 }
 
@@ -933,7 +1022,8 @@ int orc_model_recognize_online(orc_model *m, const void *audio, int nbytes, int 
     orc_model_mel_from_audio(m, audio, nbytes, fmt, mel + (size_t)P * m->nbanks);
     orc_online_norm(mel + (size_t)P * m->nbanks, T, m->nbanks, interval, mean_norm, var_norm);
     for (int p = 0; p < P; ++p) memcpy(mel + (size_t)p * m->nbanks, mel + (size_t)P * m->nbanks, sizeof(float) * m->nbanks);
-    orc_posteriors_from_normed_mel(mel, T + P, m->nbanks, m->win, m->b0, m->b1, m->mg, post);
+    if (m->system == 0) orc_posteriors_from_normed_mel(mel, T + P, m->nbanks, m->win, m->b0, m->b1, m->mg, post);
+    else orc_posteriors_trap_system(mel, T + P, m->nbanks, m->system, m->trap_len, m->hamming, m->add_c0, m->bands, m->mg, post);
     const int k = orc_model_decode(m, post, T + P, wp, out, cap);
     free(mel);
     free(post);

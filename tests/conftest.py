@@ -118,3 +118,117 @@ def front_end_variants():
     meta = json.loads(str(z["meta"]))
     for i, m in enumerate(meta):
         yield m["name"], m["model"], m["audio"], m["nbytes"], m["edits"], z[f"mel{i}"], str(z[f"rec{i}"])
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Synthetic model directories for the TRAPS systems no shipped model uses (posteriors/system = 1BT, 3BT, 1BT_DCT; SURVEY
+# section 8(f) rank 4): random nets written as the reference's .nbin cache files (nn.cpp:464-531), a config, a phoneme list.
+# Deterministic in `seed`, so the generator of the fixtures (tests/golden/make_golden.py) and the tests build the same files.
+def write_nbin(path, rng, nin, nhid, nout, w_scale=1.0):
+    a4 = lambda n: (n + 3) // 4 * 4
+    nin4, nhid4, nout4 = a4(nin), a4(nhid), a4(nout)
+    w1 = np.zeros((nhid4, nin4), dtype=np.float32)
+    w2 = np.zeros((nout4, nhid4), dtype=np.float32)
+    b1, b2 = np.zeros(nhid4, dtype=np.float32), np.zeros(nout4, dtype=np.float32)
+    mean, dev = np.zeros(nin4, dtype=np.float32), np.ones(nin4, dtype=np.float32)
+    w1[:nhid, :nin] = (rng.standard_normal((nhid, nin)) * w_scale / np.sqrt(nin)).astype(np.float32)
+    w2[:nout, :nhid] = (rng.standard_normal((nout, nhid)) * 2.0 / np.sqrt(nhid)).astype(np.float32)
+    b1[:nhid] = (rng.standard_normal(nhid) * 0.3).astype(np.float32)
+    b2[:nout] = (rng.standard_normal(nout) * 0.3).astype(np.float32)
+    mean[:nin] = (rng.standard_normal(nin) * 0.5 + 1.0).astype(np.float32)
+    dev[:nin] = (1.0 / (0.5 + rng.random(nin))).astype(np.float32)
+    with open(path, "wb") as f:
+        np.array([2, nin, nhid, nout], dtype=np.int32).tofile(f)
+        for a in (w1, w2, b1, b2, mean, dev):
+            a.tofile(f)
+
+
+def synthetic_trap_model(dst, system: str, seed: int, nb: int = 15, length: int = 31, hamming: bool = False, add_c0: bool = True,
+                         band_hid: int = 24, band_out: int = 9, merger_hid: int = 40, n_phn: int = 7, shift: int = 6, fs: int = 8000,
+                         sent_mean_norm: bool = True) -> Path:
+    """A model directory for posteriors/system `system` with random nets; returns its path."""
+    dst = Path(dst)
+    (dst / "weights").mkdir(parents=True, exist_ok=True)
+    (dst / "dicts").mkdir(exist_ok=True)
+    rng = np.random.default_rng(seed)
+    nout = 3 * n_phn + 3                       # 3 states per phoneme + the omitted last model, like the shipped systems
+    if system == "1BT_DCT":
+        merger_in = nb * shift
+    else:
+        tb = nb - 2 if system == "3BT" else nb
+        for i in range(tb):
+            write_nbin(dst / "weights" / f"band{i}.nbin", rng, length, band_hid, band_out, w_scale=2.5)
+        merger_in = tb * band_out
+    write_nbin(dst / "weights" / "merger.nbin", rng, merger_in, merger_hid, nout, w_scale=3.0)
+    (dst / "dicts" / "phonemes").write_text("".join(f"p{i}\n" for i in range(n_phn)))
+    vs, step = (200, 80) if fs == 8000 else (400, 160)
+    b = lambda v: "true" if v else "false"
+    (dst / "config").write_text(f"""[source]
+format=lin16
+sample_freq={fs}
+
+[posteriors]
+system={system}
+length={length}
+add_c0={b(add_c0)}
+hamming={b(hamming)}
+suffix=lop
+bunch_size=5
+softening_func=none 0 0 0
+
+[params]
+kind=fbanks
+suffix=mel
+
+[melbanks]
+nbanks={nb}
+lower_freq=64
+higher_freq={fs // 2}
+vector_size={vs}
+vector_step={step}
+preem_coef=0.0
+
+[decoder]
+type=phndec
+num_states_per_phn=3
+softening_func=log 0 0 0
+wpenalty=-1.5
+lm_scale=1
+time_pruning=40
+mode=decode
+
+[offlinenorm]
+sent_mean_norm={b(sent_mean_norm)}
+sent_var_norm=false
+
+[dirs]
+tmp=$C/tmp
+
+[models]
+hmm_defs=$T/models
+nstates=3
+gen_from_phn_list=true
+
+[dicts]
+phoneme_list=$C/dicts/phonemes
+
+[networks]
+default=$C/net/network
+omit_phn=oth
+
+[labels]
+suffix=rec
+remove_path=true
+""")
+    return dst
+
+
+TRAP_CASES = [  # (name, system, seed, options)
+    ("1bt", "1BT", 11, {}),
+    ("1bt_hamming", "1BT", 12, {"hamming": True}),
+    ("1bt_len21_en", "1BT", 13, {"length": 21, "nb": 23, "fs": 16000, "sent_mean_norm": False}),
+    ("1bt_dct", "1BT_DCT", 14, {}),
+    ("1bt_dct_noc0_hamming", "1BT_DCT", 15, {"add_c0": False, "hamming": True, "shift": 5}),
+    ("1bt_dct_len51", "1BT_DCT", 16, {"length": 51, "shift": 12}),
+    ("3bt", "3BT", 17, {}),
+]

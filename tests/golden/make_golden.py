@@ -24,6 +24,8 @@ Outputs
                     SpeechRec::ProcessOnline / ProcessTail (srec.cpp:793-927) - several block sizes, penalties and
                     [onlinenorm] settings (on edited copies of model directories); the .rec text of each run.
                     (`python tests/golden/make_golden.py online` regenerates only this one.)
+  ref_trap_systems.npz  oracle/_ref/phnrec_ref on synthetic model directories of the other TRAPS systems (1BT, 3BT, 1BT_DCT):
+                    posteriors and .rec text (`python tests/golden/make_golden.py trap`).
 Nothing in tests/ reads /root/reference at run time; only these files.
 """
 import json
@@ -96,10 +98,35 @@ def online_stream():
     (OUT / "ref_online_stream.json").write_text(json.dumps(out, indent=1))
 
 
+def trap_systems():
+    """ref_trap_systems.npz: oracle/_ref/phnrec_ref on SYNTHETIC model directories (tests/conftest.py: synthetic_trap_model)
+    for the TRAPS systems no shipped model uses - 1BT, 3BT, 1BT_DCT (traps.cpp:249-283, 413-433): `-t post` + .rec."""
+    sys.path.insert(0, str(ROOT / "tests"))
+    from conftest import synthetic_trap_model, TRAP_CASES  # noqa: E402
+    out = {}
+    with tempfile.TemporaryDirectory() as td:
+        td = Path(td)
+        for name, system, seed, opt in TRAP_CASES:
+            cfg = synthetic_trap_model(td / name, system, seed, **opt)
+            nbytes = 60000 if opt.get("fs", 8000) == 8000 else 100000
+            (td / "a.raw").write_bytes((orc.REF_AUDIO / "test.raw").read_bytes()[:nbytes])
+            orc.run_ref(["-c", cfg, "-t", "post", "-i", td / "a.raw", "-o", td / "o.post"])
+            orc.run_ref(["-c", cfg, "-i", td / "a.raw", "-o", td / "o.rec"])
+            out[f"post_{name}"] = orc.read_htk(td / "o.post")
+            out[f"rec_{name}"] = np.array((td / "o.rec").read_text())
+            out[f"nbytes_{name}"] = np.array(nbytes)
+            print("trap", name, out[f"post_{name}"].shape, len(str(out[f"rec_{name}"]).splitlines()), "labels")
+    np.savez_compressed(OUT / "ref_trap_systems.npz", **out)
+
+
 def main():
     if len(sys.argv) > 1 and sys.argv[1] == "online":
         online_stream()
         return
+    if len(sys.argv) > 1 and sys.argv[1] == "trap":
+        trap_systems()
+        return
+    trap_systems()
     online_stream()
     labels = {}
     for g, model, audio, mlf in GOLDENS:

@@ -193,3 +193,21 @@ def test_online_path_restatement_equals_reference_objects(orc, tmp_path):
         m.close()
         n += 1
     assert n >= 14
+
+
+def test_other_trap_systems_restatement_equals_reference_binary(orc, tmp_path):
+    """SURVEY section 8(f) rank 4 pinned: posteriors/system = 1BT, 3BT (as the reference executes it), 1BT_DCT - with and without
+    the Hamming window / C0, trap lengths 21, 31, 51, 15 and 23 banks - on synthetic model directories (random nets,
+    tests/conftest.py:synthetic_trap_model): the restatement's posteriors and labels are the reference binary's, bit for bit
+    (tests/golden/ref_trap_systems.npz, written by oracle/_ref/phnrec_ref)."""
+    from conftest import GOLDEN, TRAP_CASES, audio_bytes, synthetic_trap_model
+    z = np.load(GOLDEN / "ref_trap_systems.npz")
+    for name, system, seed, opt in TRAP_CASES:
+        m = orc.Model(synthetic_trap_model(tmp_path / name, system, seed, **opt))
+        a = audio_bytes("test.raw")[:int(z[f"nbytes_{name}"])]
+        post = m.posteriors(m.mel(a))
+        want = z[f"post_{name}"]
+        assert post.shape == want.shape, name
+        assert np.array_equal(post.view(np.uint32), want.view(np.uint32)), name
+        assert orc.format_rec(m.recognize(a), m.phonemes) == str(z[f"rec_{name}"]), name
+        m.close()
