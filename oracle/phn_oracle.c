@@ -1009,13 +1009,15 @@ int orc_model_recognize_online(orc_model *m, const void *audio, int nbytes, int 
     const int n = fmt == 0 ? nbytes / 2 : nbytes;
     if (n < m->vs) return 0;
     const int T = (n - m->vs) / m->step + 1;
-    /* first row handed to the decoder: the first bunch whose last vector is the 16th or later starts at vector a0 */
+    /* first row handed to the decoder: the first bunch whose last vector is number shift + 1 or later starts at vector a0
+     * (shift = Traps::GetTrapShift = (length - 1) / 2 = 15 for the 31-frame systems) */
+    const int shift = (m->trap_len - 1) / 2;
     int a0 = -1;
     for (int a = 1; a <= T; a += m->bunch) {
         const int b = a + m->bunch - 1 < T ? a + m->bunch - 1 : T;
-        if (b >= 16) { a0 = a; break; }
+        if (b >= shift + 1) { a0 = a; break; }
     }
-    const int r_first = a0 > 0 ? a0 - 16 : T - 15;
+    const int r_first = a0 > 0 ? a0 - (shift + 1) : T - shift;
     const int P = r_first < 0 ? -r_first : 0;
     float *mel = (float *)malloc(sizeof(float) * (size_t)(T + P) * m->nbanks);
     float *post = (float *)malloc(sizeof(float) * (size_t)(T + P) * m->mg->nout);

@@ -118,16 +118,12 @@ static int upload(phn_ctx *c, T **dst, const T *src, size_t n)
 
 static int up16(int n) { return (n + 15) / 16 * 16; }
 
-static int upload_net(phn_ctx *c, int which)
+static int upload_one_net(phn_ctx *c, const HostNet &h, DevNet &d, int kin)
 {
-    const HostNet &h = c->hnet[which];
-    DevNet &d = c->net[which];
     d.nin = h.nin; d.nhid = h.nhid; d.nout = h.nout; d.nin4 = h.nin4; d.nhid4 = h.nhid4; d.nout4 = h.nout4;
     d.kp = up16(h.nin4);
     d.ldh = up16(h.nhid4);
     d.w1h = nullptr; d.w2h = nullptr; d.nhidP = 0; d.noutP = 0;
-    // fp16 image width: the merger's image keeps its two halves 8-column aligned (k_mlp_tc.cu)
-    const int kin = which == 2 ? (c->hnet[0].nout + 7) / 8 * 8 + c->hnet[0].nout : h.nin;
     d.kin = kin;
     d.k1P = (kin + 2 + 63) / 64 * 64;   // + the two bias columns (k_mlp_tc.cu)
     int rc;
@@ -138,6 +134,14 @@ static int upload_net(phn_ctx *c, int which)
     if ((rc = upload(c, &d.mean, h.mean.data(), h.mean.size()))) return rc;
     if ((rc = upload(c, &d.dev, h.dev.data(), h.dev.size()))) return rc;
     return PHN_OK;
+}
+
+static int upload_net(phn_ctx *c, int which)
+{
+    const HostNet &h = c->hnet[which];
+    // fp16 image width: the merger's image keeps its two halves 8-column aligned (k_mlp_tc.cu)
+    const int kin = which == 2 && c->system == PHN_SYS_LCRC ? (c->hnet[0].nout + 7) / 8 * 8 + c->hnet[0].nout : h.nin;
+    return upload_one_net(c, h, c->net[which], kin);
 }
 
 // frames of one utterance (srec.cpp:945)
@@ -240,6 +244,15 @@ static int prepare_posteriors(phn_ctx *c)
     if (ch > F) ch = (F + 127) / 128 * 128;
     c->chunk_frames = ch;
     if (ch == 0) return PHN_OK;
+    if (c->system != PHN_SYS_LCRC) {   // the other TRAPS systems: exact mode only
+        if (tc) return fail(c, PHN_ERR_UNSUPPORTED, "the tensor-core mode implements the LCRC system only\n");
+        int ldh = c->net[2].ldh;
+        for (auto &d : c->dband) ldh = d.ldh > ldh ? d.ldh : ldh;
+        if ((rc = ensure(c, c->d_xm, sizeof(float) * ch * c->net[2].kp))) return rc;
+        if ((rc = ensure(c, c->d_h, sizeof(float) * ch * ldh))) return rc;
+        if (!c->dband.empty() && (rc = ensure(c, c->d_xb, sizeof(float) * ch * c->dband[0].kp * c->dband.size()))) return rc;
+        return PHN_OK;
+    }
     if (tc) {
         if ((rc = mlp_tc_prepare(c))) return rc;
         if (c->fuse_logp && (rc = ensure(c, c->d_logp, sizeof(float) * (size_t)((F + 127) / 128 * 128 + 128) * c->ldp))) return rc;
@@ -277,6 +290,11 @@ static int run_posteriors(phn_ctx *c, bool front_done = false)
     }
     for (int64_t f0 = 0; f0 < F; f0 += ch) {
         const int64_t nf = F - f0 < ch ? F - f0 : ch;
+        if (c->system != PHN_SYS_LCRC) {
+            { StageTimer t(c, PHN_K_STC); if ((rc = launch_trap(c, f0, nf))) return rc; }
+            { StageTimer t(c, PHN_K_MLP); if ((rc = launch_mlp_trap(c, f0, nf))) return rc; }
+            continue;
+        }
         if (!front_done) { StageTimer t(c, PHN_K_STC); if ((rc = launch_stc(c, f0, nf))) return rc; }
         { StageTimer t(c, PHN_K_MLP); if ((rc = tc ? launch_mlp_tc(c, f0, nf) : launch_mlp_exact(c, f0, nf))) return rc; }
     }
@@ -437,10 +455,23 @@ int phn_create(const char *cfg_dir, int device, phn_ctx **out)
     const Config &C = c->cfg;
     // ---- what this hot path implements: fbanks -> LCRC -> phndec, offline
     if (C.str("params", "kind") != "fbanks") return bail(fail(c, PHN_ERR_UNSUPPORTED, "Unsupported parameter kind: %s\n", C.str("params", "kind").c_str()));
-    if (C.str("posteriors", "system") != "LCRC") return bail(fail(c, PHN_ERR_UNSUPPORTED, "Unsupported posterior estimator: %s (only LCRC)\n", C.str("posteriors", "system").c_str()));
+    {   // Traps::SetSystem (traps.cpp:572-585)
+        const std::string &sy = C.str("posteriors", "system");
+        if (sy == "LCRC") c->system = PHN_SYS_LCRC;
+        else if (sy == "1BT") c->system = PHN_SYS_1BT;
+        else if (sy == "1BT_DCT") c->system = PHN_SYS_1BT_DCT;
+        else if (sy == "3BT") c->system = PHN_SYS_3BT;
+        else return bail(fail(c, PHN_ERR_UNSUPPORTED, "Unknown system, check configuration: %s\n", sy.c_str()));
+    }
     if (C.str("decoder", "type") != "phndec") return bail(fail(c, PHN_ERR_UNSUPPORTED, "Unsupported decoder type: %s (only phndec)\n", C.str("decoder", "type").c_str()));
-    if (C.i("posteriors", "length") != 31 || !C.b("posteriors", "add_c0") || C.b("posteriors", "hamming"))
+    c->trap_len = C.i("posteriors", "length");
+    c->tshift = (c->trap_len - 1) / 2;          // Traps::GetTrapShift, traps.h:67
+    c->use_hamming = C.b("posteriors", "hamming");
+    c->add_c0 = C.b("posteriors", "add_c0");
+    if (c->system == PHN_SYS_LCRC && (c->trap_len != 31 || !c->add_c0 || c->use_hamming))
         return bail(fail(c, PHN_ERR_UNSUPPORTED, "Unsupported LCRC set-up (needs length=31, add_c0=true, hamming=false)\n"));
+    if (c->trap_len < 3 || c->trap_len > 255 || !(c->trap_len & 1))
+        return bail(fail(c, PHN_ERR_UNSUPPORTED, "posteriors/length must be odd and in 3..255\n"));
     if (C.str("posteriors", "softening_func").rfind("none", 0) != 0 || C.str("decoder", "softening_func").rfind("log", 0) != 0)
         return bail(fail(c, PHN_ERR_UNSUPPORTED, "Unsupported softening functions (needs posteriors none, decoder log)\n"));
     if (C.b("offlinenorm", "sent_var_norm") || C.b("offlinenorm", "sent_max_norm") || C.b("offlinenorm", "sent_chmax_norm"))
@@ -474,18 +505,22 @@ int phn_create(const char *cfg_dir, int device, phn_ctx **out)
     if (c->nbanks < 1 || c->nbanks > 32 || c->vs < 2 || c->vs > 4096 || c->step < 1 || c->hist < 1)
         return bail(fail(c, PHN_ERR_CFG_BADVAL, "Front-end sizes out of range in '%s'\n", cfg_file.c_str()));
     // ---- nets (traps.cpp:139-166: .nbin tried first; it is the only weight source we read)
-    const char *names[3] = {"band0", "band1", "merger"};
-    for (int i = 0; i < 3; ++i) {
+    auto load_net = [&](HostNet &hn, const std::string &name) -> int {
         // NeuralNet::Load (nn.cpp:594-621): the binary cache first, else the ASCII pair, then the cache is written
-        const std::string p = c->cfg_dir + "/weights/" + names[i] + ".nbin";
-        rc = c->hnet[i].load(p);
-        if (rc != PHN_OK) {
-            const std::string w = c->cfg_dir + "/weights/" + names[i] + ".weights", nr = c->cfg_dir + "/norms/" + names[i] + ".norms";
-            rc = c->hnet[i].load_ascii(w, nr);
-            if (rc == PHN_OK) c->hnet[i].save_nbin(p);   // (failure to write the cache is ignored, as in the reference)
+        const std::string p = c->cfg_dir + "/weights/" + name + ".nbin";
+        int r = hn.load(p);
+        if (r != PHN_OK) {
+            const std::string w = c->cfg_dir + "/weights/" + name + ".weights", nr = c->cfg_dir + "/norms/" + name + ".norms";
+            r = hn.load_ascii(w, nr);
+            if (r == PHN_OK) hn.save_nbin(p);   // (failure to write the cache is ignored, as in the reference)
         }
-        if (rc != PHN_OK) return bail(fail(c, rc, "Can not load neural network: %s\n", p.c_str()));
-    }
+        if (r != PHN_OK) return fail(c, r, "Can not load neural network: %s\n", p.c_str());
+        return PHN_OK;
+    };
+    if (c->system == PHN_SYS_LCRC) {
+    const char *names[3] = {"band0", "band1", "merger"};
+    for (int i = 0; i < 3; ++i)
+        if ((rc = load_net(c->hnet[i], names[i]))) return bail(rc);
     if (c->hnet[0].nin % c->nbanks || c->hnet[0].nin != c->hnet[1].nin || c->hnet[0].nout != c->hnet[1].nout ||
         c->hnet[2].nin != 2 * c->hnet[0].nout)
         return bail(fail(c, PHN_ERR_NN_FORMAT, "Inconsistent network sizes in %s/weights\n", cfg_dir));
@@ -499,6 +534,31 @@ int phn_create(const char *cfg_dir, int device, phn_ctx **out)
         for (int i = 0; i < 16; ++i)
             if (fscanf(f, "%f", &c->win[w * 16 + i]) != 1) { fclose(f); return bail(fail(c, PHN_ERR_DEC_INPUT, "Invalid window file: %s\n", p.c_str())); }
         fclose(f);
+    }
+    } else {
+        // the other TRAPS systems (traps.cpp:86-171): one net per band (1BT; 3BT: the first nbanks - 2 bands) or none (1BT_DCT), no windows
+        c->trap_bands = c->system == PHN_SYS_3BT ? c->nbanks - 2 : c->nbanks;
+        if (c->trap_bands < 1) return bail(fail(c, PHN_ERR_CFG_BADVAL, "too few mel banks for system 3BT\n"));
+        if ((rc = load_net(c->hnet[2], "merger"))) return bail(rc);
+        c->ldp = (c->hnet[2].nout + 3) / 4 * 4;
+        if (c->system == PHN_SYS_1BT_DCT) {
+            c->trap_shift_out = c->hnet[2].nin / c->trap_bands;   // merger_input_shift, traps.cpp:170
+            const int nd = c->add_c0 ? c->trap_shift_out - 1 : c->trap_shift_out;
+            if (c->trap_shift_out * c->trap_bands != c->hnet[2].nin || nd < (c->add_c0 ? 0 : 1))
+                return bail(fail(c, PHN_ERR_NN_FORMAT, "merger inputs (%d) are not a whole number of coefficients per band (%d bands)\n", c->hnet[2].nin, c->trap_bands));
+        } else {
+            c->hband.resize((size_t)c->trap_bands);
+            int tot = 0;
+            for (int i = 0; i < c->trap_bands; ++i) {
+                if ((rc = load_net(c->hband[i], "band" + std::to_string(i)))) return bail(rc);
+                // (the reference copies ONE band's `length` values per net, traps.cpp:249-261: a net with any other input size
+                // would read uninitialised memory there)
+                if (c->hband[i].nin != c->trap_len)
+                    return bail(fail(c, PHN_ERR_NN_FORMAT, "band net %d takes %d inputs; the trajectory has %d points\n", i, c->hband[i].nin, c->trap_len));
+                tot += c->hband[i].nout;
+            }
+            if (tot != c->hnet[2].nin) return bail(fail(c, PHN_ERR_NN_FORMAT, "Inconsistent network sizes in %s/weights\n", cfg_dir));
+        }
     }
     {   // phoneme list (phndec.cpp:305-350); $C substitution as srec.cpp:219-233
         const std::string p = C.str("dicts", "phoneme_list");
@@ -543,8 +603,11 @@ int phn_create(const char *cfg_dir, int device, phn_ctx **out)
     if ((rc = cu(cudaEventCreateWithFlags(&c->ev_audio_free, cudaEventDisableTiming), "cudaEventCreate"))) return bail(rc);
     for (int i = 0; i < 2 * PHN_K_COUNT; ++i)
         if ((rc = cu(cudaEventCreate(&c->ev[i]), "cudaEventCreate"))) return bail(rc);
-    for (int i = 0; i < 3; ++i)
+    for (int i = c->system == PHN_SYS_LCRC ? 0 : 2; i < 3; ++i)
         if ((rc = upload_net(c, i))) return bail(rc);
+    c->dband.resize(c->hband.size());
+    for (size_t i = 0; i < c->hband.size(); ++i)
+        if ((rc = upload_one_net(c, c->hband[i], c->dband[i], c->hband[i].nin))) return bail(rc);
     const MelTables &mt = c->mt;
     std::vector<double2> tw((size_t)mt.N);
     for (int i = 0; i < mt.N - 1; ++i) tw[i] = make_double2(mt.tw[2 * i], mt.tw[2 * i + 1]);
@@ -577,7 +640,7 @@ void phn_destroy(phn_ctx *c)
         if (c->vit_stream) cudaStreamSynchronize(c->vit_stream);
         tl_dump(c);
     }
-    phn_ctx::Buf *bufs[] = {&c->d_st_hist, &c->d_st_norm, &c->d_st_cnt, &c->d_st_vit, &c->d_st_args, &c->d_win, &c->d_st_labels, &c->d_st_nlab, &c->d_audio, &c->d_byte_off, &c->d_frame_off, &c->d_lab_off, &c->d_mel, &c->d_mean, &c->d_post,
+    phn_ctx::Buf *bufs[] = {&c->d_xb, &c->d_st_hist, &c->d_st_norm, &c->d_st_cnt, &c->d_st_vit, &c->d_st_args, &c->d_win, &c->d_st_labels, &c->d_st_nlab, &c->d_audio, &c->d_byte_off, &c->d_frame_off, &c->d_lab_off, &c->d_mel, &c->d_mean, &c->d_post,
                             &c->d_rec, &c->d_pen, &c->d_x0, &c->d_x1, &c->d_h, &c->d_xm,
                             &c->d_x0h, &c->d_x1h, &c->d_xmh, &c->d_tile_ctr, &c->d_logp, &c->d_pair_off,
                             &c->slot[0].d_labels, &c->slot[0].d_nlab, &c->slot[0].d_lab_off, &c->slot[0].d_frame_off, &c->slot[0].d_coff, &c->slot[0].d_labels_c,
@@ -590,6 +653,14 @@ void phn_destroy(phn_ctx *c)
     if (c->stc_bias) cudaFree(c->stc_bias);
     if (c->stc_cf) cudaFree(c->stc_cf);
     if (c->stc_sb) cudaFree(c->stc_sb);
+    for (auto &d : c->dband) {
+        void *ps[] = {d.w1, d.w2, d.b1, d.b2, d.mean, d.dev};
+        for (void *q : ps) if (q) cudaFree(q);
+    }
+    if (c->d_trap_ham) cudaFree(c->d_trap_ham);
+    if (c->d_trap_cos) cudaFree(c->d_trap_cos);
+    if (c->d_trap_pm) cudaFree(c->d_trap_pm);
+    if (c->d_trap_pd) cudaFree(c->d_trap_pd);
     for (int i = 0; i < 3; ++i) {
         DevNet &d = c->net[i];
         void *ps[] = {d.w1, d.w2, d.b1, d.b2, d.mean, d.dev, d.w1h, d.w2h};
@@ -620,8 +691,8 @@ int phn_get_info(const phn_ctx *c, phn_info *o)
     if (!c || !o) return PHN_ERR_ARG;
     o->sample_freq = c->fs; o->wave_format = c->fmt; o->nbanks = c->nbanks; o->vector_size = c->vs;
     o->vector_step = c->step; o->fft_size = c->mt.N; o->n_phonemes = c->P; o->n_states = c->S;
-    o->n_outputs = c->hnet[2].nout; o->band_inputs = c->hnet[0].nin; o->merger_inputs = c->hnet[2].nin;
-    o->hidden = c->hnet[0].nhid; o->sent_mean_norm = c->sent_mean_norm; o->time_pruning = c->hist;
+    o->n_outputs = c->hnet[2].nout; o->band_inputs = c->system == PHN_SYS_LCRC ? c->hnet[0].nin : (c->hband.empty() ? 0 : c->hband[0].nin); o->merger_inputs = c->hnet[2].nin;
+    o->hidden = c->system == PHN_SYS_LCRC ? c->hnet[0].nhid : c->hnet[2].nhid; o->sent_mean_norm = c->sent_mean_norm; o->time_pruning = c->hist;
     o->mlp_mode = c->mlp_mode; o->device = c->device; o->wpenalty = c->wpenalty;
     return PHN_OK;
 }
@@ -652,6 +723,7 @@ int phn_set_mlp_mode(phn_ctx *c, int mode)
 {
     if (!c) return PHN_ERR_ARG;
     if (mode != PHN_MLP_EXACT_FP32 && mode != PHN_MLP_TC_F16) return fail(c, PHN_ERR_ARG, "Unknown MLP mode\n");
+    if (mode == PHN_MLP_TC_F16 && c->system != PHN_SYS_LCRC) return fail(c, PHN_ERR_UNSUPPORTED, "the tensor-core mode implements the LCRC system only\n");
     c->mlp_mode = mode;
     return PHN_OK;
 }
@@ -1040,16 +1112,16 @@ int phn_stream_open(phn_ctx *c, int n_streams)
 {
     if (!c || n_streams < 0) return PHN_ERR_ARG;
     PHN_CUDA(c, cudaSetDevice(c->device));
-    if (c->bunch < 1 || 15 % c->bunch != 0)
-        return fail(c, PHN_ERR_UNSUPPORTED, "streaming needs a posteriors/bunch_size that divides the trap shift 15 (1, 3, 5, 15); it is %d: the reference's online path "
-                                            "then hands warm-up rows to the decoder depending on where bunches fall\n", c->bunch);
+    if (c->bunch < 1 || c->tshift % c->bunch != 0)
+        return fail(c, PHN_ERR_UNSUPPORTED, "streaming needs a posteriors/bunch_size that divides the trap shift %d; it is %d: the reference's online path "
+                                            "then hands warm-up rows to the decoder depending on where bunches fall\n", c->tshift, c->bunch);
     if (c->hist + 1 > 64) return fail(c, PHN_ERR_UNSUPPORTED, "streaming keeps a 64-slot decoder history; decoder/time_pruning is %d\n", c->hist);
     if (c->on_var && !c->on_mean) return fail(c, PHN_ERR_ARG, "online normalisation: var_norm without mean_norm (the reference asserts, norm.cpp:152)\n");
     if (c->cfg.str("onlinenorm", "file") != "none") return fail(c, PHN_ERR_UNSUPPORTED, "onlinenorm/file (XML persistence of the estimates) is not supported\n");
     if (c->cfg.b("onlinenorm", "scale_to_gvar")) return fail(c, PHN_ERR_UNSUPPORTED, "onlinenorm/scale_to_gvar is not supported\n");
     int rc;
     const size_t n = (size_t)n_streams;
-    if ((rc = ensure(c, c->d_st_hist, sizeof(float) * n * 30 * c->nbanks))) return rc;
+    if ((rc = ensure(c, c->d_st_hist, sizeof(float) * n * 2 * c->tshift * c->nbanks))) return rc;
     if ((rc = ensure(c, c->d_st_norm, sizeof(float) * n * 4 * c->nbanks))) return rc;
     if ((rc = ensure(c, c->d_st_cnt, sizeof(unsigned) * n))) return rc;
     if ((rc = ensure(c, c->d_st_vit, sizeof(VitStreamState) * n))) return rc;
@@ -1103,6 +1175,7 @@ int phn_stream_push(phn_ctx *c, const int *sids, int n, const void *audio, const
     std::vector<int64_t> boff((size_t)n + 1, 0), noff((size_t)n + 1, 0), woff((size_t)n + 1, 0), row0((size_t)n), loff((size_t)n + 1, 0);
     std::vector<int> pad((size_t)n), hist((size_t)n), cnt((size_t)n), fresh((size_t)n), lastv((size_t)n);
     c->h_stage.clear();
+    const int TS = c->tshift;   // the trap shift: rows wait for this many frames of right context (15 for the 31-frame systems)
     for (int i = 0; i < n; ++i) {
         phn_ctx::StreamHost &S = c->streams[sids[i]];
         const int64_t nb = (byte_off[i + 1] - byte_off[i]) / bps * bps;
@@ -1119,10 +1192,10 @@ int phn_stream_push(phn_ctx *c, const int *sids, int n, const void *audio, const
         const bool is_last = last && last[i];
         const int64_t T = S.frames + nf;                       // frames of the stream so far
         const int64_t w0 = S.frames - S.hist;                  // global index of the window's first real frame
-        const int64_t avail = is_last ? T : std::max<int64_t>(S.rows_done, T - 15);
+        const int64_t avail = is_last ? T : std::max<int64_t>(S.rows_done, T - TS);
         int64_t r_lo = S.rows_done;
         pad[i] = 0;
-        if (is_last && T > 0 && T < 15 && S.rows_done == 0) { pad[i] = (int)(15 - T); r_lo = -(int64_t)pad[i]; }   // the tail's warm-up rows
+        if (is_last && T > 0 && T < TS && S.rows_done == 0) { pad[i] = (int)(TS - T); r_lo = -(int64_t)pad[i]; }   // the tail's warm-up rows
         hist[i] = S.hist;
         woff[i + 1] = woff[i] + pad[i] + S.hist + nf;
         row0[i] = woff[i] + pad[i] + (r_lo - w0);
@@ -1133,7 +1206,7 @@ int phn_stream_push(phn_ctx *c, const int *sids, int n, const void *audio, const
         S.fed = S.fed || cnt[i] > 0;
         S.frames = T;
         S.rows_done = avail;
-        S.hist = (int)std::min<int64_t>(30, S.hist + nf);
+        S.hist = (int)std::min<int64_t>(2 * TS, S.hist + nf);
         if (is_last) {   // the next block starts a new utterance on this stream; the normaliser's estimate stays (it outlives
             const std::vector<uint8_t> none;   // MelBanks / Traps / decoder resets in the reference as well)
             S = phn_ctx::StreamHost();
@@ -1176,7 +1249,7 @@ int phn_stream_push(phn_ctx *c, const int *sids, int n, const void *audio, const
     // ---- windows [warm-up copies | history | new frames] -> the batch posterior estimator, no sentence normalisation
     const int64_t W = woff[n];
     if ((rc = ensure(c, c->d_win, sizeof(float) * (size_t)(W + 1) * c->nbanks))) return rc;
-    if ((rc = launch_stream_assemble(c, n, d_noff, d_woff, d_sid, d_pad, d_hist, (float *)c->d_win.p, (float *)c->d_st_hist.p))) return rc;
+    if ((rc = launch_stream_assemble(c, n, d_noff, d_woff, d_sid, d_pad, d_hist, (float *)c->d_win.p, (float *)c->d_st_hist.p, 2 * TS))) return rc;
     if ((rc = plan_frames(c, woff.data(), n, 1))) return rc;
     if (W) PHN_CUDA(c, cudaMemcpyAsync(c->d_mel.p, c->d_win.p, sizeof(float) * (size_t)W * c->nbanks, cudaMemcpyDeviceToDevice, c->stream));
     const int smn = c->sent_mean_norm;

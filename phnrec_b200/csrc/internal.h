@@ -11,6 +11,8 @@
 
 namespace phn {
 
+enum { PHN_SYS_LCRC = 0, PHN_SYS_1BT = 1, PHN_SYS_1BT_DCT = 2, PHN_SYS_3BT = 3 };
+
 // ---------------------------------------------------------------- host: config
 // The INI dialect of configz.cpp:102-165 with the typed variable table of srec.cpp:34-110.
 struct Config {
@@ -98,6 +100,13 @@ struct phn_ctx {
     int fs = 8000, fmt = 0, nbanks = 15, vs = 200, step = 80, S = 3, P = 0, hist = 40;
     int sent_mean_norm = 0, z_mean = 0;
     float lo = 0, hi = 4000, preem = 0, wpenalty = -2.f, frame_shift = 0.f, frame_floor = -9999.9f, scale = 1.f, dc_shift = 0.f;
+    // TRAPS system (posteriors/system): LCRC = the shipped systems; 1BT / 3BT / 1BT_DCT = k_trap.cu (exact mode only)
+    int system = 0, trap_len = 31, tshift = 15, use_hamming = 0, add_c0 = 1, trap_bands = 0, trap_shift_out = 0;
+    std::vector<phn::HostNet> hband;    // 1BT / 3BT: one net per band
+    std::vector<phn::DevNet> dband;
+    float *d_trap_ham = nullptr, *d_trap_cos = nullptr;
+    void *d_trap_pm = nullptr, *d_trap_pd = nullptr;
+    int trap_ready = 0;
     int mlp_mode = PHN_MLP_EXACT_FP32;
     void *tc = nullptr;  // tensor-core mode state (k_mlp_tc.cu)
     void *stc_btab = nullptr, *stc_bias = nullptr;   // K-stc tensor-core formulation: constant matrices (k_stc.cu)
@@ -133,6 +142,7 @@ struct phn_ctx {
     struct Buf { void *p = nullptr; size_t cap = 0; };
     Buf d_audio, d_byte_off, d_frame_off, d_lab_off, d_mel, d_mean, d_post, d_rec, d_pen;
     Buf d_x0, d_x1, d_h, d_xm, d_x0h, d_x1h, d_xmh;  // MLP workspace (per frame chunk)
+    Buf d_xb;                                        // 1BT / 3BT: [bands][chunk][kp] band-net inputs
     Buf d_tile_ctr, d_logp;
     // Results of one decoder launch.  Two slots, used alternately: the labels of batch k can be fetched (phn_wait) while
     // batch k+1 is already running (phn_recognize_async).  A slot carries its own copies of the frame / capacity offsets:
@@ -196,6 +206,11 @@ int launch_online_norm(phn_ctx *c, float *d_x, int64_t frames, int nb, int inter
 int launch_stc(phn_ctx *c, int64_t f0, int64_t nf, int64_t row_lo = 0, int64_t row_hi = -1);   // k_stc.cu: frames [f0, f0+nf) of the pass;
                                                                                                   // only rows row_lo <= frame < row_hi are produced
 int launch_mlp_exact(phn_ctx *c, int64_t f0, int64_t nf);                  // k_mlp_exact.cu
+// one net of the exact mode: outputs to `post` (linear posteriors) or, when post == nullptr, into the merger's input matrix at
+// column xm_col0 as (+-)sLn(p) with the merger's input normalisation (negate: the 1BT / 3BT systems, traps.cpp:425-427)
+int run_net_exact(phn_ctx *c, const phn::DevNet &n, const float *x, int ldx, int64_t nf, float *post, int ldpost, int xm_col0, int negate);
+int launch_trap(phn_ctx *c, int64_t f0, int64_t nf);                        // k_trap.cu: 1BT / 3BT / 1BT_DCT front end
+int launch_mlp_trap(phn_ctx *c, int64_t f0, int64_t nf);                    // k_mlp_exact.cu: their nets
 int launch_mlp_tc(phn_ctx *c, int64_t f0, int64_t nf);                     // k_mlp_tc.cu
 int launch_viterbi(phn_ctx *c, const float *d_pen, int n_pen, cudaStream_t s, phn_ctx::DecSlot &sl);   // k_vit.cu
 int launch_compact_labels(phn_ctx *c, int nseg, phn_ctx::DecSlot &sl);     // k_vit.cu
@@ -204,7 +219,7 @@ int launch_log_post(phn_ctx *c, int64_t rows);                               // 
 // k_stream.cu: the state-carrying kernels of the streaming path
 int launch_stream_norm(phn_ctx *c, int n, const int *d_sid, float *d_state, unsigned *d_cnt, int interval, int mean_norm, int var_norm);
 int launch_stream_assemble(phn_ctx *c, int n, const int64_t *d_new_off, const int64_t *d_win_off, const int *d_sid, const int *d_pad,
-                           const int *d_hist, float *d_win, float *d_st_hist);
+                           const int *d_hist, float *d_win, float *d_st_hist, int keep);
 int launch_stream_decode(phn_ctx *c, int n, int64_t rows, const int64_t *d_row0, const int *d_count, const int *d_sid, const int *d_fresh,
                          const int *d_last, phn::VitStreamState *d_st, phn_label *d_labels, const int64_t *d_lab_off, int *d_nlab);
 int launch_synth(phn_ctx *c, void *d_audio, int64_t bytes_per_utt, int n_utt, uint64_t seed);  // k_synth.cu

@@ -123,6 +123,7 @@ struct L2Args {
     float *xm; int ldxm; int xm_col0; const float *mmean, *mdev;
     // merger: posteriors
     float *post; int ldpost;
+    int negate;   // merger input = -sLn(p) (the 1BT / 3BT systems)
 };
 
 __global__ void __launch_bounds__(256) k_l2_exact(L2Args a)
@@ -227,26 +228,29 @@ __global__ void __launch_bounds__(256) k_l2_exact(L2Args a)
             a.post[f * a.ldpost + n] = p;
         } else {  // merger input: sLn then the merger's own input normalisation (traps.cpp:459, nn.cpp:702-716)
             const int c = a.xm_col0 + n;
-            a.xm[f * a.ldxm + c] = __fmul_rn(__fsub_rn(ln_guarded(p, s_logtab), a.mmean[c]), a.mdev[c]);
+            float v = ln_guarded(p, s_logtab);
+            if (a.negate) v = __fmul_rn(v, -1.0f);   // sMultiplication(.., -1), traps.cpp:427
+            a.xm[f * a.ldxm + c] = __fmul_rn(__fsub_rn(v, a.mmean[c]), a.mdev[c]);
         }
     }
 }
 
-static int run_net(phn_ctx *c, int which, const float *x, int ldx, int64_t nf, int64_t f0)
+int run_net_exact(phn_ctx *c, const DevNet &n, const float *x, int ldx, int64_t nf, float *post, int ldpost, int xm_col0, int negate)
 {
-    const DevNet &n = c->net[which];
     float *H = (float *)c->d_h.p;
+    if (n.nout > L2_BN) return fail(c, PHN_ERR_UNSUPPORTED, "more than %d network outputs\n", L2_BN);
     dim3 g1((n.ldh + L1_BN - 1) / L1_BN, (unsigned)((nf + L1_BM - 1) / L1_BM));
     k_l1_exact<<<g1, 256, 0, c->stream>>>(x, ldx, n.w1, n.nin4, n.b1, H, n.ldh, nf, n.nhid, n.nhid4, n.nin4, n.kp);
     PHN_CUDA(c, cudaGetLastError());
     L2Args a{};
     a.H = H; a.ldh = n.ldh; a.W = n.w2; a.ldw = n.nhid4; a.bias = n.b2; a.nf = nf;
     a.nout = n.nout; a.nout4 = n.nout4; a.K4 = n.nhid4; a.Kp = n.ldh;
-    if (which < 2) {
-        a.xm = (float *)c->d_xm.p; a.ldxm = c->net[2].kp; a.xm_col0 = which * n.nout;
+    a.negate = negate;
+    if (!post) {
+        a.xm = (float *)c->d_xm.p; a.ldxm = c->net[2].kp; a.xm_col0 = xm_col0;
         a.mmean = c->net[2].mean; a.mdev = c->net[2].dev;
     } else {
-        a.post = (float *)c->d_post.p + f0 * c->ldp; a.ldpost = c->ldp;
+        a.post = post; a.ldpost = ldpost;
     }
     k_l2_exact<<<(unsigned)((nf + L2_BM - 1) / L2_BM), 256, 0, c->stream>>>(a);
     PHN_CUDA(c, cudaGetLastError());
@@ -257,11 +261,23 @@ static int run_net(phn_ctx *c, int which, const float *x, int ldx, int64_t nf, i
 int launch_mlp_exact(phn_ctx *c, int64_t f0, int64_t nf)
 {
     if (nf == 0) return PHN_OK;
-    if (c->net[2].nout > L2_BN) return fail(c, PHN_ERR_UNSUPPORTED, "more than %d network outputs\n", L2_BN);
     int rc;
-    if ((rc = run_net(c, 0, (const float *)c->d_x0.p, c->net[0].kp, nf, f0))) return rc;
-    if ((rc = run_net(c, 1, (const float *)c->d_x1.p, c->net[1].kp, nf, f0))) return rc;
-    return run_net(c, 2, (const float *)c->d_xm.p, c->net[2].kp, nf, f0);
+    if ((rc = run_net_exact(c, c->net[0], (const float *)c->d_x0.p, c->net[0].kp, nf, nullptr, 0, 0, 0))) return rc;
+    if ((rc = run_net_exact(c, c->net[1], (const float *)c->d_x1.p, c->net[1].kp, nf, nullptr, 0, c->net[0].nout, 0))) return rc;
+    return run_net_exact(c, c->net[2], (const float *)c->d_xm.p, c->net[2].kp, nf, (float *)c->d_post.p + f0 * c->ldp, c->ldp, 0, 0);
+}
+
+// 1BT / 3BT: one net per band into the merger's input matrix (as -sLn), then the merger; 1BT_DCT: the merger only
+int launch_mlp_trap(phn_ctx *c, int64_t f0, int64_t nf)
+{
+    if (nf == 0) return PHN_OK;
+    int rc, col = 0;
+    for (size_t b = 0; b < c->dband.size(); ++b) {
+        const DevNet &n = c->dband[b];
+        if ((rc = run_net_exact(c, n, (const float *)c->d_xb.p + b * (size_t)c->chunk_frames * n.kp, n.kp, nf, nullptr, 0, col, 1))) return rc;
+        col += n.nout;
+    }
+    return run_net_exact(c, c->net[2], (const float *)c->d_xm.p, c->net[2].kp, nf, (float *)c->d_post.p + f0 * c->ldp, c->ldp, 0, 0);
 }
 
 }  // namespace phn

@@ -60,8 +60,8 @@ struct AsmArgs {
     const int64_t *win_off;      // [n + 1] window offsets (rows) in `win`
     const int *sid, *pad, *hist; // per pushed stream: state slot, virtual warm-up rows in front, frames held in the history
     float *win;                  // [sum window rows][nb]
-    float *st_hist;              // [n_streams][30][nb]
-    int nb;
+    float *st_hist;              // [n_streams][keep][nb]
+    int nb, keep;                // keep = 2 x trap shift: the frames a later row's context may reach back to (30)
 };
 
 __global__ void __launch_bounds__(128) k_stream_assemble(AsmArgs a)
@@ -70,14 +70,14 @@ __global__ void __launch_bounds__(128) k_stream_assemble(AsmArgs a)
     const int s = a.sid[i], P = a.pad[i], H = a.hist[i];
     const int64_t n0 = a.new_off[i], N = a.new_off[i + 1] - n0;
     float *w = a.win + a.win_off[i] * nb;
-    float *h = a.st_hist + (size_t)s * 30 * nb;
+    float *h = a.st_hist + (size_t)s * a.keep * nb;
     for (int64_t k = threadIdx.x; k < (int64_t)H * nb; k += blockDim.x) w[(int64_t)P * nb + k] = h[k];
     for (int64_t k = threadIdx.x; k < N * nb; k += blockDim.x) w[((int64_t)P + H) * nb + k] = a.mel[n0 * nb + k];
     __syncthreads();
     // the virtual warm-up rows of a short utterance: copies of its first frame (the FIFO starts filled with it, traps.cpp:182-199)
     for (int64_t k = threadIdx.x; k < (int64_t)P * nb; k += blockDim.x) w[k] = w[(int64_t)P * nb + k % nb];
     // new history: the last (up to) 30 real frames
-    const int64_t R = H + N, keep = R < 30 ? R : 30;
+    const int64_t R = H + N, keep = R < a.keep ? R : a.keep;
     __syncthreads();
     for (int64_t k = threadIdx.x; k < keep * nb; k += blockDim.x) h[k] = w[((int64_t)P + R - keep) * nb + k];
 }
@@ -92,10 +92,10 @@ int launch_stream_norm(phn_ctx *c, int n, const int *d_sid, float *d_state, unsi
 }
 
 int launch_stream_assemble(phn_ctx *c, int n, const int64_t *d_new_off, const int64_t *d_win_off, const int *d_sid, const int *d_pad,
-                           const int *d_hist, float *d_win, float *d_st_hist)
+                           const int *d_hist, float *d_win, float *d_st_hist, int keep)
 {
     if (n == 0) return PHN_OK;
-    AsmArgs a{(const float *)c->d_mel.p, d_new_off, d_win_off, d_sid, d_pad, d_hist, d_win, d_st_hist, c->nbanks};
+    AsmArgs a{(const float *)c->d_mel.p, d_new_off, d_win_off, d_sid, d_pad, d_hist, d_win, d_st_hist, c->nbanks, keep};
     k_stream_assemble<<<n, 128, 0, c->stream>>>(a);
     PHN_CUDA(c, cudaGetLastError());
     return PHN_OK;

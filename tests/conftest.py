@@ -232,3 +232,11 @@ TRAP_CASES = [  # (name, system, seed, options)
     ("1bt_dct_len51", "1BT_DCT", 16, {"length": 51, "shift": 12}),
     ("3bt", "3BT", 17, {}),
 ]
+
+
+def online_case_model_dir(tmp_path, case) -> Path:
+    """The model directory of one tests/golden/ref_online_stream.json run: a shipped model, an edited copy of one, or a synthetic one."""
+    if case["model"].startswith("synthetic:"):
+        _, system, seed, opt = next(c for c in TRAP_CASES if c[0] == case["model"].split(":")[1])
+        return synthetic_trap_model(Path(tmp_path) / case["name"], system, seed, **opt)
+    return variant_model_dir(Path(tmp_path) / case["name"], case["model"], case["edits"]) if case["edits"] else model_dir(case["model"])

@@ -72,6 +72,11 @@ ONLINE_CASES = [  # (name, model, audio, bytes used, wave format, block bytes, p
     ("cz_alaw_17_frames", "PHN_CZ_SPDAT_LCRC_N1500", "8580.wav", 200 + 16 * 80, "alaw", 400, None, {}),
     ("cz_bunch4", "PHN_CZ_SPDAT_LCRC_N1500", "test.raw", 40000, "lin16", 1600, None, {"posteriors/bunch_size": "4"}),
     ("cz_bunch4_14_frames", "PHN_CZ_SPDAT_LCRC_N1500", "8580.wav", 200 + 13 * 80, "alaw", 400, None, {"posteriors/bunch_size": "4"}),
+    # synthetic models of the other TRAPS systems (tests/conftest.py): trap shifts 25 and 10 instead of 15
+    ("syn_dct51", "synthetic:1bt_dct_len51", "test.raw", 40000, "lin16", 3200, None, {}),
+    ("syn_dct51_8_frames", "synthetic:1bt_dct_len51", "test.raw", 2 * (200 + 7 * 80), "lin16", 700, None, {}),
+    ("syn_1bt21_en", "synthetic:1bt_len21_en", "test.raw", 50000, "lin16", 2500, None, {}),
+    ("syn_1bt21_en_7_frames", "synthetic:1bt_len21_en", "test.raw", 2 * (400 + 6 * 160), "lin16", 900, None, {}),
     ("hu_framenorm", "PHN_HU_SPDAT_LCRC_N1500", "test.raw", 64000, "lin16", 1600, None,
      {"framenorm/shift": "0.75", "onlinenorm/estim_interval": "30", "onlinenorm/mean_norm": "true"}),
 ]
@@ -80,13 +85,17 @@ ONLINE_CASES = [  # (name, model, audio, bytes used, wave format, block bytes, p
 def online_stream():
     """ref_online_stream.json: the reference's online path, block by block (oracle/_ref/online_ref stream)."""
     sys.path.insert(0, str(ROOT / "tests"))
-    from conftest import variant_model_dir  # noqa: E402
+    from conftest import variant_model_dir, synthetic_trap_model, TRAP_CASES  # noqa: E402
     online_ref = orc.REF_BIN.parent / "online_ref"
     out = []
     with tempfile.TemporaryDirectory() as td:
         td = Path(td)
         for name, model, audio, nbytes, fmt, block, pen, edits in ONLINE_CASES:
-            cfg = variant_model_dir(td / name, model, edits) if edits else orc.REF_MODELS / model
+            if model.startswith("synthetic:"):
+                _, system, seed, opt = next(c for c in TRAP_CASES if c[0] == model.split(":")[1])
+                cfg = synthetic_trap_model(td / name, system, seed, **opt)
+            else:
+                cfg = variant_model_dir(td / name, model, edits) if edits else orc.REF_MODELS / model
             (td / "a.raw").write_bytes((orc.REF_AUDIO / audio).read_bytes()[:nbytes])
             r = subprocess.run([str(online_ref), "stream", str(cfg), str(td / "a.raw"), str(block), fmt, "-" if pen is None else str(pen),
                                 str(td / "o.rec")], capture_output=True, text=True)

@@ -9,7 +9,7 @@ import json
 import numpy as np
 import pytest
 
-from conftest import GOLDEN, audio_bytes, model_dir, variant_model_dir
+from conftest import GOLDEN, audio_bytes, model_dir, online_case_model_dir, variant_model_dir
 import phnrec_b200 as pb
 
 pytestmark = pytest.mark.gpu
@@ -32,8 +32,7 @@ def stream_one(r, audio: bytes, block: int, sid: int = 0):
 
 @pytest.mark.parametrize("case", [c for c in CASES if "bunch4" not in c["name"]], ids=lambda c: c["name"])
 def test_stream_equals_reference_online_objects(tmp_path, case):
-    cfg = variant_model_dir(tmp_path, case["model"], case["edits"]) if case["edits"] else model_dir(case["model"])
-    r = pb.Recognizer(cfg, device=0)
+    r = pb.Recognizer(online_case_model_dir(tmp_path, case), device=0)
     try:
         r.set_wave_format(case["fmt"])
         if case["penalty"] is not None:

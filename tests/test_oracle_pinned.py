@@ -182,17 +182,16 @@ def test_online_path_restatement_equals_reference_objects(orc, tmp_path):
     """§8(f) rank 1 pinned: the whole-signal restatement of the online path (orc_model_recognize_online: streaming frame count,
     FrameBasedNormalization, the live normaliser, clamped context, decoder) prints what the reference's streaming objects
     print when they are fed in blocks - every block size, penalty and [onlinenorm] setting of the fixture, labels AND scores."""
-    from conftest import audio_bytes, variant_model_dir, model_dir
+    from conftest import audio_bytes, online_case_model_dir
     n = 0
     for c in online_stream_cases():
-        cfg = variant_model_dir(tmp_path / c["name"], c["model"], c["edits"]) if c["edits"] else model_dir(c["model"])
-        m = orc.Model(cfg)
+        m = orc.Model(online_case_model_dir(tmp_path, c))
         a = audio_bytes(c["audio"])[:c["nbytes"]]
         got = m.recognize_online(a, fmt=c["fmt"], wp=c["penalty"])
         assert orc.format_rec(got, m.phonemes) == c["rec"], c["name"]
         m.close()
         n += 1
-    assert n >= 14
+    assert n >= 18
 
 
 def test_other_trap_systems_restatement_equals_reference_binary(orc, tmp_path):
