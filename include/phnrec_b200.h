@@ -68,6 +68,7 @@ typedef struct {
     int32_t band_inputs, merger_inputs, hidden;  /* .nbin header sizes (nn.cpp:464-531) */
     int32_t sent_mean_norm, time_pruning, mlp_mode, device;
     float wpenalty;
+    int32_t n_params;   /* columns of the parameter matrix phn_mel returns / `-t par` saves: nbanks, or the PLP coefficients (params/kind = plp) */
 } phn_info;
 
 /* -- lifetime ---------------------------------------------------------------------- */

@@ -54,6 +54,8 @@ def lib() -> C.CDLL:
     L.orc_mel_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_int]
     L.orc_mel_create.restype = vp
     L.orc_mel_destroy.argtypes = [vp]
+    L.orc_mel_set_plp.argtypes = [vp, C.c_int, C.c_float, C.c_float, C.c_float, C.c_int]
+    L.orc_mel_nparams.argtypes = [vp]
     L.orc_mel_fft_size.argtypes = [vp]
     L.orc_mel_tables.argtypes = [vp, _f32p, _f32p, _i16p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.orc_num_frames.argtypes = [C.c_int] * 3
@@ -96,6 +98,7 @@ def lib() -> C.CDLL:
     L.orc_model_mel.argtypes = [vp]
     L.orc_model_mel.restype = vp
     L.orc_model_num_frames.argtypes = [vp, C.c_int, C.c_int]
+    L.orc_model_nparams.argtypes = [vp]
     L.orc_model_mel_from_audio.argtypes = [vp, vp, C.c_int, C.c_int, _f32p]
     L.orc_model_mel_from_audio.restype = C.c_int
     L.orc_model_posteriors.argtypes = [vp, _f32p, C.c_int, _f32p]
@@ -182,7 +185,7 @@ class Model:
         a, p, n = _buf(audio)
         f = -1 if fmt is None else FMT[fmt]
         T = lib().orc_model_num_frames(self.h, n, f)
-        out = np.zeros((T, self.nbanks), dtype=np.float32)
+        out = np.zeros((T, lib().orc_model_nparams(self.h)), dtype=np.float32)   # nbanks, or the PLP coefficients (params/kind = plp)
         lib().orc_model_mel_from_audio(self.h, p, n, f, out)
         return out
 

@@ -99,6 +99,11 @@ typedef struct {
     float *fft;     /* [2N+1] NR 1-based work array, melbanks.cpp:62 */
     float *frame;   /* [vs] */
     float *pw;      /* [N2] */
+    float *f0;      /* [nbanks + 1] centres of the banks in Hz (dspc.cpp:156-162), used by PLP */
+    /* PLP (plp.cpp; params/kind = plp): order 0 = plain mel-banks */
+    int plp_order, plp_add_c0;
+    float plp_compress, plp_lifter, plp_scale;
+    float *plp_eql, *plp_idft, *plp_lift;   /* [nbanks], [order+1][nbanks+2], [order] */
 } orc_mel;
 
 static float scale_mel(float f) { return 1127.0f * logf(1.0f + f / 700.0f); } /* dspc.h:174-177 */
@@ -134,9 +139,11 @@ orc_mel *orc_mel_create(int nbanks, int vs, int step, int fs, float lo, float hi
     m->fftlo = fftlo; m->ffthi = ffthi;
     float delta = (mhi - mlo) / (nbanks + 1);
     float mf = mlo;
+    m->f0 = (float *)malloc(sizeof(float) * (nbanks + 1));
     for (int i = 0; i <= nbanks; ++i) { /* dspc.cpp:156-162 (repeated float addition) */
         mf = mf + delta;
         f0m[i] = mf;
+        m->f0[i] = 700.0f * (expf(mf / 1127.0f) - 1.0f); /* Scale_MelToLinear, dspc.h:169-172 */
     }
     int ch = 0;
     for (int i = 0; i < m->N2; ++i) { /* dspc.cpp:165-180 */
@@ -256,7 +263,78 @@ static void mel_frame(orc_mel *m, float *fr, float *out)
         if (B > 0) out[B - 1] += v;
         if (B < nb) out[B] += (m->pw[k] - v);
     }
+    if (m->plp_order > 0) return; /* PLPCoefs switches the logarithm off (plp.cpp:70, SetTakeLog(false)) */
     for (int b = 0; b < nb; ++b) out[b] = (out[b] > 0.0f ? logf(out[b]) : 0.0f); /* dspc.h:155-160 */
+}
+
+/* PLP coefficients (params/kind = plp).  PLPCoefs::Init / ProcessFrame (plp.cpp:38-141), CreateIDFTMatrix (plp.cpp:143-165),
+ * sEqualLaudnessCurve / sPower / sLowerFloor (dspc.h:235-265), sDurbin / sLPC2Cepstrum / sLifteringWindow (dspc.cpp:275-335).
+ * Compiled out of the reference's PHNREC_ONLY build (srec.cpp:563-583); pinned against the class itself through
+ * oracle/_ref/online_ref plp (tests/golden/ref_plp.npz). */
+void orc_mel_set_plp(orc_mel *m, int order, float compress, float lifter, float scale, int add_c0)
+{
+    const int nb = m->nbanks, dim = nb + 2;
+    m->plp_order = order; m->plp_compress = compress; m->plp_lifter = lifter; m->plp_scale = scale; m->plp_add_c0 = add_c0;
+    m->plp_eql = (float *)malloc(sizeof(float) * nb);
+    for (int i = 0; i < nb; ++i) {
+        float fsq = (m->f0[i] * m->f0[i]);
+        float fsub = fsq / (fsq + 1.6e5f);
+        m->plp_eql[i] = fsub * fsub * ((fsq + 1.44e6f) / (fsq + 9.61e6f));
+    }
+    m->plp_idft = (float *)malloc(sizeof(float) * (order + 1) * dim);
+    float angle = M_PI / (float)(dim - 1);
+    float scl = 1.0f / (2.0f * (dim - 1));
+    for (int i = 0; i <= order; ++i) {
+        float *row = m->plp_idft + (size_t)i * dim;
+        row[0] = 1.0f * scl;
+        /* C++: cos(float) is the float overload, i.e. cosf; `2.0 * scale * ...` is then evaluated in double and rounded once */
+        for (int j = 1; j < dim - 1; ++j) row[j] = (float)(2.0 * scl * cosf(angle * (float)i * (float)j));
+        row[dim - 1] = scl * cosf(angle * (float)i * (float)(dim - 1));
+    }
+    m->plp_lift = (float *)malloc(sizeof(float) * (order > 0 ? order : 1));
+    int Q = (int)lifter;
+    for (int i = 0; i < order; ++i) m->plp_lift[i] = 1.0f + 0.5f * Q * sinf(M_PI * (float)(i + 1) / (float)Q);
+}
+
+int orc_mel_nparams(const orc_mel *m) { return m->plp_order > 0 ? m->plp_order + (m->plp_add_c0 ? 1 : 0) : m->nbanks; }
+
+/* energies [nbanks] (no logarithm) -> coefficients [nparams] */
+static void plp_frame(const orc_mel *m, const float *en_in, float *out)
+{
+    const int nb = m->nbanks, dim = nb + 2, P = m->plp_order;
+    float en[64], ac[64], lp[64], tmp[64], cep[64];
+    for (int i = 0; i < nb; ++i) {
+        float v = en_in[i];
+        if (v < 1.0f) v = 1.0f;                 /* sLowerFloor(.., 1.0f) */
+        v = v * m->plp_eql[i];                  /* equal loudness */
+        en[i + 1] = powf(v, m->plp_compress);   /* sPower; stored shifted right by one */
+    }
+    en[0] = en[1];                              /* duplicate the first and the last value */
+    en[nb + 1] = en[nb];
+    for (int i = 0; i <= P; ++i) {              /* ApplyLinTransform */
+        float s = 0.0f;
+        for (int j = 0; j < dim; ++j) s += en[j] * m->plp_idft[(size_t)i * dim + j];
+        ac[i] = s;
+    }
+    float E = ac[0];                            /* sDurbin */
+    for (int i = 0; i < P; ++i) {
+        float ki = ac[i + 1];
+        for (int j = 0; j < i; ++j) ki = ki + lp[j] * ac[i - j];
+        ki = ki / E;
+        E *= 1 - ki * ki;
+        tmp[i] = -ki;
+        for (int j = 0; j < i; ++j) tmp[j] = lp[j] - ki * lp[i - j - 1];
+        for (int j = 0; j <= i; ++j) lp[j] = tmp[j];
+    }
+    for (int i = 0; i < P; ++i) {               /* sLPC2Cepstrum */
+        float sum = 0.0f;
+        for (int j = 0; j < i; ++j) sum += (float)(i - j) * lp[j] * cep[i - j - 1];
+        cep[i] = -lp[i] - sum / (float)(i + 1);
+    }
+    cep[P] = -logf(1.0f / E);                   /* C0 */
+    if (m->plp_lifter != 0.0f) for (int i = 0; i < P; ++i) cep[i] *= m->plp_lift[i];
+    if (m->plp_scale != 1.0f) for (int i = 0; i <= P; ++i) cep[i] *= m->plp_scale;
+    for (int i = 0; i < (m->plp_add_c0 ? P + 1 : P); ++i) out[i] = cep[i];
 }
 
 /* Whole utterance (framing of melbanks.cpp:151-204 + srec.cpp:945,965-971):
@@ -271,12 +349,19 @@ int orc_mel_compute(orc_mel *m, const float *wav, int len, float frame_shift, fl
             int idx = t * m->step + i;
             m->frame[i] = (idx < len || idx < ORC_MB_VECTORSIZE) ? wav[idx] : 0.0f;
         }
-        float *o = mel + (size_t)t * m->nbanks;
-        mel_frame(m, m->frame, o);
+        const int np = orc_mel_nparams(m);
+        float *o = mel + (size_t)t * np;
+        if (m->plp_order > 0) {
+            float en[64];
+            mel_frame(m, m->frame, en);
+            plp_frame(m, en, o);
+        } else {
+            mel_frame(m, m->frame, o);
+        }
         if (frame_shift != 0.0f)
-            for (int b = 0; b < m->nbanks; ++b) o[b] += frame_shift;
+            for (int b = 0; b < np; ++b) o[b] += frame_shift;
         if (frame_floor != -9999.9f)
-            for (int b = 0; b < m->nbanks; ++b)
+            for (int b = 0; b < np; ++b)
                 if (o[b] < frame_floor) o[b] = frame_floor;
     }
     return T;
@@ -808,6 +893,8 @@ typedef struct {
     int z_mean;
     int on_interval, on_mean, on_var;   /* [onlinenorm] estim_interval, mean_norm, var_norm */
     int bunch;                          /* [posteriors] bunch_size */
+    int plp, plp_order, plp_add_c0;     /* [params] kind = plp, [plp] order / add_c0 */
+    float plp_compress, plp_lifter, plp_scale;
     int system, trap_len, hamming, add_c0;   /* [posteriors] system (0 LCRC, 1 1BT, 2 1BT_DCT, 3 3BT), length, hamming, add_c0 */
     orc_nn *bands[32];                  /* 1BT / 3BT: one net per band */
     float win[32];
@@ -870,6 +957,12 @@ orc_model *orc_model_load(const char *dir)
     cfg_get(txt, "offlinenorm", "sent_mean_norm", buf, "false"); m->sent_mean_norm = strcmp(buf, "true") == 0;
     cfg_get(txt, "framenorm", "shift", buf, "0"); sscanf(buf, "%f", &m->frame_shift);
     cfg_get(txt, "framenorm", "min_floor", buf, "-9999.9"); sscanf(buf, "%f", &m->frame_floor);
+    cfg_get(txt, "params", "kind", buf, "fbanks"); m->plp = strcmp(buf, "plp") == 0;     /* srec.cpp:41, 544-583 */
+    cfg_get(txt, "plp", "order", buf, "12"); m->plp_order = atoi(buf);                   /* srec.cpp:51-55 */
+    cfg_get(txt, "plp", "compress_fact", buf, "0.3333333"); sscanf(buf, "%f", &m->plp_compress);
+    cfg_get(txt, "plp", "cep_lifter", buf, "22"); sscanf(buf, "%f", &m->plp_lifter);
+    cfg_get(txt, "plp", "cep_scale", buf, "10"); sscanf(buf, "%f", &m->plp_scale);
+    cfg_get(txt, "plp", "add_c0", buf, "false"); m->plp_add_c0 = strcmp(buf, "true") == 0;
     cfg_get(txt, "posteriors", "bunch_size", buf, "1"); m->bunch = atoi(buf) > 0 ? atoi(buf) : 1;
     cfg_get(txt, "posteriors", "system", buf, "1BT_DCT");
     m->system = !strcmp(buf, "LCRC") ? 0 : !strcmp(buf, "1BT") ? 1 : !strcmp(buf, "1BT_DCT") ? 2 : !strcmp(buf, "3BT") ? 3 : -1;
@@ -917,6 +1010,7 @@ orc_model *orc_model_load(const char *dir)
     }
     fclose(f);
     m->mel = orc_mel_create(m->nbanks, m->vs, m->step, m->fs, m->lo, m->hi, m->preem, m->z_mean);
+    if (m->plp) orc_mel_set_plp(m->mel, m->plp_order, m->plp_compress, m->plp_lifter, m->plp_scale, m->plp_add_c0);
     return m;
 }
 
@@ -927,6 +1021,8 @@ void orc_model_destroy(orc_model *m)
     for (int i = 0; i < 32; ++i) orc_nn_destroy(m->bands[i]);
     free(m);
 }
+
+int orc_model_nparams(const orc_model *m) { return orc_mel_nparams(m->mel); }   /* columns of the `-t par` matrix */
 
 /* info: fs, nbanks, vs, step, fmt, sent_mean_norm, hist, S, P, nout, nin_band, nhid */
 void orc_model_info(const orc_model *m, int *info, float *wpenalty)

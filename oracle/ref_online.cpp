@@ -8,6 +8,9 @@
 //
 //   online_ref norm  <in.f32> <rows> <cols> <interval> <mean 0|1> <var 0|1> <out.f32>
 //        Normalization::{StartEstimation, SetMeanNorm, SetVarNorm, ProcessFrame} row by row over a raw float32 matrix.
+//   online_ref plp <audio.lin16> <out.f32> <fs> <vs> <step> <nbanks> <lo> <hi> <preem> <zmean 0|1> <order> <compress> <lifter> <scale> <add_c0 0|1>
+//        PLPCoefs (plp.cpp:91-141 - compiled out of the reference's PHNREC_ONLY build, srec.cpp:563-583, so the phnrec binary cannot
+//        produce it): AddWaveform + GetFeatures over a 16-bit file; rows of order (+1) float32 coefficients.
 //   online_ref stream <config_dir> <audio> <block_bytes> <lin16|alaw> <penalty|-> <out.rec>
 //        SpeechRec::Init + PhnDec::Init(out.rec) + ProcessOnline in blocks of <block_bytes> (last block flagged), Done.
 #include <cstdio>
@@ -21,6 +24,7 @@
 
 #include "srec.h"
 #include "norm.h"
+#include "plp.h"
 
 // Linked with -Wl,--wrap=sprintf (oracle/Makefile): Normalization::Save (norm.cpp:339,353) prints " %e" into a char[10];
 // for that format at most 9 characters are stored, every other call is the plain sprintf.
@@ -122,9 +126,39 @@ static int run_stream(int argc, char **argv)
     return 0;
 }
 
+static int run_plp(int argc, char **argv)
+{
+    if (argc != 17) return 2;
+    FILE *f = fopen(argv[2], "rb");
+    if (!f) return 3;
+    std::vector<short> raw;
+    short buf[4096];
+    size_t n;
+    while ((n = fread(buf, sizeof(short), 4096, f)) > 0) raw.insert(raw.end(), buf, buf + n);
+    fclose(f);
+    std::vector<float> wav(raw.size() + 8);
+    for (size_t i = 0; i < raw.size(); ++i) wav[i] = (float)raw[i];   // srec.cpp:742-743
+    PLPCoefs P;
+    P.SetSampleFreq(atoi(argv[4])); P.SetVectorSize(atoi(argv[5])); P.SetStep(atoi(argv[6]));
+    P.SetBanksNum(atoi(argv[7])); P.SetLowFreq((float)atof(argv[8])); P.SetHighFreq((float)atof(argv[9]));
+    P.SetPreemCoef((float)atof(argv[10])); P.SetZMeanSource(atoi(argv[11]) != 0);
+    P.SetLPCOrder(atoi(argv[12])); P.SetCompressFactor((float)atof(argv[13])); P.SetCepstralLifter((float)atof(argv[14]));
+    P.SetCepstralScale((float)atof(argv[15])); P.SetAddC0(atoi(argv[16]) != 0);
+    if ((int)raw.size() < atoi(argv[5])) return 4;
+    FILE *fo = fopen(argv[3], "wb");
+    if (!fo) return 5;
+    P.AddWaveform(wav.data(), (int)raw.size());
+    std::vector<float> out(64);
+    const int np = P.GetNParams();
+    while (P.GetFeatures(out.data())) fwrite(out.data(), sizeof(float), np, fo);
+    fclose(fo);
+    return 0;
+}
+
 int main(int argc, char **argv)
 {
     if (argc >= 2 && !strcmp(argv[1], "norm")) return run_norm(argc, argv);
+    if (argc >= 2 && !strcmp(argv[1], "plp")) return run_plp(argc, argv);
     if (argc >= 2 && !strcmp(argv[1], "stream")) return run_stream(argc, argv);
     fprintf(stderr, "usage: online_ref norm|stream ...\n");
     return 2;

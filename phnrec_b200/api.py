@@ -34,7 +34,7 @@ class _Info(C.Structure):
     _fields_ = [(n, C.c_int32) for n in
                 ("sample_freq", "wave_format", "nbanks", "vector_size", "vector_step", "fft_size", "n_phonemes",
                  "n_states", "n_outputs", "band_inputs", "merger_inputs", "hidden", "sent_mean_norm", "time_pruning",
-                 "mlp_mode", "device")] + [("wpenalty", C.c_float)]
+                 "mlp_mode", "device")] + [("wpenalty", C.c_float), ("n_params", C.c_int32)]
 
 
 def lib_path() -> Path:
@@ -210,7 +210,7 @@ class Recognizer:
         n = len(utts)
         foff = np.zeros(n + 1, dtype=np.int64)
         self._ck(self._L.phn_mel(self._h, audio.ctypes.data, boff, n, None, foff))
-        out = np.zeros((int(foff[-1]), self.nbanks), dtype=np.float32)
+        out = np.zeros((int(foff[-1]), self.n_params), dtype=np.float32)   # nbanks, or the PLP coefficients (params/kind = plp)
         self._ck(self._L.phn_mel(self._h, audio.ctypes.data, boff, n, out.ctypes.data, foff))
         return [out[foff[i]:foff[i + 1]] for i in range(n)]
 
@@ -330,7 +330,7 @@ class Recognizer:
         return self._split_labels(labels, loff)
 
     def fetch_mel(self, total_frames: int):
-        out = np.zeros((total_frames, self.nbanks), dtype=np.float32)
+        out = np.zeros((total_frames, self.n_params), dtype=np.float32)
         self._ck(self._L.phn_fetch_mel(self._h, out.reshape(-1)))
         return out
 

@@ -234,6 +234,7 @@ static void reset_timing(phn_ctx *c)
 static int prepare_posteriors(phn_ctx *c)
 {
     int rc;
+    if (c->plp) return fail(c, PHN_ERR_UNSUPPORTED, "params/kind = plp is a parameterisation for `-t par` only: the TRAPS nets take mel-bank energies\n");
     const bool tc = c->mlp_mode == PHN_MLP_TC_F16;
     const int64_t F = c->total_frames;
     int64_t ch = tc ? (int64_t)1 << 20 : (int64_t)1 << 15;   // frames per pass of the MLP workspace (tensor-core: 1.4 KB per frame)
@@ -454,7 +455,15 @@ int phn_create(const char *cfg_dir, int device, phn_ctx **out)
     }
     const Config &C = c->cfg;
     // ---- what this hot path implements: fbanks -> LCRC -> phndec, offline
-    if (C.str("params", "kind") != "fbanks") return bail(fail(c, PHN_ERR_UNSUPPORTED, "Unsupported parameter kind: %s\n", C.str("params", "kind").c_str()));
+    if (C.str("params", "kind") == "plp") {   // srec.cpp:563-583 (compiled out of the reference's PHNREC_ONLY build)
+        c->plp = 1;
+        c->plp_order = C.i("plp", "order"); c->plp_compress = C.f("plp", "compress_fact"); c->plp_lifter = C.f("plp", "cep_lifter");
+        c->plp_scale = C.f("plp", "cep_scale"); c->plp_add_c0 = C.b("plp", "add_c0");
+        if (c->plp_order < 1 || c->plp_order > 31) return bail(fail(c, PHN_ERR_CFG_BADVAL, "plp/order out of range (1..31)\n"));
+    } else if (C.str("params", "kind") != "fbanks")
+        return bail(fail(c, PHN_ERR_UNSUPPORTED, "Unknown parameterization (parameters/kind): '%s'\n", C.str("params", "kind").c_str()));
+    if (C.i("melbanks", "nbanks_full") != -1 && C.i("melbanks", "nbanks_full") != C.i("melbanks", "nbanks"))
+        return bail(fail(c, PHN_ERR_UNSUPPORTED, "melbanks/nbanks_full other than nbanks is not supported\n"));
     {   // Traps::SetSystem (traps.cpp:572-585)
         const std::string &sy = C.str("posteriors", "system");
         if (sy == "LCRC") c->system = PHN_SYS_LCRC;
@@ -619,6 +628,29 @@ int phn_create(const char *cfg_dir, int device, phn_ctx **out)
             for (int j = 0; j < 16; ++j) dct[k * 16 + j] = cosf(v * ((float)j + 0.5f));
         }
     }
+    c->nparams = c->plp ? c->plp_order + (c->plp_add_c0 ? 1 : 0) : c->nbanks;
+    if (c->plp) {   // PLPCoefs::Init (plp.cpp:38-70): equal-loudness curve, IDFT matrix, liftering window - the reference's float expressions
+        const int nb = c->nbanks, dim = nb + 2, P = c->plp_order;
+        std::vector<float> eql((size_t)nb), idft((size_t)(P + 1) * dim), lift((size_t)P);
+        for (int i = 0; i < nb; ++i) {   // sEqualLaudnessCurve, dspc.h:235-244
+            const float fsq = (mt.f0[i] * mt.f0[i]);
+            const float fsub = fsq / (fsq + 1.6e5f);
+            eql[i] = fsub * fsub * ((fsq + 1.44e6f) / (fsq + 9.61e6f));
+        }
+        const float angle = M_PI / (float)(dim - 1);   // CreateIDFTMatrix, plp.cpp:143-165 (cos on a float is cosf in C++)
+        const float scl = 1.0f / (2.0f * (dim - 1));
+        for (int i = 0; i <= P; ++i) {
+            float *row = idft.data() + (size_t)i * dim;
+            row[0] = 1.0f * scl;
+            for (int j = 1; j < dim - 1; ++j) row[j] = (float)(2.0 * scl * cosf(angle * (float)i * (float)j));
+            row[dim - 1] = scl * cosf(angle * (float)i * (float)(dim - 1));
+        }
+        const int Q = (int)c->plp_lifter;   // sLifteringWindow, dspc.cpp:326-335
+        for (int i = 0; i < P; ++i) lift[i] = 1.0f + 0.5f * Q * sinf(M_PI * (float)(i + 1) / (float)Q);
+        if ((rc = upload(c, &c->d_plp_eql, eql.data(), eql.size()))) return bail(rc);
+        if ((rc = upload(c, &c->d_plp_idft, idft.data(), idft.size()))) return bail(rc);
+        if ((rc = upload(c, &c->d_plp_lift, lift.data(), lift.size()))) return bail(rc);
+    }
     if ((rc = upload(c, &c->tab.hamming, mt.hamming.data(), mt.hamming.size()))) return bail(rc);
     if ((rc = upload(c, &c->tab.coeffs, mt.coeffs.data(), mt.coeffs.size()))) return bail(rc);
     if ((rc = upload(c, &c->tab.banks, mt.banks.data(), mt.banks.size()))) return bail(rc);
@@ -640,7 +672,7 @@ void phn_destroy(phn_ctx *c)
         if (c->vit_stream) cudaStreamSynchronize(c->vit_stream);
         tl_dump(c);
     }
-    phn_ctx::Buf *bufs[] = {&c->d_xb, &c->d_st_hist, &c->d_st_norm, &c->d_st_cnt, &c->d_st_vit, &c->d_st_args, &c->d_win, &c->d_st_labels, &c->d_st_nlab, &c->d_audio, &c->d_byte_off, &c->d_frame_off, &c->d_lab_off, &c->d_mel, &c->d_mean, &c->d_post,
+    phn_ctx::Buf *bufs[] = {&c->d_par, &c->d_xb, &c->d_st_hist, &c->d_st_norm, &c->d_st_cnt, &c->d_st_vit, &c->d_st_args, &c->d_win, &c->d_st_labels, &c->d_st_nlab, &c->d_audio, &c->d_byte_off, &c->d_frame_off, &c->d_lab_off, &c->d_mel, &c->d_mean, &c->d_post,
                             &c->d_rec, &c->d_pen, &c->d_x0, &c->d_x1, &c->d_h, &c->d_xm,
                             &c->d_x0h, &c->d_x1h, &c->d_xmh, &c->d_tile_ctr, &c->d_logp, &c->d_pair_off,
                             &c->slot[0].d_labels, &c->slot[0].d_nlab, &c->slot[0].d_lab_off, &c->slot[0].d_frame_off, &c->slot[0].d_coff, &c->slot[0].d_labels_c,
@@ -657,6 +689,9 @@ void phn_destroy(phn_ctx *c)
         void *ps[] = {d.w1, d.w2, d.b1, d.b2, d.mean, d.dev};
         for (void *q : ps) if (q) cudaFree(q);
     }
+    if (c->d_plp_eql) cudaFree(c->d_plp_eql);
+    if (c->d_plp_idft) cudaFree(c->d_plp_idft);
+    if (c->d_plp_lift) cudaFree(c->d_plp_lift);
     if (c->d_trap_ham) cudaFree(c->d_trap_ham);
     if (c->d_trap_cos) cudaFree(c->d_trap_cos);
     if (c->d_trap_pm) cudaFree(c->d_trap_pm);
@@ -693,7 +728,7 @@ int phn_get_info(const phn_ctx *c, phn_info *o)
     o->vector_step = c->step; o->fft_size = c->mt.N; o->n_phonemes = c->P; o->n_states = c->S;
     o->n_outputs = c->hnet[2].nout; o->band_inputs = c->system == PHN_SYS_LCRC ? c->hnet[0].nin : (c->hband.empty() ? 0 : c->hband[0].nin); o->merger_inputs = c->hnet[2].nin;
     o->hidden = c->system == PHN_SYS_LCRC ? c->hnet[0].nhid : c->hnet[2].nhid; o->sent_mean_norm = c->sent_mean_norm; o->time_pruning = c->hist;
-    o->mlp_mode = c->mlp_mode; o->device = c->device; o->wpenalty = c->wpenalty;
+    o->mlp_mode = c->mlp_mode; o->device = c->device; o->wpenalty = c->wpenalty; o->n_params = c->nparams;
     return PHN_OK;
 }
 
@@ -833,7 +868,7 @@ int phn_fetch_mel(phn_ctx *c, float *mel_out)
 {
     if (!c || !mel_out) return PHN_ERR_ARG;
     PHN_CUDA(c, cudaSetDevice(c->device));
-    PHN_CUDA(c, cudaMemcpyAsync(mel_out, c->d_mel.p, sizeof(float) * c->total_frames * c->nbanks, cudaMemcpyDeviceToHost, c->stream));
+    PHN_CUDA(c, cudaMemcpyAsync(mel_out, c->plp ? c->d_par.p : c->d_mel.p, sizeof(float) * c->total_frames * c->nparams, cudaMemcpyDeviceToHost, c->stream));
     PHN_CUDA(c, cudaStreamSynchronize(c->stream));
     return PHN_OK;
 }
@@ -903,7 +938,7 @@ int phn_mel(phn_ctx *c, const void *audio, const int64_t *byte_off, int n_utt, f
     if (c->total_bytes)
         PHN_CUDA(c, cudaMemcpyAsync(c->d_audio.p, audio, (size_t)c->total_bytes, cudaMemcpyHostToDevice, c->stream));
     c->force_exact_wave = 1;
-    { StageTimer t(c, PHN_K_WAVE); rc = launch_wave(c, c->d_audio.p); }
+    { StageTimer t(c, PHN_K_WAVE); rc = launch_wave(c, c->d_audio.p); if (!rc && c->plp) rc = launch_plp(c); }
     c->force_exact_wave = 0;
     if (rc) return rc;
     return phn_fetch_mel(c, mel_out);
@@ -1116,6 +1151,7 @@ int phn_stream_open(phn_ctx *c, int n_streams)
         return fail(c, PHN_ERR_UNSUPPORTED, "streaming needs a posteriors/bunch_size that divides the trap shift %d; it is %d: the reference's online path "
                                             "then hands warm-up rows to the decoder depending on where bunches fall\n", c->tshift, c->bunch);
     if (c->hist + 1 > 64) return fail(c, PHN_ERR_UNSUPPORTED, "streaming keeps a 64-slot decoder history; decoder/time_pruning is %d\n", c->hist);
+    if (c->plp) return fail(c, PHN_ERR_UNSUPPORTED, "params/kind = plp is a parameterisation for `-t par` only\n");
     if (c->on_var && !c->on_mean) return fail(c, PHN_ERR_ARG, "online normalisation: var_norm without mean_norm (the reference asserts, norm.cpp:152)\n");
     if (c->cfg.str("onlinenorm", "file") != "none") return fail(c, PHN_ERR_UNSUPPORTED, "onlinenorm/file (XML persistence of the estimates) is not supported\n");
     if (c->cfg.b("onlinenorm", "scale_to_gvar")) return fail(c, PHN_ERR_UNSUPPORTED, "onlinenorm/scale_to_gvar is not supported\n");

@@ -435,9 +435,9 @@ struct Runner {
                 return;
             }
             ck(phn_mel(ctx, audio.data(), off.data(), n, nullptr, foff.data()));
-            mel.resize((size_t)foff[n] * info.nbanks);
+            mel.resize((size_t)foff[n] * info.n_params);
             ck(phn_mel(ctx, audio.data(), off.data(), n, mel.data(), foff.data()));
-            if (outf == dfParams) { emit_matrix(jobs, n, mel, foff, info.nbanks); return; }
+            if (outf == dfParams) { emit_matrix(jobs, n, mel, foff, info.n_params); return; }
         } else if (inf == dfParams) {
             mel.swap(mat);
         } else {

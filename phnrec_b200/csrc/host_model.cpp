@@ -152,7 +152,8 @@ void MelTables::build(int nbanks_, int vs_, int step_, int fs_, float lo, float 
     std::vector<float> centre(nbanks + 2);
     const float dmel = (mhi - mlo) / (nbanks + 1);
     float acc = mlo;
-    for (int i = 0; i <= nbanks; ++i) { acc = acc + dmel; centre[i] = acc; }  // repeated addition, dspc.cpp:156-162
+    f0.assign((size_t)nbanks + 1, 0.0f);
+    for (int i = 0; i <= nbanks; ++i) { acc = acc + dmel; centre[i] = acc; f0[i] = 700.0f * (expf(acc / 1127.0f) - 1.0f); }  // repeated addition, dspc.cpp:156-162; Scale_MelToLinear
     centre[nbanks + 1] = INFINITY;
     banks.assign(N2, -1);
     coeffs.assign(N2, 0.0f);

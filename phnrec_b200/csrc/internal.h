@@ -41,6 +41,7 @@ struct MelTables {  // melbanks.cpp:38-70, dspc.cpp:80-225, dspc.h:162-167
     std::vector<int> banks;
     std::vector<int> bank_klo, bank_khi;  // per bank: contiguous bin range that feeds it
     std::vector<double> tw;               // (wr, wi) pairs: stage h=1,2,4..N/2, index m<h at [2*(h-1+m)]
+    std::vector<float> f0;                // centres of the banks in Hz (dspc.cpp:156-162), used by PLP's equal-loudness curve
     void build(int nbanks, int vs, int step, int fs, float lo, float hi);
 };
 
@@ -107,6 +108,10 @@ struct phn_ctx {
     float *d_trap_ham = nullptr, *d_trap_cos = nullptr;
     void *d_trap_pm = nullptr, *d_trap_pd = nullptr;
     int trap_ready = 0;
+    // params/kind = plp (k_plp.cu): `-t par` / phn_mel only
+    int plp = 0, plp_order = 12, plp_add_c0 = 0, nparams = 0;
+    float plp_compress = 0.3333333f, plp_lifter = 22.f, plp_scale = 10.f;
+    float *d_plp_eql = nullptr, *d_plp_idft = nullptr, *d_plp_lift = nullptr;
     int mlp_mode = PHN_MLP_EXACT_FP32;
     void *tc = nullptr;  // tensor-core mode state (k_mlp_tc.cu)
     void *stc_btab = nullptr, *stc_bias = nullptr;   // K-stc tensor-core formulation: constant matrices (k_stc.cu)
@@ -143,6 +148,7 @@ struct phn_ctx {
     Buf d_audio, d_byte_off, d_frame_off, d_lab_off, d_mel, d_mean, d_post, d_rec, d_pen;
     Buf d_x0, d_x1, d_h, d_xm, d_x0h, d_x1h, d_xmh;  // MLP workspace (per frame chunk)
     Buf d_xb;                                        // 1BT / 3BT: [bands][chunk][kp] band-net inputs
+    Buf d_par;                                       // PLP coefficients [F][nparams]
     Buf d_tile_ctr, d_logp;
     // Results of one decoder launch.  Two slots, used alternately: the labels of batch k can be fetched (phn_wait) while
     // batch k+1 is already running (phn_recognize_async).  A slot carries its own copies of the frame / capacity offsets:
@@ -209,6 +215,7 @@ int launch_mlp_exact(phn_ctx *c, int64_t f0, int64_t nf);                  // k_
 // one net of the exact mode: outputs to `post` (linear posteriors) or, when post == nullptr, into the merger's input matrix at
 // column xm_col0 as (+-)sLn(p) with the merger's input normalisation (negate: the 1BT / 3BT systems, traps.cpp:425-427)
 int run_net_exact(phn_ctx *c, const phn::DevNet &n, const float *x, int ldx, int64_t nf, float *post, int ldpost, int xm_col0, int negate);
+int launch_plp(phn_ctx *c);                                                // k_plp.cu: d_mel (raw bank energies) -> d_par
 int launch_trap(phn_ctx *c, int64_t f0, int64_t nf);                        // k_trap.cu: 1BT / 3BT / 1BT_DCT front end
 int launch_mlp_trap(phn_ctx *c, int64_t f0, int64_t nf);                    // k_mlp_exact.cu: their nets
 int launch_mlp_tc(phn_ctx *c, int64_t f0, int64_t nf);                     // k_mlp_tc.cu

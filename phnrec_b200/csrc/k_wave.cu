@@ -31,6 +31,7 @@ struct WaveArgs {
     int fmt, vs, step, N, logN, nbanks;
     float scale, dc_shift, frame_shift, frame_floor, preem;
     int z_mean;
+    int raw_energy;           // 1: bank energies as they are (no logarithm, no frame normalisation): the input of K-plp
     int mel_len;              // k_wave_pair: longest bank range in bins (rows of the filterbank weight table)
     const float *hamming, *coeffs;
     const int *banks, *klo, *khi;
@@ -251,9 +252,12 @@ __global__ void __launch_bounds__(kWaveWarps * 32) k_wave(WaveArgs a)
                 const float v2 = __fmul_rn(s_coef[k], p);
                 acc = __fadd_rn(acc, s_bank[k] == lane ? __fsub_rn(p, v2) : v2);
             }
-            float o = ln_guarded(acc, s_logtab);
-            if (a.frame_shift != 0.0f) o = __fadd_rn(o, a.frame_shift);           // srec.cpp:1594-1620
-            if (a.frame_floor != -9999.9f && o < a.frame_floor) o = a.frame_floor;
+            float o = acc;
+            if (!a.raw_energy) {
+                o = ln_guarded(acc, s_logtab);
+                if (a.frame_shift != 0.0f) o = __fadd_rn(o, a.frame_shift);           // srec.cpp:1594-1620
+                if (a.frame_floor != -9999.9f && o < a.frame_floor) o = a.frame_floor;
+            }
             a.mel[f * a.nbanks + lane] = o;
         }
         __syncwarp();
@@ -624,6 +628,7 @@ int launch_wave(phn_ctx *c, const void *d_audio, int u0, int u1)
     a.fmt = c->fmt; a.vs = c->vs; a.step = c->step; a.N = c->mt.N; a.logN = c->mt.logN; a.nbanks = c->nbanks;
     a.scale = c->scale; a.dc_shift = c->dc_shift; a.frame_shift = c->frame_shift; a.frame_floor = c->frame_floor;
     a.preem = c->preem; a.z_mean = c->z_mean;
+    a.raw_energy = c->plp;
     a.hamming = c->tab.hamming; a.coeffs = c->tab.coeffs; a.banks = c->tab.banks;
     a.klo = c->tab.bank_klo; a.khi = c->tab.bank_khi; a.tw = c->tab.tw;
     a.mel = (float *)c->d_mel.p;

@@ -26,6 +26,7 @@ Outputs
                     (`python tests/golden/make_golden.py online` regenerates only this one.)
   ref_trap_systems.npz  oracle/_ref/phnrec_ref on synthetic model directories of the other TRAPS systems (1BT, 3BT, 1BT_DCT):
                     posteriors and .rec text (`python tests/golden/make_golden.py trap`).
+  ref_plp.npz       PLP coefficients of the reference's PLPCoefs class (`python tests/golden/make_golden.py plp`).
 Nothing in tests/ reads /root/reference at run time; only these files.
 """
 import json
@@ -107,6 +108,52 @@ def online_stream():
     (OUT / "ref_online_stream.json").write_text(json.dumps(out, indent=1))
 
 
+PLP_CASES = [  # (name, model whose [melbanks]/[source] settings are used, config edits incl. the [plp] section, bytes of test.raw)
+    ("cz_default", "PHN_CZ_SPDAT_LCRC_N1500", {"params/kind": "plp"}, 60000),
+    ("cz_order8_c0_nolifter", "PHN_CZ_SPDAT_LCRC_N1500", {"params/kind": "plp", "plp/order": "8", "plp/add_c0": "true", "plp/cep_lifter": "0",
+                                                          "plp/cep_scale": "1", "plp/compress_fact": "0.5"}, 40000),
+    ("en_preem_zmean", "PHN_EN_TIMIT_LCRC_N500", {"params/kind": "plp", "plp/order": "13", "plp/add_c0": "true", "melbanks/preem_coef": "0.97",
+                                                  "melbanks/z_mean_source": "true"}, 100000),
+]
+
+
+def plp():
+    """ref_plp.npz: the reference's PLPCoefs class (plp.cpp, compiled out of the PHNREC_ONLY binary) driven by oracle/_ref/online_ref plp
+    with the [melbanks] / [plp] settings of edited model directories; rows of coefficients."""
+    sys.path.insert(0, str(ROOT / "tests"))
+    from conftest import variant_model_dir  # noqa: E402
+    online_ref = orc.REF_BIN.parent / "online_ref"
+    out = {}
+    with tempfile.TemporaryDirectory() as td:
+        td = Path(td)
+        for name, model, edits, nbytes in PLP_CASES:
+            cfg = variant_model_dir(td / name, model, edits)
+            m = orc.Model(cfg)   # (only to read the settings the way the reference's Init would)
+            cget = lambda sec, var, dflt: next((ln.split("=", 1)[1].strip() for ln in _section((cfg / "config").read_text(), sec) if ln.split("=")[0].strip() == var), dflt)
+            (td / "a.raw").write_bytes((orc.REF_AUDIO / "test.raw").read_bytes()[:nbytes])
+            args = [str(online_ref), "plp", str(td / "a.raw"), str(td / "o.f32"), str(m.fs), str(m.vs), str(m.step), str(m.nbanks),
+                    cget("melbanks", "lower_freq", "0"), cget("melbanks", "higher_freq", "4000"), cget("melbanks", "preem_coef", "0.0"),
+                    "1" if cget("melbanks", "z_mean_source", "false") == "true" else "0", cget("plp", "order", "12"),
+                    cget("plp", "compress_fact", "0.3333333"), cget("plp", "cep_lifter", "22"), cget("plp", "cep_scale", "10"),
+                    "1" if cget("plp", "add_c0", "false") == "true" else "0"]
+            subprocess.run(args, check=True, capture_output=True)
+            np_ = int(cget("plp", "order", "12")) + (1 if cget("plp", "add_c0", "false") == "true" else 0)
+            out[name] = np.fromfile(td / "o.f32", dtype=np.float32).reshape(-1, np_)
+            m.close()
+            print("plp", name, out[name].shape)
+    np.savez_compressed(OUT / "ref_plp.npz", **out)
+
+
+def _section(text, sec):
+    on = False
+    for ln in text.splitlines():
+        st = ln.strip()
+        if st.startswith("["):
+            on = st == f"[{sec}]"
+        elif on and "=" in st:
+            yield st
+
+
 def trap_systems():
     """ref_trap_systems.npz: oracle/_ref/phnrec_ref on SYNTHETIC model directories (tests/conftest.py: synthetic_trap_model)
     for the TRAPS systems no shipped model uses - 1BT, 3BT, 1BT_DCT (traps.cpp:249-283, 413-433): `-t post` + .rec."""
@@ -135,6 +182,10 @@ def main():
     if len(sys.argv) > 1 and sys.argv[1] == "trap":
         trap_systems()
         return
+    if len(sys.argv) > 1 and sys.argv[1] == "plp":
+        plp()
+        return
+    plp()
     trap_systems()
     online_stream()
     labels = {}

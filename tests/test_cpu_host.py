@@ -70,7 +70,7 @@ def test_bad_value_and_bad_notation(tmp_path):
 
 
 def test_out_of_scope_configurations_fail_loudly(tmp_path):
-    for i, (a, b) in enumerate([("system=LCRC", "system=5BT"), ("type=phndec", "type=stkint"), ("kind=fbanks", "kind=plp")]):
+    for i, (a, b) in enumerate([("system=LCRC", "system=5BT"), ("type=phndec", "type=stkint"), ("kind=fbanks", "kind=mfcc")]):
         err = _create_err(_copy_model(tmp_path / str(i), lambda c: c.replace(a, b)))
         assert err.code == 30, (a, b, err)
 

@@ -210,3 +210,20 @@ def test_other_trap_systems_restatement_equals_reference_binary(orc, tmp_path):
         assert np.array_equal(post.view(np.uint32), want.view(np.uint32)), name
         assert orc.format_rec(m.recognize(a), m.phonemes) == str(z[f"rec_{name}"]), name
         m.close()
+
+
+def test_plp_restatement_equals_reference_class(orc, tmp_path):
+    """params/kind = plp (plp.cpp:38-165, dspc.cpp:275-335): the restatement's coefficients are those of the reference's own
+    PLPCoefs class (tests/golden/ref_plp.npz, written by oracle/_ref/online_ref plp), bit for bit - default settings, order 8 with
+    C0 and no lifter, 23 banks at 16 kHz with pre-emphasis and mean removal."""
+    import sys
+    from conftest import GOLDEN, ROOT, audio_bytes, variant_model_dir
+    sys.path.insert(0, str(ROOT / "tests" / "golden"))
+    from make_golden import PLP_CASES
+    z = np.load(GOLDEN / "ref_plp.npz")
+    for name, model, edits, nbytes in PLP_CASES:
+        m = orc.Model(variant_model_dir(tmp_path / name, model, edits))
+        got = m.mel(audio_bytes("test.raw")[:nbytes])
+        assert got.shape == z[name].shape, name
+        assert np.array_equal(got.view(np.uint32), z[name].view(np.uint32)), name
+        m.close()
