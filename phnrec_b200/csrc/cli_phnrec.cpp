@@ -127,6 +127,10 @@ bool load_htk(const std::string &path, std::vector<float> &m, int &rows, int &co
     const int samp_size = (int)((uint32_t)h[8] << 8 | h[9]);
     cols = samp_size / 4;
     if (rows < 0 || cols <= 0) { fclose(f); return false; }
+    {   // the header is not trusted beyond what the file holds (a corrupt row count must not become a huge allocation)
+        struct stat sb;
+        if (fstat(fileno(f), &sb) != 0 || !S_ISREG(sb.st_mode) || (unsigned long long)sb.st_size < 12ull + 4ull * (unsigned long long)rows * cols) { fclose(f); return false; }
+    }
     m.resize((size_t)rows * cols);
     const size_t n = fread(m.data(), 4, m.size(), f);
     fclose(f);
@@ -159,6 +163,7 @@ bool load_bytes(const std::string &path, std::vector<unsigned char> &out)
     if (!f) return false;
     fseek(f, 0, SEEK_END);
     long n = ftell(f);
+    if (n < 0) { fclose(f); return false; }   // a directory, a FIFO: "Can not open waveform file" like the reference's failed read
     fseek(f, 0, SEEK_SET);
     const size_t at = out.size();
     out.resize(at + (size_t)n);
