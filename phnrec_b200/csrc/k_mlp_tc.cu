@@ -306,6 +306,9 @@ __device__ __forceinline__ uint32_t pack_half2(float lo, float hi)
 #ifndef PHN_TC_D1_EARLY   // 1: d1_empty right after the second TMEM load of E1 instead of after its arithmetic (measured: 3.12 against 3.10 ms, not kept)
 #define PHN_TC_D1_EARLY 0
 #endif
+#ifndef PHN_TC_HRING   // 1: H lives in a ring of 16-column quarter slots behind D2 (see "H ring" in the kernel) instead of one 64-column buffer
+#define PHN_TC_HRING 1
+#endif
 #ifndef PHN_TC_RCP4
 #define PHN_TC_RCP4 0
 #endif
@@ -543,6 +546,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs a)
     uint64_t *pw2_full = pw1_full + 4;       // [4] PAIR, CTA 0: the peer's layer-2 weights of chunk n have landed (n & 3)
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(pw2_full + 4);
     volatile int *s_par = reinterpret_cast<volatile int *>(bars + 100);   // [8] loop bounds for the issuer warps (see there)
+    // H ring: the hidden activations of a chunk are four QUARTERS of 16 TMEM columns (32 hidden units as fp16 pairs; quarter j is
+    // written by the epilogue warps of column quarter j and read by layer-2 k-steps 2j, 2j + 1).  Quarter j of chunk g lives in
+    // slot (4 g + j) mod HR of the HR = (256 - N2P) / 16 slots behind D2 (7 for 144 outputs, 6 for 160, 8 for 128, 4 for 192),
+    // and every slot has its own full / free barrier pair: an epilogue warp stores its quarter as soon as THAT slot's previous
+    // reader - two layer-2 MMAs of an earlier chunk - has completed, instead of waiting for the whole of layer 2 of the
+    // previous chunk (one 64-column buffer).  With 7 slots only the warps of quarter 3 ever wait, and only for the first two
+    // MMAs of the previous chunk.
+    constexpr int HR = (256 - N2P) / 16;
+    static_assert(HR >= 4 && HR <= 8, "H ring: 4..8 quarter slots");
+    uint64_t *hq_full = bars + 104;          // [8] the four (PAIR: eight) warps of a quarter have stored it
+    uint64_t *hq_free = bars + 112;          // [8] the two MMAs that read the slot have completed
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr int WARP_TMA = TC_EPI_WARPS, WARP_MMA1 = TC_EPI_WARPS + 1, WARP_MMA2 = TC_EPI_WARPS + 2, EPI0 = 0;
@@ -556,6 +570,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs a)
         constexpr uint32_t EPI_ARRIVALS = PAIR ? 2 * TC_EPI_WARPS : TC_EPI_WARPS;   // PAIR: both CTAs' epilogue warps arrive on CTA 0
         for (int i = 0; i < 2; ++i) { mbar_init(&d1_full[i], 1); mbar_init(&d1_empty[i], EPI_ARRIVALS); }
         mbar_init(h_full, EPI_ARRIVALS); mbar_init(h_empty, 1);
+        for (int i = 0; i < 8; ++i) { mbar_init(&hq_full[i], EPI_ARRIVALS / 4); mbar_init(&hq_free[i], 1); }
         mbar_init(d2_full, 1); mbar_init(d2_empty, EPI_ARRIVALS);
         for (int i = 0; i < 4; ++i) mbar_init(&pw1_full[i], 1);
         for (int i = 0; i < 4; ++i) mbar_init(&pw2_full[i], 1);
@@ -586,7 +601,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs a)
     const uint32_t tmem = *tmem_slot;
     const uint32_t tD1[2] = {tmem, tmem + 128u};
     const uint32_t tD2 = tmem + 256u;
-    const uint32_t tH = tmem + 448u;
+    const uint32_t tH = PHN_TC_HRING ? tmem + 256u + (uint32_t)N2P : tmem + 448u;   // H ring base / the single H buffer
 
     if (warp == WARP_TMA) {
         // ===================================================================== TMA producer
@@ -818,6 +833,37 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs a)
             mbar_wait(&w2c_full[g & 3], (uint32_t)(g >> 2) & 1u);
             if (PAIR) mbar_wait_cluster(&pw2_full[g & 3], (uint32_t)(g >> 2) & 1u);
             if (c2 == 0 && g > 0) { if (PAIR) mbar_wait_cluster(d2_empty, ph_d2_empty); else mbar_wait(d2_empty, ph_d2_empty); ph_d2_empty ^= 1; }
+#if PHN_TC_HRING
+            const uint32_t bar_hqf = smem_u32(hq_free);
+#pragma unroll 1
+            for (int j = 0; j < 4; ++j) {   // quarter j: k-steps 2 j, 2 j + 1 of the chunk (k-block j >> 1 of the W2 chunk)
+                const int lin = 4 * g + j, slot = lin % HR;
+                const uint32_t use = (uint32_t)(lin / HR);
+                if (PAIR) mbar_wait_cluster(&hq_full[slot], use & 1u); else mbar_wait(&hq_full[slot], use & 1u);
+                if (lane == 0 && j == 0) TC_DBG(6, c2);   // first quarter of H + weights there
+                tc_fence_after();
+                const uint32_t b2lo = w2lo + w2s * (W2_ST >> 4) + (uint32_t)(j & 1) * 4u;
+                const uint32_t ta = tH + (uint32_t)slot * 16u;
+                const uint32_t acc0 = (j | c2) ? 1u : 0u;
+                if (leader) {
+                    if (PAIR) {
+                        umma2_f16_ts(tD2, ta, ((uint64_t)kDescHi << 32) | b2lo, idesc2, acc0);
+                        umma2_ts_lo<1>(tD2, ta + 8u, b2lo + 2, idesc2);
+                        tc_commit2_u(bar_hqf + (uint32_t)slot * 8u);
+                        if (j & 1) tc_commit2_u(bar_w2e + w2s * 8u);
+                    } else {
+                        umma_f16_ts(tD2, ta, ((uint64_t)kDescHi << 32) | b2lo, idesc2, acc0);
+                        umma_ts_lo<1>(tD2, ta + 8u, b2lo + 2, idesc2);
+                        tc_commit_u(bar_hqf + (uint32_t)slot * 8u);
+                        if (j & 1) tc_commit_u(bar_w2e + w2s * 8u);
+                    }
+                }
+                __syncwarp();
+                if ((j & 1) && ++w2s == (uint32_t)p_s2) w2s = 0;
+            }
+            if (leader && c2 == p_nch - 1) { if (PAIR) tc_commit2_u(bar_d2f); else tc_commit_u(bar_d2f); }
+            (void)bar_he;
+#else
             if (PAIR) mbar_wait_cluster(h_full, (uint32_t)g & 1u); else mbar_wait(h_full, (uint32_t)g & 1u);
             if (lane == 0) TC_DBG(6, c2);   // H + weights there
             tc_fence_after();
@@ -849,6 +895,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs a)
                 if (PAIR) { tc_commit2_u(bar_he); if (c2 == p_nch - 1) tc_commit2_u(bar_d2f); }   // H goes back to the epilogue warps
                 else      { tc_commit_u(bar_he);  if (c2 == p_nch - 1) tc_commit_u(bar_d2f); }
             }
+#endif
             __syncwarp();
             if (lane == 0) TC_DBG(7, c2);   // issued
             if (++c2 == p_nch) { c2 = 0; tile += tstep; }
@@ -954,6 +1001,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs a)
                 if (lane == 0) signal(&d1_empty[b]);      // (the layer-1 issuer may overwrite this accumulator buffer)
 #endif
                 if (threadIdx.x == EPI0 * 32) TC_DBG(10, c);   // e1: math done
+#if PHN_TC_HRING
+                {
+                    const int lin = 4 * g + cq, slot = lin % HR;
+                    const int use = lin / HR;
+                    if (use > 0) mbar_wait(&hq_free[slot], (uint32_t)(use - 1) & 1u);   // (the slot's previous readers have completed)
+                    if (threadIdx.x == EPI0 * 32) TC_DBG(11, c);   // e1: H slot free
+                    tc_fence_after();
+                    tmem_st16(tH + lane_addr + (uint32_t)slot * 16u, hp);
+                    tmem_st_wait();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) signal(&hq_full[slot]);
+                    (void)first_h; (void)ph_h_empty;
+                }
+#else
                 if (!first_h) { mbar_wait(h_empty, ph_h_empty); ph_h_empty ^= 1; }
                 first_h = false;
                 if (threadIdx.x == EPI0 * 32) TC_DBG(11, c);   // e1: H buffer free
@@ -963,6 +1025,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs a)
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) signal(h_full);
+#endif
                 if (threadIdx.x == EPI0 * 32) TC_DBG(12, c);   // e1: H published
             }
             // ------------------------------------------------------------- E2 stages: soft-max + outputs of tile e2_tile
@@ -1294,7 +1357,7 @@ static int run_net_tc(phn_ctx *c, int which, const uint8_t *x_img, int64_t nf, i
     int xspare = pair && im.KB1 <= 3;
     if (const char *e = getenv("PHNREC_TC_XSPARE")) xspare = atoi(e) != 0 && im.KB1 < 8;
     a.XR = im.KB1 + (xspare ? 1 : 0);
-    const size_t fixed = (size_t)a.XR * TC_BLK + sizeof(float) * (3 * (size_t)im.N2P + 8 * 128) + 112 * 8 + 1024;
+    const size_t fixed = (size_t)a.XR * TC_BLK + sizeof(float) * (3 * (size_t)im.N2P + 8 * 128) + 128 * 8 + 1024;
     const size_t max_smem = 232448;
     // Ring plan.  Both weight streams want two chunks resident (the one being multiplied and the one in flight):
     // W2 ring 4 stages, W1 ring 2 KB1 stages.  When that does not fit (wide merger next to its wide X tile), W2
