@@ -21,6 +21,19 @@ utts = [a[0].tobytes(), a[1].tobytes()[:9002], a[2].tobytes()[:700]]
 rec.set_mlp_mode(pb.MLP_TC_F16)
 print('EN', [len(l) for l in rec.recognize(utts)])
 rec.close()
+# streaming mode (state kernels, windows, resumable decoder) and two batches in flight
+rec = pb.Recognizer('oracle/_ref/models/PHN_CZ_SPDAT_LCRC_N1500', device=0)
+a = open('oracle/_ref/audio/test.raw', 'rb').read()
+rec.stream_open(3)
+n = 0
+for k in range(0, 30000, 3001):
+    last = k + 3001 >= 30000
+    out = rec.stream_push([0, 2], [a[k:k + 3001], a[40000 + k:40000 + k + 2000]], [last, last])
+    n += sum(len(x) for x in out)
+print('stream labels', n)
+rec.set_mlp_mode(pb.MLP_TC_F16)
+print('pipelined', [len(b) for b in rec.recognize_pipelined([[a[:20000], a[:9000]], [a[20000:50000]], [a[:398], a[1000:12000]]])])
+rec.close()
 PY
 timeout 600 compute-sanitizer --tool memcheck --error-exitcode 7 python /tmp/san.py > gpurun_out/sanitize_memcheck.log 2>&1; echo "memcheck rc=$?"
 tail -8 gpurun_out/sanitize_memcheck.log
