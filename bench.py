@@ -163,12 +163,12 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(self.rows), "power_w_max": max(pw) if pw else None}
 
 
-def measured_traffic(frames, mode):
+def measured_traffic(frames, mode, config="cz"):
     """DRAM bytes of the MLP launches of one step from the committed ncu --set full capture (same workload), or None."""
     for name in ("r2_mlp_traffic.json", "r1_mlp_traffic.json"):
         try:
             j = json.loads((ROOT / "profiles" / name).read_text())
-            if int(j.get("frames", -1)) == int(frames) and mode == "tc":
+            if int(j.get("frames", -1)) == int(frames) and mode == "tc" and config == j.get("config", "cz"):
                 return int(j["k_mlp_per_step"]), name
         except Exception:
             pass
@@ -524,7 +524,7 @@ def main():
             line["config"]["value_counts"] = f"audio seconds x {n_pass} decoder passes"
         if mlp_ms > 0:
             ach = frames * flop_per_frame / (mlp_ms * 1e-3) / 1e12
-            traffic, tfile = measured_traffic(frames, mode)
+            traffic, tfile = measured_traffic(frames, mode, args.config)
             pk = peaks["tflops_sustained"] if mode == "tc" else 74.4
             line["roofline"] = {
                 "bound": "tensor" if mode == "tc" else "fp32", "kernel": "K-mlp (3 MLPs per frame)", "achieved": ach, "peak": pk,
