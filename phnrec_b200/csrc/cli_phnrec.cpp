@@ -3,8 +3,9 @@
 // Same switches, same config/model directory, same output files (HTK .rec / MLF labels, HTK
 // parameter and posterior matrices) as phnrec.cpp:113-299 + SpeechRec::ProcessFile*
 // (srec.cpp:1113-1291); the work itself is done by libphnrec_b200 through its C ABI, batching
-// the lines of a file list into ragged GPU batches.  `-a` (live soundcard input) is outside the
-// hot path and reports an error.
+// the lines of a file list into ragged GPU batches.  `-a` (live input) takes raw samples from stdin in
+// the reference's 125 ms blocks through the streaming API and prints the committed labels in the
+// reference's live formats (-f str | strlen | lab).
 #include <cctype>
 #include <cstdarg>
 #include <cstdint>
@@ -499,6 +500,7 @@ int main(int argc, char *argv[])
     const char *config_dir = nullptr, *file_list = nullptr, *input_file = nullptr, *output_file = nullptr;
     const char *output_mlf = nullptr, *wpenalty = nullptr, *wformat = nullptr;
     bool live = false;
+    enum { ofLab, ofStr, ofStrLen } live_fmt = ofStr;   // phnrec.cpp:43-58,123
     int mlp_mode = PHN_MLP_EXACT_FP32;
     Runner R;
 
@@ -537,6 +539,7 @@ int main(int argc, char *argv[])
                     fprintf(stderr, "ERROR: Invalid output format: %s. (can be 'lab', 'str', 'strlen')\n", arg);
                     return 1;
                 }
+                live_fmt = !strcmp(arg, "lab") ? ofLab : !strcmp(arg, "str") ? ofStr : ofStrLen;
                 break;
             case 'v': g_verbose = true; break;
         }
@@ -711,7 +714,54 @@ int main(int argc, char *argv[])
     }
 
     for (auto &t : more_threads) t.join();   // (contexts nobody used: -i only)
-    if (live) die("Live audio input (-a) is outside the GPU hot path of this build\n");
+
+    // -a: live input (phnrec.cpp:261-296 + SpeechRec::RunLive, srec.cpp:1438-1490).  The reference reads a sound card
+    // in blocks of sample_freq / 8 samples and hands each to ProcessOnline; the labels come out of the decoder's
+    // callback as TimePruning commits them (live_callback, phnrec.cpp:71-110).  Here the waveform source is stdin
+    // (raw samples in the context's wave format: `arecord -t raw -f S16_LE -r 8000 | phnrec -c cfg -a`), one stream
+    // of the streaming API takes the blocks, and each push's committed labels are printed in the callback's formats.
+    // End of input ends the utterance the way ProcessOnline(.., last = true) does (tail flush + Decoder::Done); the
+    // reference's loop only stops on a signal and then calls Done() without the tail.
+    if (live) {
+        const int bps = (wformat ? !strcmp(wformat, "alaw") : R.info.wave_format == PHN_WAVE_ALAW) ? 1 : 2;
+        const size_t blk = (size_t)(R.info.sample_freq / 8) * bps;
+        if (blk == 0) die("source/sample_freq is too small for live input\n");
+        R.ck(phn_stream_open(R.ctx, 1));
+        if (atoi(phn_config_get(R.ctx, "onlinenorm", "estim_interval")) != 0)
+            printf("Estimation of normalization parameters, please speak ...\n");
+        std::vector<char> buf(blk);
+        std::vector<phn_label> lab(4096);
+        const int sid = 0;
+        auto emit = [&](int64_t n) {
+            for (int64_t i = 0; i < n; ++i) {
+                const phn_label &l = lab[(size_t)i];
+                const long long start = (long long)l.start * 100000ll, stop = (long long)l.end * 100000ll;
+                const char *word = phn_phoneme(R.ctx, l.phn);
+                switch (live_fmt) {
+                    case ofLab: fprintf(stdout, "%lli %lli %s %f\n", start, stop, word, l.like); break;
+                    case ofStr: fprintf(stdout, " %s\n", word); break;
+                    case ofStrLen: fprintf(stdout, " %s(%d)\n", word, (int)((stop - start) / 100000 + 1)); break;
+                }
+            }
+            if (n) fflush(stdout);   // (a live display: every committed label is visible at once)
+        };
+        auto push = [&](size_t nbytes, int last) {
+            int64_t boff[2] = {0, (int64_t)nbytes}, loff[2] = {0, 0};
+            int rc = phn_stream_push(R.ctx, &sid, 1, buf.data(), boff, &last, lab.data(), (int64_t)lab.size(), loff);
+            if (rc) die("%s", phn_last_error(R.ctx));
+            emit(loff[1]);
+        };
+        for (;;) {   // (a pipe may deliver short reads: fill the block like WFS.read does)
+            size_t got = 0;
+            while (got < blk) {
+                const size_t r = fread(buf.data() + got, 1, blk - got, stdin);
+                if (r == 0) break;
+                got += r;
+            }
+            if (got < blk) { push(got, 1); break; }
+            push(got, 0);
+        }
+    }
     phn_destroy(R.ctx);
     phase("done");
     return 0;

@@ -194,3 +194,41 @@ def test_list_mode_rec_files_and_first_bad_file_like_the_reference(tmp_path):
     assert rr.returncode == 1 and rr.stderr.startswith("ERROR: Can not open waveform file")
     want = {p.name: p.read_text() for p in tmp_path.glob("u*.lab")}
     assert got == want
+
+
+def _live_expected(rec: str, fmt: str) -> str:
+    """live_callback's text (phnrec.cpp:71-110) for the labels of a .rec body (the decoder hands the same start/end/score
+    to the callback and to the label file, phndec.cpp:217-231,281-293)."""
+    out = []
+    for line in rec.splitlines():
+        s, e, w, sc = line.split()
+        s, e = int(s), int(e)
+        out.append({"lab": f"{s} {e} {w} {sc}\n", "str": f" {w}\n", "strlen": f" {w}({(e - s) // 100000 + 1})\n"}[fmt])
+    return "".join(out)
+
+
+@pytest.mark.parametrize("name,fmt", [("cz_2000", "lab"), ("en_odd_len", "strlen"), ("cz_alaw_17_frames", "str"),
+                                      ("cz_mean50", "lab"), ("cz_2000", None)])
+def test_live_mode_prints_the_reference_online_labels(tmp_path, name, fmt):
+    """`phnrec -a`: raw samples on stdin, cut into RunLive's 125 ms blocks (srec.cpp:1450), through the streaming API;
+    the labels must be those of the reference's own online objects (ref_online_stream.json) in live_callback's formats,
+    and the estimation banner appears exactly when onlinenorm/estim_interval != 0 (phnrec.cpp:289-292)."""
+    import os
+    from conftest import audio_bytes, online_case_model_dir
+    case = next(c for c in json.loads((GOLDEN / "ref_online_stream.json").read_text()) if c["name"] == name)
+    cfg = online_case_model_dir(tmp_path, case)
+    a = audio_bytes(case["audio"])[:case["nbytes"]]
+    args = [str(BIN / "phnrec"), "-c", str(cfg), "-a", "-w", case["fmt"]] + (["-f", fmt] if fmt else [])
+    r = subprocess.run(args, input=a, capture_output=True, env=dict(os.environ), timeout=300)
+    assert r.returncode == 0, r.stderr.decode()
+    banner = "Estimation of normalization parameters, please speak ...\n" if case["edits"].get("onlinenorm/estim_interval") else ""
+    assert r.stdout.decode() == banner + _live_expected(case["rec"], fmt or "str")
+
+
+def test_live_mode_empty_input_and_bad_format(tmp_path):
+    import os
+    cfg = model_dir("PHN_CZ_SPDAT_LCRC_N1500")
+    r = subprocess.run([str(BIN / "phnrec"), "-c", str(cfg), "-a"], input=b"", capture_output=True, env=dict(os.environ), timeout=300)
+    assert r.returncode == 0 and r.stdout == b""
+    r = run("phnrec", "-c", cfg, "-a", "-f", "words")
+    assert r.returncode == 1 and "Invalid output format: words" in r.stderr
