@@ -219,6 +219,8 @@ def test_live_mode_prints_the_reference_online_labels(tmp_path, name, fmt):
     cfg = online_case_model_dir(tmp_path, case)
     a = audio_bytes(case["audio"])[:case["nbytes"]]
     args = [str(BIN / "phnrec"), "-c", str(cfg), "-a", "-w", case["fmt"]] + (["-f", fmt] if fmt else [])
+    if case["penalty"] is not None:
+        args += ["-p", str(case["penalty"])]
     r = subprocess.run(args, input=a, capture_output=True, env=dict(os.environ), timeout=300)
     assert r.returncode == 0, r.stderr.decode()
     banner = "Estimation of normalization parameters, please speak ...\n" if case["edits"].get("onlinenorm/estim_interval") else ""
