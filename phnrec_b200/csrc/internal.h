@@ -114,6 +114,7 @@ struct phn_ctx {
     float *d_plp_eql = nullptr, *d_plp_idft = nullptr, *d_plp_lift = nullptr;
     int mlp_mode = PHN_MLP_EXACT_FP32;
     void *tc = nullptr;  // tensor-core mode state (k_mlp_tc.cu)
+    void *wave_tc = nullptr;  // tensor-core front end: DFT matrix image + filterbank tables (k_wave_tc.cu)
     void *stc_btab = nullptr, *stc_bias = nullptr;   // K-stc tensor-core formulation: constant matrices (k_stc.cu)
     void *stc_cf = nullptr, *stc_sb = nullptr;       // K-stc fp32 (FFMA2) form: window x basis table, per-column scale / bias pairs
     int force_exact_wave = 0;
@@ -231,6 +232,10 @@ int launch_stream_decode(phn_ctx *c, int n, int64_t rows, const int64_t *d_row0,
                          const int *d_last, phn::VitStreamState *d_st, phn_label *d_labels, const int64_t *d_lab_off, int *d_nlab);
 int launch_synth(phn_ctx *c, void *d_audio, int64_t bytes_per_utt, int n_utt, uint64_t seed);  // k_synth.cu
 int mlp_tc_fill_merger_bias(phn_ctx *c, int64_t rows);                     // constant-1 bias columns of the merger image
+int wave_tc_prepare(phn_ctx *c);                                           // k_wave_tc.cu
+void wave_tc_release(phn_ctx *c);
+bool wave_tc_applies(phn_ctx *c);
+int launch_wave_tc(phn_ctx *c, const void *d_audio, int64_t f_begin, int64_t f_end);
 int mlp_tc_prepare(phn_ctx *c);                                            // fp16 weight images (k_mlp_tc.cu)
 void mlp_tc_release(phn_ctx *c);
 }  // namespace phn

@@ -1,0 +1,22 @@
+"""K-wave on the tensor cores (k_wave_tc.cu) against the exact front end: ragged A-law batch, max |mel difference|."""
+import sys
+import numpy as np
+sys.path.insert(0, ".")
+sys.path.insert(0, "tests")
+from conftest import model_dir
+import phnrec_b200 as pb
+
+r = pb.Recognizer(model_dir("PHN_CZ_SPDAT_LCRC_N1500"), device=0)
+r.set_wave_format("alaw")
+rng = np.random.default_rng(3)
+a = r.synth_audio(80000, 40, seed=11)
+lens = [80000, 79999, 201, 200, 199, 5, 0, 12345, 64000, 333] + [int(x) for x in rng.integers(150, 80000, 30)]
+utts = [a[i].tobytes()[:n] for i, n in enumerate(lens)]
+exact = np.concatenate(r.mel(utts))
+r.set_mlp_mode(pb.MLP_TC_F16)
+lab = r.recognize(utts)
+fast = r.fetch_mel(exact.shape[0])
+d = np.abs(fast - exact)
+print("frames", exact.shape[0], "finite", bool(np.isfinite(fast).all()), "max |dmel|", float(d.max()), "at", np.unravel_index(d.argmax(), d.shape),
+      "rows >1e-4:", int((d.max(axis=1) > 1e-4).sum()))
+print("labels", sum(len(x) for x in lab))
