@@ -256,7 +256,6 @@ static int prepare_posteriors(phn_ctx *c)
     }
     if (tc) {
         if ((rc = mlp_tc_prepare(c))) return rc;
-        if ((rc = wave_tc_prepare(c))) return rc;
         if (c->fuse_logp && (rc = ensure(c, c->d_logp, sizeof(float) * (size_t)((F + 127) / 128 * 128 + 128) * c->ldp))) return rc;
         if ((rc = ensure(c, c->d_x0h, sizeof(__half) * ch * c->net[0].k1P))) return rc;
         if ((rc = ensure(c, c->d_x1h, sizeof(__half) * ch * c->net[1].k1P))) return rc;

@@ -31,6 +31,7 @@
 #include "tc_ptx.cuh"
 
 #include <cuda_fp16.h>
+#include <algorithm>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -40,18 +41,28 @@ namespace phn {
 
 constexpr int WT_K = 208;                 // window columns fed to the tensor cores (13 k-steps of 16; the window is <= 208)
 constexpr int WT_NBIN = 128;              // bins 0..127 of the 256-point transform
-constexpr int WT_PROD = 8;                // producer warps per CTA
-constexpr int WT_EPI = 4;                 // epilogue warps per CTA (warp = TMEM lane quarter)
+constexpr int WT_PROD = 4;                // producer warps per CTA (32 rows of the tile each)
+constexpr int WT_EPI = 8;                 // epilogue warps per CTA (warp % 4 = TMEM lane quarter, warp / 4 = half of the bins)
 constexpr int WT_THREADS = (WT_EPI + 1 + WT_PROD) * 32;
 constexpr int WT_BLK = 16384;             // [128 rows x 64 fp16], SWIZZLE_128B
 constexpr int WT_BBLK = 7;                // matrix blocks per CTA: 3 hi, 3 lo, 1 shared tail
-constexpr size_t WT_SMEM = (size_t)(WT_BBLK + 2 * 3 + 1) * WT_BLK + 128 + 1024;   // + barriers + alignment slack
+constexpr int WT_HCH = 7;                  // chunks of 16 bins one epilogue half may walk (its weights sit in shared memory)
+constexpr size_t WT_SMEM = (size_t)(WT_BBLK + 2 * 3 + 1) * WT_BLK + 128 + 2 * WT_HCH * 128 + 1024;   // + barriers + filterbank weights + alignment slack
 
-struct WaveTcTab {                        // kernel parameters: read with compile-time offsets from the constant bank
-    float4 wlo[WT_NBIN / 4];              // bin k -> c[k] for bank Banks[k] - 1   (0 when that bank does not exist)
+// The filterbank as one half of the epilogue sees it (kernel parameters: constant bank).  Banks[] (dspc.cpp:236-269) does not
+// decrease with the bin; a half owns a contiguous range of banks and walks the 16-bin chunks that hold their bins.
+struct WaveTcHalf {
+    float4 wlo[WT_NBIN / 4];              // bin k -> c[k] for bank Banks[k] - 1   (0 when that bank is not this half's)
     float4 whi[WT_NBIN / 4];              // bin k -> 1 - c[k] for bank Banks[k]
-    uint32_t shift[WT_NBIN / 32];         // bit k % 32 of word k / 32: Banks[] grows (by one) at bin k, relative to the last bin inside the filterbank
+    uint32_t shift[WT_NBIN / 32];         // bit k: Banks[] grows (by one) at bin k, relative to the last bin inside the filterbank
+    uint32_t emit[WT_NBIN / 32];          // bit k: the bank completed by that step is this half's
+    int c_begin, c_end;                   // chunks of 16 bins
+    int cur0;                             // Banks[] in effect at the first bin of chunk c_begin
+    int flush_lo, flush_hi;               // banks cur - 1 / cur pending after the last chunk are this half's
+    int b_begin, b_end;                   // the half's banks (finished in place after the walk)
+    int z_begin, z_end;                   // banks no bin belongs to (value: ln of silence)
 };
+struct WaveTcTab { WaveTcHalf h[2]; };
 
 struct WaveTcArgs {
     const uint8_t *audio, *audio_end;     // the batch's audio and one past its last byte
@@ -59,29 +70,13 @@ struct WaveTcArgs {
     int n_utt;
     int64_t f_begin, f_end;               // frames of this launch
     int vs, step, nbanks;
+    long long *tl;                        // kernel development (PHNREC_WTC_DBG & 8): clock64() timeline of CTA 0, [role][tile][event]
     int dbg;                              // kernel development (PHNREC_WTC_DBG): 1 producers store zeros, 2 epilogue skips the filterbank, 4 no MMAs
     float frame_shift, frame_floor;
     const uint8_t *w_img;                 // [2 ranks][WT_BBLK][16 KB]
     float *mel;
     WaveTcTab tab;
 };
-
-__device__ __forceinline__ void mbar_arrive_cluster_rel(uint64_t *bar, uint32_t cta)
-{
-    asm volatile("{\n\t.reg .b32 ra;\n\tmapa.shared::cluster.u32 ra, %0, %1;\n\t"
-                 "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(smem_u32(bar)), "r"(cta) : "memory");
-}
-__device__ __forceinline__ void mbar_wait_acq_cluster(uint64_t *bar, uint32_t parity)
-{
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "W_%=:\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra D_%=;\n\t"
-        "bra W_%=;\n\t"
-        "D_%=:\n\t}"
-        ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
 
 // two A-law bytes (bits 0..7 and 16..23 of x) -> half2 bits of 8 * ALawTableD5 (alaw.cpp:14-48, the value alaw8_float of
 // k_wave.cu produces).  With t = byte ^ 0xD5, segment s = t[6:4], mantissa m = t[3:0]: for s >= 1 the value
@@ -106,6 +101,12 @@ __device__ __noinline__ uint3 load3_tail(const uint8_t *p, const uint8_t *end)
     return make_uint3(r[0], r[1], r[2]);
 }
 
+// predicated store: the value is computed whether or not it is stored (no branch around it)
+__device__ __forceinline__ void st_global_if(float *p, float v, bool pred)
+{
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q st.global.f32 [%0], %1;\n\t}" ::"l"(p), "f"(v), "r"((uint32_t)pred) : "memory");
+}
+
 __device__ __forceinline__ float lg2_approx_wt(float x)
 {
     float r;
@@ -123,8 +124,13 @@ __device__ __forceinline__ int find_utt(const int64_t *off, int n, int64_t f)
     return lo;
 }
 
+// DBG: the instantiation with the development switches (a.dbg) and the clock64() timeline; the product kernel carries neither.
+#define WT_TL(role, ev) do { if (DBG && a.tl && blockIdx.x == 0 && lane == 0 && it < 32) a.tl[((role) * 32 + it) * 8 + (ev)] = clock64(); } while (0)
+
+template <bool DBG>
 __global__ void __launch_bounds__(WT_THREADS, 1) k_wave_tc(const __grid_constant__ WaveTcArgs a)
 {
+    const int dbg = DBG ? a.dbg : 0;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t *sB = smem;                                   // WT_BBLK blocks
@@ -138,15 +144,19 @@ __global__ void __launch_bounds__(WT_THREADS, 1) k_wave_tc(const __grid_constant
     uint64_t *b_full = bars + 8;      // this CTA's half of the matrix has landed
     uint64_t *pb_full = bars + 9;     // CTA 0: the peer's has
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 10);
+    float4 *s_w = reinterpret_cast<float4 *>(bars + 16);   // [2 halves][WT_HCH chunks][8]: wlo (4 x float4) then whi of the chunks a half walks
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = blockIdx.x & 1u;
     const int64_t nf = a.f_end - a.f_begin;
-    const int n_units = (int)((nf + 255) / 256), unit0 = (int)(blockIdx.x >> 1), ustep = (int)(gridDim.x >> 1);
-    const int n_my = unit0 < n_units ? (n_units - 1 - unit0) / ustep + 1 : 0;
+    // a cluster walks a contiguous range of 256-frame units: consecutive tiles mostly stay inside one utterance
+    const int64_t n_units = (nf + 255) / 256, ncl = gridDim.x >> 1, cl = blockIdx.x >> 1;
+    const int64_t unit0 = cl * n_units / ncl;
+    const int n_my = (int)((cl + 1) * n_units / ncl - unit0);
     constexpr int WARP_MMA = WT_EPI, PROD0 = WT_EPI + 1;
 
     if (threadIdx.x == 0) {
+        if (DBG && a.tl && blockIdx.x == 0) a.tl[4 * 32 * 8] = clock64();
         for (int i = 0; i < 2; ++i) {
             mbar_init(&a_full[i], 2 * WT_PROD); mbar_init(&a_empty[i], 1);
             mbar_init(&d_full[i], 1); mbar_init(&d_empty[i], 2 * WT_EPI);
@@ -157,6 +167,10 @@ __global__ void __launch_bounds__(WT_THREADS, 1) k_wave_tc(const __grid_constant
     if (warp == WARP_MMA) {
         asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    for (int i = threadIdx.x; i < 2 * WT_HCH * 8; i += blockDim.x) {
+        const int hf = i / (WT_HCH * 8), cl = (i / 8) % WT_HCH, q = i & 7, c = a.tab.h[hf].c_begin + cl;
+        s_w[i] = c < WT_NBIN / 16 ? (q < 4 ? a.tab.h[hf].wlo[4 * c + q] : a.tab.h[hf].whi[4 * c + q - 4]) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
     tc_fence_before();
     __syncthreads();
@@ -174,9 +188,9 @@ __global__ void __launch_bounds__(WT_THREADS, 1) k_wave_tc(const __grid_constant
         __syncwarp();
         mbar_wait(b_full, 0);
         if (rank != 0) {
-            if (lane == 0) mbar_arrive_cluster_rel(pb_full, 0);
+            if (lane == 0) mbar_arrive_cluster(pb_full, 0);
         } else {
-            mbar_wait_acq_cluster(pb_full, 0);
+            mbar_wait_cluster(pb_full, 0);
             constexpr uint32_t idesc = make_idesc(256, false, 256);
             const uint64_t dA = make_sw128_desc(smem_u32(sA)), dB = make_sw128_desc(smem_u32(sB)), dT = make_sw128_desc(smem_u32(sT));
             const uint32_t alo0 = (uint32_t)dA, blo0 = (uint32_t)dB, tlo0 = (uint32_t)dT, hi = (uint32_t)(dA >> 32);
@@ -185,12 +199,15 @@ __global__ void __launch_bounds__(WT_THREADS, 1) k_wave_tc(const __grid_constant
 #pragma unroll 1
             for (int it = 0; it < n_my; ++it) {
                 const uint32_t s = (uint32_t)it & 1u, ph = ((uint32_t)it >> 1) & 1u;
-                mbar_wait_acq_cluster(&a_full[s], ph);
-                if (it >= 2) mbar_wait_acq_cluster(&d_empty[s], ph ^ 1u);
+                WT_TL(0, 0);
+                mbar_wait_cluster(&a_full[s], ph);
+                WT_TL(0, 1);
+                if (it >= 2) mbar_wait_cluster(&d_empty[s], ph ^ 1u);
+                WT_TL(0, 2);
                 tc_fence_after();
                 if (leader) {
                     const uint32_t td = tmem + 256u * s;
-                    if (!(a.dbg & 4)) {
+                    if (!(dbg & 4)) {
                     const uint32_t alo = alo0 + s * (3u * (WT_BLK >> 4));
 #pragma unroll
                     for (int part = 0; part < 2; ++part) {
@@ -211,91 +228,181 @@ __global__ void __launch_bounds__(WT_THREADS, 1) k_wave_tc(const __grid_constant
                     tc_commit2_u(bar_df + 8u * s);
                 }
                 __syncwarp();
+                WT_TL(0, 3);
             }
         }
     } else if (warp >= PROD0) {
         // ===================================================================== producers: audio -> A tile
-        // A warp owns 16 consecutive rows of the tile.  Per tile: lanes 0..15 look up their row's utterance (source byte
-        // offset, samples inside the signal), then the words of 8 rows are requested before the first is decoded - two
-        // memory latencies per tile, not one per row - and the stage is only waited for when the stores begin.
-        constexpr int RPW = 128 / WT_PROD, RG = 8;           // rows per warp and tile; rows per round of loads
+        // A warp owns 32 consecutive rows of the tile (lane = row for the bookkeeping), as four groups of 8.  Row r of a
+        // group starts 10 chunks (80 samples) after row r - 1, so chunk c of row r is chunk c - 10 of row r + 1: a group of
+        // 8 consecutive frames of one utterance has 7 * 10 + 26 = 96 DIFFERENT chunks = three per lane, each decoded once
+        // and stored to the (up to three) rows that contain it.  The words of a group of tile i + 1 are requested as soon as the
+        // same group of tile i has been decoded (its registers are free): a whole tile time passes before they are needed.  Groups that straddle two
+        // utterances, touch the end of the batch's audio or hold an incomplete window go row by row (one in a hundred).
+        constexpr int RPW = 128 / WT_PROD, NG = RPW / 8;
+        static_assert(RPW == 16 || RPW == 32, "rows of a warp on its lanes");
         const int pw = warp - PROD0;
-        const int cb = lane >> 3, cc = lane & 7;             // this lane's chunk: block, 16-byte column inside the block
-        const bool active = lane < WT_K / 8;
+        const int64_t audio_len = a.audio_end - a.audio;
+        const uint32_t abase = (uint32_t)reinterpret_cast<uintptr_t>(a.audio);
+        // this lane's utterance (kept across tiles: the lane's next row is 256 frames further)
         int u = 0;
+        int64_t fo_cur = 0, fo_next = -1, b0 = 0, len = 0;
+        // where this lane's three chunks of a group go: chunk q = lane + 32 i = 10 r + c belongs to row r0 = q / 10 as
+        // column c0 = q % 10, to row r0 - 1 as c0 + 10 and to row r0 - 2 as c0 + 20 (SWIZZLE_128B: 16-byte column XOR
+        // row % 8; the window's tail, columns 24 and 25, lives in the stages' shared block at column 2 s + c - 24).
+        // Shared-memory addresses for stage 0, group 0; 0 = no such row.
+        uint32_t st_addr[3][3];
+        bool st_tail[3][3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const int q = lane + 32 * i, r0 = (q * 205) >> 11, c0 = q - 10 * r0;
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                const int r = r0 - j, c = c0 + 10 * j;
+                const bool ok = r >= 0 && r < 8 && c < WT_K / 8;
+                st_tail[i][j] = c >= 24;
+                const uint32_t blk = c < 24 ? smem_u32(sA) + (uint32_t)(c >> 3) * WT_BLK : smem_u32(sT);
+                st_addr[i][j] = ok ? blk + (uint32_t)(pw * RPW + r) * 128u + ((((uint32_t)c & 7u) ^ (uint32_t)r) << 4) : 0u;
+            }
+        }
+        auto st_shared = [](uint32_t addr, const uint4 &v) {
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+        };
+        auto decode8 = [&](uint32_t w0, uint32_t w1, uint32_t w2, uint32_t sh) {
+            const uint32_t lo = __funnelshift_r(w0, w1, sh), hi = __funnelshift_r(w1, w2, sh);
+            uint4 out;
+            out.x = alaw2_half2(__byte_perm(lo, 0u, 0x4140u));
+            out.y = alaw2_half2(__byte_perm(lo, 0u, 0x4342u));
+            out.z = alaw2_half2(__byte_perm(hi, 0u, 0x4140u));
+            out.w = alaw2_half2(__byte_perm(hi, 0u, 0x4342u));
+            return out;
+        };
+        int64_t soff = 0;
+        int lim = -1;
+        uint32_t seq = 0;
+        uint32_t w[NG][3][3];
+        // row bookkeeping and loads of tile `it`
+        // row bookkeeping of tile `it` -> (bsoff, blim, bseq)
+        int64_t bsoff = 0;
+        int blim = -1;
+        uint32_t bseq = 0;
+        auto book = [&](int it) {
+            const int64_t g = a.f_begin + ((unit0 + it) * 256 + (int64_t)rank * 128) + pw * RPW + (lane & (RPW - 1));   // (RPW = 16: the upper lanes repeat the rows)
+            bsoff = 0; blim = -1;                            // -1: a row past the end of the launch (zeros)
+            if (g < a.f_end && !(dbg & 1)) {
+                if (g >= fo_next) {
+                    // the next utterance, or a search when the row jumped further
+                    if (fo_next >= 0 && u + 2 <= a.n_utt && g < a.frame_off[u + 2]) ++u; else u = find_utt(a.frame_off, a.n_utt, g);
+                    fo_cur = a.frame_off[u]; fo_next = a.frame_off[u + 1];
+                    b0 = a.byte_off[u]; len = a.byte_off[u + 1] - b0;
+                }
+                const int64_t s0 = (g - fo_cur) * a.step, left = len - s0;
+                bsoff = b0 + s0;
+                blim = left < a.vs ? (left < 0 ? 0 : (int)left) : a.vs;   // samples of the window inside the signal
+            }
+            const int64_t so0 = __shfl_sync(0xffffffffu, bsoff, lane & ~7);         // the group's first row
+            const bool in_seq = blim == a.vs && bsoff == so0 + (int64_t)(lane & 7) * 80 && so0 + 8 * 96 + 4 <= audio_len;
+            bseq = __ballot_sync(0xffffffffu, in_seq);
+        };
+        // the words of group gi of the tile whose bookkeeping is in (bsoff, bseq)
+        auto request = [&](int gi) {
+            const int64_t sg = __shfl_sync(0xffffffffu, bsoff, 8 * gi);
+            if (((bseq >> (8 * gi)) & 0xFFu) == 0xFFu) {
+                const uint8_t *p = reinterpret_cast<const uint8_t *>(reinterpret_cast<uintptr_t>(a.audio + sg + 8 * lane) & ~(uintptr_t)3);
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    w[gi][i][0] = __ldg(reinterpret_cast<const unsigned int *>(p + 256 * i));
+                    w[gi][i][1] = __ldg(reinterpret_cast<const unsigned int *>(p + 256 * i + 4));
+                    w[gi][i][2] = __ldg(reinterpret_cast<const unsigned int *>(p + 256 * i + 8));
+                }
+            }
+        };
+        if (n_my > 0) {
+            book(0);
+#pragma unroll
+            for (int gi = 0; gi < NG; ++gi) request(gi);
+        }
 #pragma unroll 1
         for (int it = 0; it < n_my; ++it) {
             const uint32_t s = (uint32_t)it & 1u, ph = ((uint32_t)it >> 1) & 1u;
-            const int64_t g0 = a.f_begin + ((int64_t)(unit0 + it * ustep) * 256 + (int64_t)rank * 128) + pw * RPW;
-            // row info on lanes 0..15
-            int64_t soff = 0;
-            int lim = -1;                                    // -1: a row past the end of the launch (zeros)
-            {
-                const int64_t g = g0 + (lane & (RPW - 1));
-                if (g < a.f_end && !(a.dbg & 1)) {
-                    if (!(a.frame_off[u] <= g && g < a.frame_off[u + 1])) u = find_utt(a.frame_off, a.n_utt, g);
-                    const int64_t b0 = a.byte_off[u], len = a.byte_off[u + 1] - b0;
-                    const int64_t s0 = (g - a.frame_off[u]) * a.step, left = len - s0;
-                    soff = b0 + s0;
-                    lim = left < a.vs ? (left < 0 ? 0 : (int)left) : a.vs;   // samples of the window inside the signal
-                }
-            }
-            // where this lane's chunk of the warp's row 0 goes; a row is 128 bytes further, its chunk index XORed with row % 8
-            uint8_t *base = (cb < 3 ? sA + ((size_t)s * 3 + cb) * WT_BLK : sT) + (size_t)pw * RPW * 128;
-            const uint32_t col = cb < 3 ? (uint32_t)cc : 2u * s + (uint32_t)cc;
-            const uint8_t *lane_src = a.audio + 8 * lane;
-#pragma unroll 1
-            for (int h = 0; h < RPW / RG; ++h) {
-                uint32_t w[RG][3];
+            if (pw == 0) WT_TL(1, 0);
+            soff = bsoff; lim = blim; seq = bseq;            // this tile's rows; then the next tile's, whose words are requested
+            const bool more = it + 1 < n_my;                 // group by group as this tile's registers become free
+            if (more) book(it + 1);
+            if (it >= 2) mbar_wait(&a_empty[s], ph ^ 1u);
+            if (pw == 0) WT_TL(1, 1);
+            const uint32_t s_blk = s * (3u * WT_BLK), s_tail = s * 32u;   // stage 1: three blocks further / tail column XOR 2
 #pragma unroll
-                for (int rr = 0; rr < RG; ++rr) {
-                    const int64_t so = __shfl_sync(0xffffffffu, soff, h * RG + rr);
-                    const int lm = __shfl_sync(0xffffffffu, lim, h * RG + rr);
-                    w[rr][0] = w[rr][1] = w[rr][2] = 0u;
-                    if (active && lm >= 0) {
-                        const uint8_t *p = reinterpret_cast<const uint8_t *>(reinterpret_cast<uintptr_t>(lane_src + so) & ~(uintptr_t)3);
-                        if (p + 12 <= a.audio_end) {
-                            w[rr][0] = __ldg(reinterpret_cast<const unsigned int *>(p));
-                            w[rr][1] = __ldg(reinterpret_cast<const unsigned int *>(p + 4));
-                            w[rr][2] = __ldg(reinterpret_cast<const unsigned int *>(p + 8));
-                        } else {
-                            const uint3 t = load3_tail(p, a.audio_end);
-                            w[rr][0] = t.x; w[rr][1] = t.y; w[rr][2] = t.z;
+            for (int gi = 0; gi < NG; ++gi) {
+                const int64_t sg = __shfl_sync(0xffffffffu, soff, 8 * gi);
+                if (((seq >> (8 * gi)) & 0xFFu) == 0xFFu) {
+                    const uint32_t sh = ((abase + (uint32_t)sg) & 3u) * 8u;
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) {
+                        const uint4 val = decode8(w[gi][i][0], w[gi][i][1], w[gi][i][2], sh);
+#pragma unroll
+                        for (int j = 0; j < 3; ++j)
+                            if (st_addr[i][j])
+                                st_shared((st_tail[i][j] ? st_addr[i][j] ^ s_tail : st_addr[i][j] + s_blk) + (uint32_t)gi * 1024u, val);
+                    }
+                } else {
+                    // row by row: lane = chunk; the eight rows' words are requested before the first is decoded
+                    uint3 t[8];
+                    uint32_t shr[8];
+                    int nn[8];
+#pragma unroll
+                    for (int rr = 0; rr < 8; ++rr) {
+                        const int64_t so = __shfl_sync(0xffffffffu, soff, 8 * gi + rr);
+                        const int lm = __shfl_sync(0xffffffffu, lim, 8 * gi + rr);
+                        nn[rr] = lane < WT_K / 8 ? lm - 8 * lane : 0;   // samples of this chunk inside the signal
+                        t[rr] = make_uint3(0u, 0u, 0u);
+                        const uint8_t *src = a.audio + so + 8 * lane;
+                        const uint8_t *p = reinterpret_cast<const uint8_t *>(reinterpret_cast<uintptr_t>(src) & ~(uintptr_t)3);
+                        shr[rr] = ((uint32_t)reinterpret_cast<uintptr_t>(src) & 3u) * 8u;
+                        if (nn[rr] > 0) {
+                            if (p + 12 <= a.audio_end) {
+                                t[rr].x = __ldg(reinterpret_cast<const unsigned int *>(p));
+                                t[rr].y = __ldg(reinterpret_cast<const unsigned int *>(p + 4));
+                                t[rr].z = __ldg(reinterpret_cast<const unsigned int *>(p + 8));
+                            } else {
+                                t[rr] = load3_tail(p, a.audio_end);
+                            }
                         }
                     }
-                }
-                if (h == 0 && it >= 2) mbar_wait(&a_empty[s], ph ^ 1u);
 #pragma unroll
-                for (int rr = 0; rr < RG; ++rr) {
-                    const int64_t so = __shfl_sync(0xffffffffu, soff, h * RG + rr);
-                    const int lm = __shfl_sync(0xffffffffu, lim, h * RG + rr);
-                    const uint32_t sh = (((uint32_t)reinterpret_cast<uintptr_t>(a.audio) + (uint32_t)so) & 3u) * 8u;   // (8 * lane keeps the alignment)
-                    const uint32_t lo = __funnelshift_r(w[rr][0], w[rr][1], sh), hi = __funnelshift_r(w[rr][1], w[rr][2], sh);
-                    uint4 out;
-                    out.x = alaw2_half2(__byte_perm(lo, 0u, 0x4140u));
-                    out.y = alaw2_half2(__byte_perm(lo, 0u, 0x4342u));
-                    out.z = alaw2_half2(__byte_perm(hi, 0u, 0x4140u));
-                    out.w = alaw2_half2(__byte_perm(hi, 0u, 0x4342u));
-                    if (lm < a.vs) {   // an utterance shorter than one window: zeros beyond the signal (melbanks.cpp:151-170); a row past the end: zeros
-                        const int n = lm - 8 * lane;         // samples of this chunk inside the signal
+                    for (int rr = 0; rr < 8; ++rr) {
+                        uint4 out = decode8(t[rr].x, t[rr].y, t[rr].z, shr[rr]);
+                        const int n = nn[rr];                // zeros beyond the signal (melbanks.cpp:151-170) and in rows past the end
                         uint32_t *o = &out.x;
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
                             if (2 * i >= n) o[i] = 0u;
                             else if (2 * i + 1 >= n) o[i] &= 0x0000FFFFu;
                         }
+                        const int r = 8 * gi + rr, c = lane;
+                        const uint32_t blk = c < 24 ? smem_u32(sA) + s_blk + (uint32_t)(c >> 3) * WT_BLK : smem_u32(sT);
+                        const uint32_t col = c < 24 ? (uint32_t)(c & 7) : 2u * s + (uint32_t)(c & 7);
+                        if (lane < WT_K / 8) st_shared(blk + (uint32_t)(pw * RPW + r) * 128u + ((col ^ ((uint32_t)r & 7u)) << 4), out);
                     }
-                    // (row % 8 = rr: RG = 8 and a group's first row is a multiple of 8)
-                    if (active) *reinterpret_cast<uint4 *>(base + (size_t)(h * RG + rr) * 128 + ((col ^ (uint32_t)rr) << 4)) = out;
                 }
+                if (more) request(gi);
             }
+            if (pw == 0) WT_TL(1, 2);
             fence_proxy_async();
             __syncwarp();
-            if (lane == 0) mbar_arrive_cluster_rel(&a_full[s], 0);
+            if (lane == 0) mbar_arrive_cluster(&a_full[s], 0);
+            if (pw == 0) WT_TL(1, 3);
         }
     } else {
         // ===================================================================== epilogue: |Z|^2 -> filterbank -> ln -> mel
-        const int nb = a.nbanks;
+        // thread = frame (TMEM lane), two warps per lane quarter: each `half` owns a range of banks and walks the chunks of
+        // 16 bins that hold them.  Bank `cur` collects (1 - c) P from the bins with Banks = cur (acc_hi) and bank cur - 1
+        // collects c P from the same bins (acc_lo); where Banks moves on, bank cur - 1 is complete.  No branch in the walk (a
+        // lone warp pays tens of clocks for each): the logarithm is taken at every bin and stored under a predicate.
+        const int qd = warp & 3, half = warp >> 2;
+        const WaveTcHalf &tb = a.tab.h[half];
+        const float4 *sw = s_w + half * WT_HCH * 8;
+        const int nb = a.nbanks, c_begin = tb.c_begin, c_end = tb.c_end;
         const float fl_eff = a.frame_floor != -9999.9f ? a.frame_floor : -INFINITY;   // srec.cpp:1594-1620 (floor switched off: -9999.9)
         // one finished bank: sLn (dspc.h:155-160: ln, digital silence -> 0) as lg2.approx * ln 2, then the frame normalisation
         auto finish = [&](float acc) {
@@ -305,58 +412,72 @@ __global__ void __launch_bounds__(WT_THREADS, 1) k_wave_tc(const __grid_constant
 #pragma unroll 1
         for (int it = 0; it < n_my; ++it) {
             const uint32_t s = (uint32_t)it & 1u, ph = ((uint32_t)it >> 1) & 1u;
-            const int64_t g = a.f_begin + ((int64_t)(unit0 + it * ustep) * 256 + (int64_t)rank * 128 + warp * 32 + lane);
+            const int64_t g = a.f_begin + ((unit0 + it) * 256 + (int64_t)rank * 128 + qd * 32 + lane);
             const bool live = g < a.f_end;
             float *dst = a.mel + (live ? g : a.f_begin) * nb;
-            mbar_wait(&d_full[s], ph);
-            tc_fence_after();
-            const uint32_t tbase = tmem + 256u * s + ((uint32_t)(warp * 32) << 16);
-            // Banks[] (dspc.cpp:236-269) does not decrease with the bin: bank `cur` collects (1 - c) P from the bins with
-            // Banks = cur (acc_hi) and bank cur - 1 collects c P from the same bins (acc_lo); when Banks moves on - at most one
-            // step per bin, wave_tc_prepare checks - bank cur - 1 is complete.  The tables are kernel parameters (constant bank).
             float acc_lo = 0.0f, acc_hi = 0.0f;
-            int cur = 0;
-            uint32_t v0[32], v1[32];
-            auto bins16 = [&](const uint32_t *v, int c2, int half) {   // bins 32 c2 + 16 half + (0..15)
-                const uint32_t mask = a.tab.shift[c2] >> (16 * half);
+            float *p = dst + tb.cur0 - 1;                    // where bank cur - 1 goes
+            uint32_t v0[32];
+            auto bins16 = [&](const uint32_t *v, int c) {    // bins 16 c + (0..15)
+                const uint32_t sm = tb.shift[c >> 1] >> (16 * (c & 1)), em = live ? tb.emit[c >> 1] >> (16 * (c & 1)) : 0u;
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                    const float4 l4 = a.tab.wlo[8 * c2 + 4 * half + q], h4 = a.tab.whi[8 * c2 + 4 * half + q];
+                    const float4 l4 = sw[8 * (c - c_begin) + q], h4 = sw[8 * (c - c_begin) + 4 + q];
                     const float lw[4] = {l4.x, l4.y, l4.z, l4.w}, hw[4] = {h4.x, h4.y, h4.z, h4.w};
+                    if (((sm >> (4 * q)) & 0xFu) == 0u) {    // (uniform) Banks[] constant over these four bins: accumulate only
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const int i = 4 * q + j;
-                        const float re = __uint_as_float(v[2 * i]), im = __uint_as_float(v[2 * i + 1]);
-                        const float pwr = fmaf(im, im, re * re);  // cPower (dspc.h:141-146)
-                        if (mask & (1u << i)) {
-                            if (live && cur >= 1 && cur <= nb) dst[cur - 1] = finish(acc_lo);
-                            acc_lo = acc_hi; acc_hi = 0.0f; ++cur;
+                        for (int j = 0; j < 4; ++j) {
+                            const int i = 4 * q + j;
+                            const float re = __uint_as_float(v[2 * i]), im = __uint_as_float(v[2 * i + 1]);
+                            const float pwr = fmaf(im, im, re * re);  // cPower (dspc.h:141-146)
+                            acc_lo = fmaf(pwr, lw[j], acc_lo);
+                            acc_hi = fmaf(pwr, hw[j], acc_hi);
                         }
-                        acc_lo = fmaf(pwr, lw[j], acc_lo);
-                        acc_hi = fmaf(pwr, hw[j], acc_hi);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const int i = 4 * q + j;
+                            const float re = __uint_as_float(v[2 * i]), im = __uint_as_float(v[2 * i + 1]);
+                            const float pwr = fmaf(im, im, re * re);
+                            const bool sh = (sm >> i) & 1u, st = (em >> i) & 1u;
+                            st_global_if(p, finish(acc_lo), st);
+                            acc_lo = sh ? acc_hi : acc_lo;
+                            acc_hi = sh ? 0.0f : acc_hi;
+                            p += sh ? 1 : 0;
+                            acc_lo = fmaf(pwr, lw[j], acc_lo);
+                            acc_hi = fmaf(pwr, hw[j], acc_hi);
+                        }
                     }
                 }
             };
-            tmem_ld32(tbase, v0);
+            if (qd == 0) WT_TL(2 + half, 0);
+            mbar_wait(&d_full[s], ph);
+            if (qd == 0) WT_TL(2 + half, 1);
+            tc_fence_after();
+            const uint32_t tbase = tmem + 256u * s + ((uint32_t)(qd * 32) << 16);
 #pragma unroll 1
-            for (int c2 = 0; c2 < 4; ++c2) {                 // 32 bins per round: the code stays small (tables at run-time offsets)
+            for (int c = c_begin; c < c_end; ++c) {          // (one chunk in registers at a time: 17 warps share the register file)
+                tmem_ld32(tbase + 32u * (uint32_t)c, v0);
                 tmem_ld_wait();
-                tmem_ld32(tbase + 64u * (uint32_t)c2 + 32u, v1);
-                if (!(a.dbg & 2)) bins16(v0, c2, 0);
-                tmem_ld_wait();
-                if (c2 < 3) tmem_ld32(tbase + 64u * (uint32_t)c2 + 64u, v0);
-                else {                                       // the accumulator is in registers: hand it back
+                if (qd == 0) WT_TL(2 + half, 2 + (c - c_begin));
+                if (c + 1 >= c_end) {                        // the half's part of the accumulator is in registers: hand it back
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive_cluster_rel(&d_empty[s], 0);
+                    if (lane == 0) mbar_arrive_cluster(&d_empty[s], 0);
                 }
-                if (!(a.dbg & 2)) bins16(v1, c2, 1);
+                if (!(dbg & 2)) bins16(v0, c);
+            }
+            if (c_begin >= c_end) {                          // (a half without banks)
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(&d_empty[s], 0);
             }
             if (live) {
-                if (cur >= 1 && cur <= nb) dst[cur - 1] = finish(acc_lo);
-                if (cur < nb) dst[cur] = finish(acc_hi);
-                for (int b = cur + 1; b < nb; ++b) dst[b] = finish(0.0f);
+                if (tb.flush_lo) p[0] = finish(acc_lo);
+                if (tb.flush_hi) p[1] = finish(acc_hi);
+                for (int b = tb.z_begin; b < tb.z_end; ++b) dst[b] = finish(0.0f);
             }
+            if (qd == 0) WT_TL(2 + half, 7);
         }
     }
 
@@ -380,7 +501,7 @@ struct WaveTcState {
 
 static bool wave_tc_fits(const phn_ctx *c)
 {
-    return c->mt.logN == 8 && c->vs <= WT_K && c->nbanks >= 1 && c->nbanks <= 64 && !c->plp && !c->z_mean && c->preem == 0.0f;
+    return c->mt.logN == 8 && c->vs <= WT_K && c->step == 80 && c->nbanks >= 1 && c->nbanks <= 64 && !c->plp && !c->z_mean && c->preem == 0.0f;
 }
 
 // The windowed DFT matrix as the two CTAs' shared-memory images, and the filterbank tables.
@@ -413,17 +534,110 @@ int wave_tc_prepare(phn_ctx *c)
     }
     PHN_CUDA(c, cudaMalloc((void **)&st->w_img, img.size()));
     PHN_CUDA(c, cudaMemcpy(st->w_img, img.data(), img.size(), cudaMemcpyHostToDevice));
-    int prev = 0;
+    // Filterbank tables.  Banks[] must grow by single steps (no bank narrower than a bin), else the FFT kernels serve the model.
     memset(&st->tab, 0, sizeof(st->tab));
-    for (int k = 0; k < WT_NBIN; ++k) {
-        const int sgm = mt.banks[k];
-        if (sgm < 0) continue;
-        if (sgm < prev || sgm - prev > 1) return PHN_OK;     // banks narrower than a bin: the FFT kernels serve this model
-        if (sgm > prev) st->tab.shift[k >> 5] |= 1u << (k & 31);
-        prev = sgm;
-        if (sgm >= 1 && sgm <= mt.nbanks) (&st->tab.wlo[k >> 2].x)[k & 3] = mt.coeffs[k];
-        if (sgm < mt.nbanks) (&st->tab.whi[k >> 2].x)[k & 3] = 1.0f - mt.coeffs[k];
+    const int nb = mt.nbanks;
+    std::vector<int> sh(WT_NBIN, 0), cur_at(WT_NBIN + 1, 0);   // shift at bin k; Banks[] in effect before bin k
+    {
+        int prev = 0;
+        for (int k = 0; k < WT_NBIN; ++k) {
+            cur_at[k] = prev;
+            const int sgm = mt.banks[k];
+            if (sgm >= 0) {
+                if (sgm < prev || sgm - prev > 1) return PHN_OK;
+                sh[k] = sgm - prev;
+                prev = sgm;
+            }
+        }
+        cur_at[WT_NBIN] = prev;
     }
+    auto bin_lo_w = [&](int k) { const int sgm = mt.banks[k]; return sgm >= 1 && sgm <= nb ? mt.coeffs[k] : 0.0f; };         // -> bank sgm - 1
+    auto bin_hi_w = [&](int k) { const int sgm = mt.banks[k]; return sgm >= 0 && sgm < nb ? 1.0f - mt.coeffs[k] : 0.0f; };   // -> bank sgm
+    // the half that owns banks [bb, be): tables, chunk range, pending banks; false if it cannot be expressed
+    auto build_half = [&](WaveTcHalf &h, int bb, int be) {
+        memset(&h, 0, sizeof(h));
+        h.b_begin = bb; h.b_end = be;
+        int kmin = WT_NBIN, kmax = -1;
+        for (int k = 0; k < WT_NBIN; ++k) {
+            const int sgm = mt.banks[k];
+            if (sgm < 0) continue;
+            const float wl = (sgm - 1 >= bb && sgm - 1 < be) ? bin_lo_w(k) : 0.0f, wh = (sgm >= bb && sgm < be) ? bin_hi_w(k) : 0.0f;
+            (&h.wlo[k >> 2].x)[k & 3] = wl;
+            (&h.whi[k >> 2].x)[k & 3] = wh;
+            if (sgm - 1 >= bb && sgm - 1 < be) { kmin = std::min(kmin, k); kmax = std::max(kmax, k); }
+            if (sgm >= bb && sgm < be) { kmin = std::min(kmin, k); kmax = std::max(kmax, k); }
+        }
+        if (kmax < 0) { h.c_begin = h.c_end = 0; h.z_begin = bb; h.z_end = be; h.b_begin = h.b_end = 0; return; }
+        h.c_begin = kmin / 16; h.c_end = kmax / 16 + 1;
+        h.cur0 = cur_at[16 * h.c_begin];
+        int cur = h.cur0;
+        std::vector<char> stored(nb + 2, 0);
+        for (int k = 16 * h.c_begin; k < 16 * h.c_end; ++k) {
+            if (!sh[k]) continue;
+            h.shift[k >> 5] |= 1u << (k & 31);
+            const int b = cur - 1;
+            if (b >= bb && b < be) { h.emit[k >> 5] |= 1u << (k & 31); stored[b] = 1; }
+            ++cur;
+        }
+        h.flush_lo = cur - 1 >= bb && cur - 1 < be;
+        h.flush_hi = cur >= bb && cur < be;
+        if (h.flush_lo) stored[cur - 1] = 1;
+        if (h.flush_hi) stored[cur] = 1;
+        // banks of the range that no bin reaches (below the first / above the last filter): one contiguous run at either end
+        int zb = bb, ze = bb;
+        for (int b = bb; b < be; ++b)
+            if (!stored[b]) { if (ze == zb) zb = b; ze = b + 1; }
+        h.z_begin = zb; h.z_end = ze;
+        // (finishing in place covers the stored banks only)
+        int fb = be, fe = bb;
+        for (int b = bb; b < be; ++b)
+            if (stored[b]) { fb = std::min(fb, b); fe = std::max(fe, b + 1); }
+        h.b_begin = fb; h.b_end = fe > fb ? fe : fb;
+    };
+    // replay of the device walk on a test spectrum against the filterbank's definition
+    auto check_half = [&](const WaveTcHalf &h, int bb, int be) {
+        std::vector<double> P(WT_NBIN), want(nb, 0.0), got(nb, -1.0);
+        for (int k = 0; k < WT_NBIN; ++k) P[k] = 1.0 + 0.37 * k + (k % 7) * 0.11;
+        for (int k = 0; k < WT_NBIN; ++k) {
+            const int sgm = mt.banks[k];
+            if (sgm < 0) continue;
+            if (sgm >= 1 && sgm <= nb) want[sgm - 1] += (double)bin_lo_w(k) * P[k];
+            if (sgm < nb) want[sgm] += (double)bin_hi_w(k) * P[k];
+        }
+        double lo = 0.0, hi = 0.0;
+        int p = h.cur0 - 1;
+        for (int k = 16 * h.c_begin; k < 16 * h.c_end; ++k) {
+            const bool s1 = (h.shift[k >> 5] >> (k & 31)) & 1u, e1 = (h.emit[k >> 5] >> (k & 31)) & 1u;
+            if (e1) { if (p < 0 || p >= nb) return false; got[p] = lo; }
+            if (s1) { lo = hi; hi = 0.0; ++p; }
+            lo += (double)(&h.wlo[k >> 2].x)[k & 3] * P[k];
+            hi += (double)(&h.whi[k >> 2].x)[k & 3] * P[k];
+        }
+        if (h.flush_lo) { if (p < 0 || p >= nb) return false; got[p] = lo; }
+        if (h.flush_hi) { if (p + 1 < 0 || p + 1 >= nb) return false; got[p + 1] = hi; }
+        for (int b = h.z_begin; b < h.z_end; ++b) got[b] = 0.0;
+        for (int b = bb; b < be; ++b)
+            if (fabs(got[b] - want[b]) > 1e-9 * (1.0 + fabs(want[b]))) return false;
+        for (int b = h.b_begin; b < h.b_end; ++b)
+            if (got[b] < 0.0) return false;      // (a bank inside the finishing range that was never stored)
+        for (int b = h.z_begin; b < h.z_end; ++b)
+            if (b >= h.b_begin && b < h.b_end) return false;
+        return true;
+    };
+    // split the banks where the two halves walk about the same number of chunks
+    int best = -1, best_cost = 1 << 30;
+    for (int split = 0; split <= nb; ++split) {
+        WaveTcHalf h0, h1;
+        build_half(h0, 0, split);
+        build_half(h1, split, nb);
+        if (!check_half(h0, 0, split) || !check_half(h1, split, nb)) continue;
+        const int cost = std::max(h0.c_end - h0.c_begin, h1.c_end - h1.c_begin);
+        if (cost > WT_HCH) continue;
+        if (cost < best_cost) { best_cost = cost; best = split; }
+    }
+    if (best < 0) return PHN_OK;
+    build_half(st->tab.h[0], 0, best);
+    build_half(st->tab.h[1], best, nb);
     st->ok = true;
     return PHN_OK;
 }
@@ -459,9 +673,17 @@ int launch_wave_tc(phn_ctx *c, const void *d_audio, int64_t f_begin, int64_t f_e
     a.tab = st->tab;
     static const int dbg = getenv("PHNREC_WTC_DBG") ? atoi(getenv("PHNREC_WTC_DBG")) : 0;
     a.dbg = dbg;
+    a.tl = nullptr;
+    static long long *d_tl = nullptr;
+    if (dbg & 8) {
+        if (!d_tl) PHN_CUDA(c, cudaMalloc((void **)&d_tl, sizeof(long long) * (4 * 32 * 8 + 8)));
+        PHN_CUDA(c, cudaMemsetAsync(d_tl, 0, sizeof(long long) * (4 * 32 * 8 + 8), c->stream));
+        a.tl = d_tl;
+    }
+    auto kern = dbg ? k_wave_tc<true> : k_wave_tc<false>;
     static bool attr_set = false;
     if (!attr_set) {
-        PHN_CUDA(c, cudaFuncSetAttribute(k_wave_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WT_SMEM));
+        PHN_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WT_SMEM));
         attr_set = true;
     }
     const int64_t units = (f_end - f_begin + 255) / 256;
@@ -473,8 +695,24 @@ int launch_wave_tc(phn_ctx *c, const void *d_audio, int64_t f_begin, int64_t f_e
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    PHN_CUDA(c, cudaLaunchKernelEx(&cfg, k_wave_tc, a));
+    PHN_CUDA(c, cudaLaunchKernelEx(&cfg, kern, a));
     PHN_CUDA(c, cudaGetLastError());
+    if (a.tl) {   // print the timeline of tiles 8..15 (clocks relative to the first event of tile 8)
+        std::vector<long long> h(4 * 32 * 8 + 8);
+        PHN_CUDA(c, cudaStreamSynchronize(c->stream));
+        PHN_CUDA(c, cudaMemcpy(h.data(), d_tl, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost));
+        const char *names[4] = {"mma", "prod", "epi_lo", "epi_hi"};
+        const long long t0 = h[(0 * 32 + 8) * 8];
+        fprintf(stderr, "wtc kernel start %lld; mma issue-done per tile:", h[4 * 32 * 8] - t0);
+        for (int it = 0; it < 32; ++it) fprintf(stderr, " %lld", h[(0 * 32 + it) * 8 + 3] - t0);
+        fprintf(stderr, "\n");
+        for (int it = 8; it < 16; ++it)
+            for (int r = 0; r < 4; ++r) {
+                fprintf(stderr, "wtc tile %2d %-6s", it, names[r]);
+                for (int e = 0; e < 8; ++e) fprintf(stderr, " %8lld", h[(r * 32 + it) * 8 + e] ? h[(r * 32 + it) * 8 + e] - t0 : -1);
+                fprintf(stderr, "\n");
+            }
+    }
     return PHN_OK;
 }
 

@@ -214,3 +214,53 @@ def test_tc_fused_path_is_batch_invariant(recs):
         single = r.recognize([u])[0]
         assert np.array_equal(single.view(np.uint8), b.view(np.uint8))
         assert np.array_equal(single.view(np.uint8), v.view(np.uint8))
+
+
+TC_DFT_MEL_ABS = 3e-5   # DFT on the tensor cores (k_wave_tc.cu) vs the reference's bits; observed 6.7e-6 (ln energies ~ 10..25)
+
+
+def test_tc_dft_front_end_ragged_alaw_batch(recs):
+    """The 8 kHz A-law front end of the tensor-core pipeline is a GEMM (k_wave_tc.cu: samples exact in fp16, the windowed DFT
+    matrix as hi + lo, fp32 accumulators): ln mel-bank energies against phn_mel (the reference's bits) on a ragged batch
+    that exercises every producer path - whole windows inside one utterance (chunks shared between rows), groups of
+    rows that straddle two utterances, utterances of exactly one window, shorter than a window (zeros beyond the signal,
+    melbanks.cpp:151-170), of a few bytes and of none, the last bytes of the audio buffer - and tiles that end inside
+    the batch; the decoded labels must equal those of the same pipeline run with the register-FFT front end."""
+    r = recs("PHN_CZ_SPDAT_LCRC_N1500")
+    r.set_wave_format("alaw")
+    try:
+        rng = np.random.default_rng(3)
+        a = r.synth_audio(80000, 40, seed=11)
+        lens = [80000, 79999, 201, 200, 199, 5, 0, 12345, 64000, 333, 280, 281, 1000] + [int(x) for x in rng.integers(150, 80000, 27)]
+        utts = [a[i].tobytes()[:n] for i, n in enumerate(lens)]
+        exact = np.concatenate(r.mel(utts))
+        lab = r.recognize(utts)
+        fast = r.fetch_mel(exact.shape[0])
+        assert np.isfinite(fast).all()
+        d = np.abs(fast - exact)
+        assert d.max() <= TC_DFT_MEL_ABS, (d.max(), np.unravel_index(d.argmax(), d.shape))
+        # one utterance at a time: other tile positions, every utterance at the end of its buffer
+        for i in (0, 2, 4, 5, 7, 12):
+            one = r.recognize([utts[i]])
+            m1 = r.fetch_mel(r.num_frames(len(utts[i])))
+            assert np.abs(m1 - r.mel([utts[i]])[0]).max() <= TC_DFT_MEL_ABS, i
+            assert np.array_equal(one[0].view(np.uint8), lab[i].view(np.uint8)), i
+    finally:
+        r.set_wave_format("lin16")
+
+
+def test_tc_dft_front_end_switch_gives_the_same_labels(tmp_path):
+    """PHNREC_WAVE_TC=0 keeps the register-FFT front end in the tensor-core pipeline: both front ends are within 1e-4 of
+    the reference's mel values, so the decoded label file of the shipped test utterance must not change."""
+    import os
+    import subprocess
+    from conftest import AUDIO, ROOT
+    out = {}
+    for sw in ("0", "1"):
+        env = dict(os.environ, PHNREC_MLP="tc", PHNREC_WAVE_TC=sw)
+        o = tmp_path / f"o{sw}.rec"
+        p = subprocess.run([str(ROOT / "phnrec_b200" / "bin" / "phnrec"), "-c", str(model_dir("PHN_CZ_SPDAT_LCRC_N1500")), "-w", "alaw",
+                            "-i", str(AUDIO / "test.raw"), "-o", str(o)], capture_output=True, text=True, env=env, timeout=300)
+        assert p.returncode == 0, p.stderr
+        out[sw] = [ln.split()[:3] for ln in o.read_text().splitlines()]
+    assert out["0"] == out["1"]
