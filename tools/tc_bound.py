@@ -3,7 +3,7 @@
 
 Same synthetic audio as bench.py (device generator, seed 1000 + rank 0), whole utterances through BOTH modes of the library:
   exact  : fp32 CUDA-core path, bit-identical to the reference binary (tests/test_gpu_parity.py)
-  tc     : the fused audio -> labels path bench.py times (fp32 pair-FFT front end, tensor-core K-stc features, tcgen05
+  tc     : the fused audio -> labels path bench.py times (DFT on the tensor cores for 8 kHz A-law, else the fp32 pair-FFT front end; fp16 K-stc features, tcgen05
            fp16 nets, ln p from the merger's epilogue)
 and compares, over EVERY frame,
   * ln p as the decoder consumed it (phn_fetch_logp, the 3P decoder-visible columns):
@@ -54,6 +54,8 @@ def measure(rec, pb, utts, chunk=250):
     hist_edges = np.concatenate([[0.0], np.logspace(-7, 1, 161)])
     hist = np.zeros(len(hist_edges) - 1, dtype=np.int64)
     mx_in = 0.0            # max over the frames that are not outliers (below)
+    n_uniform = 0
+    out_vals = []
     outlier_frames = []    # frames with a value beyond OUTLIER: the reference's undefined zone, see the module docstring
     inf_mismatch = 0
     argmax_same = frames = 0
@@ -79,6 +81,9 @@ def measure(rec, pb, utts, chunk=250):
         rowmax = mf.max(1)
         bad_rows = np.where(rowmax > OUTLIER)[0]
         outlier_frames += [int(frames + r) for r in bad_rows]
+        # is the EXACT mode's row the degenerate (uniform) soft-max of the reference's overflow zone?
+        n_uniform += int(sum(float(lp_ex[r].max() - lp_ex[r].min()) < 1e-4 for r in bad_rows))
+        out_vals += [float(rowmax[r]) for r in bad_rows]
         if (rowmax <= OUTLIER).any():
             mx_in = max(mx_in, float(rowmax[rowmax <= OUTLIER].max()))
         n_val += m.size
@@ -108,6 +113,7 @@ def measure(rec, pb, utts, chunk=250):
     return {
         "utterances": n_utt, "frames": int(frames), "values": int(n_val),
         "rel_logp_max": mx, "rel_logp_max_excl_outlier_frames": mx_in, "outlier_frames": outlier_frames[:50], "n_outlier_frames": len(outlier_frames),
+        "n_outlier_frames_where_exact_mode_is_uniform": n_uniform, "outlier_values_sorted": sorted(out_vals)[:50],
         "rel_logp_p999": quant(0.999), "rel_logp_p99": quant(0.99), "rel_logp_mean": s_sum / max(n_val, 1),
         "inf_mismatch": inf_mismatch,
         "frame_argmax_agree": argmax_same / max(frames, 1),
