@@ -42,3 +42,9 @@ tail -5 gpurun_out/sanitize_racecheck_wave.log
 # the same batch with one CTA pair for all tiles: several tiles per CTA, so the activation ring of the MLP kernel wraps
 PHNREC_TC_GRID=2 timeout 600 compute-sanitizer --tool memcheck --error-exitcode 7 python /tmp/san.py > gpurun_out/sanitize_memcheck_grid2.log 2>&1; echo "memcheck (one pair) rc=$?"
 tail -6 gpurun_out/sanitize_memcheck_grid2.log
+# the tensor-core front end: shared-memory hazards between its roles (racecheck sees generic-proxy accesses), and
+# memcheck + initcheck of a batch whose last utterances end at the very end of the audio buffer
+timeout 400 compute-sanitizer --tool racecheck --error-exitcode 7 --kernel-regex kns=k_wave_tc python /tmp/san.py > gpurun_out/sanitize_racecheck_wave_tc.log 2>&1; echo "racecheck k_wave_tc rc=$?"
+tail -5 gpurun_out/sanitize_racecheck_wave_tc.log
+timeout 400 compute-sanitizer --tool memcheck --error-exitcode 7 python tools/wave_tc_check.py > gpurun_out/sanitize_memcheck_wave_tc.log 2>&1; echo "memcheck wave_tc_check rc=$?"
+tail -6 gpurun_out/sanitize_memcheck_wave_tc.log
