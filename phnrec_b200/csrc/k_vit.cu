@@ -100,8 +100,11 @@ int launch_log_post(phn_ctx *c, int64_t rows)
     return PHN_OK;
 }
 
-template <int PPL, bool TILED>
-__global__ void __launch_bounds__(32, PPL <= 2 ? PHN_VIT_MINB : 1) k_viterbi(VitArgs a)
+// LAYOUT of ln p: 0 row-major [frame][ld]; 1 the tensor-core merger's tiles (column-major inside 128-frame tiles) staged through
+// shared-memory panels (default); 2 the same tiles read directly - no shared memory, at most 96 registers (PPL <= 2): a decoder
+// whose one-warp CTAs fit beside the next batch's persistent MLP kernel (measured and not adopted, see launch_viterbi).
+template <int PPL, int LAYOUT>
+__global__ void __launch_bounds__(32, PPL <= 2 ? (LAYOUT == 2 ? 21 : PHN_VIT_MINB) : 1) k_viterbi(VitArgs a)
 {
     const int seg = blockIdx.x;
     const int kpen = seg / a.n_utt, u = seg - kpen * a.n_utt;
@@ -128,6 +131,7 @@ __global__ void __launch_bounds__(32, PPL <= 2 ? PHN_VIT_MINB : 1) k_viterbi(Vit
     }
     int last_mi = -1;  // prev[0][0] after the last frame (phndec.cpp:240)
 
+    constexpr bool TILED = LAYOUT == 1;
     constexpr int FB = 8;  // frames whose observations are fetched ahead of the recurrence
     // TILED input (column-major inside 128-frame tiles): a warp's row read would touch one 128-byte line per
     // column, so 16-frame panels [16 frames][3P columns] are staged through shared memory with 4-byte cp.async
@@ -149,8 +153,26 @@ __global__ void __launch_bounds__(32, PPL <= 2 ? PHN_VIT_MINB : 1) k_viterbi(Vit
             asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(dst + cc)), "l"(__cvta_generic_to_global(src + (size_t)cc * 128)) : "memory");
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    for (int tb = 0; tb < T; tb += FB) {
+    // LAYOUT 2: groups start at multiples of 8 of the GLOBAL frame number (the first one may begin before the utterance), so the
+    // eight frames of a column are one aligned 32-byte run inside a tile: two 16-byte loads, every sector fetched exactly once
+    for (int tb = LAYOUT == 2 ? -(int)(f0 & 7) : 0; tb < T; tb += FB) {
         float obs[FB][PPL][3];
+        if (LAYOUT == 2) {
+            const int64_t F0 = f0 + tb;
+            const float *base = a.logp + ((F0 >> 7) * a.ld) * 128 + (F0 & 127);
+#pragma unroll
+            for (int r = 0; r < PPL; ++r)
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
+                    if (valid[r]) {
+                        const float4 *p = reinterpret_cast<const float4 *>(base + (size_t)(3 * (lane + 32 * r) + j) * 128);
+                        v0 = __ldg(p); v1 = __ldg(p + 1);
+                    }
+                    obs[0][r][j] = v0.x; obs[1][r][j] = v0.y; obs[2][r][j] = v0.z; obs[3][r][j] = v0.w;
+                    obs[4][r][j] = v1.x; obs[5][r][j] = v1.y; obs[6][r][j] = v1.z; obs[7][r][j] = v1.w;
+                }
+        }
         if (TILED) {
             int64_t need = (f0 + tb + FB - 1) >> 4;    // last panel this group of frames reads
             if (need > last_blk) need = last_blk;
@@ -165,6 +187,7 @@ __global__ void __launch_bounds__(32, PPL <= 2 ? PHN_VIT_MINB : 1) k_viterbi(Vit
             }
             __syncwarp();
         }
+        if (LAYOUT != 2)
 #pragma unroll
         for (int q = 0; q < FB; ++q)
 #pragma unroll
@@ -185,7 +208,7 @@ __global__ void __launch_bounds__(32, PPL <= 2 ? PHN_VIT_MINB : 1) k_viterbi(Vit
 #pragma unroll
         for (int q = 0; q < FB; ++q) {
             const int t = tb + q;
-            if (t < T) {   // predicated, not `break`: keeps obs[][][] in registers (fully unrolled indices)
+            if (t < T && (LAYOUT != 2 || t >= 0)) {   // predicated, not `break`: keeps obs[][][] in registers (fully unrolled indices)
             // ---- PropagateInModels (phndec.cpp:96-119): descending j, in place
 #pragma unroll
             for (int r = 0; r < PPL; ++r) {
@@ -365,12 +388,16 @@ int launch_viterbi(phn_ctx *c, const float *d_pen, int n_pen, cudaStream_t s, ph
     c->logp_layout = tiled ? 2 : 1;
     const size_t vsmem = sizeof(float) * 48 * (size_t)((3 * c->P) | 1);
     // (the panel ring of the tiled form exceeds the 48 KB default from 86 phonemes on)
+    // PHNREC_VIT_DIRECT=1: the tiled decoder without shared-memory panels (same speed alone, 0.55 ms; built for an experiment in
+    // which it ran beside the next batch's MLP kernel - tools/experiments/README.md)
+    static const bool panels = !(getenv("PHNREC_VIT_DIRECT") && atoi(getenv("PHNREC_VIT_DIRECT")) != 0);
 #define PHN_VIT(N)                                                          \
     do {                                                                    \
-        if (tiled) {                                                        \
-            PHN_CUDA(c, cudaFuncSetAttribute(k_viterbi<N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vsmem)); \
-            k_viterbi<N, true><<<nseg, 32, vsmem, s>>>(a);          \
-        } else k_viterbi<N, false><<<nseg, 32, 0, s>>>(a);                  \
+        if (tiled && panels) {                                              \
+            PHN_CUDA(c, cudaFuncSetAttribute(k_viterbi<N, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vsmem)); \
+            k_viterbi<N, 1><<<nseg, 32, vsmem, s>>>(a);                     \
+        } else if (tiled) k_viterbi<N, 2><<<nseg, 32, 0, s>>>(a);           \
+        else k_viterbi<N, 0><<<nseg, 32, 0, s>>>(a);                        \
     } while (0)
     switch (ppl) {
         case 1: PHN_VIT(1); break;

@@ -1,0 +1,24 @@
+#!/bin/bash
+# decoder without shared memory, enqueued behind the next batch's front end, co-resident with the MLP kernel: tests, then A/B
+cd "$(dirname "$0")/.." || exit 1
+O=gpurun_out; mkdir -p $O
+timeout 120 python -c "
+import __graft_entry__ as g
+g.smoke()" > $O/r2V_smoke.txt 2>&1; echo "smoke rc=$?"; tail -2 $O/r2V_smoke.txt
+if ! grep -q "mode 1 ok" $O/r2V_smoke.txt; then echo "SMOKE FAILED - stopping"; exit 1; fi
+timeout 600 python -m pytest tests/test_gpu_async.py tests/test_gpu_tensor_core.py tests/test_gpu_full_size.py -q -x --timeout 200 > $O/r2V_pytest.log 2>&1; echo "rc=$?" >> $O/r2V_pytest.log; tail -4 $O/r2V_pytest.log
+show() { python - "$1" <<'PY'
+import json,sys
+n=sys.argv[1]
+try:
+    j=json.load(open(f"gpurun_out/{n}.json")); print(f"{n:18s}", round(j["ms_per_step"],3), "ms e2e", round(j["e2e"]["ms_per_step"],3), [(k["kernel"], k["ms"]) for k in j["roofline"]["kernels"]])
+except Exception as e: print(n, "ERR", e, open(f"gpurun_out/{n}.err").read()[-1500:])
+PY
+}
+B="--steps 20 --warmup 3 --no-cpu-baseline --no-parity --profile-seconds 1"
+for i in 1 2; do
+timeout 120 python bench.py $B > $O/r2V_defer_$i.json 2> $O/r2V_defer_$i.err; show r2V_defer_$i
+PHNREC_VIT_DEFER=0 timeout 120 python bench.py $B > $O/r2V_nodefer_$i.json 2> $O/r2V_nodefer_$i.err; show r2V_nodefer_$i
+done
+PHNREC_VIT_DEFER=0 PHNREC_VIT_PANELS=1 timeout 120 python bench.py $B > $O/r2V_old.json 2> $O/r2V_old.err; show r2V_old
+timeout 100 python tools/e2e_timeline.py device 40 $O/r2V_tl_device.txt > /dev/null 2>&1; sed -n 30,34p $O/r2V_tl_device.txt | cut -c1-110
