@@ -681,11 +681,8 @@ int launch_wave_tc(phn_ctx *c, const void *d_audio, int64_t f_begin, int64_t f_e
         a.tl = d_tl;
     }
     auto kern = dbg ? k_wave_tc<true> : k_wave_tc<false>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        PHN_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WT_SMEM));
-        attr_set = true;
-    }
+    // (a function attribute belongs to the device's context: set per launch, like k_mlp_tc - contexts on several GPUs share this code)
+    PHN_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WT_SMEM));
     const int64_t units = (f_end - f_begin + 255) / 256;
     const int64_t maxp = c->num_sms / 2;
     cudaLaunchConfig_t cfg = {};
