@@ -256,11 +256,18 @@ def test_tc_dft_front_end_switch_gives_the_same_labels(tmp_path):
     import subprocess
     from conftest import AUDIO, ROOT
     out = {}
-    for sw in ("0", "1"):
-        env = dict(os.environ, PHNREC_MLP="tc", PHNREC_WAVE_TC=sw)
+    for sw in ("0", "1", "direct"):
+        # ("direct": the decoder variant that reads the merger's ln p tiles without shared-memory panels, PHNREC_VIT_DIRECT=1 -
+        # the same recurrence on the same numbers: the label file must be identical to the default's, scores included)
+        env = dict(os.environ, PHNREC_MLP="tc", PHNREC_WAVE_TC="1" if sw == "direct" else sw)
+        if sw == "direct":
+            env["PHNREC_VIT_DIRECT"] = "1"
         o = tmp_path / f"o{sw}.rec"
         p = subprocess.run([str(ROOT / "phnrec_b200" / "bin" / "phnrec"), "-c", str(model_dir("PHN_CZ_SPDAT_LCRC_N1500")), "-w", "alaw",
                             "-i", str(AUDIO / "test.raw"), "-o", str(o)], capture_output=True, text=True, env=env, timeout=300)
         assert p.returncode == 0, p.stderr
         out[sw] = [ln.split()[:3] for ln in o.read_text().splitlines()]
+        if sw != "0":
+            out[sw + "_text"] = o.read_text()
     assert out["0"] == out["1"]
+    assert out["direct_text"] == out["1_text"]
