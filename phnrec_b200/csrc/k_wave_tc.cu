@@ -92,13 +92,13 @@ __device__ __forceinline__ uint32_t alaw2_half2(uint32_t x)
     return *reinterpret_cast<const uint32_t *>(&r) | ((t & 0x00800080u) << 8);
 }
 
-// three consecutive words at p when fewer than 12 bytes are left in the batch's audio buffer (its very last chunks)
-__device__ __noinline__ uint3 load3_tail(const uint8_t *p, const uint8_t *end)
+// one word at p when fewer than 4 bytes are left in the batch's audio buffer (its very last chunks)
+__device__ __noinline__ uint32_t load_word_tail(const uint8_t *p, const uint8_t *end)
 {
-    uint32_t r[3] = {0u, 0u, 0u};
-    for (int i = 0; i < 12; ++i)
-        if (p + i < end) r[i >> 2] |= (uint32_t)p[i] << (8 * (i & 3));
-    return make_uint3(r[0], r[1], r[2]);
+    uint32_t r = 0;
+    for (int i = 0; i < 4; ++i)
+        if (p + i < end) r |= (uint32_t)p[i] << (8 * i);
+    return r;
 }
 
 // predicated store: the value is computed whether or not it is stored (no branch around it)
@@ -127,7 +127,11 @@ __device__ __forceinline__ int find_utt(const int64_t *off, int n, int64_t f)
 // DBG: the instantiation with the development switches (a.dbg) and the clock64() timeline; the product kernel carries neither.
 #define WT_TL(role, ev) do { if (DBG && a.tl && blockIdx.x == 0 && lane == 0 && it < 32) a.tl[((role) * 32 + it) * 8 + (ev)] = clock64(); } while (0)
 
-template <bool DBG>
+// LIN16: 16-bit linear samples.  A sample is hi + lo with hi = fp16(sample) and lo the rounding error (an integer of at most 4 bits),
+// both exact halves, and the tile goes through the tensor cores as two parts that share the accumulator: part 0 = hi against W_hi and
+// W_lo, part 1 = lo against W_hi (lo W_lo is below 2^-22 of the sample's own magnitude).  A part takes the place of a tile in the two-stage A ring (iteration = 2 tile + part, stage =
+// part), so shared memory, barriers and phases are those of the A-law kernel; only the accumulator hand-over is per tile.
+template <bool DBG, bool LIN16>
 __global__ void __launch_bounds__(WT_THREADS, 1) k_wave_tc(const __grid_constant__ WaveTcArgs a)
 {
     const int dbg = DBG ? a.dbg : 0;
@@ -153,6 +157,7 @@ __global__ void __launch_bounds__(WT_THREADS, 1) k_wave_tc(const __grid_constant
     const int64_t n_units = (nf + 255) / 256, ncl = gridDim.x >> 1, cl = blockIdx.x >> 1;
     const int64_t unit0 = cl * n_units / ncl;
     const int n_my = (int)((cl + 1) * n_units / ncl - unit0);
+    const int n_it = LIN16 ? 2 * n_my : n_my;   // iterations of the A ring
     constexpr int WARP_MMA = WT_EPI, PROD0 = WT_EPI + 1;
 
     if (threadIdx.x == 0) {
@@ -197,27 +202,31 @@ __global__ void __launch_bounds__(WT_THREADS, 1) k_wave_tc(const __grid_constant
             const uint32_t bar_ae = smem_u32(a_empty), bar_df = smem_u32(d_full);
             const bool leader = elect_one();
 #pragma unroll 1
-            for (int it = 0; it < n_my; ++it) {
+            for (int it = 0; it < n_it; ++it) {
                 const uint32_t s = (uint32_t)it & 1u, ph = ((uint32_t)it >> 1) & 1u;
+                const int tile = LIN16 ? it >> 1 : it;
+                const bool low = LIN16 && (it & 1);                       // the low bytes' part: accumulates on top of the high bytes'
+                const uint32_t ds = LIN16 ? (uint32_t)tile & 1u : s, dph = LIN16 ? ((uint32_t)tile >> 1) & 1u : ph;
                 WT_TL(0, 0);
                 mbar_wait_cluster(&a_full[s], ph);
                 WT_TL(0, 1);
-                if (it >= 2) mbar_wait_cluster(&d_empty[s], ph ^ 1u);
+                if (!low && tile >= 2) mbar_wait_cluster(&d_empty[ds], dph ^ 1u);
                 WT_TL(0, 2);
                 tc_fence_after();
                 if (leader) {
-                    const uint32_t td = tmem + 256u * s;
+                    const uint32_t td = tmem + 256u * ds;
                     if (!(dbg & 4)) {
                     const uint32_t alo = alo0 + s * (3u * (WT_BLK >> 4));
 #pragma unroll
                     for (int part = 0; part < 2; ++part) {
+                        if (low && part == 1) break;
                         const uint32_t blo = blo0 + (uint32_t)part * (3u * (WT_BLK >> 4));
 #pragma unroll
                         for (int b = 0; b < 3; ++b)
 #pragma unroll
                             for (int ks = 0; ks < 4; ++ks) {
                                 const uint32_t o = (uint32_t)b * (WT_BLK >> 4) + 2u * (uint32_t)ks;
-                                if (part == 0 && b == 0 && ks == 0) umma2_ss_lo<0>(td, alo + o, hi, blo + o, idesc);
+                                if (part == 0 && b == 0 && ks == 0 && !low) umma2_ss_lo<0>(td, alo + o, hi, blo + o, idesc);
                                 else umma2_ss_lo<1>(td, alo + o, hi, blo + o, idesc);
                             }
                         // the window's tail: stage s of the A tail block against part `part` of the matrix tail block
@@ -225,7 +234,7 @@ __global__ void __launch_bounds__(WT_THREADS, 1) k_wave_tc(const __grid_constant
                     }
                     }
                     tc_commit2_u(bar_ae + 8u * s);
-                    tc_commit2_u(bar_df + 8u * s);
+                    if (!LIN16 || low) tc_commit2_u(bar_df + 8u * ds);
                 }
                 __syncwarp();
                 WT_TL(0, 3);
@@ -268,130 +277,184 @@ __global__ void __launch_bounds__(WT_THREADS, 1) k_wave_tc(const __grid_constant
         auto st_shared = [](uint32_t addr, const uint4 &v) {
             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
         };
-        auto decode8 = [&](uint32_t w0, uint32_t w1, uint32_t w2, uint32_t sh) {
-            const uint32_t lo = __funnelshift_r(w0, w1, sh), hi = __funnelshift_r(w1, w2, sh);
+        constexpr int BPS = LIN16 ? 2 : 1;                   // bytes per sample
+        constexpr int CB = 8 * BPS;                          // bytes per chunk (8 samples)
+        constexpr int NW = CB / 4 + 1;                       // aligned words that cover a chunk at any byte alignment
+        // chunk of 8 samples -> 8 halves.  A-law: the G.711 expansion.  lin16 (two little-endian samples per word): the sample's
+        // fp16 rounding, or (`lowp`) what the rounding dropped.
+        auto decode_chunk = [&](const uint32_t (&wv)[NW], uint32_t sh, bool lowp) {
+            uint32_t v[NW - 1];
+#pragma unroll
+            for (int k = 0; k < NW - 1; ++k) v[k] = __funnelshift_r(wv[k], wv[k + 1], sh);
             uint4 out;
-            out.x = alaw2_half2(__byte_perm(lo, 0u, 0x4140u));
-            out.y = alaw2_half2(__byte_perm(lo, 0u, 0x4342u));
-            out.z = alaw2_half2(__byte_perm(hi, 0u, 0x4140u));
-            out.w = alaw2_half2(__byte_perm(hi, 0u, 0x4342u));
+            if constexpr (!LIN16) {
+                out.x = alaw2_half2(__byte_perm(v[0], 0u, 0x4140u));
+                out.y = alaw2_half2(__byte_perm(v[0], 0u, 0x4342u));
+                out.z = alaw2_half2(__byte_perm(v[1], 0u, 0x4140u));
+                out.w = alaw2_half2(__byte_perm(v[1], 0u, 0x4342u));
+            } else {
+                uint32_t *o = &out.x;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    // t = 256 h and l as halves (0x6400 | byte is the half 1024 + byte), then the sample as hi + lo with
+                    // hi = fp16(256 h + l) and lo = the rounding error, both exact (Fast2Sum: |256 h| >= l or h = 0)
+                    const uint32_t xh = __byte_perm(v[k], 0x64646464u, 0x4341u) ^ 0x00800080u, xl = __byte_perm(v[k], 0x64646464u, 0x4240u);
+                    const __half2 t = __hmul2(__hadd2(*reinterpret_cast<const __half2 *>(&xh), __float2half2_rn(-1152.0f)), __float2half2_rn(256.0f));
+                    const __half2 lf = __hadd2(*reinterpret_cast<const __half2 *>(&xl), __float2half2_rn(-1024.0f));
+                    const __half2 hi = __hadd2(t, lf);
+                    const __half2 r = lowp ? __hsub2(lf, __hsub2(hi, t)) : hi;
+                    o[k] = *reinterpret_cast<const uint32_t *>(&r);
+                }
+            }
             return out;
+        };
+        auto load_chunk = [&](const uint8_t *p, uint32_t (&wv)[NW]) {   // p: 4-byte aligned
+            if (p + 4 * NW <= a.audio_end) {
+#pragma unroll
+                for (int k = 0; k < NW; ++k) wv[k] = __ldg(reinterpret_cast<const unsigned int *>(p + 4 * k));
+            } else {                                         // (the last bytes of the batch)
+#pragma unroll
+                for (int k = 0; k < NW; ++k) wv[k] = load_word_tail(p + 4 * k, a.audio_end);
+            }
         };
         int64_t soff = 0;
         int lim = -1;
         uint32_t seq = 0;
-        uint32_t w[NG][3][3];
-        // row bookkeeping and loads of tile `it`
-        // row bookkeeping of tile `it` -> (bsoff, blim, bseq)
+        // row bookkeeping of tile `t` -> (bsoff, blim, bseq): byte offset of the row's first sample, samples of its window inside the signal
         int64_t bsoff = 0;
         int blim = -1;
         uint32_t bseq = 0;
-        auto book = [&](int it) {
-            const int64_t g = a.f_begin + ((unit0 + it) * 256 + (int64_t)rank * 128) + pw * RPW + (lane & (RPW - 1));   // (RPW = 16: the upper lanes repeat the rows)
+        auto book = [&](int t) {
+            const int64_t g = a.f_begin + ((unit0 + t) * 256 + (int64_t)rank * 128) + pw * RPW + (lane & (RPW - 1));   // (RPW = 16: the upper lanes repeat the rows)
             bsoff = 0; blim = -1;                            // -1: a row past the end of the launch (zeros)
             if (g < a.f_end && !(dbg & 1)) {
                 if (g >= fo_next) {
                     // the next utterance, or a search when the row jumped further
                     if (fo_next >= 0 && u + 2 <= a.n_utt && g < a.frame_off[u + 2]) ++u; else u = find_utt(a.frame_off, a.n_utt, g);
                     fo_cur = a.frame_off[u]; fo_next = a.frame_off[u + 1];
-                    b0 = a.byte_off[u]; len = a.byte_off[u + 1] - b0;
+                    b0 = a.byte_off[u]; len = (a.byte_off[u + 1] - b0) / BPS;
                 }
                 const int64_t s0 = (g - fo_cur) * a.step, left = len - s0;
-                bsoff = b0 + s0;
+                bsoff = b0 + s0 * BPS;
                 blim = left < a.vs ? (left < 0 ? 0 : (int)left) : a.vs;   // samples of the window inside the signal
             }
             const int64_t so0 = __shfl_sync(0xffffffffu, bsoff, lane & ~7);         // the group's first row
-            const bool in_seq = blim == a.vs && bsoff == so0 + (int64_t)(lane & 7) * 80 && so0 + 8 * 96 + 4 <= audio_len;
+            const bool in_seq = blim == a.vs && bsoff == so0 + (int64_t)(lane & 7) * (80 * BPS) && so0 + CB * 96 + 4 <= audio_len;
             bseq = __ballot_sync(0xffffffffu, in_seq);
         };
-        // the words of group gi of the tile whose bookkeeping is in (bsoff, bseq)
-        auto request = [&](int gi) {
-            const int64_t sg = __shfl_sync(0xffffffffu, bsoff, 8 * gi);
-            if (((bseq >> (8 * gi)) & 0xFFu) == 0xFFu) {
-                const uint8_t *p = reinterpret_cast<const uint8_t *>(reinterpret_cast<uintptr_t>(a.audio + sg + 8 * lane) & ~(uintptr_t)3);
+        // a group that is not 8 whole windows of one utterance: row by row, lane = chunk; the eight rows' words are requested
+        // before the first is decoded
+        auto slow_group = [&](int gi, uint32_t s, bool lowp) {
+            const uint32_t s_blk = s * (3u * WT_BLK);
+            uint32_t t[8][NW];
+            uint32_t shr[8];
+            int nn[8];
 #pragma unroll
-                for (int i = 0; i < 3; ++i) {
-                    w[gi][i][0] = __ldg(reinterpret_cast<const unsigned int *>(p + 256 * i));
-                    w[gi][i][1] = __ldg(reinterpret_cast<const unsigned int *>(p + 256 * i + 4));
-                    w[gi][i][2] = __ldg(reinterpret_cast<const unsigned int *>(p + 256 * i + 8));
+            for (int rr = 0; rr < 8; ++rr) {
+                const int64_t so = __shfl_sync(0xffffffffu, soff, 8 * gi + rr);
+                const int lm = __shfl_sync(0xffffffffu, lim, 8 * gi + rr);
+                nn[rr] = lane < WT_K / 8 ? lm - 8 * lane : 0;   // samples of this chunk inside the signal
+#pragma unroll
+                for (int k = 0; k < NW; ++k) t[rr][k] = 0u;
+                const uint8_t *src = a.audio + so + CB * lane;
+                shr[rr] = ((uint32_t)reinterpret_cast<uintptr_t>(src) & 3u) * 8u;
+                if (nn[rr] > 0) load_chunk(reinterpret_cast<const uint8_t *>(reinterpret_cast<uintptr_t>(src) & ~(uintptr_t)3), t[rr]);
+            }
+#pragma unroll
+            for (int rr = 0; rr < 8; ++rr) {
+                uint4 out = decode_chunk(t[rr], shr[rr], lowp);
+                const int n = nn[rr];                        // zeros beyond the signal (melbanks.cpp:151-170) and in rows past the end
+                uint32_t *o = &out.x;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    if (2 * i >= n) o[i] = 0u;
+                    else if (2 * i + 1 >= n) o[i] &= 0x0000FFFFu;
                 }
+                const int r = 8 * gi + rr, c = lane;
+                const uint32_t blk = c < 24 ? smem_u32(sA) + s_blk + (uint32_t)(c >> 3) * WT_BLK : smem_u32(sT);
+                const uint32_t col = c < 24 ? (uint32_t)(c & 7) : 2u * s + (uint32_t)(c & 7);
+                if (lane < WT_K / 8) st_shared(blk + (uint32_t)(pw * RPW + r) * 128u + ((col ^ ((uint32_t)r & 7u)) << 4), out);
             }
         };
-        if (n_my > 0) {
-            book(0);
-#pragma unroll
-            for (int gi = 0; gi < NG; ++gi) request(gi);
-        }
-#pragma unroll 1
-        for (int it = 0; it < n_my; ++it) {
-            const uint32_t s = (uint32_t)it & 1u, ph = ((uint32_t)it >> 1) & 1u;
-            if (pw == 0) WT_TL(1, 0);
-            soff = bsoff; lim = blim; seq = bseq;            // this tile's rows; then the next tile's, whose words are requested
-            const bool more = it + 1 < n_my;                 // group by group as this tile's registers become free
-            if (more) book(it + 1);
-            if (it >= 2) mbar_wait(&a_empty[s], ph ^ 1u);
-            if (pw == 0) WT_TL(1, 1);
+        // the three chunks of this lane in a whole group: decoded once, stored to every row that holds them
+        auto fast_group = [&](int gi, uint32_t s, const uint32_t (&wg)[3][NW], uint32_t sh, bool lowp) {
             const uint32_t s_blk = s * (3u * WT_BLK), s_tail = s * 32u;   // stage 1: three blocks further / tail column XOR 2
 #pragma unroll
-            for (int gi = 0; gi < NG; ++gi) {
-                const int64_t sg = __shfl_sync(0xffffffffu, soff, 8 * gi);
-                if (((seq >> (8 * gi)) & 0xFFu) == 0xFFu) {
-                    const uint32_t sh = ((abase + (uint32_t)sg) & 3u) * 8u;
+            for (int i = 0; i < 3; ++i) {
+                const uint4 val = decode_chunk(wg[i], sh, lowp);
 #pragma unroll
-                    for (int i = 0; i < 3; ++i) {
-                        const uint4 val = decode8(w[gi][i][0], w[gi][i][1], w[gi][i][2], sh);
-#pragma unroll
-                        for (int j = 0; j < 3; ++j)
-                            if (st_addr[i][j])
-                                st_shared((st_tail[i][j] ? st_addr[i][j] ^ s_tail : st_addr[i][j] + s_blk) + (uint32_t)gi * 1024u, val);
-                    }
-                } else {
-                    // row by row: lane = chunk; the eight rows' words are requested before the first is decoded
-                    uint3 t[8];
-                    uint32_t shr[8];
-                    int nn[8];
-#pragma unroll
-                    for (int rr = 0; rr < 8; ++rr) {
-                        const int64_t so = __shfl_sync(0xffffffffu, soff, 8 * gi + rr);
-                        const int lm = __shfl_sync(0xffffffffu, lim, 8 * gi + rr);
-                        nn[rr] = lane < WT_K / 8 ? lm - 8 * lane : 0;   // samples of this chunk inside the signal
-                        t[rr] = make_uint3(0u, 0u, 0u);
-                        const uint8_t *src = a.audio + so + 8 * lane;
-                        const uint8_t *p = reinterpret_cast<const uint8_t *>(reinterpret_cast<uintptr_t>(src) & ~(uintptr_t)3);
-                        shr[rr] = ((uint32_t)reinterpret_cast<uintptr_t>(src) & 3u) * 8u;
-                        if (nn[rr] > 0) {
-                            if (p + 12 <= a.audio_end) {
-                                t[rr].x = __ldg(reinterpret_cast<const unsigned int *>(p));
-                                t[rr].y = __ldg(reinterpret_cast<const unsigned int *>(p + 4));
-                                t[rr].z = __ldg(reinterpret_cast<const unsigned int *>(p + 8));
-                            } else {
-                                t[rr] = load3_tail(p, a.audio_end);
-                            }
-                        }
-                    }
-#pragma unroll
-                    for (int rr = 0; rr < 8; ++rr) {
-                        uint4 out = decode8(t[rr].x, t[rr].y, t[rr].z, shr[rr]);
-                        const int n = nn[rr];                // zeros beyond the signal (melbanks.cpp:151-170) and in rows past the end
-                        uint32_t *o = &out.x;
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            if (2 * i >= n) o[i] = 0u;
-                            else if (2 * i + 1 >= n) o[i] &= 0x0000FFFFu;
-                        }
-                        const int r = 8 * gi + rr, c = lane;
-                        const uint32_t blk = c < 24 ? smem_u32(sA) + s_blk + (uint32_t)(c >> 3) * WT_BLK : smem_u32(sT);
-                        const uint32_t col = c < 24 ? (uint32_t)(c & 7) : 2u * s + (uint32_t)(c & 7);
-                        if (lane < WT_K / 8) st_shared(blk + (uint32_t)(pw * RPW + r) * 128u + ((col ^ ((uint32_t)r & 7u)) << 4), out);
-                    }
-                }
-                if (more) request(gi);
+                for (int j = 0; j < 3; ++j)
+                    if (st_addr[i][j])
+                        st_shared((st_tail[i][j] ? st_addr[i][j] ^ s_tail : st_addr[i][j] + s_blk) + (uint32_t)gi * 1024u, val);
             }
-            if (pw == 0) WT_TL(1, 2);
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(&a_full[s], 0);
-            if (pw == 0) WT_TL(1, 3);
+        };
+        // the words of group gi of the tile whose bookkeeping is in (so_, seq_)
+        auto request = [&](int gi, int64_t so_, uint32_t seq_, uint32_t (&wg)[3][NW]) {
+            const int64_t sg = __shfl_sync(0xffffffffu, so_, 8 * gi);
+            if (((seq_ >> (8 * gi)) & 0xFFu) == 0xFFu) {
+                const uint8_t *p = reinterpret_cast<const uint8_t *>(reinterpret_cast<uintptr_t>(a.audio + sg + CB * lane) & ~(uintptr_t)3);
+#pragma unroll
+                for (int i = 0; i < 3; ++i)
+#pragma unroll
+                    for (int k = 0; k < NW; ++k) wg[i][k] = __ldg(reinterpret_cast<const unsigned int *>(p + 32 * CB * i + 4 * k));
+            }
+        };
+        if constexpr (!LIN16) {
+            // A-law: the words of a group of tile i + 1 are requested as soon as the same group of tile i has been decoded
+            uint32_t w[NG][3][NW];
+            if (n_my > 0) {
+                book(0);
+#pragma unroll
+                for (int gi = 0; gi < NG; ++gi) request(gi, bsoff, bseq, w[gi]);
+            }
+#pragma unroll 1
+            for (int it = 0; it < n_my; ++it) {
+                const uint32_t s = (uint32_t)it & 1u, ph = ((uint32_t)it >> 1) & 1u;
+                if (pw == 0) WT_TL(1, 0);
+                soff = bsoff; lim = blim; seq = bseq;        // this tile's rows; then the next tile's, whose words are requested
+                const bool more = it + 1 < n_my;             // group by group as this tile's registers become free
+                if (more) book(it + 1);
+                if (it >= 2) mbar_wait(&a_empty[s], ph ^ 1u);
+                if (pw == 0) WT_TL(1, 1);
+#pragma unroll
+                for (int gi = 0; gi < NG; ++gi) {
+                    const int64_t sg = __shfl_sync(0xffffffffu, soff, 8 * gi);
+                    if (((seq >> (8 * gi)) & 0xFFu) == 0xFFu) fast_group(gi, s, w[gi], ((abase + (uint32_t)sg) & 3u) * 8u, false);
+                    else slow_group(gi, s, false);
+                    if (more) request(gi, bsoff, bseq, w[gi]);
+                }
+                if (pw == 0) WT_TL(1, 2);
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(&a_full[s], 0);
+                if (pw == 0) WT_TL(1, 3);
+            }
+        } else {
+            // lin16: two iterations per tile (high bytes into stage 0, low bytes into stage 1); a group's words are requested while
+            // the group before it is decoded
+            uint32_t w[2][3][NW];
+#pragma unroll 1
+            for (int it = 0; it < n_it; ++it) {
+                const uint32_t s = (uint32_t)it & 1u, ph = ((uint32_t)it >> 1) & 1u;
+                const bool lowp = it & 1;
+                if (pw == 0) WT_TL(1, 0);
+                if (!lowp) { book(it >> 1); soff = bsoff; lim = blim; seq = bseq; }
+                request(0, soff, seq, w[0]);
+                if (it >= 2) mbar_wait(&a_empty[s], ph ^ 1u);
+                if (pw == 0) WT_TL(1, 1);
+#pragma unroll
+                for (int gi = 0; gi < NG; ++gi) {
+                    if (gi + 1 < NG) request(gi + 1, soff, seq, w[(gi + 1) & 1]);
+                    const int64_t sg = __shfl_sync(0xffffffffu, soff, 8 * gi);
+                    if (((seq >> (8 * gi)) & 0xFFu) == 0xFFu) fast_group(gi, s, w[gi & 1], ((abase + (uint32_t)sg) & 3u) * 8u, lowp);
+                    else slow_group(gi, s, lowp);
+                }
+                if (pw == 0) WT_TL(1, 2);
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(&a_full[s], 0);
+                if (pw == 0) WT_TL(1, 3);
+            }
         }
     } else {
         // ===================================================================== epilogue: |Z|^2 -> filterbank -> ln -> mel
@@ -651,13 +714,13 @@ void wave_tc_release(phn_ctx *c)
     c->wave_tc = nullptr;
 }
 
-// the tensor-core front end serves this call (model fits, A-law, plain waveform scaling, not switched off)
+// the tensor-core front end serves this call (model fits, plain waveform scaling, not switched off)
 bool wave_tc_applies(phn_ctx *c)
 {
     static const bool off = getenv("PHNREC_WAVE_TC") && atoi(getenv("PHNREC_WAVE_TC")) == 0;
     if (off || !c->wave_tc) return false;
     const WaveTcState *st = static_cast<const WaveTcState *>(c->wave_tc);
-    return st->ok && c->fmt == PHN_WAVE_ALAW && c->dc_shift == 0.0f && c->scale == 1.0f && wave_tc_fits(c);
+    return st->ok && (c->fmt == PHN_WAVE_ALAW || c->fmt == PHN_WAVE_LIN16) && c->dc_shift == 0.0f && c->scale == 1.0f && wave_tc_fits(c);
 }
 
 int launch_wave_tc(phn_ctx *c, const void *d_audio, int64_t f_begin, int64_t f_end)
@@ -680,7 +743,8 @@ int launch_wave_tc(phn_ctx *c, const void *d_audio, int64_t f_begin, int64_t f_e
         PHN_CUDA(c, cudaMemsetAsync(d_tl, 0, sizeof(long long) * (4 * 32 * 8 + 8), c->stream));
         a.tl = d_tl;
     }
-    auto kern = dbg ? k_wave_tc<true> : k_wave_tc<false>;
+    const bool lin16 = c->fmt == PHN_WAVE_LIN16;
+    auto kern = dbg ? (lin16 ? k_wave_tc<true, true> : k_wave_tc<true, false>) : (lin16 ? k_wave_tc<false, true> : k_wave_tc<false, false>);
     // (a function attribute belongs to the device's context: set per launch, like k_mlp_tc - contexts on several GPUs share this code)
     PHN_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WT_SMEM));
     const int64_t units = (f_end - f_begin + 255) / 256;

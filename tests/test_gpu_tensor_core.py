@@ -249,6 +249,35 @@ def test_tc_dft_front_end_ragged_alaw_batch(recs):
         r.set_wave_format("lin16")
 
 
+def test_tc_dft_front_end_lin16(recs):
+    """16-bit linear input through the same GEMM (k_wave_tc<.., LIN16>): a sample is fed as fp16(sample) plus the rounding error,
+    two parts of a tile sharing one accumulator - ln mel-bank energies against the reference's bits on a ragged batch with odd
+    byte counts (the last byte is dropped, srec.cpp:768-769), utterances shorter than a window, digital silence (frames of zeros
+    must stay EXACTLY 0, sLn's guard) and an utterance that starts at an odd byte of the batch buffer."""
+    r = recs("PHN_CZ_SPDAT_LCRC_N1500")
+    r.set_wave_format("lin16")
+    try:
+        rng = np.random.default_rng(4)
+        a = r.synth_audio(160000, 24, seed=12).copy()
+        a[3, 40000:90001] = 0
+        a[5, :7001] = 0
+        lens = [160000, 159999, 403, 402, 401, 400, 399, 11, 1, 0, 24691, 128000, 667] + [int(x) for x in rng.integers(300, 160000, 11)]
+        utts = [a[i].tobytes()[:n] for i, n in enumerate(lens)]
+        exact = np.concatenate(r.mel(utts))
+        lab = r.recognize(utts)
+        fast = r.fetch_mel(exact.shape[0])
+        assert np.isfinite(fast).all()
+        silent = (exact == 0.0).all(axis=1)
+        assert silent.any() and (fast[silent] == 0.0).all()
+        d = np.abs(fast - exact)
+        assert d.max() <= TC_DFT_MEL_ABS, (d.max(), np.unravel_index(d.argmax(), d.shape))
+        for i in (1, 4, 7, 10):
+            one = r.recognize([utts[i]])
+            assert np.array_equal(one[0].view(np.uint8), lab[i].view(np.uint8)), i
+    finally:
+        r.set_wave_format("lin16")
+
+
 def test_tc_dft_front_end_switch_gives_the_same_labels(tmp_path):
     """PHNREC_WAVE_TC=0 keeps the register-FFT front end in the tensor-core pipeline: both front ends are within 1e-4 of
     the reference's mel values, so the decoded label file of the shipped test utterance must not change."""
