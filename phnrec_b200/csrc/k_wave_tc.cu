@@ -3,7 +3,8 @@
 // Replaces, like k_wave.cu, ConvertWaveformFormat (srec.cpp:709-791), MelBanks::ProcessFrame (melbanks.cpp:111-204),
 // cFour1 / _mbApply (dspc.cpp:24-78, 236-269), cPower / sLn (dspc.h:141-160) and FrameBasedNormalization
 // (srec.cpp:1594-1620) - for the configuration the benchmark is quoted on (8 kHz A-law, 25 ms window = 200 samples,
-// 256-point transform, plain front end).  Everything else keeps the register-FFT kernels of k_wave.cu.
+// 256-point transform, plain front end) and the same models fed 16-bit linear samples (LIN16, see the kernel).  Everything
+// else keeps the register-FFT kernels of k_wave.cu.
 //
 // Why a GEMM: the FFT kernel spends ~17 000 thread-instructions per frame on butterflies and their two shared-memory
 // transposes and is bound by the SM's issue slots (0.76 ms for 998 000 frames).  The same spectrum is
