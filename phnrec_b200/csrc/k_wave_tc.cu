@@ -60,7 +60,7 @@ struct WaveTcHalf {
     int c_begin, c_end;                   // chunks of 16 bins
     int cur0;                             // Banks[] in effect at the first bin of chunk c_begin
     int flush_lo, flush_hi;               // banks cur - 1 / cur pending after the last chunk are this half's
-    int b_begin, b_end;                   // the half's banks (finished in place after the walk)
+    int b_begin, b_end;                   // the half's banks that the walk stores (host-side check only)
     int z_begin, z_end;                   // banks no bin belongs to (value: ln of silence)
 };
 struct WaveTcTab { WaveTcHalf h[2]; };
@@ -652,7 +652,6 @@ int wave_tc_prepare(phn_ctx *c)
         for (int b = bb; b < be; ++b)
             if (!stored[b]) { if (ze == zb) zb = b; ze = b + 1; }
         h.z_begin = zb; h.z_end = ze;
-        // (finishing in place covers the stored banks only)
         int fb = be, fe = bb;
         for (int b = bb; b < be; ++b)
             if (stored[b]) { fb = std::min(fb, b); fe = std::max(fe, b + 1); }
