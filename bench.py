@@ -10,6 +10,7 @@ independent) -> weak scaling.
   e2e   : the reference-facing C-ABI call (phn_recognize / phn_decode) with HOST buffers (pinned audio in, label arrays
           out), H2D and D2H copies inside the timed region
   --config cz|hu|ru|en : the other shipped systems (BASELINE configs[2], [3]) on the same kind of batch
+  --config cz_lin16    : configs[1]'s system fed 16-bit linear samples (the CLI's default wave format)
   --config en_sweep    : BASELINE configs[3], the 14-penalty decode from saved posteriors (srec.cpp:1080-1104 with -p)
   --impl reference     : the reference's own CPU implementation (oracle/_ref/phnrec_ref*, the reference sources compiled
                          by oracle/Makefile) on all host cores, bounded sample of the same utterances.
@@ -36,6 +37,7 @@ SWEEP_PENALTIES = [-6.0 + 0.5 * i for i in range(13)] + [None]   # None = the co
 
 CONFIGS = {  # --config -> workload
     "cz": dict(model="PHN_CZ_SPDAT_LCRC_N1500", fmt="alaw", fs=8000, bytes_per_utt=80000, baseline="configs[1]"),
+    "cz_lin16": dict(model="PHN_CZ_SPDAT_LCRC_N1500", fmt="lin16", fs=8000, bytes_per_utt=160000, baseline="configs[1] with 16-bit linear input"),
     "hu": dict(model="PHN_HU_SPDAT_LCRC_N1500", fmt="alaw", fs=8000, bytes_per_utt=80000, baseline="configs[2]"),
     "ru": dict(model="PHN_RU_SPDAT_LCRC_N1500", fmt="alaw", fs=8000, bytes_per_utt=80000, baseline="configs[2]"),
     "en": dict(model="PHN_EN_TIMIT_LCRC_N500", fmt="lin16", fs=16000, bytes_per_utt=320000, baseline="configs[3]"),
@@ -489,10 +491,10 @@ def main():
             ach = frames * per_frame / (ms * 1e-3) / 1e9
             kernels.append({"kernel": f"K-{k}", "bound": "hbm", "algorithmic_per_frame": per_frame, "what": what, "ms": round(ms, 4),
                             "launches": nl, "achieved": round(ach, 1), "unit": "GB/s", "peak": peaks["hbm_gbs"], "frac": round(ach / peaks["hbm_gbs"], 4)})
-            if k == "wave" and mode == "tc" and cfg["fmt"] == "alaw" and cfg["fs"] == 8000 and os.environ.get("PHNREC_WAVE_TC", "1") != "0":
+            if k == "wave" and mode == "tc" and cfg["fs"] == 8000 and os.environ.get("PHNREC_WAVE_TC", "1") != "0":
                 # k_wave_tc.cu: the windowed DFT runs as a GEMM on the tensor cores (208 x 256 per frame, matrix as fp16 hi + lo); the
                 # algorithmic figure above stays audio in + mel out - the GEMM's FLOPs are the kernel's own choice, reported for what they are
-                gf = 2 * 208 * 256 * 2
+                gf = 2 * 208 * 256 * (2 if cfg["fmt"] == "alaw" else 3)   # (lin16: fp16(sample) against W_hi, W_lo; the rounding error against W_hi)
                 kernels[-1]["tensor_work"] = {"flop_per_frame": gf, "tflops": round(frames * gf / (ms * 1e-3) / 1e12, 1),
                                               "of_sustained_peak": round(frames * gf / (ms * 1e-3) / 1e12 / peaks["tflops_sustained"], 3),
                                               "note": "DFT as a tcgen05 GEMM; what the kernel executes, not algorithmic work"}
