@@ -300,3 +300,31 @@ def test_tc_dft_front_end_switch_gives_the_same_labels(tmp_path):
             out[sw + "_text"] = o.read_text()
     assert out["0"] == out["1"]
     assert out["direct_text"] == out["1_text"]
+
+
+@pytest.mark.parametrize("fmt", ["alaw", "lin16"])
+def test_tc_dft_front_end_many_short_utterances(recs, fmt):
+    """2500 utterances of one to a dozen frames each (random byte lengths, so nearly every group of 8 rows straddles utterances and
+    every utterance starts at an arbitrary byte of the batch buffer): the row-by-row path of the producers, the utterance lookup
+    and the last bytes of the buffer.  ln mel-bank energies against the reference's bits; labels equal to those of a second call
+    with the utterances in reverse order (nothing depends on where in the batch an utterance sits)."""
+    r = recs("PHN_CZ_SPDAT_LCRC_N1500")
+    r.set_wave_format(fmt)
+    try:
+        bps = 2 if fmt == "lin16" else 1
+        rng = np.random.default_rng(9)
+        pool = r.synth_audio(200000, 8, seed=21).reshape(-1)
+        utts = []
+        for _ in range(2500):
+            n = int(rng.integers(1, 1100 * bps))
+            o = int(rng.integers(0, pool.size - n))
+            utts.append(pool[o:o + n].tobytes())
+        exact = np.concatenate(r.mel(utts))
+        lab = r.recognize(utts)
+        fast = r.fetch_mel(exact.shape[0])
+        d = np.abs(fast - exact)
+        assert np.isfinite(fast).all() and d.max() <= TC_DFT_MEL_ABS, (d.max(), np.unravel_index(d.argmax(), d.shape))
+        rev = r.recognize(utts[::-1])[::-1]
+        assert all(np.array_equal(x.view(np.uint8), y.view(np.uint8)) for x, y in zip(lab, rev))
+    finally:
+        r.set_wave_format("lin16")
