@@ -681,6 +681,7 @@ void phn_destroy(phn_ctx *c)
         if (b->p) cudaFree(b->p);
     mlp_tc_release(c);
     wave_tc_release(c);
+    wave_tc16_release(c);
     if (c->tc_dbg) cudaFree(c->tc_dbg);
     if (c->stc_btab) cudaFree(c->stc_btab);
     if (c->stc_bias) cudaFree(c->stc_bias);

@@ -115,6 +115,7 @@ struct phn_ctx {
     int mlp_mode = PHN_MLP_EXACT_FP32;
     void *tc = nullptr;  // tensor-core mode state (k_mlp_tc.cu)
     void *wave_tc = nullptr;  // tensor-core front end: DFT matrix image + filterbank tables (k_wave_tc.cu)
+    void *wave_tc16 = nullptr;  // ... of the 16 kHz systems (k_wave_tc16.cu)
     void *stc_btab = nullptr, *stc_bias = nullptr;   // K-stc tensor-core formulation: constant matrices (k_stc.cu)
     void *stc_cf = nullptr, *stc_sb = nullptr;       // K-stc fp32 (FFMA2) form: window x basis table, per-column scale / bias pairs
     int force_exact_wave = 0;
@@ -236,6 +237,10 @@ int wave_tc_prepare(phn_ctx *c);                                           // k_
 void wave_tc_release(phn_ctx *c);
 bool wave_tc_applies(phn_ctx *c);
 int launch_wave_tc(phn_ctx *c, const void *d_audio, int64_t f_begin, int64_t f_end);
+int wave_tc16_prepare(phn_ctx *c);                                         // k_wave_tc16.cu
+void wave_tc16_release(phn_ctx *c);
+bool wave_tc16_applies(phn_ctx *c);
+int launch_wave_tc16(phn_ctx *c, const void *d_audio, int64_t f_begin, int64_t f_end);
 int mlp_tc_prepare(phn_ctx *c);                                            // fp16 weight images (k_mlp_tc.cu)
 void mlp_tc_release(phn_ctx *c);
 }  // namespace phn

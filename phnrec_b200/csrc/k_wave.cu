@@ -637,6 +637,12 @@ int launch_wave(phn_ctx *c, const void *d_audio, int u0, int u1)
     const bool exact = c->mlp_mode != PHN_MLP_TC_F16 || c->force_exact_wave;
     int rc;
     if (!exact && !c->wave_tc && (rc = wave_tc_prepare(c))) return rc;   // (first call in this mode: the DFT matrix image)
+    if (!exact && !c->wave_tc16 && (rc = wave_tc16_prepare(c))) return rc;
+    if (!exact && wave_tc16_applies(c)) {   // ... of the 16 kHz systems (k_wave_tc16.cu)
+        if ((rc = launch_wave_tc16(c, d_audio, f_begin, f_end))) return rc;
+        c->k_launches[PHN_K_WAVE] += 1;
+        return PHN_OK;
+    }
     if (!exact && wave_tc_applies(c)) {   // the windowed DFT on the tensor cores (k_wave_tc.cu)
         if ((rc = launch_wave_tc(c, d_audio, f_begin, f_end))) return rc;
         c->k_launches[PHN_K_WAVE] += 1;

@@ -278,6 +278,47 @@ def test_tc_dft_front_end_lin16(recs):
         r.set_wave_format("lin16")
 
 
+def test_tc_dft_front_end_16khz(recs):
+    """The 16 kHz systems (25 ms window = 400 samples, 512-point transform, 256 bins: k_wave_tc16.cu - the product cut into two
+    passes over the bins, two halves of the window and the two fp16 parts of a 16-bit sample): ln mel-bank energies against
+    the reference's bits on a ragged lin16 batch - utterances of exactly one window, one sample short of it, a few bytes, none,
+    odd byte counts, digital silence (frames of zeros stay EXACTLY 0), tiles that end inside the batch - then one utterance at
+    a time and 1500 utterances of a few frames each at arbitrary byte offsets (row-by-row producer path); labels equal to
+    those of the same pipeline run in another batch order."""
+    r = recs("PHN_EN_TIMIT_LCRC_N500")
+    r.set_wave_format("lin16")
+    rng = np.random.default_rng(5)
+    a = r.synth_audio(320000, 24, seed=13).copy()
+    a[2, 100000:200001] = 0
+    a[6, :9001] = 0
+    lens = [320000, 319999, 803, 802, 801, 800, 799, 401, 21, 1, 0, 64691, 256000, 1667] + [int(x) for x in rng.integers(500, 320000, 10)]
+    utts = [a[i].tobytes()[:n] for i, n in enumerate(lens)]
+    exact = np.concatenate(r.mel(utts))
+    lab = r.recognize(utts)
+    fast = r.fetch_mel(exact.shape[0])
+    assert np.isfinite(fast).all()
+    silent = (exact == 0.0).all(axis=1)
+    assert silent.any() and (fast[silent] == 0.0).all()
+    d = np.abs(fast - exact)
+    assert d.max() <= TC_DFT_MEL_ABS, (d.max(), np.unravel_index(d.argmax(), d.shape))
+    for i in (1, 4, 7, 11, 13):
+        one = r.recognize([utts[i]])
+        assert np.array_equal(one[0].view(np.uint8), lab[i].view(np.uint8)), i
+    pool = a.reshape(-1)
+    short = []
+    for _ in range(1500):
+        n = int(rng.integers(1, 4400))
+        o = int(rng.integers(0, pool.size - n))
+        short.append(pool[o:o + n].tobytes())
+    exact = np.concatenate(r.mel(short))
+    lab = r.recognize(short)
+    fast = r.fetch_mel(exact.shape[0])
+    d = np.abs(fast - exact)
+    assert np.isfinite(fast).all() and d.max() <= TC_DFT_MEL_ABS, (d.max(), np.unravel_index(d.argmax(), d.shape))
+    rev = r.recognize(short[::-1])[::-1]
+    assert all(np.array_equal(x.view(np.uint8), y.view(np.uint8)) for x, y in zip(lab, rev))
+
+
 def test_tc_dft_front_end_switch_gives_the_same_labels(tmp_path):
     """PHNREC_WAVE_TC=0 keeps the register-FFT front end in the tensor-core pipeline: both front ends are within 1e-4 of
     the reference's mel values, so the decoded label file of the shipped test utterance must not change."""
