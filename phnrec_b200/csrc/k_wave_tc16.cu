@@ -34,7 +34,8 @@ constexpr int W16_KH = 200;               // samples of the window per K-half
 constexpr int W16_KC = 26;                // 16-byte chunks (8 samples) of a K-half fed to the tensor cores (208 columns)
 constexpr int W16_NBIN = 256;             // bins of the 512-point transform
 constexpr int W16_NCH = W16_NBIN / 16;    // chunks of 16 bins
-constexpr int W16_PROD = 4, W16_EPI = 8;
+constexpr int W16_PROD = 8, W16_EPI = 8;
+constexpr int W16_RPW = 128 / W16_PROD;     // rows of a CTA's half tile per producer warp
 constexpr int W16_THREADS = (W16_EPI + 1 + W16_PROD) * 32;
 constexpr int W16_BLK = 16384;
 constexpr int W16_BBLK = 7;
@@ -184,7 +185,9 @@ __global__ void __launch_bounds__(W16_THREADS, 1) k_wave_tc16(const __grid_const
         const int pw = warp - PROD0;
         int u = 0;
         int64_t fo_cur = 0, fo_next = -1, b0 = 0, len = 0;
-        int64_t soff = 0;
+        int64_t soff = 0, soff0 = 0;
+        uint32_t soff32 = 0;
+        bool fast = false;
         int lim = -1;
         auto st_shared = [](uint32_t addr, const uint4 &v) {
             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
@@ -194,7 +197,7 @@ __global__ void __launch_bounds__(W16_THREADS, 1) k_wave_tc16(const __grid_const
             const int tile = na >> 2, pi = na & 3, kh = pi & 1;
             const bool lowp = pi >> 1;
             if (pi == 0) {   // this lane's row of the tile: byte offset of its first sample, samples of its window inside the signal
-                const int64_t g = a.f_begin + ((unit0 + tile) * 256 + (int64_t)rank * 128) + pw * 32 + lane;
+                const int64_t g = a.f_begin + ((unit0 + tile) * 256 + (int64_t)rank * 128) + pw * W16_RPW + (lane & (W16_RPW - 1));
                 soff = 0; lim = -1;
                 if (g < a.f_end) {
                     if (g >= fo_next) {
@@ -206,10 +209,55 @@ __global__ void __launch_bounds__(W16_THREADS, 1) k_wave_tc16(const __grid_const
                     soff = b0 + 2 * s0;
                     lim = left < a.vs ? (left < 0 ? 0 : (int)left) : a.vs;
                 }
+                // the common case - every row of this warp a whole 400-sample window, all reads inside the buffer: a loop without
+                // per-row bounds, lengths and 64-bit shuffles (offsets from the warp's first row)
+                soff0 = __shfl_sync(0xffffffffu, soff, 0);
+                fast = __all_sync(0xffffffffu, lim == 2 * W16_KH && soff >= soff0 && soff - soff0 < (int64_t)1 << 30 &&
+                                                   a.audio + soff + 2 * (2 * W16_KH) + 4 <= a.audio_end);
+                soff32 = (uint32_t)(soff - soff0);
             }
             bool waited = na < 2;                                        // (a stage's first production has nothing to wait for)
+            if (fast) {
+                const uint8_t *wsrc = a.audio + soff0 + 2 * (W16_KH * kh + 8 * lane);
+                const bool ld = lane < W16_KH / 8;                       // chunks 0..24 hold samples, chunk 25 is the K padding
 #pragma unroll 1
-            for (int gi = 0; gi < 4; ++gi) {
+                for (int gi = 0; gi < W16_RPW / 8; ++gi) {
+                    uint32_t t[8][5];
+                    uint32_t shr[8];
+#pragma unroll
+                    for (int rr = 0; rr < 8; ++rr) {
+                        const uint8_t *src = wsrc + __shfl_sync(0xffffffffu, soff32, 8 * gi + rr);
+                        const uint32_t *p = reinterpret_cast<const uint32_t *>(reinterpret_cast<uintptr_t>(src) & ~(uintptr_t)3);
+                        shr[rr] = ((uint32_t)reinterpret_cast<uintptr_t>(src) & 3u) * 8u;
+#pragma unroll
+                        for (int k = 0; k < 5; ++k) t[rr][k] = ld ? __ldg(p + k) : 0u;
+                    }
+                    if (!waited) { mbar_wait(&a_empty[kh], lowp ? 0u : 1u); waited = true; }
+#pragma unroll
+                    for (int rr = 0; rr < 8; ++rr) {
+                        uint4 oh;
+                        uint32_t *ph_ = &oh.x;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const uint32_t v = __funnelshift_r(t[rr][k], t[rr][k + 1], shr[rr]);
+                            const uint32_t xh = __byte_perm(v, 0x64646464u, 0x4341u) ^ 0x00800080u, xl = __byte_perm(v, 0x64646464u, 0x4240u);
+                            const __half2 th = __hmul2(__hadd2(*reinterpret_cast<const __half2 *>(&xh), __float2half2_rn(-1152.0f)), __float2half2_rn(256.0f));
+                            const __half2 lf = __hadd2(*reinterpret_cast<const __half2 *>(&xl), __float2half2_rn(-1024.0f));
+                            const __half2 hh = __hadd2(th, lf);
+                            const __half2 r = lowp ? __hsub2(lf, __hsub2(hh, th)) : hh;
+                            ph_[k] = ld ? *reinterpret_cast<const uint32_t *>(&r) : 0u;
+                        }
+                        const int r = 8 * gi + rr, c = lane;
+                        if (lane < W16_KC) {
+                            const uint32_t rowoff = (uint32_t)(pw * W16_RPW + r) * 128u;
+                            if (c < 24) st_shared(smem_u32(sA) + (uint32_t)(3 * kh + (c >> 3)) * W16_BLK + rowoff + ((((uint32_t)c & 7u) ^ ((uint32_t)r & 7u)) << 4), oh);
+                            else st_shared(smem_u32(sT) + rowoff + (((2u * (uint32_t)kh + (uint32_t)(c & 7)) ^ ((uint32_t)r & 7u)) << 4), oh);
+                        }
+                    }
+                }
+            } else
+#pragma unroll 1
+            for (int gi = 0; gi < W16_RPW / 8; ++gi) {
                 uint32_t t[8][5];
                 uint32_t shr[8];
                 int nn[8];
@@ -261,7 +309,7 @@ __global__ void __launch_bounds__(W16_THREADS, 1) k_wave_tc16(const __grid_const
                     }
                     const int r = 8 * gi + rr, c = lane;
                     if (lane < W16_KC) {
-                        const uint32_t rowoff = (uint32_t)(pw * 32 + r) * 128u;
+                        const uint32_t rowoff = (uint32_t)(pw * W16_RPW + r) * 128u;
                         if (c < 24) st_shared(smem_u32(sA) + (uint32_t)(3 * kh + (c >> 3)) * W16_BLK + rowoff + ((((uint32_t)c & 7u) ^ ((uint32_t)r & 7u)) << 4), oh);
                         else st_shared(smem_u32(sT) + rowoff + (((2u * (uint32_t)kh + (uint32_t)(c & 7)) ^ ((uint32_t)r & 7u)) << 4), oh);
                     }
