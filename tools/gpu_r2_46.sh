@@ -2,7 +2,7 @@
 # 16 kHz tensor-core front end (k_wave_tc16.cu): full GPU suite, EN bench lines with both front ends, default line, memcheck of the 16 kHz batch
 cd "$(dirname "$0")/.." || exit 1
 O=gpurun_out; mkdir -p $O
-timeout 500 python -m pytest tests -m gpu -q -x --timeout 200 > $O/r2e_pytest.log 2>&1; echo "rc=$?" >> $O/r2e_pytest.log; tail -3 $O/r2e_pytest.log
+timeout 700 python -m pytest tests -m gpu -q -x --timeout 200 > $O/r2e_pytest.log 2>&1; echo "rc=$?" >> $O/r2e_pytest.log; tail -3 $O/r2e_pytest.log
 timeout 300 python bench.py --config en --steps 20 --warmup 3 --no-cpu-baseline > $O/r2e_bench_en.json 2> $O/r2e_bench_en.err; echo "rc=$?"
 PHNREC_WAVE_TC=0 timeout 300 python bench.py --config en --steps 20 --warmup 3 --no-cpu-baseline --no-parity > $O/r2e_bench_en_fft.json 2> $O/r2e_bench_en_fft.err; echo "rc=$?"
 timeout 300 python bench.py --config en_sweep --steps 20 --warmup 3 --no-cpu-baseline > $O/r2e_bench_en_sweep.json 2> $O/r2e_bench_en_sweep.err; echo "rc=$?"
