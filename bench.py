@@ -491,6 +491,12 @@ def main():
             ach = frames * per_frame / (ms * 1e-3) / 1e9
             kernels.append({"kernel": f"K-{k}", "bound": "hbm", "algorithmic_per_frame": per_frame, "what": what, "ms": round(ms, 4),
                             "launches": nl, "achieved": round(ach, 1), "unit": "GB/s", "peak": peaks["hbm_gbs"], "frac": round(ach / peaks["hbm_gbs"], 4)})
+            if k == "wave" and mode == "tc" and cfg["fs"] == 16000 and os.environ.get("PHNREC_WAVE_TC", "1") != "0":
+                # k_wave_tc16.cu: 2 bin passes x 2 window halves x (fp16(sample) against W_hi, W_lo; the rounding error against W_hi), 208 x 256 each
+                gf = 2 * 208 * 256 * 2 * 2 * 3
+                kernels[-1]["tensor_work"] = {"flop_per_frame": gf, "tflops": round(frames * gf / (ms * 1e-3) / 1e12, 1),
+                                              "of_sustained_peak": round(frames * gf / (ms * 1e-3) / 1e12 / peaks["tflops_sustained"], 3),
+                                              "note": "DFT as a tcgen05 GEMM; what the kernel executes, not algorithmic work"}
             if k == "wave" and mode == "tc" and cfg["fs"] == 8000 and os.environ.get("PHNREC_WAVE_TC", "1") != "0":
                 # k_wave_tc.cu: the windowed DFT runs as a GEMM on the tensor cores (208 x 256 per frame, matrix as fp16 hi + lo); the
                 # algorithmic figure above stays audio in + mel out - the GEMM's FLOPs are the kernel's own choice, reported for what they are
