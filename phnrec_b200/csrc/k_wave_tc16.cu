@@ -40,7 +40,7 @@ constexpr int W16_THREADS = (W16_EPI + 1 + W16_PROD) * 32;
 constexpr int W16_BLK = 16384;
 constexpr int W16_BBLK = 7;
 constexpr int W16_HCH = 10;               // chunks one epilogue half may walk
-constexpr size_t W16_SMEM = (size_t)(W16_BBLK + 6 + 1) * W16_BLK + 128 + 2 * W16_HCH * 128;   // the base must be 1024-byte aligned (checked)
+constexpr size_t W16_SMEM = (size_t)(W16_BBLK + 6 + 1) * W16_BLK + 160 + 2 * W16_HCH * 128;   // the base must be 1024-byte aligned (checked)
 
 struct Wave16Half {
     uint32_t shift[W16_NBIN / 32], emit[W16_NBIN / 32];
@@ -96,9 +96,9 @@ __global__ void __launch_bounds__(W16_THREADS, 1) k_wave_tc16(const __grid_const
     uint8_t *sT = sA + (size_t)6 * W16_BLK;               // the stages' shared tail block
     uint64_t *bars = reinterpret_cast<uint64_t *>(sT + W16_BLK);
     uint64_t *a_full = bars, *a_empty = bars + 2, *d_full = bars + 4, *d_empty = bars + 6;
-    uint64_t *b_full = bars + 8, *pb_full = bars + 9, *b_free = bars + 10;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 11);
-    float4 *s_w = reinterpret_cast<float4 *>(bars + 16);
+    uint64_t *m_full = bars + 8, *m_pfull = bars + 11, *m_free = bars + 14;   // matrix units X0, X1, X2 (see the MMA warp)
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 17);
+    float4 *s_w = reinterpret_cast<float4 *>(bars + 20);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = blockIdx.x & 1u;
@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(W16_THREADS, 1) k_wave_tc16(const __grid_const
             mbar_init(&a_full[i], 2 * W16_PROD); mbar_init(&a_empty[i], 1);
             mbar_init(&d_full[i], 1); mbar_init(&d_empty[i], 2 * W16_EPI);
         }
-        mbar_init(b_full, 1); mbar_init(pb_full, 1); mbar_init(b_free, 1);
+        for (int i = 0; i < 3; ++i) { mbar_init(&m_full[i], 1); mbar_init(&m_pfull[i], 1); mbar_init(&m_free[i], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == WARP_MMA) {
@@ -132,53 +132,95 @@ __global__ void __launch_bounds__(W16_THREADS, 1) k_wave_tc16(const __grid_const
         constexpr uint32_t idesc = make_idesc(256, false, 256);
         const uint64_t dA = make_sw128_desc(smem_u32(sA)), dB = make_sw128_desc(smem_u32(sB)), dT = make_sw128_desc(smem_u32(sT));
         const uint32_t alo0 = (uint32_t)dA, blo0 = (uint32_t)dB, tlo0 = (uint32_t)dT, hi = (uint32_t)(dA >> 32);
-        const uint32_t bar_ae = smem_u32(a_empty), bar_df = smem_u32(d_full), bar_bf = smem_u32(b_free);
+        const uint32_t bar_ae = smem_u32(a_empty), bar_df = smem_u32(d_full), bar_fr = smem_u32(m_free);
         const bool leader = elect_one();
         // A tile has four PRODUCTIONS of an A stage - (khalf 0, hi), (khalf 1, hi), (khalf 0, lo), (khalf 1, lo); hi = fp16(sample),
-        // lo = its rounding error; stage = khalf - and each serves two PIECES (pass 0, pass 1): a piece reloads the matrix of
-        // (pass, khalf) and multiplies the stage into its pass's accumulator (hi against W_hi and W_lo, lo against W_hi).
+        // lo = its rounding error; stage = khalf - and each serves two PIECES (pass 0, pass 1): a piece multiplies the stage by the
+        // matrix of (pass, khalf) into its pass's accumulator (hi against W_hi and W_lo, lo against W_hi).
+        // The matrix buffer is three UNITS with a full / free barrier pair each - X0 = blocks 0..2, X1 = blocks 3..5, X2 = the tail
+        // block - and a unit is reloaded as soon as the MMAs that read it have completed, while those of the other units run:
+        //   hi piece: X0 = W_hi, X1 = W_lo, X2 = both tails (12 + 12 + 2 MMAs); lo pieces need W_hi only and alternate between
+        //   X0 and X1 for it (12 + 1 MMAs).  Uses of a unit per tile: X0 in pieces 0 1 2 3 4 6, X1 in 0 1 2 3 5 7, X2 in all eight
+        //   (even counts: the barrier parity of a use depends on the piece's place in the tile only).
         const int n_piece = 8 * n_my;
+        auto use_parity = [](int X, int q) -> uint32_t { return (uint32_t)((X == 2 || q < 4 ? q : q >> 1) & 1); };
+        auto load_unit = [&](int X, int pc) {   // the contents piece pc needs in unit X (the caller has waited for the unit to be free)
+            if (!leader) return;
+            const int q = pc & 7, pass = q & 1, kh = (q >> 1) & 1;
+            const bool low = q >= 4;
+            const uint8_t *src = a.w_img + ((size_t)((pass * 2 + kh) * 2 + (int)rank) * W16_BBLK) * W16_BLK;
+            if (X == 2) {
+                mbar_expect_tx(&m_full[2], W16_BLK);
+                tma_load_1d(sB + (size_t)6 * W16_BLK, src + (size_t)6 * W16_BLK, W16_BLK, &m_full[2]);
+            } else {
+                const int sb = (X == 1 && !low) ? 3 : 0;                 // W_lo for a hi piece's X1, W_hi otherwise
+                mbar_expect_tx(&m_full[X], 3 * W16_BLK);
+                for (int b = 0; b < 3; ++b) tma_load_1d(sB + (size_t)(3 * X + b) * W16_BLK, src + (size_t)(sb + b) * W16_BLK, W16_BLK, &m_full[X]);
+            }
+        };
+        auto next_use = [](int X, int pc) {     // the next piece that reads unit X after piece pc
+            const int q = pc & 7, base = pc - q;
+            if (X == 2 || q < 3) return pc + 1;
+            if (q == 3) return base + (X == 0 ? 4 : 5);
+            return q >= 6 ? base + 8 : pc + 2;
+        };
+        if (n_piece > 0) { load_unit(0, 0); load_unit(1, 0); load_unit(2, 0); }
+        int prevX = -1, prev_pc = 0;
 #pragma unroll 1
         for (int pc = 0; pc < n_piece; ++pc) {
             const int q = pc & 7, tile = pc >> 3, pi = q >> 1, pass = q & 1, kh = pi & 1;
             const bool low = pi >> 1;
-            // the matrix piece: once the MMAs that read the previous one have completed (the low part needs W_hi only)
-            if (pc > 0) mbar_wait(b_free, (uint32_t)(pc - 1) & 1u);
-            if (leader) {
-                mbar_expect_tx(b_full, (low ? 4 : W16_BBLK) * W16_BLK);
-                const uint8_t *src = a.w_img + ((size_t)((pass * 2 + kh) * 2 + (int)rank) * W16_BBLK) * W16_BLK;
-                for (int b = 0; b < W16_BBLK; ++b)
-                    if (!low || b < 3 || b == 6) tma_load_1d(sB + (size_t)b * W16_BLK, src + (size_t)b * W16_BLK, W16_BLK, b_full);
-            }
-            __syncwarp();
-            mbar_wait(b_full, (uint32_t)pc & 1u);
-            if (rank != 0) { if (lane == 0) mbar_arrive_cluster(pb_full, 0); continue; }
-            mbar_wait_cluster(pb_full, (uint32_t)pc & 1u);
-            if (pass == 0) mbar_wait_cluster(&a_full[kh], low ? 1u : 0u);   // (two productions per stage and tile: parity = part)
-            if (pi == 0 && tile >= 1) mbar_wait_cluster(&d_empty[pass], ((uint32_t)tile & 1u) ^ 1u);
-            tc_fence_after();
-            if (leader) {
-                const uint32_t td = tmem + 256u * (uint32_t)pass;
-                const uint32_t alo = alo0 + (uint32_t)kh * (3u * (W16_BLK >> 4));   // A stage = K-half
+            const int n_units = low ? 2 : 3;
+#pragma unroll 1
+            for (int k = 0; k < n_units; ++k) {
+                const int X = low ? (k == 0 ? (q & 1) : 2) : k;
+                const uint32_t par = use_parity(X, q);
+                mbar_wait(&m_full[X], par);
+                if (rank != 0) {
+                    if (lane == 0) mbar_arrive_cluster(&m_pfull[X], 0);
+                } else {
+                    mbar_wait_cluster(&m_pfull[X], par);
+                    if (k == 0) {
+                        if (pass == 0) mbar_wait_cluster(&a_full[kh], low ? 1u : 0u);   // (two productions per stage and tile: parity = part)
+                        if (pi == 0 && tile >= 1) mbar_wait_cluster(&d_empty[pass], ((uint32_t)tile & 1u) ^ 1u);
+                    }
+                    tc_fence_after();
+                    if (leader) {
+                        const uint32_t td = tmem + 256u * (uint32_t)pass;
+                        const uint32_t alo = alo0 + (uint32_t)kh * (3u * (W16_BLK >> 4));   // A stage = K-half
+                        if (X < 2) {
+                            const uint32_t blo = blo0 + (uint32_t)X * (3u * (W16_BLK >> 4));
 #pragma unroll
-                for (int part = 0; part < 2; ++part) {                   // against W_hi, then (hi only) W_lo
-                    if (low && part == 1) break;
-                    const uint32_t blo = blo0 + (uint32_t)part * (3u * (W16_BLK >> 4));
+                            for (int b = 0; b < 3; ++b)
 #pragma unroll
-                    for (int b = 0; b < 3; ++b)
-#pragma unroll
-                        for (int ks = 0; ks < 4; ++ks) {
-                            const uint32_t o = (uint32_t)b * (W16_BLK >> 4) + 2u * (uint32_t)ks;
-                            if (part == 0 && b == 0 && ks == 0 && pi == 0) umma2_ss_lo<0>(td, alo + o, hi, blo + o, idesc);
-                            else umma2_ss_lo<1>(td, alo + o, hi, blo + o, idesc);
+                                for (int ks = 0; ks < 4; ++ks) {
+                                    const uint32_t o = (uint32_t)b * (W16_BLK >> 4) + 2u * (uint32_t)ks;
+                                    if (k == 0 && b == 0 && ks == 0 && pi == 0) umma2_ss_lo<0>(td, alo + o, hi, blo + o, idesc);
+                                    else umma2_ss_lo<1>(td, alo + o, hi, blo + o, idesc);
+                                }
+                        } else {
+                            umma2_ss_lo<1>(td, tlo0 + 2u * (uint32_t)kh, hi, blo0 + 6u * (W16_BLK >> 4), idesc);
+                            if (!low) umma2_ss_lo<1>(td, tlo0 + 2u * (uint32_t)kh, hi, blo0 + 6u * (W16_BLK >> 4) + 2u, idesc);
                         }
-                    umma2_ss_lo<1>(td, tlo0 + 2u * (uint32_t)kh, hi, blo0 + 6u * (W16_BLK >> 4) + 2u * (uint32_t)part, idesc);
+                        tc_commit2_u(bar_fr + 8u * (uint32_t)X);
+                        if (X == 2) {                                    // the piece's last unit
+                            if (pass == 1) tc_commit2_u(bar_ae + 8u * (uint32_t)kh);
+                            if (pi == 3) tc_commit2_u(bar_df + 8u * (uint32_t)pass);
+                        }
+                    }
                 }
-                tc_commit2_u(bar_bf);
-                if (pass == 1) tc_commit2_u(bar_ae + 8u * (uint32_t)kh);
-                if (pi == 3) tc_commit2_u(bar_df + 8u * (uint32_t)pass);
+                __syncwarp();
+                // the unit issued before this one: once its MMAs have completed (those just issued are running), its next contents
+                if (prevX >= 0) {
+                    const int nx = next_use(prevX, prev_pc);
+                    if (nx < n_piece) {
+                        mbar_wait(&m_free[prevX], use_parity(prevX, prev_pc & 7));
+                        load_unit(prevX, nx);
+                    }
+                }
+                prevX = X; prev_pc = pc;
+                __syncwarp();
             }
-            __syncwarp();
         }
     } else if (warp >= PROD0) {
         // ===================================================================== producers: audio -> A stage
