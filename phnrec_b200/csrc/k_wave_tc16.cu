@@ -2,22 +2,23 @@
 // transform, 256 bins): the windowed DFT of every frame as a GEMM on tcgen05, like k_wave_tc.cu for the 8 kHz systems.
 //
 // Replaces ConvertWaveformFormat (srec.cpp:709-791), MelBanks::ProcessFrame (melbanks.cpp:111-204), cFour1 / _mbApply
-// (dspc.cpp:24-78, 236-269), cPower / sLn (dspc.h:141-160) and FrameBasedNormalization (srec.cpp:1594-1620) where the register FFT
-// of k_wave.cu takes 2.27 ms per 998 000 frames.
+// (dspc.cpp:24-78, 236-269), cPower / sLn (dspc.h:141-160) and FrameBasedNormalization (srec.cpp:1594-1620).
 //
-// The [400 x 512] matrix (hi + lo halves: 819 KB) does not fit beside the operands, so the product is cut four ways and the kernel
-// of k_wave_tc.cu is run over the pieces: two PASSES (bins 0..127, 128..255: N = 256 each, one accumulator each - the epilogue of
+// The [400 x 512] matrix (hi + lo halves: 819 KB) does not fit beside the operands, so the product is cut four ways and the machinery
+// of k_wave_tc.cu runs over the pieces: two PASSES (bins 0..127, 128..255: N = 256 each, one accumulator each - the epilogue of
 // pass 0 runs under the MMAs of pass 1), two K-HALVES (samples 0..199, 200..399 of the window: the A stage of the 8 kHz kernel,
 // 208 columns) that accumulate into the pass's accumulator, and for each of them the two PARTS of a 16-bit sample (fp16(sample)
-// against W_hi and W_lo, the rounding error against W_hi).  Iteration = 8 tile + 4 pass + 2 khalf + part; A stage = part (the
-// two-stage ring, barriers and phases of the 8 kHz kernel); the matrix piece of (pass, khalf) - 7 blocks of 16 KB per CTA - is
-// reloaded by bulk copies every second iteration, after the MMAs that read the previous piece have completed (one buffer:
-// the reload is exposed, ~1.5 k clk against ~6.5 k clk of MMAs per piece).
-// Producers: lane = 16-byte chunk of a row, the words of 8 rows requested before the first is decoded (rows are 20 chunks apart:
-// little to share between them).  Epilogue: the filterbank walk of k_wave_tc.cu over 256 bins, its state carried across the two
+// against W_hi and W_lo, the rounding error against W_hi).  Per tile: four PRODUCTIONS of an A stage - (khalf 0, hi), (khalf 1, hi),
+// (khalf 0, lo), (khalf 1, lo); stage = khalf (two stages) - each serving two PIECES (pass 0, pass 1) = 8 pieces, 156 MMAs.
+// The matrix of a piece's (pass, khalf) - 7 blocks of 16 KB per CTA - comes from L2 by bulk copies into a buffer of three units
+// (W_hi blocks, W_lo blocks, tail block) with a full / free barrier pair each: a unit is refilled for its next piece while the
+// MMAs of the other units run (lo pieces need W_hi only and alternate between the two block units).
+// Producers (8 warps, 16 rows each): lane = 16-byte chunk of a row, the words of 8 rows requested before the first is decoded (rows
+// are 20 chunks apart: little to share between them); per tile a loop without bounds / lengths when all of a warp's rows are whole
+// windows inside the buffer.  Epilogue: the filterbank walk of k_wave_tc.cu over 256 bins, its state carried across the two
 // passes of a tile in registers; weights in shared memory, shift / store masks as kernel parameters.
-// (A first version ran eight iterations per tile - pass x khalf x part, each producing its A stage - and was producer-bound at
-// 2.72 ms; now a K-half's two stages are produced once and serve both passes.)
+// History on 998 000 frames: 2.72 ms (eight productions per tile) -> 1.91 (a K-half's stages serve both passes) -> 1.30 (8 producer
+// warps) -> 1.18 (fast producer loop) -> 1.10 ms (matrix units refilled under the MMAs); register FFT: 2.28 ms.
 #include "internal.h"
 #include "tc_ptx.cuh"
 

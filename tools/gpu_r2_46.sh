@@ -28,3 +28,4 @@ print('EN16k single', [len(l) for l in rec.recognize([utts[1]])])
 rec.close()
 PY
 timeout 400 compute-sanitizer --tool memcheck --error-exitcode 9 python /tmp/san16.py > $O/sanitize_memcheck_wave_tc16.log 2>&1; echo "memcheck rc=$?"; tail -4 $O/sanitize_memcheck_wave_tc16.log
+timeout 400 compute-sanitizer --tool racecheck --kernel-regex kns=k_wave_tc16 --error-exitcode 9 python /tmp/san16.py > $O/sanitize_racecheck_wave_tc16.log 2>&1; echo "racecheck rc=$?"; grep -c "Race reported" $O/sanitize_racecheck_wave_tc16.log; tail -3 $O/sanitize_racecheck_wave_tc16.log
