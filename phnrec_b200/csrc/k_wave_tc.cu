@@ -42,9 +42,11 @@ namespace phn {
 
 constexpr int WT_K = 208;                 // window columns fed to the tensor cores (13 k-steps of 16; the window is <= 208)
 constexpr int WT_NBIN = 128;              // bins 0..127 of the 256-point transform
-constexpr int WT_PROD = 4;                // producer warps per CTA (32 rows of the tile each)
+// producer warps per CTA: 8 (16 rows of the tile each) for A-law - 0.245 -> 0.217 ms on 998 000 frames: a producer warp is one
+// dependent instruction stream - 4 (32 rows each) for lin16, whose two parts per tile then fit 128 registers (8 warps: 0.49 against 0.42 ms)
+template <bool LIN16> constexpr int WT_PROD = LIN16 ? 4 : 8;
 constexpr int WT_EPI = 8;                 // epilogue warps per CTA (warp % 4 = TMEM lane quarter, warp / 4 = half of the bins)
-constexpr int WT_THREADS = (WT_EPI + 1 + WT_PROD) * 32;
+template <bool LIN16> constexpr int WT_THREADS = (WT_EPI + 1 + WT_PROD<LIN16>) * 32;
 constexpr int WT_BLK = 16384;             // [128 rows x 64 fp16], SWIZZLE_128B
 constexpr int WT_BBLK = 7;                // matrix blocks per CTA: 3 hi, 3 lo, 1 shared tail
 constexpr int WT_HCH = 7;                  // chunks of 16 bins one epilogue half may walk (its weights sit in shared memory)
@@ -133,7 +135,7 @@ __device__ __forceinline__ int find_utt(const int64_t *off, int n, int64_t f)
 // W_lo, part 1 = lo against W_hi (lo W_lo is below 2^-22 of the sample's own magnitude).  A part takes the place of a tile in the two-stage A ring (iteration = 2 tile + part, stage =
 // part), so shared memory, barriers and phases are those of the A-law kernel; only the accumulator hand-over is per tile.
 template <bool DBG, bool LIN16>
-__global__ void __launch_bounds__(WT_THREADS, 1) k_wave_tc(const __grid_constant__ WaveTcArgs a)
+__global__ void __launch_bounds__(WT_THREADS<LIN16>, 1) k_wave_tc(const __grid_constant__ WaveTcArgs a)
 {
     const int dbg = DBG ? a.dbg : 0;
     extern __shared__ uint8_t smem_raw[];
@@ -164,7 +166,7 @@ __global__ void __launch_bounds__(WT_THREADS, 1) k_wave_tc(const __grid_constant
     if (threadIdx.x == 0) {
         if (DBG && a.tl && blockIdx.x == 0) a.tl[4 * 32 * 8] = clock64();
         for (int i = 0; i < 2; ++i) {
-            mbar_init(&a_full[i], 2 * WT_PROD); mbar_init(&a_empty[i], 1);
+            mbar_init(&a_full[i], 2 * WT_PROD<LIN16>); mbar_init(&a_empty[i], 1);
             mbar_init(&d_full[i], 1); mbar_init(&d_empty[i], 2 * WT_EPI);
         }
         mbar_init(b_full, 1); mbar_init(pb_full, 1);
@@ -249,7 +251,7 @@ __global__ void __launch_bounds__(WT_THREADS, 1) k_wave_tc(const __grid_constant
         // and stored to the (up to three) rows that contain it.  The words of a group of tile i + 1 are requested as soon as the
         // same group of tile i has been decoded (its registers are free): a whole tile time passes before they are needed.  Groups that straddle two
         // utterances, touch the end of the batch's audio or hold an incomplete window go row by row (one in a hundred).
-        constexpr int RPW = 128 / WT_PROD, NG = RPW / 8;
+        constexpr int RPW = 128 / WT_PROD<LIN16>, NG = RPW / 8;
         static_assert(RPW == 16 || RPW == 32, "rows of a warp on its lanes");
         const int pw = warp - PROD0;
         const int64_t audio_len = a.audio_end - a.audio;
@@ -750,7 +752,7 @@ int launch_wave_tc(phn_ctx *c, const void *d_audio, int64_t f_begin, int64_t f_e
     const int64_t units = (f_end - f_begin + 255) / 256;
     const int64_t maxp = c->num_sms / 2;
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)(2 * (units < maxp ? units : maxp))); cfg.blockDim = dim3(WT_THREADS);
+    cfg.gridDim = dim3((unsigned)(2 * (units < maxp ? units : maxp))); cfg.blockDim = dim3(lin16 ? WT_THREADS<true> : WT_THREADS<false>);
     cfg.dynamicSmemBytes = WT_SMEM; cfg.stream = c->stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
