@@ -319,6 +319,34 @@ def test_tc_dft_front_end_16khz(recs):
     assert all(np.array_equal(x.view(np.uint8), y.view(np.uint8)) for x, y in zip(lab, rev))
 
 
+@pytest.mark.parametrize("model,fmt,vs", [("PHN_EN_TIMIT_LCRC_N500", "lin16", 320), ("PHN_EN_TIMIT_LCRC_N500", "lin16", 393),
+                                          ("PHN_CZ_SPDAT_LCRC_N1500", "alaw", 160), ("PHN_CZ_SPDAT_LCRC_N1500", "lin16", 187)])
+def test_tc_dft_front_end_shorter_analysis_window(tmp_path, model, fmt, vs):
+    """melbanks/vector_size below the kernels' 400 / 200 samples (an edited copy of the model directory; the nets do not depend
+    on it): the window's matrix rows end at vector_size, every row of the A tile carries zeros beyond it (odd lengths: half a
+    chunk), the producers' whole-window loops must not be taken for granted.  ln mel-bank energies of the tensor-core front
+    ends against phn_mel of the same directory (the exact front end: melbanks.cpp:111-204 with that vector_size) on a ragged batch."""
+    from conftest import variant_model_dir
+    r = pb.Recognizer(variant_model_dir(tmp_path / f"vs{vs}", model, {"melbanks/vector_size": str(vs)}), device=0)
+    try:
+        assert r.vector_size == vs
+        r.set_wave_format(fmt)
+        bps = 2 if fmt == "lin16" else 1
+        rng = np.random.default_rng(vs)
+        a = r.synth_audio(60000 * bps, 12, seed=31)
+        step = r.vector_step
+        lens = [60000, vs, vs - 1, vs + step, vs + step - 1, 7, 0, 33333] + [int(x) for x in rng.integers(vs, 60000, 4)]
+        utts = [a[i].tobytes()[:n * bps] for i, n in enumerate(lens)]
+        exact = np.concatenate(r.mel(utts))
+        r.set_mlp_mode(pb.MLP_TC_F16)
+        r.recognize(utts)
+        fast = r.fetch_mel(exact.shape[0])
+        d = np.abs(fast - exact)
+        assert np.isfinite(fast).all() and d.max() <= TC_DFT_MEL_ABS, (d.max(), np.unravel_index(d.argmax(), d.shape))
+    finally:
+        r.close()
+
+
 def test_tc_dft_front_end_switch_gives_the_same_labels(tmp_path):
     """PHNREC_WAVE_TC=0 keeps the register-FFT front end in the tensor-core pipeline: both front ends are within 1e-4 of
     the reference's mel values, so the decoded label file of the shipped test utterance must not change."""
