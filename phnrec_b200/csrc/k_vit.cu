@@ -388,11 +388,22 @@ int launch_viterbi(phn_ctx *c, const float *d_pen, int n_pen, cudaStream_t s, ph
     c->logp_layout = tiled ? 2 : 1;
     const size_t vsmem = sizeof(float) * 48 * (size_t)((3 * c->P) | 1);
     // (the panel ring of the tiled form exceeds the 48 KB default from 86 phonemes on)
-    // PHNREC_VIT_DIRECT=1: the tiled decoder without shared-memory panels (same speed alone, 0.55 ms; built for an experiment in
-    // which it ran beside the next batch's MLP kernel - tools/experiments/README.md)
-    static const bool panels = !(getenv("PHNREC_VIT_DIRECT") && atoi(getenv("PHNREC_VIT_DIRECT")) != 0);
+    // PHNREC_VIT_DIRECT=1 / 0: the tiled decoder without / with shared-memory panels (CZ: 0.55 against 0.53 ms alone; first built for
+    // an experiment in which it ran beside the next batch's MLP kernel - tools/experiments/README.md).
+    // Unset: panels, unless their shared memory keeps the batch from being resident at once while the panel-free form is - one
+    // warp per utterance is a latency-bound chain, a second wave doubles the time (HU, 61 phonemes: 35 KB of panels = 6 CTAs per SM
+    // = 888 of 1000 utterances: 0.92 ms; panel-free 0.56 ms).
+    static const int direct_env = getenv("PHNREC_VIT_DIRECT") ? (atoi(getenv("PHNREC_VIT_DIRECT")) != 0 ? 1 : 0) : -1;
+    bool panels = direct_env != 1;
 #define PHN_VIT(N)                                                          \
     do {                                                                    \
+        if (tiled && direct_env < 0) {                                      \
+            int occ_p = 0, occ_d = 0;                                       \
+            PHN_CUDA(c, cudaFuncSetAttribute(k_viterbi<N, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vsmem)); \
+            PHN_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_p, k_viterbi<N, 1>, 32, vsmem)); \
+            PHN_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_d, k_viterbi<N, 2>, 32, 0)); \
+            panels = !((int64_t)nseg > (int64_t)occ_p * c->num_sms && (int64_t)nseg <= (int64_t)occ_d * c->num_sms); \
+        }                                                                   \
         if (tiled && panels) {                                              \
             PHN_CUDA(c, cudaFuncSetAttribute(k_viterbi<N, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vsmem)); \
             k_viterbi<N, 1><<<nseg, 32, vsmem, s>>>(a);                     \

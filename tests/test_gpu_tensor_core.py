@@ -347,6 +347,28 @@ def test_tc_dft_front_end_shorter_analysis_window(tmp_path, model, fmt, vs):
         r.close()
 
 
+def test_tc_decoder_form_chosen_by_residency_gives_the_same_labels(recs):
+    """HU has 61 phonemes: the decoder's shared-memory panels (35 KB per one-warp CTA) let 6 CTAs on an SM, 888 utterances on the
+    GPU - a batch of 1000 takes the panel-free form of the same recurrence (k_viterbi<.., 2>, launch_viterbi), halves of it the
+    panel form.  Same ln p tiles, same recurrence: the labels must be identical, scores included."""
+    r = recs("PHN_HU_SPDAT_LCRC_N1500")
+    r.set_wave_format("alaw")
+    try:
+        rng = np.random.default_rng(17)
+        pool = r.synth_audio(200000, 8, seed=23).reshape(-1)
+        utts = []
+        for _ in range(1000):
+            n = int(rng.integers(1500, 6000))
+            o = int(rng.integers(0, pool.size - n))
+            utts.append(pool[o:o + n].tobytes())
+        whole = r.recognize(utts)
+        halves = r.recognize(utts[:500]) + r.recognize(utts[500:])
+        assert sum(len(x) for x in whole) > 3000
+        assert all(np.array_equal(x.view(np.uint8), y.view(np.uint8)) for x, y in zip(whole, halves))
+    finally:
+        r.set_wave_format("lin16")
+
+
 def test_tc_dft_front_end_switch_gives_the_same_labels(tmp_path):
     """PHNREC_WAVE_TC=0 keeps the register-FFT front end in the tensor-core pipeline: both front ends are within 1e-4 of
     the reference's mel values, so the decoded label file of the shipped test utterance must not change."""
